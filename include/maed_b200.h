@@ -1,0 +1,124 @@
+/* libmaed_b200.so — C ABI of the B200-native MAED hot path.
+ *
+ * Boundary being replaced: the reference has NO native code; its hot path is the Python call
+ *   preds = model(inp)                         (reference lib/core/trainer.py:253, lib/core/evaluate.py:78)
+ * on `lib.models.MAED` (lib/models/maed.py:52-66).  `maed_b200.models.MAED` keeps that Python surface and
+ * forwards to the entry points below through ctypes (see INTEGRATION.md for the binding).
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure (maed_last_error() gives the
+ * message).  All pointers are DEVICE pointers owned by the caller (PyTorch); nothing is allocated on the
+ * hot path; `stream` is a cudaStream_t passed as void*.  No torch types appear in any signature.
+ */
+#ifndef MAED_B200_H
+#define MAED_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* maed_last_error(void);
+int maed_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long maed_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-op entry points (unit-test / microbenchmark granularity).
+ * "planes": an activation or weight matrix in split precision is two fp16 matrices, hi = rn(x) and
+ * lo = rn(x - hi), `plane` elements apart.  nsplit = 3 uses both (3 MMAs per K step), nsplit = 1 only hi.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* out = act(A[M,K] * B[N,K]^T + bias) + residual   — tcgen05 GEMM (replaces every nn.Linear / 1x1 conv
+ * matmul: reference vision_transformer.py:105-111,139-177; resnetv2.py:91-93).
+ * act: 0 none, 1 exact GELU, 2 ReLU.  out_mode: 0 fp32, 1 fp16, 2 fp16 hi+lo planes. */
+int maed_op_gemm(const void* A, long long a_plane, int lda, const void* B, long long b_plane, int ldb,
+                 int M, int N, int K, int nsplit, const float* bias, const float* residual, int act,
+                 int out_mode, void* out, long long out_plane, int ldc, int force_block_n, void* stream);
+
+/* Implicit-GEMM stride-1 KHxKW convolution over an NHWC activation [n_img,H,W,Cin] (x planes) with
+ * weights [Cout, KH*KW*Cin] (x planes); zero padding (pad_h, pad_w) on the top/left, SAME-style on the
+ * bottom/right (reference resnetv2.py:54-59,91-93).  Output [n_img*H*W, Cout]. */
+int maed_op_conv_gemm(const void* A, long long a_plane, const void* B, long long b_plane, int n_img, int H,
+                      int W, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w, int nsplit, int out_mode,
+                      void* out, long long out_plane, int force_block_n, void* stream);
+
+/* fp32 -> fp16 hi/lo planes (elementwise) */
+int maed_op_split_f32(const float* in, void* out_hi, long long plane, long long n, void* stream);
+
+/* Conv weight preparation: per-output-channel standardisation (w-mean)/(std_biased+1e-5) (reference
+ * resnetv2.py:86-89) when `standardize`, OIHW -> [Cout][kh][kw][Cin], zero-pad K to k_pad, split. */
+int maed_op_prep_conv_weight(const float* w, int Cout, int Cin, int KH, int KW, int k_pad, int standardize,
+                             void* out_hi, long long plane, void* stream);
+/* explicit im2col gathers (stem from fp32 NCHW; strided convs from NHWC planes) */
+int maed_op_im2col_stem(const float* x, int n_img, int Cin, int H, int W, int KH, int KW, int stride, int pad_t,
+                        int pad_l, int OH, int OW, int k_pad, void* out_hi, long long plane, void* stream);
+int maed_op_im2col_nhwc(const void* in_hi, long long in_plane, int n_img, int H, int W, int C, int KH, int KW,
+                        int stride, int pad_t, int pad_l, int OH, int OW, void* out_hi, long long out_plane,
+                        void* stream);
+/* GroupNorm(32, eps) over an NHWC fp32 map (+ optional residual planes, ReLU) -> planes
+ * (reference resnetv2.py:35-49).  `stats_scratch`: n_img*64 doubles. */
+int maed_op_groupnorm(const float* x, int n_img, int HW, int C, const float* gamma, const float* beta, float eps,
+                      int relu, const void* res_hi, long long res_plane, void* out_hi, long long out_plane,
+                      double* stats_scratch, void* stream);
+/* stem: GN + ReLU + MaxPool2dSame(3,2) (reference resnetv2.py:61-72,245-274) */
+int maed_op_groupnorm_maxpool(const float* x, int n_img, int H, int W, int C, const float* gamma, const float* beta,
+                              float eps, void* out_hi, long long out_plane, double* stats_scratch, void* stream);
+/* LayerNorm(eps) rows of fp32 -> planes (reference vision_transformer.py:258-261) */
+int maed_op_layernorm(const float* x, long long row_stride, const float* gamma, const float* beta, int rows, int C,
+                      float eps, void* out_hi, long long out_plane, void* stream);
+/* attention over qkv planes [BT*ntok, 3*heads*64]; outputs fp32 and/or planes [BT*ntok, heads*64]
+ * (reference vision_transformer.py:206-228,180-204).  kind: 0 spatial (tcgen05), 1 temporal, 2 generic. */
+int maed_op_attention(int kind, const void* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads,
+                      float scale, int nsplit, float* out_f32, void* out_hi, long long out_plane, void* stream);
+/* small fp32 linear (tail): out = act(x W^T + b) + residual; act 0 none / 3 tanh */
+int maed_op_linear_f32(const float* x, int ldx, const float* W, int ldw, const float* bias, int R, int N, int K,
+                       int act, const float* residual, int ldr, float* out, int ldo, void* stream);
+/* rot6d -> rotmat, angle-axis, theta, kp_2d (reference geometry.py:320-334,58-223; spin.py:113-157) */
+int maed_op_decode_outputs(const float* pose6d, const float* shape, const float* cam, int R, const float* kp3d,
+                           int n_joints, float* rotmat, float* theta, float* kp2d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-model engine: MAED(encoder='ste').forward (reference lib/models/maed.py:52-66).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct maed_engine maed_engine;
+typedef struct maed_config {
+  int num_blocks;   /* MODEL.ENCODER.NUM_BLOCKS (6) */
+  int num_heads;    /* MODEL.ENCODER.NUM_HEADS (12; head_dim must be 64) */
+  int mode;         /* st_mode: 0 vanilla, 1 parallel, 2 series, 3 coupling, 4 temporal */
+  int decoder;      /* 0 ktd, 1 iterative */
+  int hidden_dim;   /* MODEL.DECODER.HIDDEN_DIM (1024) */
+  int nsplit;       /* 3 split-fp16 operands (parity mode), 1 plain fp16 (fast mode) */
+  int temp_frames;  /* rows of encoder.temp_embed (16 in the reference; 32 for the T=32 extension) */
+} maed_config;
+typedef struct maed_outputs {
+  float* feat;       /* [N*T, 768]  encoder feature (MAED.extract_feature) */
+  float* pose6d;     /* [N*T, 144] */
+  float* shape;      /* [N*T, 10] */
+  float* cam;        /* [N*T, 3] */
+  float* rotmat;     /* [N*T, 24, 3, 3] */
+  float* theta;      /* [N*T, 85] = cam | angle-axis pose | shape */
+  float* kp2d;       /* [N*T, n_joints, 2] */
+  const float* kp3d; /* [N*T, n_joints, 3] joints to project, or NULL (zeros) */
+  int n_joints;
+} maed_outputs;
+
+int maed_engine_create(const maed_config* cfg, maed_engine** out);
+void maed_engine_destroy(maed_engine* e);
+/* parameter table: the engine wants one fp32 device pointer per reference state_dict key, in this order */
+int maed_engine_num_params(const maed_engine* e);
+const char* maed_engine_param_name(const maed_engine* e, int i);
+long long maed_engine_param_numel(const maed_engine* e, int i);
+size_t maed_engine_packed_bytes(const maed_engine* e);
+size_t maed_engine_workspace_bytes(const maed_engine* e, int n_frames);
+/* derive the packed tensor-core weights (standardised, K-major fp16 planes) from the fp32 parameters */
+int maed_engine_pack(const maed_engine* e, const void* const* params, void* packed, void* stream);
+/* x: fp32 [N, T, 3, 224, 224].  taps: NULL or MAED_TAP_COUNT pointers (NULL entries skipped). */
+#define MAED_TAP_COUNT 13
+int maed_engine_forward(const maed_engine* e, const void* const* params, const void* packed, const float* x, int N,
+                        int T, void* workspace, size_t workspace_bytes, const maed_outputs* outs,
+                        float* const* taps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAED_B200_H */

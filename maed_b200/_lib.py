@@ -1,0 +1,102 @@
+"""ctypes binding of libmaed_b200.so (C ABI declared in include/maed_b200.h).
+
+The library is built in-tree by ``maed_b200/build.py`` (nvcc, sm_100a).  There is NO fallback: if the
+shared object is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmaed_b200.so")
+
+c_void_pp = C.POINTER(C.c_void_p)
+c_float_p = C.c_void_p          # device pointers are passed as integers
+_P = C.c_void_p
+_I = C.c_int
+_L = C.c_longlong
+_F = C.c_float
+_Z = C.c_size_t
+
+
+class MaedConfig(C.Structure):
+    _fields_ = [("num_blocks", _I), ("num_heads", _I), ("mode", _I), ("decoder", _I), ("hidden_dim", _I),
+                ("nsplit", _I), ("temp_frames", _I)]
+
+
+class MaedOutputs(C.Structure):
+    _fields_ = [("feat", _P), ("pose6d", _P), ("shape", _P), ("cam", _P), ("rotmat", _P), ("theta", _P),
+                ("kp2d", _P), ("kp3d", _P), ("n_joints", _I)]
+
+
+MODES = {"vanilla": 0, "parallel": 1, "series": 2, "coupling": 3, "temporal": 4}
+DECODERS = {"ktd": 0, "iterative": 1}
+TAP_NAMES = ["stem", "stage0", "stage1", "stage2", "embed"] + ["block%d" % i for i in range(8)]
+
+# name -> (restype, argtypes); every symbol declared in include/maed_b200.h
+SIGNATURES = {
+    "maed_last_error": (C.c_char_p, []),
+    "maed_version": (_I, []),
+    "maed_launch_count": (_L, []),
+    "maed_op_gemm": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _L, _I, _I, _P]),
+    "maed_op_conv_gemm": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _I, _P]),
+    "maed_op_split_f32": (_I, [_P, _P, _L, _L, _P]),
+    "maed_op_prep_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "maed_op_im2col_stem": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "maed_op_im2col_nhwc": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "maed_op_groupnorm": (_I, [_P, _I, _I, _I, _P, _P, _F, _I, _P, _L, _P, _L, _P, _P]),
+    "maed_op_groupnorm_maxpool": (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _L, _P, _P]),
+    "maed_op_layernorm": (_I, [_P, _L, _P, _P, _I, _I, _F, _P, _L, _P]),
+    "maed_op_attention": (_I, [_I, _P, _L, _I, _I, _I, _I, _F, _I, _P, _P, _L, _P]),
+    "maed_op_linear_f32": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
+    "maed_op_decode_outputs": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
+    "maed_engine_create": (_I, [C.POINTER(MaedConfig), C.POINTER(_P)]),
+    "maed_engine_destroy": (None, [_P]),
+    "maed_engine_num_params": (_I, [_P]),
+    "maed_engine_param_name": (C.c_char_p, [_P, _I]),
+    "maed_engine_param_numel": (_L, [_P, _I]),
+    "maed_engine_packed_bytes": (_Z, [_P]),
+    "maed_engine_workspace_bytes": (_Z, [_P, _I]),
+    "maed_engine_pack": (_I, [_P, c_void_pp, _P, _P]),
+    "maed_engine_forward": (_I, [_P, c_void_pp, _P, _P, _I, _I, _P, _Z, C.POINTER(MaedOutputs), c_void_pp, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once) and installs the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "maed_b200: %s not found — build it with `python -m maed_b200.build` (or "
+            "__graft_entry__.build()).  There is no CPU / PyTorch fallback for the hot path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = load().maed_last_error()
+        raise RuntimeError("maed_b200 %s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))
+
+
+def call(name, *args):
+    lib = load()
+    check(getattr(lib, name)(*args), name)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

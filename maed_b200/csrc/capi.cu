@@ -1,0 +1,125 @@
+// extern "C" surface of libmaed_b200.so (declared in include/maed_b200.h).
+#include "../../include/maed_b200.h"
+
+#include <atomic>
+
+#include "common.h"
+#include "gemm_host.h"
+#include "engine.h"
+#include "kernels.h"
+
+using namespace maed;
+
+extern "C" {
+
+const char* maed_last_error(void) { return last_error(); }
+int maed_version(void) { return 1; }
+long long maed_launch_count(void) { return launch_count(); }
+
+int maed_op_gemm(const void* A, long long a_plane, int lda, const void* B, long long b_plane, int ldb, int M, int N,
+                 int K, int nsplit, const float* bias, const float* residual, int act, int out_mode, void* out,
+                 long long out_plane, int ldc, int force_block_n, void* stream) {
+  GemmArgs g;
+  g.A = (const __half*)A; g.a_plane = a_plane; g.lda = lda;
+  g.B = (const __half*)B; g.b_plane = b_plane; g.ldb = ldb;
+  g.M = M; g.N = N; g.K = K; g.nsplit = nsplit;
+  g.bias = bias; g.residual = residual; g.act = act; g.out_mode = out_mode; g.out = out; g.out_plane = out_plane;
+  g.ldc = ldc; g.force_block_n = force_block_n;
+  return launch_gemm(g, (cudaStream_t)stream);
+}
+
+int maed_op_conv_gemm(const void* A, long long a_plane, const void* B, long long b_plane, int n_img, int H, int W,
+                      int Cin, int Cout, int KH, int KW, int pad_h, int pad_w, int nsplit, int out_mode, void* out,
+                      long long out_plane, int force_block_n, void* stream) {
+  GemmArgs g;
+  g.A = (const __half*)A; g.a_plane = a_plane;
+  g.B = (const __half*)B; g.b_plane = b_plane;
+  g.M = n_img * H * W; g.N = Cout; g.K = KH * KW * Cin; g.nsplit = nsplit;
+  g.out_mode = out_mode; g.out = out; g.out_plane = out_plane; g.ldc = Cout;
+  g.conv = 1; g.n_img = n_img; g.H = H; g.W = W; g.Cin = Cin; g.KH = KH; g.KW = KW; g.pad_h = pad_h; g.pad_w = pad_w;
+  g.force_block_n = force_block_n;
+  return launch_gemm(g, (cudaStream_t)stream);
+}
+
+int maed_op_split_f32(const float* in, void* out_hi, long long plane, long long n, void* stream) {
+  return split_f32(in, (__half*)out_hi, plane, n, (cudaStream_t)stream);
+}
+
+int maed_op_prep_conv_weight(const float* w, int Cout, int Cin, int KH, int KW, int k_pad, int standardize, void* out_hi,
+                             long long plane, void* stream) {
+  return prep_conv_weight(w, Cout, Cin, KH, KW, k_pad, standardize, (__half*)out_hi, plane, (cudaStream_t)stream);
+}
+int maed_op_im2col_stem(const float* x, int n_img, int Cin, int H, int W, int KH, int KW, int stride, int pad_t, int pad_l,
+                        int OH, int OW, int k_pad, void* out_hi, long long plane, void* stream) {
+  return im2col_stem(x, n_img, Cin, H, W, KH, KW, stride, pad_t, pad_l, OH, OW, k_pad, (__half*)out_hi, plane,
+                     (cudaStream_t)stream);
+}
+int maed_op_im2col_nhwc(const void* in_hi, long long in_plane, int n_img, int H, int W, int C, int KH, int KW, int stride,
+                        int pad_t, int pad_l, int OH, int OW, void* out_hi, long long out_plane, void* stream) {
+  return im2col_nhwc((const __half*)in_hi, in_plane, n_img, H, W, C, KH, KW, stride, pad_t, pad_l, OH, OW, (__half*)out_hi,
+                     out_plane, (cudaStream_t)stream);
+}
+int maed_op_groupnorm(const float* x, int n_img, int HW, int C, const float* gamma, const float* beta, float eps, int relu,
+                      const void* res_hi, long long res_plane, void* out_hi, long long out_plane, double* stats_scratch,
+                      void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_CUDA_CHECK(cudaMemsetAsync(stats_scratch, 0, (size_t)n_img * 64 * sizeof(double), st));
+  MAED_PROPAGATE(gn_stats(x, n_img, HW, C, stats_scratch, st));
+  return gn_apply(x, stats_scratch, gamma, beta, n_img, HW, C, eps, relu, (const __half*)res_hi, res_plane, (__half*)out_hi,
+                  out_plane, st);
+}
+int maed_op_groupnorm_maxpool(const float* x, int n_img, int H, int W, int C, const float* gamma, const float* beta, float eps,
+                              void* out_hi, long long out_plane, double* stats_scratch, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_CUDA_CHECK(cudaMemsetAsync(stats_scratch, 0, (size_t)n_img * 64 * sizeof(double), st));
+  MAED_PROPAGATE(gn_stats(x, n_img, H * W, C, stats_scratch, st));
+  return gn_apply_maxpool(x, stats_scratch, gamma, beta, n_img, H, W, C, eps, (__half*)out_hi, out_plane, st);
+}
+int maed_op_layernorm(const float* x, long long row_stride, const float* gamma, const float* beta, int rows, int C, float eps,
+                      void* out_hi, long long out_plane, void* stream) {
+  return layernorm_planes(x, row_stride, gamma, beta, rows, C, eps, (__half*)out_hi, out_plane, (cudaStream_t)stream);
+}
+int maed_op_attention(int kind, const void* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads, float scale,
+                      int nsplit, float* out_f32, void* out_hi, long long out_plane, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const __half* q = (const __half*)qkv_hi;
+  if (kind == 0) return attn_spatial(q, qkv_plane, B * T, ntok, heads, scale, nsplit, out_f32, (__half*)out_hi, out_plane, st);
+  if (kind == 1) return attn_temporal(q, nsplit == 3 ? qkv_plane : 0, B, T, ntok, heads, scale, out_f32, (__half*)out_hi, out_plane, st);
+  if (kind == 2) return attn_generic(q, nsplit == 3 ? qkv_plane : 0, B, T * ntok, heads, scale, ntok, T, out_f32, (__half*)out_hi, out_plane, st);
+  set_error("maed_op_attention: unknown kind %d", kind);
+  return MAED_ERR_ARG;
+}
+int maed_op_linear_f32(const float* x, int ldx, const float* W, int ldw, const float* bias, int R, int N, int K, int act,
+                       const float* residual, int ldr, float* out, int ldo, void* stream) {
+  return linear_f32(x, ldx, W, ldw, bias, R, N, K, act, residual, ldr, out, ldo, (cudaStream_t)stream);
+}
+int maed_op_decode_outputs(const float* pose6d, const float* shape, const float* cam, int R, const float* kp3d, int n_joints,
+                           float* rotmat, float* theta, float* kp2d, void* stream) {
+  return decode_outputs(pose6d, shape, cam, R, kp3d, n_joints, rotmat, theta, kp2d, (cudaStream_t)stream);
+}
+
+// ---- engine
+static_assert(sizeof(maed_config) == sizeof(EngineConfig), "maed_config must mirror EngineConfig");
+static_assert(sizeof(maed_outputs) == sizeof(EngineOutputs), "maed_outputs must mirror EngineOutputs");
+static_assert(MAED_TAP_COUNT == TAP_COUNT, "tap count mismatch");
+int maed_engine_create(const maed_config* cfg, maed_engine** out) {
+  return engine_create(reinterpret_cast<const EngineConfig*>(cfg), reinterpret_cast<Engine**>(out));
+}
+void maed_engine_destroy(maed_engine* e) { engine_destroy(reinterpret_cast<Engine*>(e)); }
+int maed_engine_num_params(const maed_engine* e) { return engine_num_params(reinterpret_cast<const Engine*>(e)); }
+const char* maed_engine_param_name(const maed_engine* e, int i) { return engine_param_name(reinterpret_cast<const Engine*>(e), i); }
+long long maed_engine_param_numel(const maed_engine* e, int i) { return engine_param_numel(reinterpret_cast<const Engine*>(e), i); }
+size_t maed_engine_packed_bytes(const maed_engine* e) { return engine_packed_bytes(reinterpret_cast<const Engine*>(e)); }
+size_t maed_engine_workspace_bytes(const maed_engine* e, int n_frames) {
+  return engine_workspace_bytes(reinterpret_cast<const Engine*>(e), n_frames);
+}
+int maed_engine_pack(const maed_engine* e, const void* const* params, void* packed, void* stream) {
+  return engine_pack(reinterpret_cast<const Engine*>(e), params, packed, (cudaStream_t)stream);
+}
+int maed_engine_forward(const maed_engine* e, const void* const* params, const void* packed, const float* x, int N, int T,
+                        void* workspace, size_t workspace_bytes, const maed_outputs* outs, float* const* taps, void* stream) {
+  return engine_forward(reinterpret_cast<const Engine*>(e), params, packed, x, N, T, workspace, workspace_bytes,
+                        reinterpret_cast<const EngineOutputs*>(outs), taps, (cudaStream_t)stream);
+}
+
+}  // extern "C"

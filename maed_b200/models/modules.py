@@ -1,0 +1,220 @@
+"""Parameter containers with the reference's module tree, so ``state_dict()`` keys, shapes and
+initialisation match ``lib/models`` exactly.  These modules only HOLD parameters (plus
+the reference's init distributions); no forward arithmetic lives here — the hot path is the CUDA engine
+(``maed_b200/csrc``) driven by ``maed.py``.  Calling them directly raises.
+
+Reference files mirrored:
+  lib/models/resnetv2.py:74-93,35-49,159-274,277-348   (StdConv2dSame / GroupNormAct / Bottleneck / stem / ResNetV2)
+  lib/models/vision_transformer.py:96-130,244-261,287-375 (Mlp / Attention / Block / HybridEmbed / VisionTransformer)
+  lib/models/ktd.py:37-67, lib/models/spin.py:17-48       (KTD / Regressor)
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+ANCESTOR_INDEX = [
+    [], [0], [0], [0], [0, 1], [0, 2], [0, 3], [0, 1, 4], [0, 2, 5], [0, 3, 6], [0, 1, 4, 7],
+    [0, 2, 5, 8], [0, 3, 6, 9], [0, 3, 6, 9], [0, 3, 6, 9], [0, 3, 6, 9, 12], [0, 3, 6, 9, 13],
+    [0, 3, 6, 9, 14], [0, 3, 6, 9, 13, 16], [0, 3, 6, 9, 14, 17], [0, 3, 6, 9, 13, 16, 18],
+    [0, 3, 6, 9, 14, 17, 19], [0, 3, 6, 9, 13, 16, 18, 20], [0, 3, 6, 9, 14, 17, 19, 21],
+]
+
+
+class _Holder(nn.Module):
+    """Base class: parameters only; arithmetic happens in libmaed_b200.so."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError(
+            "%s holds parameters for the B200 engine and has no PyTorch forward; call MAED.forward "
+            "(there is no eager/CPU fallback)" % type(self).__name__)
+
+
+class StdConv(_Holder):
+    """`StdConv2dSame` parameters: weight (Cout,Cin,k,k), no bias; kaiming-normal fan_out (resnetv2.py:334-335)."""
+
+    def __init__(self, cin, cout, k, stride=1):
+        super().__init__()
+        self.stride, self.kernel_size = stride, k
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k))
+        nn.init.kaiming_normal_(self.weight, mode="fan_out", nonlinearity="relu")
+
+
+class Norm(_Holder):
+    """GroupNorm / LayerNorm affine parameters (weight=1, bias=0)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+
+
+class Lin(_Holder):
+    def __init__(self, cin, cout, init="trunc02"):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin))
+        self.bias = nn.Parameter(torch.zeros(cout))
+        if init == "trunc02":          # vision_transformer.py:366-370
+            nn.init.trunc_normal_(self.weight, std=0.02)
+        elif init == "xavier001":      # ktd.py:61,66-67 / spin.py:38-40
+            nn.init.xavier_uniform_(self.weight, gain=0.01)
+            bound = 1.0 / math.sqrt(cin)
+            nn.init.uniform_(self.bias, -bound, bound)
+        else:                          # nn.Linear default (ktd.py:53,55 / spin.py:31,33)
+            nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+            bound = 1.0 / math.sqrt(cin)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+
+class Downsample(_Holder):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv = StdConv(cin, cout, 1, stride)
+        self.norm = Norm(cout)
+
+
+class Bottleneck(_Holder):
+    def __init__(self, cin, cout, stride, has_ds):
+        super().__init__()
+        mid = cout // 4
+        if has_ds:
+            self.downsample = Downsample(cin, cout, stride)
+        self.conv1 = StdConv(cin, mid, 1)
+        self.norm1 = Norm(mid)
+        self.conv2 = StdConv(mid, mid, 3, stride)
+        self.norm2 = Norm(mid)
+        self.conv3 = StdConv(mid, cout, 1)
+        self.norm3 = Norm(cout)
+
+
+class Stage(_Holder):
+    def __init__(self, cin, cout, stride, depth):
+        super().__init__()
+        self.blocks = nn.Sequential(OrderedDict(
+            (str(i), Bottleneck(cin if i == 0 else cout, cout, stride if i == 0 else 1, i == 0))
+            for i in range(depth)))
+
+
+class ResNetV2(_Holder):
+    """layers=(3,4,9), preact=False, stem_type='same' (vision_transformer.py:564-566)."""
+
+    def __init__(self):
+        super().__init__()
+        self.stem = nn.Sequential(OrderedDict([("conv", StdConv(3, 64, 7, 2)), ("norm", Norm(64))]))
+        self.stages = nn.Sequential(OrderedDict([
+            ("0", Stage(64, 256, 1, 3)), ("1", Stage(256, 512, 2, 4)), ("2", Stage(512, 1024, 2, 9))]))
+
+
+class ProjConv(_Holder):
+    """HybridEmbed.proj = nn.Conv2d(1024, 768, 1) (vision_transformer.py:304) — default Conv2d init."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin, 1, 1))
+        self.bias = nn.Parameter(torch.zeros(cout))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(cin)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
+class HybridEmbed(_Holder):
+    def __init__(self):
+        super().__init__()
+        self.backbone = ResNetV2()
+        self.proj = ProjConv(1024, 768)
+        self.num_patches = 196
+
+
+class Attention(_Holder):
+    def __init__(self, dim, st_mode):
+        super().__init__()
+        self.proj = Lin(dim, dim)
+        if st_mode == "parallel":
+            self.ts_attn = Lin(2 * dim, 2 * dim)
+        self.qkv = Lin(dim, 3 * dim)
+        self.mode = st_mode
+
+
+class Mlp(_Holder):
+    def __init__(self, dim):
+        super().__init__()
+        self.fc1 = Lin(dim, 4 * dim)
+        self.fc2 = Lin(4 * dim, dim)
+
+
+class Block(_Holder):
+    def __init__(self, dim, st_mode):
+        super().__init__()
+        self.norm1 = Norm(dim)
+        self.attn = Attention(dim, st_mode)
+        self.norm2 = Norm(dim)
+        self.mlp = Mlp(dim)
+
+
+class PreLogits(_Holder):
+    def __init__(self, dim):
+        super().__init__()
+        self.fc = Lin(dim, dim)
+
+
+class STEncoder(_Holder):
+    """`vit_custom_resnet50_224_in21k(num_blocks, num_heads, st_mode)` parameters (vision_transformer.py:560-576)."""
+
+    def __init__(self, num_blocks, num_heads, st_mode, temp_frames=16):
+        super().__init__()
+        if st_mode not in ("series", "parallel", "coupling", "vanilla", "temporal"):
+            raise NotImplementedError(st_mode)                     # vision_transformer.py:175
+        dim = 768
+        self.embed_dim = self.num_features = dim
+        self.num_heads, self.st_mode = num_heads, st_mode
+        self.patch_embed = HybridEmbed()
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, 197, dim))
+        self.blocks = nn.ModuleList([Block(dim, st_mode) for _ in range(num_blocks)])
+        self.norm = Norm(dim)
+        self.pre_logits = PreLogits(dim)
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        nn.init.trunc_normal_(self.cls_token, std=0.02)
+        if st_mode in ("coupling", "parallel", "series"):
+            # the reference hard-codes 16 frames (vision_transformer.py:364); temp_frames=32 is the T=32 extension
+            self.temp_embed = nn.Parameter(torch.zeros(1, temp_frames, 1, dim))
+            nn.init.trunc_normal_(self.temp_embed, std=0.02)
+
+
+class SMPLHead(_Holder):
+    """Placeholder for `lib/models/smpl.py` (smplx.SMPL subclass): smplx==0.1.13 and the licensed SMPL assets
+    are absent, so verts / kp_3d are zeros and kp_2d is the projection of zero joints — exactly what the
+    shimmed reference returns in this environment ("next" tier).  Holds no parameters;
+    checkpoints drop every key containing 'smpl' anyway (train.py:101, eval.py:29)."""
+    n_joints = 49
+
+
+class KTD(_Holder):
+    def __init__(self, feat_dim=768, hidden_dim=1024):
+        super().__init__()
+        self.feat_dim = feat_dim
+        self.smpl = SMPLHead()
+        self.fc1 = Lin(feat_dim, hidden_dim, "default")
+        self.fc2 = Lin(hidden_dim, hidden_dim, "default")
+        self.joint_regs = nn.ModuleList(
+            [Lin(hidden_dim + 6 * len(a), 6, "xavier001") for a in ANCESTOR_INDEX])
+        self.decshape = Lin(hidden_dim, 10, "xavier001")
+        self.deccam = Lin(hidden_dim, 3, "xavier001")
+
+
+class Regressor(_Holder):
+    def __init__(self, feat_dim=768, hidden_dim=1024, mean_params=None):
+        super().__init__()
+        self.smpl = SMPLHead()
+        self.fc1 = Lin(feat_dim + 144 + 10 + 3, hidden_dim, "default")
+        self.fc2 = Lin(hidden_dim, hidden_dim, "default")
+        self.decpose = Lin(hidden_dim, 144, "xavier001")
+        self.decshape = Lin(hidden_dim, 10, "xavier001")
+        self.deccam = Lin(hidden_dim, 3, "xavier001")
+        if mean_params is None:     # 6-D identity pose, zero shape, unit scale (stand-in for smpl_mean_params.npz)
+            mean_params = {"pose": torch.tensor([1., 0., 0., 1., 0., 0.]).repeat(24).numpy(),
+                           "shape": torch.zeros(10).numpy(), "cam": torch.tensor([0.9, 0., 0.]).numpy()}
+        self.register_buffer("init_pose", torch.as_tensor(mean_params["pose"], dtype=torch.float32).reshape(1, 144))
+        self.register_buffer("init_shape", torch.as_tensor(mean_params["shape"], dtype=torch.float32).reshape(1, 10))
+        self.register_buffer("init_cam", torch.as_tensor(mean_params["cam"], dtype=torch.float32).reshape(1, 3))
