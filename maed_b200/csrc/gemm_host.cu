@@ -146,6 +146,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     p.tiles_h = cdiv(g.H, p.tile_h); p.tiles_w = cdiv(g.W, p.tile_w);
     p.m_tiles = g.n_img * p.tiles_h * p.tiles_w;
     p.num_k_blocks = g.KH * g.KW * p.cin_blocks;
+    p.a_tx_bytes = (uint32_t)(p.tile_h * p.tile_w * 128);
     const uint64_t dims[5] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.n_img, (uint64_t)nplanes};
     const uint64_t str[4] = {(uint64_t)g.Cin * 2, (uint64_t)g.W * g.Cin * 2, (uint64_t)g.H * g.W * g.Cin * 2,
                              (uint64_t)(nplanes == 2 ? g.a_plane : (long long)g.M * g.Cin) * 2};
@@ -156,6 +157,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     MAED_CHECK_ARG(lda % 8 == 0, "gemm: lda=%d must be a multiple of 8 (16-byte TMA strides)", lda);
     p.m_tiles = cdiv(g.M, kBlockM);
     p.num_k_blocks = cdiv(g.K, kBlockK);
+    p.a_tx_bytes = kBlockM * kBlockK * 2;
     const uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)g.M, (uint64_t)nplanes};
     const uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(nplanes == 2 ? g.a_plane : (long long)g.M * lda) * 2};
     const uint32_t box[3] = {64, 128, 1};

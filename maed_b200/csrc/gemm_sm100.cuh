@@ -39,6 +39,7 @@ struct GemmParams {
   // conv (implicit GEMM) mode
   int conv;                    // 0 plain, 1 tap mode
   int H, W, cin_blocks, KW, pad_h, pad_w, tile_h, tile_w, tiles_h, tiles_w;
+  uint32_t a_tx_bytes;         // bytes one A-plane TMA box delivers (conv boxes cover tile_h*tile_w <= 128 rows)
 };
 
 static constexpr int kBlockM = 128;
@@ -114,7 +115,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
           uint8_t* sB = sA + nplanes * kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          mbar_arrive_expect_tx(&full_bar[stage], nplanes * (p.a_tx_bytes + kBBytes));
           for (int pl = 0; pl < nplanes; ++pl) {
             if (p.conv) {
               const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
