@@ -55,6 +55,11 @@ int maed_op_im2col_stem(const float* x, int n_img, int Cin, int H, int W, int KH
 int maed_op_im2col_nhwc(const void* in_hi, long long in_plane, int n_img, int H, int W, int C, int KH, int KW,
                         int stride, int pad_t, int pad_l, int OH, int OW, void* out_hi, long long out_plane,
                         void* stream);
+/* stem: StdConv 7x7/2 SAME 3->64 on fp32 NCHW frames [n,3,224,224] -> fp32 NHWC [n*112*112, 64]; tcgen05 implicit
+ * GEMM with the im2col tile built in shared memory; accumulates the GroupNorm (sum, sumsq) of the output into
+ * stats[n][32][2] (zeroed by this call).  w: prep_conv_weight(k_pad) planes (reference resnetv2.py:245-274). */
+int maed_op_stem_conv(const float* x, int n_img, const void* w_hi, long long w_plane, int k_pad, int nsplit,
+                      float* out, double* stats, void* stream);
 /* GroupNorm(32, eps) over an NHWC fp32 map (+ optional residual planes, ReLU) -> planes
  * (reference resnetv2.py:35-49).  `stats_scratch`: n_img*64 doubles. */
 int maed_op_groupnorm(const float* x, int n_img, int HW, int C, const float* gamma, const float* beta, float eps,

@@ -297,61 +297,91 @@ int attn_spatial(const __half* qkv_hi, long long qkv_plane, int BT, int ntok, in
 }
 
 // ======================================================================================== temporal
-// One warp per (clip, head, token).  K and V rows of the T frames are staged as fp32 in shared memory;
-// lane (t, seg) owns query frame t and a 64/SEGS-wide slice of the head dimension (slices are skewed by one
-// word in shared memory so the SEGS broadcast reads of a step hit different banks).
+// One warp per (clip, head, token).  The T K-rows and V-rows (64 halfs = 128 B each, hi + lo planes) are fetched
+// with 16-byte loads (8 lanes per row, 4 rows per instruction), summed to fp32 and staged in shared memory; lane
+// (t, seg) then owns query frame t and every SEGS-th float4 of the head dimension, so the inner products read
+// shared memory with conflict-free 128-bit loads (one LDS per 4 FMAs).
+__device__ __forceinline__ void cvt8(const uint4& hi, const uint4& lo, bool has_lo, float* out) {
+  const __half2* h = reinterpret_cast<const __half2*>(&hi);
+  const __half2* l = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    if (has_lo) { const float2 g = __half22float2(l[i]); f.x += g.x; f.y += g.y; }
+    out[2 * i] = f.x; out[2 * i + 1] = f.y;
+  }
+}
+
 template <int SEGS, int TMAX>
 __global__ void attn_temporal_kernel(const __half* __restrict__ qkv, long long plane, int B, int T, int ntok, int heads,
                                      float scale, float* __restrict__ out_f32, __half* __restrict__ out_hi,
                                      long long out_plane, long long total) {
-  extern __shared__ float sm[];
-  constexpr int DS = kHeadDim / SEGS;                     // head-dim slice per lane
-  constexpr int RS = kHeadDim + SEGS;                     // padded row stride
+  extern __shared__ __align__(16) float sm[];
+  constexpr int NJ = 16 / SEGS;                           // float4 chunks of the head dim owned by a lane
   const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sK = sm + (size_t)w * 2 * TMAX * RS;
-  float* sV = sK + TMAX * RS;
+  float* sK = sm + (size_t)w * 2 * TMAX * kHeadDim;
+  float* sV = sK + TMAX * kHeadDim;
   const int ld = 3 * heads * kHeadDim, C = heads * kHeadDim;
-  const int d0 = lane * 2, d1 = lane * 2 + 1;
-  const int c0 = (d0 / DS) * (DS + 1) + (d0 % DS), c1 = (d1 / DS) * (DS + 1) + (d1 % DS);
+  const bool has_lo = plane != 0;
+  const int lrow = lane >> 3, lchunk = lane & 7;
   for (long long item = (long long)blockIdx.x * warps + w; item < total; item += (long long)gridDim.x * warps) {
     const int n = (int)(item % ntok);
     const int h = (int)((item / ntok) % heads);
     const int b = (int)(item / ((long long)ntok * heads));
     __syncwarp();
-    for (int t = 0; t < T; ++t) {                         // coalesced 128-byte row loads (hi + lo planes)
-      const long long row = ((long long)b * T + t) * ntok + n;
-      const __half* kp = qkv + row * ld + C + h * kHeadDim + lane * 2;
-      const __half* vp = kp + C;
-      float2 kf = __half22float2(*reinterpret_cast<const __half2*>(kp));
-      float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vp));
-      if (plane) {
-        const float2 kl = __half22float2(*reinterpret_cast<const __half2*>(kp + plane));
-        const float2 vl = __half22float2(*reinterpret_cast<const __half2*>(vp + plane));
-        kf.x += kl.x; kf.y += kl.y; vf.x += vl.x; vf.y += vl.y;
+    // ---- stage K, V (all loads of the item issued before the first use)
+    uint4 kh[TMAX / 4], kl[TMAX / 4], vh[TMAX / 4], vl[TMAX / 4];
+#pragma unroll
+    for (int i = 0; i < TMAX / 4; ++i) {
+      const int r = lrow + 4 * i;
+      kh[i] = kl[i] = vh[i] = vl[i] = make_uint4(0, 0, 0, 0);
+      if (r < T) {
+        const __half* kp = qkv + (((long long)b * T + r) * ntok + n) * ld + C + h * kHeadDim + lchunk * 8;
+        kh[i] = *reinterpret_cast<const uint4*>(kp);
+        vh[i] = *reinterpret_cast<const uint4*>(kp + C);
+        if (has_lo) {
+          kl[i] = *reinterpret_cast<const uint4*>(kp + plane);
+          vl[i] = *reinterpret_cast<const uint4*>(kp + C + plane);
+        }
       }
-      sK[t * RS + c0] = kf.x; sK[t * RS + c1] = kf.y;
-      sV[t * RS + c0] = vf.x; sV[t * RS + c1] = vf.y;
     }
-    __syncwarp();
     const int t = (SEGS == 1) ? lane : (lane % T);
     const int seg = (SEGS == 1) ? 0 : (lane / T);
     const bool act = t < T;
     const long long qrow = ((long long)b * T + (act ? t : 0)) * ntok + n;
-    float q[DS];
+    float q[NJ * 4];
     {
-      const __half* qp = qkv + qrow * ld + h * kHeadDim + seg * DS;
+      const __half* qp = qkv + qrow * ld + h * kHeadDim;
 #pragma unroll
-      for (int d = 0; d < DS; d += 2) {
-        float2 f = __half22float2(*reinterpret_cast<const __half2*>(qp + d));
-        if (plane) {
-          const float2 l = __half22float2(*reinterpret_cast<const __half2*>(qp + d + plane));
-          f.x += l.x; f.y += l.y;
+      for (int i = 0; i < NJ; ++i) {
+        const int d = 4 * (i * SEGS + seg);
+        const uint2 a = *reinterpret_cast<const uint2*>(qp + d);
+        float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+        float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+        if (has_lo) {
+          const uint2 c = *reinterpret_cast<const uint2*>(qp + d + plane);
+          const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&c.x));
+          const float2 g1 = __half22float2(*reinterpret_cast<const __half2*>(&c.y));
+          f0.x += g0.x; f0.y += g0.y; f1.x += g1.x; f1.y += g1.y;
         }
-        q[d] = f.x; q[d + 1] = f.y;
+        q[4 * i] = f0.x * scale; q[4 * i + 1] = f0.y * scale; q[4 * i + 2] = f1.x * scale; q[4 * i + 3] = f1.y * scale;
       }
     }
-    const float* kbase = sK + seg * (DS + 1);
-    const float* vbase = sV + seg * (DS + 1);
+#pragma unroll
+    for (int i = 0; i < TMAX / 4; ++i) {
+      const int r = lrow + 4 * i;
+      if (r < T) {
+        float f[8];
+        cvt8(kh[i], kl[i], has_lo, f);
+        *reinterpret_cast<float4*>(&sK[r * kHeadDim + lchunk * 8]) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(&sK[r * kHeadDim + lchunk * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
+        cvt8(vh[i], vl[i], has_lo, f);
+        *reinterpret_cast<float4*>(&sV[r * kHeadDim + lchunk * 8]) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(&sV[r * kHeadDim + lchunk * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
+      }
+    }
+    __syncwarp();
+    // ---- scores (q already carries the softmax scale)
     float s[TMAX];
     float mx = -INFINITY;
 #pragma unroll
@@ -359,11 +389,13 @@ __global__ void attn_temporal_kernel(const __half* __restrict__ qkv, long long p
       float acc = 0.f;
       if (u < T) {
 #pragma unroll
-        for (int d = 0; d < DS; ++d) acc += q[d] * kbase[u * RS + d];
+        for (int i = 0; i < NJ; ++i) {
+          const float4 k4 = *reinterpret_cast<const float4*>(&sK[u * kHeadDim + 4 * (i * SEGS + seg)]);
+          acc += q[4 * i] * k4.x + q[4 * i + 1] * k4.y + q[4 * i + 2] * k4.z + q[4 * i + 3] * k4.w;
+        }
       }
       if (SEGS >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, T);
       if (SEGS >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2 * T);
-      acc *= scale;
       s[u] = (u < T) ? acc : -INFINITY;
       mx = fmaxf(mx, s[u]);
     }
@@ -371,30 +403,36 @@ __global__ void attn_temporal_kernel(const __half* __restrict__ qkv, long long p
 #pragma unroll
     for (int u = 0; u < TMAX; ++u) { s[u] = (u < T) ? expf(s[u] - mx) : 0.f; sum += s[u]; }
     const float inv = 1.0f / sum;
-    float o[DS];
+    float o[NJ * 4];
 #pragma unroll
-    for (int d = 0; d < DS; ++d) o[d] = 0.f;
+    for (int d = 0; d < NJ * 4; ++d) o[d] = 0.f;
 #pragma unroll
     for (int u = 0; u < TMAX; ++u) {
       if (u < T) {
         const float pu = s[u] * inv;
 #pragma unroll
-        for (int d = 0; d < DS; ++d) o[d] += pu * vbase[u * RS + d];
+        for (int i = 0; i < NJ; ++i) {
+          const float4 v4 = *reinterpret_cast<const float4*>(&sV[u * kHeadDim + 4 * (i * SEGS + seg)]);
+          o[4 * i] += pu * v4.x; o[4 * i + 1] += pu * v4.y; o[4 * i + 2] += pu * v4.z; o[4 * i + 3] += pu * v4.w;
+        }
       }
     }
     if (act) {
-      const long long off = qrow * C + h * kHeadDim + seg * DS;
-      if (out_f32) {
+      const long long off = qrow * C + h * kHeadDim;
 #pragma unroll
-        for (int d = 0; d < DS; d += 4) *reinterpret_cast<float4*>(out_f32 + off + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
-      }
-      if (out_hi) {
-#pragma unroll
-        for (int d = 0; d < DS; d += 2) {
-          const __half2 h2 = __floats2half2_rn(o[d], o[d + 1]);
-          const float2 hf = __half22float2(h2);
-          *reinterpret_cast<__half2*>(out_hi + off + d) = h2;
-          *reinterpret_cast<__half2*>(out_hi + off + d + out_plane) = __floats2half2_rn(o[d] - hf.x, o[d + 1] - hf.y);
+      for (int i = 0; i < NJ; ++i) {
+        const int d = 4 * (i * SEGS + seg);
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + off + d) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        if (out_hi) {
+          const __half2 h0 = __floats2half2_rn(o[4 * i], o[4 * i + 1]), h1 = __floats2half2_rn(o[4 * i + 2], o[4 * i + 3]);
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          const __half2 l0 = __floats2half2_rn(o[4 * i] - f0.x, o[4 * i + 1] - f0.y);
+          const __half2 l1 = __floats2half2_rn(o[4 * i + 2] - f1.x, o[4 * i + 3] - f1.y);
+          uint2 H, L;
+          H.x = *reinterpret_cast<const uint32_t*>(&h0); H.y = *reinterpret_cast<const uint32_t*>(&h1);
+          L.x = *reinterpret_cast<const uint32_t*>(&l0); L.y = *reinterpret_cast<const uint32_t*>(&l1);
+          *reinterpret_cast<uint2*>(out_hi + off + d) = H;
+          *reinterpret_cast<uint2*>(out_hi + off + d + out_plane) = L;
         }
       }
     }
@@ -404,11 +442,12 @@ __global__ void attn_temporal_kernel(const __half* __restrict__ qkv, long long p
 int attn_temporal(const __half* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads, float scale, float* out_f32,
                   __half* out_hi, long long out_plane, cudaStream_t st) {
   MAED_CHECK_ARG(T >= 1 && T <= 32, "attn_temporal: T=%d unsupported (1..32)", T);
+  MAED_CHECK_ARG(qkv_plane % 8 == 0 && out_plane % 4 == 0, "attn_temporal: plane strides must be 16-byte aligned");
   const long long total = (long long)B * heads * ntok;
-  const long long cap = (long long)sm_count() * 16;
+  const long long cap = (long long)sm_count() * 32;
 #define TEMPORAL_LAUNCH(SEGS, TMAX, WARPS)                                                                          \
   do {                                                                                                              \
-    const size_t smem = (size_t)(WARPS) * 2 * (TMAX) * (kHeadDim + (SEGS)) * sizeof(float);                         \
+    const size_t smem = (size_t)(WARPS) * 2 * (TMAX) * kHeadDim * sizeof(float);                                    \
     static bool attr_set = false;                                                                                   \
     if (!attr_set) {                                                                                                \
       MAED_CUDA_CHECK(cudaFuncSetAttribute(attn_temporal_kernel<SEGS, TMAX>,                                        \
@@ -420,9 +459,9 @@ int attn_temporal(const __half* qkv_hi, long long qkv_plane, int B, int T, int n
     attn_temporal_kernel<SEGS, TMAX><<<(int)blocks, (WARPS) * 32, smem, st>>>(                                      \
         qkv_hi, qkv_plane, B, T, ntok, heads, scale, out_f32, out_hi, out_plane, total);                            \
   } while (0)
-  if (T == 16) TEMPORAL_LAUNCH(2, 16, 8);
-  else if (T == 8) TEMPORAL_LAUNCH(4, 8, 8);
-  else if (T <= 16) TEMPORAL_LAUNCH(1, 16, 8);
+  if (T == 16) TEMPORAL_LAUNCH(2, 16, 4);
+  else if (T == 8) TEMPORAL_LAUNCH(4, 8, 4);
+  else if (T <= 16) TEMPORAL_LAUNCH(1, 16, 4);
   else TEMPORAL_LAUNCH(1, 32, 4);
 #undef TEMPORAL_LAUNCH
   LAUNCH_CHECK();

@@ -59,6 +59,12 @@ int maed_op_im2col_nhwc(const void* in_hi, long long in_plane, int n_img, int H,
   return im2col_nhwc((const __half*)in_hi, in_plane, n_img, H, W, C, KH, KW, stride, pad_t, pad_l, OH, OW, (__half*)out_hi,
                      out_plane, (cudaStream_t)stream);
 }
+int maed_op_stem_conv(const float* x, int n_img, const void* w_hi, long long w_plane, int k_pad, int nsplit, float* out,
+                      double* stats, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)n_img * 64 * sizeof(double), st));
+  return stem_conv(x, n_img, (const __half*)w_hi, w_plane, k_pad, nsplit, out, stats, st);
+}
 int maed_op_groupnorm(const float* x, int n_img, int HW, int C, const float* gamma, const float* beta, float eps, int relu,
                       const void* res_hi, long long res_plane, void* out_hi, long long out_plane, double* stats_scratch,
                       void* stream) {

@@ -81,17 +81,23 @@ __constant__ int c_anc[24][8] = {
     {0, 3, 6, 9, 13, 16, 18, 20}, {0, 3, 6, 9, 14, 17, 19, 21}};
 // w_anc: for joint j, a [6][6*cnt(j)] row-major block (columns 1024.. of joint_regs.j.weight), blocks
 // concatenated in joint order.  One thread per frame; weights are warp-uniform broadcast loads.
-__global__ void ktd_tree_kernel(const float* __restrict__ base, const float* __restrict__ w_anc, int R,
-                                float* __restrict__ pose6d) {
+__global__ void ktd_tree_kernel(const float* __restrict__ base, int ld, const float* __restrict__ w_anc, int R,
+                                float* __restrict__ pose6d, float* __restrict__ shape, float* __restrict__ cam) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
+  if (shape) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) shape[r * 10 + i] = base[(long long)r * ld + 144 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cam[r * 3 + i] = base[(long long)r * ld + 154 + i];
+  }
   float pose[144];
   int woff = 0;
   for (int j = 0; j < 24; ++j) {
     const int cnt = c_anc_cnt[j];
     float o[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) o[i] = base[(long long)r * 144 + j * 6 + i];
+    for (int i = 0; i < 6; ++i) o[i] = base[(long long)r * ld + j * 6 + i];
     for (int a = 0; a < cnt; ++a) {
       const int aj = c_anc[j][a];
 #pragma unroll
@@ -106,8 +112,9 @@ __global__ void ktd_tree_kernel(const float* __restrict__ base, const float* __r
     for (int i = 0; i < 6; ++i) { pose[j * 6 + i] = o[i]; pose6d[(long long)r * 144 + j * 6 + i] = o[i]; }
   }
 }
-int ktd_tree(const float* base, const float* w_anc, int R, float* pose6d, cudaStream_t st) {
-  ktd_tree_kernel<<<cdiv(R, 64), 64, 0, st>>>(base, w_anc, R, pose6d);
+int ktd_tree(const float* base, int ld, const float* w_anc, int R, float* pose6d, float* shape, float* cam,
+             cudaStream_t st) {
+  ktd_tree_kernel<<<cdiv(R, 32), 32, 0, st>>>(base, ld, w_anc, R, pose6d, shape, cam);
   LAUNCH_CHECK();
   return MAED_OK;
 }

@@ -5,6 +5,7 @@
 // a CUDA graph.
 #include "engine.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -70,10 +71,12 @@ struct Engine {
   struct BlockOff { size_t ds, c1, c2, c3; };
   std::vector<BlockOff> bb_off;
   size_t off_proj;
-  struct SteOff { size_t qkv, proj, fc1, fc2; };
+  struct SteOff { size_t qkv, proj, fc1, fc2, ts; };
   std::vector<SteOff> blk_off;
   size_t off_ktd_wx, off_ktd_b, off_ktd_anc;
+  size_t off_pl, off_kfc1, off_kfc2, off_kheads, off_kheads_b;   // tensor-core planes of the tail (KTD)
   size_t packed_bytes;
+  bool fuse_gn = true;                      // MAED_B200_FUSE_GN=0 selects the unfused conv / gn_stats / gn_apply kernels
   int feat_dim() const { return 768; }
   int np() const { return cfg.nsplit == 3 ? 2 : 1; }
 };
@@ -203,8 +206,14 @@ static void build_tables(Engine& e) {
     so.proj = planes((long long)C * C);
     so.fc1 = planes(4LL * C * C);
     so.fc2 = planes(4LL * C * C);
+    so.ts = (c.mode == MODE_PARALLEL) ? planes(4LL * C * C) : 0;
     e.blk_off.push_back(so);
   }
+  e.off_pl = planes((long long)C * C);
+  e.off_kfc1 = planes((long long)HD * C);
+  e.off_kfc2 = planes((long long)HD * HD);
+  e.off_kheads = planes(192LL * HD);
+  e.off_kheads_b = off; off = align_up(off + 192 * 4);
   e.off_ktd_wx = off; off = align_up(off + 144 * (size_t)HD * 4);
   e.off_ktd_b = off; off = align_up(off + 144 * 4);
   e.off_ktd_anc = off; off = align_up(off + 36 * 95 * 4);
@@ -224,6 +233,7 @@ int engine_create(const EngineConfig* cfg, Engine** out) {
   MAED_CHECK_ARG(cfg->temp_frames >= 1 && cfg->temp_frames <= 32, "engine: temp_frames=%d (1..32)", cfg->temp_frames);
   Engine* e = new Engine();
   e->cfg = *cfg;
+  { const char* v = getenv("MAED_B200_FUSE_GN"); e->fuse_gn = !(v && v[0] == '0'); }
   build_tables(*e);
   *out = e;
   return MAED_OK;
@@ -245,6 +255,7 @@ struct Workspace {
   long long ln_plane, qkv_plane, ao_plane, hid_plane;
   // tail
   float* cls; float* h1; float* h2; float* base; float* xc; float* pose_it; float* shape_it; float* cam_it;
+  float* tokscratch; __half* alpha_p; __half* tail_a; __half* tail_b; long long tail_plane;
   size_t total;
 };
 static constexpr long long kColPerImg = 12544LL * kStemKPad;      // largest explicit-im2col matrix (stem)
@@ -274,11 +285,16 @@ static void carve(const Engine& e, int BT, uint8_t* base, Workspace& w) {
   w.cls = (float*)take((size_t)BT * 768 * 4);
   w.h1 = (float*)take((size_t)BT * HD * 4);
   w.h2 = (float*)take((size_t)BT * HD * 4);
-  w.base = (float*)take((size_t)BT * 144 * 4);
+  w.base = (float*)take((size_t)BT * 192 * 4);
   w.xc = (float*)take((size_t)BT * 1024 * 4);
   w.pose_it = (float*)take((size_t)BT * 144 * 4);
   w.shape_it = (float*)take((size_t)BT * 16 * 4);
   w.cam_it = (float*)take((size_t)BT * 4 * 4);
+  w.tokscratch = (float*)take((size_t)BT * kTokenChunks * 1536 * 4);
+  w.alpha_p = (__half*)take((size_t)BT * 1536 * 4);
+  w.tail_plane = (long long)BT * 1024 > (long long)BT * HD ? (long long)BT * 1024 : (long long)BT * HD;
+  w.tail_a = (__half*)take((size_t)w.tail_plane * 4);
+  w.tail_b = (__half*)take((size_t)w.tail_plane * 4);
   w.total = off;
 }
 size_t engine_workspace_bytes(const Engine* e, int BT) {
@@ -317,7 +333,9 @@ int engine_pack(const Engine* e, const void* const* params, void* packed, cudaSt
     MAED_PROPAGATE(split_f32(P(ix.proj_w), H(of.proj), CC, CC, st));
     MAED_PROPAGATE(split_f32(P(ix.fc1_w), H(of.fc1), 4 * CC, 4 * CC, st));
     MAED_PROPAGATE(split_f32(P(ix.fc2_w), H(of.fc2), 4 * CC, 4 * CC, st));
+    if (e->cfg.mode == MODE_PARALLEL) MAED_PROPAGATE(split_f32(P(ix.ts_w), H(of.ts), 4 * CC, 4 * CC, st));
   }
+  MAED_PROPAGATE(split_f32(P(e->i_pl_w), H(e->off_pl), CC, CC, st));
   if (e->cfg.decoder == DEC_KTD) {
     // joint_regs.j.weight [6, HD + 6k] -> Wx rows (first HD columns), ancestor blocks (last 6k columns), biases
     const int HD = e->cfg.hidden_dim;
@@ -338,6 +356,20 @@ int engine_pack(const Engine* e, const void* const* params, void* packed, cudaSt
       MAED_CUDA_CHECK(cudaMemcpyAsync(bj + j * 6, bjs, 24, cudaMemcpyDeviceToDevice, st));
       aoff += 36 * k;
     }
+    // tensor-core operands of the tail: fc1, fc2 and one [192, HD] head matrix = [24 joint bases (144) | shape (10) |
+    // cam (3) | 35 zero rows] with its bias vector
+    MAED_PROPAGATE(split_f32(P(e->i_fc1_w), H(e->off_kfc1), (long long)HD * 768, (long long)HD * 768, st));
+    MAED_PROPAGATE(split_f32(P(e->i_fc2_w), H(e->off_kfc2), (long long)HD * HD, (long long)HD * HD, st));
+    float* hb = (float*)(pk + e->off_kheads_b);
+    MAED_CUDA_CHECK(cudaMemsetAsync(pk + e->off_kheads, 0, (size_t)192 * HD * 4, st));
+    MAED_CUDA_CHECK(cudaMemsetAsync(hb, 0, 192 * 4, st));
+    const long long hp = 192LL * HD;
+    MAED_PROPAGATE(split_f32(wx, H(e->off_kheads), hp, 144LL * HD, st));
+    MAED_PROPAGATE(split_f32(P(e->i_shape_w), H(e->off_kheads) + 144LL * HD, hp, 10LL * HD, st));
+    MAED_PROPAGATE(split_f32(P(e->i_cam_w), H(e->off_kheads) + 154LL * HD, hp, 3LL * HD, st));
+    MAED_CUDA_CHECK(cudaMemcpyAsync(hb, bj, 144 * 4, cudaMemcpyDeviceToDevice, st));
+    MAED_CUDA_CHECK(cudaMemcpyAsync(hb + 144, P(e->i_shape_b), 40, cudaMemcpyDeviceToDevice, st));
+    MAED_CUDA_CHECK(cudaMemcpyAsync(hb + 154, P(e->i_cam_b), 12, cudaMemcpyDeviceToDevice, st));
   }
   return MAED_OK;
 }
@@ -366,6 +398,17 @@ static int conv_gn(const Engine& e, Workspace& w, int& gn_counter, int BT, const
     MAED_PROPAGATE(im2col_nhwc(A, a_plane, BT, Hin, Hin, Cin, ksz, ksz, stride, pad_total / 2, pad_total / 2, Hout, Hout,
                                w.col, w.col_plane, st));
     g.A = w.col; g.a_plane = w.col_plane; g.K = ksz * ksz * Cin;
+  }
+  if (e.fuse_gn) {
+    ConvGnArgs f;
+    f.A = g.A; f.a_plane = g.a_plane; f.B = Wp; f.b_plane = w_plane;
+    f.n_img = BT; f.H_out = Hout; f.W_out = Hout; f.C = Cout; f.K = g.K; f.nsplit = e.cfg.nsplit;
+    f.conv = g.conv; f.Cin = Cin; f.KH = ksz; f.KW = ksz; f.pad_h = g.pad_h; f.pad_w = g.pad_w;
+    f.gamma = gamma; f.beta = beta; f.eps = 1e-5f; f.relu = relu; f.res = res; f.res_plane = res_plane;
+    f.out = out; f.out_plane = out_plane;
+    const int rc = conv_gn_fused(f, st);
+    if (rc == MAED_OK) return MAED_OK;
+    if (rc != MAED_ERR_UNSUPPORTED) return rc;
   }
   MAED_PROPAGATE(launch_gemm(g, st));
   double* stats = w.stats + (size_t)gn_counter * BT * 64;
@@ -402,16 +445,9 @@ int engine_forward(const Engine* ep, const void* const* params, const void* pack
   int gn = 0;
   {
     // stem: 7x7/2 SAME (pad 2 top/left, 3 bottom/right) -> GN+ReLU -> 3x3/2 SAME max-pool
-    MAED_PROPAGATE(im2col_stem(x_in, BT, 3, 224, 224, 7, 7, 2, 2, 2, 112, 112, kStemKPad, w.col, w.col_plane, st));
-    GemmArgs g;
-    g.nsplit = ns;
-    g.A = w.col; g.a_plane = w.col_plane; g.lda = kStemKPad;
-    g.B = Hh(e.off_stem); g.b_plane = 64LL * kStemKPad; g.ldb = kStemKPad;
-    g.M = BT * 12544; g.N = 64; g.K = kStemKPad; g.out_mode = OUT_F32; g.out = w.convout; g.ldc = 64;
-    MAED_PROPAGATE(launch_gemm(g, st));
     double* stats = w.stats + (size_t)gn * BT * 64;
     ++gn;
-    MAED_PROPAGATE(gn_stats(w.convout, BT, 12544, 64, stats, st));
+    MAED_PROPAGATE(stem_conv(x_in, BT, Hh(e.off_stem), 64LL * kStemKPad, kStemKPad, ns, w.convout, stats, st));
     MAED_PROPAGATE(gn_apply_maxpool(w.convout, stats, P(e.i_stem_g), P(e.i_stem_g + 1), BT, 112, 112, 64, 1e-5f, w.act[0],
                                     w.act_plane, st));
   }
@@ -493,9 +529,9 @@ int engine_forward(const Engine* ep, const void* const* params, const void* pack
       if (c.mode == MODE_PARALLEL) {
         MAED_PROPAGATE(attn_temporal(w.qkv, qp, N, T, ntok, heads, scale, w.xt, nullptr, 0, st));
         MAED_PROPAGATE(attn_spatial(w.qkv, w.qkv_plane, BT, ntok, heads, scale, ns, w.xs, nullptr, 0, st));
-        MAED_PROPAGATE(token_mean(w.xs, BT, ntok, C, w.alpha, 2 * C, 0, st));
-        MAED_PROPAGATE(token_mean(w.xt, BT, ntok, C, w.alpha, 2 * C, C, st));
-        MAED_PROPAGATE(linear_f32(w.alpha, 2 * C, P(ix.ts_w), 2 * C, P(ix.ts_b), BT, 2 * C, 2 * C, 0, nullptr, 0, w.logits, 2 * C, st));
+        MAED_PROPAGATE(token_mean2_planes(w.xs, w.xt, BT, ntok, C, w.tokscratch, w.alpha_p, (long long)BT * 2 * C, st));
+        MAED_PROPAGATE(linear_tc(w.alpha_p, (long long)BT * 2 * C, BT, 2 * C, of.ts, 2 * C, P(ix.ts_b), ACT_NONE, nullptr, OUT_F32,
+                                 w.logits, 0));
         MAED_PROPAGATE(ts_blend(w.xs, w.xt, w.logits, BT, ntok, C, w.ao, w.ao_plane, st));
       } else if (c.mode == MODE_SERIES) {
         MAED_PROPAGATE(attn_spatial(w.qkv, w.qkv_plane, BT, ntok, heads, scale, ns, nullptr, w.ao, w.ao_plane, st));
@@ -516,17 +552,27 @@ int engine_forward(const Engine* ep, const void* const* params, const void* pack
   }
 
   // ------------------------------------------------------------------------------------------ tail
-  MAED_PROPAGATE(layernorm_f32(w.x, (long long)ntok * C, P(e.i_norm), P(e.i_norm + 1), BT, C, 1e-6f, w.cls, st));
-  MAED_PROPAGATE(linear_f32(w.cls, C, P(e.i_pl_w), C, P(e.i_pl_b), BT, C, C, 3, nullptr, 0, outs->feat, C, st));
+  // The tail always runs in split precision (nsplit = 3), also in the fp16 fast mode: its GEMMs feed the outputs
+  // without a damping residual path and are ~0.5 GFLOP.
   const int HD = c.hidden_dim;
+  auto tail_tc = [&](const __half* A, long long a_plane, int K, size_t w_off, int Nout, const float* bias, int act,
+                     int out_mode, void* out, long long out_plane) -> int {
+    GemmArgs g;
+    g.nsplit = 3;
+    g.A = A; g.a_plane = a_plane; g.B = Hh(w_off); g.b_plane = (long long)Nout * K;
+    g.M = BT; g.N = Nout; g.K = K; g.bias = bias; g.act = act; g.out_mode = out_mode; g.out = out; g.out_plane = out_plane;
+    g.ldc = Nout;
+    return launch_gemm(g, st);
+  };
+  MAED_PROPAGATE(layernorm_planes(w.x, (long long)ntok * C, P(e.i_norm), P(e.i_norm + 1), BT, C, 1e-6f, w.tail_a, w.tail_plane, st));
+  MAED_PROPAGATE(tail_tc(w.tail_a, w.tail_plane, C, e.off_pl, C, P(e.i_pl_b), ACT_TANH, OUT_F32, outs->feat, 0));
   if (c.decoder == DEC_KTD) {
-    MAED_PROPAGATE(linear_f32(outs->feat, C, P(e.i_fc1_w), C, P(e.i_fc1_b), BT, HD, C, 0, nullptr, 0, w.h1, HD, st));
-    MAED_PROPAGATE(linear_f32(w.h1, HD, P(e.i_fc2_w), HD, P(e.i_fc2_b), BT, HD, HD, 0, nullptr, 0, w.h2, HD, st));
-    MAED_PROPAGATE(linear_f32(w.h2, HD, P(e.i_shape_w), HD, P(e.i_shape_b), BT, 10, HD, 0, nullptr, 0, outs->shape, 10, st));
-    MAED_PROPAGATE(linear_f32(w.h2, HD, P(e.i_cam_w), HD, P(e.i_cam_b), BT, 3, HD, 0, nullptr, 0, outs->cam, 3, st));
-    MAED_PROPAGATE(linear_f32(w.h2, HD, (const float*)(pk + e.off_ktd_wx), HD, (const float*)(pk + e.off_ktd_b), BT, 144, HD, 0,
-                              nullptr, 0, w.base, 144, st));
-    MAED_PROPAGATE(ktd_tree(w.base, (const float*)(pk + e.off_ktd_anc), BT, outs->pose6d, st));
+    MAED_PROPAGATE(split_f32(outs->feat, w.tail_a, w.tail_plane, (long long)BT * C, st));
+    MAED_PROPAGATE(tail_tc(w.tail_a, w.tail_plane, C, e.off_kfc1, HD, P(e.i_fc1_b), ACT_NONE, OUT_F16_SPLIT, w.tail_b, w.tail_plane));
+    MAED_PROPAGATE(tail_tc(w.tail_b, w.tail_plane, HD, e.off_kfc2, HD, P(e.i_fc2_b), ACT_NONE, OUT_F16_SPLIT, w.tail_a, w.tail_plane));
+    MAED_PROPAGATE(tail_tc(w.tail_a, w.tail_plane, HD, e.off_kheads, 192, (const float*)(pk + e.off_kheads_b), ACT_NONE, OUT_F32,
+                           w.base, 0));
+    MAED_PROPAGATE(ktd_tree(w.base, 192, (const float*)(pk + e.off_ktd_anc), BT, outs->pose6d, outs->shape, outs->cam, st));
   } else {
     const int KI = C + 157;
     MAED_PROPAGATE(broadcast_row(P(e.i_init_pose), 144, BT, outs->pose6d, st));

@@ -24,6 +24,19 @@ struct GemmArgs {
 };
 
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
+
+// Fused conv (GEMM) + GroupNorm(32) + optional shortcut + optional ReLU -> planes (gemm_gn_sm100.cu).
+struct ConvGnArgs {
+  const __half* A = nullptr; long long a_plane = 0;      // plain: [n_img*HW, K]; conv: NHWC [n_img, H, W, Cin]
+  const __half* B = nullptr; long long b_plane = 0;      // [C, K]
+  int n_img = 0, H_out = 0, W_out = 0, C = 0, K = 0, nsplit = 3;
+  int conv = 0, Cin = 0, KH = 0, KW = 0, pad_h = 0, pad_w = 0;   // conv: stride-1 tap mode, H_out x W_out == input size
+  const float* gamma = nullptr; const float* beta = nullptr; float eps = 1e-5f; int relu = 0;
+  const __half* res = nullptr; long long res_plane = 0;
+  __half* out = nullptr; long long out_plane = 0;
+};
+// MAED_ERR_UNSUPPORTED (nothing launched) when the shape does not fit the fused kernel.
+int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st);
 void conv_tile_shape(int H, int W, int* tile_h, int* tile_w);
 
 }  // namespace maed

@@ -20,7 +20,7 @@
 namespace maed {
 
 enum : int { OUT_F32 = 0, OUT_F16 = 1, OUT_F16_SPLIT = 2 };
-enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
 
 struct GemmParams {
   int M, N, K;                 // logical sizes (K per plane)
@@ -215,6 +215,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else if (p.act == ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          } else if (p.act == ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
           }
           if (p.residual) {
             const float4* rp = reinterpret_cast<const float4*>(p.residual + out_row * p.ldc + col0);

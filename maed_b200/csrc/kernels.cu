@@ -492,6 +492,61 @@ int token_mean(const float* x, int BT, int ntok, int C, float* out, int out_ld, 
   return MAED_OK;
 }
 
+// stage 1: grid (kTokenChunks, BT, 2): partial column sums of a token chunk; thread = float4 of channels
+__global__ void token_sum_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int ntok, int C,
+                                         float* __restrict__ scratch) {
+  const float* x = blockIdx.z == 0 ? a : b;
+  const long long bt = blockIdx.y;
+  const int per = (ntok + kTokenChunks - 1) / kTokenChunks;
+  const int t0 = blockIdx.x * per, t1 = min(ntok, t0 + per);
+  const int c = threadIdx.x * 4;
+  if (c >= C) return;
+  float4 s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
+  const float* xb = x + bt * ntok * C + c;
+  int t = t0;
+  for (; t + 1 < t1; t += 2) {
+    const float4 u = *reinterpret_cast<const float4*>(xb + (long long)t * C);
+    const float4 v = *reinterpret_cast<const float4*>(xb + (long long)(t + 1) * C);
+    s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
+    s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+  }
+  if (t < t1) {
+    const float4 u = *reinterpret_cast<const float4*>(xb + (long long)t * C);
+    s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
+  }
+  s0.x += s1.x; s0.y += s1.y; s0.z += s1.z; s0.w += s1.w;
+  *reinterpret_cast<float4*>(scratch + ((bt * kTokenChunks + blockIdx.x) * 2 + blockIdx.z) * C + c) = s0;
+}
+// stage 2: sum the chunk partials in a fixed order, scale by 1/ntok, write planes [BT, 2C]
+__global__ void token_mean_finalize_kernel(const float* __restrict__ scratch, int ntok, int C, long long total4,
+                                           __half* __restrict__ out, long long out_plane) {
+  const int c4n = (2 * C) >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % c4n) * 4;
+    const long long bt = i / c4n;
+    const int which = col / C, c = col % C;
+    float4 s = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < kTokenChunks; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(scratch + ((bt * kTokenChunks + k) * 2 + which) * C + c);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float inv = 1.0f / (float)ntok;
+    s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+    store_split4(out + bt * 2 * C + col, out_plane, s);
+  }
+}
+int token_mean2_planes(const float* a, const float* b, int BT, int ntok, int C, float* scratch, __half* out_hi,
+                       long long out_plane, cudaStream_t st) {
+  MAED_CHECK_ARG(C % 4 == 0 && C <= 4096, "token_mean2: C=%d unsupported", C);
+  token_sum_partial_kernel<<<dim3(kTokenChunks, BT, 2), (C / 4 + 31) / 32 * 32, 0, st>>>(a, b, ntok, C, scratch);
+  LAUNCH_CHECK();
+  const long long total4 = (long long)BT * 2 * C / 4;
+  token_mean_finalize_kernel<<<grid_for(total4, 256), 256, 0, st>>>(scratch, ntok, C, total4, out_hi, out_plane);
+  LAUNCH_CHECK();
+  return MAED_OK;
+}
+
 __global__ void ts_blend_kernel(const float* __restrict__ xs, const float* __restrict__ xt, const float* __restrict__ logits,
                                 int ntok, int C, long long total4, __half* __restrict__ out, long long out_plane) {
   const int c4n = C >> 2;

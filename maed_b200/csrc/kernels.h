@@ -30,6 +30,11 @@ int im2col_stem(const float* x, int n_img, int Cin, int H, int W, int KH, int KW
 int im2col_nhwc(const __half* in_hi, long long in_plane, int n_img, int H, int W, int C, int KH, int KW, int stride,
                 int pad_t, int pad_l, int OH, int OW, __half* out_hi, long long out_plane, cudaStream_t st);
 
+// ---- stem conv 7x7/2 (3 -> 64) as a tcgen05 implicit GEMM with in-kernel im2col (stem_sm100.cu); also accumulates
+// the GroupNorm statistics of its output into `stats` (pre-zeroed [n_img][32][2] doubles)
+int stem_conv(const float* x, int n_img, const __half* w_hi, long long w_plane, int k_pad, int nsplit, float* out,
+              double* stats, cudaStream_t st);
+
 // ---- GroupNorm(32 groups, eps) over NHWC fp32 conv outputs (reference resnetv2.py:45-49)
 // stats: double [n_img][32][2] = (sum, sumsq), must be zeroed by the caller (gn_stats accumulates).
 int gn_stats(const float* x, int n_img, int HW, int C, double* stats, cudaStream_t st);
@@ -53,6 +58,11 @@ int layernorm_f32(const float* x, long long row_stride, const float* gamma, cons
                   float eps, float* out, cudaStream_t st);
 // mean over the ntok tokens of each frame: in fp32 [BT, ntok, C] -> out[BT, out_ld] at column offset col0
 int token_mean(const float* x, int BT, int ntok, int C, float* out, int out_ld, int col0, cudaStream_t st);
+// mean over tokens of two fp32 tensors at once -> planes [BT, 2C] = [mean(a) | mean(b)] (deterministic two-stage
+// reduction; `scratch` holds BT * kTokenChunks * 2C floats)
+static constexpr int kTokenChunks = 8;
+int token_mean2_planes(const float* a, const float* b, int BT, int ntok, int C, float* scratch, __half* out_hi,
+                       long long out_plane, cudaStream_t st);
 // parallel-mode attentive addition (reference vision_transformer.py:152-158):
 //   logits [BT, 2C] (channel c uses entries 2c, 2c+1); out = x_t*softmax_1 + x_s*softmax_0 -> planes
 int ts_blend(const float* x_s, const float* x_t, const float* logits, int BT, int ntok, int C, __half* out_hi,
@@ -77,7 +87,9 @@ int attn_generic(const __half* qkv_hi, long long qkv_plane, int batch, int seq, 
 int linear_f32(const float* x, int ldx, const float* W, int ldw, const float* bias, int R, int N, int K, int act,
                const float* residual, int ldr, float* out, int ldo, cudaStream_t st);
 // KTD kinematic-tree pass (reference ktd.py:81-86): pose6d[r, j] = base[r, j] + W_anc[j] . pose6d[r, ancestors(j)]
-int ktd_tree(const float* base, const float* w_anc, int R, float* pose6d, cudaStream_t st);
+// `base` has row stride ld (>= 157): columns [0,144) joint bases, [144,154) shape, [154,157) cam (copied out).
+int ktd_tree(const float* base, int ld, const float* w_anc, int R, float* pose6d, float* shape, float* cam,
+             cudaStream_t st);
 // rot6d -> rotmat -> angle-axis; theta = [cam, aa, shape]; kp_2d from kp_3d and cam
 // (reference geometry.py:320-334,58-223; ktd.py:94-124; spin.py:113-157)
 int decode_outputs(const float* pose6d, const float* shape, const float* cam, int R, const float* kp3d, int n_joints,

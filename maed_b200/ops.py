@@ -78,6 +78,16 @@ def im2col_stem(x, k_pad=152):
     return out
 
 
+def stem_conv(x, w_planes, nsplit=3):
+    """x: fp32 (n,3,224,224); w_planes: prep_conv_weight(w, k_pad=152) -> (fp32 (n*112*112, 64), stats (n,32,2) f64)."""
+    n = x.shape[0]
+    out = torch.empty(n * 112 * 112, 64, dtype=torch.float32, device=x.device)
+    stats = torch.empty(n, 32, 2, dtype=torch.float64, device=x.device)
+    call("maed_op_stem_conv", ptr(x.contiguous()), n, ptr(w_planes), plane_stride(w_planes), w_planes.shape[2], nsplit,
+         ptr(out), ptr(stats), stream_ptr())
+    return out, stats
+
+
 def im2col_nhwc(a, KH, KW, stride, pad_t, pad_l, OH, OW):
     _, n, H, W, Cc = a.shape
     out = _planes_like((n * OH * OW, KH * KW * Cc), a.device)

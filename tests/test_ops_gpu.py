@@ -38,10 +38,10 @@ def test_gemm_plain(ops, M, N, K, bn, nsplit):
     out = ops.gemm(pa, pb, nsplit=nsplit, block_n=bn)
     if nsplit == 3:
         ref = a.double() @ b.double().t()
-        assert rel_err(out, ref) < 1e-5          # fp32 accumulation over K up to 3072
+        assert rel_err(out, ref) < 2e-5          # fp32 tensor-core accumulation over K up to 3072
     else:
         ref = pa[0].double() @ pb[0].double().t()
-        assert rel_err(out, ref) < 1e-5
+        assert rel_err(out, ref) < 2e-5
         assert rel_err(out, a.double() @ b.double().t()) < 2e-3
 
 
@@ -97,6 +97,20 @@ def test_im2col_stem_and_stem_conv(ops):
     out = ops.gemm(col, wp)
     ref = F.conv2d(xp.double(), w.double(), stride=2).permute(0, 2, 3, 1).reshape(-1, 64)
     assert rel_err(out, ref) < 3e-6
+
+
+def test_stem_conv_fused(ops):
+    """tcgen05 stem conv with in-kernel im2col + fused GroupNorm statistics vs F.conv2d (SAME pad 2/3)."""
+    n = 3
+    x = _rand(n, 3, 224, 224, seed=40)
+    w = _rand(64, 3, 7, 7, scale=0.2, seed=41)
+    wp = ops.prep_conv_weight(w, k_pad=152, standardize=False)
+    out, stats = ops.stem_conv(x, wp)
+    ref = F.conv2d(F.pad(x, [2, 3, 2, 3]).double(), w.double(), stride=2).permute(0, 2, 3, 1)     # (n,112,112,64)
+    assert rel_err(out.reshape(n, 112, 112, 64), ref) < 3e-6
+    g = ref.reshape(n, 112 * 112, 32, 2)
+    assert rel_err(stats[:, :, 0], g.sum(dim=(1, 3))) < 1e-5
+    assert rel_err(stats[:, :, 1], (g * g).sum(dim=(1, 3))) < 1e-5
 
 
 @pytest.mark.parametrize("H,C,k,s", [(56, 128, 3, 2), (56, 256, 1, 2), (28, 256, 3, 2)])
