@@ -24,6 +24,11 @@ namespace maed {
 
 // =================================================================================== spatial (tcgen05)
 static constexpr int kHeadDim = 64;
+__device__ __forceinline__ float fast_exp2(float x) {   // one MUFU.EX2 (inputs are <= 0 here; flush-to-zero is fine)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 static constexpr int kQRows = 256;        // two M=128 query tiles
 static constexpr int kKvRows = 208;       // keys padded to a multiple of 16 (UMMA N / K granularity)
 static constexpr int kSpThreads = 384;    // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 / 8-11 softmax groups
@@ -112,52 +117,88 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       constexpr uint32_t idesc_s = umma_idesc_f16(128, kKvRows, 0, 0, 0);   // Q K^T : both K-major
       constexpr uint32_t idesc_o = umma_idesc_f16(128, kHeadDim, 0, 0, 1);  // P V   : B (=V) MN-major
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-        const uint32_t ph = it & 1;
-        // ---- S_g = Q_g K^T
-        mbar_wait(qk_full, ph);
-        tc_fence_after();
-        for (int g = 0; g < (two_tiles ? 2 : 1); ++g) {
-          const uint32_t d = tmem_base + (g ? kS1 : kS0);
+      auto issue_qk = [&](int g) {                 // S_g = Q_g K^T
+        const uint32_t d = tmem_base + (g ? kS1 : kS0);
 #pragma unroll
-          for (int k = 0; k < kHeadDim / 16; ++k) {
-            const uint64_t dq = umma_desc_k_sw128(aQ + g * (128 * 128) + k * 32);
-            const uint64_t dk = umma_desc_k_sw128(aK + k * 32);
-            umma_f16(d, dq, dk, idesc_s, k != 0);
-            if (np == 2) {
-              const uint64_t dql = umma_desc_k_sw128(aQ + kQBytes + g * (128 * 128) + k * 32);
-              const uint64_t dkl = umma_desc_k_sw128(aK + kKVBytes + k * 32);
-              umma_f16(d, dql, dk, idesc_s, 1);
-              umma_f16(d, dq, dkl, idesc_s, 1);
-            }
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          const uint64_t dq = umma_desc_k_sw128(aQ + g * (128 * 128) + k * 32);
+          const uint64_t dk = umma_desc_k_sw128(aK + k * 32);
+          umma_f16(d, dq, dk, idesc_s, k != 0);
+          if (np == 2) {
+            const uint64_t dql = umma_desc_k_sw128(aQ + kQBytes + g * (128 * 128) + k * 32);
+            const uint64_t dkl = umma_desc_k_sw128(aK + kKVBytes + k * 32);
+            umma_f16(d, dql, dk, idesc_s, 1);
+            umma_f16(d, dq, dkl, idesc_s, 1);
           }
-          umma_commit(&s_full[g]);
         }
-        umma_commit(qk_empty);                       // Q/K tiles may be overwritten once these MMAs retire
-        // ---- O = P_g V   (single O accumulator: tile g waits for the previous tile's epilogue)
-        mbar_wait(v_full, ph);
-        for (int g = 0; g < (two_tiles ? 2 : 1); ++g) {
-          mbar_wait(&p_full[g], ph);
-          if (g == 0) { if (two_tiles) mbar_wait(&o_empty[1], ph ^ 1); else mbar_wait(&o_empty[0], ph ^ 1); }
-          else mbar_wait(&o_empty[0], ph);
-          tc_fence_after();
-          const uint32_t a_p = tmem_base + (g ? kS1 : kS0);
-          const uint32_t d = tmem_base + kO;
+        umma_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int g) {                 // O = P_g V, P read from TMEM in place of S_g
+        const uint32_t a_p = tmem_base + (g ? kS1 : kS0);
+        const uint32_t d = tmem_base + kO;
 #pragma unroll 1
-          for (int kk = 0; kk < kKvRows / 16; ++kk) {
-            // V rows [16kk, 16kk+16): two 8-row swizzle atoms 1024 B apart; N = 64 fits one 128-byte atom row
-            const uint64_t dv = umma_desc_mn_sw128(aV + kk * 2048, 1024, 1024);
-            umma_f16_ts(d, a_p + kk * 16, dv, idesc_o, kk != 0);
-            if (np == 2) {
-              const uint64_t dvl = umma_desc_mn_sw128(aV + kKVBytes + kk * 2048, 1024, 1024);
-              umma_f16_ts(d, a_p + kk * 16 + 8, dv, idesc_o, 1);       // P_lo * V_hi
-              umma_f16_ts(d, a_p + kk * 16, dvl, idesc_o, 1);          // P_hi * V_lo
-            }
+        for (int kk = 0; kk < kKvRows / 16; ++kk) {
+          // V rows [16kk, 16kk+16): two 8-row swizzle atoms 1024 B apart; N = 64 fits one 128-byte atom row
+          const uint64_t dv = umma_desc_mn_sw128(aV + kk * 2048, 1024, 1024);
+          umma_f16_ts(d, a_p + kk * 16, dv, idesc_o, kk != 0);
+          if (np == 2) {
+            const uint64_t dvl = umma_desc_mn_sw128(aV + kKVBytes + kk * 2048, 1024, 1024);
+            umma_f16_ts(d, a_p + kk * 16 + 8, dv, idesc_o, 1);       // P_lo * V_hi
+            umma_f16_ts(d, a_p + kk * 16, dvl, idesc_o, 1);          // P_hi * V_lo
           }
-          umma_commit(&o_full[g]);
         }
-        umma_commit(v_empty);
+        umma_commit(&o_full[g]);
+      };
+      if (two_tiles) {
+        // Software-pipelined issue order  PV0(i), QK0(i+1), PV1(i), QK1(i+1): the two softmax groups run half a period
+        // apart, so the tensor pipe always has the other group's MMAs to execute while one group is in its softmax.
+        uint32_t it = 0;
+        int item = blockIdx.x;
+        if (item < items) {
+          mbar_wait(qk_full, 0);
+          tc_fence_after();
+          issue_qk(0);
+          issue_qk(1);
+          umma_commit(qk_empty);
+        }
+        for (; item < items; item += gridDim.x, ++it) {
+          const uint32_t ph = it & 1;
+          const bool has_next = item + (int)gridDim.x < items;
+          mbar_wait(v_full, ph);
+          mbar_wait(&p_full[0], ph);
+          mbar_wait(&o_empty[1], ph ^ 1);
+          tc_fence_after();
+          issue_pv(0);
+          if (has_next) {
+            mbar_wait(qk_full, ph ^ 1);
+            tc_fence_after();
+            issue_qk(0);
+          }
+          mbar_wait(&p_full[1], ph);
+          mbar_wait(&o_empty[0], ph);
+          tc_fence_after();
+          issue_pv(1);
+          umma_commit(v_empty);
+          if (has_next) {
+            issue_qk(1);
+            umma_commit(qk_empty);
+          }
+        }
+      } else {
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+          const uint32_t ph = it & 1;
+          mbar_wait(qk_full, ph);
+          tc_fence_after();
+          issue_qk(0);
+          umma_commit(qk_empty);
+          mbar_wait(v_full, ph);
+          mbar_wait(&p_full[0], ph);
+          mbar_wait(&o_empty[0], ph ^ 1);
+          tc_fence_after();
+          issue_pv(0);
+          umma_commit(v_empty);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -176,40 +217,52 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int bt = item / p.heads, h = item % p.heads;
         mbar_wait(&s_full[g], ph);
         tc_fence_after();
+        // Both passes read S in batches of 64 columns (64 + 64 + 64 + 16) with ONE tcgen05.wait::ld per batch: the TMEM
+        // load latency is paid 8 times per tile instead of 26 times.
+        uint32_t r[64];
+#define LD32(i, col) tmem_ld_32x32b_x32(tS + (col), reinterpret_cast<uint32_t(&)[32]>(r[32 * (i)]))
+#define LD16(i, col) tmem_ld_32x32b_x16(tS + (col), reinterpret_cast<uint32_t(&)[16]>(r[32 * (i)]))
         // pass 1: row max of the raw scores over the valid keys
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < kKvRows / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(tS + c * 16, r);
+        for (int b4 = 0; b4 < 4; ++b4) {
+          const int col0 = b4 * 64, ncols = b4 < 3 ? 64 : 16;
+          if (b4 < 3) { LD32(0, col0); LD32(1, col0 + 32); } else { LD16(0, col0); }
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c * 16 + j < p.ntok) mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int j = 0; j < 64; ++j)
+            if (j < ncols && col0 + j < p.ntok) mx = fmaxf(mx, __uint_as_float(r[j]));
         }
         const float mb = mx * p.scale_log2e;
-        // pass 2: p = exp2(s*scale*log2e - max*scale*log2e); P written back in place as fp16 hi | lo
+        // pass 2: p = exp2(s*scale*log2e - max*scale*log2e); P written back in place, per 16 columns: 8 packed hi | 8 packed lo
         float sum = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < kKvRows / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(tS + c * 16, r);
+        for (int b4 = 0; b4 < 4; ++b4) {
+          const int col0 = b4 * 64, ncols = b4 < 3 ? 64 : 16;
+          if (b4 < 3) { LD32(0, col0); LD32(1, col0 + 32); } else { LD16(0, col0); }
           tmem_ld_wait();
-          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            float p0 = (c * 16 + j < p.ntok) ? exp2f(__uint_as_float(r[j]) * p.scale_log2e - mb) : 0.f;
-            float p1 = (c * 16 + j + 1 < p.ntok) ? exp2f(__uint_as_float(r[j + 1]) * p.scale_log2e - mb) : 0.f;
-            sum += p0 + p1;
-            const __half2 h2 = __floats2half2_rn(p0, p1);
-            const float2 hf = __half22float2(h2);
-            const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
-            hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-            lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+          for (int c = 0; c < 4; ++c) {
+            if (c * 16 < ncols) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int jj = 0; jj < 16; jj += 2) {
+                const int col = col0 + c * 16 + jj;
+                const float p0 = (col < p.ntok) ? fast_exp2(__uint_as_float(r[c * 16 + jj]) * p.scale_log2e - mb) : 0.f;
+                const float p1 = (col + 1 < p.ntok) ? fast_exp2(__uint_as_float(r[c * 16 + jj + 1]) * p.scale_log2e - mb) : 0.f;
+                sum += p0 + p1;
+                const __half2 h2 = __floats2half2_rn(p0, p1);
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+                pk[jj >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                pk[8 + (jj >> 1)] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+              tmem_st_32x32b_x16(tS + col0 + c * 16, pk);
+            }
           }
-          tmem_st_32x32b_x8(tS + c * 16, hi);
-          tmem_st_32x32b_x8(tS + c * 16 + 8, lo);
         }
+#undef LD32
+#undef LD16
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -219,7 +272,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tc_fence_after();
         const float inv = 1.0f / sum;
         const long long orow = (long long)bt * p.ntok + qrow;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < kHeadDim / 32; ++c) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tO + c * 32, r);

@@ -15,7 +15,8 @@
 
 namespace maed {
 
-static constexpr int kStemThreads = 256;      // warps 0-3 builders (+MMA issue), warps 4-7 epilogue
+static constexpr int kStemThreads = 384;      // warps 0-7 builders (+MMA issue by thread 0), warps 8-11 epilogue
+static constexpr int kStemBuilders = 256;
 static constexpr int kOW = 112, kOH = 112, kIW = 224, kIH = 224;
 static constexpr int kPatchW = 232;            // 2 zero columns left, 224 data, 6 right (3 needed)
 static constexpr int kPatchFloats = 3 * 7 * kPatchW;
@@ -38,6 +39,39 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// patch offset of im2col column k (k = (r*7 + s)*3 + c), or -1 for the zero padding columns 147..159
+__host__ __device__ constexpr int stem_patch_off(int k) {
+  return k < kKReal ? ((k % 3) * 7 + (k / 3) / 7) * kPatchW + (k / 3) % 7 : -1;
+}
+// Builds chunks [CH0, CH0 + 10) of A row `row` (pixel ow = row): all gather offsets are compile-time immediates.
+template <int CH0>
+__device__ __forceinline__ void stem_build_row(const float* __restrict__ pb, bool valid, int row, uint8_t* sA, uint32_t a_plane,
+                                               int np) {
+#pragma unroll
+  for (int ch = CH0; ch < CH0 + 10; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      constexpr int dummy = 0; (void)dummy;
+      const int off = stem_patch_off(ch * 8 + j);
+      v[j] = (valid && off >= 0) ? pb[off >= 0 ? off : 0] : 0.f;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const __half2 h2 = __floats2half2_rn(v[j], v[j + 1]);
+      const float2 hf = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn(v[j] - hf.x, v[j + 1] - hf.y);
+      hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    const int kb = ch >> 3, cin = ch & 7;                 // K block, 16-byte chunk inside the 128-byte row
+    const uint32_t off = kb * (128 * 128) + row * 128 + ((cin ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(sA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (np == 2) *reinterpret_cast<uint4*>(sA + a_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p) {
   using namespace sm100;
@@ -50,8 +84,7 @@ stem_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p)
   uint8_t* sB = sA + 2 * kAPlane;                       // [2 planes][3 kb][64 x 128 B]
   float* sPatch = reinterpret_cast<float*>(sB + 2 * kBPlane);   // [2][3][7][232]
   float* sStage = sPatch + 2 * kPatchFloats;            // [4 warps][32 rows x 64 floats]
-  int* sLut = reinterpret_cast<int*>(sStage + 4 * 32 * 64);     // [160] patch offset of k, or -1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 160);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 4 * 32 * 64);
   uint64_t* w_full = bars + 0;
   uint64_t* mma_done = bars + 1;
   uint64_t* tmem_full = bars + 2;    // [2]
@@ -64,12 +97,6 @@ stem_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p)
   const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;       // contiguous tile ranges: few image changes
   const int tile_lo = blockIdx.x * per_cta, tile_hi = min(total_tiles, tile_lo + per_cta);
 
-  if (threadIdx.x < 160) {
-    const int k = threadIdx.x;
-    int off = -1;
-    if (k < kKReal) { const int c = k % 3, tap = k / 3, r = tap / 7, s = tap % 7; off = (c * 7 + r) * kPatchW + s; }
-    sLut[k] = off;
-  }
   if (warp == 1 && elect_one()) {
     mbar_init(w_full, 1);
     mbar_init(mma_done, 1);
@@ -96,14 +123,15 @@ stem_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p)
       for (int kb = 0; kb < 3; ++kb) tma_load_3d(sB + pl * kBPlane + kb * kBKb, &tmW, w_full, kb * 64, 0, pl);
   }
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =================================================================== builders (+ MMA issue by thread 0)
-    const int tid = threadIdx.x;               // 0..127 = output pixel (ow) of the tile row; >= 112 -> zero rows
+    const int tid = threadIdx.x;               // 0..255: row = tid & 127 (output pixel ow; >= 112 -> zero rows), half = tid >> 7
+    const int brow = tid & 127, bhalf = tid >> 7;
     auto issue_patch = [&](int tile, int buf) {
       const int img = tile / kOH, oh = tile % kOH;
       float* dst = sPatch + buf * kPatchFloats;
       // 21 (c, r) rows x 56 float4
-      for (int i = tid; i < 21 * 56; i += 128) {
+      for (int i = tid; i < 21 * 56; i += kStemBuilders) {
         const int row = i / 56, q = i % 56;
         const int c = row / 7, r = row % 7;
         const int ih = 2 * oh + r - 2;
@@ -127,36 +155,16 @@ stem_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p)
     for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
       const int buf = it & 1;
       cp_async_wait_all();
-      named_bar_sync(1, 128);                                  // patch(tile) visible to all builders
+      named_bar_sync(1, kStemBuilders);                        // patch(tile) visible to all builders
       if (tile + 1 < tile_hi) issue_patch(tile + 1, buf ^ 1);
       if (it > 0) { mbar_wait(mma_done, done_phase); done_phase ^= 1; }   // A tile free again
-      // ---- build A row `tid` (pixel ow = tid): 20 chunks of 8 k-values, swizzled 16-byte stores
-      const float* pb = sPatch + buf * kPatchFloats + 2 * tid;
-      const bool valid = tid < kOW;
-#pragma unroll 1
-      for (int ch = 0; ch < 20; ++ch) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int off = sLut[ch * 8 + j];
-          v[j] = (valid && off >= 0) ? pb[off] : 0.f;
-        }
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          const __half2 h2 = __floats2half2_rn(v[j], v[j + 1]);
-          const float2 hf = __half22float2(h2);
-          const __half2 l2 = __floats2half2_rn(v[j] - hf.x, v[j + 1] - hf.y);
-          hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-          lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
-        }
-        const int kb = ch >> 3, cin = ch & 7;                 // K block, 16-byte chunk inside the 128-byte row
-        const uint32_t off = kb * kAKb + tid * 128 + ((cin ^ (tid & 7)) << 4);
-        *reinterpret_cast<uint4*>(sA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (np == 2) *reinterpret_cast<uint4*>(sA + kAPlane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
+      // ---- build A row `brow` (pixel ow): this thread's 10 of the 20 chunks of 8 k-values, swizzled 16-byte stores
+      const float* pb = sPatch + buf * kPatchFloats + 2 * brow;
+      const bool valid = brow < kOW;
+      if (bhalf == 0) stem_build_row<0>(pb, valid, brow, sA, kAPlane, np);
+      else stem_build_row<10>(pb, valid, brow, sA, kAPlane, np);
       fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core
-      named_bar_sync(2, 128);
+      named_bar_sync(2, kStemBuilders);
       if (tid == 0) {
         if (it == 0) mbar_wait(w_full, 0);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -210,17 +218,17 @@ stem_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p)
       const int row = ew * 32 + lane;                          // pixel ow
       const bool valid = row < kOW;
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + acc * 64 + ((uint32_t)(ew * 32) << 16) + c0, r);
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_base + acc * 64 + ((uint32_t)(ew * 32) << 16) + c0, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
+        for (int j = 0; j < 16; j += 2) {
           const float a = __uint_as_float(r[j]), b = __uint_as_float(r[j + 1]);
           if (valid) { gs[(c0 + j) >> 1] += a + b; gq[(c0 + j) >> 1] += a * a + b * b; }
         }
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 16; j += 4) {
           const int q = (c0 + j) >> 2;                         // logical 16-byte chunk (0..15) of this row
           *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ (lane & 7)) << 2)) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         }
@@ -260,7 +268,7 @@ int stem_conv(const float* x, int n_img, const __half* w_hi, long long w_plane, 
   MAED_PROPAGATE(make_tmap_f16(&tmW, w_hi, 3, dims, str, box));
   StemParams p;
   p.x = x; p.out = out; p.stats = stats; p.n_img = n_img; p.nsplit = nsplit;
-  const size_t smem = 1024 + 2 * 3 * 128 * 128 + 2 * 3 * 64 * 128 + 2 * kPatchFloats * 4 + 4 * 32 * 64 * 4 + 160 * 4 + 128;
+  const size_t smem = 1024 + 2 * 3 * 128 * 128 + 2 * 3 * 64 * 128 + 2 * kPatchFloats * 4 + 4 * 32 * 64 * 4 + 128;
   static bool attr_set = false;
   if (!attr_set) {
     MAED_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
