@@ -52,7 +52,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   constexpr uint32_t kS0 = 0, kS1 = kKvRows, kO = 2 * kKvRows;   // TMEM column map: S0 | S1 | O
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic ST/LD)
   const int np = p.nplanes;
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + np * kQBytes;

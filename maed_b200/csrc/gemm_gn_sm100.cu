@@ -57,33 +57,28 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0, spins = 0;
-  const uint32_t a = sm100::smem_u32(bar);
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t}"
-        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    if (!ok && ++spins > (1u << 26)) __trap();
-  }
+  // Poll with the default (CTA-scope) try_wait: a cluster-scope acquire poll makes ptxas emit an L1 invalidate
+  // (CCTL.IVALL) per iteration.  One cluster-scope fence after success orders the peers' DSMEM stores before our reads.
+  sm100::mbar_wait(bar, parity);
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int BN, int GSZ>
 __global__ void __launch_bounds__(kGnThreads, 1)
-gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmGnParams p) {
+gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const GemmGnParams p) {
   using namespace sm100;
   constexpr int G = BN / GSZ;                 // groups in the channel block
   static_assert(G >= 1 && G <= 32 && BN % 32 == 0 && BN <= 128, "unsupported block / group shape");
   constexpr uint32_t kABytes = 128 * 64 * 2, kBBytes = BN * 64 * 2;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic ST/LD)
   const int np = p.nsplit == 3 ? 2 : 1;
   const uint32_t stage_bytes = np * (kABytes + kBBytes);
-  uint8_t* sXpose = smem + (size_t)p.stages * stage_bytes;                 // [8 warps][32 rows x 64 B]
-  double* s_warp_part = reinterpret_cast<double*>(sXpose + 8 * 2048);      // [2 groups][4 warps][32 groups][2]
+  uint8_t* sOut = smem + (size_t)p.stages * stage_bytes;                   // [2 groups][2 planes][128 rows x 128 B], SW128 boxes
+  double* s_warp_part = reinterpret_cast<double*>(sOut + 4 * 16384);       // [2 groups][4 warps][32 groups][2]
   double* s_parts = s_warp_part + 2 * 4 * 32 * 2;                          // [2 groups][8 ranks][32 groups][2]
   float* s_mr = reinterpret_cast<float*>(s_parts + 2 * kGnMaxCluster * 32 * 2);   // [2 groups][32][2] mean, rstd
   float* s_coef = s_mr + 2 * 64;                                           // [2 groups][a_c[128] | b_c[128]]
@@ -102,7 +97,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int t_lo = crank * p.tpc;
   const int my_tiles = max(0, min(p.tpc, p.tiles_per_image - t_lo));
 
-  if (warp == 0 && elect_one()) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+  if (warp == 0 && elect_one()) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO); }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int t = 0; t < 2 * kGnMaxTpc; ++t) mbar_init(&tile_full[t], 1);
@@ -189,7 +184,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int gt = threadIdx.x - 128 - grp * 128;   // 0..127 inside the group
     const int row_in_tile = qw * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qw * 32) << 16;
-    uint8_t* xp = sXpose + e * 2048;
+    uint8_t* obox = sOut + grp * 32768;       // hi box | lo box (16 KB each) of this group
     double* wpart = s_warp_part + grp * (4 * 32 * 2);     // [4 warps][32 groups][2]
     float* mr = s_mr + grp * 64;
     float* coef = s_coef + grp * 256;
@@ -302,8 +297,11 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         coef[128 + c] = be - mr[g * 2] * a;
       }
       named_bar(bar_a, 128);
-      // ------------------------------------------------- pass 2: normalise, shortcut, ReLU, split, transpose, store
-      // iterations (tile, 32-column chunk) flattened; the shortcut of iteration i+1 is loaded while i is processed
+      // ------------------------------------------- pass 2: normalise, shortcut, ReLU, split -> smem boxes -> TMA stores
+      // Unit of work = (tile, 64-channel block): every thread writes its row's 64 channels (128 B per plane) into the
+      // group's hi / lo staging boxes in the 128-byte-swizzled layout of the output tensor map; one thread then issues
+      // two bulk tensor stores (rows outside the image are clipped by the tensor map).  The shortcut of the next
+      // 32-column chunk is loaded while the current one is processed.
       constexpr int NCH = BN / 32;
       const int n_it = my_tiles * NCH;
       uint4 rh[4], rl[4];
@@ -366,28 +364,33 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           hi[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
           lo[i >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
         }
-        // per-warp transpose through shared memory (32 rows x 64 B, 16-byte chunks XOR-swizzled), one plane at a time
-        const int my_ok = (int)my_valid;
+        const int sub = (c0 >> 5) & 1;                       // which 32-channel half of the 64-channel box
+        if (sub == 0) {
+          // the previous unit's bulk stores must have finished READING the staging boxes before they are refilled
+          if (gt == 0) tma_store_wait_read<0>();
+          named_bar(bar_b, 128);
+        }
 #pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-          const uint32_t* src = pl ? lo : hi;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(xp + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(src[4 * q], src[4 * q + 1], src[4 * q + 2], src[4 * q + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int it4 = 0; it4 < 4; ++it4) {                    // 8 rows x 64 B per instruction
-            const int rr = it4 * 8 + (lane >> 2), pq = lane & 3;
-            const int lq = pq ^ ((rr >> 1) & 3);
-            const long long row_g = __shfl_sync(0xffffffffu, my_row, rr);
-            const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
-            if (ok) {
-              __half* dst = p.out + (pl ? p.out_plane : 0) + row_g * p.C + nb * BN + c0 + lq * 8;
-              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(xp + rr * 64 + pq * 16);
+        for (int q = 0; q < 4; ++q) {                        // 16-byte chunks sub*4 + q of this row, XOR-swizzled by (row & 7)
+          const uint32_t off = row_in_tile * 128 + ((((sub << 2) + q) ^ (row_in_tile & 7)) << 4);
+          *reinterpret_cast<uint4*>(obox + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          *reinterpret_cast<uint4*>(obox + 16384 + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+        if (sub == 1 || BN == 32) {
+          fence_proxy_async();
+          named_bar(bar_a, 128);
+          if (gt == 0) {
+            const int t = t_lo + tl, ch = nb * BN + (c0 & ~63);
+            if (p.conv) {
+              const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
+              tma_store_5d(&tmO, obox, ch, w0, h0, img, 0);
+              tma_store_5d(&tmO, obox + 16384, ch, w0, h0, img, 1);
+            } else {
+              tma_store_4d(&tmO, obox, ch, t * 128, img, 0);
+              tma_store_4d(&tmO, obox + 16384, ch, t * 128, img, 1);
             }
+            tma_store_commit();
           }
-          __syncwarp();
         }
       }
       tc_fence_before();
@@ -396,6 +399,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (warp >= 4 && (threadIdx.x & 127) == 0) tma_store_wait_all();       // this thread issued the group's bulk stores
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();
@@ -404,10 +408,10 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------------ host
 template <int BN, int GSZ>
-static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmGnParams& p, cudaStream_t st) {
+static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmGnParams& p, cudaStream_t st) {
   const int np = p.nsplit == 3 ? 2 : 1;
   const size_t stage_bytes = (size_t)np * (128 * 64 * 2 + BN * 64 * 2);
-  const size_t fixed = 1024 + 8 * 2048 + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
+  const size_t fixed = 1024 + 4 * 16384 + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
                        (2 * kGnMaxStages + 2 * kGnMaxTpc + 4) * 8 + 64;
   int stages = (int)((232448 - fixed) / stage_bytes);
   if (stages > kGnMaxStages) stages = kGnMaxStages;
@@ -442,7 +446,7 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmGnParam
   int n_clusters = max_clusters[p.cluster];
   if (n_clusters > p.items) n_clusters = p.items;
   cfg.gridDim = dim3(n_clusters * p.cluster);
-  MAED_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_gn_kernel<BN, GSZ>, tmA, tmB, p));
+  MAED_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_gn_kernel<BN, GSZ>, tmA, tmB, tmO, p));
   count_launch();
   return MAED_OK;
 }
@@ -458,7 +462,7 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   p.HW = a.H_out * a.W_out; p.C = a.C; p.nsplit = a.nsplit;
   p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.relu = a.relu; p.res = a.res; p.res_plane = a.res_plane;
   p.out = a.out; p.out_plane = a.out_plane;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
   const long long M = (long long)a.n_img * p.HW;
   if (a.conv) {
     if (a.Cin % 64 != 0) return MAED_ERR_UNSUPPORTED;
@@ -504,13 +508,26 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
     const uint32_t box[3] = {64, (uint32_t)bn, 1};
     MAED_PROPAGATE(make_tmap_f16(&tmB, a.B, 3, dims, str, box));
   }
-  if (bn == 128 && gsz == 4) return launch_gn<128, 4>(tmA, tmB, p, st);
-  if (bn == 128 && gsz == 8) return launch_gn<128, 8>(tmA, tmB, p, st);
-  if (bn == 128 && gsz == 16) return launch_gn<128, 16>(tmA, tmB, p, st);
-  if (bn == 128 && gsz == 32) return launch_gn<128, 32>(tmA, tmB, p, st);
-  if (bn == 64 && gsz == 2) return launch_gn<64, 2>(tmA, tmB, p, st);
-  if (bn == 64 && gsz == 4) return launch_gn<64, 4>(tmA, tmB, p, st);
-  if (bn == 64 && gsz == 8) return launch_gn<64, 8>(tmA, tmB, p, st);
+  // output planes [n_img, HW (or H, W), C] x 2 planes; 64-channel x one-tile boxes, 128-byte swizzle
+  MAED_CHECK_ARG(a.out_plane > 0, "conv_gn_fused: output planes required");
+  if (a.conv) {
+    const uint64_t dims[5] = {(uint64_t)a.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)a.n_img, 2};
+    const uint64_t str[4] = {(uint64_t)a.C * 2, (uint64_t)p.W * a.C * 2, (uint64_t)p.H * p.W * a.C * 2, (uint64_t)a.out_plane * 2};
+    const uint32_t box[5] = {64, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1, 1};
+    MAED_PROPAGATE(make_tmap_f16(&tmO, a.out, 5, dims, str, box));
+  } else {
+    const uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)p.HW, (uint64_t)a.n_img, 2};
+    const uint64_t str[3] = {(uint64_t)a.C * 2, (uint64_t)p.HW * a.C * 2, (uint64_t)a.out_plane * 2};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    MAED_PROPAGATE(make_tmap_f16(&tmO, a.out, 4, dims, str, box));
+  }
+  if (bn == 128 && gsz == 4) return launch_gn<128, 4>(tmA, tmB, tmO, p, st);
+  if (bn == 128 && gsz == 8) return launch_gn<128, 8>(tmA, tmB, tmO, p, st);
+  if (bn == 128 && gsz == 16) return launch_gn<128, 16>(tmA, tmB, tmO, p, st);
+  if (bn == 128 && gsz == 32) return launch_gn<128, 32>(tmA, tmB, tmO, p, st);
+  if (bn == 64 && gsz == 2) return launch_gn<64, 2>(tmA, tmB, tmO, p, st);
+  if (bn == 64 && gsz == 4) return launch_gn<64, 4>(tmA, tmB, tmO, p, st);
+  if (bn == 64 && gsz == 8) return launch_gn<64, 8>(tmA, tmB, tmO, p, st);
   return MAED_ERR_UNSUPPORTED;
 }
 

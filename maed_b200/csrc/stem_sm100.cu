@@ -79,7 +79,7 @@ stem_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p)
   constexpr uint32_t kBKb = 64 * 128;
   constexpr uint32_t kAPlane = 3 * kAKb, kBPlane = 3 * kBKb;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic ST/LD)
   uint8_t* sA = smem;                                   // [2 planes][3 kb][128 x 128 B]
   uint8_t* sB = sA + 2 * kAPlane;                       // [2 planes][3 kb][64 x 128 B]
   float* sPatch = reinterpret_cast<float*>(sB + 2 * kBPlane);   // [2][3][7][232]
