@@ -229,9 +229,14 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const int col0 = b4 * 64, ncols = b4 < 3 ? 64 : 16;
           if (b4 < 3) { LD32(0, col0); LD32(1, col0 + 32); } else { LD16(0, col0); }
           tmem_ld_wait();
+          if (col0 + 64 <= p.ntok) {           // whole batch valid: no per-column predicates
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if (j < ncols && col0 + j < p.ntok) mx = fmaxf(mx, __uint_as_float(r[j]));
+            for (int j = 0; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (j < ncols && col0 + j < p.ntok) mx = fmaxf(mx, __uint_as_float(r[j]));
+          }
         }
         const float mb = mx * p.scale_log2e;
         // pass 2: p = exp2(s*scale*log2e - max*scale*log2e); P written back in place, per 16 columns: 8 packed hi | 8 packed lo
@@ -241,6 +246,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const int col0 = b4 * 64, ncols = b4 < 3 ? 64 : 16;
           if (b4 < 3) { LD32(0, col0); LD32(1, col0 + 32); } else { LD16(0, col0); }
           tmem_ld_wait();
+          const bool all_valid = col0 + 64 <= p.ntok;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c * 16 < ncols) {
@@ -248,8 +254,12 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
               for (int jj = 0; jj < 16; jj += 2) {
                 const int col = col0 + c * 16 + jj;
-                const float p0 = (col < p.ntok) ? fast_exp2(__uint_as_float(r[c * 16 + jj]) * p.scale_log2e - mb) : 0.f;
-                const float p1 = (col + 1 < p.ntok) ? fast_exp2(__uint_as_float(r[c * 16 + jj + 1]) * p.scale_log2e - mb) : 0.f;
+                float p0 = fast_exp2(__uint_as_float(r[c * 16 + jj]) * p.scale_log2e - mb);
+                float p1 = fast_exp2(__uint_as_float(r[c * 16 + jj + 1]) * p.scale_log2e - mb);
+                if (!all_valid) {
+                  if (col >= p.ntok) p0 = 0.f;
+                  if (col + 1 >= p.ntok) p1 = 0.f;
+                }
                 sum += p0 + p1;
                 const __half2 h2 = __floats2half2_rn(p0, p1);
                 const float2 hf = __half22float2(h2);
