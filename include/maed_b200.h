@@ -55,6 +55,13 @@ int maed_op_im2col_stem(const float* x, int n_img, int Cin, int H, int W, int KH
 int maed_op_im2col_nhwc(const void* in_hi, long long in_plane, int n_img, int H, int W, int C, int KH, int KW,
                         int stride, int pad_t, int pad_l, int OH, int OW, void* out_hi, long long out_plane,
                         void* stream);
+/* Fused StdConv (1x1 plain GEMM when KH = KW = 1, else stride-1 KHxKW implicit GEMM) -> GroupNorm(32, eps) -> (+ residual
+ * planes) -> optional ReLU -> planes [n_img*H*W, C] (reference resnetv2.py:189-204).  Returns 3 (unsupported shape, nothing
+ * launched) when the image does not fit the TMEM of one cluster.  dbg: NULL or items*8 int64 clock stamps. */
+int maed_op_conv_gn(const void* A, long long a_plane, const void* W, long long w_plane, int n_img, int H, int Wd, int Cin,
+                    int C, int KH, int KW, int nsplit, const float* gamma, const float* beta, float eps, int relu,
+                    const void* res_hi, long long res_plane, void* out_hi, long long out_plane, long long* dbg,
+                    void* stream);
 /* stem: StdConv 7x7/2 SAME 3->64 on fp32 NCHW frames [n,3,224,224] -> fp32 NHWC [n*112*112, 64]; tcgen05 implicit
  * GEMM with the im2col tile built in shared memory; accumulates the GroupNorm (sum, sumsq) of the output into
  * stats[n][32][2] (zeroed by this call).  w: prep_conv_weight(k_pad) planes (reference resnetv2.py:245-274). */

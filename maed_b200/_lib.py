@@ -43,6 +43,7 @@ SIGNATURES = {
     "maed_op_prep_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     "maed_op_im2col_stem": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     "maed_op_im2col_nhwc": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "maed_op_conv_gn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _L, _P, _L, _P, _P]),
     "maed_op_stem_conv": (_I, [_P, _I, _P, _L, _I, _I, _P, _P, _P]),
     "maed_op_groupnorm": (_I, [_P, _I, _I, _I, _P, _P, _F, _I, _P, _L, _P, _L, _P, _P]),
     "maed_op_groupnorm_maxpool": (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _L, _P, _P]),

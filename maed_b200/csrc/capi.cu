@@ -59,6 +59,17 @@ int maed_op_im2col_nhwc(const void* in_hi, long long in_plane, int n_img, int H,
   return im2col_nhwc((const __half*)in_hi, in_plane, n_img, H, W, C, KH, KW, stride, pad_t, pad_l, OH, OW, (__half*)out_hi,
                      out_plane, (cudaStream_t)stream);
 }
+int maed_op_conv_gn(const void* A, long long a_plane, const void* W, long long w_plane, int n_img, int H, int Wd, int Cin, int C,
+                    int KH, int KW, int nsplit, const float* gamma, const float* beta, float eps, int relu, const void* res_hi,
+                    long long res_plane, void* out_hi, long long out_plane, long long* dbg, void* stream) {
+  ConvGnArgs f;
+  f.A = (const __half*)A; f.a_plane = a_plane; f.B = (const __half*)W; f.b_plane = w_plane;
+  f.n_img = n_img; f.H_out = H; f.W_out = Wd; f.C = C; f.K = KH * KW * Cin; f.nsplit = nsplit;
+  f.conv = (KH * KW > 1) ? 1 : 0; f.Cin = Cin; f.KH = KH; f.KW = KW; f.pad_h = (KH - 1) / 2; f.pad_w = (KW - 1) / 2;
+  f.gamma = gamma; f.beta = beta; f.eps = eps; f.relu = relu; f.res = (const __half*)res_hi; f.res_plane = res_plane;
+  f.out = (__half*)out_hi; f.out_plane = out_plane; f.dbg = dbg;
+  return conv_gn_fused(f, (cudaStream_t)stream);
+}
 int maed_op_stem_conv(const float* x, int n_img, const void* w_hi, long long w_plane, int k_pad, int nsplit, float* out,
                       double* stats, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;

@@ -47,7 +47,7 @@ int get_encode_tiled(PFN_encodeTiled* fn);
 
 // fp16 tensor map with 128-byte swizzle; dims/box innermost first; strides in bytes for dims 1..rank-1.
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box);
+                  const uint32_t* box, int swizzle_bytes = 128);
 
 int sm_count();
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -26,15 +26,19 @@ static constexpr int kGnEpiThreads = 256;
 static constexpr int kGnMaxTpc = 4;
 static constexpr int kGnMaxStages = 4;
 static constexpr int kGnMaxCluster = 8;
+// shortcut prefetch slots of the epilogue (iterations in flight + 1): 3 when shared memory allows (BN = 64), else 2
+template <int BN> struct ResSlots { static constexpr int value = (BN <= 64) ? 2 : 1; };
 
 struct GemmGnParams {
   int HW, C, K, num_k_blocks, nsplit, stages;
   int tiles_per_image, tpc, n_blocks, cluster, items;
   uint32_t a_tx_bytes;
+  uint32_t o_tx_bytes;         // bytes of one 32-channel half-box plane (rows x 64 B)
   int conv, H, W, cin_blocks, KW, pad_h, pad_w, tile_h, tile_w, tiles_h, tiles_w;
   const float* gamma; const float* beta; float eps; int relu;
   const __half* res; long long res_plane;
   __half* out; long long out_plane;
+  long long* dbg;              // optional [items][8] clock64 timestamps of (cluster 0, rank 0, group 0); nullptr = off
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -67,18 +71,20 @@ __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.syn
 template <int BN, int GSZ>
 __global__ void __launch_bounds__(kGnThreads, 1)
 gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmO, const GemmGnParams p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmGnParams p) {
   using namespace sm100;
   constexpr int G = BN / GSZ;                 // groups in the channel block
   static_assert(G >= 1 && G <= 32 && BN % 32 == 0 && BN <= 128, "unsupported block / group shape");
   constexpr uint32_t kABytes = 128 * 64 * 2, kBBytes = BN * 64 * 2;
+  constexpr int kResSlots = ResSlots<BN>::value;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic ST/LD)
   const int np = p.nsplit == 3 ? 2 : 1;
   const uint32_t stage_bytes = np * (kABytes + kBBytes);
-  uint8_t* sOut = smem + (size_t)p.stages * stage_bytes;                   // [2 groups][2 planes][128 rows x 128 B], SW128 boxes
-  double* s_warp_part = reinterpret_cast<double*>(sOut + 4 * 16384);       // [2 groups][4 warps][32 groups][2]
+  uint8_t* sOut = smem + (size_t)p.stages * stage_bytes;                   // [2 groups][hi | lo][128 rows x 64 B], SW64 half-boxes
+  uint8_t* sRes = sOut + 2 * 16384;                                        // [2 groups][kResSlots][hi | lo][128 rows x 64 B]
+  double* s_warp_part = reinterpret_cast<double*>(sRes + 2 * kResSlots * 16384);   // [2 groups][4 warps][32 groups][2]
   double* s_parts = s_warp_part + 2 * 4 * 32 * 2;                          // [2 groups][8 ranks][32 groups][2]
   float* s_mr = reinterpret_cast<float*>(s_parts + 2 * kGnMaxCluster * 32 * 2);   // [2 groups][32][2] mean, rstd
   float* s_coef = s_mr + 2 * 64;                                           // [2 groups][a_c[128] | b_c[128]]
@@ -88,7 +94,8 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tile_full = bars + 2 * kGnMaxStages;                           // [2 halves][kGnMaxTpc]
   uint64_t* half_empty = tile_full + 2 * kGnMaxTpc;                        // [2]
   uint64_t* parts_full = half_empty + 2;                                   // [2 buf]
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(parts_full + 2);
+  uint64_t* res_full = parts_full + 2;                                     // [2 groups][2 slots]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CS = p.cluster;
@@ -97,11 +104,12 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int t_lo = crank * p.tpc;
   const int my_tiles = max(0, min(p.tpc, p.tiles_per_image - t_lo));
 
-  if (warp == 0 && elect_one()) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO); }
+  if (warp == 0 && elect_one()) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO); if (p.res) prefetch_tmap(&tmR); }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int t = 0; t < 2 * kGnMaxTpc; ++t) mbar_init(&tile_full[t], 1);
     for (int h = 0; h < 2; ++h) { mbar_init(&half_empty[h], 4); mbar_init(&parts_full[h], CS * G); }
+    for (int h = 0; h < 4; ++h) mbar_init(&res_full[h], 1);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_base_ptr, 512); tmem_relinquish(); }
@@ -117,6 +125,17 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       for (int item = cluster_id; item < p.items; item += n_clusters) {
         const int img = item / p.n_blocks, nb = item % p.n_blocks;
+        if (p.res) {
+          // pull the shortcut boxes of this item into L2 now: the epilogue reads them ~2 items later
+          for (int tl = 0; tl < my_tiles; ++tl) {
+            const int t = t_lo + tl;
+            for (int cb = 0; cb < BN; cb += 32)
+              for (int pl = 0; pl < 2; ++pl) {
+                if (p.conv) tma_prefetch_l2_5d(&tmR, nb * BN + cb, (t % p.tiles_w) * p.tile_w, (t / p.tiles_w) * p.tile_h, img, pl);
+                else tma_prefetch_l2_4d(&tmR, nb * BN + cb, t * 128, img, pl);
+              }
+          }
+        }
         for (int tl = 0; tl < my_tiles; ++tl) {
           const int t = t_lo + tl;
           int h0 = 0, w0 = 0;
@@ -184,13 +203,13 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int gt = threadIdx.x - 128 - grp * 128;   // 0..127 inside the group
     const int row_in_tile = qw * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qw * 32) << 16;
-    uint8_t* obox = sOut + grp * 32768;       // hi box | lo box (16 KB each) of this group
     double* wpart = s_warp_part + grp * (4 * 32 * 2);     // [4 warps][32 groups][2]
     float* mr = s_mr + grp * 64;
     float* coef = s_coef + grp * 256;
     const int bar_a = 1 + grp * 2, bar_b = 2 + grp * 2;
     const uint32_t t_half = tmem_base + grp * 256 + lane_off;
     uint32_t jj = 0;                           // per-group item counter
+    uint32_t res_issue = 0, res_use = 0;       // running shortcut-slot counters (slot = n % kResSlots, parity = (n / kResSlots) & 1)
     for (int item = cluster_id + grp * n_clusters; item < p.items; item += 2 * n_clusters, ++jj) {
       const int img = item / p.n_blocks, nb = item % p.n_blocks;
       const uint32_t hphase = jj & 1;
@@ -207,20 +226,8 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         *orow = (long long)img * p.HW + r;
         return r < p.HW;
       };
-      // the shortcut rows are needed only in pass 2: pull them towards L2 now, before the statistics round trip
-      if (p.res) {
-        for (int tl = 0; tl < my_tiles; ++tl) {
-          long long orow;
-          if (row_info(tl, &orow)) {
-            const __half* rp = p.res + orow * p.C + nb * BN;
-#pragma unroll
-            for (int b2 = 0; b2 < BN * 2; b2 += 128) {
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(rp) + b2));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(rp + p.res_plane) + b2));
-            }
-          }
-        }
-      }
+      const bool dbg_on = p.dbg && blockIdx.x == 0 && gt == 0 && grp == 0;
+      if (dbg_on) p.dbg[jj * 8 + 0] = clock64();
       // ---------------------------------------------------------------- pass 1: group statistics
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -229,7 +236,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int g = 0; g < GC; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
         for (int tl = 0; tl < my_tiles; ++tl) {
-          if (c0 == 0) { mbar_wait(&tile_full[grp * kGnMaxTpc + tl], hphase); tc_fence_after(); }
+          if (c0 == 0) { mbar_wait(&tile_full[grp * kGnMaxTpc + tl], hphase); tc_fence_after(); if (dbg_on && tl == 0) p.dbg[jj * 8 + 6] = clock64(); }
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_half + tl * BN + c0, r);
           tmem_ld_wait();
@@ -256,7 +263,9 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      if (dbg_on) p.dbg[jj * 8 + 1] = clock64();
       named_bar(bar_a, 128);
+      if (dbg_on) p.dbg[jj * 8 + 2] = clock64();
       // ---- CTA partial of group g (thread g), pushed to every CTA of the cluster (including this one)
       if (gt < G) {
         const int g = gt;
@@ -288,6 +297,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mr[g * 2] = (float)m;
         mr[g * 2 + 1] = (float)(1.0 / sqrt(var + (double)p.eps));
       }
+      if (dbg_on) p.dbg[jj * 8 + 3] = clock64();
       named_bar(bar_b, 128);
       if (gt < BN) {                           // y = v * a_c + b_c
         const int c = gt, g = c / GSZ;
@@ -302,27 +312,33 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // group's hi / lo staging boxes in the 128-byte-swizzled layout of the output tensor map; one thread then issues
       // two bulk tensor stores (rows outside the image are clipped by the tensor map).  The shortcut of the next
       // 32-column chunk is loaded while the current one is processed.
+      if (dbg_on) p.dbg[jj * 8 + 4] = clock64();
+      // Iteration = (tile, 32-channel chunk).  All global traffic of the epilogue is bulk and asynchronous:
+      //   * the shortcut half-box (128 rows x 32 channels, hi + lo plane) of iteration it + kResSlots is fetched by TMA into
+      //     a shared-memory slot while earlier iterations compute (row-per-thread loads touched 32 cache lines per
+      //     instruction and made the LSU the bottleneck);
+      //   * results are staged in a 64-byte-swizzled half-box and written by TMA stores (clipped at the image edge).
       constexpr int NCH = BN / 32;
       const int n_it = my_tiles * NCH;
-      uint4 rh[4], rl[4];
-      auto load_res = [&](int it) {
-        const int tl = it / NCH, c0 = (it % NCH) * 32;
-        long long orow;
-        if (p.res && it < n_it && row_info(tl, &orow)) {
-          const __half* rp = p.res + orow * p.C + nb * BN + c0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            rh[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
-            rl[i] = *reinterpret_cast<const uint4*>(rp + i * 8 + p.res_plane);
-          }
+      uint8_t* obox = sOut + grp * 16384;                                  // hi (8 KB) | lo (8 KB)
+      uint8_t* rbase = sRes + (size_t)grp * (kResSlots * 16384);
+      uint64_t* rfull = res_full + grp * 2;
+      auto tma_res = [&](int it) {                                         // executed by the group's thread 0 only
+        const int tl = it / NCH, c0 = (it % NCH) * 32, t = t_lo + tl;
+        const uint32_t slot = res_issue % kResSlots;
+        uint8_t* dst = rbase + slot * 16384;
+        mbar_arrive_expect_tx(&rfull[slot], 2 * p.o_tx_bytes);
+        for (int pl = 0; pl < 2; ++pl) {
+          if (p.conv) tma_load_5d(dst + pl * 8192, &tmR, &rfull[slot], nb * BN + c0, (t % p.tiles_w) * p.tile_w, (t / p.tiles_w) * p.tile_h, img, pl);
+          else tma_load_4d(dst + pl * 8192, &tmR, &rfull[slot], nb * BN + c0, t * 128, img, pl);
         }
+        ++res_issue;
       };
-      load_res(0);
+      if (p.res && gt == 0)
+        for (int i = 0; i < kResSlots && i < n_it; ++i) tma_res(i);
 #pragma unroll 1
       for (int it = 0; it < n_it; ++it) {
         const int tl = it / NCH, c0 = (it % NCH) * 32;
-        long long my_row;
-        const bool my_valid = row_info(tl, &my_row);
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_half + tl * BN + c0, r);
         tmem_ld_wait();
@@ -337,62 +353,65 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           v[i + 2] = __uint_as_float(r[i + 2]) * a4.z + b4.z;
           v[i + 3] = __uint_as_float(r[i + 3]) * a4.w + b4.w;
         }
-        if (p.res && my_valid) {
+        const uint32_t sw = (row_in_tile >> 1) & 3;                        // 64-byte swizzle: chunk ^= (row >> 1) & 3
+        if (p.res) {
+          const uint32_t slot = res_use % kResSlots;
+          mbar_wait(&rfull[slot], (res_use / kResSlots) & 1);
+          ++res_use;
+          const uint8_t* src = rbase + slot * 16384 + row_in_tile * 64;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __half2* h2 = reinterpret_cast<const __half2*>(&rh[i]);
-            const __half2* l2 = reinterpret_cast<const __half2*>(&rl[i]);
+          for (int q = 0; q < 4; ++q) {
+            const uint4 H = *reinterpret_cast<const uint4*>(src + ((q ^ sw) << 4));
+            const uint4 L = *reinterpret_cast<const uint4*>(src + 8192 + ((q ^ sw) << 4));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&H);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&L);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 a = __half22float2(h2[k]), b = __half22float2(l2[k]);
-              v[i * 8 + 2 * k] += a.x + b.x;
-              v[i * 8 + 2 * k + 1] += a.y + b.y;
+              v[q * 8 + 2 * k] += a.x + b.x;
+              v[q * 8 + 2 * k + 1] += a.y + b.y;
             }
           }
         }
-        load_res(it + 1);
         if (p.relu) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        uint32_t hi[16], lo[16];
+        // staging box free?  (the previous iteration's bulk stores must have finished READING it)
+        if (gt == 0) tma_store_wait_read<0>();
+        named_bar(bar_b, 128);                  // also: every thread has consumed this iteration's shortcut slot
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const __half2 h2 = __floats2half2_rn(v[i], v[i + 1]);
-          const float2 hf = __half22float2(h2);
-          const __half2 l2 = __floats2half2_rn(v[i] - hf.x, v[i + 1] - hf.y);
-          hi[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-          lo[i >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
-        }
-        const int sub = (c0 >> 5) & 1;                       // which 32-channel half of the 64-channel box
-        if (sub == 0) {
-          // the previous unit's bulk stores must have finished READING the staging boxes before they are refilled
-          if (gt == 0) tma_store_wait_read<0>();
-          named_bar(bar_b, 128);
-        }
+        for (int q = 0; q < 4; ++q) {
+          uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {                        // 16-byte chunks sub*4 + q of this row, XOR-swizzled by (row & 7)
-          const uint32_t off = row_in_tile * 128 + ((((sub << 2) + q) ^ (row_in_tile & 7)) << 4);
-          *reinterpret_cast<uint4*>(obox + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-          *reinterpret_cast<uint4*>(obox + 16384 + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-        }
-        if (sub == 1 || BN == 32) {
-          fence_proxy_async();
-          named_bar(bar_a, 128);
-          if (gt == 0) {
-            const int t = t_lo + tl, ch = nb * BN + (c0 & ~63);
-            if (p.conv) {
-              const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
-              tma_store_5d(&tmO, obox, ch, w0, h0, img, 0);
-              tma_store_5d(&tmO, obox + 16384, ch, w0, h0, img, 1);
-            } else {
-              tma_store_4d(&tmO, obox, ch, t * 128, img, 0);
-              tma_store_4d(&tmO, obox + 16384, ch, t * 128, img, 1);
-            }
-            tma_store_commit();
+          for (int k = 0; k < 4; ++k) {
+            const __half2 h2 = __floats2half2_rn(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(v[q * 8 + 2 * k] - hf.x, v[q * 8 + 2 * k + 1] - hf.y);
+            hi[k] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[k] = *reinterpret_cast<const uint32_t*>(&l2);
           }
+          const uint32_t off = row_in_tile * 64 + ((q ^ sw) << 4);
+          *reinterpret_cast<uint4*>(obox + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(obox + 8192 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();
+        named_bar(bar_a, 128);
+        if (gt == 0) {
+          const int t = t_lo + tl, ch = nb * BN + c0;
+          if (p.conv) {
+            const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
+            tma_store_5d(&tmO, obox, ch, w0, h0, img, 0);
+            tma_store_5d(&tmO, obox + 8192, ch, w0, h0, img, 1);
+          } else {
+            tma_store_4d(&tmO, obox, ch, t * 128, img, 0);
+            tma_store_4d(&tmO, obox + 8192, ch, t * 128, img, 1);
+          }
+          tma_store_commit();
+          if (p.res && it + kResSlots < n_it) tma_res(it + kResSlots);     // refill the slot everybody has just released
         }
       }
+      if (dbg_on) p.dbg[jj * 8 + 5] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&half_empty[grp]);
@@ -408,11 +427,12 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------------ host
 template <int BN, int GSZ>
-static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmGnParams& p, cudaStream_t st) {
+static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, GemmGnParams& p,
+                     cudaStream_t st) {
   const int np = p.nsplit == 3 ? 2 : 1;
   const size_t stage_bytes = (size_t)np * (128 * 64 * 2 + BN * 64 * 2);
-  const size_t fixed = 1024 + 4 * 16384 + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
-                       (2 * kGnMaxStages + 2 * kGnMaxTpc + 4) * 8 + 64;
+  const size_t fixed = 1024 + 2 * 16384 + 2 * ResSlots<BN>::value * 16384 + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
+                       (2 * kGnMaxStages + 2 * kGnMaxTpc + 8) * 8 + 64;
   int stages = (int)((232448 - fixed) / stage_bytes);
   if (stages > kGnMaxStages) stages = kGnMaxStages;
   if (stages < 2) { set_error("gemm_gn: tile too large for shared memory"); return MAED_ERR_UNSUPPORTED; }
@@ -446,7 +466,7 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   int n_clusters = max_clusters[p.cluster];
   if (n_clusters > p.items) n_clusters = p.items;
   cfg.gridDim = dim3(n_clusters * p.cluster);
-  MAED_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_gn_kernel<BN, GSZ>, tmA, tmB, tmO, p));
+  MAED_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_gn_kernel<BN, GSZ>, tmA, tmB, tmO, tmR, p));
   count_launch();
   return MAED_OK;
 }
@@ -462,7 +482,8 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   p.HW = a.H_out * a.W_out; p.C = a.C; p.nsplit = a.nsplit;
   p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.relu = a.relu; p.res = a.res; p.res_plane = a.res_plane;
   p.out = a.out; p.out_plane = a.out_plane;
-  CUtensorMap tmA, tmB, tmO;
+  p.dbg = a.dbg;
+  CUtensorMap tmA, tmB, tmO, tmR;
   const long long M = (long long)a.n_img * p.HW;
   if (a.conv) {
     if (a.Cin % 64 != 0) return MAED_ERR_UNSUPPORTED;
@@ -513,21 +534,32 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   if (a.conv) {
     const uint64_t dims[5] = {(uint64_t)a.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)a.n_img, 2};
     const uint64_t str[4] = {(uint64_t)a.C * 2, (uint64_t)p.W * a.C * 2, (uint64_t)p.H * p.W * a.C * 2, (uint64_t)a.out_plane * 2};
-    const uint32_t box[5] = {64, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1, 1};
-    MAED_PROPAGATE(make_tmap_f16(&tmO, a.out, 5, dims, str, box));
+    const uint32_t box[5] = {32, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1, 1};
+    p.o_tx_bytes = (uint32_t)(p.tile_w * p.tile_h * 64);
+    MAED_PROPAGATE(make_tmap_f16(&tmO, a.out, 5, dims, str, box, 64));
+    if (a.res) {
+      const uint64_t rstr[4] = {str[0], str[1], str[2], (uint64_t)a.res_plane * 2};
+      MAED_PROPAGATE(make_tmap_f16(&tmR, a.res, 5, dims, rstr, box, 64));
+    }
   } else {
     const uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)p.HW, (uint64_t)a.n_img, 2};
     const uint64_t str[3] = {(uint64_t)a.C * 2, (uint64_t)p.HW * a.C * 2, (uint64_t)a.out_plane * 2};
-    const uint32_t box[4] = {64, 128, 1, 1};
-    MAED_PROPAGATE(make_tmap_f16(&tmO, a.out, 4, dims, str, box));
+    const uint32_t box[4] = {32, 128, 1, 1};
+    p.o_tx_bytes = 128 * 64;
+    MAED_PROPAGATE(make_tmap_f16(&tmO, a.out, 4, dims, str, box, 64));
+    if (a.res) {
+      const uint64_t rstr[3] = {str[0], str[1], (uint64_t)a.res_plane * 2};
+      MAED_PROPAGATE(make_tmap_f16(&tmR, a.res, 4, dims, rstr, box, 64));
+    }
   }
-  if (bn == 128 && gsz == 4) return launch_gn<128, 4>(tmA, tmB, tmO, p, st);
-  if (bn == 128 && gsz == 8) return launch_gn<128, 8>(tmA, tmB, tmO, p, st);
-  if (bn == 128 && gsz == 16) return launch_gn<128, 16>(tmA, tmB, tmO, p, st);
-  if (bn == 128 && gsz == 32) return launch_gn<128, 32>(tmA, tmB, tmO, p, st);
-  if (bn == 64 && gsz == 2) return launch_gn<64, 2>(tmA, tmB, tmO, p, st);
-  if (bn == 64 && gsz == 4) return launch_gn<64, 4>(tmA, tmB, tmO, p, st);
-  if (bn == 64 && gsz == 8) return launch_gn<64, 8>(tmA, tmB, tmO, p, st);
+  if (!a.res) tmR = tmO;
+  if (bn == 128 && gsz == 4) return launch_gn<128, 4>(tmA, tmB, tmO, tmR, p, st);
+  if (bn == 128 && gsz == 8) return launch_gn<128, 8>(tmA, tmB, tmO, tmR, p, st);
+  if (bn == 128 && gsz == 16) return launch_gn<128, 16>(tmA, tmB, tmO, tmR, p, st);
+  if (bn == 128 && gsz == 32) return launch_gn<128, 32>(tmA, tmB, tmO, tmR, p, st);
+  if (bn == 64 && gsz == 2) return launch_gn<64, 2>(tmA, tmB, tmO, tmR, p, st);
+  if (bn == 64 && gsz == 4) return launch_gn<64, 4>(tmA, tmB, tmO, tmR, p, st);
+  if (bn == 64 && gsz == 8) return launch_gn<64, 8>(tmA, tmB, tmO, tmR, p, st);
   return MAED_ERR_UNSUPPORTED;
 }
 

@@ -34,6 +34,7 @@ struct ConvGnArgs {
   const float* gamma = nullptr; const float* beta = nullptr; float eps = 1e-5f; int relu = 0;
   const __half* res = nullptr; long long res_plane = 0;
   __half* out = nullptr; long long out_plane = 0;
+  long long* dbg = nullptr;                               // optional in-kernel timeline (see gemm_gn_sm100.cu)
 };
 // MAED_ERR_UNSUPPORTED (nothing launched) when the shape does not fit the fused kernel.
 int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st);

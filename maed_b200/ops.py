@@ -78,6 +78,18 @@ def im2col_stem(x, k_pad=152):
     return out
 
 
+def conv_gn(a, w, KH, KW, gamma, beta, relu, residual=None, nsplit=3, eps=1e-5, dbg=None):
+    """Fused conv + GroupNorm(32) (+ residual) (+ ReLU).  a: planes (2, n, H, W, Cin); w: planes (2, C, KH*KW*Cin);
+    residual: planes (2, n, H, W, C) -> planes (2, n, H, W, C)."""
+    _, n, H, W, Cin = a.shape
+    Cc = w.shape[1]
+    out = _planes_like((n, H, W, Cc), a.device)
+    call("maed_op_conv_gn", ptr(a), plane_stride(a), ptr(w), plane_stride(w), n, H, W, Cin, Cc, KH, KW, nsplit, ptr(gamma),
+         ptr(beta), C.c_float(eps), int(relu), ptr(residual), plane_stride(residual) if residual is not None else 0, ptr(out),
+         plane_stride(out), ptr(dbg), stream_ptr())
+    return out
+
+
 def stem_conv(x, w_planes, nsplit=3):
     """x: fp32 (n,3,224,224); w_planes: prep_conv_weight(w, k_pad=152) -> (fp32 (n*112*112, 64), stats (n,32,2) f64)."""
     n = x.shape[0]

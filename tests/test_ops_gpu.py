@@ -142,6 +142,28 @@ def test_groupnorm(ops, HW, C, relu, res):
     assert rel_err(out, ref) < 1e-6
 
 
+@pytest.mark.parametrize("n,H,Cin,C,k,relu,res", [(5, 56, 64, 256, 1, True, True), (3, 56, 64, 64, 3, True, False),
+                                                  (6, 28, 128, 512, 1, False, False), (4, 28, 128, 128, 3, True, False),
+                                                  (9, 14, 256, 1024, 1, True, True), (7, 14, 256, 256, 3, True, False),
+                                                  (2, 56, 256, 128, 1, True, False), (40, 14, 1024, 256, 1, True, False)])
+def test_conv_gn_fused(ops, n, H, Cin, C, k, relu, res):
+    """Fused tcgen05 conv + GroupNorm (+shortcut, ReLU), incl. the 4- and 8-CTA cluster (DSMEM) variants, vs PyTorch."""
+    x = _rand(n, Cin, H, H, seed=50)
+    w = _rand(C, Cin, k, k, scale=0.1, seed=51)
+    gamma, beta = 1 + 0.1 * _rand(C, seed=52), 0.1 * _rand(C, seed=53)
+    r = _rand(n, C, H, H, seed=54) if res else None
+    a = ops.split(x.permute(0, 2, 3, 1).contiguous())
+    wp = ops.split(w.permute(0, 2, 3, 1).reshape(C, -1).contiguous())
+    rp = ops.split(r.permute(0, 2, 3, 1).contiguous()) if res else None
+    out = ops.join(ops.conv_gn(a, wp, k, k, gamma, beta, relu, rp))
+    y = F.group_norm(F.conv2d(x.double(), w.double(), padding=k // 2), 32, gamma.double(), beta.double(), 1e-5)
+    if res:
+        y = y + r.double()
+    if relu:
+        y = F.relu(y)
+    assert rel_err(out, y.permute(0, 2, 3, 1)) < 2e-5
+
+
 def test_groupnorm_maxpool(ops):
     n, H, C = 2, 112, 64
     x = _rand(n, H, H, C, scale=1.5, seed=19)
