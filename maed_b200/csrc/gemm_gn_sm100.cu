@@ -34,6 +34,7 @@ struct GemmGnParams {
   int tiles_per_image, tpc, n_blocks, cluster, items;
   uint32_t a_tx_bytes;
   uint32_t o_tx_bytes;         // bytes of one 32-channel half-box plane (rows x 64 B)
+  uint32_t box_bytes;          // staging bytes after the pipeline stages: 32 KB + shortcut slots, or 64 KB (wide path)
   int conv, H, W, cin_blocks, KW, pad_h, pad_w, tile_h, tile_w, tiles_h, tiles_w;
   const float* gamma; const float* beta; float eps; int relu;
   const __half* res; long long res_plane;
@@ -71,7 +72,8 @@ __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.syn
 template <int BN, int GSZ>
 __global__ void __launch_bounds__(kGnThreads, 1)
 gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmGnParams p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmOw, const GemmGnParams p) {
   using namespace sm100;
   constexpr int G = BN / GSZ;                 // groups in the channel block
   static_assert(G >= 1 && G <= 32 && BN % 32 == 0 && BN <= 128, "unsupported block / group shape");
@@ -84,7 +86,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_bytes = np * (kABytes + kBBytes);
   uint8_t* sOut = smem + (size_t)p.stages * stage_bytes;                   // [2 groups][hi | lo][128 rows x 64 B], SW64 half-boxes
   uint8_t* sRes = sOut + 2 * 16384;                                        // [2 groups][kResSlots][hi | lo][128 rows x 64 B]
-  double* s_warp_part = reinterpret_cast<double*>(sRes + 2 * kResSlots * 16384);   // [2 groups][4 warps][32 groups][2]
+  double* s_warp_part = reinterpret_cast<double*>(sOut + p.box_bytes);     // [2 groups][4 warps][32 groups][2]
   double* s_parts = s_warp_part + 2 * 4 * 32 * 2;                          // [2 groups][8 ranks][32 groups][2]
   float* s_mr = reinterpret_cast<float*>(s_parts + 2 * kGnMaxCluster * 32 * 2);   // [2 groups][32][2] mean, rstd
   float* s_coef = s_mr + 2 * 64;                                           // [2 groups][a_c[128] | b_c[128]]
@@ -104,7 +106,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int t_lo = crank * p.tpc;
   const int my_tiles = max(0, min(p.tpc, p.tiles_per_image - t_lo));
 
-  if (warp == 0 && elect_one()) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO); if (p.res) prefetch_tmap(&tmR); }
+  if (warp == 0 && elect_one()) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO); prefetch_tmap(&tmOw); if (p.res) prefetch_tmap(&tmR); }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int t = 0; t < 2 * kGnMaxTpc; ++t) mbar_init(&tile_full[t], 1);
@@ -377,38 +379,80 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        // staging box free?  (the previous iteration's bulk stores must have finished READING it)
-        if (gt == 0) tma_store_wait_read<0>();
-        named_bar(bar_b, 128);                  // also: every thread has consumed this iteration's shortcut slot
+        if (p.res) {
+          // ---- narrow path (layers with a shortcut): one 32-channel half-box per iteration
+          if (gt == 0) tma_store_wait_read<0>();   // the previous iteration's bulk stores have finished READING the box
+          named_bar(bar_b, 128);                  // also: every thread has consumed this iteration's shortcut slot
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t hi[4], lo[4];
+          for (int q = 0; q < 4; ++q) {
+            uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const __half2 h2 = __floats2half2_rn(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]);
-            const float2 hf = __half22float2(h2);
-            const __half2 l2 = __floats2half2_rn(v[q * 8 + 2 * k] - hf.x, v[q * 8 + 2 * k + 1] - hf.y);
-            hi[k] = *reinterpret_cast<const uint32_t*>(&h2);
-            lo[k] = *reinterpret_cast<const uint32_t*>(&l2);
+            for (int k = 0; k < 4; ++k) {
+              const __half2 h2 = __floats2half2_rn(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]);
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(v[q * 8 + 2 * k] - hf.x, v[q * 8 + 2 * k + 1] - hf.y);
+              hi[k] = *reinterpret_cast<const uint32_t*>(&h2);
+              lo[k] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            const uint32_t off = row_in_tile * 64 + ((q ^ sw) << 4);
+            *reinterpret_cast<uint4*>(obox + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(obox + 8192 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-          const uint32_t off = row_in_tile * 64 + ((q ^ sw) << 4);
-          *reinterpret_cast<uint4*>(obox + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(obox + 8192 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        fence_proxy_async();
-        named_bar(bar_a, 128);
-        if (gt == 0) {
-          const int t = t_lo + tl, ch = nb * BN + c0;
-          if (p.conv) {
-            const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
-            tma_store_5d(&tmO, obox, ch, w0, h0, img, 0);
-            tma_store_5d(&tmO, obox + 8192, ch, w0, h0, img, 1);
-          } else {
-            tma_store_4d(&tmO, obox, ch, t * 128, img, 0);
-            tma_store_4d(&tmO, obox + 8192, ch, t * 128, img, 1);
+          fence_proxy_async();
+          named_bar(bar_a, 128);
+          if (gt == 0) {
+            const int t = t_lo + tl, ch = nb * BN + c0;
+            if (p.conv) {
+              const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
+              tma_store_5d(&tmO, obox, ch, w0, h0, img, 0);
+              tma_store_5d(&tmO, obox + 8192, ch, w0, h0, img, 1);
+            } else {
+              tma_store_4d(&tmO, obox, ch, t * 128, img, 0);
+              tma_store_4d(&tmO, obox + 8192, ch, t * 128, img, 1);
+            }
+            tma_store_commit();
+            if (it + kResSlots < n_it) tma_res(it + kResSlots);          // refill the slot everybody has just released
           }
-          tma_store_commit();
-          if (p.res && it + kResSlots < n_it) tma_res(it + kResSlots);     // refill the slot everybody has just released
+        } else {
+          // ---- wide path (no shortcut): 64-channel boxes (128-byte swizzle), one barrier pair per two iterations; the
+          // unused shortcut slots provide the extra staging space
+          uint8_t* wbox = sOut + grp * 32768;                            // hi (16 KB) | lo (16 KB)
+          const int sub = (c0 >> 5) & 1;
+          if (sub == 0) {
+            if (gt == 0) tma_store_wait_read<0>();
+            named_bar(bar_b, 128);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const __half2 h2 = __floats2half2_rn(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]);
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(v[q * 8 + 2 * k] - hf.x, v[q * 8 + 2 * k + 1] - hf.y);
+              hi[k] = *reinterpret_cast<const uint32_t*>(&h2);
+              lo[k] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            const uint32_t off = row_in_tile * 128 + ((((sub << 2) + q) ^ (row_in_tile & 7)) << 4);
+            *reinterpret_cast<uint4*>(wbox + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(wbox + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          if (sub == 1) {
+            fence_proxy_async();
+            named_bar(bar_a, 128);
+            if (gt == 0) {
+              const int t = t_lo + tl, ch = nb * BN + (c0 & ~63);
+              if (p.conv) {
+                const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
+                tma_store_5d(&tmOw, wbox, ch, w0, h0, img, 0);
+                tma_store_5d(&tmOw, wbox + 16384, ch, w0, h0, img, 1);
+              } else {
+                tma_store_4d(&tmOw, wbox, ch, t * 128, img, 0);
+                tma_store_4d(&tmOw, wbox + 16384, ch, t * 128, img, 1);
+              }
+              tma_store_commit();
+            }
+          }
         }
       }
       if (dbg_on) p.dbg[jj * 8 + 5] = clock64();
@@ -427,11 +471,12 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------------ host
 template <int BN, int GSZ>
-static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, GemmGnParams& p,
-                     cudaStream_t st) {
+static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
+                     const CUtensorMap& tmOw, GemmGnParams& p, cudaStream_t st) {
   const int np = p.nsplit == 3 ? 2 : 1;
   const size_t stage_bytes = (size_t)np * (128 * 64 * 2 + BN * 64 * 2);
-  const size_t fixed = 1024 + 2 * 16384 + 2 * ResSlots<BN>::value * 16384 + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
+  p.box_bytes = p.res ? (2 * 16384 + 2 * ResSlots<BN>::value * 16384) : 65536;
+  const size_t fixed = 1024 + p.box_bytes + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
                        (2 * kGnMaxStages + 2 * kGnMaxTpc + 8) * 8 + 64;
   int stages = (int)((232448 - fixed) / stage_bytes);
   if (stages > kGnMaxStages) stages = kGnMaxStages;
@@ -466,7 +511,7 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   int n_clusters = max_clusters[p.cluster];
   if (n_clusters > p.items) n_clusters = p.items;
   cfg.gridDim = dim3(n_clusters * p.cluster);
-  MAED_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_gn_kernel<BN, GSZ>, tmA, tmB, tmO, tmR, p));
+  MAED_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_gn_kernel<BN, GSZ>, tmA, tmB, tmO, tmR, tmOw, p));
   count_launch();
   return MAED_OK;
 }
@@ -483,7 +528,7 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.relu = a.relu; p.res = a.res; p.res_plane = a.res_plane;
   p.out = a.out; p.out_plane = a.out_plane;
   p.dbg = a.dbg;
-  CUtensorMap tmA, tmB, tmO, tmR;
+  CUtensorMap tmA, tmB, tmO, tmR, tmOw;
   const long long M = (long long)a.n_img * p.HW;
   if (a.conv) {
     if (a.Cin % 64 != 0) return MAED_ERR_UNSUPPORTED;
@@ -537,6 +582,7 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
     const uint32_t box[5] = {32, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1, 1};
     p.o_tx_bytes = (uint32_t)(p.tile_w * p.tile_h * 64);
     MAED_PROPAGATE(make_tmap_f16(&tmO, a.out, 5, dims, str, box, 64));
+    { const uint32_t wb[5] = {64, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1, 1}; MAED_PROPAGATE(make_tmap_f16(&tmOw, a.out, 5, dims, str, wb, 128)); }
     if (a.res) {
       const uint64_t rstr[4] = {str[0], str[1], str[2], (uint64_t)a.res_plane * 2};
       MAED_PROPAGATE(make_tmap_f16(&tmR, a.res, 5, dims, rstr, box, 64));
@@ -547,19 +593,20 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
     const uint32_t box[4] = {32, 128, 1, 1};
     p.o_tx_bytes = 128 * 64;
     MAED_PROPAGATE(make_tmap_f16(&tmO, a.out, 4, dims, str, box, 64));
+    { const uint32_t wb[4] = {64, 128, 1, 1}; MAED_PROPAGATE(make_tmap_f16(&tmOw, a.out, 4, dims, str, wb, 128)); }
     if (a.res) {
       const uint64_t rstr[3] = {str[0], str[1], (uint64_t)a.res_plane * 2};
       MAED_PROPAGATE(make_tmap_f16(&tmR, a.res, 4, dims, rstr, box, 64));
     }
   }
   if (!a.res) tmR = tmO;
-  if (bn == 128 && gsz == 4) return launch_gn<128, 4>(tmA, tmB, tmO, tmR, p, st);
-  if (bn == 128 && gsz == 8) return launch_gn<128, 8>(tmA, tmB, tmO, tmR, p, st);
-  if (bn == 128 && gsz == 16) return launch_gn<128, 16>(tmA, tmB, tmO, tmR, p, st);
-  if (bn == 128 && gsz == 32) return launch_gn<128, 32>(tmA, tmB, tmO, tmR, p, st);
-  if (bn == 64 && gsz == 2) return launch_gn<64, 2>(tmA, tmB, tmO, tmR, p, st);
-  if (bn == 64 && gsz == 4) return launch_gn<64, 4>(tmA, tmB, tmO, tmR, p, st);
-  if (bn == 64 && gsz == 8) return launch_gn<64, 8>(tmA, tmB, tmO, tmR, p, st);
+  if (bn == 128 && gsz == 4) return launch_gn<128, 4>(tmA, tmB, tmO, tmR, tmOw, p, st);
+  if (bn == 128 && gsz == 8) return launch_gn<128, 8>(tmA, tmB, tmO, tmR, tmOw, p, st);
+  if (bn == 128 && gsz == 16) return launch_gn<128, 16>(tmA, tmB, tmO, tmR, tmOw, p, st);
+  if (bn == 128 && gsz == 32) return launch_gn<128, 32>(tmA, tmB, tmO, tmR, tmOw, p, st);
+  if (bn == 64 && gsz == 2) return launch_gn<64, 2>(tmA, tmB, tmO, tmR, tmOw, p, st);
+  if (bn == 64 && gsz == 4) return launch_gn<64, 4>(tmA, tmB, tmO, tmR, tmOw, p, st);
+  if (bn == 64 && gsz == 8) return launch_gn<64, 8>(tmA, tmB, tmO, tmR, tmOw, p, st);
   return MAED_ERR_UNSUPPORTED;
 }
 
