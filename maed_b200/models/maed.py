@@ -171,6 +171,11 @@ class MAED(nn.Module):
         """reference maed.py:52-66.  `J_regressor` (17x6890) only matters once the SMPL tier exists: with the
         placeholder body model verts are zeros, so J_regressor @ verts is zeros as well."""
         N, T = x.shape[:2]
+        if self.training and any(p.requires_grad for p in self.parameters()) and kwargs.get("_allow_train_mode") is None:
+            import warnings
+            warnings.warn("maed_b200.MAED.forward is inference-only in this version: outputs carry no autograd graph and "
+                          "train()-mode dropout (reference ktd.py:54-56) is not applied; call .eval() for inference.",
+                          RuntimeWarning, stacklevel=2)
         o = self._run(x, want_taps=kwargs.get("_taps"))
         BT = N * T
         nj = 17 if J_regressor is not None else self.decoder.smpl.n_joints

@@ -78,3 +78,15 @@ def test_cpu_input_fails_loudly():
     m = MAED("ste", 1, 12, "vanilla", "ktd")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 1, 3, 224, 224))
+
+
+def test_train_mode_warns_inference_only():
+    """The backward / train step is not built yet: calling the module in train() mode must say so (loudly)."""
+    import warnings
+    from maed_b200.models import MAED
+    m = MAED("ste", 1, 12, "vanilla", "ktd").train()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m(torch.zeros(1, 1, 3, 224, 224))
+    assert any("inference-only" in str(x.message) for x in w)
