@@ -27,7 +27,7 @@ static constexpr int kGnMaxTpc = 4;
 static constexpr int kGnMaxStages = 4;
 static constexpr int kGnMaxCluster = 8;
 // shortcut prefetch slots of the epilogue (iterations in flight + 1): 3 when shared memory allows (BN = 64), else 2
-template <int BN> struct ResSlots { static constexpr int value = (BN <= 64) ? 2 : 1; };
+template <int BN> struct ResSlots { static constexpr int value = (BN <= 64) ? 3 : 2; };
 
 struct GemmGnParams {
   int HW, C, K, num_k_blocks, nsplit, stages;
@@ -84,8 +84,10 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic ST/LD)
   const int np = p.nsplit == 3 ? 2 : 1;
   const uint32_t stage_bytes = np * (kABytes + kBBytes);
-  uint8_t* sOut = smem + (size_t)p.stages * stage_bytes;                   // [2 groups][hi | lo][128 rows x 64 B], SW64 half-boxes
-  uint8_t* sRes = sOut + 2 * 16384;                                        // [2 groups][kResSlots][hi | lo][128 rows x 64 B]
+  // staging after the pipeline stages.  Shortcut layers: [2 groups][kResSlots][hi | lo][128 rows x 64 B] half-boxes (the
+  // shortcut lands here by TMA, is updated IN PLACE and stored by TMA); other layers: [2 groups][hi | lo][128 x 128 B] boxes.
+  uint8_t* sOut = smem + (size_t)p.stages * stage_bytes;
+  uint8_t* sRes = sOut;
   double* s_warp_part = reinterpret_cast<double*>(sOut + p.box_bytes);     // [2 groups][4 warps][32 groups][2]
   double* s_parts = s_warp_part + 2 * 4 * 32 * 2;                          // [2 groups][8 ranks][32 groups][2]
   float* s_mr = reinterpret_cast<float*>(s_parts + 2 * kGnMaxCluster * 32 * 2);   // [2 groups][32][2] mean, rstd
@@ -96,8 +98,8 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tile_full = bars + 2 * kGnMaxStages;                           // [2 halves][kGnMaxTpc]
   uint64_t* half_empty = tile_full + 2 * kGnMaxTpc;                        // [2]
   uint64_t* parts_full = half_empty + 2;                                   // [2 buf]
-  uint64_t* res_full = parts_full + 2;                                     // [2 groups][2 slots]
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
+  uint64_t* res_full = parts_full + 2;                                     // [2 groups][4 slots]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(res_full + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CS = p.cluster;
@@ -111,7 +113,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int t = 0; t < 2 * kGnMaxTpc; ++t) mbar_init(&tile_full[t], 1);
     for (int h = 0; h < 2; ++h) { mbar_init(&half_empty[h], 4); mbar_init(&parts_full[h], CS * G); }
-    for (int h = 0; h < 4; ++h) mbar_init(&res_full[h], 1);
+    for (int h = 0; h < 8; ++h) mbar_init(&res_full[h], 1);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_base_ptr, 512); tmem_relinquish(); }
@@ -322,9 +324,8 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       //   * results are staged in a 64-byte-swizzled half-box and written by TMA stores (clipped at the image edge).
       constexpr int NCH = BN / 32;
       const int n_it = my_tiles * NCH;
-      uint8_t* obox = sOut + grp * 16384;                                  // hi (8 KB) | lo (8 KB)
       uint8_t* rbase = sRes + (size_t)grp * (kResSlots * 16384);
-      uint64_t* rfull = res_full + grp * 2;
+      uint64_t* rfull = res_full + grp * 4;
       auto tma_res = [&](int it) {                                         // executed by the group's thread 0 only
         const int tl = it / NCH, c0 = (it % NCH) * 32, t = t_lo + tl;
         const uint32_t slot = res_issue % kResSlots;
@@ -336,8 +337,10 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         ++res_issue;
       };
-      if (p.res && gt == 0)
-        for (int i = 0; i < kResSlots && i < n_it; ++i) tma_res(i);
+      if (p.res && gt == 0) {
+        tma_store_wait_read<0>();                                          // the previous item's stores have released every slot
+        for (int i = 0; i < kResSlots - 1 && i < n_it; ++i) tma_res(i);
+      }
 #pragma unroll 1
       for (int it = 0; it < n_it; ++it) {
         const int tl = it / NCH, c0 = (it % NCH) * 32;
@@ -360,7 +363,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t slot = res_use % kResSlots;
           mbar_wait(&rfull[slot], (res_use / kResSlots) & 1);
           ++res_use;
-          const uint8_t* src = rbase + slot * 16384 + row_in_tile * 64;
+          const uint8_t* src = rbase + slot * 16384 + row_in_tile * 64;   // (the result goes back to the same place)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 H = *reinterpret_cast<const uint4*>(src + ((q ^ sw) << 4));
@@ -380,9 +383,9 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (p.res) {
-          // ---- narrow path (layers with a shortcut): one 32-channel half-box per iteration
-          if (gt == 0) tma_store_wait_read<0>();   // the previous iteration's bulk stores have finished READING the box
-          named_bar(bar_b, 128);                  // also: every thread has consumed this iteration's shortcut slot
+          // ---- narrow path (layers with a shortcut): the result replaces the shortcut IN PLACE in its slot (every thread
+          // touches only its own row, so no barrier is needed before the writes) and is stored from there by TMA
+          uint8_t* dstb = rbase + ((res_use - 1) % kResSlots) * 16384 + row_in_tile * 64;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint32_t hi[4], lo[4];
@@ -394,24 +397,27 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               hi[k] = *reinterpret_cast<const uint32_t*>(&h2);
               lo[k] = *reinterpret_cast<const uint32_t*>(&l2);
             }
-            const uint32_t off = row_in_tile * 64 + ((q ^ sw) << 4);
-            *reinterpret_cast<uint4*>(obox + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(obox + 8192 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(dstb + ((q ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(dstb + 8192 + ((q ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async();
           named_bar(bar_a, 128);
           if (gt == 0) {
             const int t = t_lo + tl, ch = nb * BN + c0;
+            const uint8_t* sb = rbase + ((res_use - 1) % kResSlots) * 16384;
             if (p.conv) {
               const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
-              tma_store_5d(&tmO, obox, ch, w0, h0, img, 0);
-              tma_store_5d(&tmO, obox + 8192, ch, w0, h0, img, 1);
+              tma_store_5d(&tmO, sb, ch, w0, h0, img, 0);
+              tma_store_5d(&tmO, sb + 8192, ch, w0, h0, img, 1);
             } else {
-              tma_store_4d(&tmO, obox, ch, t * 128, img, 0);
-              tma_store_4d(&tmO, obox + 8192, ch, t * 128, img, 1);
+              tma_store_4d(&tmO, sb, ch, t * 128, img, 0);
+              tma_store_4d(&tmO, sb + 8192, ch, t * 128, img, 1);
             }
             tma_store_commit();
-            if (it + kResSlots < n_it) tma_res(it + kResSlots);          // refill the slot everybody has just released
+            if (it + kResSlots - 1 < n_it) {
+              tma_store_wait_read<1>();          // every store but the one just issued has released its slot
+              tma_res(it + kResSlots - 1);
+            }
           }
         } else {
           // ---- wide path (no shortcut): 64-channel boxes (128-byte swizzle), one barrier pair per two iterations; the
@@ -475,9 +481,9 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      const CUtensorMap& tmOw, GemmGnParams& p, cudaStream_t st) {
   const int np = p.nsplit == 3 ? 2 : 1;
   const size_t stage_bytes = (size_t)np * (128 * 64 * 2 + BN * 64 * 2);
-  p.box_bytes = p.res ? (2 * 16384 + 2 * ResSlots<BN>::value * 16384) : 65536;
+  p.box_bytes = p.res ? (2 * ResSlots<BN>::value * 16384) : 65536;
   const size_t fixed = 1024 + p.box_bytes + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
-                       (2 * kGnMaxStages + 2 * kGnMaxTpc + 8) * 8 + 64;
+                       (2 * kGnMaxStages + 2 * kGnMaxTpc + 12) * 8 + 64;
   int stages = (int)((232448 - fixed) / stage_bytes);
   if (stages > kGnMaxStages) stages = kGnMaxStages;
   if (stages < 2) { set_error("gemm_gn: tile too large for shared memory"); return MAED_ERR_UNSUPPORTED; }
