@@ -34,7 +34,8 @@ struct GemmGnParams {
   int tiles_per_image, tpc, n_blocks, cluster, items;
   uint32_t a_tx_bytes;
   uint32_t o_tx_bytes;         // bytes of one 32-channel half-box plane (rows x 64 B)
-  uint32_t box_bytes;          // staging bytes after the pipeline stages: 32 KB + shortcut slots, or 64 KB (wide path)
+  uint32_t box_bytes;          // staging bytes after the pipeline stages: 2 groups x res_slots x 16 KB
+  int res_slots;               // staging half-box slots per epilogue group (2 or 3)
   int conv, H, W, cin_blocks, KW, pad_h, pad_w, tile_h, tile_w, tiles_h, tiles_w;
   const float* gamma; const float* beta; float eps; int relu;
   const __half* res; long long res_plane;
@@ -78,7 +79,6 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int G = BN / GSZ;                 // groups in the channel block
   static_assert(G >= 1 && G <= 32 && BN % 32 == 0 && BN <= 128, "unsupported block / group shape");
   constexpr uint32_t kABytes = 128 * 64 * 2, kBBytes = BN * 64 * 2;
-  constexpr int kResSlots = ResSlots<BN>::value;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic ST/LD)
@@ -98,8 +98,9 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tile_full = bars + 2 * kGnMaxStages;                           // [2 halves][kGnMaxTpc]
   uint64_t* half_empty = tile_full + 2 * kGnMaxTpc;                        // [2]
   uint64_t* parts_full = half_empty + 2;                                   // [2 buf]
-  uint64_t* res_full = parts_full + 2;                                     // [2 groups][4 slots]
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(res_full + 8);
+  uint64_t* res_full = parts_full + 2;                                     // [2 groups][4 slots]: slot may be used by the epilogue
+  uint64_t* box_ready = res_full + 8;                                      // [2 groups][4 slots]: slot holds a finished result
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(box_ready + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CS = p.cluster;
@@ -113,7 +114,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int t = 0; t < 2 * kGnMaxTpc; ++t) mbar_init(&tile_full[t], 1);
     for (int h = 0; h < 2; ++h) { mbar_init(&half_empty[h], 4); mbar_init(&parts_full[h], CS * G); }
-    for (int h = 0; h < 8; ++h) mbar_init(&res_full[h], 1);
+    for (int h = 0; h < 8; ++h) { mbar_init(&res_full[h], 1); mbar_init(&box_ready[h], 128); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_base_ptr, 512); tmem_relinquish(); }
@@ -197,6 +198,63 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  } else if (warp == 2 || warp == 3) {
+    // ============================================================ epilogue I/O streams (one thread per epilogue group)
+    // All global traffic of pass 2 is bulk + asynchronous and issued from here, so the epilogue warps never block on a
+    // named barrier: they wait for a slot (res_full), update it in place and signal box_ready.
+    //   slot life cycle:  [TMA load of the shortcut half-box | plain arrive]  -> res_full -> epilogue -> box_ready
+    //                     -> TMA store -> (store has read the slot) -> refill
+    if (elect_one()) {
+      const int grp = warp - 2;
+      const int RS = p.res_slots;
+      constexpr int NCH = BN / 32;
+      uint8_t* rbase = sRes + (size_t)grp * (RS * 16384);
+      uint64_t* rfull = res_full + grp * 4;
+      uint64_t* bready = box_ready + grp * 4;
+      uint32_t n_fill = 0, n_store = 0;                   // running slot counters of this stream
+      for (int item = cluster_id + grp * n_clusters; item < p.items; item += 2 * n_clusters) {
+        const int img = item / p.n_blocks, nb = item % p.n_blocks;
+        const int n_it = my_tiles * NCH;
+        auto fill = [&](int it) {                         // make slot (n_fill % RS) usable for iteration `it`
+          const uint32_t slot = n_fill % RS;
+          if (p.res) {
+            const int tl = it / NCH, c0 = (it % NCH) * 32, t = t_lo + tl;
+            uint8_t* dst = rbase + slot * 16384;
+            mbar_arrive_expect_tx(&rfull[slot], 2 * p.o_tx_bytes);
+            for (int pl = 0; pl < 2; ++pl) {
+              if (p.conv) tma_load_5d(dst + pl * 8192, &tmR, &rfull[slot], nb * BN + c0, (t % p.tiles_w) * p.tile_w, (t / p.tiles_w) * p.tile_h, img, pl);
+              else tma_load_4d(dst + pl * 8192, &tmR, &rfull[slot], nb * BN + c0, t * 128, img, pl);
+            }
+          } else {
+            mbar_arrive(&rfull[slot]);
+          }
+          ++n_fill;
+        };
+        tma_store_wait_read<0>();                         // every slot of the previous item has been stored
+        for (int i = 0; i < RS - 1 && i < n_it; ++i) fill(i);
+        for (int it = 0; it < n_it; ++it) {
+          const uint32_t slot = n_store % RS;
+          mbar_wait(&bready[slot], (n_store / RS) & 1);
+          ++n_store;
+          const int tl = it / NCH, c0 = (it % NCH) * 32, t = t_lo + tl, ch = nb * BN + c0;
+          const uint8_t* sb = rbase + slot * 16384;
+          if (p.conv) {
+            const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
+            tma_store_5d(&tmO, sb, ch, w0, h0, img, 0);
+            tma_store_5d(&tmO, sb + 8192, ch, w0, h0, img, 1);
+          } else {
+            tma_store_4d(&tmO, sb, ch, t * 128, img, 0);
+            tma_store_4d(&tmO, sb + 8192, ch, t * 128, img, 1);
+          }
+          tma_store_commit();
+          if (it + RS - 1 < n_it) {
+            tma_store_wait_read<1>();                     // every store but the one just issued has released its slot
+            fill(it + RS - 1);
+          }
+        }
+      }
+      tma_store_wait_all();
+    }
   } else if (warp >= 4) {
     // =============================================================================== epilogue warps
     // Two independent groups of 4 warps: group g owns TMEM half g and the items of parity g, so the statistics
@@ -213,7 +271,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int bar_a = 1 + grp * 2, bar_b = 2 + grp * 2;
     const uint32_t t_half = tmem_base + grp * 256 + lane_off;
     uint32_t jj = 0;                           // per-group item counter
-    uint32_t res_issue = 0, res_use = 0;       // running shortcut-slot counters (slot = n % kResSlots, parity = (n / kResSlots) & 1)
+    uint32_t res_use = 0;                      // running slot counter of this group (slot = n % RS, parity = (n / RS) & 1)
     for (int item = cluster_id + grp * n_clusters; item < p.items; item += 2 * n_clusters, ++jj) {
       const int img = item / p.n_blocks, nb = item % p.n_blocks;
       const uint32_t hphase = jj & 1;
@@ -324,23 +382,11 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       //   * results are staged in a 64-byte-swizzled half-box and written by TMA stores (clipped at the image edge).
       constexpr int NCH = BN / 32;
       const int n_it = my_tiles * NCH;
-      uint8_t* rbase = sRes + (size_t)grp * (kResSlots * 16384);
+      const int RS = p.res_slots;
+      uint8_t* rbase = sRes + (size_t)grp * (RS * 16384);
       uint64_t* rfull = res_full + grp * 4;
-      auto tma_res = [&](int it) {                                         // executed by the group's thread 0 only
-        const int tl = it / NCH, c0 = (it % NCH) * 32, t = t_lo + tl;
-        const uint32_t slot = res_issue % kResSlots;
-        uint8_t* dst = rbase + slot * 16384;
-        mbar_arrive_expect_tx(&rfull[slot], 2 * p.o_tx_bytes);
-        for (int pl = 0; pl < 2; ++pl) {
-          if (p.conv) tma_load_5d(dst + pl * 8192, &tmR, &rfull[slot], nb * BN + c0, (t % p.tiles_w) * p.tile_w, (t / p.tiles_w) * p.tile_h, img, pl);
-          else tma_load_4d(dst + pl * 8192, &tmR, &rfull[slot], nb * BN + c0, t * 128, img, pl);
-        }
-        ++res_issue;
-      };
-      if (p.res && gt == 0) {
-        tma_store_wait_read<0>();                                          // the previous item's stores have released every slot
-        for (int i = 0; i < kResSlots - 1 && i < n_it; ++i) tma_res(i);
-      }
+      uint64_t* bready = box_ready + grp * 4;
+      const uint32_t sw = (row_in_tile >> 1) & 3;                          // 64-byte swizzle: chunk ^= (row >> 1) & 3
 #pragma unroll 1
       for (int it = 0; it < n_it; ++it) {
         const int tl = it / NCH, c0 = (it % NCH) * 32;
@@ -358,16 +404,15 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           v[i + 2] = __uint_as_float(r[i + 2]) * a4.z + b4.z;
           v[i + 3] = __uint_as_float(r[i + 3]) * a4.w + b4.w;
         }
-        const uint32_t sw = (row_in_tile >> 1) & 3;                        // 64-byte swizzle: chunk ^= (row >> 1) & 3
+        const uint32_t slot = res_use % RS;
+        mbar_wait(&rfull[slot], (res_use / RS) & 1);                       // slot free (and, with a shortcut, loaded)
+        ++res_use;
+        uint8_t* box = rbase + slot * 16384 + row_in_tile * 64;            // this thread's row: hi at +0, lo at +8192
         if (p.res) {
-          const uint32_t slot = res_use % kResSlots;
-          mbar_wait(&rfull[slot], (res_use / kResSlots) & 1);
-          ++res_use;
-          const uint8_t* src = rbase + slot * 16384 + row_in_tile * 64;   // (the result goes back to the same place)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 H = *reinterpret_cast<const uint4*>(src + ((q ^ sw) << 4));
-            const uint4 L = *reinterpret_cast<const uint4*>(src + 8192 + ((q ^ sw) << 4));
+            const uint4 H = *reinterpret_cast<const uint4*>(box + ((q ^ sw) << 4));
+            const uint4 L = *reinterpret_cast<const uint4*>(box + 8192 + ((q ^ sw) << 4));
             const __half2* h2 = reinterpret_cast<const __half2*>(&H);
             const __half2* l2 = reinterpret_cast<const __half2*>(&L);
 #pragma unroll
@@ -382,84 +427,22 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (p.res) {
-          // ---- narrow path (layers with a shortcut): the result replaces the shortcut IN PLACE in its slot (every thread
-          // touches only its own row, so no barrier is needed before the writes) and is stored from there by TMA
-          uint8_t* dstb = rbase + ((res_use - 1) % kResSlots) * 16384 + row_in_tile * 64;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t hi[4], lo[4];
+        for (int q = 0; q < 4; ++q) {                                      // in place: each thread touches only its own row
+          uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const __half2 h2 = __floats2half2_rn(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]);
-              const float2 hf = __half22float2(h2);
-              const __half2 l2 = __floats2half2_rn(v[q * 8 + 2 * k] - hf.x, v[q * 8 + 2 * k + 1] - hf.y);
-              hi[k] = *reinterpret_cast<const uint32_t*>(&h2);
-              lo[k] = *reinterpret_cast<const uint32_t*>(&l2);
-            }
-            *reinterpret_cast<uint4*>(dstb + ((q ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(dstb + 8192 + ((q ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int k = 0; k < 4; ++k) {
+            const __half2 h2 = __floats2half2_rn(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(v[q * 8 + 2 * k] - hf.x, v[q * 8 + 2 * k + 1] - hf.y);
+            hi[k] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[k] = *reinterpret_cast<const uint32_t*>(&l2);
           }
-          fence_proxy_async();
-          named_bar(bar_a, 128);
-          if (gt == 0) {
-            const int t = t_lo + tl, ch = nb * BN + c0;
-            const uint8_t* sb = rbase + ((res_use - 1) % kResSlots) * 16384;
-            if (p.conv) {
-              const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
-              tma_store_5d(&tmO, sb, ch, w0, h0, img, 0);
-              tma_store_5d(&tmO, sb + 8192, ch, w0, h0, img, 1);
-            } else {
-              tma_store_4d(&tmO, sb, ch, t * 128, img, 0);
-              tma_store_4d(&tmO, sb + 8192, ch, t * 128, img, 1);
-            }
-            tma_store_commit();
-            if (it + kResSlots - 1 < n_it) {
-              tma_store_wait_read<1>();          // every store but the one just issued has released its slot
-              tma_res(it + kResSlots - 1);
-            }
-          }
-        } else {
-          // ---- wide path (no shortcut): 64-channel boxes (128-byte swizzle), one barrier pair per two iterations; the
-          // unused shortcut slots provide the extra staging space
-          uint8_t* wbox = sOut + grp * 32768;                            // hi (16 KB) | lo (16 KB)
-          const int sub = (c0 >> 5) & 1;
-          if (sub == 0) {
-            if (gt == 0) tma_store_wait_read<0>();
-            named_bar(bar_b, 128);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const __half2 h2 = __floats2half2_rn(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]);
-              const float2 hf = __half22float2(h2);
-              const __half2 l2 = __floats2half2_rn(v[q * 8 + 2 * k] - hf.x, v[q * 8 + 2 * k + 1] - hf.y);
-              hi[k] = *reinterpret_cast<const uint32_t*>(&h2);
-              lo[k] = *reinterpret_cast<const uint32_t*>(&l2);
-            }
-            const uint32_t off = row_in_tile * 128 + ((((sub << 2) + q) ^ (row_in_tile & 7)) << 4);
-            *reinterpret_cast<uint4*>(wbox + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(wbox + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-          if (sub == 1) {
-            fence_proxy_async();
-            named_bar(bar_a, 128);
-            if (gt == 0) {
-              const int t = t_lo + tl, ch = nb * BN + (c0 & ~63);
-              if (p.conv) {
-                const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
-                tma_store_5d(&tmOw, wbox, ch, w0, h0, img, 0);
-                tma_store_5d(&tmOw, wbox + 16384, ch, w0, h0, img, 1);
-              } else {
-                tma_store_4d(&tmOw, wbox, ch, t * 128, img, 0);
-                tma_store_4d(&tmOw, wbox + 16384, ch, t * 128, img, 1);
-              }
-              tma_store_commit();
-            }
-          }
+          *reinterpret_cast<uint4*>(box + ((q ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(box + 8192 + ((q ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
+        fence_proxy_async();                                               // generic-proxy writes -> visible to the TMA store
+        mbar_arrive(&bready[slot]);
       }
       if (dbg_on) p.dbg[jj * 8 + 5] = clock64();
       tc_fence_before();
@@ -468,7 +451,6 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
-  if (warp >= 4 && (threadIdx.x & 127) == 0) tma_store_wait_all();       // this thread issued the group's bulk stores
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();
@@ -481,9 +463,10 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      const CUtensorMap& tmOw, GemmGnParams& p, cudaStream_t st) {
   const int np = p.nsplit == 3 ? 2 : 1;
   const size_t stage_bytes = (size_t)np * (128 * 64 * 2 + BN * 64 * 2);
-  p.box_bytes = p.res ? (2 * ResSlots<BN>::value * 16384) : 65536;
+  p.res_slots = p.res ? ResSlots<BN>::value : 2;
+  p.box_bytes = 2 * p.res_slots * 16384;
   const size_t fixed = 1024 + p.box_bytes + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
-                       (2 * kGnMaxStages + 2 * kGnMaxTpc + 12) * 8 + 64;
+                       (2 * kGnMaxStages + 2 * kGnMaxTpc + 20) * 8 + 64;
   int stages = (int)((232448 - fixed) / stage_bytes);
   if (stages > kGnMaxStages) stages = kGnMaxStages;
   if (stages < 2) { set_error("gemm_gn: tile too large for shared memory"); return MAED_ERR_UNSUPPORTED; }
