@@ -535,7 +535,14 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   // channel-block width, tiles per CTA and cluster size: an image's tiles x BN columns must fit half of the TMEM
   // (256 columns) of the CTAs of one cluster
   int bn, cluster, tpc;
-  if (p.tiles_per_image <= 2 && a.C % 128 == 0) { bn = 128; tpc = 2; cluster = 1; }
+  if (a.res) {
+    // shortcut layers are epilogue-bound: 64-wide blocks leave shared memory for 3 shortcut slots (2 TMA loads in flight)
+    if (p.tiles_per_image <= 2) { bn = 64; tpc = 2; cluster = 1; }
+    else if (p.tiles_per_image <= 8) { bn = 64; tpc = 4; cluster = 2; }
+    else if (p.tiles_per_image <= 32) { bn = 64; tpc = 4; cluster = 8; }
+    else return MAED_ERR_UNSUPPORTED;
+  }
+  else if (p.tiles_per_image <= 2 && a.C % 128 == 0) { bn = 128; tpc = 2; cluster = 1; }
   else if (p.tiles_per_image <= 8 && a.C % 128 == 0) { bn = 128; tpc = 2; cluster = 4; }
   else if (p.tiles_per_image <= 8) { bn = 64; tpc = 4; cluster = 2; }
   else if (p.tiles_per_image <= 32) { bn = 64; tpc = 4; cluster = 8; }
@@ -596,6 +603,8 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   if (bn == 64 && gsz == 2) return launch_gn<64, 2>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 64 && gsz == 4) return launch_gn<64, 4>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 64 && gsz == 8) return launch_gn<64, 8>(tmA, tmB, tmO, tmR, tmOw, p, st);
+  if (bn == 64 && gsz == 16) return launch_gn<64, 16>(tmA, tmB, tmO, tmR, tmOw, p, st);
+  if (bn == 64 && gsz == 32) return launch_gn<64, 32>(tmA, tmB, tmO, tmR, tmOw, p, st);
   return MAED_ERR_UNSUPPORTED;
 }
 
