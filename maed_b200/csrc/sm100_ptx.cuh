@@ -216,6 +216,16 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                 // SWIZZLE_128B
   return d;
 }
+// Same for 64-byte rows (32 halfs per K block) with the 64-byte swizzle: 8-row groups are 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;          // SBO = 512 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;                 // SWIZZLE_64B
+  return d;
+}
 // MN-major operand tile (e.g. V[kv][d] used as B with N=d contiguous): atoms of 64 (MN) x 8 (K) halfs,
 // 128-byte swizzle; LBO = byte distance between 64-element MN blocks, SBO = between 8-row K groups.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
