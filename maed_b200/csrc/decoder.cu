@@ -1,7 +1,7 @@
-// Tail of the hot path, fp32 on CUDA cores (exact w.r.t. the reference's fp32 arithmetic up to summation
-// order): pre_logits, the KTD / iterative SMPL-parameter regressors and the rotation conversions.
-// These layers are ~0.5 GFLOP per step but feed the outputs directly, without a residual path that would
-// damp rounding error, so they are NOT run on fp16 tensor-core operands.
+// Tail of the hot path: fp32 CUDA-core kernels for the parts that are not GEMM-shaped or too small to matter —
+// the KTD kinematic-tree pass, the iterative regressor's linears (linear_f32) and the rotation conversions.
+// (pre_logits and the KTD fc1 / fc2 / head GEMMs run as split-precision tcgen05 GEMMs from engine.cu; they are never run
+// on plain fp16 operands because they feed the outputs without a damping residual path)
 // References: lib/models/ktd.py:69-124, lib/models/spin.py:51-157, lib/utils/geometry.py:58-223,320-334.
 #include "kernels.h"
 

@@ -49,8 +49,6 @@ static const int kStageDepth[3] = {3, 4, 9};
 static const int kStageOut[3] = {256, 512, 1024};
 static constexpr int kStemKPad = 152;        // 7*7*3 = 147 padded to a multiple of 8 (16-byte TMA rows)
 
-struct ConvSpec { int cin, cout, k, stride, hin, hout; int w_idx; int gn_idx; size_t packed_off; };
-
 struct Engine {
   EngineConfig cfg;
   std::vector<std::string> names;          // reference state_dict keys, in engine order

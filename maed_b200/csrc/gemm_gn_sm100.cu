@@ -3,18 +3,22 @@
 // memory until the GroupNorm statistics of that image are known, so the fp32 conv output never goes to HBM.
 //
 //   item    = (image, channel block of BN output channels); BN is a multiple of the group size C/32
-//   cluster = CS CTAs (1, 4 or 8) share an item; CTA r owns the image's M tiles [r*TPC, (r+1)*TPC), TPC*BN <= 256 columns
-//   Persistent, warp specialised, TMEM double buffered (2 x 256 columns): while the 8 epilogue warps normalise and
-//   store item i from one half, the TMA / MMA warps already accumulate item i+1 into the other half.
-//   main loop : TMA -> smem -> tcgen05.mma (split fp16, 3 MMAs / K step) into TMEM columns half*256 + t*BN
-//   pass 1    : per-group sum / sum of squares of the valid rows (as soon as a tile's MMAs retire)
-//   reduce    : warp shuffles -> smem (CTA) -> every CTA pushes its partials into all peers' shared memory (DSMEM
-//               stores + remote mbarrier arrive); no cluster-wide barrier, so producers never stall on the epilogue
-//   pass 2    : TMEM -> v*a_c + b_c (folded mean/rstd/gamma/beta) (+ shortcut planes) -> ReLU -> fp16 hi/lo ->
-//               per-warp smem transpose -> coalesced 16-byte stores
+//   cluster = CS CTAs (1, 2, 4 or 8) share an item; CTA r owns the image's M tiles [r*TPC, (r+1)*TPC), TPC*BN <= 256 columns
+//   Persistent, warp specialised (384 threads), TMEM double buffered (2 x 256 columns = 2 items in flight):
+//     warp 0      TMA producer (A/B operand stages; also TMA-prefetches the shortcut boxes of the item into L2)
+//     warp 1      MMA issuer (split fp16: 3 tcgen05.mma per K step into TMEM columns half*256 + t*BN)
+//     warps 2, 3  epilogue I/O streams, one per epilogue group: TMA loads of shortcut half-boxes, TMA stores of results
+//     warps 4-7 / 8-11  two epilogue groups; group g owns TMEM half g and the items of parity g
+//   epilogue of an item:
+//     pass 1   per-group sum / sum of squares of the valid rows (as soon as a tile's MMAs retire)
+//     reduce   warp shuffles -> smem (CTA) -> every CTA pushes its partials into all peers' shared memory (DSMEM stores
+//              + remote mbarrier arrive); no cluster-wide barrier, so producers never stall on the epilogue
+//     pass 2   TMEM -> v*a_c + b_c (folded mean/rstd/gamma/beta) (+ shortcut, read from its smem slot) -> ReLU -> fp16
+//              hi/lo written IN PLACE into the slot (64-byte-swizzled half-box) -> mbarrier arrive; the I/O stream
+//              stores the slot with TMA and refills it.  No named barrier, no per-thread global access.
 //
 // Versus the unfused pipeline (GEMM writes fp32, gn_stats reads it, gn_apply reads it again and writes planes)
-// this removes 12 of the 16 bytes of HBM traffic per conv-output element.
+// this removes 12 of the 16 bytes of HBM traffic per conv-output element.  In-kernel timeline: scripts/dbg_gn_timeline.py.
 #include "gemm_host.h"
 #include "kernels.h"
 #include "sm100_ptx.cuh"
@@ -22,7 +26,6 @@
 namespace maed {
 
 static constexpr int kGnThreads = 384;       // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
-static constexpr int kGnEpiThreads = 256;
 static constexpr int kGnMaxTpc = 4;
 static constexpr int kGnMaxStages = 4;
 static constexpr int kGnMaxCluster = 8;

@@ -82,7 +82,8 @@ int attn_generic(const __half* qkv_hi, long long qkv_plane, int batch, int seq, 
                  int tokens_per_frame, int frames_per_batch, float* out_f32, __half* out_hi, long long out_plane,
                  cudaStream_t st);
 
-// ---- tail / decoders (decoder.cu), all fp32 on CUDA cores
+// ---- tail / decoders (decoder.cu): fp32 CUDA-core helpers (the KTD / pre_logits GEMMs themselves run as split-precision
+// tcgen05 GEMMs from engine.cu; linear_f32 serves the iterative regressor and the tests)
 // out[R,N] = act(x[R,K] @ W[N,K]^T + bias) (+ residual);  act: 0 none, 3 tanh
 int linear_f32(const float* x, int ldx, const float* W, int ldw, const float* bias, int R, int N, int K, int act,
                const float* residual, int ldr, float* out, int ldo, cudaStream_t st);
