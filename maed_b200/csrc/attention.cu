@@ -11,6 +11,8 @@
 //    addressing instead of by copies).
 //  * attn_generic_kernel — fp32 CUDA-core flash-style attention over arbitrary sequence length: 'coupling'
 //    mode (T*197 tokens) and the test cross-check of the tensor-core kernel.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "sm100_ptx.cuh"
 
@@ -29,9 +31,14 @@ __device__ __forceinline__ float fast_exp2(float x) {   // one MUFU.EX2 (inputs 
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-static constexpr int kQRows = 256;        // two M=128 query tiles
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+static constexpr int kQRows = 208;        // query rows fetched; the second M=128 tile reads past them into the next buffer
+                                          // (rows >= ntok only feed accumulator rows that are never stored)
 static constexpr int kKvRows = 208;       // keys padded to a multiple of 16 (UMMA N / K granularity)
-static constexpr int kSpThreads = 384;    // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 / 8-11 softmax groups
+static constexpr int kSpThreads = 640;    // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 / 12-19 softmax groups (2 threads per row)
+static constexpr int kColSplit = 112;     // key columns [0,112) -> half 0, [112,208) -> half 1
 
 struct SpatialParams {
   int BT, ntok, heads, nplanes;           // nplanes 2 (split precision) or 1
@@ -40,15 +47,25 @@ struct SpatialParams {
   __half* out_hi;
   long long out_plane;
   int ldo;                                // heads * 64
+  int f32_tma;                            // fp32 output leaves by TMA store (out_f32 only, no planes requested)
+  int direct_store;                       // debug knob (MAED_B200_ATTN_DIRECT=1): per-thread global stores instead of TMA
+  long long* dbg;                         // optional clock64 timeline of CTA 0 ([item][32] slots), MAED_B200_ATTN_DBG=1
 };
+
+#define ATTN_STAMP(slot)                                                                   \
+  do {                                                                                     \
+    if (p.dbg != nullptr && blockIdx.x == 0 && it < 16) p.dbg[it * 32 + (slot)] = clock64(); \
+  } while (0)
 
 __global__ void __launch_bounds__(kSpThreads, 1)
 attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                       const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                        const SpatialParams p) {
   using namespace sm100;
   constexpr uint32_t kQBytes = kQRows * 128;     // per plane
   constexpr uint32_t kKVBytes = kKvRows * 128;   // per plane
   constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kOStage = 128 * 128;        // one plane of one query tile
   constexpr uint32_t kS0 = 0, kS1 = kKvRows, kO = 2 * kKvRows;   // TMEM column map: S0 | S1 | O
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -57,7 +74,8 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + np * kQBytes;
   uint8_t* sV = sK + np * kKVBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + np * kKVBytes);
+  uint8_t* sO = sV + np * kKVBytes;                   // output staging [tile][plane] 128 rows x 128 B, 128-byte swizzle
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 4 * kOStage);
   uint64_t* qk_full = bars + 0;
   uint64_t* v_full = bars + 1;
   uint64_t* qk_empty = bars + 2;
@@ -67,6 +85,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t* o_full = bars + 8;      // [2]
   uint64_t* o_empty = bars + 10;    // [2]
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  float* xch = reinterpret_cast<float*>(bars + 16);   // [tile][half][row]{max, sum} exchanged between the two threads of a row
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,8 +100,8 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
       mbar_init(&o_full[g], 1);
-      mbar_init(&p_full[g], g == 0 ? warps_g0 : max(warps_g1, 1));
-      mbar_init(&o_empty[g], g == 0 ? warps_g0 : max(warps_g1, 1));
+      mbar_init(&p_full[g], 2 * (g == 0 ? warps_g0 : max(warps_g1, 1)));
+      mbar_init(&o_empty[g], 2 * (g == 0 ? warps_g0 : max(warps_g1, 1)));
     }
     fence_barrier_init();
   }
@@ -101,12 +120,14 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int row0 = bt * p.ntok;
         const int ldq = p.heads * kHeadDim;                    // q | k | v column blocks
         mbar_wait(qk_empty, (it & 1) ^ 1);
+        ATTN_STAMP(28);
         mbar_arrive_expect_tx(qk_full, np * (kQBytes + kKVBytes));
         for (int pl = 0; pl < np; ++pl) {
           tma_load_3d(sQ + pl * kQBytes, &tmQ, qk_full, h * kHeadDim, row0, pl);
           tma_load_3d(sK + pl * kKVBytes, &tmKV, qk_full, ldq + h * kHeadDim, row0, pl);
         }
         mbar_wait(v_empty, (it & 1) ^ 1);
+        ATTN_STAMP(29);
         mbar_arrive_expect_tx(v_full, np * kKVBytes);
         for (int pl = 0; pl < np; ++pl)
           tma_load_3d(sV + pl * kKVBytes, &tmKV, v_full, 2 * ldq + h * kHeadDim, row0, pl);
@@ -165,17 +186,25 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const uint32_t ph = it & 1;
           const bool has_next = item + (int)gridDim.x < items;
           mbar_wait(v_full, ph);
+          ATTN_STAMP(0);
           mbar_wait(&p_full[0], ph);
+          ATTN_STAMP(1);
           mbar_wait(&o_empty[1], ph ^ 1);
+          ATTN_STAMP(2);
           tc_fence_after();
           issue_pv(0);
+          ATTN_STAMP(3);
           if (has_next) {
             mbar_wait(qk_full, ph ^ 1);
+            ATTN_STAMP(4);
             tc_fence_after();
             issue_qk(0);
           }
+          ATTN_STAMP(5);
           mbar_wait(&p_full[1], ph);
+          ATTN_STAMP(6);
           mbar_wait(&o_empty[0], ph);
+          ATTN_STAMP(7);
           tc_fence_after();
           issue_pv(1);
           umma_commit(v_empty);
@@ -183,6 +212,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             issue_qk(1);
             umma_commit(qk_empty);
           }
+          ATTN_STAMP(8);
         }
       } else {
         uint32_t it = 0;
@@ -203,52 +233,70 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
   } else if (warp >= 4) {
     // ============================================================ softmax + epilogue warps
-    const int g = (warp - 4) >> 2;                 // query tile
-    const int wq = warp & 3;                       // TMEM lane quarter
+    // Two threads per query row: warps (g, half, wq) — half 0 owns key columns [0,112), half 1 owns [112,208) and,
+    // in the epilogue, output columns [32*half, 32*half+32).  The halves exchange row max and row sum through
+    // shared memory under a 64-thread named barrier, so the softmax and the epilogue each take half as long and
+    // every SM sub-partition has 4 softmax warps to hide TMEM-load / MUFU latency behind.
+    const int g = (warp - 4) >> 3;                 // query tile
+    const int half = ((warp - 4) >> 2) & 1;        // key-column half
+    const int wq = warp & 3;                       // TMEM lane quarter (hardware: warp id % 4)
     const bool active = g == 0 ? (wq < warps_g0) : (wq < warps_g1);
     if (active) {
       const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
       const uint32_t tS = tmem_base + (g ? kS1 : kS0) + lane_off;
       const uint32_t tO = tmem_base + kO + lane_off;
       const int qrow = g * 128 + wq * 32 + lane;   // token index of this thread's query row
+      const int trow = wq * 32 + lane;
+      float* x_mine = xch + ((g * 2 + half) * 128 + trow) * 2;          // {max, sum}
+      const float* x_peer = xch + ((g * 2 + (half ^ 1)) * 128 + trow) * 2;
+      const uint32_t pair_bar = 1 + g * 4 + wq;
+      const int cbeg = half ? kColSplit : 0;
+      const int nbatch = half ? (kKvRows - kColSplit) / 32 : (kColSplit + 31) / 32;   // 3 | 4 (last of half 0: 16 cols)
       uint32_t it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
         const int bt = item / p.heads, h = item % p.heads;
         mbar_wait(&s_full[g], ph);
         tc_fence_after();
-        // Both passes read S in batches of 64 columns (64 + 64 + 64 + 16) with ONE tcgen05.wait::ld per batch: the TMEM
-        // load latency is paid 8 times per tile instead of 26 times.
-        uint32_t r[64];
-#define LD32(i, col) tmem_ld_32x32b_x32(tS + (col), reinterpret_cast<uint32_t(&)[32]>(r[32 * (i)]))
-#define LD16(i, col) tmem_ld_32x32b_x16(tS + (col), reinterpret_cast<uint32_t(&)[16]>(r[32 * (i)]))
-        // pass 1: row max of the raw scores over the valid keys
+#define SM_STAMP(k) do { if (wq == 0 && half == 0 && lane == 0) ATTN_STAMP(10 + 8 * g + (k)); } while (0)
+        SM_STAMP(0);
+        uint32_t r[32];
+        // pass 1: row max of the raw scores over the valid keys of this half
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int b4 = 0; b4 < 4; ++b4) {
-          const int col0 = b4 * 64, ncols = b4 < 3 ? 64 : 16;
-          if (b4 < 3) { LD32(0, col0); LD32(1, col0 + 32); } else { LD16(0, col0); }
+        for (int b = 0; b < nbatch; ++b) {
+          const int col0 = cbeg + b * 32;
+          const int ncols = min(32, (half ? kKvRows : kColSplit) - col0);
+          if (ncols == 32) tmem_ld_32x32b_x32(tS + col0, r);
+          else tmem_ld_32x32b_x16(tS + col0, reinterpret_cast<uint32_t(&)[16]>(r[0]));
           tmem_ld_wait();
-          if (col0 + 64 <= p.ntok) {           // whole batch valid: no per-column predicates
+          if (col0 + 32 <= p.ntok && ncols == 32) {           // whole batch valid: no per-column predicates
 #pragma unroll
-            for (int j = 0; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 64; ++j)
+            for (int j = 0; j < 32; ++j)
               if (j < ncols && col0 + j < p.ntok) mx = fmaxf(mx, __uint_as_float(r[j]));
           }
         }
+        SM_STAMP(1);
+        x_mine[0] = mx;
+        named_bar_sync(pair_bar, 64);
+        SM_STAMP(2);
+        mx = fmaxf(mx, x_peer[0]);
         const float mb = mx * p.scale_log2e;
         // pass 2: p = exp2(s*scale*log2e - max*scale*log2e); P written back in place, per 16 columns: 8 packed hi | 8 packed lo
         float sum = 0.f;
 #pragma unroll 1
-        for (int b4 = 0; b4 < 4; ++b4) {
-          const int col0 = b4 * 64, ncols = b4 < 3 ? 64 : 16;
-          if (b4 < 3) { LD32(0, col0); LD32(1, col0 + 32); } else { LD16(0, col0); }
+        for (int b = 0; b < nbatch; ++b) {
+          const int col0 = cbeg + b * 32;
+          const int ncols = min(32, (half ? kKvRows : kColSplit) - col0);
+          if (ncols == 32) tmem_ld_32x32b_x32(tS + col0, r);
+          else tmem_ld_32x32b_x16(tS + col0, reinterpret_cast<uint32_t(&)[16]>(r[0]));
           tmem_ld_wait();
-          const bool all_valid = col0 + 64 <= p.ntok;
+          const bool all_valid = col0 + 32 <= p.ntok;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             if (c * 16 < ncols) {
               uint32_t pk[16];
 #pragma unroll
@@ -271,42 +319,69 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             }
           }
         }
-#undef LD32
-#undef LD16
+        x_mine[1] = sum;
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
-        // epilogue: O / sum -> global
+        SM_STAMP(3);
+        named_bar_sync(pair_bar, 64);
+        const float inv = 1.0f / (sum + x_peer[1]);
+        // epilogue: O / sum.  O is pulled into registers and released at once (the other tile's P V may start);
+        // the fp16 hi/lo planes go through a swizzled staging tile and leave by TMA store, so the softmax warps
+        // never wait on global-memory back-pressure.
         mbar_wait(&o_full[g], ph);
         tc_fence_after();
-        const float inv = 1.0f / sum;
+        SM_STAMP(4);
         const long long orow = (long long)bt * p.ntok + qrow;
-#pragma unroll 1
-        for (int c = 0; c < kHeadDim / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tO + c * 32, r);
-          tmem_ld_wait();
-          if (qrow < p.ntok) {
-            if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + h * kHeadDim + c * 32);
+        tmem_ld_32x32b_x32(tO + half * 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[g]);
+        SM_STAMP(5);
+        if (p.f32_tma) {
+          // fp32 output: each (tile, half) staging buffer is one 32-float-wide box (128 B rows, 128-byte swizzle)
+          const bool store_thread = wq == 0 && half == 0 && lane == 0;
+          const uint32_t group_threads = 64u * (g == 0 ? warps_g0 : warps_g1);
+          if (store_thread) tma_store_wait_read<0>();          // previous item's tile has left the staging buffers
+          named_bar_sync(9 + 2 * g, group_threads);
+          uint8_t* st_row = sO + (2 * g + half) * kOStage + trow * 128;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                op[j >> 2] = make_float4(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv,
-                                         __uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
-            }
-            if (p.out_hi) {
-              __half* oh = p.out_hi + orow * p.ldo + h * kHeadDim + c * 32;
-              uint32_t hi[16], lo[16];
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(st_row + ((j ^ (trow & 7)) * 16)) =
+                make_float4(__uint_as_float(r[4 * j]) * inv, __uint_as_float(r[4 * j + 1]) * inv,
+                            __uint_as_float(r[4 * j + 2]) * inv, __uint_as_float(r[4 * j + 3]) * inv);
+          fence_proxy_async();
+          named_bar_sync(10 + 2 * g, group_threads);
+          if (store_thread) {
+            const CUtensorMap* tmO = g ? &tmO1 : &tmO0;       // fp32 matrix described as 2x as many 16-bit columns
+            const int row_g = bt * p.ntok + g * 128;
+            tma_store_3d(tmO, sO + (2 * g) * kOStage, 2 * (h * kHeadDim), row_g, 0);
+            tma_store_3d(tmO, sO + (2 * g + 1) * kOStage, 2 * (h * kHeadDim + 32), row_g, 0);
+            tma_store_commit();
+          }
+        } else if (p.out_f32 && qrow < p.ntok) {
+          float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + h * kHeadDim + half * 32);
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const float a = __uint_as_float(r[j]) * inv, b = __uint_as_float(r[j + 1]) * inv;
-                const __half2 h2 = __floats2half2_rn(a, b);
-                const float2 hf = __half22float2(h2);
-                const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
-                hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
-              }
+          for (int j = 0; j < 32; j += 4)
+            op[j >> 2] = make_float4(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv,
+                                     __uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+        }
+        if (p.out_hi) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float a = __uint_as_float(r[j]) * inv, b = __uint_as_float(r[j + 1]) * inv;
+            const __half2 h2 = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+            hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          if (p.direct_store) {
+            if (qrow < p.ntok) {
+              __half* oh = p.out_hi + orow * p.ldo + h * kHeadDim + half * 32;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 reinterpret_cast<uint4*>(oh)[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
@@ -314,12 +389,35 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
               }
             }
+            SM_STAMP(6);
+            continue;
+          }
+          const bool store_thread = wq == 0 && half == 0 && lane == 0;
+          const uint32_t group_threads = 64u * (g == 0 ? warps_g0 : warps_g1);
+          if (store_thread) tma_store_wait_read<0>();          // previous item's tile has left the staging buffer
+          named_bar_sync(9 + 2 * g, group_threads);
+          uint8_t* st_hi = sO + (2 * g) * kOStage + trow * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = ((half * 4 + j) ^ (trow & 7)) * 16;
+            *reinterpret_cast<uint4*>(st_hi + chunk) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            *reinterpret_cast<uint4*>(st_hi + kOStage + chunk) =
+                make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+          fence_proxy_async();
+          named_bar_sync(10 + 2 * g, group_threads);
+          if (store_thread) {
+            const CUtensorMap* tmO = g ? &tmO1 : &tmO0;
+            const int row_g = bt * p.ntok + g * 128;
+            tma_store_3d(tmO, sO + (2 * g) * kOStage, h * kHeadDim, row_g, 0);
+            tma_store_3d(tmO, sO + (2 * g + 1) * kOStage, h * kHeadDim, row_g, 1);
+            tma_store_commit();
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_empty[g]);
+        SM_STAMP(6);
+#undef SM_STAMP
       }
+      if (wq == 0 && half == 0 && lane == 0) tma_store_wait_all();
     }
   }
 
@@ -342,11 +440,40 @@ int attn_spatial(const __half* qkv_hi, long long qkv_plane, int BT, int ntok, in
   const uint32_t boxkv[3] = {64, kKvRows, 1};
   MAED_PROPAGATE(make_tmap_f16(&tmQ, qkv_hi, 3, dims, str, boxq));
   MAED_PROPAGATE(make_tmap_f16(&tmKV, qkv_hi, 3, dims, str, boxkv));
+  // output planes leave by TMA store: one box per query tile (tile 1 holds only ntok - 128 rows of the frame)
+  CUtensorMap tmO0 = tmKV, tmO1 = tmKV;
+  if (out_hi) {
+    MAED_CHECK_ARG(out_plane >= rows * heads * kHeadDim && (out_plane % 8) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out_hi) & 15) == 0,
+                   "attn_spatial: output planes must be 16-byte aligned and at least rows*heads*64 apart");
+    const uint64_t odims[3] = {(uint64_t)heads * kHeadDim, (uint64_t)rows, 2};
+    const uint64_t ostr[2] = {(uint64_t)heads * kHeadDim * 2, (uint64_t)out_plane * 2};
+    const uint32_t box0[3] = {64, (uint32_t)(ntok < 128 ? ntok : 128), 1};
+    MAED_PROPAGATE(make_tmap_f16(&tmO0, out_hi, 3, odims, ostr, box0));
+    if (ntok > 128) {
+      const uint32_t box1[3] = {64, (uint32_t)(ntok - 128), 1};
+      MAED_PROPAGATE(make_tmap_f16(&tmO1, out_hi, 3, odims, ostr, box1));
+    }
+  }
+  static const bool f32_tma_on = getenv("MAED_B200_ATTN_DIRECT") == nullptr;   // debug knob: per-thread global stores
+  const bool f32_tma = f32_tma_on && out_f32 && !out_hi && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0;
+  if (f32_tma) {
+    const uint64_t odims[3] = {(uint64_t)heads * kHeadDim * 2, (uint64_t)rows, 1};
+    const uint64_t ostr[2] = {(uint64_t)heads * kHeadDim * 4, (uint64_t)rows * heads * kHeadDim * 4};
+    const uint32_t box0[3] = {64, (uint32_t)(ntok < 128 ? ntok : 128), 1};
+    MAED_PROPAGATE(make_tmap_f16(&tmO0, out_f32, 3, odims, ostr, box0));
+    if (ntok > 128) {
+      const uint32_t box1[3] = {64, (uint32_t)(ntok - 128), 1};
+      MAED_PROPAGATE(make_tmap_f16(&tmO1, out_f32, 3, odims, ostr, box1));
+    }
+  }
   SpatialParams p;
+  p.f32_tma = f32_tma ? 1 : 0;
   p.BT = BT; p.ntok = ntok; p.heads = heads; p.nplanes = np;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out_f32 = out_f32; p.out_hi = out_hi; p.out_plane = out_plane; p.ldo = heads * kHeadDim;
-  const size_t smem = 1024 + (size_t)np * (kQRows * 128 + 2 * kKvRows * 128) + 256;
+  const size_t smem = 1024 + (size_t)np * (kQRows * 128 + 2 * kKvRows * 128) + 4 * 128 * 128 + 256 +
+                      2 * 2 * 128 * 2 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     MAED_CUDA_CHECK(cudaFuncSetAttribute(attn_spatial_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -354,8 +481,30 @@ int attn_spatial(const __half* qkv_hi, long long qkv_plane, int BT, int ntok, in
   }
   const int items = BT * heads;
   const int grid = items < sm_count() ? items : sm_count();
-  attn_spatial_tc_kernel<<<grid, kSpThreads, smem, st>>>(tmQ, tmKV, p);
+  static const bool direct = getenv("MAED_B200_ATTN_DIRECT") != nullptr;
+  p.direct_store = direct ? 1 : 0;
+  static const bool dbg_on = getenv("MAED_B200_ATTN_DBG") != nullptr;
+  static long long* dbg_buf = nullptr;
+  p.dbg = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) MAED_CUDA_CHECK(cudaMalloc(&dbg_buf, 16 * 32 * sizeof(long long)));
+    MAED_CUDA_CHECK(cudaMemsetAsync(dbg_buf, 0, 16 * 32 * sizeof(long long), st));
+    p.dbg = dbg_buf;
+  }
+  attn_spatial_tc_kernel<<<grid, kSpThreads, smem, st>>>(tmQ, tmKV, tmO0, tmO1, p);
   LAUNCH_CHECK();
+  if (dbg_on) {   // debug only: per-item event times of CTA 0, cycles relative to the first stamp
+    static long long h[16 * 32];
+    MAED_CUDA_CHECK(cudaStreamSynchronize(st));
+    MAED_CUDA_CHECK(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    long long t0 = 0;
+    for (int i = 0; i < 16 * 32; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
+    for (int i = 0; i < 16; ++i) {
+      fprintf(stderr, "ATTN_DBG item %2d:", i);
+      for (int sl = 0; sl < 32; ++sl) fprintf(stderr, " %lld", h[i * 32 + sl] ? h[i * 32 + sl] - t0 : -1LL);
+      fprintf(stderr, "\n");
+    }
+  }
   return MAED_OK;
 }
 

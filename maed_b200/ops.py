@@ -136,11 +136,17 @@ def layernorm(x, gamma, beta, eps=1e-6):
     return out
 
 
-def attention(kind, qkv, B, T, ntok, heads, scale, nsplit=3):
-    """qkv: planes (2, B*T*ntok, 3*heads*64) -> fp32 (B*T*ntok, heads*64).  kind: 'spatial'|'temporal'|'generic'."""
+def attention(kind, qkv, B, T, ntok, heads, scale, nsplit=3, planes=False):
+    """qkv: planes (2, B*T*ntok, 3*heads*64) -> fp32 (B*T*ntok, heads*64), or with `planes=True` the fp16 hi/lo
+    planes (2, rows, heads*64) the engine consumes.  kind: 'spatial'|'temporal'|'generic'."""
     rows = qkv.shape[1]
-    out = torch.empty(rows, heads * 64, dtype=torch.float32, device=qkv.device)
     k = {"spatial": 0, "temporal": 1, "generic": 2}[kind]
+    if planes:
+        out = torch.empty(2, rows, heads * 64, dtype=torch.float16, device=qkv.device)
+        call("maed_op_attention", k, ptr(qkv), plane_stride(qkv), B, T, ntok, heads, C.c_float(scale), nsplit, None, ptr(out),
+             plane_stride(out), stream_ptr())
+        return out
+    out = torch.empty(rows, heads * 64, dtype=torch.float32, device=qkv.device)
     call("maed_op_attention", k, ptr(qkv), plane_stride(qkv), B, T, ntok, heads, C.c_float(scale), nsplit, ptr(out), None, 0,
          stream_ptr())
     return out

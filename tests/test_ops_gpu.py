@@ -209,6 +209,18 @@ def test_attention(ops, kind, B, T, ntok):
     assert rel_err(out, ref) < 5e-6, kind
 
 
+@pytest.mark.parametrize("kind,B,T,ntok", [("spatial", 3, 4, 197), ("spatial", 20, 8, 197), ("spatial", 1, 3, 128),
+                                           ("spatial", 2, 2, 60), ("spatial", 1, 2, 129), ("temporal", 2, 16, 197)])
+def test_attention_plane_output(ops, kind, B, T, ntok):
+    """The fp16 hi/lo plane output (what the engine consumes; the spatial kernel writes it by TMA store)."""
+    heads = 12
+    qkv = _rand(B * T * ntok, 3 * heads * 64, scale=1.5, seed=32)
+    out = ops.attention(kind, ops.split(qkv), B, T, ntok, heads, 0.125, planes=True)
+    ref = _ref_attention(qkv, B, T, ntok, heads, 0.125, kind)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out[0].double() + out[1].double(), ref) < 5e-6, kind
+
+
 def test_attention_spatial_plain_fp16(ops):
     B, T, ntok, heads = 2, 2, 197, 12
     qkv = _rand(B * T * ntok, 3 * heads * 64, scale=1.0, seed=26)
