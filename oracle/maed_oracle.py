@@ -327,3 +327,20 @@ def maed_forward(x, sd, st_mode="parallel", decoder="ktd", num_blocks=6, num_hea
         "kp_2d": out["kp_2d"].reshape(N, T, -1, 2), "kp_3d": out["kp_3d"].reshape(N, T, -1, 3),
         "rotmat": out["rotmat"].reshape(N, T, -1, 3, 3),
     }
+
+
+# --------------------------------------------------------------------------------------------------
+# gradients (training-path oracle): autograd over the restatement above
+# --------------------------------------------------------------------------------------------------
+def maed_param_grads(x, sd, probe_pose, probe_shape, probe_cam, st_mode="parallel", decoder="ktd", num_blocks=6,
+                     num_heads=12):
+    """dL/dp for every entry of `sd` with L = sum(pose6d*A) + sum(shape*B) + sum(cam*C) — the scalar
+    tests/golden/make_golden_grads.py back-propagates through the reference (eval mode: no dropout).
+    Returns (L, {key: grad}, {pose6d, shape, cam})."""
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    taps = {}
+    maed_forward(x, sd, st_mode, decoder, num_blocks, num_heads, taps=taps)
+    L = (taps["pose6d"] * probe_pose).sum() + (taps["shape"] * probe_shape).sum() + (taps["cam"] * probe_cam).sum()
+    keys = [k for k, v in sd.items() if v.requires_grad]
+    grads = torch.autograd.grad(L, [sd[k] for k in keys], allow_unused=True)
+    return L.detach(), {k: g for k, g in zip(keys, grads) if g is not None}, {k: taps[k].detach() for k in ("pose6d", "shape", "cam")}

@@ -34,3 +34,10 @@ def state_dict_of(model):
     sd = {k: v.detach() for k, v in model.named_parameters()}
     sd.update({k: v.detach() for k, v in model.named_buffers()})
     return sd
+
+
+def reference_shapes(mode, decoder):
+    """{state_dict key: shape} of the reference model for (st_mode, decoder), from tests/golden/state_dict_keys.json."""
+    import json
+    spec = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_keys.json")))
+    return {k: tuple(v) for k, v in spec["%s/%s" % (mode, decoder)].items() if "smpl" not in k}
