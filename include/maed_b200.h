@@ -130,6 +130,74 @@ int maed_engine_forward(const maed_engine* e, const void* const* params, const v
                         int T, void* workspace, size_t workspace_bytes, const maed_outputs* outs,
                         float* const* taps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training path (maed_b200/csrc/train.cu): forward with a saved-activation tape + backward to every parameter.
+ * Replaces `loss.backward()` through lib/models/maed.py:52-66 (reference lib/core/trainer.py:238-255); the boundary
+ * is the decoder output pose6d / shape / cam (the geometry tail behind it stays under autograd).
+ * Supported: st_mode parallel / series / vanilla, KTD decoder, split precision.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct maed_train_outputs {
+  float* feat;    /* [N*T, 768] or NULL */
+  float* pose6d;  /* [N*T, 144] */
+  float* shape;   /* [N*T, 10] */
+  float* cam;     /* [N*T, 3] */
+} maed_train_outputs;
+size_t maed_train_pack_bytes(const maed_engine* e);
+size_t maed_train_workspace_bytes(const maed_engine* e, int n_frames);
+/* derived weights of the data-gradient GEMMs; redo after every parameter update (like maed_engine_pack) */
+int maed_train_pack(const maed_engine* e, const void* const* params, void* tpack, void* stream);
+/* dropout_p = 0: the reference in eval() mode (parity configuration); > 0: KTD dropout (ktd.py:54-56) */
+int maed_train_forward(const maed_engine* e, const void* const* params, const void* packed, const float* x, int N, int T,
+                       void* workspace, size_t workspace_bytes, float dropout_p, unsigned long long seed,
+                       const maed_train_outputs* outs, void* stream);
+/* grads[i]: fp32 [maed_engine_param_numel(e, i)], overwritten with dL/dparam_i.  workspace: the one the matching
+ * maed_train_forward call filled.  loss_scale multiplies the activation gradients internally (fp16 range). */
+int maed_train_backward(const maed_engine* e, const void* const* params, const void* packed, const void* tpack,
+                        const float* x, int N, int T, void* workspace, size_t workspace_bytes, const float* d_pose6d,
+                        const float* d_shape, const float* d_cam, float loss_scale, float dropout_p, float* const* grads,
+                        void* stream);
+/* torch.optim.Adam step on flat fp32 buffers (reference lib/utils/utils.py:127-131); g is multiplied by grad_scale */
+int maed_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, float grad_scale, void* stream);
+
+/* per-op entry points of the backward kernels (unit tests; semantics in maed_b200/csrc/bwd_kernels.h) */
+int maed_bwd_transpose_planes(const void* in_hi, long long in_plane, int R, int C, int ld_in, void* out_hi, long long out_plane,
+                              int ld_out, void* stream);
+int maed_bwd_colsum(const float* in, long long ld, int R, int C, float scale, int accumulate, float* scratch, float* out,
+                    void* stream);
+int maed_bwd_layernorm(const float* dy, long long dy_stride, const float* x, long long x_stride, const float* gamma, int rows,
+                       int C, float eps, const float* dx_add, float* dx_out, long long dx_stride, float* partial,
+                       float* scratch, float* dgamma, float* dbeta, void* stream);
+int maed_bwd_layernorm_partial_rows(void);
+int maed_bwd_groupnorm(const float* dy, const float* x, int n_img, int HW, int C, const float* gamma, float eps,
+                       double* stats_scratch, float* red, float* dgb_partial, void* dx_hi, long long dx_plane, void* stream);
+int maed_bwd_wstd(const float* g, int k_pad, const float* w, int Cout, int Cin, int KH, int KW, float eps, float scale, float* dw,
+                  void* stream);
+int maed_bwd_gelu(const float* d_hid, const float* pre, long long n, void* out_hi, long long out_plane, void* stream);
+int maed_bwd_relu_mask(float* d, const void* act_hi, long long n, void* stream);
+int maed_bwd_maxpool(const float* x, int n_img, int H, int W, int C, const float* gamma, const float* beta, float eps,
+                     double* stats_scratch, void* out_hi, long long out_plane, unsigned char* idx, const float* d_pool,
+                     float* d_y, void* stream);
+int maed_bwd_dilate2(const void* in_hi, long long in_plane, int n_img, int OH, int OW, int C, int H, int W, void* out_hi,
+                     long long out_plane, void* stream);
+int maed_bwd_scatter_stride2(const float* src, int n_img, int OH, int OW, int C, int H, int W, const float* add, float* d_in,
+                             void* stream);
+int maed_bwd_blend(const float* d_ao, const float* x_s, const float* x_t, const float* logits, const float* d_pool, int BT,
+                   int ntok, int C, float* d_logits, float* d_xs, float* d_xt, void* stream);
+int maed_bwd_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+                   float beta, float* C, int ldc, void* stream);
+int maed_bwd_ktd_tree(const float* d_pose6d, const float* d_shape, const float* d_cam, const float* w_anc, const float* pose6d,
+                      int R, float scale, float* g_total, float* d_base, int ld, float* d_w_anc, void* stream);
+int maed_bwd_attention(int kind, const void* qkv_hi, long long qkv_plane, const float* d_out, int B, int T, int ntok, int heads,
+                       float scale, int accumulate, float* d_qkv, void* stream);
+size_t maed_bwd_wgrad_slab_floats(int Mo, int No, int R);
+int maed_bwd_wgrad_splitk(const void* A, long long a_plane, int lda, const void* B, long long b_plane, int ldb, int Mo, int No,
+                          int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, void* stream);
+int maed_bwd_split_transposed(const float* w, int N, int K, void* out_hi, long long plane, void* stream);
+int maed_bwd_prep_conv_weight_dgrad(const float* w, int Cout, int Cin, int KH, int KW, int standardize, void* out_hi,
+                                    long long plane, void* stream);
+int maed_bwd_dropout(float* x, long long n, float p, unsigned long long seed, unsigned char* mask, float* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

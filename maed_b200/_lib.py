@@ -28,6 +28,11 @@ class MaedOutputs(C.Structure):
                 ("kp2d", _P), ("kp3d", _P), ("n_joints", _I)]
 
 
+class MaedTrainOutputs(C.Structure):
+    _fields_ = [("feat", _P), ("pose6d", _P), ("shape", _P), ("cam", _P)]
+
+
+_U = C.c_ulonglong
 MODES = {"vanilla": 0, "parallel": 1, "series": 2, "coupling": 3, "temporal": 4}
 DECODERS = {"ktd": 0, "iterative": 1}
 TAP_NAMES = ["stem", "stage0", "stage1", "stage2", "embed"] + ["block%d" % i for i in range(8)]
@@ -60,6 +65,33 @@ SIGNATURES = {
     "maed_engine_workspace_bytes": (_Z, [_P, _I]),
     "maed_engine_pack": (_I, [_P, c_void_pp, _P, _P]),
     "maed_engine_forward": (_I, [_P, c_void_pp, _P, _P, _I, _I, _P, _Z, C.POINTER(MaedOutputs), c_void_pp, _P]),
+    # ---- training path
+    "maed_train_pack_bytes": (_Z, [_P]),
+    "maed_train_workspace_bytes": (_Z, [_P, _I]),
+    "maed_train_pack": (_I, [_P, c_void_pp, _P, _P]),
+    "maed_train_forward": (_I, [_P, c_void_pp, _P, _P, _I, _I, _P, _Z, _F, _U, C.POINTER(MaedTrainOutputs), _P]),
+    "maed_train_backward": (_I, [_P, c_void_pp, _P, _P, _P, _I, _I, _P, _Z, _P, _P, _P, _F, _F, c_void_pp, _P]),
+    "maed_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "maed_bwd_transpose_planes": (_I, [_P, _L, _I, _I, _I, _P, _L, _I, _P]),
+    "maed_bwd_colsum": (_I, [_P, _L, _I, _I, _F, _I, _P, _P, _P]),
+    "maed_bwd_layernorm": (_I, [_P, _L, _P, _L, _P, _I, _I, _F, _P, _P, _L, _P, _P, _P, _P, _P]),
+    "maed_bwd_layernorm_partial_rows": (_I, []),
+    "maed_bwd_groupnorm": (_I, [_P, _P, _I, _I, _I, _P, _F, _P, _P, _P, _P, _L, _P]),
+    "maed_bwd_wstd": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _F, _P, _P]),
+    "maed_bwd_gelu": (_I, [_P, _P, _L, _P, _L, _P]),
+    "maed_bwd_relu_mask": (_I, [_P, _P, _L, _P]),
+    "maed_bwd_maxpool": (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _L, _P, _P, _P, _P]),
+    "maed_bwd_dilate2": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "maed_bwd_scatter_stride2": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "maed_bwd_blend": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "maed_bwd_sgemm": (_I, [_I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P]),
+    "maed_bwd_ktd_tree": (_I, [_P, _P, _P, _P, _P, _I, _F, _P, _P, _I, _P, _P]),
+    "maed_bwd_attention": (_I, [_I, _P, _L, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
+    "maed_bwd_wgrad_slab_floats": (_Z, [_I, _I, _I]),
+    "maed_bwd_wgrad_splitk": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _F, _I, _P, _P, _I, _P]),
+    "maed_bwd_split_transposed": (_I, [_P, _I, _I, _P, _L, _P]),
+    "maed_bwd_prep_conv_weight_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "maed_bwd_dropout": (_I, [_P, _L, _F, _U, _P, _P, _P]),
 }
 
 _lib = None

@@ -6,7 +6,9 @@
 #include "common.h"
 #include "gemm_host.h"
 #include "engine.h"
+#include "bwd_kernels.h"
 #include "kernels.h"
+#include "train.h"
 
 using namespace maed;
 
@@ -137,6 +139,131 @@ int maed_engine_forward(const maed_engine* e, const void* const* params, const v
                         void* workspace, size_t workspace_bytes, const maed_outputs* outs, float* const* taps, void* stream) {
   return engine_forward(reinterpret_cast<const Engine*>(e), params, packed, x, N, T, workspace, workspace_bytes,
                         reinterpret_cast<const EngineOutputs*>(outs), taps, (cudaStream_t)stream);
+}
+
+// ---- training path
+static_assert(sizeof(maed_train_outputs) == sizeof(TrainOutputs), "maed_train_outputs must mirror TrainOutputs");
+size_t maed_train_pack_bytes(const maed_engine* e) { return train_pack_bytes(reinterpret_cast<const Engine*>(e)); }
+size_t maed_train_workspace_bytes(const maed_engine* e, int n_frames) {
+  return train_workspace_bytes(reinterpret_cast<const Engine*>(e), n_frames);
+}
+int maed_train_pack(const maed_engine* e, const void* const* params, void* tpack, void* stream) {
+  return train_pack(reinterpret_cast<const Engine*>(e), params, tpack, (cudaStream_t)stream);
+}
+int maed_train_forward(const maed_engine* e, const void* const* params, const void* packed, const float* x, int N, int T,
+                       void* workspace, size_t workspace_bytes, float dropout_p, unsigned long long seed,
+                       const maed_train_outputs* outs, void* stream) {
+  return train_forward(reinterpret_cast<const Engine*>(e), params, packed, x, N, T, workspace, workspace_bytes, dropout_p, seed,
+                       reinterpret_cast<const TrainOutputs*>(outs), (cudaStream_t)stream);
+}
+int maed_train_backward(const maed_engine* e, const void* const* params, const void* packed, const void* tpack,
+                        const float* x, int N, int T, void* workspace, size_t workspace_bytes, const float* d_pose6d,
+                        const float* d_shape, const float* d_cam, float loss_scale, float dropout_p, float* const* grads,
+                        void* stream) {
+  return train_backward(reinterpret_cast<const Engine*>(e), params, packed, tpack, x, N, T, workspace, workspace_bytes, d_pose6d,
+                        d_shape, d_cam, loss_scale, dropout_p, grads, (cudaStream_t)stream);
+}
+int maed_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, float grad_scale, void* stream) {
+  return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream);
+}
+
+// ---- per-op backward entry points (unit tests)
+int maed_bwd_transpose_planes(const void* in_hi, long long in_plane, int R, int C, int ld_in, void* out_hi, long long out_plane,
+                              int ld_out, void* stream) {
+  return transpose_planes((const __half*)in_hi, in_plane, R, C, ld_in, (__half*)out_hi, out_plane, ld_out, (cudaStream_t)stream);
+}
+int maed_bwd_colsum(const float* in, long long ld, int R, int C, float scale, int accumulate, float* scratch, float* out,
+                    void* stream) {
+  return colsum_f32(in, ld, R, C, scale, accumulate, scratch, out, (cudaStream_t)stream);
+}
+int maed_bwd_layernorm_partial_rows(void) { return ln_bwd_partial_rows(); }
+int maed_bwd_layernorm(const float* dy, long long dy_stride, const float* x, long long x_stride, const float* gamma, int rows,
+                       int C, float eps, const float* dx_add, float* dx_out, long long dx_stride, float* partial,
+                       float* scratch, float* dgamma, float* dbeta, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_PROPAGATE(layernorm_bwd(dy, dy_stride, x, x_stride, gamma, rows, C, eps, dx_add, dx_out, dx_stride, partial, st));
+  const int pr = ln_bwd_partial_rows();
+  MAED_PROPAGATE(colsum_f32(partial, 2 * C, pr, C, 1.f, 0, scratch, dgamma, st));
+  return colsum_f32(partial + C, 2 * C, pr, C, 1.f, 0, scratch, dbeta, st);
+}
+int maed_bwd_groupnorm(const float* dy, const float* x, int n_img, int HW, int C, const float* gamma, float eps,
+                       double* stats_scratch, float* red, float* dgb_partial, void* dx_hi, long long dx_plane, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_CUDA_CHECK(cudaMemsetAsync(stats_scratch, 0, (size_t)n_img * 64 * sizeof(double), st));
+  MAED_PROPAGATE(gn_stats(x, n_img, HW, C, stats_scratch, st));
+  return groupnorm_bwd(dy, x, stats_scratch, gamma, n_img, HW, C, eps, red, dgb_partial, (__half*)dx_hi, dx_plane, st);
+}
+int maed_bwd_wstd(const float* g, int k_pad, const float* w, int Cout, int Cin, int KH, int KW, float eps, float scale, float* dw,
+                  void* stream) {
+  return wstd_bwd(g, k_pad, w, Cout, Cin, KH, KW, eps, scale, dw, (cudaStream_t)stream);
+}
+int maed_bwd_gelu(const float* d_hid, const float* pre, long long n, void* out_hi, long long out_plane, void* stream) {
+  return gelu_bwd(d_hid, pre, n, (__half*)out_hi, out_plane, (cudaStream_t)stream);
+}
+int maed_bwd_relu_mask(float* d, const void* act_hi, long long n, void* stream) {
+  return relu_mask_f32(d, (const __half*)act_hi, n, (cudaStream_t)stream);
+}
+int maed_bwd_maxpool(const float* x, int n_img, int H, int W, int C, const float* gamma, const float* beta, float eps,
+                     double* stats_scratch, void* out_hi, long long out_plane, unsigned char* idx, const float* d_pool,
+                     float* d_y, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_CUDA_CHECK(cudaMemsetAsync(stats_scratch, 0, (size_t)n_img * 64 * sizeof(double), st));
+  MAED_PROPAGATE(gn_stats(x, n_img, H * W, C, stats_scratch, st));
+  MAED_PROPAGATE(gn_apply_maxpool_idx(x, stats_scratch, gamma, beta, n_img, H, W, C, eps, (__half*)out_hi, out_plane, idx, st));
+  return maxpool_gn_relu_bwd(d_pool, idx, x, stats_scratch, gamma, beta, n_img, H, W, C, eps, d_y, st);
+}
+int maed_bwd_dilate2(const void* in_hi, long long in_plane, int n_img, int OH, int OW, int C, int H, int W, void* out_hi,
+                     long long out_plane, void* stream) {
+  return dilate2_planes((const __half*)in_hi, in_plane, n_img, OH, OW, C, H, W, (__half*)out_hi, out_plane, (cudaStream_t)stream);
+}
+int maed_bwd_scatter_stride2(const float* src, int n_img, int OH, int OW, int C, int H, int W, const float* add, float* d_in,
+                             void* stream) {
+  return scatter_stride2_f32(src, n_img, OH, OW, C, H, W, add, d_in, (cudaStream_t)stream);
+}
+int maed_bwd_blend(const float* d_ao, const float* x_s, const float* x_t, const float* logits, const float* d_pool, int BT,
+                   int ntok, int C, float* d_logits, float* d_xs, float* d_xt, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_PROPAGATE(blend_bwd(d_ao, x_s, x_t, logits, BT, ntok, C, d_logits, d_xs, d_xt, st));
+  if (d_pool) return blend_bwd_pool(d_pool, BT, ntok, C, d_xs, d_xt, st);
+  return MAED_OK;
+}
+int maed_bwd_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+                   float beta, float* C, int ldc, void* stream) {
+  return sgemm_f32(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, (cudaStream_t)stream);
+}
+int maed_bwd_ktd_tree(const float* d_pose6d, const float* d_shape, const float* d_cam, const float* w_anc, const float* pose6d,
+                      int R, float scale, float* g_total, float* d_base, int ld, float* d_w_anc, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_PROPAGATE(ktd_tree_bwd(d_pose6d, d_shape, d_cam, w_anc, R, g_total, d_base, ld, st));
+  return ktd_anc_wgrad(g_total, pose6d, R, scale, d_w_anc, st);
+}
+int maed_bwd_attention(int kind, const void* qkv_hi, long long qkv_plane, const float* d_out, int B, int T, int ntok, int heads,
+                       float scale, int accumulate, float* d_qkv, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kind == 0) return attn_spatial_bwd((const __half*)qkv_hi, qkv_plane, d_out, B * T, ntok, heads, scale, accumulate, d_qkv, st);
+  if (kind == 1) return attn_temporal_bwd((const __half*)qkv_hi, qkv_plane, d_out, B, T, ntok, heads, scale, accumulate, d_qkv, st);
+  set_error("maed_bwd_attention: unknown kind %d", kind);
+  return MAED_ERR_ARG;
+}
+size_t maed_bwd_wgrad_slab_floats(int Mo, int No, int R) { return splitk_slab_floats(Mo, No, R); }
+int maed_bwd_wgrad_splitk(const void* A, long long a_plane, int lda, const void* B, long long b_plane, int ldb, int Mo, int No,
+                          int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, void* stream) {
+  return gemm_wgrad_splitk((const __half*)A, a_plane, lda, (const __half*)B, b_plane, ldb, Mo, No, R, nsplit, scale, accumulate,
+                           slabs, D, ldd, (cudaStream_t)stream);
+}
+int maed_bwd_split_transposed(const float* w, int N, int K, void* out_hi, long long plane, void* stream) {
+  return split_f32_transposed(w, N, K, (__half*)out_hi, plane, (cudaStream_t)stream);
+}
+int maed_bwd_prep_conv_weight_dgrad(const float* w, int Cout, int Cin, int KH, int KW, int standardize, void* out_hi,
+                                    long long plane, void* stream) {
+  return prep_conv_weight_dgrad(w, Cout, Cin, KH, KW, standardize, (__half*)out_hi, plane, (cudaStream_t)stream);
+}
+int maed_bwd_dropout(float* x, long long n, float p, unsigned long long seed, unsigned char* mask, float* d, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_PROPAGATE(dropout_fwd(x, n, p, seed, mask, st));
+  if (d) return dropout_bwd(d, n, p, mask, st);
+  return MAED_OK;
 }
 
 }  // extern "C"

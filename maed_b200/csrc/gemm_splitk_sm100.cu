@@ -1,0 +1,261 @@
+// Split-K tcgen05 GEMM for the weight gradients of the MAED training path.
+//
+//   D[Mo, No] (+)= scale * sum_r A[Mo, r] * B[No, r]          A = dY^T, B = X^T (planes, r contiguous)
+//
+// The reduction dimension r is the number of activation rows (25 216 tokens ... 1.6 M stem pixels) while Mo x No is a
+// weight matrix of at most a few hundred tiles, so the K loop is cut into `S` slices: tile index = (slice, m, n), every
+// CTA accumulates its slice in TMEM and writes an fp32 slab; splitk_reduce_kernel sums the slabs in a fixed order
+// (deterministic, no atomics).  Same pipeline as gemm_sm100.cuh (TMA producer warp, single-thread MMA issuer,
+// double-buffered TMEM accumulators, 4 epilogue warps, split-precision 3-MMA scheme); kept as a separate kernel so the
+// validated forward GEMM is untouched.
+#include "bwd_kernels.h"
+
+#include "device_utils.cuh"
+#include "gemm_host.h"
+#include "sm100_ptx.cuh"
+
+namespace maed {
+
+namespace {
+
+struct SplitKParams {
+  int M, N;                    // output rows / cols (Mo, No)
+  int num_k_blocks;            // ceil(R / 64)
+  int kb_per_slice, slices;
+  int nsplit, stages;
+  int m_tiles, n_tiles;
+  float* slabs;                // [slices][M][N]
+};
+
+constexpr int kBM = 128, kBK = 64, kThreads = 256, kStagesMax = 8;
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SplitKParams p) {
+  using namespace sm100;
+  constexpr int kAccStages = (2 * BLOCK_N <= 512) ? 2 : 1;
+  constexpr int kTmemCols = (kAccStages * BLOCK_N <= 32) ? 32 : (kAccStages * BLOCK_N <= 64) ? 64
+                          : (kAccStages * BLOCK_N <= 128) ? 128 : (kAccStages * BLOCK_N <= 256) ? 256 : 512;
+  constexpr uint32_t kABytes = kBM * kBK * 2;
+  constexpr uint32_t kBBytes = BLOCK_N * kBK * 2;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int nplanes = (p.nsplit == 3) ? 2 : 1;
+  const uint32_t stage_bytes = nplanes * (kABytes + kBBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStagesMax;
+  uint64_t* tmem_full = bars + 2 * kStagesMax;
+  uint64_t* tmem_empty = bars + 2 * kStagesMax + 2;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStagesMax + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int num_tiles = tiles_mn * p.slices;
+
+  if (warp == 0 && elect_one()) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < kAccStages; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_base_ptr, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int slice = tile / tiles_mn, mn = tile % tiles_mn;
+        const int m_tile = mn / p.n_tiles, n_tile = mn % p.n_tiles;
+        const int kb0 = slice * p.kb_per_slice;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_slice);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + (size_t)stage * stage_bytes;
+          uint8_t* sB = sA + nplanes * kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], nplanes * (kABytes + kBBytes));
+          for (int pl = 0; pl < nplanes; ++pl) {
+            tma_load_3d(sA + pl * kABytes, &tmA, &full_bar[stage], kb * kBK, m_tile * kBM, pl);
+            tma_load_3d(sB + pl * kBBytes, &tmB, &full_bar[stage], kb * kBK, n_tile * BLOCK_N, pl);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBM, BLOCK_N, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int slice = tile / tiles_mn;
+        const int kb0 = slice * p.kb_per_slice;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_slice);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t aH = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t bH = aH + nplanes * kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = umma_desc_k_sw128(aH + k * 32);
+            const uint64_t db = umma_desc_k_sw128(bH + k * 32);
+            umma_f16(d_tmem, da, db, idesc, (kb != kb0) || (k != 0));
+            if (p.nsplit == 3) {
+              const uint64_t dal = umma_desc_k_sw128(aH + kABytes + k * 32);
+              const uint64_t dbl = umma_desc_k_sw128(bH + kBBytes + k * 32);
+              umma_f16(d_tmem, dal, db, idesc, 1);
+              umma_f16(d_tmem, da, dbl, idesc, 1);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp & 3;
+    const int row_in_tile = ew * 32 + lane_id();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int slice = tile / tiles_mn, mn = tile % tiles_mn;
+      const int m_tile = mn / p.n_tiles, n_tile = mn % p.n_tiles;
+      const long long out_row = (long long)m_tile * kBM + row_in_tile;
+      const bool row_ok = out_row < p.M;
+      float* slab = p.slabs + (long long)slice * p.M * p.N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c0, r);
+        tmem_ld_wait();
+        const int col0 = n_tile * BLOCK_N + c0;
+        if (row_ok && col0 < p.N) {                        // N is a multiple of 32
+          float4* op = reinterpret_cast<float4*>(slab + out_row * p.N + col0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            op[j >> 2] = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ slabs, int slices, long long mn, int N, float scale,
+                                     int accumulate, float* __restrict__ D, int ldd) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < mn; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < slices; ++k) s += slabs[(long long)k * mn + i];
+    float* d = D + (i / N) * ldd + (i % N);
+    *d = (accumulate ? *d : 0.f) + scale * s;
+  }
+}
+
+struct SliceChoice { int block_n, m_tiles, n_tiles, nkb, kb_per, slices; };
+SliceChoice choose_slices(int Mo, int No, int R) {
+  SliceChoice c;
+  c.block_n = (No % 256 == 0) ? 256 : (No % 128 == 0) ? 128 : 64;
+  c.m_tiles = cdiv(Mo, kBM);
+  c.n_tiles = cdiv(No, c.block_n);
+  c.nkb = cdiv(R, kBK);
+  const int tiles = c.m_tiles * c.n_tiles;
+  int s = (2 * sm_count() + tiles - 1) / tiles;
+  if (s > 64) s = 64;
+  if (s > c.nkb) s = c.nkb;
+  if (s < 1) s = 1;
+  c.kb_per = cdiv(c.nkb, s);
+  c.slices = cdiv(c.nkb, c.kb_per);
+  return c;
+}
+
+template <int BN>
+int launch_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, const SplitKParams& p, int grid, size_t smem,
+                  cudaStream_t st) {
+  static size_t attr = 0;
+  if (smem > attr) {
+    MAED_CUDA_CHECK(cudaFuncSetAttribute(gemm_splitk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  gemm_splitk_kernel<BN><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  MAED_BW_LAUNCH_CHECK();
+  return MAED_OK;
+}
+
+}  // namespace
+
+size_t splitk_slab_floats(int Mo, int No, int R) {
+  const SliceChoice c = choose_slices(Mo, No, R);
+  return (size_t)c.slices * Mo * No;
+}
+
+int gemm_wgrad_splitk(const __half* A, long long a_plane, int lda, const __half* B, long long b_plane, int ldb, int Mo,
+                      int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd,
+                      cudaStream_t st) {
+  MAED_CHECK_ARG(A && B && slabs && D, "gemm_wgrad_splitk: null argument");
+  MAED_CHECK_ARG(Mo >= 1 && No >= 32 && No % 32 == 0 && R >= 1, "gemm_wgrad_splitk: bad shape Mo=%d No=%d R=%d", Mo, No, R);
+  MAED_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && lda >= R && ldb >= R, "gemm_wgrad_splitk: row strides must be multiples of 8 "
+                 "and >= R (lda=%d ldb=%d R=%d)", lda, ldb, R);
+  MAED_CHECK_ARG(nsplit == 1 || nsplit == 3, "gemm_wgrad_splitk: nsplit must be 1 or 3");
+  const int np = nsplit == 3 ? 2 : 1;
+  const SliceChoice c = choose_slices(Mo, No, R);
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[3] = {(uint64_t)R, (uint64_t)Mo, (uint64_t)np};
+    const uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(np == 2 ? a_plane : (long long)Mo * lda) * 2};
+    const uint32_t box[3] = {(uint32_t)kBK, (uint32_t)kBM, 1};
+    MAED_PROPAGATE(make_tmap_f16(&tmA, A, 3, dims, str, box));
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)R, (uint64_t)No, (uint64_t)np};
+    const uint64_t str[2] = {(uint64_t)ldb * 2, (uint64_t)(np == 2 ? b_plane : (long long)No * ldb) * 2};
+    const uint32_t box[3] = {(uint32_t)kBK, (uint32_t)c.block_n, 1};
+    MAED_PROPAGATE(make_tmap_f16(&tmB, B, 3, dims, str, box));
+  }
+  SplitKParams p;
+  p.M = Mo; p.N = No; p.num_k_blocks = c.nkb; p.kb_per_slice = c.kb_per; p.slices = c.slices; p.nsplit = nsplit;
+  p.m_tiles = c.m_tiles; p.n_tiles = c.n_tiles; p.slabs = slabs;
+  const size_t stage_bytes = (size_t)np * (kBM * kBK * 2 + c.block_n * kBK * 2);
+  int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+  if (stages > kStagesMax) stages = kStagesMax;
+  MAED_CHECK_ARG(stages >= 2, "gemm_wgrad_splitk: tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = 1024 + stages * stage_bytes + 256;
+  const int tiles = c.m_tiles * c.n_tiles * c.slices;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  int rc;
+  if (c.block_n == 256) rc = launch_splitk<256>(tmA, tmB, p, grid, smem, st);
+  else if (c.block_n == 128) rc = launch_splitk<128>(tmA, tmB, p, grid, smem, st);
+  else rc = launch_splitk<64>(tmA, tmB, p, grid, smem, st);
+  MAED_PROPAGATE(rc);
+  const long long mn = (long long)Mo * No;
+  splitk_reduce_kernel<<<bw::grid_for(mn, 256), 256, 0, st>>>(slabs, c.slices, mn, No, scale, accumulate, D, ldd);
+  MAED_BW_LAUNCH_CHECK();
+  return MAED_OK;
+}
+
+}  // namespace maed

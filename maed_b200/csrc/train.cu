@@ -1,0 +1,712 @@
+// Training path of the MAED engine: forward with a saved-activation tape + backward to every parameter
+// (reference: autograd of lib/models/maed.py:52-66 as driven by lib/core/trainer.py:238-255).
+//
+// Boundary: the decoder outputs pose6d / shape / cam (the geometry tail behind them — rot6d -> rotmat -> angle-axis,
+// projection — is differentiated by autograd on the Python side; it is O(BT * 24) work).
+//
+//   train_forward : same arithmetic as engine_forward, but every layer writes into its own tape slot (GroupNorm runs
+//                   unfused so the fp32 conv outputs and their statistics are kept; fc1 keeps its pre-GELU output).
+//   train_backward: walks the tape in reverse.  All data-gradient and weight-gradient contractions run on the tensor
+//                   cores in split precision: dX = dY * W through the forward GEMM kernel with transposed packed
+//                   weights (3x3: the implicit-GEMM conv kernel with flipped taps), dW = dY^T * X through the split-K
+//                   kernel on transposed activation planes.  Activation gradients carry `loss_scale`; parameter
+//                   gradients are written un-scaled, in the reference's parameter layout, to `grads[i]`.
+//
+// Supported for training: st_mode parallel / series / vanilla with the KTD decoder (the published configurations).
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "bwd_kernels.h"
+#include "engine_internal.h"
+#include "gemm_host.h"
+#include "gemm_sm100.cuh"
+#include "kernels.h"
+#include "train.h"
+
+namespace maed {
+
+namespace {
+
+size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
+int ld8(long long r) { return (int)((r + 7) / 8 * 8); }
+
+// ------------------------------------------------------------------------------------ backbone layer table
+struct ConvL {
+  int Hin, Cin, Cout, k, stride, Hout, relu;
+  int w_idx, g_idx;            // parameter indices (conv weight; norm weight, bias = +1)
+  size_t pk_off;               // forward packed weight (engine pack)
+  size_t tp_off;               // dgrad packed weight (train pack); stem: unused
+  int in_layer;                // producing layer (-1: network input for the stem)
+  int res_layer;               // layer whose output is added before the ReLU (-2: none)
+  long long Min(int BT) const { return (long long)BT * Hin * Hin; }
+  long long Mout(int BT) const { return (long long)BT * Hout * Hout; }
+  int Kcols() const { return k * k * Cin; }
+};
+struct BlockL { int ds, c1, c2, c3, in_layer; };   // layer ids (ds = -1 when absent)
+
+struct Net {
+  std::vector<ConvL> L;        // 0 = stem (its "output" is the pooled 56x56x64 map), then the 52 bottleneck convs
+  std::vector<BlockL> B;
+  size_t tp_proj;              // dgrad weights of patch_embed.proj
+  struct SteT { size_t qkv, proj, fc1, fc2; };
+  std::vector<SteT> ste;
+  size_t tpack_bytes;
+};
+
+Net build_net(const Engine& e) {
+  Net n;
+  size_t off = 0;
+  auto planes = [&](long long elems) { size_t o = off; off = align_up(off + (size_t)elems * 2 * 2); return o; };
+  ConvL stem{224, 3, 64, 7, 2, 112, 1, e.i_stem_w, e.i_stem_g, e.off_stem, 0, -1, -2};
+  n.L.push_back(stem);
+  int prev = 64, Hc = 56, cur = 0, bi = 0;
+  for (int s = 0; s < 3; ++s) {
+    const int out = kStageOut[s], mid = out / 4;
+    for (int b = 0; b < kStageDepth[s]; ++b, ++bi) {
+      const Engine::BlockIdx& ix = e.bb[bi];
+      const Engine::BlockOff& of = e.bb_off[bi];
+      const int stride = (s > 0 && b == 0) ? 2 : 1;
+      const int Ho = Hc / stride;
+      BlockL bl;
+      bl.in_layer = cur;
+      bl.ds = -1;
+      int shortcut = cur;
+      if (b == 0) {
+        n.L.push_back(ConvL{Hc, prev, out, 1, stride, Ho, 0, ix.ds_w, ix.ds_g, of.ds, planes((long long)out * prev), cur, -2});
+        bl.ds = (int)n.L.size() - 1;
+        shortcut = bl.ds;
+      }
+      n.L.push_back(ConvL{Hc, prev, mid, 1, 1, Hc, 1, ix.c1_w, ix.c1_g, of.c1, planes((long long)mid * prev), cur, -2});
+      bl.c1 = (int)n.L.size() - 1;
+      n.L.push_back(ConvL{Hc, mid, mid, 3, stride, Ho, 1, ix.c2_w, ix.c2_g, of.c2, planes((long long)mid * mid * 9), bl.c1, -2});
+      bl.c2 = (int)n.L.size() - 1;
+      n.L.push_back(ConvL{Ho, mid, out, 1, 1, Ho, 1, ix.c3_w, ix.c3_g, of.c3, planes((long long)out * mid), bl.c2, shortcut});
+      bl.c3 = (int)n.L.size() - 1;
+      n.B.push_back(bl);
+      cur = bl.c3;
+      prev = out;
+      Hc = Ho;
+    }
+  }
+  n.tp_proj = planes(768LL * 1024);
+  const long long CC = 768LL * 768;
+  for (int i = 0; i < e.cfg.num_blocks; ++i) {
+    Net::SteT t;
+    t.qkv = planes(3 * CC);
+    t.proj = planes(CC);
+    t.fc1 = planes(4 * CC);
+    t.fc2 = planes(4 * CC);
+    n.ste.push_back(t);
+  }
+  n.tpack_bytes = off;
+  return n;
+}
+
+// --------------------------------------------------------------------------------------------- workspace
+struct SteTape {
+  float* x_in; __half* ln1; __half* qkv; float* xs; float* xt; __half* ao_s; __half* qkv2; float* pooled; float* logits;
+  __half* ao; float* x_mid; __half* ln2; float* h_pre; __half* hid;
+};
+struct TrainWs {
+  // ---- tape
+  std::vector<__half*> out; std::vector<float*> convout; std::vector<double*> stats;
+  std::vector<long long> out_plane;
+  unsigned char* pool_idx;
+  float* tok;                                    // proj output [BT*196, 768]
+  std::vector<SteTape> ste;
+  float* x_final;
+  float* cls_ln; float* h1; float* h2; float* base; unsigned char* mask1; unsigned char* mask2;
+  float* feat_copy; float* pose_copy;
+  // ---- scratch shared by forward and backward
+  __half* col; long long col_plane;              // im2col matrix / small planes
+  __half* pl_a; long long pl_a_plane;            // generic planes (max rows*3072 or M*C)
+  __half* pl_t; long long pl_t_plane;            // transposed planes of a gradient
+  __half* pl_x; long long pl_x_plane;            // transposed planes of an activation / im2col matrix
+  __half* dil; long long dil_plane;
+  float* fa; float* fb; float* fc; float* fd;    // fp32 activation-gradient buffers (backbone size)
+  float* big;                                    // fp32 [rows, 3072]
+  float* dxs; float* dxt;
+  float* wg;                                     // fp32 dW_hat temp
+  float* slabs;
+  float* red; float* dgb; float* colsum_scratch; float* ln_partial;
+  float* small[8];                               // [BT, 2048] fp32 each
+  __half* small_p; long long small_plane;
+  float* anc_grad;
+  long long ln_rows, ln_plane, qkv_plane, hid_plane;
+  size_t total;
+};
+
+long long max_ll(long long a, long long b) { return a > b ? a : b; }
+
+void carve(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off = align_up(off + bytes); return p; };
+  const int nl = (int)net.L.size();
+  w.out.resize(nl); w.convout.resize(nl); w.stats.resize(nl); w.out_plane.resize(nl);
+  long long max_mc = 0, max_col = 0, max_xt = 0, max_slab = 0, max_wg = 0;
+  for (int l = 0; l < nl; ++l) {
+    const ConvL& L = net.L[l];
+    const long long Mo = L.Mout(BT);
+    const long long out_elems = (l == 0) ? (long long)BT * 3136 * 64 : Mo * L.Cout;
+    w.out_plane[l] = out_elems;
+    w.out[l] = (__half*)take((size_t)out_elems * 4);
+    w.convout[l] = (float*)take((size_t)Mo * L.Cout * 4);
+    w.stats[l] = (double*)take((size_t)BT * 64 * 8);
+    max_mc = max_ll(max_mc, max_ll(Mo * L.Cout, L.Min(BT) * L.Cin));
+    const int kc = (l == 0) ? kStemKPad : L.Kcols();
+    const int kc_pad = (kc + 31) / 32 * 32;
+    if (L.k > 1 || L.stride > 1) max_col = max_ll(max_col, Mo * kc);
+    max_xt = max_ll(max_xt, (long long)kc_pad * ld8(Mo));
+    max_xt = max_ll(max_xt, (long long)L.Cout * ld8(Mo));
+    max_slab = max_ll(max_slab, (long long)splitk_slab_floats(L.Cout, kc_pad, (int)Mo));
+    max_wg = max_ll(max_wg, (long long)L.Cout * kc_pad);
+  }
+  w.pool_idx = (unsigned char*)take((size_t)BT * 3136 * 64);
+  const long long rows = (long long)BT * 197;
+  const int C = 768;
+  w.tok = (float*)take((size_t)BT * 196 * C * 4);
+  w.ln_rows = rows; w.ln_plane = rows * C; w.qkv_plane = rows * 3 * C; w.hid_plane = rows * 4 * C;
+  w.ste.resize(e.cfg.num_blocks);
+  for (int i = 0; i < e.cfg.num_blocks; ++i) {
+    SteTape& t = w.ste[i];
+    t.x_in = (float*)take((size_t)rows * C * 4);
+    t.ln1 = (__half*)take((size_t)w.ln_plane * 4);
+    t.qkv = (__half*)take((size_t)w.qkv_plane * 4);
+    t.xs = (float*)take((size_t)rows * C * 4);
+    t.xt = (float*)take((size_t)rows * C * 4);
+    t.ao_s = (e.cfg.mode == MODE_SERIES) ? (__half*)take((size_t)w.ln_plane * 4) : nullptr;
+    t.qkv2 = (e.cfg.mode == MODE_SERIES) ? (__half*)take((size_t)w.qkv_plane * 4) : nullptr;
+    t.pooled = (float*)take((size_t)BT * 2 * C * 4);
+    t.logits = (float*)take((size_t)BT * 2 * C * 4);
+    t.ao = (__half*)take((size_t)w.ln_plane * 4);
+    t.x_mid = (float*)take((size_t)rows * C * 4);
+    t.ln2 = (__half*)take((size_t)w.ln_plane * 4);
+    t.h_pre = (float*)take((size_t)rows * 4 * C * 4);
+    t.hid = (__half*)take((size_t)w.hid_plane * 4);
+  }
+  w.x_final = (float*)take((size_t)rows * C * 4);
+  const int HD = e.cfg.hidden_dim;
+  w.cls_ln = (float*)take((size_t)BT * C * 4);
+  w.h1 = (float*)take((size_t)BT * HD * 4);
+  w.h2 = (float*)take((size_t)BT * HD * 4);
+  w.base = (float*)take((size_t)BT * 192 * 4);
+  w.mask1 = (unsigned char*)take((size_t)BT * HD);
+  w.mask2 = (unsigned char*)take((size_t)BT * HD);
+  w.feat_copy = (float*)take((size_t)BT * C * 4);
+  w.pose_copy = (float*)take((size_t)BT * 144 * 4);
+  // ---- scratch
+  const long long ste_big = rows * 4 * C;                                   // rows x 3072
+  max_xt = max_ll(max_xt, (long long)4 * C * ld8(rows));
+  max_xt = max_ll(max_xt, 1024LL * ld8((long long)BT * 196));
+  const long long pl_elems = max_ll(max_mc, ste_big);
+  w.col_plane = max_ll(max_col, 8); w.col = (__half*)take((size_t)w.col_plane * 4);
+  w.pl_a_plane = pl_elems; w.pl_a = (__half*)take((size_t)pl_elems * 4);
+  w.pl_t_plane = max_xt; w.pl_t = (__half*)take((size_t)max_xt * 4);
+  w.pl_x_plane = max_xt; w.pl_x = (__half*)take((size_t)max_xt * 4);
+  w.dil_plane = max_mc; w.dil = (__half*)take((size_t)max_mc * 4);
+  w.fa = (float*)take((size_t)max_mc * 4);
+  w.fb = (float*)take((size_t)max_mc * 4);
+  w.fc = (float*)take((size_t)max_mc * 4);
+  w.fd = (float*)take((size_t)max_mc * 4);
+  w.big = (float*)take((size_t)ste_big * 4);
+  w.dxs = (float*)take((size_t)rows * C * 4);
+  w.dxt = (float*)take((size_t)rows * C * 4);
+  // split-K slabs / weight-gradient temp: also cover the STE and proj linears
+  const int lin_shapes[6][2] = {{3 * C, C}, {C, C}, {4 * C, C}, {C, 4 * C}, {C, 1024}, {2 * C, 2 * C}};
+  for (int i = 0; i < 6; ++i) {
+    max_slab = max_ll(max_slab, (long long)splitk_slab_floats(lin_shapes[i][0], lin_shapes[i][1], (int)rows));
+    max_wg = max_ll(max_wg, (long long)lin_shapes[i][0] * lin_shapes[i][1]);
+  }
+  w.wg = (float*)take((size_t)max_wg * 4);
+  w.slabs = (float*)take((size_t)max_slab * 4);
+  w.red = (float*)take((size_t)BT * (64 + 32 * 1024) * 4);
+  w.dgb = (float*)take((size_t)BT * 2 * 1024 * 4);
+  w.colsum_scratch = (float*)take((size_t)kColsumChunks * 197 * C * 4);
+  w.ln_partial = (float*)take((size_t)ln_bwd_partial_rows() * 2 * C * 4);
+  for (int i = 0; i < 8; ++i) w.small[i] = (float*)take((size_t)BT * 2048 * 4);
+  w.small_plane = (long long)BT * 2048; w.small_p = (__half*)take((size_t)w.small_plane * 4);
+  w.anc_grad = (float*)take(36 * 95 * 4);
+  w.total = off;
+}
+
+struct Ctx {
+  const Engine& e; const Net& net; TrainWs& w; const void* const* params; const uint8_t* pk; const uint8_t* tp;
+  int BT, N, T; cudaStream_t st; float inv_ls; float* const* grads; const float* x_img;
+  const float* P(int i) const { return (const float*)params[i]; }
+  float* G(int i) const { return grads[i]; }
+  const __half* H(size_t off) const { return (const __half*)(pk + off); }
+  const __half* TH(size_t off) const { return (const __half*)(tp + off); }
+};
+
+int gemm_plain(const Ctx& c, const __half* A, long long a_plane, int M, int K, const __half* B, long long b_plane, int Nout,
+               const float* bias, int act, const float* residual, int out_mode, void* out, long long out_plane) {
+  GemmArgs g;
+  g.nsplit = 3;
+  g.A = A; g.a_plane = a_plane; g.B = B; g.b_plane = b_plane;
+  g.M = M; g.N = Nout; g.K = K; g.bias = bias; g.act = act; g.residual = residual; g.out_mode = out_mode; g.out = out;
+  g.out_plane = out_plane; g.ldc = Nout;
+  return launch_gemm(g, c.st);
+}
+
+}  // namespace
+
+// ================================================================================================ API
+size_t train_pack_bytes(const Engine* e) { return build_net(*e).tpack_bytes + 1024; }
+
+size_t train_workspace_bytes(const Engine* e, int BT) {
+  const Net net = build_net(*e);
+  TrainWs w;
+  carve(*e, net, BT, nullptr, w);
+  return w.total + 1024;
+}
+
+static int check_train_cfg(const Engine& e) {
+  const int m = e.cfg.mode;
+  MAED_CHECK_ARG(m == MODE_PARALLEL || m == MODE_SERIES || m == MODE_VANILLA,
+                 "training supports st_mode parallel / series / vanilla (got mode %d)", m);
+  MAED_CHECK_ARG(e.cfg.decoder == DEC_KTD, "training supports the KTD decoder only");
+  MAED_CHECK_ARG(e.cfg.nsplit == 3, "training runs in split precision (precision='split')");
+  return MAED_OK;
+}
+
+int train_pack(const Engine* ep, const void* const* params, void* tpack, cudaStream_t st) {
+  MAED_CHECK_ARG(ep && params && tpack, "train_pack: null argument");
+  const Engine& e = *ep;
+  MAED_PROPAGATE(check_train_cfg(e));
+  const Net net = build_net(e);
+  uint8_t* tp = (uint8_t*)(((uintptr_t)tpack + 1023) & ~(uintptr_t)1023);
+  auto P = [&](int i) { return (const float*)params[i]; };
+  for (size_t l = 1; l < net.L.size(); ++l) {
+    const ConvL& L = net.L[l];
+    MAED_PROPAGATE(prep_conv_weight_dgrad(P(L.w_idx), L.Cout, L.Cin, L.k, L.k, 1, (__half*)(tp + L.tp_off),
+                                          (long long)L.Cout * L.Cin * L.k * L.k, st));
+  }
+  MAED_PROPAGATE(split_f32_transposed(P(e.i_proj_w), 768, 1024, (__half*)(tp + net.tp_proj), 768LL * 1024, st));
+  const int C = 768;
+  const long long CC = (long long)C * C;
+  for (int i = 0; i < e.cfg.num_blocks; ++i) {
+    const Engine::SteIdx& ix = e.blk[i];
+    MAED_PROPAGATE(split_f32_transposed(P(ix.qkv_w), 3 * C, C, (__half*)(tp + net.ste[i].qkv), 3 * CC, st));
+    MAED_PROPAGATE(split_f32_transposed(P(ix.proj_w), C, C, (__half*)(tp + net.ste[i].proj), CC, st));
+    MAED_PROPAGATE(split_f32_transposed(P(ix.fc1_w), 4 * C, C, (__half*)(tp + net.ste[i].fc1), 4 * CC, st));
+    MAED_PROPAGATE(split_f32_transposed(P(ix.fc2_w), C, 4 * C, (__half*)(tp + net.ste[i].fc2), 4 * CC, st));
+  }
+  return MAED_OK;
+}
+
+// -------------------------------------------------------------------------------------------- forward
+static int conv_fwd(const Ctx& c, int l) {
+  const ConvL& L = c.net.L[l];
+  TrainWs& w = c.w;
+  const int BT = c.BT;
+  const __half* A = w.out[L.in_layer];
+  const long long a_plane = w.out_plane[L.in_layer];
+  const long long M = L.Mout(BT);
+  GemmArgs g;
+  g.nsplit = 3;
+  g.B = c.H(L.pk_off); g.b_plane = (long long)L.Cout * L.Kcols();
+  g.M = (int)M; g.N = L.Cout; g.out_mode = OUT_F32; g.out = w.convout[l]; g.ldc = L.Cout;
+  const int pad_total = std::max((L.Hout - 1) * L.stride + L.k - L.Hin, 0);
+  if (L.k == 1 && L.stride == 1) {
+    g.A = A; g.a_plane = a_plane; g.K = L.Cin;
+  } else if (L.stride == 1) {
+    g.A = A; g.a_plane = a_plane; g.K = L.Kcols();
+    g.conv = 1; g.n_img = BT; g.H = L.Hin; g.W = L.Hin; g.Cin = L.Cin; g.KH = L.k; g.KW = L.k;
+    g.pad_h = pad_total / 2; g.pad_w = pad_total / 2;
+  } else {
+    MAED_PROPAGATE(im2col_nhwc(A, a_plane, BT, L.Hin, L.Hin, L.Cin, L.k, L.k, L.stride, pad_total / 2, pad_total / 2, L.Hout,
+                               L.Hout, w.col, w.col_plane, c.st));
+    g.A = w.col; g.a_plane = w.col_plane; g.K = L.Kcols();
+  }
+  MAED_PROPAGATE(launch_gemm(g, c.st));
+  MAED_CUDA_CHECK(cudaMemsetAsync(w.stats[l], 0, (size_t)BT * 64 * 8, c.st));
+  MAED_PROPAGATE(gn_stats(w.convout[l], BT, L.Hout * L.Hout, L.Cout, w.stats[l], c.st));
+  const __half* res = L.res_layer >= 0 ? w.out[L.res_layer] : nullptr;
+  const long long res_plane = L.res_layer >= 0 ? w.out_plane[L.res_layer] : 0;
+  MAED_PROPAGATE(gn_apply(w.convout[l], w.stats[l], c.P(L.g_idx), c.P(L.g_idx + 1), BT, L.Hout * L.Hout, L.Cout, 1e-5f, L.relu,
+                          res, res_plane, w.out[l], w.out_plane[l], c.st));
+  return MAED_OK;
+}
+
+int train_forward(const Engine* ep, const void* const* params, const void* packed, const float* x_in, int N, int T,
+                  void* workspace, size_t workspace_bytes, float dropout_p, unsigned long long seed, const TrainOutputs* outs,
+                  cudaStream_t st) {
+  MAED_CHECK_ARG(ep && params && packed && x_in && workspace && outs, "train_forward: null argument");
+  const Engine& e = *ep;
+  MAED_PROPAGATE(check_train_cfg(e));
+  const EngineConfig& cf = e.cfg;
+  const int BT = N * T;
+  MAED_CHECK_ARG(N >= 1 && T >= 1 && T <= 32, "train_forward: bad batch N=%d T=%d", N, T);
+  const bool has_temp = e.i_temp >= 0;
+  MAED_CHECK_ARG(!has_temp || T <= cf.temp_frames, "train_forward: seqlen T=%d exceeds temp_embed frames %d", T, cf.temp_frames);
+  MAED_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "train_forward: dropout_p=%f", (double)dropout_p);
+  const Net net = build_net(e);
+  TrainWs w;
+  carve(e, net, BT, (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023), w);
+  MAED_CHECK_ARG(w.total + 1024 <= workspace_bytes, "train_forward: workspace too small (%zu < %zu)", workspace_bytes,
+                 w.total + 1024);
+  Ctx c{e, net, w, params, (const uint8_t*)packed, nullptr, BT, N, T, st, 1.f, nullptr, x_in};
+
+  // ---- backbone (GroupNorm unfused: conv outputs and statistics stay on the tape)
+  MAED_CUDA_CHECK(cudaMemsetAsync(w.stats[0], 0, (size_t)BT * 64 * 8, st));
+  MAED_PROPAGATE(stem_conv(x_in, BT, c.H(e.off_stem), 64LL * kStemKPad, kStemKPad, 3, w.convout[0], w.stats[0], st));
+  MAED_PROPAGATE(gn_apply_maxpool_idx(w.convout[0], w.stats[0], c.P(e.i_stem_g), c.P(e.i_stem_g + 1), BT, 112, 112, 64, 1e-5f,
+                                      w.out[0], w.out_plane[0], w.pool_idx, st));
+  for (size_t l = 1; l < net.L.size(); ++l) MAED_PROPAGATE(conv_fwd(c, (int)l));
+  const int last = (int)net.L.size() - 1;
+
+  // ---- patch embedding
+  const int ntok = 197, C = 768, heads = cf.num_heads;
+  const int rows = BT * ntok;
+  MAED_PROPAGATE(gemm_plain(c, w.out[last], w.out_plane[last], BT * 196, 1024, c.H(e.off_proj), 768LL * 1024, 768,
+                            c.P(e.i_proj_b), ACT_NONE, nullptr, OUT_F32, w.tok, 0));
+  MAED_PROPAGATE(embed_assemble(w.tok, c.P(e.i_cls), c.P(e.i_pos), has_temp ? c.P(e.i_temp) : nullptr, BT, T, ntok, C,
+                                w.ste[0].x_in, st));
+
+  // ---- STE blocks
+  const float scale = 0.125f;
+  const long long CC = (long long)C * C;
+  for (int i = 0; i < cf.num_blocks; ++i) {
+    const Engine::SteIdx& ix = e.blk[i];
+    const Engine::SteOff& of = e.blk_off[i];
+    SteTape& t = w.ste[i];
+    float* x_out = (i + 1 < cf.num_blocks) ? w.ste[i + 1].x_in : w.x_final;
+    MAED_PROPAGATE(layernorm_planes(t.x_in, C, c.P(ix.n1), c.P(ix.n1 + 1), rows, C, 1e-6f, t.ln1, w.ln_plane, st));
+    MAED_PROPAGATE(gemm_plain(c, t.ln1, w.ln_plane, rows, C, c.H(of.qkv), 3 * CC, 3 * C, c.P(ix.qkv_b), ACT_NONE, nullptr,
+                              OUT_F16_SPLIT, t.qkv, w.qkv_plane));
+    if (cf.mode == MODE_PARALLEL) {
+      MAED_PROPAGATE(attn_temporal(t.qkv, w.qkv_plane, N, T, ntok, heads, scale, t.xt, nullptr, 0, st));
+      MAED_PROPAGATE(attn_spatial(t.qkv, w.qkv_plane, BT, ntok, heads, scale, 3, t.xs, nullptr, 0, st));
+      MAED_PROPAGATE(token_mean(t.xs, BT, ntok, C, t.pooled, 2 * C, 0, st));
+      MAED_PROPAGATE(token_mean(t.xt, BT, ntok, C, t.pooled, 2 * C, C, st));
+      MAED_PROPAGATE(split_f32(t.pooled, w.small_p, w.small_plane, (long long)BT * 2 * C, st));
+      MAED_PROPAGATE(gemm_plain(c, w.small_p, w.small_plane, BT, 2 * C, c.H(of.ts), 4 * CC, 2 * C, c.P(ix.ts_b), ACT_NONE, nullptr,
+                                OUT_F32, t.logits, 0));
+      MAED_PROPAGATE(ts_blend(t.xs, t.xt, t.logits, BT, ntok, C, t.ao, w.ln_plane, st));
+    } else if (cf.mode == MODE_SERIES) {
+      MAED_PROPAGATE(attn_spatial(t.qkv, w.qkv_plane, BT, ntok, heads, scale, 3, nullptr, t.ao_s, w.ln_plane, st));
+      MAED_PROPAGATE(gemm_plain(c, t.ao_s, w.ln_plane, rows, C, c.H(of.qkv), 3 * CC, 3 * C, c.P(ix.qkv_b), ACT_NONE, nullptr,
+                                OUT_F16_SPLIT, t.qkv2, w.qkv_plane));
+      MAED_PROPAGATE(attn_temporal(t.qkv2, w.qkv_plane, N, T, ntok, heads, scale, nullptr, t.ao, w.ln_plane, st));
+    } else {
+      MAED_PROPAGATE(attn_spatial(t.qkv, w.qkv_plane, BT, ntok, heads, scale, 3, nullptr, t.ao, w.ln_plane, st));
+    }
+    MAED_PROPAGATE(gemm_plain(c, t.ao, w.ln_plane, rows, C, c.H(of.proj), CC, C, c.P(ix.proj_b), ACT_NONE, t.x_in, OUT_F32,
+                              t.x_mid, 0));
+    MAED_PROPAGATE(layernorm_planes(t.x_mid, C, c.P(ix.n2), c.P(ix.n2 + 1), rows, C, 1e-6f, t.ln2, w.ln_plane, st));
+    MAED_PROPAGATE(gemm_plain(c, t.ln2, w.ln_plane, rows, C, c.H(of.fc1), 4 * CC, 4 * C, c.P(ix.fc1_b), ACT_NONE, nullptr,
+                              OUT_F32, t.h_pre, 0));
+    MAED_PROPAGATE(gelu_fwd_planes(t.h_pre, (long long)rows * 4 * C, t.hid, w.hid_plane, st));
+    MAED_PROPAGATE(gemm_plain(c, t.hid, w.hid_plane, rows, 4 * C, c.H(of.fc2), 4 * CC, C, c.P(ix.fc2_b), ACT_NONE, t.x_mid,
+                              OUT_F32, x_out, 0));
+  }
+
+  // ---- tail (always split precision; fp32 copies of every activation stay on the tape)
+  const int HD = cf.hidden_dim;
+  auto tail = [&](const float* a_f32, int K, size_t w_off, int Nout, const float* bias, int act, float* out) -> int {
+    MAED_PROPAGATE(split_f32(a_f32, w.small_p, w.small_plane, (long long)BT * K, st));
+    return gemm_plain(c, w.small_p, w.small_plane, BT, K, c.H(w_off), (long long)Nout * K, Nout, bias, act, nullptr, OUT_F32, out, 0);
+  };
+  MAED_PROPAGATE(layernorm_f32(w.x_final, (long long)ntok * C, c.P(e.i_norm), c.P(e.i_norm + 1), BT, C, 1e-6f, w.cls_ln, st));
+  MAED_PROPAGATE(tail(w.cls_ln, C, e.off_pl, C, c.P(e.i_pl_b), ACT_TANH, w.feat_copy));
+  MAED_PROPAGATE(tail(w.feat_copy, C, e.off_kfc1, HD, c.P(e.i_fc1_b), ACT_NONE, w.h1));
+  if (dropout_p > 0.f) MAED_PROPAGATE(dropout_fwd(w.h1, (long long)BT * HD, dropout_p, seed, w.mask1, st));
+  MAED_PROPAGATE(tail(w.h1, HD, e.off_kfc2, HD, c.P(e.i_fc2_b), ACT_NONE, w.h2));
+  if (dropout_p > 0.f) MAED_PROPAGATE(dropout_fwd(w.h2, (long long)BT * HD, dropout_p, seed ^ 0x5851F42D4C957F2Dull, w.mask2, st));
+  MAED_PROPAGATE(tail(w.h2, HD, e.off_kheads, 192, (const float*)(c.pk + e.off_kheads_b), ACT_NONE, w.base));
+  MAED_PROPAGATE(ktd_tree(w.base, 192, (const float*)(c.pk + e.off_ktd_anc), BT, w.pose_copy, outs->shape, outs->cam, st));
+  MAED_CUDA_CHECK(cudaMemcpyAsync(outs->pose6d, w.pose_copy, (size_t)BT * 144 * 4, cudaMemcpyDeviceToDevice, st));
+  if (outs->feat) MAED_CUDA_CHECK(cudaMemcpyAsync(outs->feat, w.feat_copy, (size_t)BT * C * 4, cudaMemcpyDeviceToDevice, st));
+  return MAED_OK;
+}
+
+// ------------------------------------------------------------------------------------------- backward
+// dW [Nw, Kw] = scale * dY^T X  for a linear layer; dY, X as planes [R, *] (dense rows)
+static int linear_wgrad(const Ctx& c, const __half* dy, long long dy_plane, int Nw, const __half* x, long long x_plane, int Kw,
+                        int R, int accumulate, float* dW) {
+  TrainWs& w = c.w;
+  const int ld = ld8(R);
+  MAED_PROPAGATE(transpose_planes(dy, dy_plane, R, Nw, Nw, w.pl_t, w.pl_t_plane, ld, c.st));
+  MAED_PROPAGATE(transpose_planes(x, x_plane, R, Kw, Kw, w.pl_x, w.pl_x_plane, ld, c.st));
+  return gemm_wgrad_splitk(w.pl_t, w.pl_t_plane, ld, w.pl_x, w.pl_x_plane, ld, Nw, Kw, R, 3, c.inv_ls, accumulate, w.slabs, dW,
+                           Kw, c.st);
+}
+
+// Backward of one conv + GroupNorm layer.  d_y: gradient w.r.t. the GN output (ReLU mask already applied), fp32
+// [Mout, Cout].  Writes the parameter gradients; when d_in != nullptr also d_in = dgrad (+ d_in_add), fp32 [Min, Cin]
+// (d_in may alias d_in_add).  tmp_f32: scratch of Mout*Cin floats (1x1 stride-2 data gradient only).
+static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_in_add, float* d_in, float* tmp_f32) {
+  const ConvL& L = c.net.L[l];
+  TrainWs& w = c.w;
+  const int BT = c.BT;
+  const long long Mo = L.Mout(BT);
+  const int HWo = L.Hout * L.Hout;
+  // ---- GroupNorm backward -> dconv planes [Mo, Cout] in pl_a; dgamma / dbeta
+  MAED_PROPAGATE(groupnorm_bwd(d_y, w.convout[l], w.stats[l], c.P(L.g_idx), BT, HWo, L.Cout, 1e-5f, w.red, w.dgb, w.pl_a,
+                               w.pl_a_plane, c.st));
+  MAED_PROPAGATE(colsum_f32(w.dgb, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx), c.st));
+  MAED_PROPAGATE(colsum_f32(w.dgb + L.Cout, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx + 1), c.st));
+  // ---- weight gradient: dW_hat [Cout, kc] = dconv^T * im2col(x), then through the weight standardisation
+  const int ld = ld8(Mo);
+  const int kc = (l == 0) ? kStemKPad : L.Kcols();
+  const int kc_pad = (kc + 31) / 32 * 32;                  // split-K output width (multiple of 32); extra rows are zero
+  const int pad_total = std::max((L.Hout - 1) * L.stride + L.k - L.Hin, 0);
+  MAED_PROPAGATE(transpose_planes(w.pl_a, w.pl_a_plane, (int)Mo, L.Cout, L.Cout, w.pl_t, w.pl_t_plane, ld, c.st));
+  const __half* xm;                                        // [Mo, kc] activation matrix of the wgrad
+  long long xm_plane;
+  if (l == 0) {
+    MAED_PROPAGATE(im2col_stem(c.x_img, BT, 3, 224, 224, 7, 7, 2, pad_total / 2, pad_total / 2, 112, 112, kStemKPad, w.col,
+                               w.col_plane, c.st));
+    xm = w.col; xm_plane = w.col_plane;
+  } else if (L.k == 1 && L.stride == 1) {
+    xm = w.out[L.in_layer]; xm_plane = w.out_plane[L.in_layer];
+  } else {
+    MAED_PROPAGATE(im2col_nhwc(w.out[L.in_layer], w.out_plane[L.in_layer], BT, L.Hin, L.Hin, L.Cin, L.k, L.k, L.stride,
+                               pad_total / 2, pad_total / 2, L.Hout, L.Hout, w.col, w.col_plane, c.st));
+    xm = w.col; xm_plane = w.col_plane;
+  }
+  if (kc_pad != kc) {                                      // rows kc..kc_pad of the transposed matrix must read as zeros
+    MAED_CUDA_CHECK(cudaMemsetAsync(w.pl_x + (long long)kc * ld, 0, (size_t)(kc_pad - kc) * ld * 2, c.st));
+    MAED_CUDA_CHECK(cudaMemsetAsync(w.pl_x + w.pl_x_plane + (long long)kc * ld, 0, (size_t)(kc_pad - kc) * ld * 2, c.st));
+  }
+  MAED_PROPAGATE(transpose_planes(xm, xm_plane, (int)Mo, kc, kc, w.pl_x, w.pl_x_plane, ld, c.st));
+  MAED_PROPAGATE(gemm_wgrad_splitk(w.pl_t, w.pl_t_plane, ld, w.pl_x, w.pl_x_plane, ld, L.Cout, kc_pad, (int)Mo, 3, 1.0f, 0,
+                                   w.slabs, w.wg, kc_pad, c.st));
+  MAED_PROPAGATE(wstd_bwd(w.wg, kc_pad, c.P(L.w_idx), L.Cout, L.Cin, L.k, L.k, 1e-5f, c.inv_ls, c.G(L.w_idx), c.st));
+  if (!d_in) return MAED_OK;
+  // ---- data gradient
+  const long long tplane = (long long)L.Cout * L.Cin * L.k * L.k;
+  if (L.k == 1 && L.stride == 1) {
+    return gemm_plain(c, w.pl_a, w.pl_a_plane, (int)Mo, L.Cout, c.TH(L.tp_off), tplane, L.Cin, nullptr, ACT_NONE, d_in_add,
+                      OUT_F32, d_in, 0);
+  }
+  if (L.k == 1) {                                          // 1x1 stride 2: dense GEMM, then scatter to the even positions
+    MAED_PROPAGATE(gemm_plain(c, w.pl_a, w.pl_a_plane, (int)Mo, L.Cout, c.TH(L.tp_off), tplane, L.Cin, nullptr, ACT_NONE, nullptr,
+                              OUT_F32, tmp_f32, 0));
+    return scatter_stride2_f32(tmp_f32, BT, L.Hout, L.Hout, L.Cin, L.Hin, L.Hin, d_in_add, d_in, c.st);
+  }
+  // k x k: stride-1 convolution of (dilated) dconv with the flipped, channel-transposed kernel
+  const __half* src = w.pl_a;
+  long long src_plane = w.pl_a_plane;
+  if (L.stride == 2) {
+    MAED_PROPAGATE(dilate2_planes(w.pl_a, w.pl_a_plane, BT, L.Hout, L.Hout, L.Cout, L.Hin, L.Hin, w.dil, w.dil_plane, c.st));
+    src = w.dil; src_plane = w.dil_plane;
+  }
+  GemmArgs g;
+  g.nsplit = 3;
+  g.A = src; g.a_plane = src_plane; g.B = c.TH(L.tp_off); g.b_plane = tplane;
+  g.M = (int)L.Min(BT); g.N = L.Cin; g.K = L.k * L.k * L.Cout;
+  g.conv = 1; g.n_img = BT; g.H = L.Hin; g.W = L.Hin; g.Cin = L.Cout; g.KH = L.k; g.KW = L.k;
+  g.pad_h = (L.k - 1) - pad_total / 2; g.pad_w = (L.k - 1) - pad_total / 2;
+  g.residual = d_in_add; g.out_mode = OUT_F32; g.out = d_in; g.ldc = L.Cin;
+  return launch_gemm(g, c.st);
+}
+
+int train_backward(const Engine* ep, const void* const* params, const void* packed, const void* tpack, const float* x_in, int N,
+                   int T, void* workspace, size_t workspace_bytes, const float* d_pose6d, const float* d_shape,
+                   const float* d_cam, float loss_scale, float dropout_p, float* const* grads, cudaStream_t st) {
+  MAED_CHECK_ARG(ep && params && packed && tpack && x_in && workspace && d_pose6d && d_shape && d_cam && grads,
+                 "train_backward: null argument");
+  MAED_CHECK_ARG(loss_scale > 0.f, "train_backward: loss_scale must be positive");
+  const Engine& e = *ep;
+  MAED_PROPAGATE(check_train_cfg(e));
+  const EngineConfig& cf = e.cfg;
+  const int BT = N * T;
+  const Net net = build_net(e);
+  TrainWs w;
+  carve(e, net, BT, (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023), w);
+  MAED_CHECK_ARG(w.total + 1024 <= workspace_bytes, "train_backward: workspace too small");
+  const uint8_t* tp = (const uint8_t*)(((uintptr_t)tpack + 1023) & ~(uintptr_t)1023);
+  Ctx c{e, net, w, params, (const uint8_t*)packed, tp, BT, N, T, st, 1.0f / loss_scale, grads, x_in};
+  const int ntok = 197, C = 768, heads = cf.num_heads, HD = cf.hidden_dim;
+  const int rows = BT * ntok;
+  const float scale = 0.125f;
+  const long long CC = (long long)C * C;
+  const bool has_temp = e.i_temp >= 0;
+  float** sm = w.small;
+
+  // ================================================================================ tail (fp32 CUDA cores)
+  // loss scale enters here: every activation gradient below carries it
+  float* dpose = sm[0]; float* dshape = sm[1]; float* dcam = sm[2];
+  MAED_PROPAGATE(scale_f32(d_pose6d, loss_scale, (long long)BT * 144, dpose, st));
+  MAED_PROPAGATE(scale_f32(d_shape, loss_scale, (long long)BT * 10, dshape, st));
+  MAED_PROPAGATE(scale_f32(d_cam, loss_scale, (long long)BT * 3, dcam, st));
+  float* g_total = sm[3];                       // [BT, 144]
+  float* d_base = sm[4];                        // [BT, 192]
+  const float* w_anc = (const float*)(c.pk + e.off_ktd_anc);
+  MAED_PROPAGATE(ktd_tree_bwd(dpose, dshape, dcam, w_anc, BT, g_total, d_base, 192, st));
+  MAED_PROPAGATE(ktd_anc_wgrad(g_total, w.pose_copy, BT, c.inv_ls, w.anc_grad, st));
+  // heads: base[:, 0:144] = h2 Wx^T + b (joint_regs.*.weight[:, :HD]), [144:154] decshape, [154:157] deccam
+  float* d_h2 = sm[5];
+  {
+    // per-joint weight / bias gradients: joint_regs.j.weight = [6, HD + 6k]: first HD columns from dbase^T h2, last 6k from anc_grad
+    int aoff = 0;
+    for (int j = 0; j < 24; ++j) {
+      const int k = kAncCnt[j];
+      float* gw = c.G(e.i_joint0 + 2 * j);
+      const int ldw = HD + 6 * k;
+      MAED_PROPAGATE(sgemm_f32(1, 0, 6, HD, BT, c.inv_ls, d_base + 6 * j, 192, w.h2, HD, 0.f, gw, ldw, st));
+      if (k > 0)
+        MAED_CUDA_CHECK(cudaMemcpy2DAsync(gw + HD, (size_t)ldw * 4, w.anc_grad + aoff, (size_t)6 * k * 4, (size_t)6 * k * 4, 6,
+                                          cudaMemcpyDeviceToDevice, st));
+      MAED_PROPAGATE(colsum_f32(d_base + 6 * j, 192, BT, 6, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_joint0 + 2 * j + 1), st));
+      aoff += 36 * k;
+    }
+    MAED_PROPAGATE(sgemm_f32(1, 0, 10, HD, BT, c.inv_ls, d_base + 144, 192, w.h2, HD, 0.f, c.G(e.i_shape_w), HD, st));
+    MAED_PROPAGATE(colsum_f32(d_base + 144, 192, BT, 10, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_shape_b), st));
+    MAED_PROPAGATE(sgemm_f32(1, 0, 3, HD, BT, c.inv_ls, d_base + 154, 192, w.h2, HD, 0.f, c.G(e.i_cam_w), HD, st));
+    MAED_PROPAGATE(colsum_f32(d_base + 154, 192, BT, 3, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_cam_b), st));
+    // d_h2 = dbase[:, :144] Wx + dbase[:, 144:154] Wshape + dbase[:, 154:157] Wcam
+    const float* wx = (const float*)(c.pk + e.off_ktd_wx);            // [144, HD] fp32 (engine pack)
+    MAED_PROPAGATE(sgemm_f32(0, 0, BT, HD, 144, 1.f, d_base, 192, wx, HD, 0.f, d_h2, HD, st));
+    MAED_PROPAGATE(sgemm_f32(0, 0, BT, HD, 10, 1.f, d_base + 144, 192, c.P(e.i_shape_w), HD, 1.f, d_h2, HD, st));
+    MAED_PROPAGATE(sgemm_f32(0, 0, BT, HD, 3, 1.f, d_base + 154, 192, c.P(e.i_cam_w), HD, 1.f, d_h2, HD, st));
+  }
+  if (dropout_p > 0.f) MAED_PROPAGATE(dropout_bwd(d_h2, (long long)BT * HD, dropout_p, w.mask2, st));
+  // fc2: h2 = h1 W2^T + b2
+  float* d_h1 = sm[6];
+  MAED_PROPAGATE(sgemm_f32(1, 0, HD, HD, BT, c.inv_ls, d_h2, HD, w.h1, HD, 0.f, c.G(e.i_fc2_w), HD, st));
+  MAED_PROPAGATE(colsum_f32(d_h2, HD, BT, HD, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_fc2_b), st));
+  MAED_PROPAGATE(sgemm_f32(0, 0, BT, HD, HD, 1.f, d_h2, HD, c.P(e.i_fc2_w), HD, 0.f, d_h1, HD, st));
+  if (dropout_p > 0.f) MAED_PROPAGATE(dropout_bwd(d_h1, (long long)BT * HD, dropout_p, w.mask1, st));
+  // fc1: h1 = feat W1^T + b1
+  float* d_feat = sm[7];
+  MAED_PROPAGATE(sgemm_f32(1, 0, HD, C, BT, c.inv_ls, d_h1, HD, w.feat_copy, C, 0.f, c.G(e.i_fc1_w), C, st));
+  MAED_PROPAGATE(colsum_f32(d_h1, HD, BT, HD, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_fc1_b), st));
+  MAED_PROPAGATE(sgemm_f32(0, 0, BT, C, HD, 1.f, d_h1, HD, c.P(e.i_fc1_w), C, 0.f, d_feat, C, st));
+  // pre_logits: feat = tanh(cls_ln Wp^T + bp)
+  float* d_pre = sm[0];
+  MAED_PROPAGATE(tanh_bwd(d_feat, w.feat_copy, (long long)BT * C, d_pre, st));
+  MAED_PROPAGATE(sgemm_f32(1, 0, C, C, BT, c.inv_ls, d_pre, C, w.cls_ln, C, 0.f, c.G(e.i_pl_w), C, st));
+  MAED_PROPAGATE(colsum_f32(d_pre, C, BT, C, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_pl_b), st));
+  float* d_cls = sm[1];
+  MAED_PROPAGATE(sgemm_f32(0, 0, BT, C, C, 1.f, d_pre, C, c.P(e.i_pl_w), C, 0.f, d_cls, C, st));
+  // final LayerNorm acts on the cls row of every frame; all other rows of dL/dx_final are zero
+  float* dx = w.fa;                              // residual-stream gradient [rows, C]
+  float* dx2 = w.fb;
+  MAED_CUDA_CHECK(cudaMemsetAsync(dx, 0, (size_t)rows * C * 4, st));
+  MAED_PROPAGATE(layernorm_bwd(d_cls, C, w.x_final, (long long)ntok * C, c.P(e.i_norm), BT, C, 1e-6f, nullptr, dx,
+                               (long long)ntok * C, w.ln_partial, st));
+  const int lnr = ln_bwd_partial_rows();
+  MAED_PROPAGATE(colsum_f32(w.ln_partial, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_norm), st));
+  MAED_PROPAGATE(colsum_f32(w.ln_partial + C, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_norm + 1), st));
+
+  // ====================================================================================== STE blocks
+  for (int i = cf.num_blocks - 1; i >= 0; --i) {
+    const Engine::SteIdx& ix = e.blk[i];
+    const SteTape& t = w.ste[i];
+    const Net::SteT& tt = net.ste[i];
+    // ---- MLP: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))));  dx = dL/dx_out
+    MAED_PROPAGATE(split_f32(dx, w.pl_a, w.pl_a_plane, (long long)rows * C, st));                       // d_y2 planes
+    MAED_PROPAGATE(colsum_f32(dx, C, rows, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.fc2_b), st));
+    MAED_PROPAGATE(linear_wgrad(c, w.pl_a, w.pl_a_plane, C, t.hid, w.hid_plane, 4 * C, rows, 0, c.G(ix.fc2_w)));
+    MAED_PROPAGATE(gemm_plain(c, w.pl_a, w.pl_a_plane, rows, C, c.TH(tt.fc2), 4 * CC, 4 * C, nullptr, ACT_NONE, nullptr, OUT_F32,
+                              w.big, 0));                                                                 // d_hid
+    MAED_PROPAGATE(gelu_bwd(w.big, t.h_pre, (long long)rows * 4 * C, w.pl_a, w.pl_a_plane, st));         // d_pre planes
+    MAED_PROPAGATE(colsum_planes(w.pl_a, w.pl_a_plane, 4 * C, rows, 4 * C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.fc1_b), st));
+    MAED_PROPAGATE(linear_wgrad(c, w.pl_a, w.pl_a_plane, 4 * C, t.ln2, w.ln_plane, C, rows, 0, c.G(ix.fc1_w)));
+    MAED_PROPAGATE(gemm_plain(c, w.pl_a, w.pl_a_plane, rows, 4 * C, c.TH(tt.fc1), 4 * CC, C, nullptr, ACT_NONE, nullptr, OUT_F32,
+                              dx2, 0));                                                                   // d_ln2
+    MAED_PROPAGATE(layernorm_bwd(dx2, C, t.x_mid, C, c.P(ix.n2), rows, C, 1e-6f, dx, dx, C, w.ln_partial, st));   // dx = d_xmid
+    MAED_PROPAGATE(colsum_f32(w.ln_partial, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.n2), st));
+    MAED_PROPAGATE(colsum_f32(w.ln_partial + C, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.n2 + 1), st));
+    // ---- attention: x_mid = x_in + proj(ao)
+    MAED_PROPAGATE(split_f32(dx, w.pl_a, w.pl_a_plane, (long long)rows * C, st));
+    MAED_PROPAGATE(colsum_f32(dx, C, rows, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.proj_b), st));
+    MAED_PROPAGATE(linear_wgrad(c, w.pl_a, w.pl_a_plane, C, t.ao, w.ln_plane, C, rows, 0, c.G(ix.proj_w)));
+    float* d_ao = dx2;
+    MAED_PROPAGATE(gemm_plain(c, w.pl_a, w.pl_a_plane, rows, C, c.TH(tt.proj), CC, C, nullptr, ACT_NONE, nullptr, OUT_F32, d_ao, 0));
+    float* dqkv = w.big;                           // [rows, 3C] fp32
+    if (cf.mode == MODE_PARALLEL) {
+      float* d_logits = sm[2]; float* d_pool = sm[3];
+      MAED_PROPAGATE(blend_bwd(d_ao, t.xs, t.xt, t.logits, BT, ntok, C, d_logits, w.dxs, w.dxt, st));
+      MAED_PROPAGATE(sgemm_f32(1, 0, 2 * C, 2 * C, BT, c.inv_ls, d_logits, 2 * C, t.pooled, 2 * C, 0.f, c.G(ix.ts_w), 2 * C, st));
+      MAED_PROPAGATE(colsum_f32(d_logits, 2 * C, BT, 2 * C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.ts_b), st));
+      MAED_PROPAGATE(sgemm_f32(0, 0, BT, 2 * C, 2 * C, 1.f, d_logits, 2 * C, c.P(ix.ts_w), 2 * C, 0.f, d_pool, 2 * C, st));
+      MAED_PROPAGATE(blend_bwd_pool(d_pool, BT, ntok, C, w.dxs, w.dxt, st));
+      MAED_PROPAGATE(attn_spatial_bwd(t.qkv, w.qkv_plane, w.dxs, BT, ntok, heads, scale, 0, dqkv, st));
+      MAED_PROPAGATE(attn_temporal_bwd(t.qkv, w.qkv_plane, w.dxt, N, T, ntok, heads, scale, 1, dqkv, st));
+    } else if (cf.mode == MODE_SERIES) {
+      // ao = temporal(qkv2), qkv2 = qkv(ao_s), ao_s = spatial(qkv), qkv = qkv(ln1): the qkv weights are used twice
+      MAED_PROPAGATE(attn_temporal_bwd(t.qkv2, w.qkv_plane, d_ao, N, T, ntok, heads, scale, 0, dqkv, st));
+      MAED_PROPAGATE(split_f32(dqkv, w.pl_a, w.pl_a_plane, (long long)rows * 3 * C, st));
+      MAED_PROPAGATE(colsum_f32(dqkv, 3 * C, rows, 3 * C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.qkv_b), st));
+      MAED_PROPAGATE(linear_wgrad(c, w.pl_a, w.pl_a_plane, 3 * C, t.ao_s, w.ln_plane, C, rows, 0, c.G(ix.qkv_w)));
+      MAED_PROPAGATE(gemm_plain(c, w.pl_a, w.pl_a_plane, rows, 3 * C, c.TH(tt.qkv), 3 * CC, C, nullptr, ACT_NONE, nullptr, OUT_F32,
+                                w.dxs, 0));                                                               // d_ao_s
+      MAED_PROPAGATE(attn_spatial_bwd(t.qkv, w.qkv_plane, w.dxs, BT, ntok, heads, scale, 0, dqkv, st));
+    } else {
+      MAED_PROPAGATE(attn_spatial_bwd(t.qkv, w.qkv_plane, d_ao, BT, ntok, heads, scale, 0, dqkv, st));
+    }
+    const int acc = cf.mode == MODE_SERIES ? 1 : 0;
+    MAED_PROPAGATE(split_f32(dqkv, w.pl_a, w.pl_a_plane, (long long)rows * 3 * C, st));
+    MAED_PROPAGATE(colsum_f32(dqkv, 3 * C, rows, 3 * C, c.inv_ls, acc, w.colsum_scratch, c.G(ix.qkv_b), st));
+    MAED_PROPAGATE(linear_wgrad(c, w.pl_a, w.pl_a_plane, 3 * C, t.ln1, w.ln_plane, C, rows, acc, c.G(ix.qkv_w)));
+    MAED_PROPAGATE(gemm_plain(c, w.pl_a, w.pl_a_plane, rows, 3 * C, c.TH(tt.qkv), 3 * CC, C, nullptr, ACT_NONE, nullptr, OUT_F32,
+                              dx2, 0));                                                                   // d_ln1
+    MAED_PROPAGATE(layernorm_bwd(dx2, C, t.x_in, C, c.P(ix.n1), rows, C, 1e-6f, dx, dx, C, w.ln_partial, st));    // dx = d_xin
+    MAED_PROPAGATE(colsum_f32(w.ln_partial, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.n1), st));
+    MAED_PROPAGATE(colsum_f32(w.ln_partial + C, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.n1 + 1), st));
+  }
+
+  // ================================================================================== patch embedding
+  // x0[bt, 0] = cls + pos[0] (+ temp[t]);  x0[bt, 1+i] = tok[bt, i] + pos[1+i] (+ temp[t])
+  MAED_PROPAGATE(colsum_f32(dx, (long long)ntok * C, BT, ntok * C, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_pos), st));
+  MAED_CUDA_CHECK(cudaMemcpyAsync(c.G(e.i_cls), c.G(e.i_pos), (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
+  if (has_temp) {
+    float* tsum = sm[0];                                   // [BT, C] sum over the tokens of each frame
+    MAED_PROPAGATE(token_sum(dx, BT, ntok, C, tsum, st));
+    MAED_PROPAGATE(colsum_f32(tsum, (long long)T * C, N, T * C, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_temp), st));
+    if (T < cf.temp_frames)
+      MAED_CUDA_CHECK(cudaMemsetAsync(c.G(e.i_temp) + (size_t)T * C, 0, (size_t)(cf.temp_frames - T) * C * 4, st));
+  }
+  // d_tok [BT*196, C]: rows 1..196 of every frame
+  const int trow = BT * 196;
+  // compact the token rows (drops the cls row of every frame)
+  MAED_CUDA_CHECK(cudaMemcpy2DAsync(dx2, (size_t)196 * C * 4, dx + C, (size_t)ntok * C * 4, (size_t)196 * C * 4, BT,
+                                    cudaMemcpyDeviceToDevice, st));
+  MAED_PROPAGATE(split_f32(dx2, w.pl_a, w.pl_a_plane, (long long)trow * C, st));
+  MAED_PROPAGATE(colsum_f32(dx2, C, trow, C, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_proj_b), st));
+  const int last = (int)net.L.size() - 1;
+  MAED_PROPAGATE(linear_wgrad(c, w.pl_a, w.pl_a_plane, C, w.out[last], w.out_plane[last], 1024, trow, 0, c.G(e.i_proj_w)));
+  float* d_out = w.fc;                                     // gradient w.r.t. the stage-2 output [BT*196, 1024]
+  MAED_PROPAGATE(gemm_plain(c, w.pl_a, w.pl_a_plane, trow, C, c.TH(net.tp_proj), 768LL * 1024, 1024, nullptr, ACT_NONE, nullptr,
+                            OUT_F32, d_out, 0));
+
+  // ========================================================================================= backbone
+  // free fp32 buffers: fa, fb, fd (+ fc holding d_out).  Roles per bottleneck: g (= d_out), d_short, d_t2, d_t1.
+  float* bufs[4] = {w.fc, w.fa, w.fb, w.fd};
+  for (int b = (int)net.B.size() - 1; b >= 0; --b) {
+    const BlockL& bl = net.B[b];
+    float* g = bufs[0]; float* d_short = bufs[1]; float* d_t2 = bufs[2]; float* d_t1 = bufs[3];
+    const ConvL& L3 = net.L[bl.c3];
+    const ConvL& L2 = net.L[bl.c2];
+    const ConvL& L1 = net.L[bl.c1];
+    MAED_PROPAGATE(relu_mask_f32(g, w.out[bl.c3], L3.Mout(BT) * L3.Cout, st));
+    const float* shortcut_grad = g;
+    float* d_xin = g;
+    if (bl.ds >= 0) {
+      MAED_PROPAGATE(conv_layer_bwd(c, bl.ds, g, nullptr, d_short, d_t2));
+      shortcut_grad = d_short;
+      d_xin = d_short;
+    }
+    MAED_PROPAGATE(conv_layer_bwd(c, bl.c3, g, nullptr, d_t2, nullptr));
+    MAED_PROPAGATE(relu_mask_f32(d_t2, w.out[bl.c2], L2.Mout(BT) * L2.Cout, st));
+    MAED_PROPAGATE(conv_layer_bwd(c, bl.c2, d_t2, nullptr, d_t1, nullptr));
+    MAED_PROPAGATE(relu_mask_f32(d_t1, w.out[bl.c1], L1.Mout(BT) * L1.Cout, st));
+    MAED_PROPAGATE(conv_layer_bwd(c, bl.c1, d_t1, shortcut_grad, d_xin, nullptr));
+    if (bl.ds >= 0) std::swap(bufs[0], bufs[1]);            // the block-input gradient now lives in d_short's buffer
+  }
+  // stem: max-pool + ReLU + GroupNorm + conv (no data gradient: the input frames need none)
+  float* d_pool = bufs[0];
+  float* d_y = bufs[1];
+  MAED_PROPAGATE(maxpool_gn_relu_bwd(d_pool, w.pool_idx, w.convout[0], w.stats[0], c.P(e.i_stem_g), c.P(e.i_stem_g + 1), BT, 112,
+                                     112, 64, 1e-5f, d_y, st));
+  MAED_PROPAGATE(conv_layer_bwd(c, 0, d_y, nullptr, nullptr, nullptr));
+  return MAED_OK;
+}
+
+}  // namespace maed
