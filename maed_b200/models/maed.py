@@ -6,7 +6,8 @@ CUDA: tcgen05/TMA GEMMs and attention, fused norm kernels) through one C-ABI cal
 
 Differences a caller can observe (documented in INTEGRATION.md):
   * inputs must be CUDA float32 tensors — there is no CPU / eager fallback, by design;
-  * `forward` is inference-only in this round (outputs carry no autograd graph);
+  * `forward` is inference-only unless `enable_training()` is called (the CUDA training path of maed_b200/train.py
+    is written but not yet validated on a GPU; opt-in until then);
   * `encoder='cnn'` (torchvision ResNet-50, stage-1 config) is not built yet -> NotImplementedError;
   * `decoder.smpl.*` buffers do not exist (smplx and the SMPL assets are absent): `verts`/`kp_3d` are zeros.
 """
@@ -59,6 +60,9 @@ class MAED(nn.Module):
         self._packed_key = None
         self._workspace = None
         self._param_ptrs = None
+        self._training_enabled = False
+        self._train_dropout_p = None
+        self._train_state = None
 
     # ------------------------------------------------------------------------------------------ engine
     def _get_engine(self):
@@ -166,18 +170,32 @@ class MAED(nn.Module):
         N, T = x.shape[:2]
         return self._run(x)["feat"].reshape(N, T, -1)
 
-    @torch.no_grad()
+    def enable_training(self, flag=True, dropout_p=None):
+        """Route train()-mode forwards (with autograd enabled) through the engine's training path
+        (maed_b200/train.py: saved-activation tape + CUDA backward).  Opt-in while that path awaits its GPU validation;
+        the environment variable MAED_B200_TRAINING=1 enables it for every model."""
+        self._training_enabled = bool(flag)
+        self._train_dropout_p = dropout_p       # None: nn.Dropout() default 0.5 (ktd.py:54-56); 0.0 for parity runs
+        return self
+
     def forward(self, x, J_regressor=None, **kwargs):
         """reference maed.py:52-66.  `J_regressor` (17x6890) only matters once the SMPL tier exists: with the
         placeholder body model verts are zeros, so J_regressor @ verts is zeros as well."""
-        N, T = x.shape[:2]
-        if self.training and any(p.requires_grad for p in self.parameters()) and kwargs.get("_allow_train_mode") is None:
+        wants_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if wants_grad and kwargs.get("_allow_train_mode") is None:
+            if getattr(self, "_training_enabled", False) or os.environ.get("MAED_B200_TRAINING"):
+                from .. import train as _train
+                return _train.train_forward(self, x, J_regressor)
             import warnings
-            warnings.warn("maed_b200.MAED.forward is inference-only in this version: outputs carry no autograd graph and "
-                          "train()-mode dropout (reference ktd.py:54-56) is not applied; call .eval() for inference.",
-                          RuntimeWarning, stacklevel=2)
+            warnings.warn("maed_b200.MAED.forward is inference-only unless enable_training() was called: outputs carry no "
+                          "autograd graph and train()-mode dropout (reference ktd.py:54-56) is not applied; call .eval() "
+                          "for inference.", RuntimeWarning, stacklevel=2)
+        with torch.no_grad():
+            return self._forward_inference(x, J_regressor, **kwargs)
+
+    def _forward_inference(self, x, J_regressor=None, **kwargs):
+        N, T = x.shape[:2]
         o = self._run(x, want_taps=kwargs.get("_taps"))
-        BT = N * T
         nj = 17 if J_regressor is not None else self.decoder.smpl.n_joints
         kp2d = o["kp_2d"] if nj == o["kp_2d"].shape[1] else o["kp_2d"][:, :nj].contiguous()
         out = {

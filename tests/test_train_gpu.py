@@ -1,0 +1,147 @@
+"""Model-level tests of the training path: tape forward == inference forward, parameter gradients against the
+reference's gradient digests (tests/golden/grads_*.npz) and against oracle autograd on fresh inputs, Adam, a short fit.
+
+Written at the end of round 1 after the GPU budget was spent: NOT yet run on a B200, therefore skipped unless
+MAED_B200_TRAIN_TESTS=1 (round 2 starts by running them)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_DIR, rel_err, state_dict_of
+from oracle import maed_oracle as O
+from oracle import synth
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
+                                 reason="training path not yet validated on a GPU (set MAED_B200_TRAIN_TESTS=1)")]
+
+GRAD_CASES = ["grads_vanilla_ktd", "grads_series_ktd", "grads_parallel_ktd"]
+
+
+def _model(mode, seed, lib):
+    from maed_b200.models import MAED
+    m = MAED("ste", 6, 12, mode, "ktd", 1024)
+    synth.fill_module_(m, seed)
+    return m.cuda().train().enable_training(True, dropout_p=0.0)
+
+
+def _probes(nt, seed):
+    return [synth.synth_tensor("grad_probe.%s" % k, (nt, n), seed).cuda() for k, n in (("pose", 144), ("shape", 10), ("cam", 3))]
+
+
+def _loss(out, A, B, C_):
+    d = out["_debug"]
+    return (d["pose6d"] * A).sum() + (d["shape"] * B).sum() + (d["cam"] * C_).sum()
+
+
+def _digest(g, nsamp=8):
+    g = g.detach().double().reshape(-1).cpu()
+    idx = np.unique(np.linspace(0, g.numel() - 1, nsamp).round().astype(np.int64))
+    return g.norm().item(), g[torch.from_numpy(idx)].numpy()
+
+
+@pytest.mark.parametrize("mode", ["vanilla", "series", "parallel"])
+def test_tape_forward_matches_inference(lib, mode):
+    m = _model(mode, 21, lib)
+    x = synth.synth_frames(1, 3, 21).cuda()
+    out = m(x)
+    with torch.no_grad():
+        ref = m.eval()(x, _debug=True)
+    for k in ("pose6d", "shape", "cam"):
+        assert rel_err(out["_debug"][k], ref["_debug"][k]) < 1e-5, k
+    assert rel_err(out["theta"], ref["theta"]) < 1e-4 and rel_err(out["rotmat"], ref["rotmat"]) < 1e-5
+    assert out["theta"].requires_grad
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_gradients_match_reference_digests(lib, name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    N, T, seed = [int(v) for v in z["meta"]]
+    m = _model(str(z["mode"]), seed, lib)
+    A, B, C_ = _probes(N * T, seed)
+    loss = _loss(m(synth.synth_frames(N, T, seed).cuda()), A, B, C_)
+    assert abs(loss.item() - float(z["loss"])) < 1e-3 * max(1.0, abs(float(z["loss"])))
+    loss.backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    worst = ("", 0.0)
+    for k in [str(s) for s in z["names"]]:
+        assert grads.get(k) is not None, "no gradient for %s" % k
+        norm, samp = _digest(grads[k])
+        ref_norm, ref_samp = float(z["g_stats/" + k][0]), z["g_samp/" + k]
+        err = abs(norm - ref_norm) / max(ref_norm, 1e-12)
+        rms = ref_norm / np.sqrt(grads[k].numel())
+        serr = np.abs(samp - ref_samp).max() / max(rms, 1e-20)
+        if max(err, serr / 50) > worst[1]:
+            worst = (k, max(err, serr / 50))
+        assert err < 5e-3, "%s: |g| %.6e vs reference %.6e" % (k, norm, ref_norm)
+        assert serr < 0.25, "%s: sampled entries off by %.3f rms" % (k, serr)
+    print("%s: worst %s %.2e" % (name, worst[0], worst[1]))
+
+
+def test_gradients_match_oracle_autograd(lib):
+    """Every entry of every parameter gradient against autograd over the CPU oracle (parallel mode, 2 clips x 2 frames)."""
+    seed, N, T = 33, 2, 2
+    m = _model("parallel", seed, lib)
+    A, B, C_ = _probes(N * T, seed)
+    x = synth.synth_frames(N, T, seed)
+    _loss(m(x.cuda()), A, B, C_).backward()
+    sd = {k: v.cpu() for k, v in state_dict_of(m).items()}
+    _, ref, _ = O.maed_param_grads(x, sd, A.cpu(), B.cpu(), C_.cpu(), "parallel", "ktd")
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        e = rel_err(p.grad, ref[k])
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < 5e-3, "%s: relative gradient error %.3e" % (k, e)
+    print("worst parameter-gradient error vs oracle autograd: %s %.2e" % worst)
+
+
+def test_loss_scale_invariance_and_determinism(lib):
+    m = _model("vanilla", 5, lib)
+    x = synth.synth_frames(1, 2, 5).cuda()
+    A, B, C_ = _probes(2, 5)
+    gs = []
+    for scale in (4096.0, 4096.0, 256.0):
+        m.zero_grad(set_to_none=True)
+        out = m(x)
+        m._train_state.loss_scale = scale
+        _loss(out, A, B, C_).backward()
+        gs.append(torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone())
+    assert torch.equal(gs[0], gs[1])                       # bit-reproducible
+    assert rel_err(gs[2], gs[0]) < 1e-3
+
+
+def test_fused_adam_matches_torch_adam(lib):
+    from maed_b200.train import FusedAdam
+    m1, m2 = _model("vanilla", 6, lib), _model("vanilla", 6, lib)
+    x = synth.synth_frames(1, 2, 6).cuda()
+    A, B, C_ = _probes(2, 6)
+    o1 = FusedAdam.for_model(m1, lr=1e-4, weight_decay=1e-5)
+    o2 = torch.optim.Adam([{"params": p, "name": n} for n, p in m2.named_parameters()], lr=1e-4, weight_decay=1e-5)
+    for _ in range(2):
+        for m, o in ((m1, o1), (m2, o2)):
+            o.zero_grad(set_to_none=True)
+            _loss(m(x), A, B, C_).backward()
+            o.step()
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert rel_err(a, b) < 1e-5, k
+
+
+def test_short_fit_reduces_loss(lib):
+    """A few Adam steps on one synthetic batch with the reference's parameter-space losses (theta MSE) must go down."""
+    from maed_b200.train import FusedAdam
+    m = _model("parallel", 7, lib)
+    x = synth.synth_frames(1, 4, 7).cuda()
+    target = torch.zeros(1, 4, 85, device="cuda")
+    target[..., 0] = 1.0
+    opt = FusedAdam.for_model(m, lr=1e-4)
+    losses = []
+    for _ in range(5):
+        opt.zero_grad(set_to_none=True)
+        loss = ((m(x)["theta"] - target) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0], losses
