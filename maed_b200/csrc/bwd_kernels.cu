@@ -16,7 +16,9 @@ __global__ void transpose_planes_kernel(const __half* __restrict__ in, long long
   __shared__ __half th[64][66];
   __shared__ __half tl[64][66];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
-  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int c0 = blockIdx.x * 64;
+  for (int r0 = blockIdx.y * 64; r0 < R; r0 += gridDim.y * 64) {
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int r = r0 + ty + 8 * k;
@@ -46,13 +48,14 @@ __global__ void transpose_planes_kernel(const __half* __restrict__ in, long long
       }
     }
   }
+  }
 }
 int transpose_planes(const __half* in_hi, long long in_plane, int R, int C, int ld_in, __half* out_hi, long long out_plane,
                      int ld_out, cudaStream_t st) {
   MAED_CHECK_ARG(R > 0 && C > 0 && ld_in >= C && ld_out >= R, "transpose_planes: bad shape R=%d C=%d ld_in=%d ld_out=%d", R, C,
                  ld_in, ld_out);
-  transpose_planes_kernel<<<dim3(cdiv(C, 64), cdiv(R, 64)), 256, 0, st>>>(in_hi, in_plane, R, C, ld_in, out_hi, out_plane,
-                                                                          ld_out);
+  const int row_blocks = cdiv(R, 64) < 32768 ? cdiv(R, 64) : 32768;      // the kernel strides over further row tiles
+  transpose_planes_kernel<<<dim3(cdiv(C, 64), row_blocks), 256, 0, st>>>(in_hi, in_plane, R, C, ld_in, out_hi, out_plane, ld_out);
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
 }
