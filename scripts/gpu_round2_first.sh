@@ -1,0 +1,16 @@
+#!/bin/bash
+# First GPU call of round 2: (1) the validated suite must still be green, (2) run the unvalidated training-path tests and
+# keep their full logs, (3) re-capture the in-step ncu numbers of the spatial attention kernel (fp32 TMA-store epilogue).
+mkdir -p gpurun_out
+echo "=== validated suite"; timeout 900 python -m pytest -q -m gpu --timeout 300 tests > gpurun_out/tests.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/tests.log
+export MAED_B200_TRAIN_TESTS=1
+echo "=== backward kernels"; timeout 900 python -m pytest -q -m gpu --timeout 300 tests/test_bwd_ops_gpu.py > gpurun_out/bwd_ops.log 2>&1; echo "exit $?"
+grep -E "passed|failed|^FAILED|^ERROR" gpurun_out/bwd_ops.log | tail -n 45
+echo "=== training path"; timeout 1200 python -m pytest -q -m gpu --timeout 600 -s tests/test_train_gpu.py > gpurun_out/train.log 2>&1; echo "exit $?"
+grep -E "passed|failed|^FAILED|^ERROR|worst" gpurun_out/train.log | tail -n 30
+unset MAED_B200_TRAIN_TESTS
+M=sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum
+timeout 400 ncu --metrics $M --clock-control none -k regex:attn_spatial -s 12 -c 3 --csv --log-file gpurun_out/attn_inbench.csv \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/attn_inbench.log 2>&1; echo "ncu exit $?"
+grep -E "attn_spatial" gpurun_out/attn_inbench.csv | awk -F'","' '{print $(NF-2), $(NF-1), $NF}' | tail -n 6
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cut -c1-300 gpurun_out/bench.json
