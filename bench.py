@@ -190,6 +190,109 @@ def time_dominant_gemm(dev, reps=20):
     return 2.0 * M * N * K / 1e12, ms
 
 
+def run_train(args):
+    """BASELINE configs[2]/[3]: bs = 8 clips x T = 16 per GPU, forward + backward + Adam, random init, synthetic clips;
+    N > 1: one all-reduce of the flat gradient buffer per step (data parallel over clips).  The loss is the reference's
+    parameter-space terms on theta (MSE), the keypoint terms need the SMPL tier.  NOTE: the training path was written
+    after round 1's GPU budget; this mode is not part of the driver's default metric."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --mode train: no CUDA device")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    from maed_b200 import build, ops, train
+    from maed_b200.models import MAED
+    from oracle import synth
+    build.build()
+    st_mode = args.st_mode or MODE
+    torch.manual_seed(0)
+    model = MAED("ste", 6, 12, st_mode, DECODER, 1024).to(dev).train().enable_training(True)
+    opt = train.FusedAdam.for_model(model, lr=1e-4, weight_decay=1e-5)          # configs/config_stage2.yaml:63-66
+    xs = [synth.synth_frames(CLIPS_PER_GPU, T, 300 + i).to(dev) for i in range(4)]
+    target = torch.zeros(CLIPS_PER_GPU, T, 85, device=dev)
+    target[..., 0] = 1.0
+    h_loss = torch.empty(1).pin_memory()
+
+    def step(x):
+        opt.zero_grad(set_to_none=True)
+        loss = ((model(x)["theta"] - target) ** 2).mean()
+        loss.backward()
+        if dist:
+            train.allreduce_gradients(model, world)
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        step(xs[i % 4])
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    if sampler:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(xs[i % 4])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * CLIPS_PER_GPU * args.steps / (ms_total / 1000.0)
+    # end to end: pinned host frames -> H2D -> train step -> D2H of the loss, every step
+    hx = [synth.synth_frames(CLIPS_PER_GPU, T, 400 + i).pin_memory() for i in range(2)]
+    dxb = torch.empty_like(xs[0])
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        dxb.copy_(hx[i % 2], non_blocking=True)
+        h_loss.copy_(step(dxb).detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1000.0], device=dev)
+    if dist:
+        dist.barrier()
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        step_tflops = 3.0 * CLIPS_PER_GPU * GFLOP_PER_CLIP / 1000.0 / (ms_total / args.steps / 1000.0)
+        print(json.dumps({
+            "metric": "clips/sec (T=16, 224x224, bs=8/gpu), MAED ste-%s+ktd train step (fwd+bwd+Adam)" % st_mode,
+            "mode": "train", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 hi/lo split operands for forward, data- and weight-gradient GEMMs; fp32 reductions / Adam",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: 1xB200 bs=8 T=16 train step (fwd+bwd+Adam), random-init",
+                       "clips_per_gpu": CLIPS_PER_GPU, "seq_len": T, "st_mode": st_mode, "decoder": DECODER,
+                       "loss": "MSE on theta (the reference's parameter-space terms; keypoint terms need the SMPL tier)",
+                       "parallelism": "data parallel x%d, one all-reduce of the flat gradient buffer per step" % world},
+            "clocks": clocks, "gpu_launches": int(launches), "final_loss": float(loss.item()),
+            "e2e": {"value": world * CLIPS_PER_GPU * args.steps / (float(e2e_ms.item()) / 1000.0), "unit": "clips/s",
+                    "h2d_bytes_per_step": xs[0].numel() * 4, "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf, "peak_source": peak_src,
+                         "achieved": step_tflops, "frac": step_tflops / peak_tf, "traffic": None,
+                         "note": "whole step, algorithmic FLOPs = 3 x forward (SURVEY.md 8d)"},
+        }))
+    if dist:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,10 +300,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="maed_b200", choices=["maed_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward: BASELINE configs[1] (the driver's metric); train: configs[2] fwd+bwd+Adam (opt-in)")
+    ap.add_argument("--st-mode", default=None, help="train mode only: parallel (default) or series")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "train":
+        return run_train(args)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
