@@ -1,4 +1,6 @@
 // Host side of the tcgen05 GEMM: tensor-map construction, tile-shape choice, launch.
+#include <stdlib.h>
+
 #include "gemm_host.h"
 
 #include <mutex>
@@ -104,24 +106,25 @@ static int choose_block_n(long long m_tiles, int N, int force) {
   return best_bn;
 }
 
-template <int BN>
-static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t st) {
+template <int BN, bool TMA_EPI>
+static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmParams& p, cudaStream_t st) {
   const int nplanes = p.nsplit == 3 ? 2 : 1;
   const size_t stage_bytes = (size_t)nplanes * (kBlockM * kBlockK * 2 + BN * kBlockK * 2);
-  const size_t budget = 232448 - 1024 - 512;
+  const size_t epi_bytes = TMA_EPI ? kEpiStageBytes : 0;
+  const size_t budget = 232448 - 1024 - 512 - epi_bytes;
   int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) { set_error("gemm: tile too large for shared memory"); return MAED_ERR_UNSUPPORTED; }
   p.stages = stages;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
+  const size_t smem = 1024 + epi_bytes + (size_t)stages * stage_bytes + 512;
   static bool attr_set = false;
   if (!attr_set) {
-    MAED_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    MAED_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, TMA_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const long long tiles = (long long)p.m_tiles * p.n_tiles;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  gemm_tc_kernel<BN><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN, TMA_EPI><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmO, p);
   MAED_CUDA_CHECK(cudaGetLastError());
   return MAED_OK;
 }
@@ -176,9 +179,31 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     const uint32_t box[3] = {64, (uint32_t)bn, 1};
     MAED_PROPAGATE(make_tmap_f16(&tmB, g.B, 3, dims, str, box));
   }
-  if (bn == 256) return launch_bn<256>(tmA, tmB, p, st);
-  if (bn == 128) return launch_bn<128>(tmA, tmB, p, st);
-  return launch_bn<64>(tmA, tmB, p, st);
+  // opt-in TMA-store epilogue (MAED_B200_GEMM_TMA_EPI=1): plain mode, 16-byte aligned output rows
+  static const bool tma_epi_on = getenv("MAED_B200_GEMM_TMA_EPI") != nullptr;
+  const bool split_out = g.out_mode == OUT_F16_SPLIT;
+  const bool tma_epi = tma_epi_on && !g.conv && g.out != nullptr && (reinterpret_cast<uintptr_t>(g.out) & 15) == 0 &&
+                       (g.out_mode == OUT_F32 ? (p.ldc % 4 == 0) : (p.ldc % 8 == 0)) && (!split_out || g.out_plane % 8 == 0);
+  CUtensorMap tmO = tmB;
+  if (tma_epi) {
+    if (g.out_mode == OUT_F32) {      // fp32 [M, ldc] described as 16-bit elements: 2N columns, 64-wide (= 32 floats) boxes
+      const uint64_t dims[3] = {(uint64_t)g.N * 2, (uint64_t)g.M, 1};
+      const uint64_t str[2] = {(uint64_t)p.ldc * 4, (uint64_t)g.M * p.ldc * 4};
+      const uint32_t box[3] = {64, 128, 1};
+      MAED_PROPAGATE(make_tmap_f16(&tmO, g.out, 3, dims, str, box, 128));
+    } else {
+      const uint64_t dims[3] = {(uint64_t)g.N, (uint64_t)g.M, (uint64_t)(split_out ? 2 : 1)};
+      const uint64_t str[2] = {(uint64_t)p.ldc * 2, (uint64_t)(split_out ? g.out_plane : (long long)g.M * p.ldc) * 2};
+      const uint32_t box[3] = {32, 128, 1};
+      MAED_PROPAGATE(make_tmap_f16(&tmO, g.out, 3, dims, str, box, 64));
+    }
+    if (bn == 256) return launch_bn<256, true>(tmA, tmB, tmO, p, st);
+    if (bn == 128) return launch_bn<128, true>(tmA, tmB, tmO, p, st);
+    return launch_bn<64, true>(tmA, tmB, tmO, p, st);
+  }
+  if (bn == 256) return launch_bn<256, false>(tmA, tmB, tmO, p, st);
+  if (bn == 128) return launch_bn<128, false>(tmA, tmB, tmO, p, st);
+  return launch_bn<64, false>(tmA, tmB, tmO, p, st);
 }
 
 }  // namespace maed

@@ -47,10 +47,48 @@ static constexpr int kBlockK = 64;
 static constexpr int kGemmThreads = 256;
 static constexpr int kMaxStages = 8;
 
-template <int BLOCK_N>
+// out = act(acc + bias) + residual for one row x 32 columns
+__device__ __forceinline__ void epilogue_math(float (&v)[32], const uint32_t (&r)[32], const GemmParams& p, int col0,
+                                              long long out_row) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
+  } else if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (p.act == ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+  }
+  if (p.residual) {
+    const float4* rp = reinterpret_cast<const float4*>(p.residual + out_row * p.ldc + col0);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = rp[j >> 2];
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+}
+
+// TMA_EPI = true (opt-in: MAED_B200_GEMM_TMA_EPI=1, plain mode only): the epilogue stages every 128 x 32 output chunk in
+// shared memory (swizzled like the output tensor map) and one thread writes it with a TMA store, instead of 16-byte
+// row-per-thread global stores.  Same arithmetic.  Added (not yet measured) after the spatial-attention kernel gained 20 %
+// from the same change (profiles/README.md); the default instantiation keeps the original epilogue.
+static constexpr uint32_t kEpiStageBytes = 2 * 16384;       // two 16 KB staging buffers (TMA_EPI only)
+
+template <int BLOCK_N, bool TMA_EPI = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   using namespace sm100;
   constexpr int kAccStages = (2 * BLOCK_N <= 512) ? 2 : 1;
   constexpr int kTmemCols = (kAccStages * BLOCK_N <= 32) ? 32 : (kAccStages * BLOCK_N <= 64) ? 64
@@ -59,7 +97,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic ST/LD)
+  uint8_t* smem0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic ST/LD)
+  uint8_t* smem = smem0 + (TMA_EPI ? kEpiStageBytes : 0u);                          // pipeline stages stay 1024-byte aligned
   const int nplanes = (p.nsplit == 3) ? 2 : 1;
   const uint32_t stage_bytes = nplanes * (kABytes + kBBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
@@ -173,6 +212,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row_in_tile = ew * 32 + lane_id();
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t epi_chunk = 0;                                 // TMA_EPI: staging buffer = chunk counter & 1
+    (void)epi_chunk;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
       long long out_row;
@@ -198,57 +239,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_32x32b_x32(t_row + c0, r);
         tmem_ld_wait();
         const int col0 = n_tile * BLOCK_N + c0;
-        if (row_ok && col0 < p.N) {                        // N is a multiple of 32 for every MAED layer
+        if constexpr (TMA_EPI) {
+          // every epilogue thread takes part in the barriers; rows / columns outside the matrix are clipped by the TMA store
           float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (p.act == ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
-          } else if (p.act == ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-          } else if (p.act == ACT_TANH) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-          }
-          if (p.residual) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + out_row * p.ldc + col0);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = rp[j >> 2];
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (p.out_mode == OUT_F32) {
-            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_row * p.ldc + col0);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) op[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (row_ok && col0 < p.N) {
+            epilogue_math(v, r, p, col0, out_row);
           } else {
-            __half* oh = static_cast<__half*>(p.out) + out_row * p.ldc + col0;
-            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const __half2 h2 = __floats2half2_rn(v[j], v[j + 1]);
-              const float2 hf = __half22float2(h2);
-              const __half2 l2 = __floats2half2_rn(v[j] - hf.x, v[j + 1] - hf.y);
-              hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-              lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          const int epi_tid = threadIdx.x - 128;
+          uint8_t* stg = smem0 + (epi_chunk & 1) * 16384;
+          ++epi_chunk;
+          if (epi_tid == 0) tma_store_wait_read<1>();        // the store issued two chunks ago has left this buffer
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (p.out_mode == OUT_F32) {                       // 128 rows x 128 B, 128-byte swizzle
+            uint8_t* rowp = stg + row_in_tile * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rowp + ((j ^ (row_in_tile & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {                                           // hi (and lo at +8192): 128 rows x 64 B, 64-byte swizzle
+            uint8_t* rowp = stg + row_in_tile * 64;
+            const uint32_t sw = (row_in_tile >> 1) & 3;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const __half2 h2 = __floats2half2_rn(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]);
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(v[q * 8 + 2 * k] - hf.x, v[q * 8 + 2 * k + 1] - hf.y);
+                hi[k] = *reinterpret_cast<const uint32_t*>(&h2);
+                lo[k] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+              *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(rowp + 8192 + ((q ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            uint4* o4 = reinterpret_cast<uint4*>(oh);
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (epi_tid == 0 && col0 < p.N) {
+            const int row0 = m_tile * kBlockM;
+            if (p.out_mode == OUT_F32) {
+              tma_store_3d(&tmO, stg, 2 * col0, row0, 0);     // fp32 matrix described as 2x as many 16-bit columns
+            } else {
+              tma_store_3d(&tmO, stg, col0, row0, 0);
+              if (p.out_mode == OUT_F16_SPLIT) tma_store_3d(&tmO, stg + 8192, col0, row0, 1);
+            }
+            tma_store_commit();
+          }
+        } else {
+          if (row_ok && col0 < p.N) {                        // N is a multiple of 32 for every MAED layer
+            float v[32];
+            epilogue_math(v, r, p, col0, out_row);
+            if (p.out_mode == OUT_F32) {
+              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_row * p.ldc + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            if (p.out_mode == OUT_F16_SPLIT) {
-              uint4* l4 = reinterpret_cast<uint4*>(oh + p.out_plane_stride);
+              for (int j = 0; j < 32; j += 4) op[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              __half* oh = static_cast<__half*>(p.out) + out_row * p.ldc + col0;
+              uint32_t hi[16], lo[16];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) l4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              for (int j = 0; j < 32; j += 2) {
+                const __half2 h2 = __floats2half2_rn(v[j], v[j + 1]);
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(v[j] - hf.x, v[j + 1] - hf.y);
+                hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+              uint4* o4 = reinterpret_cast<uint4*>(oh);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (p.out_mode == OUT_F16_SPLIT) {
+                uint4* l4 = reinterpret_cast<uint4*>(oh + p.out_plane_stride);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) l4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
             }
           }
         }
@@ -257,6 +324,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (TMA_EPI) {
+      if (threadIdx.x == 128) tma_store_wait_all();       // staging must outlive the last bulk store
     }
   }
 

@@ -14,3 +14,7 @@ timeout 400 ncu --metrics $M --clock-control none -k regex:attn_spatial -s 12 -c
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/attn_inbench.log 2>&1; echo "ncu exit $?"
 grep -E "attn_spatial" gpurun_out/attn_inbench.csv | awk -F'","' '{print $(NF-2), $(NF-1), $NF}' | tail -n 6
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cut -c1-300 gpurun_out/bench.json
+# (4) opt-in TMA-store epilogue of gemm_tc_kernel: parity of every GEMM / model test, then A/B bench
+echo "=== GEMM TMA-store epilogue"
+MAED_B200_GEMM_TMA_EPI=1 timeout 900 python -m pytest -q -m gpu --timeout 300 tests/test_ops_gpu.py tests/test_model_gpu.py > gpurun_out/tma_epi_tests.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/tma_epi_tests.log
+MAED_B200_GEMM_TMA_EPI=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tma_epi.json 2> gpurun_out/bench_tma_epi.err; echo "bench exit $?"; cut -c1-300 gpurun_out/bench_tma_epi.json
