@@ -198,6 +198,28 @@ int maed_bwd_prep_conv_weight_dgrad(const float* w, int Cout, int Cin, int KH, i
                                     long long plane, void* stream);
 int maed_bwd_dropout(float* x, long long n, float p, unsigned long long seed, unsigned char* mask, float* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SMPL body model forward (maed_b200/csrc/smpl.cu): replaces the `self.smpl(...)` call of the decoders
+ * (reference lib/models/ktd.py:100-114 -> lib/models/smpl.py:84-106 -> smplx.lbs.lbs, smplx not vendored: the published
+ * algorithm is restated; parity with smplx itself is unpinned).  fp32 / int32 device pointers.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct maed_smpl_assets {
+  const float* v_template;        /* [6890, 3] */
+  const float* shapedirs;         /* [6890*3, 10] */
+  const float* posedirs;          /* [207, 6890*3] */
+  const float* J_template;        /* [24, 3]    = J_regressor @ v_template */
+  const float* J_shapedirs;       /* [24*3, 10] = J_regressor @ shapedirs */
+  const float* lbs_weights;       /* [6890, 24] */
+  const float* J_regressor_extra; /* [9, 6890] */
+  const int* parents;             /* [24] */
+  const int* extra_vertex_ids;    /* [21] */
+  const int* joint_map;           /* [49] */
+} maed_smpl_assets;
+size_t maed_smpl_scratch_bytes(int n_frames);
+/* betas [R,10], rotmat [R,24,3,3] -> verts [R,6890,3]; joints [R,49,3], or [R,n_reg,3] = J_regressor @ verts when given */
+int maed_smpl_forward(const maed_smpl_assets* assets, const float* betas, const float* rotmat, int R, const float* J_regressor,
+                      int n_reg, float* verts, float* joints, void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,11 @@ class MaedTrainOutputs(C.Structure):
     _fields_ = [("feat", _P), ("pose6d", _P), ("shape", _P), ("cam", _P)]
 
 
+class MaedSmplAssets(C.Structure):
+    _fields_ = [("v_template", _P), ("shapedirs", _P), ("posedirs", _P), ("J_template", _P), ("J_shapedirs", _P),
+                ("lbs_weights", _P), ("J_regressor_extra", _P), ("parents", _P), ("extra_vertex_ids", _P), ("joint_map", _P)]
+
+
 _U = C.c_ulonglong
 MODES = {"vanilla": 0, "parallel": 1, "series": 2, "coupling": 3, "temporal": 4}
 DECODERS = {"ktd": 0, "iterative": 1}
@@ -92,6 +97,9 @@ SIGNATURES = {
     "maed_bwd_split_transposed": (_I, [_P, _I, _I, _P, _L, _P]),
     "maed_bwd_prep_conv_weight_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "maed_bwd_dropout": (_I, [_P, _L, _F, _U, _P, _P, _P]),
+    # ---- SMPL
+    "maed_smpl_scratch_bytes": (_Z, [_I]),
+    "maed_smpl_forward": (_I, [C.POINTER(MaedSmplAssets), _P, _P, _I, _P, _I, _P, _P, _P, _Z, _P]),
 }
 
 _lib = None

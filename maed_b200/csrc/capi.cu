@@ -8,6 +8,7 @@
 #include "engine.h"
 #include "bwd_kernels.h"
 #include "kernels.h"
+#include "smpl.h"
 #include "train.h"
 
 using namespace maed;
@@ -264,6 +265,15 @@ int maed_bwd_dropout(float* x, long long n, float p, unsigned long long seed, un
   MAED_PROPAGATE(dropout_fwd(x, n, p, seed, mask, st));
   if (d) return dropout_bwd(d, n, p, mask, st);
   return MAED_OK;
+}
+
+// ---- SMPL
+static_assert(sizeof(maed_smpl_assets) == sizeof(SmplAssets), "maed_smpl_assets must mirror SmplAssets");
+size_t maed_smpl_scratch_bytes(int n_frames) { return smpl_scratch_bytes(n_frames); }
+int maed_smpl_forward(const maed_smpl_assets* assets, const float* betas, const float* rotmat, int R, const float* J_regressor,
+                      int n_reg, float* verts, float* joints, void* scratch, size_t scratch_bytes, void* stream) {
+  return smpl_forward(reinterpret_cast<const SmplAssets*>(assets), betas, rotmat, R, J_regressor, n_reg, verts, joints, scratch,
+                      scratch_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

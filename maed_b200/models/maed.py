@@ -52,6 +52,8 @@ class MAED(nn.Module):
             self.decoder = Regressor(feat_dim=feat_dim, hidden_dim=hidden_dim, mean_params=kwargs.get("mean_params"))
         else:
             raise NotImplementedError(decoder)
+        if kwargs.get("smpl_assets") is not None:
+            self.decoder.smpl.load_assets(kwargs["smpl_assets"])
         self.precision = precision or _default_precision()
         self._cfg = _lib.MaedConfig(num_blocks, num_heads, _lib.MODES[st_mode], _lib.DECODERS[decoder.lower()],
                                     hidden_dim, 3 if self.precision == "split" else 1, temp_frames)
@@ -193,16 +195,59 @@ class MAED(nn.Module):
         with torch.no_grad():
             return self._forward_inference(x, J_regressor, **kwargs)
 
+    def load_smpl_assets(self, assets):
+        """Install a body model (see SMPLHead.load_assets); afterwards verts / kp_3d / kp_2d are computed by csrc/smpl.cu."""
+        self.decoder.smpl.load_assets(assets)
+        dev = next(self.parameters()).device
+        self.decoder.smpl.to(dev)
+        return self
+
+    def _smpl(self, o, J_regressor):
+        """verts, joints and their projection from the engine's shape / rotmat (reference ktd.py:100-114)."""
+        smpl = self.decoder.smpl
+        BT = o["shape"].shape[0]
+        dev = o["shape"].device
+        f32 = dict(dtype=torch.float32, device=dev)
+        if smpl.v_template.device != dev:
+            smpl.to(dev)
+        assets = _lib.MaedSmplAssets(*[_lib.ptr(getattr(smpl, k)) for k in (
+            "v_template", "shapedirs", "posedirs", "J_template", "J_shapedirs", "lbs_weights", "J_regressor_extra", "parents",
+            "extra_vertex_ids", "joint_map")])
+        reg, n_reg = None, 0
+        if J_regressor is not None:
+            reg = J_regressor.to(dev, torch.float32).contiguous()
+            n_reg = reg.shape[0]
+        nj = n_reg if reg is not None else smpl.n_joints
+        verts = torch.empty(BT, 6890, 3, **f32)
+        joints = torch.empty(BT, nj, 3, **f32)
+        kp2d = torch.empty(BT, nj, 2, **f32)
+        with torch.cuda.device(dev):
+            lib = _lib.load()
+            nbytes = lib.maed_smpl_scratch_bytes(BT)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.call("maed_smpl_forward", C.byref(assets), _lib.ptr(o["shape"]), _lib.ptr(o["rotmat"]), BT, _lib.ptr(reg), n_reg,
+                      _lib.ptr(verts), _lib.ptr(joints), _lib.ptr(scratch), C.c_size_t(nbytes), _lib.stream_ptr())
+            rot, theta = torch.empty_like(o["rotmat"]), torch.empty_like(o["theta"])
+            _lib.call("maed_op_decode_outputs", _lib.ptr(o["pose6d"]), _lib.ptr(o["shape"]), _lib.ptr(o["cam"]), BT,
+                      _lib.ptr(joints), nj, _lib.ptr(rot), _lib.ptr(theta), _lib.ptr(kp2d), _lib.stream_ptr())
+        return verts, joints, kp2d
+
     def _forward_inference(self, x, J_regressor=None, **kwargs):
         N, T = x.shape[:2]
         o = self._run(x, want_taps=kwargs.get("_taps"))
         nj = 17 if J_regressor is not None else self.decoder.smpl.n_joints
-        kp2d = o["kp_2d"] if nj == o["kp_2d"].shape[1] else o["kp_2d"][:, :nj].contiguous()
+        if self.decoder.smpl.has_assets:
+            verts, kp3d, kp2d = self._smpl(o, J_regressor)
+            nj = kp3d.shape[1]
+        else:
+            kp2d = o["kp_2d"] if nj == o["kp_2d"].shape[1] else o["kp_2d"][:, :nj].contiguous()
+            verts = torch.zeros(N * T, 6890, 3, dtype=torch.float32, device=x.device)
+            kp3d = torch.zeros(N * T, nj, 3, dtype=torch.float32, device=x.device)
         out = {
             "theta": o["theta"].reshape(N, T, -1),
-            "verts": torch.zeros(N, T, 6890, 3, dtype=torch.float32, device=x.device),
+            "verts": verts.reshape(N, T, 6890, 3),
             "kp_2d": kp2d.reshape(N, T, -1, 2),
-            "kp_3d": torch.zeros(N, T, nj, 3, dtype=torch.float32, device=x.device),
+            "kp_3d": kp3d.reshape(N, T, nj, 3),
             "rotmat": o["rotmat"].reshape(N, T, -1, 3, 3),
         }
         if kwargs.get("_taps") or kwargs.get("_debug"):

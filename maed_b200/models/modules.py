@@ -182,12 +182,51 @@ class STEncoder(_Holder):
             nn.init.trunc_normal_(self.temp_embed, std=0.02)
 
 
+# SMPL kinematic tree (parent of joint j = last entry of ANCESTOR_INDEX[j]); vertex ids of the 21 vertex-selected joints
+# (smplx VertexJointSelector: face, feet, finger tips); indices of the 49 output joints in the 54-joint list
+# [24 SMPL | 21 selected | 9 regressed] (= JOINT_MAP[name] for name in JOINT_NAMES, reference lib/models/smpl.py:15-55).
+SMPL_PARENTS = [-1] + [a[-1] for a in ANCESTOR_INDEX[1:]]
+SMPL_EXTRA_VERTEX_IDS = [332, 6260, 2800, 4071, 583, 3216, 3226, 3387, 6617, 6624, 6787,
+                         2746, 2319, 2445, 2556, 2673, 6191, 5782, 5905, 6016, 6133]
+SMPL_JOINT_MAP = [24, 12, 17, 19, 21, 16, 18, 20, 0, 2, 5, 8, 1, 4, 7, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34,
+                  8, 5, 45, 46, 4, 7, 21, 19, 17, 16, 18, 20, 47, 48, 49, 50, 51, 52, 53, 24, 26, 25, 28, 27]
+
+
 class SMPLHead(_Holder):
-    """Placeholder for `lib/models/smpl.py` (smplx.SMPL subclass): smplx==0.1.13 and the licensed SMPL assets
-    are absent, so verts / kp_3d are zeros and kp_2d is the projection of zero joints — exactly what the
-    shimmed reference returns in this environment ("next" tier, SURVEY.md §8f-1).  Holds no parameters;
-    checkpoints drop every key containing 'smpl' anyway (train.py:101, eval.py:29)."""
+    """Stand-in for `lib/models/smpl.py` (smplx.SMPL subclass).  smplx==0.1.13 and the licensed SMPL assets are absent
+    here, so by default verts / kp_3d are zeros and kp_2d is the projection of zero joints — exactly what the shimmed
+    reference returns in this environment.  `load_assets()` installs a body model (the arrays of SMPL_NEUTRAL.pkl +
+    J_regressor_extra.npy, or the seeded synthetic pack used by the tests) as NON-persistent buffers: `state_dict()`
+    keys stay those of the reference minus `decoder.smpl.*`, which every reference loader drops anyway (train.py:101,
+    eval.py:29).  The forward itself runs in libmaed_b200.so (csrc/smpl.cu)."""
     n_joints = 49
+
+    def __init__(self):
+        super().__init__()
+        self.has_assets = False
+
+    def load_assets(self, assets):
+        """assets: mapping with v_template [6890,3], shapedirs [6890,3,10], posedirs [207,20670], J_regressor [24,6890],
+        lbs_weights [6890,24], J_regressor_extra [9,6890]; optional parents [24], extra_vertex_ids [21], joint_map [49]."""
+        def f(name, shape):
+            t = torch.as_tensor(assets[name], dtype=torch.float32).reshape(shape).contiguous()
+            return t
+        v_template, shapedirs = f("v_template", (6890, 3)), f("shapedirs", (6890, 3, 10))
+        J_regressor = f("J_regressor", (24, 6890))
+        bufs = {
+            "v_template": v_template, "shapedirs": shapedirs.reshape(6890 * 3, 10), "posedirs": f("posedirs", (207, 6890 * 3)),
+            "J_template": J_regressor @ v_template,
+            "J_shapedirs": torch.einsum("jv,vkl->jkl", J_regressor, shapedirs).reshape(72, 10).contiguous(),
+            "lbs_weights": f("lbs_weights", (6890, 24)), "J_regressor_extra": f("J_regressor_extra", (9, 6890)),
+        }
+        ints = {"parents": assets.get("parents", SMPL_PARENTS), "extra_vertex_ids": assets.get("extra_vertex_ids", SMPL_EXTRA_VERTEX_IDS),
+                "joint_map": assets.get("joint_map", SMPL_JOINT_MAP)}
+        for k, v in bufs.items():
+            self.register_buffer(k, v, persistent=False)
+        for k, v in ints.items():
+            self.register_buffer(k, torch.as_tensor(v, dtype=torch.int32).reshape(-1).contiguous(), persistent=False)
+        self.has_assets = True
+        return self
 
 
 class KTD(_Holder):

@@ -1,0 +1,71 @@
+"""SMPL forward kernels (csrc/smpl.cu) against oracle/smpl_oracle.py on the seeded synthetic asset pack, and the wiring of
+verts / kp_3d / kp_2d into MAED.forward.  Written after round 1's GPU budget: NOT yet run on a B200, skipped unless
+MAED_B200_TRAIN_TESTS=1 (the same gate as the other unvalidated tests)."""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import maed_oracle as O
+from oracle import smpl_oracle as S
+from oracle import synth
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
+                                 reason="SMPL tier not yet validated on a GPU (set MAED_B200_TRAIN_TESTS=1)")]
+
+
+def _inputs(R, seed):
+    g = torch.Generator().manual_seed(seed)
+    pose6d = torch.randn(R, 144, generator=g)
+    pose6d[0] = torch.tensor([1., 0., 0., 1., 0., 0.]).repeat(24)               # rest pose
+    betas = 0.5 * torch.randn(R, 10, generator=g)
+    betas[0] = 0
+    return betas, O.rot6d_to_rotmat(pose6d).reshape(R, 24, 3, 3)
+
+
+@pytest.mark.parametrize("R,use_reg", [(5, False), (130, False), (7, True)])
+def test_smpl_forward_matches_oracle(lib, R, use_reg):
+    from maed_b200 import _lib
+    from maed_b200.models.modules import SMPLHead
+    a = S.synthetic_assets(0)
+    head = SMPLHead().load_assets(a).cuda()
+    betas, rot = _inputs(R, 50)
+    reg = a["J_regressor_h36m"] if use_reg else None
+    v_ref, j_ref = S.smpl_forward(betas.double(), rot.double(), {k: (v.double() if v.dtype.is_floating_point else v) for k, v in a.items()},
+                                  reg.double() if use_reg else None)
+    assets = _lib.MaedSmplAssets(*[_lib.ptr(getattr(head, k)) for k in (
+        "v_template", "shapedirs", "posedirs", "J_template", "J_shapedirs", "lbs_weights", "J_regressor_extra", "parents",
+        "extra_vertex_ids", "joint_map")])
+    nj = 17 if use_reg else 49
+    verts = torch.empty(R, 6890, 3, device="cuda")
+    joints = torch.empty(R, nj, 3, device="cuda")
+    nbytes = _lib.load().maed_smpl_scratch_bytes(R)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    regd = reg.cuda().contiguous() if use_reg else None
+    _lib.call("maed_smpl_forward", C.byref(assets), _lib.ptr(betas.cuda()), _lib.ptr(rot.cuda().contiguous()), R, _lib.ptr(regd),
+              17 if use_reg else 0, _lib.ptr(verts), _lib.ptr(joints), _lib.ptr(scratch), C.c_size_t(nbytes), _lib.stream_ptr())
+    assert rel_err(verts, v_ref) < 1e-5 and rel_err(joints, j_ref) < 1e-5
+    assert rel_err(verts[0], a["v_template"]) < 1e-6                             # rest pose, zero betas
+
+
+def test_model_outputs_with_body_model(lib):
+    from maed_b200.models import MAED
+    a = S.synthetic_assets(1)
+    m = MAED("ste", 6, 12, "vanilla", "ktd", 1024, smpl_assets=a)
+    synth.fill_module_(m, 3)
+    m = m.cuda().eval()
+    x = synth.synth_frames(1, 2, 3)
+    out = m(x.cuda())
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    taps = {}
+    O.maed_forward(x, sd, "vanilla", "ktd", taps=taps)
+    rot = O.rot6d_to_rotmat(taps["pose6d"]).reshape(2, 24, 3, 3)
+    v_ref, j_ref = S.smpl_forward(taps["shape"], rot, a)
+    assert rel_err(out["verts"].reshape(2, 6890, 3), v_ref) < 1e-3
+    assert rel_err(out["kp_3d"].reshape(2, 49, 3), j_ref) < 1e-3
+    assert rel_err(out["kp_2d"].reshape(2, 49, 2), O.project_keypoints(j_ref, taps["cam"])) < 1e-3
+    out17 = m(x.cuda(), J_regressor=a["J_regressor_h36m"])
+    assert out17["kp_3d"].shape == (1, 2, 17, 3) and out17["kp_2d"].shape == (1, 2, 17, 2)

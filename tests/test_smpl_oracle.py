@@ -1,0 +1,61 @@
+"""Known-answer tests of the SMPL restatement (oracle/smpl_oracle.py) — properties of linear blend skinning that hold for
+any asset pack.  Parity with smplx itself is unpinned (smplx and the SMPL assets are absent); CPU only."""
+import math
+
+import torch
+
+from oracle import smpl_oracle as S
+
+
+def _rot(axis, angle):
+    axis = torch.tensor(axis, dtype=torch.float64)
+    axis = axis / axis.norm()
+    K = torch.tensor([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]], dtype=torch.float64)
+    return torch.eye(3, dtype=torch.float64) + math.sin(angle) * K + (1 - math.cos(angle)) * (K @ K)
+
+
+def test_rest_pose_returns_template_and_regressed_joints():
+    a = S.synthetic_assets(0, torch.float64)
+    betas = torch.zeros(2, 10, dtype=torch.float64)
+    R = torch.eye(3, dtype=torch.float64).expand(2, 24, 3, 3).contiguous()
+    verts, j24 = S.lbs(betas, R, a)
+    assert torch.allclose(verts, a["v_template"].expand(2, -1, -1), atol=1e-12)
+    assert torch.allclose(j24, (a["J_regressor"] @ a["v_template"]).expand(2, -1, -1), atol=1e-12)
+
+
+def test_shape_blend_is_linear_in_betas():
+    a = S.synthetic_assets(1, torch.float64)
+    R = torch.eye(3, dtype=torch.float64).expand(1, 24, 3, 3).contiguous()
+    b1, b2 = torch.randn(1, 10, dtype=torch.float64), torch.randn(1, 10, dtype=torch.float64)
+    v0, _ = S.lbs(torch.zeros(1, 10, dtype=torch.float64), R, a)
+    v1, _ = S.lbs(b1, R, a)
+    v2, _ = S.lbs(b2, R, a)
+    v12, _ = S.lbs(b1 + b2, R, a)
+    assert torch.allclose(v12 - v0, (v1 - v0) + (v2 - v0), atol=1e-10)       # rest pose: skinning is the identity
+
+
+def test_pure_global_rotation_rotates_about_the_root_joint():
+    a = S.synthetic_assets(2, torch.float64)
+    betas = 0.5 * torch.randn(1, 10, dtype=torch.float64)
+    Rg = _rot([0.3, -1.0, 0.5], 1.1)
+    R = torch.eye(3, dtype=torch.float64).expand(1, 24, 3, 3).clone()
+    R[0, 0] = Rg
+    rest, j_rest = S.lbs(betas, torch.eye(3, dtype=torch.float64).expand(1, 24, 3, 3).contiguous(), a)
+    verts, j24 = S.lbs(betas, R, a)
+    J0 = j_rest[0, 0]
+    assert torch.allclose(verts[0], (rest[0] - J0) @ Rg.t() + J0, atol=1e-10)
+    assert torch.allclose(j24[0], (j_rest[0] - J0) @ Rg.t() + J0, atol=1e-10)
+
+
+def test_joint_selection_and_regressor_override():
+    a = S.synthetic_assets(3, torch.float64)
+    betas = 0.3 * torch.randn(2, 10, dtype=torch.float64)
+    R = torch.stack([torch.stack([_rot([1, j % 3, 0.2 * j], 0.1 * j + 0.05 * b) for j in range(24)]) for b in range(2)])
+    verts, j49 = S.smpl_forward(betas, R, a)
+    _, j24 = S.lbs(betas, R, a)
+    assert j49.shape == (2, 49, 3)
+    assert torch.equal(j49[:, 8], j24[:, 0])                                    # 'OP MidHip' -> SMPL joint 0
+    assert torch.equal(j49[:, 0], verts[:, S.EXTRA_VERTEX_IDS[0]])              # 'OP Nose' -> joint 24 = first selected vertex
+    assert torch.allclose(j49[:, 39], a["J_regressor_extra"][4] @ verts, atol=1e-12)   # 'Pelvis (MPII)' -> 49 = 45 + 4
+    _, j17 = S.smpl_forward(betas, R, a, a["J_regressor_h36m"])
+    assert j17.shape == (2, 17, 3) and torch.allclose(j17, torch.einsum("jv,bvk->bjk", a["J_regressor_h36m"], verts))
