@@ -78,14 +78,46 @@ def project_keypoints(joints, cam):
     return 5000.0 * pts[:, :, :2] / 112.0
 
 
-def decode_outputs(pose6d, shape, cam, n_joints=49):
-    """reference lib/models/ktd.py:94-124 with the placeholder body model (verts / joints are zeros, see SMPLHead)."""
+def smpl_forward_torch(betas, rotmats, head, J_regressor=None):
+    """Differentiable SMPL forward for the training tail (keypoint losses need d kp / d pose, d shape): the algorithm of
+    smplx.lbs.lbs as in csrc/smpl.cu, on the buffers of `SMPLHead` (torch matmuls: ~2 GFLOP per 128 frames).
+    betas [B,10], rotmats [B,24,3,3] -> verts [B,6890,3], joints [B,49,3] (or J_regressor @ verts)."""
+    B = betas.shape[0]
+    v_shaped = head.v_template.reshape(1, -1) + betas @ head.shapedirs.t()                  # [B, 20670]
+    J = (head.J_template.reshape(1, -1) + betas @ head.J_shapedirs.t()).reshape(B, 24, 3)
+    pose_feature = (rotmats[:, 1:] - torch.eye(3, dtype=rotmats.dtype, device=rotmats.device)).reshape(B, 207)
+    v_posed = (v_shaped + pose_feature @ head.posedirs).reshape(B, 6890, 3)
+    parents = head.parents.tolist()
+    bottom = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=rotmats.dtype, device=rotmats.device).expand(B, 1, 4)
+    G = []
+    for j in range(24):
+        rel = J[:, j] - (J[:, parents[j]] if parents[j] >= 0 else 0)
+        M = torch.cat([torch.cat([rotmats[:, j], rel.unsqueeze(-1)], dim=2), bottom], dim=1)
+        G.append(M if parents[j] < 0 else G[parents[j]] @ M)
+    G = torch.stack(G, dim=1)
+    joints24 = G[:, :, :3, 3]
+    A_t = G[:, :, :3, 3] - torch.einsum("bjrc,bjc->bjr", G[:, :, :3, :3], J)
+    A = torch.cat([G[:, :, :3, :3], A_t.unsqueeze(-1)], dim=3).reshape(B, 24, 12)
+    T = torch.einsum("vj,bjk->bvk", head.lbs_weights, A).reshape(B, 6890, 3, 4)
+    verts = torch.einsum("bvrc,bvc->bvr", T[..., :3], v_posed) + T[..., 3]
+    if J_regressor is not None:
+        return verts, torch.einsum("jv,bvk->bjk", J_regressor.to(verts), verts)
+    extra = verts[:, head.extra_vertex_ids.long()]
+    reg = torch.einsum("jv,bvk->bjk", head.J_regressor_extra, verts)
+    return verts, torch.cat([joints24, extra, reg], dim=1)[:, head.joint_map.long()]
+
+
+def decode_outputs(pose6d, shape, cam, n_joints=49, smpl_head=None, J_regressor=None):
+    """reference lib/models/ktd.py:94-124.  Without a body model (see SMPLHead) verts / joints are zeros."""
     nt = pose6d.shape[0]
     rot = rot6d_to_rotmat(pose6d).reshape(nt, 24, 3, 3)
-    kp3d = pose6d.new_zeros(nt, n_joints, 3)
+    if smpl_head is not None and smpl_head.has_assets:
+        verts, kp3d = smpl_forward_torch(shape, rot, smpl_head, J_regressor)
+    else:
+        verts, kp3d = pose6d.new_zeros(nt, 6890, 3), pose6d.new_zeros(nt, n_joints, 3)
     aa = rotmat_to_angle_axis(rot.reshape(-1, 3, 3)).reshape(nt, 72)
-    return {"theta": torch.cat([cam, aa, shape], dim=1), "verts": pose6d.new_zeros(nt, 6890, 3),
-            "kp_2d": project_keypoints(kp3d, cam), "kp_3d": kp3d, "rotmat": rot}
+    return {"theta": torch.cat([cam, aa, shape], dim=1), "verts": verts, "kp_2d": project_keypoints(kp3d, cam), "kp_3d": kp3d,
+            "rotmat": rot}
 
 
 # --------------------------------------------------------------------------------------------- engine state
@@ -206,7 +238,7 @@ def train_forward(model, x, J_regressor=None):
     dropout_p = model._train_dropout_p if model._train_dropout_p is not None else 0.5   # nn.Dropout() default (ktd.py:54-56)
     pose, shape, cam = MaedTrainFunction.apply(model, x, dropout_p, *params)
     nj = 17 if J_regressor is not None else model.decoder.smpl.n_joints
-    o = decode_outputs(pose, shape, cam, nj)
+    o = decode_outputs(pose, shape, cam, nj, model.decoder.smpl, J_regressor)
     return {"theta": o["theta"].reshape(N, T, -1), "verts": o["verts"].reshape(N, T, -1, 3),
             "kp_2d": o["kp_2d"].reshape(N, T, -1, 2), "kp_3d": o["kp_3d"].reshape(N, T, -1, 3),
             "rotmat": o["rotmat"].reshape(N, T, -1, 3, 3),
