@@ -1,8 +1,10 @@
 """SMPL forward kernels (csrc/smpl.cu) against oracle/smpl_oracle.py on the seeded synthetic asset pack, and the wiring of
-verts / kp_3d / kp_2d into MAED.forward.  Written after round 1's GPU budget: NOT yet run on a B200, skipped unless
-MAED_B200_TRAIN_TESTS=1 (the same gate as the other unvalidated tests)."""
+verts / kp_3d / kp_2d into MAED.forward.  Two backends (see tests/test_bwd_ops.py): ``emu`` = the real kernel sources on
+the CUDA-on-CPU shim (default CPU suite), ``cuda`` = the product library on a B200 — written after round 1's GPU budget,
+NOT yet run on hardware, skipped unless MAED_B200_TRAIN_TESTS=1."""
 import ctypes as C
 import os
+import sys
 
 import pytest
 import torch
@@ -12,9 +14,23 @@ from oracle import maed_oracle as O
 from oracle import smpl_oracle as S
 from oracle import synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
-                                 reason="SMPL tier not yet validated on a GPU (set MAED_B200_TRAIN_TESTS=1)")]
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+
+_CUDA_MARKS = [pytest.mark.gpu,
+               pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
+                                  reason="SMPL tier not yet validated on a GPU (set MAED_B200_TRAIN_TESTS=1)")]
+
+
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=_CUDA_MARKS)])
+def dev(request):
+    if request.param == "emu":
+        import harness
+        with harness.activate():
+            yield "cpu"
+    else:
+        from maed_b200 import build
+        build.build()
+        yield "cuda"
 
 
 def _inputs(R, seed):
@@ -27,11 +43,11 @@ def _inputs(R, seed):
 
 
 @pytest.mark.parametrize("R,use_reg", [(5, False), (130, False), (7, True)])
-def test_smpl_forward_matches_oracle(lib, R, use_reg):
+def test_smpl_forward_matches_oracle(dev, R, use_reg):
     from maed_b200 import _lib
     from maed_b200.models.modules import SMPLHead
     a = S.synthetic_assets(0)
-    head = SMPLHead().load_assets(a).cuda()
+    head = SMPLHead().load_assets(a).to(dev)
     betas, rot = _inputs(R, 50)
     reg = a["J_regressor_h36m"] if use_reg else None
     v_ref, j_ref = S.smpl_forward(betas.double(), rot.double(), {k: (v.double() if v.dtype.is_floating_point else v) for k, v in a.items()},
@@ -40,17 +56,27 @@ def test_smpl_forward_matches_oracle(lib, R, use_reg):
         "v_template", "shapedirs", "posedirs", "J_template", "J_shapedirs", "lbs_weights", "J_regressor_extra", "parents",
         "extra_vertex_ids", "joint_map")])
     nj = 17 if use_reg else 49
-    verts = torch.empty(R, 6890, 3, device="cuda")
-    joints = torch.empty(R, nj, 3, device="cuda")
+    verts = torch.empty(R, 6890, 3, device=dev)
+    joints = torch.empty(R, nj, 3, device=dev)
     nbytes = _lib.load().maed_smpl_scratch_bytes(R)
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-    regd = reg.cuda().contiguous() if use_reg else None
-    _lib.call("maed_smpl_forward", C.byref(assets), _lib.ptr(betas.cuda()), _lib.ptr(rot.cuda().contiguous()), R, _lib.ptr(regd),
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    regd = reg.to(dev).contiguous() if use_reg else None
+    betas_d, rot_d = betas.to(dev).contiguous(), rot.to(dev).contiguous()       # must outlive the call
+    _lib.call("maed_smpl_forward", C.byref(assets), _lib.ptr(betas_d), _lib.ptr(rot_d), R, _lib.ptr(regd),
               17 if use_reg else 0, _lib.ptr(verts), _lib.ptr(joints), _lib.ptr(scratch), C.c_size_t(nbytes), _lib.stream_ptr())
     assert rel_err(verts, v_ref) < 1e-5 and rel_err(joints, j_ref) < 1e-5
     assert rel_err(verts[0], a["v_template"]) < 1e-6                             # rest pose, zero betas
+    # projection of the joints (maed_op_decode_outputs), as MAED._smpl chains it
+    g = torch.Generator().manual_seed(51)
+    pose6d, cam = torch.randn(R, 144, generator=g).to(dev), (torch.rand(R, 3, generator=g) + 0.5).to(dev)
+    rot_o, theta, kp2d = torch.empty(R, 24, 3, 3, device=dev), torch.empty(R, 85, device=dev), torch.empty(R, nj, 2, device=dev)
+    _lib.call("maed_op_decode_outputs", _lib.ptr(pose6d), _lib.ptr(betas_d), _lib.ptr(cam), R, _lib.ptr(joints), nj, _lib.ptr(rot_o),
+              _lib.ptr(theta), _lib.ptr(kp2d), _lib.stream_ptr())
+    assert rel_err(kp2d, O.project_keypoints(j_ref.float(), cam.cpu())) < 1e-5
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"), reason="SMPL tier not yet validated on a GPU")
 def test_model_outputs_with_body_model(lib):
     from maed_b200.models import MAED
     a = S.synthetic_assets(1)
