@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(HERE, f) for f in sorted(os.listdir(HERE))
                                                                          if f.endswith((".h", ".cpp", ".py"))]
     deps.append(os.path.join(ROOT, "include", "maed_b200.h"))
-    h = hashlib.sha1()
+    h = hashlib.sha1(os.environ.get("MAED_EMU_ASAN", "").encode())
     for d in deps:
         with open(d, "rb") as f:
             h.update(f.read())
@@ -73,6 +73,8 @@ def build(force=False, verbose=False):
     with open(os.path.join(OUT, "emu_gemm_enums.h"), "w") as f:
         f.write("// generated from maed_b200/csrc/gemm_sm100.cuh by build_emu.py\n#pragma once\nnamespace maed {\n%s\n}\n" % "\n".join(enums))
     flags += ["-I", OUT]
+    if os.environ.get("MAED_EMU_ASAN"):      # one-off memory checking (tests/emu/README.md): heap redzones around every tensor
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer", "--param", "asan-stack=0"]
     objs, jobs = [], []
     for name in CU_SOURCES:
         with open(os.path.join(CSRC, name)) as f:
@@ -100,7 +102,8 @@ def build(force=False, verbose=False):
             print(out[-3000:])
     if failed:
         raise RuntimeError("emulator build failed")
-    _run(["g++", "-shared", "-o", LIB] + objs + ["-lpthread", "-Wl,-Bsymbolic"])
+    _run(["g++", "-shared", "-o", LIB] + objs + ["-lpthread", "-Wl,-Bsymbolic"] +
+         (["-fsanitize=address"] if os.environ.get("MAED_EMU_ASAN") else []))
     with open(stamp, "w") as f:
         f.write(h.hexdigest())
     return LIB

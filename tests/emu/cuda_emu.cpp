@@ -73,6 +73,7 @@ struct Worker {
   unsigned warp_gen[32];
   uint64_t slots[32][32];
   dim3 bdim;
+  bool reverse = false;    // MAED_EMU_ORDER=reverse: threads are scheduled from the last to the first (see README)
 };
 
 thread_local Worker* t_worker = nullptr;
@@ -127,7 +128,8 @@ void run_block(Worker& w) {
   int done = 0;
   while (done < n) {
     bool progress = false;
-    for (int t = 0; t < n; ++t) {
+    for (int i = 0; i < n; ++i) {
+      const int t = w.reverse ? n - 1 - i : i;
       Fiber& f = w.fibers[t];
       if (f.state == DONE) continue;
       if (f.state == WAIT_BLOCK && f.gen == w.bar_gen) continue;
@@ -200,7 +202,8 @@ static int worker_count() {
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& thread_fn) {
   const long long nblocks = (long long)grid.x * grid.y * grid.z;
   const int nthreads = (int)(block.x * block.y * block.z);
-  if (nblocks <= 0 || nthreads <= 0 || nthreads > 1024) {
+  if (nblocks <= 0 || nthreads <= 0 || nthreads > 1024 || grid.y > 65535 || grid.z > 65535 || grid.x > 2147483647u ||
+      block.z > 64) {
     fprintf(stderr, "emu: invalid launch configuration grid=(%u,%u,%u) block=(%u,%u,%u)\n", grid.x, grid.y, grid.z, block.x,
             block.y, block.z);
     abort();
@@ -219,6 +222,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& t
     w.nthreads = nthreads;
     w.fn = &thread_fn;
     w.bdim = block;
+    { const char* o = getenv("MAED_EMU_ORDER"); w.reverse = o && o[0] == 'r'; }
     t_worker = &w;
     t_blockDim = block;
     t_gridDim = grid;
