@@ -208,9 +208,17 @@ int launch_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, const SplitKPa
 
 }  // namespace
 
+// Upper bound over every R <= the given one: the slice count is not monotonic in R (slices = ceil(nkb / ceil(nkb / s))), and
+// callers size one scratch buffer for a family of launches (e.g. BT*197 token rows and BT*196 patch rows), so the bound uses
+// the cap `s` on the number of slices instead of the exact count for this R.
 size_t splitk_slab_floats(int Mo, int No, int R) {
   const SliceChoice c = choose_slices(Mo, No, R);
-  return (size_t)c.slices * Mo * No;
+  const int tiles = c.m_tiles * c.n_tiles;
+  int s = (2 * sm_count() + tiles - 1) / tiles;
+  if (s > 64) s = 64;
+  if (s > c.nkb) s = c.nkb;
+  if (s < c.slices) s = c.slices;
+  return (size_t)s * Mo * No;
 }
 
 int gemm_wgrad_splitk(const __half* A, long long a_plane, int lda, const __half* B, long long b_plane, int ldb, int Mo,

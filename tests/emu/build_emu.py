@@ -57,6 +57,11 @@ def build(force=False, verbose=False):
                                                                          if f.endswith((".h", ".cpp", ".py"))]
     deps.append(os.path.join(ROOT, "include", "maed_b200.h"))
     h = hashlib.sha1(os.environ.get("MAED_EMU_ASAN", "").encode())
+    try:                                    # -march=native: never reuse a library built on another CPU model
+        with open("/proc/cpuinfo") as f:
+            h.update("".join(l for l in f if l.startswith(("model name", "flags"))).encode())
+    except OSError:
+        pass
     for d in deps:
         with open(d, "rb") as f:
             h.update(f.read())

@@ -4,8 +4,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <sys/mman.h>
+#include <time.h>
 
+#include <dlfcn.h>
+
+#include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -56,6 +62,7 @@ struct Fiber {
   uint8_t* stack = nullptr;
   int state = FRESH;
   unsigned gen = 0;        // generation of the barrier the fiber waits on
+  unsigned shfl = 0;       // shuffles executed by this thread (selects the slot set)
 };
 
 struct Worker {
@@ -71,7 +78,7 @@ struct Worker {
   // warp barriers
   int warp_live[32], warp_arrived[32];
   unsigned warp_gen[32];
-  uint64_t slots[32][32];
+  uint64_t slots[32][64];
   dim3 bdim;
   bool reverse = false;    // MAED_EMU_ORDER=reverse: threads are scheduled from the last to the first (see README)
 };
@@ -124,7 +131,7 @@ void run_block(Worker& w) {
     w.warp_live[i] = (i == nwarps - 1) ? n - 32 * i : 32;
     w.warp_arrived[i] = 0;
   }
-  for (int t = 0; t < n; ++t) w.fibers[t].state = FRESH;
+  for (int t = 0; t < n; ++t) { w.fibers[t].state = FRESH; w.fibers[t].shfl = 0; }
   int done = 0;
   while (done < n) {
     bool progress = false;
@@ -160,6 +167,7 @@ int warp_lanes() {
   return rem < 32 ? rem : 32;
 }
 uint64_t* warp_slots() { return t_worker->slots[t_worker->cur >> 5]; }
+unsigned shfl_parity() { return t_worker->fibers[t_worker->cur].shfl++; }
 
 void block_sync() {
   Worker& w = *t_worker;
@@ -199,7 +207,16 @@ static int worker_count() {
   return n;
 }
 
+double g_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // seconds: [0] fiber kernels, [1..] stubs (tc_stubs.cpp)
+static double now_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+struct ProfScope { double t0; int slot; ProfScope(int s) : t0(now_s()), slot(s) {} ~ProfScope() { g_prof[slot] += now_s() - t0; } };
+
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& thread_fn) {
+  ProfScope prof(0);
   const long long nblocks = (long long)grid.x * grid.y * grid.z;
   const int nthreads = (int)(block.x * block.y * block.z);
   if (nblocks <= 0 || nthreads <= 0 || nthreads > 1024 || grid.y > 65535 || grid.z > 65535 || grid.x > 2147483647u ||
@@ -248,3 +265,34 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& t
 }
 
 }  // namespace emu
+
+namespace emu {
+double prof_now() { return now_s(); }
+namespace {
+struct KernelProf {
+  std::mutex mu;
+  std::map<const void*, std::pair<double, long>> t;
+  ~KernelProf() {
+    if (!getenv("MAED_EMU_PROFILE")) return;
+    std::vector<std::pair<double, const void*>> v;
+    for (auto& kv : t) v.push_back({kv.second.first, kv.first});
+    std::sort(v.rbegin(), v.rend());
+    for (auto& e : v) {
+      Dl_info info;
+      const char* name = (dladdr(e.second, &info) && info.dli_sname) ? info.dli_sname : "?";
+      fprintf(stderr, "emu-profile %8.2fs %6ld launches  %s\n", e.first, t[e.second].second, name);
+    }
+  }
+} g_kprof;
+}  // namespace
+void prof_kernel(const void* fn, double seconds) {
+  std::lock_guard<std::mutex> lk(g_kprof.mu);
+  auto& e = g_kprof.t[fn];
+  e.first += seconds;
+  e.second += 1;
+}
+}  // namespace emu
+
+extern "C" void emu_profile(double* out8, int reset) {
+  for (int i = 0; i < 8; ++i) { out8[i] = emu::g_prof[i]; if (reset) emu::g_prof[i] = 0; }
+}

@@ -46,10 +46,13 @@ extern thread_local uint8_t* t_dyn_smem;
 
 void block_sync();                       // __syncthreads
 void warp_sync();                        // __syncwarp / both halves of a shuffle
-uint64_t* warp_slots();                  // 32 exchange slots of the running thread's warp
+uint64_t* warp_slots();                  // 2 x 32 exchange slots of the running thread's warp
+unsigned shfl_parity();                  // per-thread shuffle counter (post-incremented)
 int lane_id();
 int warp_lanes();                        // live width of the running thread's warp (blockDim tail)
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& thread_fn);
+void prof_kernel(const void* fn, double seconds);      // per-kernel wall time (MAED_EMU_PROFILE=1, dumped at exit)
+double prof_now();
 
 struct Launch {
   dim3 g, b;
@@ -58,14 +61,18 @@ struct Launch {
   template <class... P, class... A>
   void call(void (*k)(P...), A&&... a) {
     std::tuple<std::decay_t<P>...> args(std::forward<A>(a)...);      // kernel parameters are passed by value
+    const double t0 = prof_now();
     run_grid(g, b, smem, [&]() { std::apply(k, args); });
+    prof_kernel(reinterpret_cast<const void*>(k), prof_now() - t0);
   }
 };
 
 template <class T>
 inline T shfl_from(T v, int src) {
   static_assert(sizeof(T) <= 8, "shuffle payload");
-  uint64_t* s = warp_slots();
+  // two slot sets used alternately: a lane can run at most one shuffle ahead of the slowest lane (the next warp_sync stops
+  // it), so the set it overwrites then has been read by everybody — one barrier per shuffle instead of two
+  uint64_t* s = warp_slots() + 32 * (shfl_parity() & 1);
   const int lane = lane_id();
   uint64_t raw = 0;
   memcpy(&raw, &v, sizeof(T));
@@ -73,7 +80,6 @@ inline T shfl_from(T v, int src) {
   warp_sync();
   T r = v;
   if (src >= 0 && src < warp_lanes()) memcpy(&r, &s[src], sizeof(T));
-  warp_sync();
   return r;
 }
 

@@ -10,6 +10,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
 #include <atomic>
@@ -20,6 +21,16 @@
 #include "emu_gemm_enums.h"      // OUT_* / ACT_* extracted from gemm_sm100.cuh by build_emu.py
 #include "gemm_host.h"
 #include "kernels.h"
+
+namespace emu { extern double g_prof[8]; }
+namespace {
+struct Prof {
+  double t0; int slot;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+  explicit Prof(int s) : t0(now()), slot(s) {}
+  ~Prof() { emu::g_prof[slot] += now() - t0; }
+};
+}  // namespace
 
 namespace maed {
 
@@ -79,36 +90,51 @@ static inline void st_split(__half* p, long long plane, float v, bool lo) {
   if (lo) p[plane] = __float2half_rn(v - __half2float(h));
 }
 
-// C[M,N] = A[M,K] * B[N,K]^T, fp32, row-major dense.  Bt-panel kernel: vectorises over n without reassociation.
+// C[M,N] = A[M,K] * B[N,K]^T, fp32, row-major dense.  Register-tiled 6 x 32 micro-kernel on GCC vector types over a
+// K-major packed panel of B (no reassociation inside a dot product beyond the fixed k order).
+typedef float vf16 __attribute__((vector_size(64), aligned(4)));
 static void sgemm_nt(long long M, int N, int K, const float* A, const float* B, float* C) {
-  std::vector<float> Bt((size_t)K * N);
-  parallel_for((N + 63) / 64, [&](long long nb) {
-    const int n0 = (int)nb * 64, n1 = std::min(N, n0 + 64);
-    for (int n = n0; n < n1; ++n)
-      for (int k = 0; k < K; ++k) Bt[(size_t)k * N + n] = B[(size_t)n * K + k];
+  constexpr int NR = 32, MR = 6;
+  const int npanels = (N + NR - 1) / NR;
+  // Bp[panel][k][NR]
+  std::vector<float> Bp((size_t)npanels * K * NR, 0.f);
+  parallel_for(npanels, [&](long long pb) {
+    float* dst = &Bp[(size_t)pb * K * NR];
+    const int n0 = (int)pb * NR, nn = std::min(NR, N - n0);
+    for (int n = 0; n < nn; ++n) {
+      const float* src = B + (size_t)(n0 + n) * K;
+      for (int k = 0; k < K; ++k) dst[(size_t)k * NR + n] = src[k];
+    }
   });
-  constexpr int MB = 4, NB = 256;
-  const long long mblocks = (M + 31) / 32;
-  parallel_for(mblocks, [&](long long mb) {
-    const long long m_lo = mb * 32, m_hi = std::min<long long>(M, m_lo + 32);
-    float acc[MB][NB];
-    for (int n0 = 0; n0 < N; n0 += NB) {
-      const int nn = std::min(NB, N - n0);
-      for (long long m0 = m_lo; m0 < m_hi; m0 += MB) {
-        const int mm = (int)std::min<long long>(MB, m_hi - m0);
-        for (int i = 0; i < MB; ++i)
-          for (int n = 0; n < nn; ++n) acc[i][n] = 0.f;
+  const long long mblocks = (M + MR - 1) / MR;
+  const long long chunk = 8;                                   // row blocks per work item
+  parallel_for((mblocks + chunk - 1) / chunk, [&](long long wi) {
+    for (long long mb = wi * chunk; mb < std::min(mblocks, (wi + 1) * chunk); ++mb) {
+      const long long m0 = mb * MR;
+      const int mm = (int)std::min<long long>(MR, M - m0);
+      const float* a[MR];
+      for (int i = 0; i < MR; ++i) a[i] = A + (size_t)(m0 + (i < mm ? i : 0)) * K;
+      for (int pb = 0; pb < npanels; ++pb) {
+        const float* bp = &Bp[(size_t)pb * K * NR];
+        vf16 acc[MR][2];
+        for (int i = 0; i < MR; ++i) { acc[i][0] = vf16{} ; acc[i][1] = vf16{}; }
         for (int k = 0; k < K; ++k) {
-          const float* bt = &Bt[(size_t)k * N + n0];
-          float a[MB];
-          for (int i = 0; i < MB; ++i) a[i] = (i < mm) ? A[(size_t)(m0 + i) * K + k] : 0.f;
-          for (int n = 0; n < nn; ++n) {
-            const float b = bt[n];
-            acc[0][n] += a[0] * b; acc[1][n] += a[1] * b; acc[2][n] += a[2] * b; acc[3][n] += a[3] * b;
+          const vf16 b0 = *reinterpret_cast<const vf16*>(bp + (size_t)k * NR);
+          const vf16 b1 = *reinterpret_cast<const vf16*>(bp + (size_t)k * NR + 16);
+#pragma GCC unroll 6
+          for (int i = 0; i < MR; ++i) {
+            const float av = a[i][k];
+            acc[i][0] += av * b0;
+            acc[i][1] += av * b1;
           }
         }
-        for (int i = 0; i < mm; ++i)
-          for (int n = 0; n < nn; ++n) C[(size_t)(m0 + i) * N + n0 + n] = acc[i][n];
+        const int n0 = pb * NR, nn = std::min(NR, N - n0);
+        for (int i = 0; i < mm; ++i) {
+          float tmp[NR];
+          memcpy(tmp, &acc[i][0], 64);
+          memcpy(tmp + 16, &acc[i][1], 64);
+          memcpy(C + (size_t)(m0 + i) * N + n0, tmp, (size_t)nn * 4);
+        }
       }
     }
   });
@@ -125,6 +151,7 @@ static void planes_to_dense(const __half* p, long long plane, long long rows, in
 
 // ------------------------------------------------------------------------------------------------- launch_gemm
 int launch_gemm(const GemmArgs& g, cudaStream_t) {
+  Prof prof(1);
   MAED_CHECK_ARG(g.nsplit == 1 || g.nsplit == 3, "gemm: nsplit must be 1 or 3");
   MAED_CHECK_ARG(g.N % 32 == 0, "gemm: N=%d must be a multiple of 32", g.N);
   MAED_CHECK_ARG(g.M > 0 && g.K > 0, "gemm: empty problem M=%d K=%d", g.M, g.K);
@@ -226,6 +253,7 @@ int conv_gn_fused(const ConvGnArgs&, cudaStream_t) { return MAED_ERR_UNSUPPORTED
 // --------------------------------------------------------------------------------------------------- stem conv
 int stem_conv(const float* x, int n_img, const __half* w_hi, long long w_plane, int k_pad, int nsplit, float* out,
               double* stats, cudaStream_t) {
+  Prof prof(2);
   MAED_CHECK_ARG(k_pad % 8 == 0 && k_pad >= 147, "stem_conv: bad k_pad %d", k_pad);
   const int np = nsplit == 3 ? 2 : 1;
   const uint64_t dims[3] = {(uint64_t)k_pad, 64, (uint64_t)np};
@@ -275,6 +303,7 @@ int stem_conv(const float* x, int n_img, const __half* w_hi, long long w_plane, 
 template <class RowFn>
 static void attention_ref(const __half* qkv, long long plane, long long groups, int seq, int heads, float scale, RowFn row_of,
                           float* out_f32, __half* out_hi, long long out_plane) {
+  Prof prof(3);
   const int ldq = 3 * heads * 64, C = heads * 64;
   parallel_for(groups * heads, [&](long long gh) {
     const long long g = gh / heads;
@@ -356,6 +385,7 @@ size_t splitk_slab_floats(int Mo, int No, int) { return (size_t)Mo * No; }
 
 int gemm_wgrad_splitk(const __half* A, long long a_plane, int lda, const __half* B, long long b_plane, int ldb, int Mo,
                       int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, cudaStream_t) {
+  Prof prof(4);
   MAED_CHECK_ARG(A && B && slabs && D, "gemm_wgrad_splitk: null argument");
   MAED_CHECK_ARG(Mo >= 1 && No >= 32 && No % 32 == 0 && R >= 1, "gemm_wgrad_splitk: bad shape Mo=%d No=%d R=%d", Mo, No, R);
   MAED_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && lda >= R && ldb >= R, "gemm_wgrad_splitk: row strides must be multiples of 8 "
