@@ -60,6 +60,7 @@ class MAED(nn.Module):
         self._engine = None
         self._packed = None
         self._packed_key = None
+        self._pack_gen = 0
         self._workspace = None
         self._param_ptrs = None
         self._training_enabled = False
@@ -113,6 +114,7 @@ class MAED(nn.Module):
                 self._packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
             _lib.call("maed_engine_pack", eng, arr, _lib.ptr(self._packed), _lib.stream_ptr())
             self._packed_key = key
+            self._pack_gen += 1          # derived caches elsewhere (train.TrainState.tpack) follow this counter
         return eng
 
     def invalidate_cache(self):

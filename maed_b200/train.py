@@ -178,7 +178,9 @@ class MaedTrainFunction(torch.autograd.Function):
         dev = x.device
         with torch.cuda.device(dev):
             eng = model._prepare(dev)                   # engine + forward packed weights (version-keyed cache)
-            st.ensure_tpack(eng, model._param_ptrs, model._packed_key, dev)
+            # keyed by the pack generation, not by _packed_key: FusedAdam updates parameters behind autograd's version
+            # counters, so the key can repeat although the weights changed (invalidate_cache() forces a re-pack)
+            st.ensure_tpack(eng, model._param_ptrs, model._pack_gen, dev)
             ws = st.ensure_workspace(eng, N * T, dev)
             f32 = dict(dtype=torch.float32, device=dev)
             pose = torch.empty(N * T, 144, **f32)

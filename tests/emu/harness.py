@@ -49,6 +49,33 @@ def activate():
         _lib._lib, _lib.stream_ptr, ops.stream_ptr = saved
 
 
+@contextlib.contextmanager
+def product_on_cpu():
+    """Runs the PRODUCT Python modules (maed_b200.models.MAED, maed_b200.train) on CPU tensors against the emulator library,
+    so that the autograd boundary, the flat gradient buffer, FusedAdam and the geometry tail are exercised without a GPU.
+    Test-only trickery: `torch.Tensor.is_cuda` is shadowed by a property that answers True and `torch.cuda.device` by a
+    no-op context manager for the duration of the block — the product code keeps refusing CPU tensors everywhere else."""
+    class _NoDevice:
+        def __init__(self, *a, **k):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    with activate() as lib:
+        saved = torch.cuda.device
+        torch.cuda.device = _NoDevice
+        torch.Tensor.is_cuda = property(lambda self: True)
+        try:
+            yield lib
+        finally:
+            del torch.Tensor.is_cuda
+            torch.cuda.device = saved
+
+
 class EmuModel:
     """Engine driver on CPU tensors: the same C-ABI call sequence as maed_b200.models.MAED._run and
     maed_b200.train.MaedTrainFunction, minus torch.cuda."""

@@ -1,9 +1,16 @@
-"""Model-level tests of the training path: tape forward == inference forward, parameter gradients against the
-reference's gradient digests (tests/golden/grads_*.npz) and against oracle autograd on fresh inputs, Adam, a short fit.
+"""Model-level tests of the training path through the PRODUCT modules (maed_b200.models.MAED + maed_b200.train): tape
+forward == inference forward, parameter gradients against the reference's gradient digests (tests/golden/grads_*.npz) and
+against oracle autograd on fresh inputs, loss-scale invariance, FusedAdam vs torch Adam, a short fit.  Two backends (see
+tests/test_bwd_ops.py):
 
-Written at the end of round 1 after the GPU budget was spent: NOT yet run on a B200, therefore skipped unless
-MAED_B200_TRAIN_TESTS=1 (round 2 starts by running them)."""
+  * ``emu``  — CPU, default suite: product Python code + real CUDA-core kernel sources + engine/train orchestration on the
+    CUDA-on-CPU shim (tests/emu/harness.py::product_on_cpu); the tcgen05 kernels are contract stubs there.  The long cases
+    run only with MAED_EMU_FULL=1 (the digest check of all three modes is in tests/test_emu_model.py either way);
+  * ``cuda`` — `-m gpu`, the product library on a B200.  Written after round 1's GPU budget was spent: NOT yet run on
+    hardware, skipped unless MAED_B200_TRAIN_TESTS=1 (round 2 starts by running them).
+"""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -13,9 +20,34 @@ from helpers import GOLDEN_DIR, rel_err, state_dict_of
 from oracle import maed_oracle as O
 from oracle import synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
-                                 reason="training path not yet validated on a GPU (set MAED_B200_TRAIN_TESTS=1)")]
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+
+DEV = "cuda"
+_CUDA_MARKS = [pytest.mark.gpu,
+               pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
+                                  reason="training path not yet validated on a GPU (set MAED_B200_TRAIN_TESTS=1)")]
+_EMU_FULL = bool(os.environ.get("MAED_EMU_FULL"))
+
+
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=_CUDA_MARKS)])
+def lib(request):
+    global DEV
+    if request.param == "emu":
+        import harness
+        DEV = "cpu"
+        with harness.product_on_cpu() as l:
+            yield l
+    else:
+        from maed_b200 import _lib, build
+        build.build()
+        DEV = "cuda"
+        yield _lib.load()
+
+
+def _slow_on_emu():
+    if DEV == "cpu" and not _EMU_FULL:
+        pytest.skip("long on the emulator: set MAED_EMU_FULL=1")
+
 
 GRAD_CASES = ["grads_vanilla_ktd", "grads_series_ktd", "grads_parallel_ktd"]
 
@@ -24,11 +56,11 @@ def _model(mode, seed, lib):
     from maed_b200.models import MAED
     m = MAED("ste", 6, 12, mode, "ktd", 1024)
     synth.fill_module_(m, seed)
-    return m.cuda().train().enable_training(True, dropout_p=0.0)
+    return m.to(DEV).train().enable_training(True, dropout_p=0.0)
 
 
 def _probes(nt, seed):
-    return [synth.synth_tensor("grad_probe.%s" % k, (nt, n), seed).cuda() for k, n in (("pose", 144), ("shape", 10), ("cam", 3))]
+    return [synth.synth_tensor("grad_probe.%s" % k, (nt, n), seed).to(DEV) for k, n in (("pose", 144), ("shape", 10), ("cam", 3))]
 
 
 def _loss(out, A, B, C_):
@@ -44,8 +76,10 @@ def _digest(g, nsamp=8):
 
 @pytest.mark.parametrize("mode", ["vanilla", "series", "parallel"])
 def test_tape_forward_matches_inference(lib, mode):
+    if mode != "parallel":
+        _slow_on_emu()
     m = _model(mode, 21, lib)
-    x = synth.synth_frames(1, 3, 21).cuda()
+    x = synth.synth_frames(1, 3 if DEV == "cuda" else 2, 21).to(DEV)
     out = m(x)
     with torch.no_grad():
         ref = m.eval()(x, _debug=True)
@@ -57,11 +91,13 @@ def test_tape_forward_matches_inference(lib, mode):
 
 @pytest.mark.parametrize("name", GRAD_CASES)
 def test_gradients_match_reference_digests(lib, name):
+    if name != "grads_series_ktd":
+        _slow_on_emu()
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     N, T, seed = [int(v) for v in z["meta"]]
     m = _model(str(z["mode"]), seed, lib)
     A, B, C_ = _probes(N * T, seed)
-    loss = _loss(m(synth.synth_frames(N, T, seed).cuda()), A, B, C_)
+    loss = _loss(m(synth.synth_frames(N, T, seed).to(DEV)), A, B, C_)
     assert abs(loss.item() - float(z["loss"])) < 1e-3 * max(1.0, abs(float(z["loss"])))
     loss.backward()
     grads = {k: p.grad for k, p in m.named_parameters()}
@@ -82,11 +118,12 @@ def test_gradients_match_reference_digests(lib, name):
 
 def test_gradients_match_oracle_autograd(lib):
     """Every entry of every parameter gradient against autograd over the CPU oracle (parallel mode, 2 clips x 2 frames)."""
+    _slow_on_emu()
     seed, N, T = 33, 2, 2
     m = _model("parallel", seed, lib)
     A, B, C_ = _probes(N * T, seed)
     x = synth.synth_frames(N, T, seed)
-    _loss(m(x.cuda()), A, B, C_).backward()
+    _loss(m(x.to(DEV)), A, B, C_).backward()
     sd = {k: v.cpu() for k, v in state_dict_of(m).items()}
     _, ref, _ = O.maed_param_grads(x, sd, A.cpu(), B.cpu(), C_.cpu(), "parallel", "ktd")
     worst = ("", 0.0)
@@ -100,8 +137,9 @@ def test_gradients_match_oracle_autograd(lib):
 
 def test_loss_scale_invariance_and_determinism(lib):
     m = _model("vanilla", 5, lib)
-    x = synth.synth_frames(1, 2, 5).cuda()
-    A, B, C_ = _probes(2, 5)
+    nt = 2 if DEV == "cuda" else 1
+    x = synth.synth_frames(1, nt, 5).to(DEV)
+    A, B, C_ = _probes(nt, 5)
     gs = []
     for scale in (4096.0, 4096.0, 256.0):
         m.zero_grad(set_to_none=True)
@@ -116,25 +154,30 @@ def test_loss_scale_invariance_and_determinism(lib):
 def test_fused_adam_matches_torch_adam(lib):
     from maed_b200.train import FusedAdam
     m1, m2 = _model("vanilla", 6, lib), _model("vanilla", 6, lib)
-    x = synth.synth_frames(1, 2, 6).cuda()
-    A, B, C_ = _probes(2, 6)
+    nt = 2 if DEV == "cuda" else 1
+    x = synth.synth_frames(1, nt, 6).to(DEV)
+    A, B, C_ = _probes(nt, 6)
     o1 = FusedAdam.for_model(m1, lr=1e-4, weight_decay=1e-5)
     o2 = torch.optim.Adam([{"params": p, "name": n} for n, p in m2.named_parameters()], lr=1e-4, weight_decay=1e-5)
-    for _ in range(2):
+    # step 1 sees identical gradients: the two optimisers must agree to rounding.  The 1e-9 parameter differences that
+    # leaves are amplified to ~1e-2 in the step-2 gradients (random weight-standardised backbone, ReLU / arg-max flips), so
+    # the second comparison only guards against gross errors such as stale derived weights.
+    for step, tol in ((1, 1e-7), (2, 2e-4)):
         for m, o in ((m1, o1), (m2, o2)):
             o.zero_grad(set_to_none=True)
             _loss(m(x), A, B, C_).backward()
             o.step()
-    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
-        assert rel_err(a, b) < 1e-5, k
+        for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+            assert rel_err(a, b) < tol, (step, k)
 
 
 def test_short_fit_reduces_loss(lib):
     """A few Adam steps on one synthetic batch with the reference's parameter-space losses (theta MSE) must go down."""
     from maed_b200.train import FusedAdam
+    _slow_on_emu()
     m = _model("parallel", 7, lib)
-    x = synth.synth_frames(1, 4, 7).cuda()
-    target = torch.zeros(1, 4, 85, device="cuda")
+    x = synth.synth_frames(1, 4, 7).to(DEV)
+    target = torch.zeros(1, 4, 85, device=DEV)
     target[..., 0] = 1.0
     opt = FusedAdam.for_model(m, lr=1e-4)
     losses = []
