@@ -16,7 +16,7 @@ runs in libmaed_b200.so:
     box, gloo in the CPU tests): one all-reduce of the flat gradient buffer.
 
 STATUS: written at the end of round 1 after the GPU budget was spent — compiled, CPU-side logic tested, NOT yet run on a
-B200.  The GPU tests (tests/test_bwd_ops_gpu.py, tests/test_train_gpu.py) are skipped unless MAED_B200_TRAIN_TESTS=1.
+B200.  The GPU tests (tests/test_bwd_ops.py, tests/test_train.py) are skipped unless MAED_B200_TRAIN_TESTS=1.
 """
 import ctypes as C
 

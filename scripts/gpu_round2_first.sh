@@ -4,10 +4,10 @@
 mkdir -p gpurun_out
 echo "=== validated suite"; timeout 900 python -m pytest -q -m gpu --timeout 300 tests > gpurun_out/tests.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/tests.log
 export MAED_B200_TRAIN_TESTS=1
-echo "=== backward kernels"; timeout 900 python -m pytest -q -m gpu --timeout 300 tests/test_bwd_ops_gpu.py > gpurun_out/bwd_ops.log 2>&1; echo "exit $?"
+echo "=== backward kernels"; timeout 900 python -m pytest -q -m gpu --timeout 300 tests/test_bwd_ops.py > gpurun_out/bwd_ops.log 2>&1; echo "exit $?"
 grep -E "passed|failed|^FAILED|^ERROR" gpurun_out/bwd_ops.log | tail -n 45
-echo "=== SMPL tier"; timeout 600 python -m pytest -q -m gpu --timeout 300 tests/test_smpl_gpu.py > gpurun_out/smpl.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/smpl.log
-echo "=== training path"; timeout 1200 python -m pytest -q -m gpu --timeout 600 -s tests/test_train_gpu.py > gpurun_out/train.log 2>&1; echo "exit $?"
+echo "=== SMPL tier"; timeout 600 python -m pytest -q -m gpu --timeout 300 tests/test_smpl.py > gpurun_out/smpl.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/smpl.log
+echo "=== training path"; timeout 1200 python -m pytest -q -m gpu --timeout 600 -s tests/test_train.py > gpurun_out/train.log 2>&1; echo "exit $?"
 grep -E "passed|failed|^FAILED|^ERROR|worst" gpurun_out/train.log | tail -n 30
 unset MAED_B200_TRAIN_TESTS
 M=sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum

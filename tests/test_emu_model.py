@@ -77,8 +77,9 @@ def test_emulated_training_matches_reference_gradients(harness, name):
         serr = np.abs(samp - ref_samp).max() / max(rms, 1e-20)
         if max(err, serr / 25) > worst[1]:
             worst = (k, max(err, serr / 25))
-        # fp32 rounding is amplified ~80x by the weight-standardised backbone: 1e-2 on the norm
-        assert err < 1e-2, "%s: |g| %.6e vs reference %.6e" % (k, norm, ref_norm)
+        # fp32 noise floor: the oracle's own fp32 vs fp64 autograd differ by up to 1.7e-2 per parameter (median 2e-3) on this
+        # random weight-standardised network; observed here: worst 5.8e-3
+        assert err < 2e-2, "%s: |g| %.6e vs reference %.6e" % (k, norm, ref_norm)
         assert serr < 0.25, "%s: sampled entries off by %.3f rms" % (k, serr)
     print("%s: worst %s %.2e" % (name, worst[0], worst[1]))
     # a different loss scale must give the same gradients (scale enters and leaves exactly once everywhere)
