@@ -24,13 +24,15 @@ def test_unvalidated_gpu_paths_in_a_subprocess():
     if os.environ.get("MAED_B200_TRAIN_TESTS") or os.environ.get("MAED_B200_NO_CANARY"):
         pytest.skip("the gated tests run in-process (MAED_B200_TRAIN_TESTS) or the canary is disabled")
     env = dict(os.environ, MAED_B200_TRAIN_TESTS="1", MAED_B200_NO_CANARY="1")
-    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_bwd_ops.py",
-           "tests/test_smpl.py", "tests/test_train.py"]
+    # per-test limit (pytest-timeout, thread method: dumps the stacks and ends the subprocess, which is what a hung kernel
+    # needs) + an overall limit well inside any sensible budget for the whole GPU suite
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "--timeout", "90",
+           "--timeout-method", "thread", "tests/test_bwd_ops.py", "tests/test_smpl.py", "tests/test_train.py"]
     try:
-        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=420)
         out, code = r.stdout + r.stderr, r.returncode
     except subprocess.TimeoutExpired as e:
-        out = ((e.stdout or b"").decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")) + "\nTIMEOUT after 900 s"
+        out = ((e.stdout or b"").decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")) + "\nTIMEOUT after 420 s"
         code = -1
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
