@@ -75,6 +75,16 @@ int maed_op_groupnorm(const float* x, int n_img, int HW, int C, const float* gam
 /* stem: GN + ReLU + MaxPool2dSame(3,2) (reference resnetv2.py:61-72,245-274) */
 int maed_op_groupnorm_maxpool(const float* x, int n_img, int H, int W, int C, const float* gamma, const float* beta,
                               float eps, void* out_hi, long long out_plane, double* stats_scratch, void* stream);
+/* 'cnn' encoder (torchvision ResNet-50, reference lib/models/maed.py:35-37), inference:
+ * eval-mode BatchNorm2d folded into the preceding bias-free conv: w_out[co,:] = w[co,:] * s, bias_out[co] = beta - mean * s
+ * with s = gamma / sqrt(var + eps); E = Cin*KH*KW weights per output channel. */
+int maed_op_fold_bn(const float* w, int Cout, long long E, const float* gamma, const float* beta, const float* mean,
+                    const float* var, float eps, float* w_out, float* bias_out, void* stream);
+/* nn.MaxPool2d(3, stride 2, padding 1) on an fp32 NHWC map [n,H,W,C] -> fp32 NHWC and / or planes (either may be NULL) */
+int maed_op_maxpool3x3s2(const float* x, int n_img, int H, int W, int C, float* out_f32, void* out_hi, long long plane,
+                         void* stream);
+/* x = relu(x) in place (fp32, n elements) and as planes: closes a bottleneck after the GEMM epilogue added the identity */
+int maed_op_relu_split(float* x, long long n, void* out_hi, long long plane, void* stream);
 /* LayerNorm(eps) rows of fp32 -> planes (reference vision_transformer.py:258-261) */
 int maed_op_layernorm(const float* x, long long row_stride, const float* gamma, const float* beta, int rows, int C,
                       float eps, void* out_hi, long long out_plane, void* stream);
@@ -90,7 +100,7 @@ int maed_op_decode_outputs(const float* pose6d, const float* shape, const float*
                            int n_joints, float* rotmat, float* theta, float* kp2d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Whole-model engine: MAED(encoder='ste').forward (reference lib/models/maed.py:52-66).
+ * Whole-model engine: MAED(encoder='ste' | 'cnn').forward (reference lib/models/maed.py:52-66).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct maed_engine maed_engine;
 typedef struct maed_config {
@@ -101,9 +111,12 @@ typedef struct maed_config {
   int hidden_dim;   /* MODEL.DECODER.HIDDEN_DIM (1024) */
   int nsplit;       /* 3 split-fp16 operands (parity mode), 1 plain fp16 (fast mode) */
   int temp_frames;  /* rows of encoder.temp_embed (16 in the reference; 32 for the T=32 extension) */
+  int encoder;      /* MODEL.ENCODER.BACKBONE: 0 'ste' (hybrid ResNetV2 + STE blocks, 768 features), 1 'cnn' (torchvision
+                       ResNet-50 conv+BN+ReLU, 2048 features, reference lib/models/maed.py:35-37; inference only,
+                       BatchNorm uses its running statistics; num_blocks / num_heads / mode are ignored) */
 } maed_config;
 typedef struct maed_outputs {
-  float* feat;       /* [N*T, 768]  encoder feature (MAED.extract_feature) */
+  float* feat;       /* [N*T, 768] ('cnn': [N*T, 2048])  encoder feature (MAED.extract_feature) */
   float* pose6d;     /* [N*T, 144] */
   float* shape;      /* [N*T, 10] */
   float* cam;        /* [N*T, 3] */

@@ -20,7 +20,7 @@ _Z = C.c_size_t
 
 class MaedConfig(C.Structure):
     _fields_ = [("num_blocks", _I), ("num_heads", _I), ("mode", _I), ("decoder", _I), ("hidden_dim", _I),
-                ("nsplit", _I), ("temp_frames", _I)]
+                ("nsplit", _I), ("temp_frames", _I), ("encoder", _I)]
 
 
 class MaedOutputs(C.Structure):
@@ -40,6 +40,7 @@ class MaedSmplAssets(C.Structure):
 _U = C.c_ulonglong
 MODES = {"vanilla": 0, "parallel": 1, "series": 2, "coupling": 3, "temporal": 4}
 DECODERS = {"ktd": 0, "iterative": 1}
+ENCODERS = {"ste": 0, "cnn": 1}
 TAP_NAMES = ["stem", "stage0", "stage1", "stage2", "embed"] + ["block%d" % i for i in range(8)]
 
 # name -> (restype, argtypes); every symbol declared in include/maed_b200.h
@@ -49,6 +50,9 @@ SIGNATURES = {
     "maed_launch_count": (_L, []),
     "maed_op_gemm": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _L, _I, _I, _P]),
     "maed_op_conv_gemm": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _I, _P]),
+    "maed_op_fold_bn": (_I, [_P, _I, _L, _P, _P, _P, _P, _F, _P, _P, _P]),
+    "maed_op_maxpool3x3s2": (_I, [_P, _I, _I, _I, _I, _P, _P, _L, _P]),
+    "maed_op_relu_split": (_I, [_P, _L, _P, _L, _P]),
     "maed_op_split_f32": (_I, [_P, _P, _L, _L, _P]),
     "maed_op_prep_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     "maed_op_im2col_stem": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),

@@ -44,6 +44,18 @@ int maed_op_conv_gemm(const void* A, long long a_plane, const void* B, long long
   return launch_gemm(g, (cudaStream_t)stream);
 }
 
+int maed_op_fold_bn(const float* w, int Cout, long long E, const float* gamma, const float* beta, const float* mean,
+                    const float* var, float eps, float* w_out, float* bias_out, void* stream) {
+  return fold_bn(w, Cout, E, gamma, beta, mean, var, eps, w_out, bias_out, (cudaStream_t)stream);
+}
+int maed_op_maxpool3x3s2(const float* x, int n_img, int H, int W, int C, float* out_f32, void* out_hi, long long plane,
+                         void* stream) {
+  return maxpool3x3s2(x, n_img, H, W, C, out_f32, (__half*)out_hi, plane, (cudaStream_t)stream);
+}
+int maed_op_relu_split(float* x, long long n, void* out_hi, long long plane, void* stream) {
+  return relu_split(x, n, (__half*)out_hi, plane, (cudaStream_t)stream);
+}
+
 int maed_op_split_f32(const float* in, void* out_hi, long long plane, long long n, void* stream) {
   return split_f32(in, (__half*)out_hi, plane, n, (cudaStream_t)stream);
 }

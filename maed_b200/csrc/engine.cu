@@ -56,6 +56,11 @@ static void build_tables(Engine& e) {
   const int C = 768, H = c.num_heads;
   (void)H;
   const std::string enc = "encoder.";
+  const bool cnn = c.encoder == ENC_CNN;
+  e.i_cls = e.i_pos = e.i_temp = e.i_stem_w = e.i_stem_g = e.i_proj_w = e.i_proj_b = e.i_norm = e.i_pl_w = e.i_pl_b = -1;
+  if (cnn) {
+    cnn_add_params(e, add_param);
+  } else {
   e.i_cls = add_param(e, enc + "cls_token", C);
   e.i_pos = add_param(e, enc + "pos_embed", 197 * C);
   const bool has_temp = (c.mode == MODE_PARALLEL || c.mode == MODE_SERIES || c.mode == MODE_COUPLING);
@@ -117,9 +122,11 @@ static void build_tables(Engine& e) {
   add_param(e, enc + "norm.bias", C);
   e.i_pl_w = add_param(e, enc + "pre_logits.fc.weight", (long long)C * C);
   e.i_pl_b = add_param(e, enc + "pre_logits.fc.bias", C);
+  }  // !cnn
   const int HD = c.hidden_dim;
+  const int F = e.feat_dim();
   const std::string dec = "decoder.";
-  const int fc1_in = c.decoder == DEC_KTD ? C : C + 144 + 10 + 3;
+  const int fc1_in = c.decoder == DEC_KTD ? F : F + 144 + 10 + 3;
   e.i_fc1_w = add_param(e, dec + "fc1.weight", (long long)HD * fc1_in);
   e.i_fc1_b = add_param(e, dec + "fc1.bias", HD);
   e.i_fc2_w = add_param(e, dec + "fc2.weight", (long long)HD * HD);
@@ -148,8 +155,12 @@ static void build_tables(Engine& e) {
   // ---- packed (derived) weights: fp16 planes, always laid out for two planes (nsplit=1 uses the first)
   size_t off = 0;
   auto planes = [&](long long elems) { size_t o = off; off = align_up(off + (size_t)elems * 2 * 2); return o; };
+  e.off_stem = e.off_proj = e.off_pl = 0;
+  if (cnn) {
+    cnn_add_packed(e, off);
+  } else {
   e.off_stem = planes(64LL * kStemKPad);
-  prev = 64;
+  int prev = 64;
   for (int s = 0; s < 3; ++s) {
     const int out = kStageOut[s], mid = out / 4;
     for (int b = 0; b < kStageDepth[s]; ++b) {
@@ -173,7 +184,8 @@ static void build_tables(Engine& e) {
     e.blk_off.push_back(so);
   }
   e.off_pl = planes((long long)C * C);
-  e.off_kfc1 = planes((long long)HD * C);
+  }  // !cnn
+  e.off_kfc1 = planes((long long)HD * F);
   e.off_kfc2 = planes((long long)HD * HD);
   e.off_kheads = planes(192LL * HD);
   e.off_kheads_b = off; off = align_up(off + 192 * 4);
@@ -186,10 +198,13 @@ static void build_tables(Engine& e) {
 // ------------------------------------------------------------------------------------------ C-level API
 int engine_create(const EngineConfig* cfg, Engine** out) {
   MAED_CHECK_ARG(cfg && out, "engine_create: null argument");
-  MAED_CHECK_ARG(cfg->num_heads == 12, "engine: num_heads=%d unsupported (head_dim must be 64: num_heads=12)",
-                 cfg->num_heads);
-  MAED_CHECK_ARG(cfg->num_blocks >= 1 && cfg->num_blocks <= 64, "engine: num_blocks=%d", cfg->num_blocks);
-  MAED_CHECK_ARG(cfg->mode >= 0 && cfg->mode <= MODE_TEMPORAL, "engine: unknown st_mode %d", cfg->mode);
+  MAED_CHECK_ARG(cfg->encoder == ENC_STE || cfg->encoder == ENC_CNN, "engine: unknown encoder %d", cfg->encoder);
+  if (cfg->encoder == ENC_STE) {
+    MAED_CHECK_ARG(cfg->num_heads == 12, "engine: num_heads=%d unsupported (head_dim must be 64: num_heads=12)",
+                   cfg->num_heads);
+    MAED_CHECK_ARG(cfg->num_blocks >= 1 && cfg->num_blocks <= 64, "engine: num_blocks=%d", cfg->num_blocks);
+    MAED_CHECK_ARG(cfg->mode >= 0 && cfg->mode <= MODE_TEMPORAL, "engine: unknown st_mode %d", cfg->mode);
+  }
   MAED_CHECK_ARG(cfg->decoder == DEC_KTD || cfg->decoder == DEC_ITERATIVE, "engine: unknown decoder %d", cfg->decoder);
   MAED_CHECK_ARG(cfg->nsplit == 1 || cfg->nsplit == 3, "engine: nsplit must be 1 or 3");
   MAED_CHECK_ARG(cfg->hidden_dim >= 64 && cfg->hidden_dim <= 4096, "engine: hidden_dim=%d", cfg->hidden_dim);
@@ -217,15 +232,26 @@ struct Workspace {
   float* alpha; float* logits; float* vbuf;
   long long ln_plane, qkv_plane, ao_plane, hid_plane;
   // tail
-  float* cls; float* h1; float* h2; float* base; float* xc; float* pose_it; float* shape_it; float* cam_it;
-  float* tokscratch; __half* alpha_p; __half* tail_a; __half* tail_b; long long tail_plane;
+  float* cls; float* tokscratch; __half* alpha_p;
+  TailWs tail;
   size_t total;
 };
 static constexpr long long kColPerImg = 12544LL * kStemKPad;      // largest explicit-im2col matrix (stem)
 static constexpr long long kActPerImg = 3136LL * 256;             // largest activation (stage-0 output)
+void carve_tail(const Engine& e, int BT, Carver& c, TailWs& t) {
+  const int HD = e.cfg.hidden_dim, F = e.feat_dim();
+  t.h1 = (float*)c.take((size_t)BT * HD * 4);
+  t.h2 = (float*)c.take((size_t)BT * HD * 4);
+  t.base = (float*)c.take((size_t)BT * 192 * 4);
+  t.xc = (float*)c.take((size_t)BT * (F + 160) * 4);                // iterative: [feat | pose6d | shape | cam] (spin.py:64)
+  t.tail_plane = (long long)BT * std::max(std::max(1024, HD), F);
+  t.tail_a = (__half*)c.take((size_t)t.tail_plane * 4);
+  t.tail_b = (__half*)c.take((size_t)t.tail_plane * 4);
+}
+
 static void carve(const Engine& e, int BT, uint8_t* base, Workspace& w) {
-  size_t off = 0;
-  auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off = align_up(off + bytes); return p; };
+  Carver cv(base);
+  auto take = [&](size_t bytes) { return (uint8_t*)cv.take(bytes); };
   const long long rows = (long long)BT * 197;
   w.col_plane = kColPerImg * BT;
   w.act_plane = kActPerImg * BT;
@@ -244,23 +270,14 @@ static void carve(const Engine& e, int BT, uint8_t* base, Workspace& w) {
   w.alpha = (float*)take((size_t)BT * 1536 * 4);
   w.logits = (float*)take((size_t)BT * 1536 * 4);
   w.vbuf = (float*)take((size_t)BT * 768 * 4);
-  const int HD = e.cfg.hidden_dim;
   w.cls = (float*)take((size_t)BT * 768 * 4);
-  w.h1 = (float*)take((size_t)BT * HD * 4);
-  w.h2 = (float*)take((size_t)BT * HD * 4);
-  w.base = (float*)take((size_t)BT * 192 * 4);
-  w.xc = (float*)take((size_t)BT * 1024 * 4);
-  w.pose_it = (float*)take((size_t)BT * 144 * 4);
-  w.shape_it = (float*)take((size_t)BT * 16 * 4);
-  w.cam_it = (float*)take((size_t)BT * 4 * 4);
   w.tokscratch = (float*)take((size_t)BT * kTokenChunks * 1536 * 4);
   w.alpha_p = (__half*)take((size_t)BT * 1536 * 4);
-  w.tail_plane = (long long)BT * 1024 > (long long)BT * HD ? (long long)BT * 1024 : (long long)BT * HD;
-  w.tail_a = (__half*)take((size_t)w.tail_plane * 4);
-  w.tail_b = (__half*)take((size_t)w.tail_plane * 4);
-  w.total = off;
+  carve_tail(e, BT, cv, w.tail);
+  w.total = cv.off;
 }
 size_t engine_workspace_bytes(const Engine* e, int BT) {
+  if (e->cfg.encoder == ENC_CNN) return cnn_workspace_bytes(*e, BT);
   Workspace w;
   carve(*e, BT, nullptr, w);
   return w.total + 1024;
@@ -272,6 +289,9 @@ int engine_pack(const Engine* e, const void* const* params, void* packed, cudaSt
   uint8_t* pk = (uint8_t*)packed;
   auto P = [&](int i) { return (const float*)params[i]; };
   auto H = [&](size_t off) { return (__half*)(pk + off); };
+  if (e->cfg.encoder == ENC_CNN) {
+    MAED_PROPAGATE(cnn_pack(*e, params, packed, st));
+  } else {
   MAED_PROPAGATE(prep_conv_weight(P(e->i_stem_w), 64, 3, 7, 7, kStemKPad, 1, H(e->off_stem), 64LL * kStemKPad, st));
   int prev = 64, bi = 0;
   for (int s = 0; s < 3; ++s) {
@@ -299,6 +319,7 @@ int engine_pack(const Engine* e, const void* const* params, void* packed, cudaSt
     if (e->cfg.mode == MODE_PARALLEL) MAED_PROPAGATE(split_f32(P(ix.ts_w), H(of.ts), 4 * CC, 4 * CC, st));
   }
   MAED_PROPAGATE(split_f32(P(e->i_pl_w), H(e->off_pl), CC, CC, st));
+  }  // !cnn
   if (e->cfg.decoder == DEC_KTD) {
     // joint_regs.j.weight [6, HD + 6k] -> Wx rows (first HD columns), ancestor blocks (last 6k columns), biases
     const int HD = e->cfg.hidden_dim;
@@ -321,7 +342,8 @@ int engine_pack(const Engine* e, const void* const* params, void* packed, cudaSt
     }
     // tensor-core operands of the tail: fc1, fc2 and one [192, HD] head matrix = [24 joint bases (144) | shape (10) |
     // cam (3) | 35 zero rows] with its bias vector
-    MAED_PROPAGATE(split_f32(P(e->i_fc1_w), H(e->off_kfc1), (long long)HD * 768, (long long)HD * 768, st));
+    const long long F = e->feat_dim();
+    MAED_PROPAGATE(split_f32(P(e->i_fc1_w), H(e->off_kfc1), HD * F, HD * F, st));
     MAED_PROPAGATE(split_f32(P(e->i_fc2_w), H(e->off_kfc2), (long long)HD * HD, (long long)HD * HD, st));
     float* hb = (float*)(pk + e->off_kheads_b);
     MAED_CUDA_CHECK(cudaMemsetAsync(pk + e->off_kheads, 0, (size_t)192 * HD * 4, st));
@@ -389,6 +411,7 @@ int engine_forward(const Engine* ep, const void* const* params, const void* pack
   const EngineConfig& c = e.cfg;
   const int BT = N * T;
   MAED_CHECK_ARG(N >= 1 && T >= 1, "engine_forward: empty batch N=%d T=%d", N, T);
+  if (c.encoder == ENC_CNN) return cnn_forward(e, params, packed, x_in, N, T, workspace, workspace_bytes, outs, taps, st);
   const bool has_temp = e.i_temp >= 0;
   MAED_CHECK_ARG(!has_temp || T <= c.temp_frames, "engine_forward: seqlen T=%d exceeds temp_embed frames %d "
                  "(reference vision_transformer.py:364,398 raises a broadcast error here)", T, c.temp_frames);
@@ -517,7 +540,6 @@ int engine_forward(const Engine* ep, const void* const* params, const void* pack
   // ------------------------------------------------------------------------------------------ tail
   // The tail always runs in split precision (nsplit = 3), also in the fp16 fast mode: its GEMMs feed the outputs
   // without a damping residual path and are ~0.5 GFLOP.
-  const int HD = c.hidden_dim;
   auto tail_tc = [&](const __half* A, long long a_plane, int K, size_t w_off, int Nout, const float* bias, int act,
                      int out_mode, void* out, long long out_plane) -> int {
     GemmArgs g;
@@ -527,8 +549,31 @@ int engine_forward(const Engine* ep, const void* const* params, const void* pack
     g.ldc = Nout;
     return launch_gemm(g, st);
   };
-  MAED_PROPAGATE(layernorm_planes(w.x, (long long)ntok * C, P(e.i_norm), P(e.i_norm + 1), BT, C, 1e-6f, w.tail_a, w.tail_plane, st));
-  MAED_PROPAGATE(tail_tc(w.tail_a, w.tail_plane, C, e.off_pl, C, P(e.i_pl_b), ACT_TANH, OUT_F32, outs->feat, 0));
+  MAED_PROPAGATE(layernorm_planes(w.x, (long long)ntok * C, P(e.i_norm), P(e.i_norm + 1), BT, C, 1e-6f, w.tail.tail_a,
+                                  w.tail.tail_plane, st));
+  MAED_PROPAGATE(tail_tc(w.tail.tail_a, w.tail.tail_plane, C, e.off_pl, C, P(e.i_pl_b), ACT_TANH, OUT_F32, outs->feat, 0));
+  return run_decoder(e, params, pk, BT, w.tail, outs, st);
+}
+
+// Decoder from the encoder feature outs->feat [BT, F] (F = 768 'ste', 2048 'cnn'): KTD (ktd.py:69-88) as three
+// split-precision tensor-core GEMMs + the kinematic-tree pass, or the iterative regressor (spin.py:51-74) in fp32;
+// then rot6d -> rotmat -> angle-axis, theta, kp_2d.
+int run_decoder(const Engine& e, const void* const* params, const uint8_t* pk, int BT, const TailWs& w, const EngineOutputs* outs,
+                cudaStream_t st) {
+  const EngineConfig& c = e.cfg;
+  auto P = [&](int i) { return (const float*)params[i]; };
+  auto Hh = [&](size_t off) { return (const __half*)(pk + off); };
+  const int HD = c.hidden_dim;
+  const int C = e.feat_dim();
+  auto tail_tc = [&](const __half* A, long long a_plane, int K, size_t w_off, int Nout, const float* bias, int act,
+                     int out_mode, void* out, long long out_plane) -> int {
+    GemmArgs g;
+    g.nsplit = 3;
+    g.A = A; g.a_plane = a_plane; g.B = Hh(w_off); g.b_plane = (long long)Nout * K;
+    g.M = BT; g.N = Nout; g.K = K; g.bias = bias; g.act = act; g.out_mode = out_mode; g.out = out; g.out_plane = out_plane;
+    g.ldc = Nout;
+    return launch_gemm(g, st);
+  };
   if (c.decoder == DEC_KTD) {
     MAED_PROPAGATE(split_f32(outs->feat, w.tail_a, w.tail_plane, (long long)BT * C, st));
     MAED_PROPAGATE(tail_tc(w.tail_a, w.tail_plane, C, e.off_kfc1, HD, P(e.i_fc1_b), ACT_NONE, OUT_F16_SPLIT, w.tail_b, w.tail_plane));
@@ -550,6 +595,8 @@ int engine_forward(const Engine* ep, const void* const* params, const void* pack
       MAED_PROPAGATE(linear_f32(w.h2, HD, P(e.i_cam_w), HD, P(e.i_cam_b), BT, 3, HD, 0, outs->cam, 3, outs->cam, 3, st));
     }
   }
+  MAED_PROPAGATE(decode_outputs(outs->pose6d, outs->shape, outs->cam, BT, outs->kp3d, outs->n_joints, outs->rotmat, outs->theta,
+                                outs->kp2d, st));
   MAED_PROPAGATE(decode_outputs(outs->pose6d, outs->shape, outs->cam, BT, outs->kp3d, outs->n_joints, outs->rotmat, outs->theta,
                                 outs->kp2d, st));
   return MAED_OK;

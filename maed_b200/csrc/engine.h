@@ -6,6 +6,7 @@ namespace maed {
 
 enum : int { MODE_VANILLA = 0, MODE_PARALLEL = 1, MODE_SERIES = 2, MODE_COUPLING = 3, MODE_TEMPORAL = 4 };
 enum : int { DEC_KTD = 0, DEC_ITERATIVE = 1 };
+enum : int { ENC_STE = 0, ENC_CNN = 1 };
 // debug taps (fp32 copies of intermediates, NHWC for the backbone): indices into the `taps` array
 enum : int { TAP_STEM = 0, TAP_STAGE0 = 1, TAP_STAGE1 = 2, TAP_STAGE2 = 3, TAP_EMBED = 4, TAP_BLOCK0 = 5, TAP_COUNT = 13 };
 
@@ -17,10 +18,12 @@ struct EngineConfig {
   int hidden_dim;     // decoder hidden size (1024)
   int nsplit;         // 3: split-fp16 (parity mode), 1: plain fp16 (fast, fails the 1e-3 gate)
   int temp_frames;    // rows of temp_embed (16 in the reference)
+  int encoder;        // ENC_STE (hybrid ResNetV2 + STE, feature 768) or ENC_CNN (torchvision ResNet-50, feature 2048;
+                      // reference maed.py:35-37, inference only); num_blocks / num_heads / mode are ignored for ENC_CNN
 };
 
 struct EngineOutputs {
-  float* feat;        // [BT, 768]
+  float* feat;        // [BT, 768] (ENC_CNN: [BT, 2048])
   float* pose6d;      // [BT, 144]
   float* shape;       // [BT, 10]
   float* cam;         // [BT, 3]

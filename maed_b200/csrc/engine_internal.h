@@ -39,8 +39,45 @@ struct Engine {
   size_t off_pl, off_kfc1, off_kfc2, off_kheads, off_kheads_b;   // tensor-core planes of the tail (KTD)
   size_t packed_bytes;
   bool fuse_gn = true;                      // MAED_B200_FUSE_GN=0 selects the unfused conv / gn_stats / gn_apply kernels
-  int feat_dim() const { return 768; }
+  // 'cnn' encoder (torchvision ResNet-50, cnn_engine.cu): the 53 conv+BN pairs in forward order
+  // (stem; per bottleneck: [downsample], conv1, conv2, conv3)
+  struct CnnConv {
+    int w, bn;                              // parameter indices: conv weight; bn.weight (bias, running_mean, running_var follow)
+    int cin, cout, k, stride, k_pad;        // k_pad: GEMM K (k*k*cin, stem padded to 152)
+    size_t off_w, off_b;                    // packed: BN-folded weight planes [cout][k_pad]; folded bias fp32 [cout]
+  };
+  std::vector<CnnConv> cnn;
+  size_t off_cnn_scratch = 0;               // fp32 scratch for one BN-scaled weight tensor (pack time only)
+  int feat_dim() const { return cfg.encoder == ENC_CNN ? 2048 : 768; }
   int np() const { return cfg.nsplit == 3 ? 2 : 1; }
 };
+
+// ---- workspace carving shared by the two encoders
+struct Carver {
+  uint8_t* base; size_t off = 0;
+  explicit Carver(uint8_t* b) : base(b) {}
+  void* take(size_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off = (off + bytes + 1023) / 1024 * 1024;
+    return p;
+  }
+};
+// buffers of the decoder tail (KTD: split-precision tensor-core GEMMs; iterative: fp32)
+struct TailWs {
+  float* h1; float* h2; float* base; float* xc;
+  __half* tail_a; __half* tail_b; long long tail_plane;
+};
+void carve_tail(const Engine& e, int BT, Carver& c, TailWs& t);
+// decoder (reference ktd.py:69-124 / spin.py:51-110) from the encoder feature in outs->feat [BT, feat_dim]
+int run_decoder(const Engine& e, const void* const* params, const uint8_t* packed, int BT, const TailWs& t,
+                const EngineOutputs* outs, cudaStream_t st);
+
+// ---- 'cnn' encoder (cnn_engine.cu)
+void cnn_add_params(Engine& e, int (*add_param)(Engine&, const std::string&, long long));
+void cnn_add_packed(Engine& e, size_t& off);
+size_t cnn_workspace_bytes(const Engine& e, int BT);
+int cnn_pack(const Engine& e, const void* const* params, void* packed, cudaStream_t st);
+int cnn_forward(const Engine& e, const void* const* params, const void* packed, const float* x, int N, int T, void* workspace,
+                size_t workspace_bytes, const EngineOutputs* outs, float* const* taps, cudaStream_t st);
 
 }  // namespace maed

@@ -46,6 +46,16 @@ int gn_apply(const float* x, const double* stats, const float* gamma, const floa
 int gn_apply_maxpool(const float* x, const double* stats, const float* gamma, const float* beta, int n_img, int H,
                      int W, int C, float eps, __half* out_hi, long long out_plane, cudaStream_t st);
 
+// ---- 'cnn' encoder (torchvision ResNet-50; cnn_kernels.cu)
+// eval-mode BatchNorm folded into the conv: w_out[co] = w[co] * s, bias_out[co] = beta - mean * s, s = gamma / sqrt(var + eps)
+int fold_bn(const float* w, int Cout, long long E, const float* gamma, const float* beta, const float* mean, const float* var,
+            float eps, float* w_out, float* bias_out, cudaStream_t st);
+// nn.MaxPool2d(3, 2, 1) on an fp32 NHWC map -> fp32 NHWC and / or planes (either output may be nullptr)
+int maxpool3x3s2(const float* x, int n_img, int H, int W, int C, float* out_f32, __half* out_hi, long long plane,
+                 cudaStream_t st);
+// x = relu(x) in place (fp32) and as planes
+int relu_split(float* x, long long n, __half* out_hi, long long plane, cudaStream_t st);
+
 // ---- STE elementwise
 // x[bt, 0] = cls + pos[0]; x[bt, 1+i] = tok[bt, i] + pos[1+i]; (+ temp[bt % T] when temp != nullptr)
 int embed_assemble(const float* tok, const float* cls, const float* pos, const float* temp, int BT, int T, int ntok,

@@ -254,9 +254,10 @@ int gemm_plain(const Ctx& c, const __half* A, long long a_plane, int M, int K, c
 }  // namespace
 
 // ================================================================================================ API
-size_t train_pack_bytes(const Engine* e) { return build_net(*e).tpack_bytes + 1024; }
+size_t train_pack_bytes(const Engine* e) { return e->cfg.encoder == ENC_STE ? build_net(*e).tpack_bytes + 1024 : 0; }
 
 size_t train_workspace_bytes(const Engine* e, int BT) {
+  if (e->cfg.encoder != ENC_STE) return 0;
   const Net net = build_net(*e);
   TrainWs w;
   carve(*e, net, BT, nullptr, w);
@@ -264,6 +265,8 @@ size_t train_workspace_bytes(const Engine* e, int BT) {
 }
 
 static int check_train_cfg(const Engine& e) {
+  MAED_CHECK_ARG(e.cfg.encoder == ENC_STE, "training supports encoder='ste' only (the 'cnn' encoder is inference-only: "
+                 "BatchNorm batch statistics and their backward are not built)");
   const int m = e.cfg.mode;
   MAED_CHECK_ARG(m == MODE_PARALLEL || m == MODE_SERIES || m == MODE_VANILLA,
                  "training supports st_mode parallel / series / vanilla (got mode %d)", m);
@@ -273,9 +276,10 @@ static int check_train_cfg(const Engine& e) {
 }
 
 int train_pack(const Engine* ep, const void* const* params, void* tpack, cudaStream_t st) {
+  MAED_CHECK_ARG(ep, "train_pack: null engine");
+  MAED_PROPAGATE(check_train_cfg(*ep));
   MAED_CHECK_ARG(ep && params && tpack, "train_pack: null argument");
   const Engine& e = *ep;
-  MAED_PROPAGATE(check_train_cfg(e));
   const Net net = build_net(e);
   uint8_t* tp = (uint8_t*)(((uintptr_t)tpack + 1023) & ~(uintptr_t)1023);
   auto P = [&](int i) { return (const float*)params[i]; };
@@ -334,9 +338,10 @@ static int conv_fwd(const Ctx& c, int l) {
 int train_forward(const Engine* ep, const void* const* params, const void* packed, const float* x_in, int N, int T,
                   void* workspace, size_t workspace_bytes, float dropout_p, unsigned long long seed, const TrainOutputs* outs,
                   cudaStream_t st) {
+  MAED_CHECK_ARG(ep, "train_forward: null engine");
+  MAED_PROPAGATE(check_train_cfg(*ep));
   MAED_CHECK_ARG(ep && params && packed && x_in && workspace && outs, "train_forward: null argument");
   const Engine& e = *ep;
-  MAED_PROPAGATE(check_train_cfg(e));
   const EngineConfig& cf = e.cfg;
   const int BT = N * T;
   MAED_CHECK_ARG(N >= 1 && T >= 1 && T <= 32, "train_forward: bad batch N=%d T=%d", N, T);
@@ -508,11 +513,12 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
 int train_backward(const Engine* ep, const void* const* params, const void* packed, const void* tpack, const float* x_in, int N,
                    int T, void* workspace, size_t workspace_bytes, const float* d_pose6d, const float* d_shape,
                    const float* d_cam, float loss_scale, float dropout_p, float* const* grads, cudaStream_t st) {
+  MAED_CHECK_ARG(ep, "train_backward: null engine");
+  MAED_PROPAGATE(check_train_cfg(*ep));
   MAED_CHECK_ARG(ep && params && packed && tpack && x_in && workspace && d_pose6d && d_shape && d_cam && grads,
                  "train_backward: null argument");
   MAED_CHECK_ARG(loss_scale > 0.f, "train_backward: loss_scale must be positive");
   const Engine& e = *ep;
-  MAED_PROPAGATE(check_train_cfg(e));
   const EngineConfig& cf = e.cfg;
   const int BT = N * T;
   const Net net = build_net(e);

@@ -8,7 +8,8 @@ Differences a caller can observe (documented in INTEGRATION.md):
   * inputs must be CUDA float32 tensors — there is no CPU / eager fallback, by design;
   * `forward` is inference-only unless `enable_training()` is called (the CUDA training path of maed_b200/train.py
     is written but not yet validated on a GPU; opt-in until then);
-  * `encoder='cnn'` (torchvision ResNet-50, stage-1 config) is not built yet -> NotImplementedError;
+  * `encoder='cnn'` (torchvision ResNet-50, stage-1 config) is inference-only: BatchNorm always uses its running
+    statistics (folded into the conv weights), the training path raises for it;
   * `decoder.smpl.*` buffers do not exist (smplx and the SMPL assets are absent): `verts`/`kp_3d` are zeros.
 """
 import ctypes as C
@@ -18,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from .modules import KTD, Regressor, STEncoder
+from .modules import KTD, CNNEncoder, Regressor, STEncoder
 
 
 def _default_precision():
@@ -38,14 +39,17 @@ class MAED(nn.Module):
         self.encoder_type = encoder
         self.decoder_type = decoder
         if encoder.lower() == "cnn":
-            raise NotImplementedError(
-                "encoder='cnn' (torchvision ResNet-50 + BatchNorm, reference maed.py:35-37) is a 'next' row of "
-                "the hot-path scope (SURVEY.md §8f-2) and is not built yet")
+            # torchvision ResNet-50, fc = Identity (reference maed.py:35-37; the stage-1 config).  Inference only:
+            # BatchNorm runs on its running statistics; num_blocks / num_heads / st_mode are ignored like in the reference
+            self.encoder = CNNEncoder()
+            if st_mode not in _lib.MODES:
+                st_mode = "vanilla"
         elif encoder.lower() == "ste":
             self.encoder = STEncoder(num_blocks, num_heads, st_mode, temp_frames=temp_frames)
         else:
             raise NotImplementedError(encoder)
-        feat_dim = 768            # what determine_output_feature_dim() measures for 'ste' (utils.py:185-198)
+        # what determine_output_feature_dim() measures (utils.py:185-198): 768 for 'ste', 2048 for 'cnn'
+        feat_dim = self.feat_dim = self.encoder.num_features
         if decoder.lower() == "ktd":
             self.decoder = KTD(feat_dim=feat_dim, hidden_dim=hidden_dim)
         elif decoder.lower() == "iterative":
@@ -56,7 +60,8 @@ class MAED(nn.Module):
             self.decoder.smpl.load_assets(kwargs["smpl_assets"])
         self.precision = precision or _default_precision()
         self._cfg = _lib.MaedConfig(num_blocks, num_heads, _lib.MODES[st_mode], _lib.DECODERS[decoder.lower()],
-                                    hidden_dim, 3 if self.precision == "split" else 1, temp_frames)
+                                    hidden_dim, 3 if self.precision == "split" else 1, temp_frames,
+                                    _lib.ENCODERS[encoder.lower()])
         self._engine = None
         self._packed = None
         self._packed_key = None
@@ -140,7 +145,7 @@ class MAED(nn.Module):
                 self._workspace = torch.empty(wbytes, dtype=torch.uint8, device=dev)
             f32 = dict(dtype=torch.float32, device=dev)
             nj = self.decoder.smpl.n_joints
-            o = {"feat": torch.empty(BT, 768, **f32), "pose6d": torch.empty(BT, 144, **f32),
+            o = {"feat": torch.empty(BT, self.feat_dim, **f32), "pose6d": torch.empty(BT, 144, **f32),
                  "shape": torch.empty(BT, 10, **f32), "cam": torch.empty(BT, 3, **f32),
                  "rotmat": torch.empty(BT, 24, 3, 3, **f32), "theta": torch.empty(BT, 85, **f32),
                  "kp_2d": torch.empty(BT, nj, 2, **f32)}
@@ -151,6 +156,8 @@ class MAED(nn.Module):
             if want_taps:
                 shapes = {"stem": (BT, 56, 56, 64), "stage0": (BT, 56, 56, 256), "stage1": (BT, 28, 28, 512),
                           "stage2": (BT, 14, 14, 1024), "embed": (BT, 197, 768)}
+                if self.encoder_type.lower() == "cnn":          # layer4's output arrives in the 'embed' slot
+                    shapes["embed"] = (BT, 7, 7, 2048)
                 for i in range(8):
                     shapes["block%d" % i] = (BT, 197, 768)
                 ptrs = []
@@ -170,7 +177,7 @@ class MAED(nn.Module):
     # ------------------------------------------------------------------------------------ public API
     @torch.no_grad()
     def extract_feature(self, x):
-        """reference maed.py:43-50: (N,T,3,H,W) -> (N,T,768)."""
+        """reference maed.py:43-50: (N,T,3,H,W) -> (N,T,768) ('cnn': 2048)."""
         N, T = x.shape[:2]
         return self._run(x)["feat"].reshape(N, T, -1)
 
@@ -178,6 +185,9 @@ class MAED(nn.Module):
         """Route train()-mode forwards (with autograd enabled) through the engine's training path
         (maed_b200/train.py: saved-activation tape + CUDA backward).  Opt-in while that path awaits its GPU validation;
         the environment variable MAED_B200_TRAINING=1 enables it for every model."""
+        if flag and self.encoder_type.lower() == "cnn":
+            raise NotImplementedError("the training path covers encoder='ste'; encoder='cnn' is inference-only "
+                                      "(BatchNorm batch statistics / SyncBN and their backward are not built)")
         self._training_enabled = bool(flag)
         self._train_dropout_p = dropout_p       # None: nn.Dropout() default 0.5 (ktd.py:54-56); 0.0 for parity runs
         return self

@@ -182,6 +182,58 @@ class STEncoder(_Holder):
             nn.init.trunc_normal_(self.temp_embed, std=0.02)
 
 
+class TVConv(_Holder):
+    """Bias-free nn.Conv2d of torchvision's ResNet: kaiming-normal fan_out / relu (torchvision models/resnet.py)."""
+
+    def __init__(self, cin, cout, k, stride=1):
+        super().__init__()
+        self.stride, self.kernel_size = stride, k
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k))
+        nn.init.kaiming_normal_(self.weight, mode="fan_out", nonlinearity="relu")
+
+
+class TVBatchNorm(_Holder):
+    """nn.BatchNorm2d state: affine parameters (1, 0) and the running statistics the inference path folds into the conv."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class TVBottleneck(_Holder):
+    """torchvision.models.resnet.Bottleneck (expansion 4, stride on conv2); downsample = Sequential(conv1x1, bn)."""
+
+    def __init__(self, cin, mid, stride, has_ds):
+        super().__init__()
+        self.conv1, self.bn1 = TVConv(cin, mid, 1), TVBatchNorm(mid)
+        self.conv2, self.bn2 = TVConv(mid, mid, 3, stride), TVBatchNorm(mid)
+        self.conv3, self.bn3 = TVConv(mid, 4 * mid, 1), TVBatchNorm(4 * mid)
+        if has_ds:
+            self.downsample = nn.Sequential(TVConv(cin, 4 * mid, 1, stride), TVBatchNorm(4 * mid))
+
+
+class CNNEncoder(_Holder):
+    """`torchvision.models.resnet50()` with `fc = nn.Identity()` (reference lib/models/maed.py:35-37): same module tree, so
+    the state_dict keys are torchvision's (conv1, bn1, layer1..4.{i}.{conv,bn}{1,2,3}, downsample.{0,1}); 2048 features."""
+
+    def __init__(self):
+        super().__init__()
+        self.num_features = 2048
+        self.conv1, self.bn1 = TVConv(3, 64, 7, 2), TVBatchNorm(64)
+        cin = 64
+        for li, (mid, depth) in enumerate(((64, 3), (128, 4), (256, 6), (512, 3))):
+            blocks = []
+            for b in range(depth):
+                blocks.append(TVBottleneck(cin, mid, 2 if (li > 0 and b == 0) else 1, b == 0))
+                cin = 4 * mid
+            setattr(self, "layer%d" % (li + 1), nn.Sequential(*blocks))
+        self.fc = nn.Identity()
+
+
 # SMPL kinematic tree (parent of joint j = last entry of ANCESTOR_INDEX[j]); vertex ids of the 21 vertex-selected joints
 # (smplx VertexJointSelector: face, feet, finger tips); indices of the 49 output joints in the 54-joint list
 # [24 SMPL | 21 selected | 9 regressed] (= JOINT_MAP[name] for name in JOINT_NAMES, reference lib/models/smpl.py:15-55).

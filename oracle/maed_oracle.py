@@ -4,7 +4,8 @@ Nothing in the shipped product (`maed_b200/`) imports this file; only `tests/`,
 `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may.
 
 It restates, function by function, what the reference computes for
-``MAED(encoder='ste', ..., decoder in {'ktd','iterative'}).forward`` (reference `lib/models/maed.py:52-66`)
+``MAED(encoder in {'ste','cnn'}, ..., decoder in {'ktd','iterative'}).forward`` (reference `lib/models/maed.py:52-66`;
+the 'cnn' encoder is torchvision's ResNet-50, restated from torchvision 0.26's `models/resnet.py`)
 from a plain ``state_dict`` with the REFERENCE's key names, so it can run on the GPU box where
 `/root/reference` does not exist.  It is pinned against the reference's own modules executed on CPU:
 ``tests/golden/*.npz`` were produced by ``tests/golden/make_golden.py`` from the unmodified reference
@@ -210,6 +211,43 @@ def ste_encoder(x, sd, mode, T, num_blocks=6, H=12, gemm_in=_ident, taps=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# 'cnn' encoder: torchvision ResNet-50 with fc = Identity                 reference lib/models/maed.py:35-37
+# --------------------------------------------------------------------------------------------------
+def batch_norm_eval(x, sd, p):
+    """nn.BatchNorm2d in eval(): (x - running_mean) / sqrt(running_var + 1e-5) * weight + bias."""
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, 1e-5)
+
+
+def tv_bottleneck(x, sd, p, stride, has_ds, gemm_in=_ident):
+    """torchvision.models.resnet.Bottleneck (v1.5: the stride sits on the 3x3 conv2); expansion 4."""
+    idt = x
+    if has_ds:
+        idt = F.conv2d(gemm_in(x), gemm_in(sd[p + "downsample.0.weight"]), None, stride)
+        idt = batch_norm_eval(idt, sd, p + "downsample.1.")
+    y = F.relu(batch_norm_eval(F.conv2d(gemm_in(x), gemm_in(sd[p + "conv1.weight"])), sd, p + "bn1."))
+    y = F.relu(batch_norm_eval(F.conv2d(gemm_in(y), gemm_in(sd[p + "conv2.weight"]), None, stride, 1), sd, p + "bn2."))
+    y = batch_norm_eval(F.conv2d(gemm_in(y), gemm_in(sd[p + "conv3.weight"])), sd, p + "bn3.")
+    return F.relu(y + idt)
+
+
+def cnn_encoder(x, sd, gemm_in=_ident, taps=None):
+    """torchvision resnet50._forward_impl with fc = nn.Identity() (maed.py:36-37): (BT,3,224,224) -> (BT,2048)."""
+    pre = "encoder."
+    y = F.conv2d(gemm_in(x), gemm_in(sd[pre + "conv1.weight"]), None, 2, 3)
+    y = F.relu(batch_norm_eval(y, sd, pre + "bn1."))
+    y = F.max_pool2d(y, 3, 2, 1)
+    if taps is not None:
+        taps["stem"] = y
+    for li, depth in enumerate((3, 4, 6, 3)):
+        for bi in range(depth):
+            stride = 2 if (li > 0 and bi == 0) else 1
+            y = tv_bottleneck(y, sd, "%slayer%d.%d." % (pre, li + 1, bi), stride, bi == 0, gemm_in)
+        if taps is not None:
+            taps["stage%d" % li] = y
+    return y.mean(dim=(2, 3))                                                  # AdaptiveAvgPool2d(1) + flatten
+
+
+# --------------------------------------------------------------------------------------------------
 # decoders                                       reference lib/models/ktd.py, lib/models/spin.py
 # --------------------------------------------------------------------------------------------------
 def ktd_regress(xf, sd, gemm_in=_ident):
@@ -309,10 +347,13 @@ def decode_outputs(pose6d, shape, cam, n_joints=49):
 
 # --------------------------------------------------------------------------------------------------
 def maed_forward(x, sd, st_mode="parallel", decoder="ktd", num_blocks=6, num_heads=12,
-                 gemm_in=_ident, taps=None):
+                 gemm_in=_ident, taps=None, encoder="ste"):
     """lib/models/maed.py:52-66.  x: (N,T,3,224,224) fp32 -> dict like the reference's."""
     N, T = x.shape[:2]
-    xf = ste_encoder(x.reshape(N * T, *x.shape[2:]), sd, st_mode, T, num_blocks, num_heads, gemm_in, taps)
+    if encoder == "cnn":
+        xf = cnn_encoder(x.reshape(N * T, *x.shape[2:]), sd, gemm_in, taps)
+    else:
+        xf = ste_encoder(x.reshape(N * T, *x.shape[2:]), sd, st_mode, T, num_blocks, num_heads, gemm_in, taps)
     if decoder == "ktd":
         pose6d, shape, cam = ktd_regress(xf, sd, gemm_in)
     elif decoder == "iterative":

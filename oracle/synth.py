@@ -39,6 +39,14 @@ def synth_tensor(key: str, shape, seed: int = 0) -> torch.Tensor:
     if leaf == "init_cam":
         return torch.tensor([0.9, 0.0, 0.0]).reshape(shape) + 0.05 * r
     is_norm = parent.startswith("norm") or parent == "norm"
+    # torchvision ResNet-50 ('cnn' encoder): bn1/bn2/bn3 and downsample.1 are BatchNorm2d with running statistics
+    is_bn = parent.startswith("bn") or (parent == "1" and ".downsample." in key)
+    if is_bn and len(shape) == 1:
+        if leaf == "weight":                              # 0.6 inside the residual stages keeps the activations O(1)
+            return (1.0 if key.startswith("encoder.bn1.") else 0.6) * (1.0 + 0.1 * r)
+        if leaf == "running_var":
+            return 0.6 + 0.4 * r.abs()
+        return 0.1 * r                                    # bias, running_mean
     if len(shape) == 1:
         if is_norm and leaf == "weight":
             return 1.0 + 0.1 * r

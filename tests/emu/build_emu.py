@@ -22,7 +22,7 @@ CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
 # compiled from the real sources through the shim
 CU_SOURCES = ["kernels.cu", "decoder.cu", "bwd_kernels.cu", "bwd_kernels2.cu", "attention_bwd.cu", "smpl.cu",
-              "engine.cu", "train.cu", "capi.cu"]
+              "cnn_kernels.cu", "cnn_engine.cu", "engine.cu", "train.cu", "capi.cu"]
 # tensor-core / TMA translation units replaced by tc_stubs.cpp
 REPLACED = ["gemm_host.cu", "gemm_gn_sm100.cu", "stem_sm100.cu", "attention.cu", "gemm_splitk_sm100.cu"]
 EMU_SOURCES = ["cuda_emu.cpp", "tc_stubs.cpp"]

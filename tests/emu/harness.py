@@ -116,14 +116,17 @@ class EmuModel:
         x = x.float().contiguous()
         ws = torch.zeros(self.lib.maed_engine_workspace_bytes(self.eng, BT), dtype=torch.uint8)
         nj = 49
-        o = {"feat": torch.zeros(BT, 768), "pose6d": torch.zeros(BT, 144), "shape": torch.zeros(BT, 10), "cam": torch.zeros(BT, 3),
-             "rotmat": torch.zeros(BT, 24, 3, 3), "theta": torch.zeros(BT, 85), "kp_2d": torch.zeros(BT, nj, 2)}
+        o = {"feat": torch.zeros(BT, getattr(self.m, "feat_dim", 768)), "pose6d": torch.zeros(BT, 144), "shape": torch.zeros(BT, 10),
+             "cam": torch.zeros(BT, 3), "rotmat": torch.zeros(BT, 24, 3, 3), "theta": torch.zeros(BT, 85),
+             "kp_2d": torch.zeros(BT, nj, 2)}
         outs = _lib.MaedOutputs(_lib.ptr(o["feat"]), _lib.ptr(o["pose6d"]), _lib.ptr(o["shape"]), _lib.ptr(o["cam"]),
                                 _lib.ptr(o["rotmat"]), _lib.ptr(o["theta"]), _lib.ptr(o["kp_2d"]), None, nj)
         shapes = {"stem": (BT, 56, 56, 64), "stage0": (BT, 56, 56, 256), "stage1": (BT, 28, 28, 512),
                   "stage2": (BT, 14, 14, 1024), "embed": (BT, 197, 768)}
         for i in range(8):
             shapes["block%d" % i] = (BT, 197, 768)
+        if getattr(self.m, "encoder_type", "ste").lower() == "cnn":
+            shapes["embed"] = (BT, 7, 7, 2048)                     # layer4's output arrives in the 'embed' slot
         tap_t, ptrs = {}, []
         for name in _lib.TAP_NAMES:
             if name in taps:

@@ -31,13 +31,17 @@ CASES = {
     "parallel_ktd_T1":     ("parallel", "ktd", 3, 1, 7, 16),      # image batches: seqlen 1 (trainer.py:177-179)
     "parallel_ktd_T32":    ("parallel", "ktd", 1, 32, 8, 32),     # BASELINE configs[4]: temp_embed data -> 32 rows
     "parallel_ktd_T16":    ("parallel", "ktd", 1, 16, 9, 16),
+    # encoder='cnn' (torchvision ResNet-50, config_stage1.yaml:68): 7-tuples, st_mode is ignored by the reference
+    "cnn_ktd":             ("vanilla", "ktd", 1, 2, 10, 16, "cnn"),
+    "cnn_iterative":       ("vanilla", "iterative", 3, 1, 11, 16, "cnn"),   # stage 1 trains on image batches (T = 1)
 }
 
 
 def run_case(name):
-    mode, dec, N, T, seed, tf = CASES[name]
+    mode, dec, N, T, seed, tf = CASES[name][:6]
+    encoder = CASES[name][6] if len(CASES[name]) > 6 else "ste"
     out_dir = os.path.dirname(os.path.abspath(__file__))   # before load_reference() chdirs away
-    model = ref_shim.build_reference_model(mode, dec, temp_frames=tf)
+    model = ref_shim.build_reference_model(mode, dec, temp_frames=tf, encoder=encoder)
     synth.fill_module_(model, seed)
     x = synth.synth_frames(N, T, seed)
     taps = {}
@@ -48,11 +52,16 @@ def run_case(name):
         return f
 
     enc = model.encoder
-    hs = [enc.patch_embed.backbone.stem.register_forward_hook(hook("stem"))]
-    for i, st in enumerate(enc.patch_embed.backbone.stages):
-        hs.append(st.register_forward_hook(hook("stage%d" % i)))
-    for i, blk in enumerate(enc.blocks):
-        hs.append(blk.register_forward_hook(hook("block%d" % i)))
+    if encoder == "cnn":
+        hs = [enc.maxpool.register_forward_hook(hook("stem"))]
+        for i, st in enumerate((enc.layer1, enc.layer2, enc.layer3, enc.layer4)):
+            hs.append(st.register_forward_hook(hook("stage%d" % i)))
+    else:
+        hs = [enc.patch_embed.backbone.stem.register_forward_hook(hook("stem"))]
+        for i, st in enumerate(enc.patch_embed.backbone.stages):
+            hs.append(st.register_forward_hook(hook("stage%d" % i)))
+        for i, blk in enumerate(enc.blocks):
+            hs.append(blk.register_forward_hook(hook("block%d" % i)))
     hs.append(enc.register_forward_hook(hook("feat")))
     orig_get_output = model.decoder.get_output
 
@@ -68,6 +77,11 @@ def run_case(name):
     for h in hs:
         h.remove()
     rec = {"meta": np.array([N, T, seed, tf], np.int64), "mode": np.array(mode), "decoder": np.array(dec)}
+    if encoder != "ste":
+        rec["encoder"] = np.array(encoder)
+        rec["state_dict_keys"] = np.array(sorted(k for k in model.state_dict() if "smpl" not in k))
+        rec["state_dict_shapes"] = np.array([",".join(str(d) for d in model.state_dict()[k].shape)
+                                             for k in sorted(k for k in model.state_dict() if "smpl" not in k)])
     for k in ("theta", "rotmat", "kp_2d"):
         rec["out_" + k] = out[k].numpy()
     rec["out_verts_absmax"] = np.array(out["verts"].abs().max().item(), np.float32)

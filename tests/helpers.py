@@ -12,7 +12,8 @@ GOLDEN_CASES = ["c1_parallel_ktd", "series_ktd", "vanilla_ktd", "coupling_ktd", 
 def load_golden(name):
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     N, T, seed, tf = [int(v) for v in g["meta"]]
-    return g, dict(N=N, T=T, seed=seed, temp_frames=tf, mode=str(g["mode"]), decoder=str(g["decoder"]))
+    return g, dict(N=N, T=T, seed=seed, temp_frames=tf, mode=str(g["mode"]), decoder=str(g["decoder"]),
+                   encoder=str(g["encoder"]) if "encoder" in g.files else "ste")
 
 
 def rel_err(a, b):
@@ -25,7 +26,8 @@ def build_model(meta, device="cpu", precision="split"):
     """B200 MAED module filled with the synthetic weights of the golden case."""
     from maed_b200.models import MAED
     from oracle import synth
-    m = MAED("ste", 6, 12, meta["mode"], meta["decoder"], 1024, precision=precision, temp_frames=meta["temp_frames"])
+    m = MAED(meta.get("encoder", "ste"), 6, 12, meta["mode"], meta["decoder"], 1024, precision=precision,
+             temp_frames=meta["temp_frames"])
     synth.fill_module_(m, meta["seed"])
     return m.to(device)
 

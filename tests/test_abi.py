@@ -41,3 +41,23 @@ def test_engine_tables_without_gpu(lib):
     bad = _lib.MaedConfig(6, 8, 1, 0, 1024, 3, 16)     # head_dim 96 unsupported -> error, not a crash
     assert lib.maed_engine_create(ctypes.byref(bad), ctypes.byref(h)) != 0
     assert b"num_heads" in lib.maed_last_error()
+
+
+def test_cnn_engine_tables_without_gpu(lib):
+    """encoder='cnn': torchvision ResNet-50 parameter table (53 conv + BN pairs) + KTD decoder on 2048 features."""
+    from maed_b200 import _lib
+    cfg = _lib.MaedConfig(6, 12, _lib.MODES["vanilla"], _lib.DECODERS["ktd"], 1024, 3, 16, _lib.ENCODERS["cnn"])
+    h = ctypes.c_void_p()
+    assert lib.maed_engine_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+    n = lib.maed_engine_num_params(h)
+    names = [lib.maed_engine_param_name(h, i).decode() for i in range(n)]
+    assert len(set(names)) == n and n == 53 * 5 + 4 + 48 + 4
+    assert "encoder.layer4.2.bn3.running_var" in names and "encoder.layer2.0.downsample.0.weight" in names
+    numel = dict(zip(names, (lib.maed_engine_param_numel(h, i) for i in range(n))))
+    assert numel["decoder.fc1.weight"] == 1024 * 2048 and numel["encoder.conv1.weight"] == 64 * 3 * 49
+    assert lib.maed_engine_workspace_bytes(h, 16) > lib.maed_engine_workspace_bytes(h, 2) > 0
+    assert lib.maed_train_workspace_bytes(h, 2) == 0          # inference only
+    lib.maed_engine_destroy(h)
+    bad = _lib.MaedConfig(6, 12, 0, 0, 1024, 3, 16, 7)
+    assert lib.maed_engine_create(ctypes.byref(bad), ctypes.byref(h)) != 0
+    assert b"encoder" in lib.maed_last_error()

@@ -1,0 +1,189 @@
+"""encoder='cnn' (torchvision ResNet-50 + decoder; reference lib/models/maed.py:35-37), inference.
+
+CPU (default suite):
+  * oracle/maed_oracle.py's ResNet-50 restatement against golden vectors of the UNMODIFIED reference (tests/golden/cnn_*.npz,
+    made by tests/golden/make_golden.py through torchvision's own resnet50) -> the oracle is pinned;
+  * the host module's state_dict keys / shapes against the reference's (stored in the same files);
+  * the real cnn_engine.cu / cnn_kernels.cu sources on the CUDA-on-CPU test build (tests/emu): whole forward against the
+    golden vectors, and the three new kernels against torch.
+GPU (`-m gpu`): the product library against the golden vectors and the oracle.  Written without GPU access, so these run
+behind MAED_B200_TRAIN_TESTS=1 / the subprocess canary (tests/test_zz_training_canary.py) like the training path.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import build_model, load_golden, rel_err, state_dict_of
+from oracle import maed_oracle as O
+from oracle import synth
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+CASES = ["cnn_ktd", "cnn_iterative"]
+GATED = pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
+                           reason="not yet validated on a GPU: runs in the canary / with MAED_B200_TRAIN_TESTS=1")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    import harness as h
+    h.load()
+    return h
+
+
+def _check_outputs(o, g, tol):
+    for k, gk in (("feat", "tap_feat"), ("pose6d", "tap_pose6d"), ("shape", "tap_shape"), ("cam", "tap_cam"),
+                  ("rotmat", "out_rotmat"), ("theta", "out_theta"), ("kp_2d", "out_kp_2d")):
+        assert rel_err(o[k].reshape(g[gk].shape), g[gk]) < tol, k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    g, meta = load_golden(name)
+    assert meta["encoder"] == "cnn"
+    sd = state_dict_of(build_model(meta))
+    taps = {}
+    with torch.no_grad():
+        out = O.maed_forward(synth.synth_frames(meta["N"], meta["T"], meta["seed"]), sd, meta["mode"], meta["decoder"], taps=taps,
+                             encoder="cnn")
+    for k in ("feat", "pose6d", "shape", "cam"):
+        assert rel_err(taps[k], g["tap_" + k]) < 1e-5, k
+    for k in ("theta", "rotmat", "kp_2d"):
+        assert rel_err(out[k], g["out_" + k]) < 1e-4, k
+    for k in ("stem", "stage0", "stage1", "stage2", "stage3"):
+        assert rel_err(synth.tap_digest(taps[k])[0], g["dig_%s_sub" % k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_state_dict_keys_match_reference(name):
+    g, meta = load_golden(name)
+    ref = {str(k): [int(d) for d in str(s).split(",") if d] for k, s in zip(g["state_dict_keys"], g["state_dict_shapes"])}
+    mine = {k: list(v.shape) for k, v in build_model(meta).state_dict().items()}
+    assert set(mine) == set(ref), sorted(set(mine) ^ set(ref))[:10]
+    for k in ref:
+        assert mine[k] == ref[k], k
+
+
+def test_cnn_module_surface():
+    from maed_b200.models import MAED
+    m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)
+    assert m.encoder_type == "cnn" and m.feat_dim == 2048 and m.decoder.fc1.weight.shape == (1024, 2048)
+    assert sum(p.numel() for p in m.encoder.parameters()) == 23508032        # torchvision resnet50 minus fc
+    with pytest.raises(NotImplementedError):
+        m.enable_training()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.eval()(torch.zeros(1, 1, 3, 224, 224))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_emulated_engine_matches_reference_golden(harness, name):
+    g, meta = load_golden(name)
+    em = harness.EmuModel(build_model(meta))
+    o = em.forward(synth.synth_frames(meta["N"], meta["T"], meta["seed"]), taps=("stem", "stage0", "stage1", "stage2", "embed"))
+    _check_outputs(o, g, 2e-4)
+    for mine, ref in (("stem", "stem"), ("stage0", "stage0"), ("stage1", "stage1"), ("stage2", "stage2"), ("embed", "stage3")):
+        nchw = o["taps"][mine].permute(0, 3, 1, 2).contiguous()              # engine taps are NHWC
+        assert rel_err(synth.tap_digest(nchw)[0], g["dig_%s_sub" % ref]) < 1e-4, mine
+
+
+def test_emulated_training_refuses_cnn(harness):
+    em = harness.EmuModel(build_model(load_golden("cnn_ktd")[1]))
+    with pytest.raises(RuntimeError, match="encoder='ste' only"):
+        em.train_forward(torch.zeros(1, 1, 3, 224, 224))
+
+
+# ------------------------------------------------------------------------------------------------ per-kernel checks
+def _planes(n, plane):
+    return torch.zeros(2 * plane if plane else n, dtype=torch.float16)
+
+
+def _run_ops(lib, stream, dev):
+    """fold_bn / maxpool3x3s2 / relu_split against torch, on `dev` through `lib`."""
+    from maed_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    # fold_bn
+    cout, cin, k = 24, 8, 3
+    w = torch.randn(cout, cin, k, k, generator=g)
+    gamma, beta, mean = [torch.randn(cout, generator=g) for _ in range(3)]
+    var = torch.rand(cout, generator=g) + 0.1
+    t = [v.to(dev) for v in (w, gamma, beta, mean, var)]
+    w_out, b_out = torch.empty_like(t[0]), torch.empty(cout, device=dev)
+    assert lib.maed_op_fold_bn(_lib.ptr(t[0]), cout, cin * k * k, _lib.ptr(t[1]), _lib.ptr(t[2]), _lib.ptr(t[3]), _lib.ptr(t[4]),
+                               1e-5, _lib.ptr(w_out), _lib.ptr(b_out), stream) == 0
+    x = torch.randn(2, cin, 9, 9, generator=g)
+    ref = F.batch_norm(F.conv2d(x, w, None, 1, 1), mean, var, gamma, beta, False, 0.0, 1e-5)
+    got = F.conv2d(x, w_out.cpu(), b_out.cpu(), 1, 1)
+    assert rel_err(got, ref) < 1e-5
+    # maxpool: odd and even sizes, negative values so that zero padding would be wrong
+    for (n, H, W, C) in ((2, 12, 10, 8), (1, 7, 9, 4)):
+        x = (torch.randn(n, H, W, C, generator=g) - 2.0).to(dev)
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        plane = n * OH * OW * C
+        o32, op = torch.empty(n, OH, OW, C, device=dev), torch.zeros(2 * plane, dtype=torch.float16, device=dev)
+        assert lib.maed_op_maxpool3x3s2(_lib.ptr(x), n, H, W, C, _lib.ptr(o32), _lib.ptr(op), plane, stream) == 0
+        ref = F.max_pool2d(x.cpu().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+        assert torch.equal(o32.cpu(), ref)
+        rec = op[:plane].float().cpu() + op[plane:].float().cpu()
+        assert rel_err(rec.reshape(ref.shape), ref) < 1e-6
+    # relu_split
+    n = 4 * 1031
+    x = torch.randn(n, generator=g).to(dev)
+    ref = x.cpu().clamp_min(0)
+    op = torch.zeros(2 * n, dtype=torch.float16, device=dev)
+    assert lib.maed_op_relu_split(_lib.ptr(x), n, _lib.ptr(op), n, stream) == 0
+    assert torch.equal(x.cpu(), ref)
+    assert rel_err(op[:n].float().cpu() + op[n:].float().cpu(), ref) < 1e-6
+    bad = torch.zeros(6, device=dev)
+    assert lib.maed_op_relu_split(_lib.ptr(bad), 6, _lib.ptr(op), n, stream) != 0           # n % 4 != 0 -> error, no launch
+
+
+def test_cnn_kernels_emulated(harness):
+    _run_ops(harness.load(), None, "cpu")
+
+
+# ---------------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@GATED
+def test_cnn_kernels_gpu(lib):
+    from maed_b200 import _lib
+    _run_ops(lib, _lib.stream_ptr(), "cuda")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
+@GATED
+@pytest.mark.parametrize("name", CASES)
+def test_cnn_forward_matches_reference_golden_gpu(name):
+    g, meta = load_golden(name)
+    m = build_model(meta, "cuda").eval()
+    x = synth.synth_frames(meta["N"], meta["T"], meta["seed"]).cuda()
+    o = m._run(x, want_taps=("stem", "stage0", "stage1", "stage2", "embed"))
+    torch.cuda.synchronize()
+    _check_outputs(o, g, 2e-4)                       # north_star gate: 1e-3 on pose / shape / cam; asserted tighter
+    for mine, ref in (("stem", "stem"), ("stage0", "stage0"), ("stage1", "stage1"), ("stage2", "stage2"), ("embed", "stage3")):
+        nchw = o["taps"][mine].permute(0, 3, 1, 2).contiguous()
+        assert rel_err(synth.tap_digest(nchw)[0], g["dig_%s_sub" % ref]) < 1e-4, mine
+    out = m(x)
+    assert out["theta"].shape == (meta["N"], meta["T"], 85) and out["kp_3d"].shape == (meta["N"], meta["T"], 49, 3)
+    assert rel_err(out["theta"].reshape(g["out_theta"].shape), g["out_theta"]) < 1e-3
+
+
+@pytest.mark.gpu
+@GATED
+def test_cnn_forward_matches_oracle_on_fresh_input_gpu():
+    """bs = 2 x T = 4 (a different batch than the golden files), KTD decoder, against the pinned oracle."""
+    from maed_b200.models import MAED
+    m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)
+    synth.fill_module_(m, 21)
+    sd = state_dict_of(m)
+    x = synth.synth_frames(2, 4, 21)
+    taps = {}
+    with torch.no_grad():
+        ref = O.maed_forward(x, sd, "vanilla", "ktd", taps=taps, encoder="cnn")
+    o = m.cuda().eval()(x.cuda())
+    for k in ("theta", "rotmat"):
+        assert rel_err(o[k], ref[k]) < 1e-3, k
+    assert rel_err(m.extract_feature(x.cuda()), taps["feat"].reshape(2, 4, -1)) < 2e-4
