@@ -266,3 +266,27 @@ class MAED(nn.Module):
             out["_debug"] = {k: o[k] for k in ("feat", "pose6d", "shape", "cam")}
             out["_debug"].update(o["taps"])
         return out
+
+    @torch.no_grad()
+    def forward_subclips(self, images, seqlen=16, interp=1, J_regressor=None):
+        """The evaluator's inner loop (reference lib/core/evaluate.py:71-100) as ONE forward.
+
+        The reference feeds a long window `images` (N, L0, 3, 224, 224) to the model as `sample_freq = L // seqlen`
+        interleaved sub-clips, `images[:, ::interp][:, i::sample_freq]` for i in range(sample_freq) (L = frames left after
+        the `interp` stride), copies five outputs to the host after each call and re-interleaves them with
+        `merge_sequence` (evaluate.py:127-133).  Here the sub-clips are gathered on the device into one batch of
+        N * sample_freq clips (the path shards by clip, so the results are the same), run through one engine call, and
+        returned already merged: every value has shape (N, L, ...) in the frame order of `images[:, ::interp]` — what
+        `merge_sequence` yields before `interpolate`.  Requires L to be a multiple of seqlen, as the reference's stacking
+        does."""
+        if images.dim() != 5:
+            raise ValueError("forward_subclips expects (N, L, 3, 224, 224) frames, got %s" % (tuple(images.shape),))
+        x = images[:, ::interp]
+        N, L = x.shape[:2]
+        if seqlen < 1 or L < seqlen or L % seqlen != 0:
+            raise ValueError("window of %d frames (after interp=%d) is not a multiple of seqlen=%d" % (L, interp, seqlen))
+        sf = L // seqlen
+        # frame t of sub-clip i is window frame t * sf + i
+        clips = x.reshape(N, seqlen, sf, *x.shape[2:]).transpose(1, 2).reshape(N * sf, seqlen, *x.shape[2:])
+        out = self._forward_inference(clips.contiguous(), J_regressor)
+        return {k: v.reshape(N, sf, seqlen, *v.shape[2:]).transpose(1, 2).reshape(N, L, *v.shape[2:]) for k, v in out.items()}

@@ -114,3 +114,19 @@ def test_fast_fp16_mode_runs_and_is_close():
     e = rel_err(out["_debug"]["feat"], g["tap_feat"])
     print("fp16 fast mode feat rel err %.2e" % e)
     assert e < 0.1
+
+
+def test_forward_subclips_equals_the_evaluator_loop():
+    """reference lib/core/evaluate.py:71-100: sample_freq interleaved sub-clips, one model call each, re-interleaved by
+    merge_sequence — against ONE batched forward over the gathered sub-clips (MAED.forward_subclips)."""
+    meta = dict(N=1, T=2, seed=11, temp_frames=16, mode="parallel", decoder="ktd")
+    model = build_model(meta, "cuda").eval()
+    images = synth.synth_frames(2, 6, 31).cuda()                 # window of 6 frames, seqlen 2 -> 3 sub-clips per window
+    got = model.forward_subclips(images, seqlen=2)
+    sf = 3
+    per = [model(images[:, i::sf]) for i in range(sf)]
+    for k in ("theta", "rotmat", "kp_2d"):
+        ref = torch.stack([p[k] for p in per], dim=2)            # (N, T, sf, ...) like np.stack(axis=2)
+        ref = ref.reshape(2, 6, *ref.shape[3:])
+        assert got[k].shape == ref.shape, k
+        assert rel_err(got[k], ref) < 1e-5, k
