@@ -233,6 +233,29 @@ size_t maed_smpl_scratch_bytes(int n_frames);
 int maed_smpl_forward(const maed_smpl_assets* assets, const float* betas, const float* rotmat, int R, const float* J_regressor,
                       int n_reg, float* verts, float* joints, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused training loss (maed_b200/csrc/loss.cu): replaces `self.criterion(preds, ...)` (reference lib/core/trainer.py:254 ->
+ * lib/core/loss.py:159-210 LossVideo / :214-283 LossImage) — every term of the reference and its gradient with respect to
+ * the predictions in three launches, no host synchronisation.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct maed_loss_weights {
+  float kp2d;   /* e_loss_weight         (LOSS.KP_2D_W) */
+  float kp3d;   /* e_3d_loss_weight      (LOSS.KP_3D_W) */
+  float pose;   /* e_pose_loss_weight    (LOSS.POSE_W);  pose and shape terms exist only when both weights are > 0 */
+  float shape;  /* e_shape_loss_weight   (LOSS.SHAPE_W) */
+  float norm;   /* e_smpl_norm_loss */
+  float accl;   /* e_smpl_accl_loss      (LOSS.ACCL_W; video only) */
+} maed_loss_weights;
+size_t maed_loss_scratch_bytes(int M2, int M3);
+/* pred_kp2d [M2,J2,2], gt_kp2d [M2,J2,3] = (x, y, conf) or NULL; pred_kp3d [M3,J3,3], gt_kp3d [M3,J3,4] = (x, y, z, conf) or
+ * NULL (49-joint layout: pelvis = mean of joints 27, 28); pred_theta / gt_theta [M3,85]; valid [M3] bytes (w_smpl) or NULL =
+ * all frames; T = frames per clip (M3 % T == 0).  losses[8] = kp2d, kp3d, shape, pose, norm, accl (weighted, the order of the
+ * reference's loss_dict), their total, n_valid.  d_kp2d / d_kp3d / d_theta = d total / d prediction (fully written). */
+int maed_loss_forward_backward(const float* pred_kp2d, const float* gt_kp2d, int M2, int J2, const float* pred_kp3d,
+                               const float* gt_kp3d, int M3, int J3, const float* pred_theta, const float* gt_theta,
+                               const unsigned char* valid, int T, const maed_loss_weights* w, float* losses, float* d_kp2d,
+                               float* d_kp3d, float* d_theta, void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,11 @@ class MaedSmplAssets(C.Structure):
                 ("lbs_weights", _P), ("J_regressor_extra", _P), ("parents", _P), ("extra_vertex_ids", _P), ("joint_map", _P)]
 
 
+class MaedLossWeights(C.Structure):
+    _fields_ = [("kp2d", C.c_float), ("kp3d", C.c_float), ("pose", C.c_float), ("shape", C.c_float), ("norm", C.c_float),
+                ("accl", C.c_float)]
+
+
 _U = C.c_ulonglong
 MODES = {"vanilla": 0, "parallel": 1, "series": 2, "coupling": 3, "temporal": 4}
 DECODERS = {"ktd": 0, "iterative": 1}
@@ -101,6 +106,10 @@ SIGNATURES = {
     "maed_bwd_split_transposed": (_I, [_P, _I, _I, _P, _L, _P]),
     "maed_bwd_prep_conv_weight_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "maed_bwd_dropout": (_I, [_P, _L, _F, _U, _P, _P, _P]),
+    # ---- fused loss
+    "maed_loss_scratch_bytes": (_Z, [_I, _I]),
+    "maed_loss_forward_backward": (_I, [_P, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _I, C.POINTER(MaedLossWeights), _P, _P, _P, _P,
+                                        _P, _Z, _P]),
     # ---- SMPL
     "maed_smpl_scratch_bytes": (_Z, [_I]),
     "maed_smpl_forward": (_I, [C.POINTER(MaedSmplAssets), _P, _P, _I, _P, _I, _P, _P, _P, _Z, _P]),

@@ -8,6 +8,7 @@
 #include "engine.h"
 #include "bwd_kernels.h"
 #include "kernels.h"
+#include "loss.h"
 #include "smpl.h"
 #include "train.h"
 
@@ -286,6 +287,19 @@ int maed_smpl_forward(const maed_smpl_assets* assets, const float* betas, const 
                       int n_reg, float* verts, float* joints, void* scratch, size_t scratch_bytes, void* stream) {
   return smpl_forward(reinterpret_cast<const SmplAssets*>(assets), betas, rotmat, R, J_regressor, n_reg, verts, joints, scratch,
                       scratch_bytes, (cudaStream_t)stream);
+}
+
+
+// ---- fused loss
+static_assert(sizeof(maed_loss_weights) == sizeof(LossWeights), "maed_loss_weights must mirror LossWeights");
+size_t maed_loss_scratch_bytes(int M2, int M3) { return loss_scratch_bytes(M2, M3); }
+int maed_loss_forward_backward(const float* pred_kp2d, const float* gt_kp2d, int M2, int J2, const float* pred_kp3d,
+                               const float* gt_kp3d, int M3, int J3, const float* pred_theta, const float* gt_theta,
+                               const unsigned char* valid, int T, const maed_loss_weights* w, float* losses, float* d_kp2d,
+                               float* d_kp3d, float* d_theta, void* scratch, size_t scratch_bytes, void* stream) {
+  return loss_forward_backward(pred_kp2d, gt_kp2d, M2, J2, pred_kp3d, gt_kp3d, M3, J3, pred_theta, gt_theta, valid, T,
+                               reinterpret_cast<const LossWeights*>(w), losses, d_kp2d, d_kp3d, d_theta, scratch, scratch_bytes,
+                               (cudaStream_t)stream);
 }
 
 }  // extern "C"

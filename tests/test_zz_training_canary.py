@@ -1,7 +1,7 @@
-"""Non-gating GPU canary for the parts that have not yet run on hardware (training path, SMPL tier, 'cnn' encoder).
+"""Non-gating GPU canary for the parts that have not yet run on hardware (training path, SMPL tier, 'cnn' encoder, fused loss).
 
 Their GPU tests (the ``cuda`` parametrisations of tests/test_bwd_ops.py, tests/test_smpl.py, tests/test_cnn.py,
-tests/test_train.py) stay
+tests/test_loss.py, tests/test_train.py) stay
 behind MAED_B200_TRAIN_TESTS=1 so that a first-contact failure cannot turn the validated suite red or poison its CUDA
 context.  This file runs them ONCE, last (file name), in a SUBPROCESS with a hard timeout:
 
@@ -28,7 +28,7 @@ def test_unvalidated_gpu_paths_in_a_subprocess():
     # per-test limit (pytest-timeout, thread method: dumps the stacks and ends the subprocess, which is what a hung kernel
     # needs) + an overall limit well inside any sensible budget for the whole GPU suite
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "--timeout", "90",
-           "--timeout-method", "thread", "tests/test_bwd_ops.py", "tests/test_smpl.py", "tests/test_cnn.py",
+           "--timeout-method", "thread", "tests/test_bwd_ops.py", "tests/test_smpl.py", "tests/test_cnn.py", "tests/test_loss.py",
            "tests/test_train.py"]
     try:
         r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=420)
