@@ -3,11 +3,13 @@
 
 #include "gemm_host.h"
 
+#include <algorithm>
 #include <mutex>
 #include <stdarg.h>
 #include <string.h>
 
 #include "gemm_sm100.cuh"
+#include "gemm2_sm100.cuh"
 
 namespace maed {
 
@@ -129,6 +131,37 @@ static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   return MAED_OK;
 }
 
+// CTA-pair kernel (gemm2_sm100.cuh): 256-row tiles, each CTA loads its 128 rows of A and half of the B tile
+template <int BN>
+static int launch_pair(const CUtensorMap& tmA, const GemmArgs& g, GemmParams p, cudaStream_t st) {
+  const int nplanes = p.nsplit == 3 ? 2 : 1;
+  CUtensorMap tmB;
+  {
+    const int ldb = g.ldb ? g.ldb : g.K;
+    const uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)g.N, (uint64_t)nplanes};
+    const uint64_t str[2] = {(uint64_t)ldb * 2, (uint64_t)(nplanes == 2 ? g.b_plane : (long long)g.N * ldb) * 2};
+    const uint32_t box[3] = {64, (uint32_t)(BN / 2), 1};
+    MAED_PROPAGATE(make_tmap_f16(&tmB, g.B, 3, dims, str, box));
+  }
+  p.m_tiles = cdiv(g.M, 2 * kBlockM);
+  p.n_tiles = g.N / BN;
+  const size_t stage_bytes = (size_t)nplanes * (kBlockM * kBlockK * 2 + (BN / 2) * kBlockK * 2);
+  int stages = (int)((232448 - 1024 - 512) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MAED_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  const long long tiles = (long long)p.m_tiles * p.n_tiles;
+  const long long pairs = std::min<long long>(tiles, sm_count() / 2);
+  gemm_tc2_kernel<BN><<<(int)(2 * pairs), kGemmThreads, smem, st>>>(tmA, tmB, p);
+  MAED_CUDA_CHECK(cudaGetLastError());
+  return MAED_OK;
+}
+
 int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   MAED_CHECK_ARG(g.nsplit == 1 || g.nsplit == 3, "gemm: nsplit must be 1 or 3");
   MAED_CHECK_ARG(g.N % 32 == 0, "gemm: N=%d must be a multiple of 32", g.N);
@@ -166,6 +199,12 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     const uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(nplanes == 2 ? g.a_plane : (long long)g.M * lda) * 2};
     const uint32_t box[3] = {64, 128, 1};
     MAED_PROPAGATE(make_tmap_f16(&tmA, g.A, 3, dims, str, box));
+  }
+  // opt-in CTA-pair path (MAED_B200_GEMM_2CTA=1): plain GEMMs with at least one full pair tile; not yet validated on a GPU
+  static const bool pair_on = getenv("MAED_B200_GEMM_2CTA") != nullptr;
+  if (pair_on && !g.conv && g.M >= 2 * kBlockM && (g.N % 128) == 0 && (g.force_block_n == 0 || g.force_block_n >= 128)) {
+    const int bn2 = g.force_block_n ? g.force_block_n : ((g.N % 256) == 0 ? 256 : 128);
+    return bn2 == 256 ? launch_pair<256>(tmA, g, p, st) : launch_pair<128>(tmA, g, p, st);
   }
   const int bn = choose_block_n(p.m_tiles, g.N, g.force_block_n);
   MAED_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "gemm: no tile width for N=%d", g.N);

@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(HERE, f) for f in sorted(os.listdir(HERE))
                                                                          if f.endswith((".h", ".cpp", ".py"))]
     deps.append(os.path.join(ROOT, "include", "maed_b200.h"))
-    h = hashlib.sha1(os.environ.get("MAED_EMU_ASAN", "").encode())
+    h = hashlib.sha1((os.environ.get("MAED_EMU_ASAN", "") + "|" + os.environ.get("MAED_EMU_UBSAN", "")).encode())
     try:                                    # -march=native: never reuse a library built on another CPU model
         with open("/proc/cpuinfo") as f:
             h.update("".join(l for l in f if l.startswith(("model name", "flags"))).encode())
@@ -80,6 +80,8 @@ def build(force=False, verbose=False):
     flags += ["-I", OUT]
     if os.environ.get("MAED_EMU_ASAN"):      # one-off memory checking (tests/emu/README.md): heap redzones around every tensor
         flags += ["-fsanitize=address", "-fno-omit-frame-pointer", "--param", "asan-stack=0"]
+    if os.environ.get("MAED_EMU_UBSAN"):     # misaligned vector accesses (float4 / uint4 / uint2 ...) fault on the GPU but not on x86:
+        flags += ["-fsanitize=alignment", "-fno-sanitize-recover=alignment"]   # make them abort here as well
     objs, jobs = [], []
     for name in CU_SOURCES:
         with open(os.path.join(CSRC, name)) as f:
@@ -108,7 +110,8 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("emulator build failed")
     _run(["g++", "-shared", "-o", LIB] + objs + ["-lpthread", "-Wl,-Bsymbolic"] +
-         (["-fsanitize=address"] if os.environ.get("MAED_EMU_ASAN") else []))
+         (["-fsanitize=address"] if os.environ.get("MAED_EMU_ASAN") else []) +
+         (["-fsanitize=alignment"] if os.environ.get("MAED_EMU_UBSAN") else []))
     with open(stamp, "w") as f:
         f.write(h.hexdigest())
     return LIB

@@ -207,6 +207,26 @@ static int worker_count() {
   return n;
 }
 
+static std::mutex g_smem_mu;
+static std::map<const void*, int> g_smem_optin;
+void set_smem_optin(const void* kernel, int bytes) {
+  std::lock_guard<std::mutex> lk(g_smem_mu);
+  g_smem_optin[kernel] = bytes;
+}
+void check_smem_optin(const void* kernel, size_t bytes) {
+  size_t limit = 48 * 1024;
+  {
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    auto it = g_smem_optin.find(kernel);
+    if (it != g_smem_optin.end()) limit = (size_t)it->second;
+  }
+  if (bytes > limit) {
+    fprintf(stderr, "emu: launch with %zu bytes of dynamic shared memory, but the kernel's limit is %zu (48 KB unless "
+            "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) raised it)\n", bytes, limit);
+    abort();
+  }
+}
+
 double g_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // seconds: [0] fiber kernels, [1..] stubs (tc_stubs.cpp)
 static double now_s() {
   timespec ts;

@@ -54,6 +54,11 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& t
 void prof_kernel(const void* fn, double seconds);      // per-kernel wall time (MAED_EMU_PROFILE=1, dumped at exit)
 double prof_now();
 
+// dynamic shared memory above 48 KB needs cudaFuncSetAttribute(MaxDynamicSharedMemorySize) on the real runtime: recorded per
+// kernel by emu_cudaFuncSetAttribute and enforced at every launch
+void set_smem_optin(const void* kernel, int bytes);
+void check_smem_optin(const void* kernel, size_t bytes);
+
 struct Launch {
   dim3 g, b;
   size_t smem;
@@ -62,6 +67,7 @@ struct Launch {
   void call(void (*k)(P...), A&&... a) {
     std::tuple<std::decay_t<P>...> args(std::forward<A>(a)...);      // kernel parameters are passed by value
     const double t0 = prof_now();
+    check_smem_optin(reinterpret_cast<const void*>(k), smem);
     run_grid(g, b, smem, [&]() { std::apply(k, args); });
     prof_kernel(reinterpret_cast<const void*>(k), prof_now() - t0);
   }
@@ -160,7 +166,10 @@ inline cudaError_t emu_cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size
 }
 inline cudaError_t emu_cudaGetLastError() { return cudaSuccess; }
 inline const char* emu_cudaGetErrorString(cudaError_t) { return "emulated"; }
-template <class F> inline cudaError_t emu_cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> inline cudaError_t emu_cudaFuncSetAttribute(F f, cudaFuncAttribute a, int v) {
+  if (a == cudaFuncAttributeMaxDynamicSharedMemorySize) ::emu::set_smem_optin(reinterpret_cast<const void*>(f), v);
+  return cudaSuccess;
+}
 #define cudaMemsetAsync emu_cudaMemsetAsync
 #define cudaMemcpyAsync emu_cudaMemcpyAsync
 #define cudaMemcpy2DAsync emu_cudaMemcpy2DAsync

@@ -94,7 +94,7 @@ class EmuModel:
         for t, k, i in zip(self.tensors, self.names, range(n)):
             assert t.numel() == self.lib.maed_engine_param_numel(h, i), k
         self.params = (C.c_void_p * n)(*[t.data_ptr() for t in self.tensors])
-        self.packed = torch.zeros(self.lib.maed_engine_packed_bytes(h), dtype=torch.uint8)
+        self.packed = torch.full((self.lib.maed_engine_packed_bytes(h),), 0xFF, dtype=torch.uint8)            # poisoned
         self._check(self.lib.maed_engine_pack(h, self.params, _lib.ptr(self.packed), None), "engine_pack")
         self.tpack = None
         self.ws = None
@@ -114,7 +114,8 @@ class EmuModel:
         N, T = x.shape[:2]
         BT = N * T
         x = x.float().contiguous()
-        ws = torch.zeros(self.lib.maed_engine_workspace_bytes(self.eng, BT), dtype=torch.uint8)
+        # poisoned like uninitialised device memory (torch.empty on the GPU): 0xFF bytes are NaN in fp32 and in fp16
+        ws = torch.full((self.lib.maed_engine_workspace_bytes(self.eng, BT),), 0xFF, dtype=torch.uint8)
         nj = 49
         o = {"feat": torch.zeros(BT, getattr(self.m, "feat_dim", 768)), "pose6d": torch.zeros(BT, 144), "shape": torch.zeros(BT, 10),
              "cam": torch.zeros(BT, 3), "rotmat": torch.zeros(BT, 24, 3, 3), "theta": torch.zeros(BT, 85),
@@ -145,9 +146,9 @@ class EmuModel:
         BT = N * T
         self.x = x.float().contiguous()
         if self.tpack is None:
-            self.tpack = torch.zeros(self.lib.maed_train_pack_bytes(self.eng), dtype=torch.uint8)
+            self.tpack = torch.full((self.lib.maed_train_pack_bytes(self.eng),), 0xFF, dtype=torch.uint8)         # poisoned
             self._check(self.lib.maed_train_pack(self.eng, self.params, _lib.ptr(self.tpack), None), "train_pack")
-        self.ws = torch.zeros(self.lib.maed_train_workspace_bytes(self.eng, BT), dtype=torch.uint8)
+        self.ws = torch.full((self.lib.maed_train_workspace_bytes(self.eng, BT),), 0xFF, dtype=torch.uint8)   # poisoned, see forward
         o = {"feat": torch.zeros(BT, 768), "pose6d": torch.zeros(BT, 144), "shape": torch.zeros(BT, 10), "cam": torch.zeros(BT, 3)}
         outs = _lib.MaedTrainOutputs(_lib.ptr(o["feat"]), _lib.ptr(o["pose6d"]), _lib.ptr(o["shape"]), _lib.ptr(o["cam"]))
         self._check(self.lib.maed_train_forward(self.eng, self.params, _lib.ptr(self.packed), _lib.ptr(self.x), N, T,

@@ -29,7 +29,7 @@ def test_unvalidated_gpu_paths_in_a_subprocess():
     # needs) + an overall limit well inside any sensible budget for the whole GPU suite
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "--timeout", "90",
            "--timeout-method", "thread", "tests/test_bwd_ops.py", "tests/test_smpl.py", "tests/test_cnn.py", "tests/test_loss.py",
-           "tests/test_train.py"]
+           "tests/test_train.py", "tests/test_gemm_pair.py"]          # the least certain kernel last: a hang ends the subprocess
     try:
         r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=420)
         out, code = r.stdout + r.stderr, r.returncode
