@@ -219,10 +219,27 @@ def run_train(args):
     target = torch.zeros(CLIPS_PER_GPU, T, 85, device=dev)
     target[..., 0] = 1.0
     h_loss = torch.empty(1).pin_memory()
+    criterion, target_3d = None, None
+    if args.loss == "fused":
+        # the reference's LossVideo (lib/core/loss.py:159-210) with the stage-2 weights (configs/config_stage2.yaml:34-40) on
+        # synthetic targets of the trainer's shapes, through the fused CUDA loss (maed_b200/loss.py)
+        from maed_b200.loss import Loss
+        criterion = Loss(e_loss_weight=300., e_3d_loss_weight=600., e_pose_loss_weight=60., e_shape_loss_weight=0.06,
+                         e_smpl_norm_loss=1., e_smpl_accl_loss=0., device=dev)
+        g = torch.Generator().manual_seed(5)
+        ones = torch.ones(CLIPS_PER_GPU, T, 49, 1)
+        th = 0.2 * torch.randn(CLIPS_PER_GPU, T, 85, generator=g)
+        th[..., :3] = torch.tensor([1.0, 0.0, 0.0])
+        target_3d = {"kp_2d": torch.cat([2 * torch.rand(CLIPS_PER_GPU, T, 49, 2, generator=g) - 1, ones], -1).to(dev),
+                     "kp_3d": torch.cat([0.3 * torch.randn(CLIPS_PER_GPU, T, 49, 3, generator=g), ones], -1).to(dev),
+                     "theta": th.to(dev), "w_smpl": torch.ones(CLIPS_PER_GPU, T, device=dev)}
 
     def step(x):
         opt.zero_grad(set_to_none=True)
-        loss = ((model(x)["theta"] - target) ** 2).mean()
+        if criterion is not None:
+            loss, _ = criterion(model(x), target_3d=target_3d, target_2d=None)
+        else:
+            loss = ((model(x)["theta"] - target) ** 2).mean()
         loss.backward()
         if dist:
             train.allreduce_gradients(model, world)
@@ -280,7 +297,9 @@ def run_train(args):
             "data": "synthetic",
             "config": {"workload": "BASELINE configs[2]: 1xB200 bs=8 T=16 train step (fwd+bwd+Adam), random-init",
                        "clips_per_gpu": CLIPS_PER_GPU, "seq_len": T, "st_mode": st_mode, "decoder": DECODER,
-                       "loss": "MSE on theta (the reference's parameter-space terms; keypoint terms need the SMPL tier)",
+                       "loss": ("reference LossVideo, stage-2 weights, fused CUDA loss (keypoint terms act on the zero body model "
+                                "unless SMPL assets are loaded)") if args.loss == "fused" else
+                               "MSE on theta (the reference's parameter-space terms; keypoint terms need the SMPL tier)",
                        "parallelism": "data parallel x%d, one all-reduce of the flat gradient buffer per step" % world},
             "clocks": clocks, "gpu_launches": int(launches), "final_loss": float(loss.item()),
             "e2e": {"value": world * CLIPS_PER_GPU * args.steps / (float(e2e_ms.item()) / 1000.0), "unit": "clips/s",
@@ -302,6 +321,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="forward: BASELINE configs[1] (the driver's metric); train: configs[2] fwd+bwd+Adam (opt-in)")
+    ap.add_argument("--loss", default="mse", choices=["mse", "fused"],
+                    help="train mode only: 'fused' = the reference's LossVideo through maed_b200.loss (not yet GPU-validated)")
     ap.add_argument("--st-mode", default=None, help="train mode only: parallel (default) or series")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
