@@ -35,6 +35,13 @@ int maed_op_gemm(const void* A, long long a_plane, int lda, const void* B, long 
                  int M, int N, int K, int nsplit, const float* bias, const float* residual, int act,
                  int out_mode, void* out, long long out_plane, int ldc, int force_block_n, void* stream);
 
+/* out = act_post(A * B^T + bias + residual), the residual given as fp16 planes [M, ldc] (hi at res_hi, lo res_plane elements
+ * further; res_plane = 0: hi only); act_post: 0 none, 2 ReLU — the tail of a ResNet bottleneck, conv3 + folded BatchNorm +
+ * identity + ReLU in one launch (torchvision models/resnet.py Bottleneck.forward; reference lib/models/maed.py:36). */
+int maed_op_gemm_bottleneck(const void* A, long long a_plane, int lda, const void* B, long long b_plane, int ldb, int M, int N,
+                            int K, int nsplit, const float* bias, const void* res_hi, long long res_plane, int act_post,
+                            int out_mode, void* out, long long out_plane, int ldc, void* stream);
+
 /* Implicit-GEMM stride-1 KHxKW convolution over an NHWC activation [n_img,H,W,Cin] (x planes) with
  * weights [Cout, KH*KW*Cin] (x planes); zero padding (pad_h, pad_w) on the top/left, SAME-style on the
  * bottom/right (reference resnetv2.py:54-59,91-93).  Output [n_img*H*W, Cout]. */
@@ -83,8 +90,6 @@ int maed_op_fold_bn(const float* w, int Cout, long long E, const float* gamma, c
 /* nn.MaxPool2d(3, stride 2, padding 1) on an fp32 NHWC map [n,H,W,C] -> fp32 NHWC and / or planes (either may be NULL) */
 int maed_op_maxpool3x3s2(const float* x, int n_img, int H, int W, int C, float* out_f32, void* out_hi, long long plane,
                          void* stream);
-/* x = relu(x) in place (fp32, n elements) and as planes: closes a bottleneck after the GEMM epilogue added the identity */
-int maed_op_relu_split(float* x, long long n, void* out_hi, long long plane, void* stream);
 /* LayerNorm(eps) rows of fp32 -> planes (reference vision_transformer.py:258-261) */
 int maed_op_layernorm(const float* x, long long row_stride, const float* gamma, const float* beta, int rows, int C,
                       float eps, void* out_hi, long long out_plane, void* stream);

@@ -54,10 +54,10 @@ SIGNATURES = {
     "maed_version": (_I, []),
     "maed_launch_count": (_L, []),
     "maed_op_gemm": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _L, _I, _I, _P]),
+    "maed_op_gemm_bottleneck": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _P, _L, _I, _I, _P, _L, _I, _P]),
     "maed_op_conv_gemm": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _I, _P]),
     "maed_op_fold_bn": (_I, [_P, _I, _L, _P, _P, _P, _P, _F, _P, _P, _P]),
     "maed_op_maxpool3x3s2": (_I, [_P, _I, _I, _I, _I, _P, _P, _L, _P]),
-    "maed_op_relu_split": (_I, [_P, _L, _P, _L, _P]),
     "maed_op_split_f32": (_I, [_P, _P, _L, _L, _P]),
     "maed_op_prep_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     "maed_op_im2col_stem": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),

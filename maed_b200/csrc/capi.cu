@@ -32,6 +32,18 @@ int maed_op_gemm(const void* A, long long a_plane, int lda, const void* B, long 
   return launch_gemm(g, (cudaStream_t)stream);
 }
 
+int maed_op_gemm_bottleneck(const void* A, long long a_plane, int lda, const void* B, long long b_plane, int ldb, int M, int N,
+                            int K, int nsplit, const float* bias, const void* res_hi, long long res_plane, int act_post,
+                            int out_mode, void* out, long long out_plane, int ldc, void* stream) {
+  GemmArgs g;
+  g.A = (const __half*)A; g.a_plane = a_plane; g.lda = lda;
+  g.B = (const __half*)B; g.b_plane = b_plane; g.ldb = ldb;
+  g.M = M; g.N = N; g.K = K; g.nsplit = nsplit;
+  g.bias = bias; g.res_hi = (const __half*)res_hi; g.res_plane = res_plane; g.act_post = act_post;
+  g.out_mode = out_mode; g.out = out; g.out_plane = out_plane; g.ldc = ldc;
+  return launch_gemm(g, (cudaStream_t)stream);
+}
+
 int maed_op_conv_gemm(const void* A, long long a_plane, const void* B, long long b_plane, int n_img, int H, int W,
                       int Cin, int Cout, int KH, int KW, int pad_h, int pad_w, int nsplit, int out_mode, void* out,
                       long long out_plane, int force_block_n, void* stream) {
@@ -52,9 +64,6 @@ int maed_op_fold_bn(const float* w, int Cout, long long E, const float* gamma, c
 int maed_op_maxpool3x3s2(const float* x, int n_img, int H, int W, int C, float* out_f32, void* out_hi, long long plane,
                          void* stream) {
   return maxpool3x3s2(x, n_img, H, W, C, out_f32, (__half*)out_hi, plane, (cudaStream_t)stream);
-}
-int maed_op_relu_split(float* x, long long n, void* out_hi, long long plane, void* stream) {
-  return relu_split(x, n, (__half*)out_hi, plane, (cudaStream_t)stream);
 }
 
 int maed_op_split_f32(const float* in, void* out_hi, long long plane, long long n, void* stream) {

@@ -4,18 +4,16 @@
 // (conv + BN + ReLU = one tcgen05 GEMM with a bias / ReLU epilogue).
 //
 //   stem     conv1 7x7/2 pad 3 (explicit im2col from the fp32 NCHW frame, K padded 147 -> 152) + BN + ReLU -> fp32
-//            MaxPool(3, 2, 1) -> fp32 + planes
+//            MaxPool(3, 2, 1) -> planes
 //   layer1-4 Bottleneck x (3, 4, 6, 3), stride on the 3x3 conv (v1.5):
-//              conv1 1x1 + BN + ReLU                  -> planes        (plain GEMM)
-//              conv2 3x3 (stride 1 or 2) + BN + ReLU  -> planes        (implicit GEMM by 5-D TMA; stride 2 and the 7x7 maps
+//              conv1 1x1 + BN + ReLU                      -> planes    (plain GEMM)
+//              conv2 3x3 (stride 1 or 2) + BN + ReLU      -> planes    (implicit GEMM by 5-D TMA; stride 2 and the 7x7 maps
 //                                                                       of layer4 through an explicit im2col)
-//              conv3 1x1 + BN + identity              -> fp32          (GEMM epilogue: bias + fp32 residual)
-//              ReLU                                   -> fp32 in place + planes
-//            identity = block input (fp32), or downsample conv 1x1 (stride s) + BN -> fp32 in the first block of a layer
-//   avgpool  mean over the 7x7 positions -> feature [BT, 2048]
+//              conv3 1x1 + BN + identity, then ReLU       -> planes    (GEMM epilogue: bias + plane residual + post-ReLU)
+//            identity = block input, or downsample conv 1x1 (stride s) + BN -> planes in the first block of a layer
+//   avgpool  the last conv3 writes fp32; mean over the 7x7 positions -> feature [BT, 2048]
 //
-// First version: the post-residual ReLU is a separate elementwise pass because the GEMM epilogue applies its activation
-// before the residual; fusing it (and an fp16-plane residual) into gemm_tc_kernel is the obvious next step.
+// Every conv + BN (+ identity) + ReLU is ONE gemm_tc_kernel launch; activations exist only as fp16 hi/lo planes.
 #include <algorithm>
 #include <string>
 
@@ -94,7 +92,8 @@ namespace {
 struct CnnWs {
   __half* col; long long col_plane;          // explicit im2col matrix (stem; stride-2 convs; 3x3 convs on 7x7 maps)
   __half* p[2]; __half* t1; __half* t2;      // block input / output planes (ping-pong), conv1 and conv2 outputs
-  float* f[2]; float* fds;                   // block input / output in fp32 (the identity path), downsample output
+  __half* pds;                               // downsample output (the identity of a layer's first block)
+  float* f32;                                // stem conv output (before the max-pool); the last block's output
   long long plane;
   TailWs tail;
   size_t total;
@@ -107,8 +106,8 @@ void cnn_carve(const Engine& e, int BT, uint8_t* base, CnnWs& w) {
   for (int i = 0; i < 2; ++i) w.p[i] = (__half*)cv.take((size_t)w.plane * 2 * 2);
   w.t1 = (__half*)cv.take((size_t)w.plane * 2 * 2);
   w.t2 = (__half*)cv.take((size_t)w.plane * 2 * 2);
-  for (int i = 0; i < 2; ++i) w.f[i] = (float*)cv.take((size_t)w.plane * 4);
-  w.fds = (float*)cv.take((size_t)w.plane * 4);
+  w.pds = (__half*)cv.take((size_t)w.plane * 2 * 2);
+  w.f32 = (float*)cv.take((size_t)w.plane * 4);
   carve_tail(e, BT, cv, w.tail);
   w.total = cv.off;
 }
@@ -120,9 +119,9 @@ size_t cnn_workspace_bytes(const Engine& e, int BT) {
   return w.total + 1024;
 }
 
-// conv + folded BN (+ ReLU | + fp32 residual) of an NHWC map [BT, Hin, Hin, cin] held as planes
+// conv + folded BN (+ ReLU | + identity planes, then ReLU) of an NHWC map [BT, Hin, Hin, cin] held as planes
 static int conv_bn(const Engine& e, const uint8_t* pk, CnnWs& w, const Engine::CnnConv& c, int BT, const __half* in, int Hin,
-                   int relu, const float* residual, int out_mode, void* out, cudaStream_t st) {
+                   int relu, const __half* identity, int out_mode, void* out, cudaStream_t st) {
   const int pad = c.k / 2;
   const int Hout = (Hin + 2 * pad - c.k) / c.stride + 1;
   GemmArgs g;
@@ -130,8 +129,10 @@ static int conv_bn(const Engine& e, const uint8_t* pk, CnnWs& w, const Engine::C
   g.B = (const __half*)(pk + c.off_w); g.b_plane = (long long)c.cout * c.k_pad; g.ldb = c.k_pad;
   g.M = BT * Hout * Hout; g.N = c.cout; g.K = c.k * c.k * c.cin;
   g.bias = (const float*)(pk + c.off_b);
-  g.act = relu ? ACT_RELU : ACT_NONE;
-  g.residual = residual;
+  g.act = (relu && !identity) ? ACT_RELU : ACT_NONE;
+  if (identity) {                                            // relu(conv3 + bn3 + identity)
+    g.res_hi = identity; g.res_plane = e.cfg.nsplit == 3 ? w.plane : 0; g.act_post = relu ? ACT_RELU : ACT_NONE;
+  }
   g.out_mode = out_mode; g.out = out; g.out_plane = w.plane; g.ldc = c.cout;
   if (c.k == 1 && c.stride == 1) {
     g.A = in; g.a_plane = w.plane;
@@ -155,12 +156,13 @@ int cnn_forward(const Engine& e, const void* const* params, const void* packed, 
                  w.total + 1024);
   const uint8_t* pk = (const uint8_t*)packed;
   const int om = e.cfg.nsplit == 3 ? OUT_F16_SPLIT : OUT_F16;
-  auto tap = [&](int which, const float* src, long long n) -> int {
-    if (taps && taps[which]) MAED_CUDA_CHECK(cudaMemcpyAsync(taps[which], src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  const long long tap_plane = e.cfg.nsplit == 3 ? w.plane : 0;
+  auto tap = [&](int which, const __half* src, long long n) -> int {
+    if (taps && taps[which]) MAED_PROPAGATE(planes_to_f32(src, tap_plane, n, taps[which], st));
     return MAED_OK;
   };
 
-  // ---- stem: conv1 7x7/2 pad 3 + BN + ReLU (112x112x64, fp32) -> MaxPool(3, 2, 1) (56x56x64)
+  // ---- stem: conv1 7x7/2 pad 3 + BN + ReLU (112x112x64, fp32) -> MaxPool(3, 2, 1) (56x56x64, planes)
   size_t ci = 0;
   {
     const Engine::CnnConv& c = e.cnn[ci++];
@@ -170,11 +172,11 @@ int cnn_forward(const Engine& e, const void* const* params, const void* packed, 
     g.A = w.col; g.a_plane = w.col_plane; g.lda = c.k_pad;
     g.B = (const __half*)(pk + c.off_w); g.b_plane = (long long)c.cout * c.k_pad; g.ldb = c.k_pad;
     g.M = BT * 12544; g.N = 64; g.K = c.k_pad;
-    g.bias = (const float*)(pk + c.off_b); g.act = ACT_RELU; g.out_mode = OUT_F32; g.out = w.f[1]; g.ldc = 64;
+    g.bias = (const float*)(pk + c.off_b); g.act = ACT_RELU; g.out_mode = OUT_F32; g.out = w.f32; g.ldc = 64;
     MAED_PROPAGATE(launch_gemm(g, st));
-    MAED_PROPAGATE(maxpool3x3s2(w.f[1], BT, 112, 112, 64, w.f[0], w.p[0], w.plane, st));
+    MAED_PROPAGATE(maxpool3x3s2(w.f32, BT, 112, 112, 64, nullptr, w.p[0], w.plane, st));
   }
-  MAED_PROPAGATE(tap(TAP_STEM, w.f[0], (long long)BT * 3136 * 64));
+  MAED_PROPAGATE(tap(TAP_STEM, w.p[0], (long long)BT * 3136 * 64));
 
   // ---- layer1..layer4
   int cur = 0, Hc = 56, prev = 64;
@@ -183,25 +185,32 @@ int cnn_forward(const Engine& e, const void* const* params, const void* packed, 
     for (int b = 0; b < kCnnDepth[l]; ++b) {
       const int stride = (l > 0 && b == 0) ? 2 : 1;
       const int Ho = Hc / stride;
-      const float* identity = w.f[cur];
+      const bool last = (l == 3 && b == kCnnDepth[l] - 1);
+      const __half* identity = w.p[cur];
       if (b == 0) {
-        MAED_PROPAGATE(conv_bn(e, pk, w, e.cnn[ci++], BT, w.p[cur], Hc, 0, nullptr, OUT_F32, w.fds, st));
-        identity = w.fds;
+        MAED_PROPAGATE(conv_bn(e, pk, w, e.cnn[ci++], BT, w.p[cur], Hc, 0, nullptr, om, w.pds, st));
+        identity = w.pds;
       }
       MAED_PROPAGATE(conv_bn(e, pk, w, e.cnn[ci++], BT, w.p[cur], Hc, 1, nullptr, om, w.t1, st));
       MAED_PROPAGATE(conv_bn(e, pk, w, e.cnn[ci++], BT, w.t1, Hc, 1, nullptr, om, w.t2, st));
-      MAED_PROPAGATE(conv_bn(e, pk, w, e.cnn[ci++], BT, w.t2, Ho, 0, identity, OUT_F32, w.f[cur ^ 1], st));
-      MAED_PROPAGATE(relu_split(w.f[cur ^ 1], (long long)BT * Ho * Ho * out, w.p[cur ^ 1], w.plane, st));
+      if (last)                                               // fp32 for the average pool
+        MAED_PROPAGATE(conv_bn(e, pk, w, e.cnn[ci++], BT, w.t2, Ho, 1, identity, OUT_F32, w.f32, st));
+      else
+        MAED_PROPAGATE(conv_bn(e, pk, w, e.cnn[ci++], BT, w.t2, Ho, 1, identity, om, w.p[cur ^ 1], st));
       cur ^= 1;
       Hc = Ho;
       prev = out;
     }
     // TAP_STAGE0..2 = layer1..3; layer4 lands in the TAP_EMBED slot (fp32 NHWC)
-    MAED_PROPAGATE(tap(l < 3 ? TAP_STAGE0 + l : TAP_EMBED, w.f[cur], (long long)BT * Hc * Hc * prev));
+    if (l < 3) {
+      MAED_PROPAGATE(tap(TAP_STAGE0 + l, w.p[cur], (long long)BT * Hc * Hc * prev));
+    } else if (taps && taps[TAP_EMBED]) {
+      MAED_CUDA_CHECK(cudaMemcpyAsync(taps[TAP_EMBED], w.f32, (size_t)BT * Hc * Hc * prev * 4, cudaMemcpyDeviceToDevice, st));
+    }
   }
 
   // ---- AdaptiveAvgPool2d(1) + flatten -> [BT, 2048]; fc = Identity
-  MAED_PROPAGATE(token_mean(w.f[cur], BT, Hc * Hc, prev, outs->feat, prev, 0, st));
+  MAED_PROPAGATE(token_mean(w.f32, BT, Hc * Hc, prev, outs->feat, prev, 0, st));
   return run_decoder(e, params, pk, BT, w.tail, outs, st);
 }
 

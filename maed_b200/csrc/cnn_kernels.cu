@@ -1,6 +1,6 @@
 // Memory-bound kernels of the 'cnn' encoder (torchvision ResNet-50, reference lib/models/maed.py:35-37): BatchNorm folding
-// at pack time, the 3x3/2 max-pool behind the stem and the ReLU that follows the residual add.  HBM-bound: 16-byte accesses
-// along the channel dimension, grids capped at a few waves of the SMs.
+// at pack time and the 3x3/2 max-pool behind the stem.  HBM-bound: 16-byte accesses along the channel dimension, grids capped
+// at a few waves of the SMs.
 #include "device_utils.cuh"
 
 namespace maed {
@@ -68,25 +68,6 @@ int maxpool3x3s2(const float* x, int n_img, int H, int W, int C, float* out_f32,
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long long total4 = (long long)n_img * OH * OW * (C / 4);
   maxpool3x3s2_kernel<<<grid_for(total4, 256), 256, 0, st>>>(x, H, W, C, OH, OW, total4, out_f32, out_hi, plane);
-  MAED_BW_LAUNCH_CHECK();
-  return MAED_OK;
-}
-
-// ------------------------------------------------------------------------------ out = relu(x): fp32 in place + planes
-// Closes a bottleneck: the GEMM epilogue wrote conv3 + folded BN + identity in fp32; the next block needs the ReLU'd map
-// both as its fp32 identity and as its tensor-core operand.
-__global__ void relu_split_kernel(float* __restrict__ x, long long n4, __half* __restrict__ out_hi, long long plane) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 v = reinterpret_cast<float4*>(x)[i];
-    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-    reinterpret_cast<float4*>(x)[i] = v;
-    store_split4(out_hi + 4 * i, plane, v);
-  }
-}
-int relu_split(float* x, long long n, __half* out_hi, long long plane, cudaStream_t st) {
-  MAED_CHECK_ARG(x && out_hi, "relu_split: null argument");
-  MAED_CHECK_ARG(n >= 4 && n % 4 == 0 && plane % 4 == 0, "relu_split: n=%lld and the plane stride must be multiples of 4", n);
-  relu_split_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(x, n / 4, out_hi, plane);
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
 }

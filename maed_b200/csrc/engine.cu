@@ -24,7 +24,7 @@ __global__ void planes_to_f32_kernel(const __half* __restrict__ hi, long long pl
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __half2float(hi[i]) + (plane ? __half2float(hi[i + plane]) : 0.f);
 }
-static int planes_to_f32(const __half* hi, long long plane, long long n, float* out, cudaStream_t st) {
+int planes_to_f32(const __half* hi, long long plane, long long n, float* out, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   planes_to_f32_kernel<<<blocks, 256, 0, st>>>(hi, plane, n, out);

@@ -72,6 +72,9 @@ void carve_tail(const Engine& e, int BT, Carver& c, TailWs& t);
 int run_decoder(const Engine& e, const void* const* params, const uint8_t* packed, int BT, const TailWs& t,
                 const EngineOutputs* outs, cudaStream_t st);
 
+// planes (hi + lo when plane != 0) -> fp32, n elements (debug taps)
+int planes_to_f32(const __half* hi, long long plane, long long n, float* out, cudaStream_t st);
+
 // ---- 'cnn' encoder (cnn_engine.cu)
 void cnn_add_params(Engine& e, int (*add_param)(Engine&, const std::string&, long long));
 void cnn_add_packed(Engine& e, size_t& off);

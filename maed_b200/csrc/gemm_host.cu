@@ -171,7 +171,10 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   p.M = g.M; p.N = g.N; p.K = g.K; p.nsplit = g.nsplit;
   p.bias = g.bias; p.residual = g.residual; p.act = g.act; p.out_mode = g.out_mode; p.out = g.out;
+  p.res_hi = g.res_hi; p.res_plane = g.res_plane; p.act_post = g.act_post;
   p.out_plane_stride = g.out_plane; p.ldc = g.ldc ? g.ldc : g.N;
+  MAED_CHECK_ARG(!g.res_hi || ((reinterpret_cast<uintptr_t>(g.res_hi) & 15) == 0 && g.res_plane % 8 == 0 && p.ldc % 8 == 0),
+                 "gemm: plane residual needs a 16-byte aligned base, plane stride and row stride");
 
   CUtensorMap tmA, tmB;
   if (g.conv) {

@@ -10,9 +10,12 @@ struct GemmArgs {
   const __half* B = nullptr; long long b_plane = 0; int ldb = 0;   // [N, ldb]
   int M = 0, N = 0, K = 0;
   int nsplit = 3;
-  // epilogue: out = act(acc + bias) + residual
+  // epilogue: out = act_post(act(acc + bias) + residual + residual planes)
   const float* bias = nullptr;
   const float* residual = nullptr;       // fp32 [M, ldc]
+  const __half* res_hi = nullptr;        // residual as planes [M, ldc]: hi, and lo at + res_plane when res_plane != 0
+  long long res_plane = 0;
+  int act_post = 0;                      // ACT_NONE / ACT_RELU after the residuals
   int act = 0;                           // ACT_*
   int out_mode = 0;                      // OUT_*
   void* out = nullptr;

@@ -31,7 +31,10 @@ struct GemmParams {
   // epilogue
   const float* bias;           // [N] or nullptr
   const float* residual;       // fp32 [M, ldc] or nullptr
+  const __half* res_hi;        // residual given as fp16 planes [M, ldc] (hi; lo at + res_plane when res_plane != 0) or nullptr
+  long long res_plane;
   int act;
+  int act_post;                // ACT_NONE or ACT_RELU, applied AFTER the residuals (ResNet bottleneck: relu(conv + identity))
   int out_mode;
   void* out;
   long long out_plane_stride;  // elements between the hi and lo output planes (OUT_F16_SPLIT)
@@ -47,7 +50,7 @@ static constexpr int kBlockK = 64;
 static constexpr int kGemmThreads = 256;
 static constexpr int kMaxStages = 8;
 
-// out = act(acc + bias) + residual for one row x 32 columns
+// out = act_post(act(acc + bias) + residual + residual_planes) for one row x 32 columns
 __device__ __forceinline__ void epilogue_math(float (&v)[32], const uint32_t (&r)[32], const GemmParams& p, int col0,
                                               long long out_row) {
 #pragma unroll
@@ -76,6 +79,33 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const uint32_t (&r
       const float4 b = rp[j >> 2];
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
+  }
+  if (p.res_hi) {
+    const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + out_row * p.ldc + col0);
+    const uint4* rl = reinterpret_cast<const uint4*>(p.res_hi + p.res_plane + out_row * p.ldc + col0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 h = rh[q];
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+        v[q * 8 + 2 * k] += f.x; v[q * 8 + 2 * k + 1] += f.y;
+      }
+      if (p.res_plane) {
+        const uint4 l = rl[q];
+        const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
+          v[q * 8 + 2 * k] += f.x; v[q * 8 + 2 * k + 1] += f.y;
+        }
+      }
+    }
+  }
+  if (p.act_post == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
 }
 

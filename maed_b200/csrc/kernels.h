@@ -53,8 +53,6 @@ int fold_bn(const float* w, int Cout, long long E, const float* gamma, const flo
 // nn.MaxPool2d(3, 2, 1) on an fp32 NHWC map -> fp32 NHWC and / or planes (either output may be nullptr)
 int maxpool3x3s2(const float* x, int n_img, int H, int W, int C, float* out_f32, __half* out_hi, long long plane,
                  cudaStream_t st);
-// x = relu(x) in place (fp32) and as planes
-int relu_split(float* x, long long n, __half* out_hi, long long plane, cudaStream_t st);
 
 // ---- STE elementwise
 // x[bt, 0] = cls + pos[0]; x[bt, 1+i] = tok[bt, i] + pos[1+i]; (+ temp[bt % T] when temp != nullptr)

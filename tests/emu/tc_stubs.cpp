@@ -213,6 +213,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t) {
                  "gemm: output base / row stride not 16-byte aligned");
   MAED_CHECK_ARG(!g.residual || (((uintptr_t)g.residual & 15) == 0), "gemm: residual not 16-byte aligned");
   MAED_CHECK_ARG(!g.bias || (((uintptr_t)g.bias & 15) == 0), "gemm: bias not 16-byte aligned");
+  MAED_CHECK_ARG(!g.res_hi || ((((uintptr_t)g.res_hi) & 15) == 0 && g.res_plane % 8 == 0 && ldc % 8 == 0),
+                 "gemm: plane residual needs a 16-byte aligned base, plane stride and row stride");
   MAED_CHECK_ARG(g.out_mode != OUT_F16_SPLIT || g.out_plane % 8 == 0, "gemm: out_plane not 16-byte aligned");
   sgemm_nt(g.M, g.N, g.K, A.data(), B.data(), C.data());
   parallel_for((g.M + 63) / 64, [&](long long rb) {
@@ -225,6 +227,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t) {
         else if (g.act == ACT_RELU) v = fmaxf(v, 0.f);
         else if (g.act == ACT_TANH) v = tanhf(v);
         if (g.residual) v += g.residual[r * ldc + n];
+        if (g.res_hi) v += ld(g.res_hi + r * ldc + n, g.res_plane);
+        if (g.act_post == ACT_RELU) v = fmaxf(v, 0.f);
         if (g.out_mode == OUT_F32) static_cast<float*>(g.out)[r * ldc + n] = v;
         else st_split(static_cast<__half*>(g.out) + r * ldc + n, g.out_plane, v, g.out_mode == OUT_F16_SPLIT);
       }

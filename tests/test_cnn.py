@@ -101,7 +101,7 @@ def _planes(n, plane):
 
 
 def _run_ops(lib, stream, dev):
-    """fold_bn / maxpool3x3s2 / relu_split against torch, on `dev` through `lib`."""
+    """fold_bn / maxpool3x3s2 / the bottleneck GEMM epilogue against torch, on `dev` through `lib`."""
     from maed_b200 import _lib
     g = torch.Generator().manual_seed(5)
     # fold_bn
@@ -128,16 +128,28 @@ def _run_ops(lib, stream, dev):
         assert torch.equal(o32.cpu(), ref)
         rec = op[:plane].float().cpu() + op[plane:].float().cpu()
         assert rel_err(rec.reshape(ref.shape), ref) < 1e-6
-    # relu_split
-    n = 4 * 1031
-    x = torch.randn(n, generator=g).to(dev)
-    ref = x.cpu().clamp_min(0)
-    op = torch.zeros(2 * n, dtype=torch.float16, device=dev)
-    assert lib.maed_op_relu_split(_lib.ptr(x), n, _lib.ptr(op), n, stream) == 0
-    assert torch.equal(x.cpu(), ref)
-    assert rel_err(op[:n].float().cpu() + op[n:].float().cpu(), ref) < 1e-6
-    bad = torch.zeros(6, device=dev)
-    assert lib.maed_op_relu_split(_lib.ptr(bad), 6, _lib.ptr(op), n, stream) != 0           # n % 4 != 0 -> error, no launch
+    # bottleneck tail: relu(A B^T + bias + identity planes) in one GEMM launch, plane and fp32 outputs, hi-only residual
+    M, N, K = 200, 128, 64
+    a, b = torch.randn(M, K, generator=g), 0.1 * torch.randn(N, K, generator=g)
+    bias, idt = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+
+    def planes(t):
+        hi = t.half()
+        return torch.stack([hi, (t - hi.float()).half()]).contiguous().to(dev)
+
+    pa, pb, pi = planes(a), planes(b), planes(idt)
+    join = lambda p: p[0].float().cpu() + p[1].float().cpu()  # noqa: E731
+    bias_d = bias.to(dev)
+    ref = torch.relu(join(pa).double() @ join(pb).double().t() + bias.double() + join(pi).double())
+    out = torch.zeros(2, M, N, dtype=torch.float16, device=dev)
+    assert lib.maed_op_gemm_bottleneck(_lib.ptr(pa), M * K, K, _lib.ptr(pb), N * K, K, M, N, K, 3, _lib.ptr(bias_d), _lib.ptr(pi),
+                                       M * N, 2, 2, _lib.ptr(out), M * N, N, stream) == 0
+    assert rel_err(join(out), ref) < 3e-6
+    out32 = torch.zeros(M, N, device=dev)
+    assert lib.maed_op_gemm_bottleneck(_lib.ptr(pa), M * K, K, _lib.ptr(pb), N * K, K, M, N, K, 3, _lib.ptr(bias_d), _lib.ptr(pi),
+                                       0, 0, 0, _lib.ptr(out32), 0, N, stream) == 0          # res_plane = 0: hi plane only, no ReLU
+    ref_hi = join(pa).double() @ join(pb).double().t() + bias.double() + pi[0].float().cpu().double()
+    assert rel_err(out32, ref_hi) < 3e-6
 
 
 def test_cnn_kernels_emulated(harness):
