@@ -61,67 +61,67 @@ static void build_tables(Engine& e) {
   if (cnn) {
     cnn_add_params(e, add_param);
   } else {
-  e.i_cls = add_param(e, enc + "cls_token", C);
-  e.i_pos = add_param(e, enc + "pos_embed", 197 * C);
-  const bool has_temp = (c.mode == MODE_PARALLEL || c.mode == MODE_SERIES || c.mode == MODE_COUPLING);
-  e.i_temp = has_temp ? add_param(e, enc + "temp_embed", (long long)c.temp_frames * C) : -1;
-  const std::string bbp = enc + "patch_embed.backbone.";
-  e.i_stem_w = add_param(e, bbp + "stem.conv.weight", 64 * 3 * 49);
-  e.i_stem_g = add_param(e, bbp + "stem.norm.weight", 64);
-  add_param(e, bbp + "stem.norm.bias", 64);
-  int prev = 64;
-  for (int s = 0; s < 3; ++s) {
-    const int out = kStageOut[s], mid = out / 4;
-    for (int b = 0; b < kStageDepth[s]; ++b) {
-      const std::string p = bbp + "stages." + std::to_string(s) + ".blocks." + std::to_string(b) + ".";
-      Engine::BlockIdx bi;
-      memset(&bi, 0xff, sizeof(bi));
-      if (b == 0) {
-        bi.ds_w = add_param(e, p + "downsample.conv.weight", (long long)out * prev);
-        bi.ds_g = add_param(e, p + "downsample.norm.weight", out);
-        add_param(e, p + "downsample.norm.bias", out);
+    e.i_cls = add_param(e, enc + "cls_token", C);
+    e.i_pos = add_param(e, enc + "pos_embed", 197 * C);
+    const bool has_temp = (c.mode == MODE_PARALLEL || c.mode == MODE_SERIES || c.mode == MODE_COUPLING);
+    e.i_temp = has_temp ? add_param(e, enc + "temp_embed", (long long)c.temp_frames * C) : -1;
+    const std::string bbp = enc + "patch_embed.backbone.";
+    e.i_stem_w = add_param(e, bbp + "stem.conv.weight", 64 * 3 * 49);
+    e.i_stem_g = add_param(e, bbp + "stem.norm.weight", 64);
+    add_param(e, bbp + "stem.norm.bias", 64);
+    int prev = 64;
+    for (int s = 0; s < 3; ++s) {
+      const int out = kStageOut[s], mid = out / 4;
+      for (int b = 0; b < kStageDepth[s]; ++b) {
+        const std::string p = bbp + "stages." + std::to_string(s) + ".blocks." + std::to_string(b) + ".";
+        Engine::BlockIdx bi;
+        memset(&bi, 0xff, sizeof(bi));
+        if (b == 0) {
+          bi.ds_w = add_param(e, p + "downsample.conv.weight", (long long)out * prev);
+          bi.ds_g = add_param(e, p + "downsample.norm.weight", out);
+          add_param(e, p + "downsample.norm.bias", out);
+        }
+        bi.c1_w = add_param(e, p + "conv1.weight", (long long)mid * prev);
+        bi.c1_g = add_param(e, p + "norm1.weight", mid);
+        add_param(e, p + "norm1.bias", mid);
+        bi.c2_w = add_param(e, p + "conv2.weight", (long long)mid * mid * 9);
+        bi.c2_g = add_param(e, p + "norm2.weight", mid);
+        add_param(e, p + "norm2.bias", mid);
+        bi.c3_w = add_param(e, p + "conv3.weight", (long long)out * mid);
+        bi.c3_g = add_param(e, p + "norm3.weight", out);
+        add_param(e, p + "norm3.bias", out);
+        e.bb.push_back(bi);
+        prev = out;
       }
-      bi.c1_w = add_param(e, p + "conv1.weight", (long long)mid * prev);
-      bi.c1_g = add_param(e, p + "norm1.weight", mid);
-      add_param(e, p + "norm1.bias", mid);
-      bi.c2_w = add_param(e, p + "conv2.weight", (long long)mid * mid * 9);
-      bi.c2_g = add_param(e, p + "norm2.weight", mid);
-      add_param(e, p + "norm2.bias", mid);
-      bi.c3_w = add_param(e, p + "conv3.weight", (long long)out * mid);
-      bi.c3_g = add_param(e, p + "norm3.weight", out);
-      add_param(e, p + "norm3.bias", out);
-      e.bb.push_back(bi);
-      prev = out;
     }
-  }
-  e.i_proj_w = add_param(e, enc + "patch_embed.proj.weight", 768LL * 1024);
-  e.i_proj_b = add_param(e, enc + "patch_embed.proj.bias", 768);
-  for (int i = 0; i < c.num_blocks; ++i) {
-    const std::string p = enc + "blocks." + std::to_string(i) + ".";
-    Engine::SteIdx si;
-    memset(&si, 0xff, sizeof(si));
-    si.n1 = add_param(e, p + "norm1.weight", C);
-    add_param(e, p + "norm1.bias", C);
-    si.qkv_w = add_param(e, p + "attn.qkv.weight", 3LL * C * C);
-    si.qkv_b = add_param(e, p + "attn.qkv.bias", 3 * C);
-    if (c.mode == MODE_PARALLEL) {
-      si.ts_w = add_param(e, p + "attn.ts_attn.weight", 4LL * C * C);
-      si.ts_b = add_param(e, p + "attn.ts_attn.bias", 2 * C);
+    e.i_proj_w = add_param(e, enc + "patch_embed.proj.weight", 768LL * 1024);
+    e.i_proj_b = add_param(e, enc + "patch_embed.proj.bias", 768);
+    for (int i = 0; i < c.num_blocks; ++i) {
+      const std::string p = enc + "blocks." + std::to_string(i) + ".";
+      Engine::SteIdx si;
+      memset(&si, 0xff, sizeof(si));
+      si.n1 = add_param(e, p + "norm1.weight", C);
+      add_param(e, p + "norm1.bias", C);
+      si.qkv_w = add_param(e, p + "attn.qkv.weight", 3LL * C * C);
+      si.qkv_b = add_param(e, p + "attn.qkv.bias", 3 * C);
+      if (c.mode == MODE_PARALLEL) {
+        si.ts_w = add_param(e, p + "attn.ts_attn.weight", 4LL * C * C);
+        si.ts_b = add_param(e, p + "attn.ts_attn.bias", 2 * C);
+      }
+      si.proj_w = add_param(e, p + "attn.proj.weight", (long long)C * C);
+      si.proj_b = add_param(e, p + "attn.proj.bias", C);
+      si.n2 = add_param(e, p + "norm2.weight", C);
+      add_param(e, p + "norm2.bias", C);
+      si.fc1_w = add_param(e, p + "mlp.fc1.weight", 4LL * C * C);
+      si.fc1_b = add_param(e, p + "mlp.fc1.bias", 4 * C);
+      si.fc2_w = add_param(e, p + "mlp.fc2.weight", 4LL * C * C);
+      si.fc2_b = add_param(e, p + "mlp.fc2.bias", C);
+      e.blk.push_back(si);
     }
-    si.proj_w = add_param(e, p + "attn.proj.weight", (long long)C * C);
-    si.proj_b = add_param(e, p + "attn.proj.bias", C);
-    si.n2 = add_param(e, p + "norm2.weight", C);
-    add_param(e, p + "norm2.bias", C);
-    si.fc1_w = add_param(e, p + "mlp.fc1.weight", 4LL * C * C);
-    si.fc1_b = add_param(e, p + "mlp.fc1.bias", 4 * C);
-    si.fc2_w = add_param(e, p + "mlp.fc2.weight", 4LL * C * C);
-    si.fc2_b = add_param(e, p + "mlp.fc2.bias", C);
-    e.blk.push_back(si);
-  }
-  e.i_norm = add_param(e, enc + "norm.weight", C);
-  add_param(e, enc + "norm.bias", C);
-  e.i_pl_w = add_param(e, enc + "pre_logits.fc.weight", (long long)C * C);
-  e.i_pl_b = add_param(e, enc + "pre_logits.fc.bias", C);
+    e.i_norm = add_param(e, enc + "norm.weight", C);
+    add_param(e, enc + "norm.bias", C);
+    e.i_pl_w = add_param(e, enc + "pre_logits.fc.weight", (long long)C * C);
+    e.i_pl_b = add_param(e, enc + "pre_logits.fc.bias", C);
   }  // !cnn
   const int HD = c.hidden_dim;
   const int F = e.feat_dim();
@@ -159,31 +159,31 @@ static void build_tables(Engine& e) {
   if (cnn) {
     cnn_add_packed(e, off);
   } else {
-  e.off_stem = planes(64LL * kStemKPad);
-  int prev = 64;
-  for (int s = 0; s < 3; ++s) {
-    const int out = kStageOut[s], mid = out / 4;
-    for (int b = 0; b < kStageDepth[s]; ++b) {
-      Engine::BlockOff bo;
-      bo.ds = (b == 0) ? planes((long long)out * prev) : 0;
-      bo.c1 = planes((long long)mid * prev);
-      bo.c2 = planes((long long)mid * mid * 9);
-      bo.c3 = planes((long long)out * mid);
-      e.bb_off.push_back(bo);
-      prev = out;
+    e.off_stem = planes(64LL * kStemKPad);
+    int prev = 64;
+    for (int s = 0; s < 3; ++s) {
+      const int out = kStageOut[s], mid = out / 4;
+      for (int b = 0; b < kStageDepth[s]; ++b) {
+        Engine::BlockOff bo;
+        bo.ds = (b == 0) ? planes((long long)out * prev) : 0;
+        bo.c1 = planes((long long)mid * prev);
+        bo.c2 = planes((long long)mid * mid * 9);
+        bo.c3 = planes((long long)out * mid);
+        e.bb_off.push_back(bo);
+        prev = out;
+      }
     }
-  }
-  e.off_proj = planes(768LL * 1024);
-  for (int i = 0; i < c.num_blocks; ++i) {
-    Engine::SteOff so;
-    so.qkv = planes(3LL * C * C);
-    so.proj = planes((long long)C * C);
-    so.fc1 = planes(4LL * C * C);
-    so.fc2 = planes(4LL * C * C);
-    so.ts = (c.mode == MODE_PARALLEL) ? planes(4LL * C * C) : 0;
-    e.blk_off.push_back(so);
-  }
-  e.off_pl = planes((long long)C * C);
+    e.off_proj = planes(768LL * 1024);
+    for (int i = 0; i < c.num_blocks; ++i) {
+      Engine::SteOff so;
+      so.qkv = planes(3LL * C * C);
+      so.proj = planes((long long)C * C);
+      so.fc1 = planes(4LL * C * C);
+      so.fc2 = planes(4LL * C * C);
+      so.ts = (c.mode == MODE_PARALLEL) ? planes(4LL * C * C) : 0;
+      e.blk_off.push_back(so);
+    }
+    e.off_pl = planes((long long)C * C);
   }  // !cnn
   e.off_kfc1 = planes((long long)HD * F);
   e.off_kfc2 = planes((long long)HD * HD);
@@ -292,33 +292,33 @@ int engine_pack(const Engine* e, const void* const* params, void* packed, cudaSt
   if (e->cfg.encoder == ENC_CNN) {
     MAED_PROPAGATE(cnn_pack(*e, params, packed, st));
   } else {
-  MAED_PROPAGATE(prep_conv_weight(P(e->i_stem_w), 64, 3, 7, 7, kStemKPad, 1, H(e->off_stem), 64LL * kStemKPad, st));
-  int prev = 64, bi = 0;
-  for (int s = 0; s < 3; ++s) {
-    const int out = kStageOut[s], mid = out / 4;
-    for (int b = 0; b < kStageDepth[s]; ++b, ++bi) {
-      const Engine::BlockIdx& ix = e->bb[bi];
-      const Engine::BlockOff& of = e->bb_off[bi];
-      if (b == 0)
-        MAED_PROPAGATE(prep_conv_weight(P(ix.ds_w), out, prev, 1, 1, prev, 1, H(of.ds), (long long)out * prev, st));
-      MAED_PROPAGATE(prep_conv_weight(P(ix.c1_w), mid, prev, 1, 1, prev, 1, H(of.c1), (long long)mid * prev, st));
-      MAED_PROPAGATE(prep_conv_weight(P(ix.c2_w), mid, mid, 3, 3, 9 * mid, 1, H(of.c2), (long long)mid * mid * 9, st));
-      MAED_PROPAGATE(prep_conv_weight(P(ix.c3_w), out, mid, 1, 1, mid, 1, H(of.c3), (long long)out * mid, st));
-      prev = out;
+    MAED_PROPAGATE(prep_conv_weight(P(e->i_stem_w), 64, 3, 7, 7, kStemKPad, 1, H(e->off_stem), 64LL * kStemKPad, st));
+    int prev = 64, bi = 0;
+    for (int s = 0; s < 3; ++s) {
+      const int out = kStageOut[s], mid = out / 4;
+      for (int b = 0; b < kStageDepth[s]; ++b, ++bi) {
+        const Engine::BlockIdx& ix = e->bb[bi];
+        const Engine::BlockOff& of = e->bb_off[bi];
+        if (b == 0)
+          MAED_PROPAGATE(prep_conv_weight(P(ix.ds_w), out, prev, 1, 1, prev, 1, H(of.ds), (long long)out * prev, st));
+        MAED_PROPAGATE(prep_conv_weight(P(ix.c1_w), mid, prev, 1, 1, prev, 1, H(of.c1), (long long)mid * prev, st));
+        MAED_PROPAGATE(prep_conv_weight(P(ix.c2_w), mid, mid, 3, 3, 9 * mid, 1, H(of.c2), (long long)mid * mid * 9, st));
+        MAED_PROPAGATE(prep_conv_weight(P(ix.c3_w), out, mid, 1, 1, mid, 1, H(of.c3), (long long)out * mid, st));
+        prev = out;
+      }
     }
-  }
-  MAED_PROPAGATE(split_f32(P(e->i_proj_w), H(e->off_proj), 768LL * 1024, 768LL * 1024, st));
-  const long long CC = 768LL * 768;
-  for (int i = 0; i < e->cfg.num_blocks; ++i) {
-    const Engine::SteIdx& ix = e->blk[i];
-    const Engine::SteOff& of = e->blk_off[i];
-    MAED_PROPAGATE(split_f32(P(ix.qkv_w), H(of.qkv), 3 * CC, 3 * CC, st));
-    MAED_PROPAGATE(split_f32(P(ix.proj_w), H(of.proj), CC, CC, st));
-    MAED_PROPAGATE(split_f32(P(ix.fc1_w), H(of.fc1), 4 * CC, 4 * CC, st));
-    MAED_PROPAGATE(split_f32(P(ix.fc2_w), H(of.fc2), 4 * CC, 4 * CC, st));
-    if (e->cfg.mode == MODE_PARALLEL) MAED_PROPAGATE(split_f32(P(ix.ts_w), H(of.ts), 4 * CC, 4 * CC, st));
-  }
-  MAED_PROPAGATE(split_f32(P(e->i_pl_w), H(e->off_pl), CC, CC, st));
+    MAED_PROPAGATE(split_f32(P(e->i_proj_w), H(e->off_proj), 768LL * 1024, 768LL * 1024, st));
+    const long long CC = 768LL * 768;
+    for (int i = 0; i < e->cfg.num_blocks; ++i) {
+      const Engine::SteIdx& ix = e->blk[i];
+      const Engine::SteOff& of = e->blk_off[i];
+      MAED_PROPAGATE(split_f32(P(ix.qkv_w), H(of.qkv), 3 * CC, 3 * CC, st));
+      MAED_PROPAGATE(split_f32(P(ix.proj_w), H(of.proj), CC, CC, st));
+      MAED_PROPAGATE(split_f32(P(ix.fc1_w), H(of.fc1), 4 * CC, 4 * CC, st));
+      MAED_PROPAGATE(split_f32(P(ix.fc2_w), H(of.fc2), 4 * CC, 4 * CC, st));
+      if (e->cfg.mode == MODE_PARALLEL) MAED_PROPAGATE(split_f32(P(ix.ts_w), H(of.ts), 4 * CC, 4 * CC, st));
+    }
+    MAED_PROPAGATE(split_f32(P(e->i_pl_w), H(e->off_pl), CC, CC, st));
   }  // !cnn
   if (e->cfg.decoder == DEC_KTD) {
     // joint_regs.j.weight [6, HD + 6k] -> Wx rows (first HD columns), ancestor blocks (last 6k columns), biases
