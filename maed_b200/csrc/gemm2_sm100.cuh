@@ -1,5 +1,5 @@
-// CTA-pair variant of the tcgen05 GEMM of gemm_sm100.cuh (opt-in: MAED_B200_GEMM_2CTA=1, plain mode only; written at the
-// end of round 1 WITHOUT GPU access — compiled and SASS-checked, not yet run).
+// CTA-pair variant of the tcgen05 GEMM of gemm_sm100.cuh (opt-in: MAED_B200_GEMM_2CTA=1; plain and implicit-conv A operands;
+// written at the end of round 1 WITHOUT GPU access — compiled and SASS-checked, not yet run).
 //
 // Why: the 128 x 256 split-precision tile of gemm_tc_kernel is shared-memory-bandwidth bound (profiles/README.md: MMA operand
 // reads 96 B/clk + TMA fills 62 B/clk against 128 B/clk; tensor pipe 65-73 %).  With tcgen05.mma.cta_group::2 two CTAs of a
@@ -47,7 +47,9 @@ __device__ __forceinline__ void epilogue_store_row32(const float (&v)[32], const
   }
 }
 
-// p.m_tiles counts 256-row tiles here.  tmB's box is {64, BLOCK_N / 2, 1}.
+// p.m_tiles counts 128-row tiles as in gemm_tc_kernel (conv mode: one (image, tile_h x tile_w) patch each); a pair works on
+// tiles 2i (leader) and 2i + 1 (peer) — an odd last tile leaves the peer with zero-filled loads and no stores.  tmB's box is
+// {64, BLOCK_N / 2, 1}.
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -72,7 +74,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const uint32_t rank = cluster_ctarank();                        // 0 = leader
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int num_tiles = m_pairs * p.n_tiles;
 
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmA);
@@ -104,17 +107,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
-        const int row0 = m_tile * 2 * kBlockM + (int)rank * kBlockM;
+        const int m_tile = 2 * (tile / p.n_tiles) + (int)rank, n_tile = tile % p.n_tiles;   // this CTA's 128-row tile
+        const int row0 = m_tile * kBlockM;
         const int col0 = n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        int img = 0, h0 = 0, w0 = 0;
+        if (p.conv) {                                               // m_tile == p.m_tiles (odd tail): img == n_img, all zero fill
+          const int tw = m_tile % p.tiles_w;
+          const int th = (m_tile / p.tiles_w) % p.tiles_h;
+          img = m_tile / (p.tiles_w * p.tiles_h);
+          h0 = th * p.tile_h;
+          w0 = tw * p.tile_w;
+        }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
           uint8_t* sB = sA + nplanes * kABytes;
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * nplanes * (kABytes + kBBytes));
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * nplanes * (p.a_tx_bytes + kBBytes));
           const uint32_t leader_full = map_to_cta(smem_u32(&full_bar[stage]), 0);
           for (int pl = 0; pl < nplanes; ++pl) {
-            tma_load_3d_pair(sA + pl * kABytes, &tmA, leader_full, kb * kBlockK, row0, pl);
+            if (p.conv) {
+              const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+              const int r = tap / p.KW, s = tap % p.KW;
+              tma_load_5d_pair(sA + pl * kABytes, &tmA, leader_full, cb * kBlockK, w0 + s - p.pad_w, h0 + r - p.pad_h, img, pl);
+            } else {
+              tma_load_3d_pair(sA + pl * kABytes, &tmA, leader_full, kb * kBlockK, row0, pl);
+            }
             tma_load_3d_pair(sB + pl * kBBytes, &tmB, leader_full, kb * kBlockK, col0, pl);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -164,9 +181,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
-      const long long out_row = (long long)m_tile * 2 * kBlockM + (long long)rank * kBlockM + row_in_tile;
-      const bool row_ok = out_row < p.M;
+      const int m_tile = 2 * (tile / p.n_tiles) + (int)rank, n_tile = tile % p.n_tiles;
+      long long out_row;
+      bool row_ok;
+      if (p.conv) {
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int img = m_tile / (p.tiles_w * p.tiles_h);
+        const int lh = row_in_tile / p.tile_w, lw = row_in_tile % p.tile_w;
+        const int h = th * p.tile_h + lh, w = tw * p.tile_w + lw;
+        row_ok = (m_tile < p.m_tiles) && (lh < p.tile_h) && (h < p.H) && (w < p.W);
+        out_row = ((long long)img * p.H + h) * p.W + w;
+      } else {
+        out_row = (long long)m_tile * kBlockM + row_in_tile;
+        row_ok = out_row < p.M;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);

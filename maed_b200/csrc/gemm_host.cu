@@ -143,8 +143,7 @@ static int launch_pair(const CUtensorMap& tmA, const GemmArgs& g, GemmParams p, 
     const uint32_t box[3] = {64, (uint32_t)(BN / 2), 1};
     MAED_PROPAGATE(make_tmap_f16(&tmB, g.B, 3, dims, str, box));
   }
-  p.m_tiles = cdiv(g.M, 2 * kBlockM);
-  p.n_tiles = g.N / BN;
+  p.n_tiles = g.N / BN;                                     // p.m_tiles: 128-row tiles, set by the caller (plain or conv)
   const size_t stage_bytes = (size_t)nplanes * (kBlockM * kBlockK * 2 + (BN / 2) * kBlockK * 2);
   int stages = (int)((232448 - 1024 - 512) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -155,7 +154,7 @@ static int launch_pair(const CUtensorMap& tmA, const GemmArgs& g, GemmParams p, 
     MAED_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
-  const long long tiles = (long long)p.m_tiles * p.n_tiles;
+  const long long tiles = (long long)((p.m_tiles + 1) / 2) * p.n_tiles;
   const long long pairs = std::min<long long>(tiles, sm_count() / 2);
   gemm_tc2_kernel<BN><<<(int)(2 * pairs), kGemmThreads, smem, st>>>(tmA, tmB, p);
   MAED_CUDA_CHECK(cudaGetLastError());
@@ -205,7 +204,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   }
   // opt-in CTA-pair path (MAED_B200_GEMM_2CTA=1): plain GEMMs with at least one full pair tile; not yet validated on a GPU
   static const bool pair_on = getenv("MAED_B200_GEMM_2CTA") != nullptr;
-  if (pair_on && !g.conv && g.M >= 2 * kBlockM && (g.N % 128) == 0 && (g.force_block_n == 0 || g.force_block_n >= 128)) {
+  if (pair_on && p.m_tiles >= 2 && (g.N % 128) == 0 && (g.force_block_n == 0 || g.force_block_n >= 128)) {
     const int bn2 = g.force_block_n ? g.force_block_n : ((g.N % 256) == 0 ? 256 : 128);
     return bn2 == 256 ? launch_pair<256>(tmA, g, p, st) : launch_pair<128>(tmA, g, p, st);
   }

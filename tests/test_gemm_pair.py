@@ -38,6 +38,17 @@ for M, N, K, bn in [(256, 256, 64, 0), (512, 128, 192, 0), (25216, 768, 768, 0),
     assert rel_err(ops.join(out), F.gelu(ref + bias.double())) < 3e-6, ("gelu/split", M, N, K)
     out = ops.gemm(pa, pb, bias=bias, residual=res)
     assert rel_err(out, ref + bias.double() + res.double()) < 3e-6, ("residual", M, N, K)
+# implicit-GEMM convs (5-D TMA A operand): even / odd numbers of 128-row tiles, the three map sizes of the backbones
+for n, H, Cin, Cout, k in [(4, 56, 64, 128, 3), (3, 28, 128, 128, 3), (5, 14, 256, 256, 3), (2, 14, 64, 128, 1)]:
+    x = rnd(n, Cin, H, H, seed=8 + n)
+    w = rnd(Cout, Cin, k, k, scale=0.1, seed=9)
+    a = ops.split(x.permute(0, 2, 3, 1).contiguous())
+    wp = ops.split(w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous())
+    out = ops.conv_gemm(a, wp, k, k, k // 2, k // 2)
+    ref = F.conv2d(x.double(), w.double(), padding=k // 2).permute(0, 2, 3, 1).reshape(-1, Cout)
+    e = rel_err(out, ref)
+    worst = max(worst, e)
+    assert e < 2e-5, ("conv", n, H, Cin, Cout, k, e)
 torch.cuda.synchronize()
 print("PAIR_GEMM_OK worst %%.2e" %% worst)
 '''
