@@ -34,7 +34,7 @@ static Engine::CnnConv make_conv(Engine& e, int (*add_param)(Engine&, const std:
   Engine::CnnConv c;
   c.cin = cin; c.cout = cout; c.k = k; c.stride = stride;
   c.k_pad = (k * k * cin + 7) / 8 * 8;
-  c.off_w = c.off_b = 0;
+  c.off_w = c.off_b = c.off_w_raw = 0;
   c.w = add_param(e, conv + ".weight", (long long)cout * cin * k * k);
   c.bn = add_param(e, bn + ".weight", cout);
   add_param(e, bn + ".bias", cout);
@@ -68,6 +68,7 @@ void cnn_add_packed(Engine& e, size_t& off) {
   for (Engine::CnnConv& c : e.cnn) {
     c.off_w = take((size_t)c.cout * c.k_pad * 2 * 2);
     c.off_b = take((size_t)c.cout * 4);
+    c.off_w_raw = take((size_t)c.cout * c.k_pad * 2 * 2);
     max_w = std::max(max_w, (long long)c.cout * c.cin * c.k * c.k);
   }
   e.off_cnn_scratch = take((size_t)max_w * 4);
@@ -82,6 +83,8 @@ int cnn_pack(const Engine& e, const void* const* params, void* packed, cudaStrea
     MAED_PROPAGATE(fold_bn(P(c.w), c.cout, E, P(c.bn), P(c.bn + 1), P(c.bn + 2), P(c.bn + 3), kBnEps, scratch,
                            (float*)(pk + c.off_b), st));
     MAED_PROPAGATE(prep_conv_weight(scratch, c.cout, c.cin, c.k, c.k, c.k_pad, 0, (__half*)(pk + c.off_w),
+                                    (long long)c.cout * c.k_pad, st));
+    MAED_PROPAGATE(prep_conv_weight(P(c.w), c.cout, c.cin, c.k, c.k, c.k_pad, 0, (__half*)(pk + c.off_w_raw),
                                     (long long)c.cout * c.k_pad, st));
   }
   return MAED_OK;

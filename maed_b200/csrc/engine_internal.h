@@ -45,6 +45,7 @@ struct Engine {
     int w, bn;                              // parameter indices: conv weight; bn.weight (bias, running_mean, running_var follow)
     int cin, cout, k, stride, k_pad;        // k_pad: GEMM K (k*k*cin, stem padded to 152)
     size_t off_w, off_b;                    // packed: BN-folded weight planes [cout][k_pad]; folded bias fp32 [cout]
+    size_t off_w_raw;                       // packed: the un-folded weight planes (training: BatchNorm on batch statistics)
   };
   std::vector<CnnConv> cnn;
   size_t off_cnn_scratch = 0;               // fp32 scratch for one BN-scaled weight tensor (pack time only)

@@ -41,6 +41,9 @@ struct ConvL {
   size_t tp_off;               // dgrad packed weight (train pack); stem: unused
   int in_layer;                // producing layer (-1: network input for the stem)
   int res_layer;               // layer whose output is added before the ReLU (-2: none)
+  int pad = -1;                // top / left zero padding; -1: TF "SAME" (ResNetV2), torchvision's convs: k / 2
+  size_t fw_off = 0;           // 'cnn' nets: un-folded forward weight planes in the ENGINE pack (BatchNorm runs on batch statistics)
+  int pad_top() const { return pad >= 0 ? pad : std::max((Hout - 1) * stride + k - Hin, 0) / 2; }
   long long Min(int BT) const { return (long long)BT * Hin * Hin; }
   long long Mout(int BT) const { return (long long)BT * Hout * Hout; }
   int Kcols() const { return k * k * Cin; }
@@ -50,6 +53,7 @@ struct BlockL { int ds, c1, c2, c3, in_layer; };   // layer ids (ds = -1 when ab
 struct Net {
   std::vector<ConvL> L;        // 0 = stem (its "output" is the pooled 56x56x64 map), then the 52 bottleneck convs
   std::vector<BlockL> B;
+  bool bn = false;             // 'cnn' encoder: BatchNorm2d (batch statistics) instead of weight standardisation + GroupNorm
   size_t tp_proj;              // dgrad weights of patch_embed.proj
   struct SteT { size_t qkv, proj, fc1, fc2; };
   std::vector<SteT> ste;
@@ -115,6 +119,8 @@ struct TrainWs {
   std::vector<__half*> out; std::vector<float*> convout; std::vector<double*> stats;
   std::vector<long long> out_plane;
   unsigned char* pool_idx;
+  std::vector<float*> bn_mean, bn_rstd;          // 'cnn': batch statistics of every BatchNorm (tape)
+  double* bn_partial; float* bn_sums;            // 'cnn': scratch of the BatchNorm reductions
   float* tok;                                    // proj output [BT*196, 768]
   std::vector<SteTape> ste;
   float* x_final;
@@ -232,6 +238,110 @@ void carve(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& w) {
   w.total = off;
 }
 
+// ------------------------------------------------------------------------------------------ 'cnn' encoder
+// torchvision ResNet-50 (cnn_engine.cu) as a layer table: 0 = stem (its "output" is the max-pooled 56x56x64 map), then per
+// bottleneck [downsample], conv1, conv2, conv3 in the order of Engine::cnn.  Symmetric padding k / 2.
+Net build_cnn_net(const Engine& e) {
+  Net n;
+  n.bn = true;
+  size_t off = 0;
+  auto planes = [&](long long elems) { size_t o = off; off = align_up(off + (size_t)elems * 2 * 2); return o; };
+  size_t ci = 0;
+  auto add = [&](int Hin, int Cin, int Cout, int k, int stride, int relu, int in_layer, int res_layer) {
+    const Engine::CnnConv& cc = e.cnn[ci++];
+    ConvL L{Hin, Cin, Cout, k, stride, (Hin + 2 * (k / 2) - k) / stride + 1, relu, cc.w, cc.bn, 0, 0, in_layer, res_layer};
+    L.pad = k / 2;
+    L.tp_off = planes((long long)Cout * Cin * k * k);
+    L.fw_off = cc.off_w_raw;
+    n.L.push_back(L);
+    return (int)n.L.size() - 1;
+  };
+  add(224, 3, 64, 7, 2, 1, -1, -2);
+  static const int depth[4] = {3, 4, 6, 3}, mids[4] = {64, 128, 256, 512};
+  int prev = 64, Hc = 56, cur = 0;
+  for (int l = 0; l < 4; ++l) {
+    const int mid = mids[l], out = 4 * mid;
+    for (int b = 0; b < depth[l]; ++b) {
+      const int stride = (l > 0 && b == 0) ? 2 : 1;
+      const int Ho = Hc / stride;
+      BlockL bl;
+      bl.in_layer = cur;
+      bl.ds = -1;
+      int shortcut = cur;
+      if (b == 0) {
+        bl.ds = add(Hc, prev, out, 1, stride, 0, cur, -2);
+        shortcut = bl.ds;
+      }
+      bl.c1 = add(Hc, prev, mid, 1, 1, 1, cur, -2);
+      bl.c2 = add(Hc, mid, mid, 3, stride, 1, bl.c1, -2);
+      bl.c3 = add(Ho, mid, out, 1, 1, 1, bl.c2, shortcut);
+      n.B.push_back(bl);
+      cur = bl.c3;
+      prev = out;
+      Hc = Ho;
+    }
+  }
+  n.tp_proj = 0;
+  n.tpack_bytes = off;
+  return n;
+}
+
+void carve_cnn(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off = align_up(off + bytes); return p; };
+  const int nl = (int)net.L.size();
+  w.out.resize(nl); w.convout.resize(nl); w.stats.assign(nl, nullptr); w.out_plane.resize(nl);
+  w.bn_mean.resize(nl); w.bn_rstd.resize(nl);
+  long long max_mc = 0, max_col = 0, max_xt = 0, max_slab = 0, max_wg = 0;
+  size_t max_partial = 0;
+  for (int l = 0; l < nl; ++l) {
+    const ConvL& L = net.L[l];
+    const long long Mo = L.Mout(BT);
+    const long long out_elems = (l == 0) ? (long long)BT * 3136 * 64 : Mo * L.Cout;
+    w.out_plane[l] = out_elems;
+    w.out[l] = (__half*)take((size_t)out_elems * 4);
+    w.convout[l] = (float*)take((size_t)Mo * L.Cout * 4);
+    w.bn_mean[l] = (float*)take((size_t)L.Cout * 4);
+    w.bn_rstd[l] = (float*)take((size_t)L.Cout * 4);
+    max_mc = max_ll(max_mc, max_ll(Mo * L.Cout, L.Min(BT) * L.Cin));
+    const int kc = (l == 0) ? kStemKPad : L.Kcols();
+    const int kc_pad = (kc + 31) / 32 * 32;
+    if (L.k > 1 || L.stride > 1) max_col = max_ll(max_col, Mo * kc);
+    max_xt = max_ll(max_xt, (long long)kc_pad * ld8(Mo));
+    max_xt = max_ll(max_xt, (long long)L.Cout * ld8(Mo));
+    max_slab = max_ll(max_slab, (long long)splitk_slab_floats(L.Cout, kc_pad, (int)Mo));
+    max_wg = max_ll(max_wg, (long long)L.Cout * kc_pad);
+    max_partial = std::max(max_partial, bn_partial_doubles(Mo, L.Cout));
+  }
+  w.pool_idx = (unsigned char*)take((size_t)BT * 3136 * 64);
+  const int HD = e.cfg.hidden_dim, F = e.feat_dim();
+  w.h1 = (float*)take((size_t)BT * HD * 4);
+  w.h2 = (float*)take((size_t)BT * HD * 4);
+  w.base = (float*)take((size_t)BT * 192 * 4);
+  w.mask1 = (unsigned char*)take((size_t)BT * HD);
+  w.mask2 = (unsigned char*)take((size_t)BT * HD);
+  w.feat_copy = (float*)take((size_t)BT * F * 4);
+  w.pose_copy = (float*)take((size_t)BT * 144 * 4);
+  w.col_plane = max_ll(max_col, 8); w.col = (__half*)take((size_t)w.col_plane * 4);
+  w.pl_a_plane = max_mc; w.pl_a = (__half*)take((size_t)max_mc * 4);
+  w.pl_t_plane = max_xt; w.pl_t = (__half*)take((size_t)max_xt * 4);
+  w.pl_x_plane = max_xt; w.pl_x = (__half*)take((size_t)max_xt * 4);
+  w.dil_plane = max_mc; w.dil = (__half*)take((size_t)max_mc * 4);
+  w.fa = (float*)take((size_t)max_mc * 4);
+  w.fb = (float*)take((size_t)max_mc * 4);
+  w.fc = (float*)take((size_t)max_mc * 4);
+  w.fd = (float*)take((size_t)max_mc * 4);
+  w.wg = (float*)take((size_t)max_wg * 4);
+  w.slabs = (float*)take((size_t)max_slab * 4);
+  w.colsum_scratch = (float*)take((size_t)kColsumChunks * 2048 * 4);
+  w.bn_partial = (double*)take(max_partial * 8);
+  w.bn_sums = (float*)take((size_t)2 * 2048 * 4);
+  for (int i = 0; i < 8; ++i) w.small[i] = (float*)take((size_t)BT * 2048 * 4);
+  w.small_plane = (long long)BT * 2048; w.small_p = (__half*)take((size_t)w.small_plane * 4);
+  w.anc_grad = (float*)take(36 * 95 * 4);
+  w.total = off;
+}
+
 struct Ctx {
   const Engine& e; const Net& net; TrainWs& w; const void* const* params; const uint8_t* pk; const uint8_t* tp;
   int BT, N, T; cudaStream_t st; float inv_ls; float* const* grads; const float* x_img;
@@ -254,24 +364,39 @@ int gemm_plain(const Ctx& c, const __half* A, long long a_plane, int M, int K, c
 }  // namespace
 
 // ================================================================================================ API
-size_t train_pack_bytes(const Engine* e) { return e->cfg.encoder == ENC_STE ? build_net(*e).tpack_bytes + 1024 : 0; }
+size_t train_pack_bytes(const Engine* e) {
+  return (e->cfg.encoder == ENC_CNN ? build_cnn_net(*e) : build_net(*e)).tpack_bytes + 1024;
+}
 
 size_t train_workspace_bytes(const Engine* e, int BT) {
-  if (e->cfg.encoder != ENC_STE) return 0;
-  const Net net = build_net(*e);
   TrainWs w;
-  carve(*e, net, BT, nullptr, w);
+  if (e->cfg.encoder == ENC_CNN) {
+    carve_cnn(*e, build_cnn_net(*e), BT, nullptr, w);
+  } else {
+    const Net net = build_net(*e);
+    carve(*e, net, BT, nullptr, w);
+  }
   return w.total + 1024;
 }
 
 static int check_train_cfg(const Engine& e) {
-  MAED_CHECK_ARG(e.cfg.encoder == ENC_STE, "training supports encoder='ste' only (the 'cnn' encoder is inference-only: "
-                 "BatchNorm batch statistics and their backward are not built)");
   const int m = e.cfg.mode;
-  MAED_CHECK_ARG(m == MODE_PARALLEL || m == MODE_SERIES || m == MODE_VANILLA,
+  MAED_CHECK_ARG(e.cfg.encoder == ENC_CNN || m == MODE_PARALLEL || m == MODE_SERIES || m == MODE_VANILLA,
                  "training supports st_mode parallel / series / vanilla (got mode %d)", m);
   MAED_CHECK_ARG(e.cfg.decoder == DEC_KTD, "training supports the KTD decoder only");
   MAED_CHECK_ARG(e.cfg.nsplit == 3, "training runs in split precision (precision='split')");
+  return MAED_OK;
+}
+
+static int cnn_train_pack(const Engine& e, const void* const* params, void* tpack, cudaStream_t st) {
+  const Net net = build_cnn_net(e);
+  uint8_t* tp = (uint8_t*)(((uintptr_t)tpack + 1023) & ~(uintptr_t)1023);
+  auto P = [&](int i) { return (const float*)params[i]; };
+  for (size_t l = 1; l < net.L.size(); ++l) {             // data-gradient weights (the stem needs none)
+    const ConvL& L = net.L[l];
+    MAED_PROPAGATE(prep_conv_weight_dgrad(P(L.w_idx), L.Cout, L.Cin, L.k, L.k, 0, (__half*)(tp + L.tp_off),
+                                          (long long)L.Cout * L.Cin * L.k * L.k, st));
+  }
   return MAED_OK;
 }
 
@@ -280,6 +405,7 @@ int train_pack(const Engine* ep, const void* const* params, void* tpack, cudaStr
   MAED_PROPAGATE(check_train_cfg(*ep));
   MAED_CHECK_ARG(ep && params && tpack, "train_pack: null argument");
   const Engine& e = *ep;
+  if (e.cfg.encoder == ENC_CNN) return cnn_train_pack(e, params, tpack, st);
   const Net net = build_net(e);
   uint8_t* tp = (uint8_t*)(((uintptr_t)tpack + 1023) & ~(uintptr_t)1023);
   auto P = [&](int i) { return (const float*)params[i]; };
@@ -311,28 +437,94 @@ static int conv_fwd(const Ctx& c, int l) {
   const long long M = L.Mout(BT);
   GemmArgs g;
   g.nsplit = 3;
-  g.B = c.H(L.pk_off); g.b_plane = (long long)L.Cout * L.Kcols();
+  g.B = c.net.bn ? c.H(L.fw_off) : c.H(L.pk_off); g.b_plane = (long long)L.Cout * L.Kcols();
   g.M = (int)M; g.N = L.Cout; g.out_mode = OUT_F32; g.out = w.convout[l]; g.ldc = L.Cout;
-  const int pad_total = std::max((L.Hout - 1) * L.stride + L.k - L.Hin, 0);
+  const int pad = L.pad_top();
   if (L.k == 1 && L.stride == 1) {
     g.A = A; g.a_plane = a_plane; g.K = L.Cin;
   } else if (L.stride == 1) {
     g.A = A; g.a_plane = a_plane; g.K = L.Kcols();
     g.conv = 1; g.n_img = BT; g.H = L.Hin; g.W = L.Hin; g.Cin = L.Cin; g.KH = L.k; g.KW = L.k;
-    g.pad_h = pad_total / 2; g.pad_w = pad_total / 2;
+    g.pad_h = pad; g.pad_w = pad;
   } else {
-    MAED_PROPAGATE(im2col_nhwc(A, a_plane, BT, L.Hin, L.Hin, L.Cin, L.k, L.k, L.stride, pad_total / 2, pad_total / 2, L.Hout,
-                               L.Hout, w.col, w.col_plane, c.st));
+    MAED_PROPAGATE(im2col_nhwc(A, a_plane, BT, L.Hin, L.Hin, L.Cin, L.k, L.k, L.stride, pad, pad, L.Hout, L.Hout, w.col,
+                               w.col_plane, c.st));
     g.A = w.col; g.a_plane = w.col_plane; g.K = L.Kcols();
   }
   MAED_PROPAGATE(launch_gemm(g, c.st));
-  MAED_CUDA_CHECK(cudaMemsetAsync(w.stats[l], 0, (size_t)BT * 64 * 8, c.st));
-  MAED_PROPAGATE(gn_stats(w.convout[l], BT, L.Hout * L.Hout, L.Cout, w.stats[l], c.st));
   const __half* res = L.res_layer >= 0 ? w.out[L.res_layer] : nullptr;
   const long long res_plane = L.res_layer >= 0 ? w.out_plane[L.res_layer] : 0;
+  if (c.net.bn) {                                          // BatchNorm2d.train(): batch statistics + running-buffer update
+    MAED_PROPAGATE(bn_train_stats(w.convout[l], M, L.Cout, 1e-5f, 0.1f, w.bn_partial, w.bn_mean[l], w.bn_rstd[l],
+                                  const_cast<float*>(c.P(L.g_idx + 2)), const_cast<float*>(c.P(L.g_idx + 3)), c.st));
+    return bn_apply(w.convout[l], w.bn_mean[l], w.bn_rstd[l], c.P(L.g_idx), c.P(L.g_idx + 1), M, L.Cout, L.relu, res, res_plane,
+                    w.out[l], w.out_plane[l], c.st);
+  }
+  MAED_CUDA_CHECK(cudaMemsetAsync(w.stats[l], 0, (size_t)BT * 64 * 8, c.st));
+  MAED_PROPAGATE(gn_stats(w.convout[l], BT, L.Hout * L.Hout, L.Cout, w.stats[l], c.st));
   MAED_PROPAGATE(gn_apply(w.convout[l], w.stats[l], c.P(L.g_idx), c.P(L.g_idx + 1), BT, L.Hout * L.Hout, L.Cout, 1e-5f, L.relu,
                           res, res_plane, w.out[l], w.out_plane[l], c.st));
   return MAED_OK;
+}
+
+// one BT-row linear of the tail: fp32 activation -> planes -> split-precision tensor-core GEMM -> fp32
+static int tail_gemm(const Ctx& c, const float* a_f32, int K, size_t w_off, int Nout, const float* bias, int act, float* out) {
+  TrainWs& w = c.w;
+  MAED_PROPAGATE(split_f32(a_f32, w.small_p, w.small_plane, (long long)c.BT * K, c.st));
+  return gemm_plain(c, w.small_p, w.small_plane, c.BT, K, c.H(w_off), (long long)Nout * K, Nout, bias, act, nullptr, OUT_F32, out, 0);
+}
+
+// KTD decoder forward from the encoder feature w.feat_copy [BT, F] (reference ktd.py:69-88), dropout masks kept
+static int decoder_fwd(const Ctx& c, int C, float dropout_p, unsigned long long seed, const TrainOutputs* outs) {
+  const Engine& e = c.e;
+  TrainWs& w = c.w;
+  const int BT = c.BT, HD = e.cfg.hidden_dim;
+  cudaStream_t st = c.st;
+  auto tail = [&](const float* a_f32, int K, size_t w_off, int Nout, const float* bias, int act, float* out) -> int {
+    return tail_gemm(c, a_f32, K, w_off, Nout, bias, act, out);
+  };
+  MAED_PROPAGATE(tail(w.feat_copy, C, e.off_kfc1, HD, c.P(e.i_fc1_b), ACT_NONE, w.h1));
+  if (dropout_p > 0.f) MAED_PROPAGATE(dropout_fwd(w.h1, (long long)BT * HD, dropout_p, seed, w.mask1, st));
+  MAED_PROPAGATE(tail(w.h1, HD, e.off_kfc2, HD, c.P(e.i_fc2_b), ACT_NONE, w.h2));
+  if (dropout_p > 0.f) MAED_PROPAGATE(dropout_fwd(w.h2, (long long)BT * HD, dropout_p, seed ^ 0x5851F42D4C957F2Dull, w.mask2, st));
+  MAED_PROPAGATE(tail(w.h2, HD, e.off_kheads, 192, (const float*)(c.pk + e.off_kheads_b), ACT_NONE, w.base));
+  MAED_PROPAGATE(ktd_tree(w.base, 192, (const float*)(c.pk + e.off_ktd_anc), BT, w.pose_copy, outs->shape, outs->cam, st));
+  MAED_CUDA_CHECK(cudaMemcpyAsync(outs->pose6d, w.pose_copy, (size_t)BT * 144 * 4, cudaMemcpyDeviceToDevice, st));
+  if (outs->feat) MAED_CUDA_CHECK(cudaMemcpyAsync(outs->feat, w.feat_copy, (size_t)BT * C * 4, cudaMemcpyDeviceToDevice, st));
+  return MAED_OK;
+}
+
+// ================================================================================== 'cnn' encoder: training path
+// conv (un-folded weights) -> BatchNorm2d on the statistics of the batch (running buffers updated in place, momentum 0.1)
+// -> (+ identity) -> ReLU; MaxPool(3, 2, 1) keeps its arg-max; 7x7 average pool; KTD decoder.  Single process: the statistics
+// are those of this rank's batch (no SyncBatchNorm exchange).
+static int cnn_train_forward(const Engine& e, const void* const* params, const void* packed, const float* x_in, int N, int T, void* workspace, size_t workspace_bytes, float dropout_p, unsigned long long seed,
+                             const TrainOutputs* outs, cudaStream_t st) {
+  const int BT = N * T;
+  MAED_CHECK_ARG(BT >= 2, "train_forward(cnn): BatchNorm in train() mode needs more than one frame per channel statistic");
+  const Net net = build_cnn_net(e);
+  TrainWs w;
+  carve_cnn(e, net, BT, (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023), w);
+  MAED_CHECK_ARG(w.total + 1024 <= workspace_bytes, "train_forward(cnn): workspace too small (%zu < %zu)", workspace_bytes,
+                 w.total + 1024);
+  Ctx c{e, net, w, params, (const uint8_t*)packed, nullptr, BT, N, T, st, 1.f, nullptr, x_in};
+  // ---- stem: conv1 7x7/2 pad 3 -> BatchNorm (batch statistics) -> ReLU -> MaxPool(3, 2, 1) with arg-max
+  {
+    const ConvL& L = net.L[0];
+    MAED_PROPAGATE(im2col_stem(x_in, BT, 3, 224, 224, 7, 7, 2, 3, 3, 112, 112, kStemKPad, w.col, w.col_plane, st));
+    MAED_PROPAGATE(gemm_plain(c, w.col, w.col_plane, BT * 12544, kStemKPad, c.H(L.fw_off), 64LL * kStemKPad, 64, nullptr, ACT_NONE,
+                              nullptr, OUT_F32, w.convout[0], 0));
+    MAED_PROPAGATE(bn_train_stats(w.convout[0], (long long)BT * 12544, 64, 1e-5f, 0.1f, w.bn_partial, w.bn_mean[0], w.bn_rstd[0],
+                                  const_cast<float*>(c.P(L.g_idx + 2)), const_cast<float*>(c.P(L.g_idx + 3)), st));
+    MAED_PROPAGATE(maxpool3x3s2_idx(w.convout[0], w.bn_mean[0], w.bn_rstd[0], c.P(L.g_idx), c.P(L.g_idx + 1), BT, 112, 112, 64,
+                                    w.out[0], w.out_plane[0], w.pool_idx, st));
+  }
+  for (size_t l = 1; l < net.L.size(); ++l) MAED_PROPAGATE(conv_fwd(c, (int)l));
+  // ---- AdaptiveAvgPool2d(1): mean over the 7x7 positions of layer4's output
+  const int last = (int)net.L.size() - 1, F = e.feat_dim();
+  MAED_PROPAGATE(planes_to_f32(w.out[last], w.out_plane[last], (long long)BT * 49 * F, w.fa, st));
+  MAED_PROPAGATE(token_mean(w.fa, BT, 49, F, w.feat_copy, F, 0, st));
+  return decoder_fwd(c, F, dropout_p, seed, outs);
 }
 
 int train_forward(const Engine* ep, const void* const* params, const void* packed, const float* x_in, int N, int T,
@@ -345,6 +537,9 @@ int train_forward(const Engine* ep, const void* const* params, const void* packe
   const EngineConfig& cf = e.cfg;
   const int BT = N * T;
   MAED_CHECK_ARG(N >= 1 && T >= 1 && T <= 32, "train_forward: bad batch N=%d T=%d", N, T);
+  MAED_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "train_forward: dropout_p=%f", (double)dropout_p);
+  if (cf.encoder == ENC_CNN)
+    return cnn_train_forward(e, params, packed, x_in, N, T, workspace, workspace_bytes, dropout_p, seed, outs, st);
   const bool has_temp = e.i_temp >= 0;
   MAED_CHECK_ARG(!has_temp || T <= cf.temp_frames, "train_forward: seqlen T=%d exceeds temp_embed frames %d", T, cf.temp_frames);
   MAED_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "train_forward: dropout_p=%f", (double)dropout_p);
@@ -410,22 +605,9 @@ int train_forward(const Engine* ep, const void* const* params, const void* packe
   }
 
   // ---- tail (always split precision; fp32 copies of every activation stay on the tape)
-  const int HD = cf.hidden_dim;
-  auto tail = [&](const float* a_f32, int K, size_t w_off, int Nout, const float* bias, int act, float* out) -> int {
-    MAED_PROPAGATE(split_f32(a_f32, w.small_p, w.small_plane, (long long)BT * K, st));
-    return gemm_plain(c, w.small_p, w.small_plane, BT, K, c.H(w_off), (long long)Nout * K, Nout, bias, act, nullptr, OUT_F32, out, 0);
-  };
   MAED_PROPAGATE(layernorm_f32(w.x_final, (long long)ntok * C, c.P(e.i_norm), c.P(e.i_norm + 1), BT, C, 1e-6f, w.cls_ln, st));
-  MAED_PROPAGATE(tail(w.cls_ln, C, e.off_pl, C, c.P(e.i_pl_b), ACT_TANH, w.feat_copy));
-  MAED_PROPAGATE(tail(w.feat_copy, C, e.off_kfc1, HD, c.P(e.i_fc1_b), ACT_NONE, w.h1));
-  if (dropout_p > 0.f) MAED_PROPAGATE(dropout_fwd(w.h1, (long long)BT * HD, dropout_p, seed, w.mask1, st));
-  MAED_PROPAGATE(tail(w.h1, HD, e.off_kfc2, HD, c.P(e.i_fc2_b), ACT_NONE, w.h2));
-  if (dropout_p > 0.f) MAED_PROPAGATE(dropout_fwd(w.h2, (long long)BT * HD, dropout_p, seed ^ 0x5851F42D4C957F2Dull, w.mask2, st));
-  MAED_PROPAGATE(tail(w.h2, HD, e.off_kheads, 192, (const float*)(c.pk + e.off_kheads_b), ACT_NONE, w.base));
-  MAED_PROPAGATE(ktd_tree(w.base, 192, (const float*)(c.pk + e.off_ktd_anc), BT, w.pose_copy, outs->shape, outs->cam, st));
-  MAED_CUDA_CHECK(cudaMemcpyAsync(outs->pose6d, w.pose_copy, (size_t)BT * 144 * 4, cudaMemcpyDeviceToDevice, st));
-  if (outs->feat) MAED_CUDA_CHECK(cudaMemcpyAsync(outs->feat, w.feat_copy, (size_t)BT * C * 4, cudaMemcpyDeviceToDevice, st));
-  return MAED_OK;
+  MAED_PROPAGATE(tail_gemm(c, w.cls_ln, C, e.off_pl, C, c.P(e.i_pl_b), ACT_TANH, w.feat_copy));
+  return decoder_fwd(c, C, dropout_p, seed, outs);
 }
 
 // ------------------------------------------------------------------------------------------- backward
@@ -449,28 +631,32 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
   const int BT = c.BT;
   const long long Mo = L.Mout(BT);
   const int HWo = L.Hout * L.Hout;
-  // ---- GroupNorm backward -> dconv planes [Mo, Cout] in pl_a; dgamma / dbeta
-  MAED_PROPAGATE(groupnorm_bwd(d_y, w.convout[l], w.stats[l], c.P(L.g_idx), BT, HWo, L.Cout, 1e-5f, w.red, w.dgb, w.pl_a,
-                               w.pl_a_plane, c.st));
-  MAED_PROPAGATE(colsum_f32(w.dgb, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx), c.st));
-  MAED_PROPAGATE(colsum_f32(w.dgb + L.Cout, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx + 1), c.st));
+  // ---- norm backward -> dconv planes [Mo, Cout] in pl_a; dgamma / dbeta
+  if (c.net.bn) {
+    MAED_PROPAGATE(bn_bwd(d_y, w.convout[l], w.bn_mean[l], w.bn_rstd[l], c.P(L.g_idx), Mo, L.Cout, c.inv_ls, w.bn_partial,
+                          w.bn_sums, c.G(L.g_idx), c.G(L.g_idx + 1), w.pl_a, w.pl_a_plane, c.st));
+  } else {
+    MAED_PROPAGATE(groupnorm_bwd(d_y, w.convout[l], w.stats[l], c.P(L.g_idx), BT, HWo, L.Cout, 1e-5f, w.red, w.dgb, w.pl_a,
+                                 w.pl_a_plane, c.st));
+    MAED_PROPAGATE(colsum_f32(w.dgb, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx), c.st));
+    MAED_PROPAGATE(colsum_f32(w.dgb + L.Cout, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx + 1), c.st));
+  }
   // ---- weight gradient: dW_hat [Cout, kc] = dconv^T * im2col(x), then through the weight standardisation
   const int ld = ld8(Mo);
   const int kc = (l == 0) ? kStemKPad : L.Kcols();
   const int kc_pad = (kc + 31) / 32 * 32;                  // split-K output width (multiple of 32); extra rows are zero
-  const int pad_total = std::max((L.Hout - 1) * L.stride + L.k - L.Hin, 0);
+  const int pad = L.pad_top();
   MAED_PROPAGATE(transpose_planes(w.pl_a, w.pl_a_plane, (int)Mo, L.Cout, L.Cout, w.pl_t, w.pl_t_plane, ld, c.st));
   const __half* xm;                                        // [Mo, kc] activation matrix of the wgrad
   long long xm_plane;
   if (l == 0) {
-    MAED_PROPAGATE(im2col_stem(c.x_img, BT, 3, 224, 224, 7, 7, 2, pad_total / 2, pad_total / 2, 112, 112, kStemKPad, w.col,
-                               w.col_plane, c.st));
+    MAED_PROPAGATE(im2col_stem(c.x_img, BT, 3, 224, 224, 7, 7, 2, pad, pad, 112, 112, kStemKPad, w.col, w.col_plane, c.st));
     xm = w.col; xm_plane = w.col_plane;
   } else if (L.k == 1 && L.stride == 1) {
     xm = w.out[L.in_layer]; xm_plane = w.out_plane[L.in_layer];
   } else {
-    MAED_PROPAGATE(im2col_nhwc(w.out[L.in_layer], w.out_plane[L.in_layer], BT, L.Hin, L.Hin, L.Cin, L.k, L.k, L.stride,
-                               pad_total / 2, pad_total / 2, L.Hout, L.Hout, w.col, w.col_plane, c.st));
+    MAED_PROPAGATE(im2col_nhwc(w.out[L.in_layer], w.out_plane[L.in_layer], BT, L.Hin, L.Hin, L.Cin, L.k, L.k, L.stride, pad, pad,
+                               L.Hout, L.Hout, w.col, w.col_plane, c.st));
     xm = w.col; xm_plane = w.col_plane;
   }
   if (kc_pad != kc) {                                      // rows kc..kc_pad of the transposed matrix must read as zeros
@@ -480,7 +666,10 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
   MAED_PROPAGATE(transpose_planes(xm, xm_plane, (int)Mo, kc, kc, w.pl_x, w.pl_x_plane, ld, c.st));
   MAED_PROPAGATE(gemm_wgrad_splitk(w.pl_t, w.pl_t_plane, ld, w.pl_x, w.pl_x_plane, ld, L.Cout, kc_pad, (int)Mo, 3, 1.0f, 0,
                                    w.slabs, w.wg, kc_pad, c.st));
-  MAED_PROPAGATE(wstd_bwd(w.wg, kc_pad, c.P(L.w_idx), L.Cout, L.Cin, L.k, L.k, 1e-5f, c.inv_ls, c.G(L.w_idx), c.st));
+  if (c.net.bn)                                            // plain conv: only the [Cout][kh][kw][Cin] -> OIHW permute
+    MAED_PROPAGATE(wgrad_permute(w.wg, kc_pad, L.Cout, L.Cin, L.k, L.k, c.inv_ls, c.G(L.w_idx), c.st));
+  else
+    MAED_PROPAGATE(wstd_bwd(w.wg, kc_pad, c.P(L.w_idx), L.Cout, L.Cin, L.k, L.k, 1e-5f, c.inv_ls, c.G(L.w_idx), c.st));
   if (!d_in) return MAED_OK;
   // ---- data gradient
   const long long tplane = (long long)L.Cout * L.Cin * L.k * L.k;
@@ -505,36 +694,20 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
   g.A = src; g.a_plane = src_plane; g.B = c.TH(L.tp_off); g.b_plane = tplane;
   g.M = (int)L.Min(BT); g.N = L.Cin; g.K = L.k * L.k * L.Cout;
   g.conv = 1; g.n_img = BT; g.H = L.Hin; g.W = L.Hin; g.Cin = L.Cout; g.KH = L.k; g.KW = L.k;
-  g.pad_h = (L.k - 1) - pad_total / 2; g.pad_w = (L.k - 1) - pad_total / 2;
+  g.pad_h = (L.k - 1) - pad; g.pad_w = (L.k - 1) - pad;
   g.residual = d_in_add; g.out_mode = OUT_F32; g.out = d_in; g.ldc = L.Cin;
   return launch_gemm(g, c.st);
 }
 
-int train_backward(const Engine* ep, const void* const* params, const void* packed, const void* tpack, const float* x_in, int N,
-                   int T, void* workspace, size_t workspace_bytes, const float* d_pose6d, const float* d_shape,
-                   const float* d_cam, float loss_scale, float dropout_p, float* const* grads, cudaStream_t st) {
-  MAED_CHECK_ARG(ep, "train_backward: null engine");
-  MAED_PROPAGATE(check_train_cfg(*ep));
-  MAED_CHECK_ARG(ep && params && packed && tpack && x_in && workspace && d_pose6d && d_shape && d_cam && grads,
-                 "train_backward: null argument");
-  MAED_CHECK_ARG(loss_scale > 0.f, "train_backward: loss_scale must be positive");
-  const Engine& e = *ep;
-  const EngineConfig& cf = e.cfg;
-  const int BT = N * T;
-  const Net net = build_net(e);
-  TrainWs w;
-  carve(e, net, BT, (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023), w);
-  MAED_CHECK_ARG(w.total + 1024 <= workspace_bytes, "train_backward: workspace too small");
-  const uint8_t* tp = (const uint8_t*)(((uintptr_t)tpack + 1023) & ~(uintptr_t)1023);
-  Ctx c{e, net, w, params, (const uint8_t*)packed, tp, BT, N, T, st, 1.0f / loss_scale, grads, x_in};
-  const int ntok = 197, C = 768, heads = cf.num_heads, HD = cf.hidden_dim;
-  const int rows = BT * ntok;
-  const float scale = 0.125f;
-  const long long CC = (long long)C * C;
-  const bool has_temp = e.i_temp >= 0;
+// KTD decoder backward (reference ktd.py:69-88): parameter gradients of the heads, fc2, fc1 and d_feat [BT, C] (C = feature
+// width: 768 'ste', 2048 'cnn').  The loss scale enters here: every activation gradient below carries it.
+static int decoder_bwd(const Ctx& c, int C, const float* d_pose6d, const float* d_shape, const float* d_cam, float loss_scale,
+                       float dropout_p, float* d_feat) {
+  const Engine& e = c.e;
+  TrainWs& w = c.w;
+  const int BT = c.BT, HD = e.cfg.hidden_dim;
+  cudaStream_t st = c.st;
   float** sm = w.small;
-
-  // ================================================================================ tail (fp32 CUDA cores)
   // loss scale enters here: every activation gradient below carries it
   float* dpose = sm[0]; float* dshape = sm[1]; float* dcam = sm[2];
   MAED_PROPAGATE(scale_f32(d_pose6d, loss_scale, (long long)BT * 144, dpose, st));
@@ -579,10 +752,89 @@ int train_backward(const Engine* ep, const void* const* params, const void* pack
   MAED_PROPAGATE(sgemm_f32(0, 0, BT, HD, HD, 1.f, d_h2, HD, c.P(e.i_fc2_w), HD, 0.f, d_h1, HD, st));
   if (dropout_p > 0.f) MAED_PROPAGATE(dropout_bwd(d_h1, (long long)BT * HD, dropout_p, w.mask1, st));
   // fc1: h1 = feat W1^T + b1
-  float* d_feat = sm[7];
   MAED_PROPAGATE(sgemm_f32(1, 0, HD, C, BT, c.inv_ls, d_h1, HD, w.feat_copy, C, 0.f, c.G(e.i_fc1_w), C, st));
   MAED_PROPAGATE(colsum_f32(d_h1, HD, BT, HD, c.inv_ls, 0, w.colsum_scratch, c.G(e.i_fc1_b), st));
   MAED_PROPAGATE(sgemm_f32(0, 0, BT, C, HD, 1.f, d_h1, HD, c.P(e.i_fc1_w), C, 0.f, d_feat, C, st));
+  return MAED_OK;
+}
+
+static int cnn_train_backward(const Engine& e, const void* const* params, const void* packed, const void* tpack, const float* x_in,
+                              int N, int T, void* workspace, size_t workspace_bytes, const float* d_pose6d, const float* d_shape,
+                              const float* d_cam, float loss_scale, float dropout_p, float* const* grads, cudaStream_t st) {
+  const int BT = N * T;
+  const Net net = build_cnn_net(e);
+  TrainWs w;
+  carve_cnn(e, net, BT, (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023), w);
+  MAED_CHECK_ARG(w.total + 1024 <= workspace_bytes, "train_backward(cnn): workspace too small");
+  const uint8_t* tp = (const uint8_t*)(((uintptr_t)tpack + 1023) & ~(uintptr_t)1023);
+  Ctx c{e, net, w, params, (const uint8_t*)packed, tp, BT, N, T, st, 1.0f / loss_scale, grads, x_in};
+  const int F = e.feat_dim();
+  float* d_feat = w.small[7];
+  MAED_PROPAGATE(decoder_bwd(c, F, d_pose6d, d_shape, d_cam, loss_scale, dropout_p, d_feat));
+  // average pool: every position of the 7x7 map receives d_feat / 49
+  MAED_PROPAGATE(avgpool_bwd(d_feat, BT, 49, F, w.fc, st));
+  float* bufs[4] = {w.fc, w.fa, w.fb, w.fd};
+  for (int b = (int)net.B.size() - 1; b >= 0; --b) {
+    const BlockL& bl = net.B[b];
+    float* g = bufs[0]; float* d_short = bufs[1]; float* d_t2 = bufs[2]; float* d_t1 = bufs[3];
+    const ConvL& L3 = net.L[bl.c3];
+    const ConvL& L2 = net.L[bl.c2];
+    const ConvL& L1 = net.L[bl.c1];
+    MAED_PROPAGATE(relu_mask_f32(g, w.out[bl.c3], L3.Mout(BT) * L3.Cout, st));
+    const float* shortcut_grad = g;
+    float* d_xin = g;
+    if (bl.ds >= 0) {
+      MAED_PROPAGATE(conv_layer_bwd(c, bl.ds, g, nullptr, d_short, d_t2));
+      shortcut_grad = d_short;
+      d_xin = d_short;
+    }
+    MAED_PROPAGATE(conv_layer_bwd(c, bl.c3, g, nullptr, d_t2, nullptr));
+    MAED_PROPAGATE(relu_mask_f32(d_t2, w.out[bl.c2], L2.Mout(BT) * L2.Cout, st));
+    MAED_PROPAGATE(conv_layer_bwd(c, bl.c2, d_t2, nullptr, d_t1, nullptr));
+    MAED_PROPAGATE(relu_mask_f32(d_t1, w.out[bl.c1], L1.Mout(BT) * L1.Cout, st));
+    MAED_PROPAGATE(conv_layer_bwd(c, bl.c1, d_t1, shortcut_grad, d_xin, nullptr));
+    if (bl.ds >= 0) std::swap(bufs[0], bufs[1]);
+  }
+  // stem: max-pool (gather by arg-max) -> ReLU mask recomputed from the conv output -> BatchNorm -> conv1 (weights only)
+  float* d_pool = bufs[0];
+  float* d_y = bufs[1];
+  const ConvL& L0 = net.L[0];
+  MAED_PROPAGATE(maxpool3x3s2_bwd(d_pool, w.pool_idx, BT, 112, 112, 64, d_y, st));
+  MAED_PROPAGATE(bn_relu_mask(d_y, w.convout[0], w.bn_mean[0], w.bn_rstd[0], c.P(L0.g_idx), c.P(L0.g_idx + 1),
+                              (long long)BT * 12544, 64, st));
+  return conv_layer_bwd(c, 0, d_y, nullptr, nullptr, nullptr);
+}
+
+int train_backward(const Engine* ep, const void* const* params, const void* packed, const void* tpack, const float* x_in, int N,
+                   int T, void* workspace, size_t workspace_bytes, const float* d_pose6d, const float* d_shape,
+                   const float* d_cam, float loss_scale, float dropout_p, float* const* grads, cudaStream_t st) {
+  MAED_CHECK_ARG(ep, "train_backward: null engine");
+  MAED_PROPAGATE(check_train_cfg(*ep));
+  MAED_CHECK_ARG(ep && params && packed && tpack && x_in && workspace && d_pose6d && d_shape && d_cam && grads,
+                 "train_backward: null argument");
+  MAED_CHECK_ARG(loss_scale > 0.f, "train_backward: loss_scale must be positive");
+  const Engine& e = *ep;
+  if (e.cfg.encoder == ENC_CNN)
+    return cnn_train_backward(e, params, packed, tpack, x_in, N, T, workspace, workspace_bytes, d_pose6d, d_shape, d_cam, loss_scale,
+                              dropout_p, grads, st);
+  const EngineConfig& cf = e.cfg;
+  const int BT = N * T;
+  const Net net = build_net(e);
+  TrainWs w;
+  carve(e, net, BT, (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023), w);
+  MAED_CHECK_ARG(w.total + 1024 <= workspace_bytes, "train_backward: workspace too small");
+  const uint8_t* tp = (const uint8_t*)(((uintptr_t)tpack + 1023) & ~(uintptr_t)1023);
+  Ctx c{e, net, w, params, (const uint8_t*)packed, tp, BT, N, T, st, 1.0f / loss_scale, grads, x_in};
+  const int ntok = 197, C = 768, heads = cf.num_heads, HD = cf.hidden_dim;
+  const int rows = BT * ntok;
+  const float scale = 0.125f;
+  const long long CC = (long long)C * C;
+  const bool has_temp = e.i_temp >= 0;
+  float** sm = w.small;
+
+  // ================================================================================ tail (fp32 CUDA cores)
+  float* d_feat = sm[7];
+  MAED_PROPAGATE(decoder_bwd(c, C, d_pose6d, d_shape, d_cam, loss_scale, dropout_p, d_feat));
   // pre_logits: feat = tanh(cls_ln Wp^T + bp)
   float* d_pre = sm[0];
   MAED_PROPAGATE(tanh_bwd(d_feat, w.feat_copy, (long long)BT * C, d_pre, st));

@@ -8,8 +8,8 @@ Differences a caller can observe (documented in INTEGRATION.md):
   * inputs must be CUDA float32 tensors — there is no CPU / eager fallback, by design;
   * `forward` is inference-only unless `enable_training()` is called (the CUDA training path of maed_b200/train.py
     is written but not yet validated on a GPU; opt-in until then);
-  * `encoder='cnn'` (torchvision ResNet-50, stage-1 config) is inference-only: BatchNorm always uses its running
-    statistics (folded into the conv weights), the training path raises for it;
+  * `encoder='cnn'` (torchvision ResNet-50, stage-1 config): eval() folds BatchNorm into the conv weights; the training
+    path normalises with the statistics of this rank's batch (no SyncBatchNorm exchange between ranks yet);
   * `decoder.smpl.*` buffers do not exist (smplx and the SMPL assets are absent): `verts`/`kp_3d` are zeros.
 """
 import ctypes as C
@@ -185,9 +185,6 @@ class MAED(nn.Module):
         """Route train()-mode forwards (with autograd enabled) through the engine's training path
         (maed_b200/train.py: saved-activation tape + CUDA backward).  Opt-in while that path awaits its GPU validation;
         the environment variable MAED_B200_TRAINING=1 enables it for every model."""
-        if flag and self.encoder_type.lower() == "cnn":
-            raise NotImplementedError("the training path covers encoder='ste'; encoder='cnn' is inference-only "
-                                      "(BatchNorm batch statistics / SyncBN and their backward are not built)")
         self._training_enabled = bool(flag)
         self._train_dropout_p = dropout_p       # None: nn.Dropout() default 0.5 (ktd.py:54-56); 0.0 for parity runs
         return self

@@ -223,8 +223,10 @@ class MaedTrainFunction(torch.autograd.Function):
 
 def train_forward(model, x, J_regressor=None):
     """MAED.forward in train() mode with autograd enabled (called from maed_b200.models.maed.MAED.forward)."""
-    if model._cfg.mode not in (_lib.MODES[m] for m in _TRAIN_MODES) or model.decoder_type.lower() != "ktd":
-        raise NotImplementedError("maed_b200 training supports st_mode in %s with the KTD decoder" % (_TRAIN_MODES,))
+    is_cnn = model.encoder_type.lower() == "cnn"
+    if (not is_cnn and model._cfg.mode not in (_lib.MODES[m] for m in _TRAIN_MODES)) or model.decoder_type.lower() != "ktd":
+        raise NotImplementedError("maed_b200 training supports st_mode in %s (or encoder='cnn') with the KTD decoder"
+                                  % (_TRAIN_MODES,))
     if model.precision != "split":
         raise NotImplementedError("maed_b200 training runs in precision='split'")
     if not x.is_cuda:
@@ -239,6 +241,12 @@ def train_forward(model, x, J_regressor=None):
     params = [p for _, p in model._train_param_order]
     dropout_p = model._train_dropout_p if model._train_dropout_p is not None else 0.5   # nn.Dropout() default (ktd.py:54-56)
     pose, shape, cam = MaedTrainFunction.apply(model, x, dropout_p, *params)
+    if is_cnn:
+        # nn.BatchNorm2d.train(): the engine has updated running_mean / running_var in place (momentum 0.1, statistics of
+        # THIS rank's batch — no SyncBatchNorm exchange); count the step and drop the eval-mode weight pack that folds them
+        with torch.no_grad():
+            torch._foreach_add_([b for n, b in model.named_buffers() if n.endswith("num_batches_tracked")], 1)
+        model.invalidate_cache()
     nj = 17 if J_regressor is not None else model.decoder.smpl.n_joints
     o = decode_outputs(pose, shape, cam, nj, model.decoder.smpl, J_regressor)
     return {"theta": o["theta"].reshape(N, T, -1), "verts": o["verts"].reshape(N, T, -1, 3),
@@ -267,6 +275,12 @@ class FusedAdam(torch.optim.Optimizer):
         TrainState.flat_grad) and builds the single-launch optimiser."""
         model._get_engine()
         tensors = model._tensor_table()
+        param_names = {n for n, _ in model.named_parameters()}
+        if any(n not in param_names for n in model._param_names):
+            # the engine table of encoder='cnn' interleaves BatchNorm running buffers with the parameters: they must not be
+            # touched by Adam (weight decay!), so no flat single-launch layout — one launch per parameter tensor
+            return cls([{"params": p, "name": n} for n, p in model.named_parameters()], lr=lr, betas=betas, eps=eps,
+                       weight_decay=weight_decay, model=model)
         total = sum((t.numel() + 3) // 4 * 4 for t in tensors)
         flat = torch.zeros(total, dtype=torch.float32, device=tensors[0].device)
         off = 0

@@ -214,8 +214,11 @@ def ste_encoder(x, sd, mode, T, num_blocks=6, H=12, gemm_in=_ident, taps=None):
 # 'cnn' encoder: torchvision ResNet-50 with fc = Identity                 reference lib/models/maed.py:35-37
 # --------------------------------------------------------------------------------------------------
 def batch_norm_eval(x, sd, p):
-    """nn.BatchNorm2d in eval(): (x - running_mean) / sqrt(running_var + 1e-5) * weight + bias."""
-    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, 1e-5)
+    """nn.BatchNorm2d: eval() -> (x - running_mean) / sqrt(running_var + 1e-5) * weight + bias; with sd["__bn_train__"] set
+    (training-path oracle) -> batch statistics, and the running buffers in `sd` are updated in place (momentum 0.1, unbiased
+    variance) like nn.BatchNorm2d.train() does."""
+    train = bool(sd.get("__bn_train__", False))
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], train, 0.1, 1e-5)
 
 
 def tv_bottleneck(x, sd, p, stride, has_ds, gemm_in=_ident):
@@ -374,14 +377,20 @@ def maed_forward(x, sd, st_mode="parallel", decoder="ktd", num_blocks=6, num_hea
 # gradients (training-path oracle): autograd over the restatement above
 # --------------------------------------------------------------------------------------------------
 def maed_param_grads(x, sd, probe_pose, probe_shape, probe_cam, st_mode="parallel", decoder="ktd", num_blocks=6,
-                     num_heads=12):
+                     num_heads=12, encoder="ste"):
     """dL/dp for every entry of `sd` with L = sum(pose6d*A) + sum(shape*B) + sum(cam*C) — the scalar
     tests/golden/make_golden_grads.py back-propagates through the reference (eval mode: no dropout).
     Returns (L, {key: grad}, {pose6d, shape, cam})."""
-    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    is_buf = lambda k: k.endswith(("running_mean", "running_var", "num_batches_tracked"))  # noqa: E731
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not is_buf(k)) for k, v in sd.items()}
+    if encoder == "cnn":
+        sd["__bn_train__"] = torch.tensor(1)        # train()-mode BatchNorm (the running buffers of this copy get updated)
     taps = {}
-    maed_forward(x, sd, st_mode, decoder, num_blocks, num_heads, taps=taps)
+    maed_forward(x, sd, st_mode, decoder, num_blocks, num_heads, taps=taps, encoder=encoder)
     L = (taps["pose6d"] * probe_pose).sum() + (taps["shape"] * probe_shape).sum() + (taps["cam"] * probe_cam).sum()
     keys = [k for k, v in sd.items() if v.requires_grad]
     grads = torch.autograd.grad(L, [sd[k] for k in keys], allow_unused=True)
-    return L.detach(), {k: g for k, g in zip(keys, grads) if g is not None}, {k: taps[k].detach() for k in ("pose6d", "shape", "cam")}
+    outs = {k: taps[k].detach() for k in ("pose6d", "shape", "cam")}
+    if encoder == "cnn":
+        outs["buffers"] = {k: v.detach() for k, v in sd.items() if k.endswith(("running_mean", "running_var"))}
+    return L.detach(), {k: g for k, g in zip(keys, grads) if g is not None}, outs

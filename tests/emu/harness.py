@@ -149,7 +149,8 @@ class EmuModel:
             self.tpack = torch.full((self.lib.maed_train_pack_bytes(self.eng),), 0xFF, dtype=torch.uint8)         # poisoned
             self._check(self.lib.maed_train_pack(self.eng, self.params, _lib.ptr(self.tpack), None), "train_pack")
         self.ws = torch.full((self.lib.maed_train_workspace_bytes(self.eng, BT),), 0xFF, dtype=torch.uint8)   # poisoned, see forward
-        o = {"feat": torch.zeros(BT, 768), "pose6d": torch.zeros(BT, 144), "shape": torch.zeros(BT, 10), "cam": torch.zeros(BT, 3)}
+        o = {"feat": torch.zeros(BT, getattr(self.m, "feat_dim", 768)), "pose6d": torch.zeros(BT, 144), "shape": torch.zeros(BT, 10),
+             "cam": torch.zeros(BT, 3)}
         outs = _lib.MaedTrainOutputs(_lib.ptr(o["feat"]), _lib.ptr(o["pose6d"]), _lib.ptr(o["shape"]), _lib.ptr(o["cam"]))
         self._check(self.lib.maed_train_forward(self.eng, self.params, _lib.ptr(self.packed), _lib.ptr(self.x), N, T,
                                                 _lib.ptr(self.ws), C.c_size_t(self.ws.numel()), C.c_float(dropout_p),
@@ -160,7 +161,8 @@ class EmuModel:
     def train_backward(self, d_pose, d_shape, d_cam, loss_scale=4096.0, dropout_p=0.0):
         N, T = self._nt
         grads = [torch.full_like(t, float("nan")) for t in self.tensors]          # every entry must be written
-        gp = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+        is_buf = [k.endswith(("running_mean", "running_var")) for k in self.names]  # buffers have no gradient: NULL slot
+        gp = (C.c_void_p * len(grads))(*[None if b else g.data_ptr() for g, b in zip(grads, is_buf)])
         d_pose, d_shape, d_cam = [t.float().contiguous() for t in (d_pose, d_shape, d_cam)]
         self._check(self.lib.maed_train_backward(self.eng, self.params, _lib.ptr(self.packed), _lib.ptr(self.tpack),
                                                  _lib.ptr(self.x), N, T, _lib.ptr(self.ws), C.c_size_t(self.ws.numel()),

@@ -26,6 +26,9 @@ CASES = {
     "grads_parallel_ktd": ("parallel", "ktd", 1, 4, 11),
     "grads_series_ktd": ("series", "ktd", 1, 2, 12),
     "grads_vanilla_ktd": ("vanilla", "ktd", 2, 1, 13),
+    # encoder='cnn' in train() mode: BatchNorm normalises with the statistics of the batch and updates its running buffers
+    # (dropout modules stay in eval mode: random); also stores the running statistics after the step
+    "grads_cnn_ktd": ("vanilla", "ktd", 2, 2, 14, "cnn"),
 }
 NSAMP = 8
 
@@ -46,11 +49,17 @@ def probes(nt, seed):
 
 
 def run_case(name):
-    mode, dec, N, T, seed = CASES[name]
+    mode, dec, N, T, seed = CASES[name][:5]
+    encoder = CASES[name][5] if len(CASES[name]) > 5 else "ste"
     out_dir = os.path.dirname(os.path.abspath(__file__))
-    model = ref_shim.build_reference_model(mode, dec)
+    model = ref_shim.build_reference_model(mode, dec, encoder=encoder)
     synth.fill_module_(model, seed)
     model.eval()
+    if encoder == "cnn":
+        model.train()
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.eval()
     x = synth.synth_frames(N, T, seed)
     grabbed = {}
     orig = model.decoder.get_output
@@ -76,6 +85,15 @@ def run_case(name):
         rec_out["g_stats/" + k] = stats
         rec_out["g_samp/" + k] = samp
     rec_out["names"] = np.array(names)
+    if encoder == "cnn":
+        rec_out["encoder"] = np.array(encoder)
+        for k in ("pose", "shape", "cam"):
+            rec_out["out_" + k] = grabbed[k].detach().numpy()
+        bufs = [k for k, b in model.named_buffers() if k.endswith(("running_mean", "running_var"))]
+        rec_out["buffers"] = np.array(bufs)
+        for k, b in model.named_buffers():
+            if k in bufs:
+                rec_out["buf/" + k] = b.detach().numpy()
     path = os.path.join(out_dir, name + ".npz")
     np.savez_compressed(path, **rec_out)
     print("%-22s %s/%s N=%d T=%d loss=%.6f params=%d -> %.0f KB" % (name, mode, dec, N, T, L.item(), len(names),

@@ -56,7 +56,7 @@ def test_cnn_engine_tables_without_gpu(lib):
     numel = dict(zip(names, (lib.maed_engine_param_numel(h, i) for i in range(n))))
     assert numel["decoder.fc1.weight"] == 1024 * 2048 and numel["encoder.conv1.weight"] == 64 * 3 * 49
     assert lib.maed_engine_workspace_bytes(h, 16) > lib.maed_engine_workspace_bytes(h, 2) > 0
-    assert lib.maed_train_workspace_bytes(h, 2) == 0          # inference only
+    assert lib.maed_train_workspace_bytes(h, 4) > lib.maed_engine_workspace_bytes(h, 4)   # the tape of the training path
     lib.maed_engine_destroy(h)
     bad = _lib.MaedConfig(6, 12, 0, 0, 1024, 3, 16, 7)
     assert lib.maed_engine_create(ctypes.byref(bad), ctypes.byref(h)) != 0

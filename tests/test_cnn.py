@@ -72,8 +72,6 @@ def test_cnn_module_surface():
     m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)
     assert m.encoder_type == "cnn" and m.feat_dim == 2048 and m.decoder.fc1.weight.shape == (1024, 2048)
     assert sum(p.numel() for p in m.encoder.parameters()) == 23508032        # torchvision resnet50 minus fc
-    with pytest.raises(NotImplementedError):
-        m.enable_training()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.eval()(torch.zeros(1, 1, 3, 224, 224))
 
@@ -89,10 +87,102 @@ def test_emulated_engine_matches_reference_golden(harness, name):
         assert rel_err(synth.tap_digest(nchw)[0], g["dig_%s_sub" % ref]) < 1e-4, mine
 
 
-def test_emulated_training_refuses_cnn(harness):
-    em = harness.EmuModel(build_model(load_golden("cnn_ktd")[1]))
-    with pytest.raises(RuntimeError, match="encoder='ste' only"):
-        em.train_forward(torch.zeros(1, 1, 3, 224, 224))
+# ------------------------------------------------------------------------------------------------ training path
+GRADS = "grads_cnn_ktd"        # reference in train() mode (BatchNorm on batch statistics), dropout modules in eval mode
+
+
+def _digest(g, nsamp=8):
+    g = g.detach().double().reshape(-1).cpu()
+    idx = np.unique(np.linspace(0, g.numel() - 1, nsamp).round().astype(np.int64))
+    return g.norm().item(), g[torch.from_numpy(idx)].numpy()
+
+
+def _check_grads(z, grads_by_name, buffers_by_name):
+    """Every parameter gradient against the digests of the unmodified reference; running statistics after the step."""
+    worst = ("", 0.0)
+    for k in [str(s) for s in z["names"]]:
+        g = grads_by_name[k]
+        assert g is not None and not torch.isnan(g).any(), "gradient of %s not (fully) written" % k
+        norm, samp = _digest(g)
+        ref_norm = float(z["g_stats/" + k][0])
+        err = abs(norm - ref_norm) / max(ref_norm, 1e-12)
+        serr = np.abs(samp - z["g_samp/" + k]).max() / max(ref_norm / np.sqrt(g.numel()), 1e-20)
+        if max(err, serr / 25) > worst[1]:
+            worst = (k, max(err, serr / 25))
+        assert err < 2e-2, "%s: |g| %.6e vs reference %.6e" % (k, norm, ref_norm)     # fp32 noise floor, see test_emu_model.py
+        assert serr < 0.25, "%s: sampled entries off by %.3f rms" % (k, serr)
+    for k in [str(s) for s in z["buffers"]]:
+        assert rel_err(buffers_by_name[k], z["buf/" + k]) < 1e-4, k
+    print("%s: worst %s %.2e" % (GRADS, worst[0], worst[1]))
+
+
+def _grad_case():
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", GRADS + ".npz"))
+    N, T, seed = [int(v) for v in z["meta"]]
+    A, B, C = [synth.synth_tensor("grad_probe.%s" % k, (N * T, n), seed) for k, n in (("pose", 144), ("shape", 10), ("cam", 3))]
+    return z, N, T, seed, A, B, C
+
+
+def test_oracle_training_gradients_match_reference():
+    """oracle autograd with train()-mode BatchNorm == the reference's gradients and running-buffer updates."""
+    z, N, T, seed, A, B, C = _grad_case()
+    from maed_b200.models import MAED
+    m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)
+    synth.fill_module_(m, seed)
+    L, g, outs = O.maed_param_grads(synth.synth_frames(N, T, seed), state_dict_of(m), A, B, C, "vanilla", "ktd", encoder="cnn")
+    assert abs(float(L) - float(z["loss"])) < 1e-6
+    for k in [str(s) for s in z["names"]]:
+        assert abs(_digest(g[k])[0] - float(z["g_stats/" + k][0])) <= 1e-5 * float(z["g_stats/" + k][0]), k
+    for k in [str(s) for s in z["buffers"]]:
+        assert rel_err(outs["buffers"][k], z["buf/" + k]) < 1e-6, k
+
+
+def test_emulated_training_matches_reference_gradients(harness):
+    """cnn_train_forward / backward (real sources on the CUDA-on-CPU build) through the C ABI: outputs, all 161 parameter
+    gradients and the 106 running buffers against the unmodified reference in train() mode."""
+    z, N, T, seed, A, B, C = _grad_case()
+    from maed_b200.models import MAED
+    m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)
+    synth.fill_module_(m, seed)
+    em = harness.EmuModel(m)
+    out = em.train_forward(synth.synth_frames(N, T, seed))
+    for k, kk in (("pose", "pose6d"), ("shape", "shape"), ("cam", "cam")):
+        assert rel_err(out[kk], z["out_" + k]) < 2e-4, k
+    loss = (out["pose6d"] * A).sum() + (out["shape"] * B).sum() + (out["cam"] * C).sum()
+    assert abs(loss.item() - float(z["loss"])) < 1e-3 * max(1.0, abs(float(z["loss"])))
+    grads = em.train_backward(A, B, C, loss_scale=4096.0)
+    _check_grads(z, grads, dict(zip(em.names, em.tensors)))
+
+
+def _product_training_step(device):
+    """The PRODUCT modules: MAED('cnn').train().enable_training() -> loss.backward(); returns what _check_grads needs."""
+    z, N, T, seed, A, B, C = _grad_case()
+    from maed_b200.models import MAED
+    m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)
+    synth.fill_module_(m, seed)
+    m = m.to(device).train().enable_training(True, dropout_p=0.0)
+    out = m(synth.synth_frames(N, T, seed).to(device))
+    d = out["_debug"]
+    loss = (d["pose6d"] * A.to(device)).sum() + (d["shape"] * B.to(device)).sum() + (d["cam"] * C.to(device)).sum()
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) < 1e-3 * max(1.0, abs(float(z["loss"])))
+    assert all(int(b) == 1 for n, b in m.named_buffers() if n.endswith("num_batches_tracked"))
+    assert all(p.grad is not None for p in m.parameters())                  # DDP needs a gradient for every parameter
+    _check_grads(z, {k: p.grad for k, p in m.named_parameters()}, dict(m.named_buffers()))
+    return m
+
+
+def test_product_training_step_on_the_emulator(harness):
+    with harness.product_on_cpu():
+        m = _product_training_step("cpu")
+        from maed_b200.train import FusedAdam
+        opt = FusedAdam.for_model(m, lr=1e-3, weight_decay=1e-2)
+        assert opt._flat is None                                             # running buffers must stay out of Adam's reach
+        before = {n: b.clone() for n, b in m.named_buffers()}
+        w0 = m.encoder.conv1.weight.detach().clone()
+        opt.step()
+        assert all(torch.equal(before[n], b) for n, b in m.named_buffers())
+        assert not torch.equal(w0, m.encoder.conv1.weight)
 
 
 # ------------------------------------------------------------------------------------------------ per-kernel checks
@@ -199,3 +289,9 @@ def test_cnn_forward_matches_oracle_on_fresh_input_gpu():
     for k in ("theta", "rotmat"):
         assert rel_err(o[k], ref[k]) < 1e-3, k
     assert rel_err(m.extract_feature(x.cuda()), taps["feat"].reshape(2, 4, -1)) < 2e-4
+
+
+@pytest.mark.gpu
+@GATED
+def test_cnn_training_step_matches_reference_gradients_gpu(lib):
+    _product_training_step("cuda")
