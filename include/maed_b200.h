@@ -160,6 +160,13 @@ typedef struct maed_train_outputs {
   float* shape;   /* [N*T, 10] */
   float* cam;     /* [N*T, 3] */
 } maed_train_outputs;
+/* SyncBatchNorm hook for encoder = 'cnn' (reference train.py:95 converts every BatchNorm to SyncBatchNorm under DDP): when set,
+ * every BatchNorm of maed_train_forward / maed_train_backward places its per-channel sums (2C + 1 doubles: sum, sum of products,
+ * row count) in `buffer` (device memory owned by the caller, >= 2 * 2048 + 1 doubles) and calls fn(user, n): the callback must
+ * add the first n doubles up over the data-parallel ranks in stream order (torch.distributed.all_reduce on the current stream:
+ * NCCL over NVLink on the GPU box, gloo in the CPU tests) and return 0.  fn == NULL: statistics of this rank's batch only. */
+typedef int (*maed_exchange_fn)(void* user, int n_doubles);
+int maed_train_set_exchange(maed_engine* e, maed_exchange_fn fn, void* user, double* buffer, int capacity_doubles);
 size_t maed_train_pack_bytes(const maed_engine* e);
 size_t maed_train_workspace_bytes(const maed_engine* e, int n_frames);
 /* derived weights of the data-gradient GEMMs; redo after every parameter update (like maed_engine_pack) */

@@ -124,18 +124,23 @@ int gemm_wgrad_splitk(const __half* A, long long a_plane, int lda, const __half*
                       cudaStream_t st);
 
 // ---- 'cnn' encoder training (cnn_kernels.cu): BatchNorm2d with batch statistics, MaxPool2d(3, 2, 1) with arg-max, pools
-size_t bn_partial_doubles(long long M, int C);            // scratch of bn_train_stats / bn_bwd
+// SyncBatchNorm hook: when `fn` is set, the per-channel sums (2C + 1 doubles: sum, sum of products, row count) are placed in
+// `buf` (device memory owned by the caller) and fn(user, n) must add the first n doubles up over the data-parallel ranks
+// (e.g. torch.distributed.all_reduce on the current stream) before the statistics are used.
+struct BnExchange { int (*fn)(void* user, int n_doubles); void* user; double* buf; int capacity; };
+size_t bn_partial_doubles(long long M, int C);
+size_t bn_scratch_doubles(long long M, int C);            // scratch (`partial`) of bn_train_stats / bn_bwd
 // mean / rstd over the M rows of x [M, C] (biased variance, eps inside the sqrt); running buffers (may be nullptr) get the
 // momentum update with the unbiased variance, like nn.BatchNorm2d in train()
 int bn_train_stats(const float* x, long long M, int C, float eps, float momentum, double* partial, float* mean, float* rstd,
-                   float* running_mean, float* running_var, cudaStream_t st);
+                   float* running_mean, float* running_var, const BnExchange* ex, cudaStream_t st);
 int bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, long long M, int C,
              int relu, const __half* res_hi, long long res_plane, __half* out_hi, long long out_plane, cudaStream_t st);
 int bn_relu_mask(float* d, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, long long M,
                  int C, cudaStream_t st);
-// dgamma / dbeta = scale * column sums (written), dx -> planes;  sums: 2C floats of scratch
+// dgamma / dbeta = scale * this rank's column sums (written), dx -> planes (means over all ranks when `ex` exchanges)
 int bn_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, long long M, int C,
-           float scale, double* partial, float* sums, float* dgamma, float* dbeta, __half* dx_hi, long long dx_plane,
+           float scale, double* partial, float* dgamma, float* dbeta, __half* dx_hi, long long dx_plane, const BnExchange* ex,
            cudaStream_t st);
 // MaxPool2d(3, 2, 1) of relu(BatchNorm(x)) (mean == nullptr: of x itself) -> planes + the arg-max tap (0..8) per element
 int maxpool3x3s2_idx(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, int n_img, int H,

@@ -82,6 +82,7 @@ static inline int bn_chunks(long long M) {
   return (int)(c < 1 ? 1 : (c > 1024 ? 1024 : c));
 }
 size_t bn_partial_doubles(long long M, int C) { return (size_t)bn_chunks(M) * 2 * C; }
+size_t bn_scratch_doubles(long long M, int C) { return bn_partial_doubles(M, C) + 2 * (size_t)C + 1; }
 
 // partial[chunk][0][c] = sum_r a, partial[chunk][1][c] = sum_r a * b over the rows of the chunk;
 // mode 0 (forward statistics): a = b = x;  mode 1 (backward): a = dy, b = xhat = (x - mean) * rstd.  Thread = channel.
@@ -115,31 +116,61 @@ static int bn_partial(const float* dy, const float* x, const float* mean, const 
   return MAED_OK;
 }
 
-__global__ void bn_finalize_fwd_kernel(const double* __restrict__ partial, int chunks, long long M, int C, float eps,
-                                       float momentum, float* __restrict__ mean, float* __restrict__ rstd,
-                                       float* __restrict__ running_mean, float* __restrict__ running_var) {
+// sums[0..C) = sum_r a, sums[C..2C) = sum_r a*b over all chunks (fixed order), sums[2C] = M: the unit a SyncBatchNorm
+// exchange adds up over the ranks
+__global__ void bn_reduce_chunks_kernel(const double* __restrict__ partial, int chunks, long long M, int C,
+                                        double* __restrict__ sums) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) sums[2 * C] = (double)M;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
   for (int k = 0; k < chunks; ++k) { s += partial[((long long)k * 2) * C + c]; q += partial[((long long)k * 2 + 1) * C + c]; }
-  const double mu = s / (double)M;
-  double var = q / (double)M - mu * mu;                    // biased: what the normalisation uses
+  sums[c] = s;
+  sums[C + c] = q;
+}
+__global__ void bn_finalize_fwd_kernel(const double* __restrict__ sums, int C, float eps, float momentum, float* __restrict__ mean,
+                                       float* __restrict__ rstd, float* __restrict__ running_mean,
+                                       float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double M = sums[2 * C];
+  const double mu = sums[c] / M;
+  double var = sums[C + c] / M - mu * mu;                  // biased: what the normalisation uses
   if (var < 0.0) var = 0.0;
   mean[c] = (float)mu;
   rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
   if (running_mean) {                                      // nn.BatchNorm2d.train(): momentum update, UNBIASED variance
-    const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    const double unb = M > 1.0 ? var * M / (M - 1.0) : var;
     running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mu);
     running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
   }
 }
+// local column sums -> (optional) sum over the data-parallel ranks -> `sums` (device, 2C + 1 doubles)
+static int bn_sums(const float* dy, const float* x, const float* mean, const float* rstd, long long M, int C, int mode,
+                   double* partial, const BnExchange* ex, double** sums_out, cudaStream_t st) {
+  MAED_PROPAGATE(bn_partial(dy, x, mean, rstd, M, C, mode, partial, st));
+  double* sums = partial + bn_partial_doubles(M, C);       // tail of the scratch buffer (see bn_partial_doubles' caller contract)
+  if (ex && ex->fn) {
+    MAED_CHECK_ARG(ex->buf && ex->capacity >= 2 * C + 1, "BatchNorm exchange buffer too small (%d < %d doubles)", ex->capacity,
+                   2 * C + 1);
+    sums = ex->buf;
+  }
+  bn_reduce_chunks_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, bn_chunks(M), M, C, sums);
+  MAED_BW_LAUNCH_CHECK();
+  if (ex && ex->fn) {
+    const int rc = ex->fn(ex->user, 2 * C + 1);            // e.g. torch.distributed.all_reduce on the caller's stream
+    MAED_CHECK_ARG(rc == 0, "BatchNorm statistics exchange failed (callback returned %d)", rc);
+  }
+  *sums_out = sums;
+  return MAED_OK;
+}
 int bn_train_stats(const float* x, long long M, int C, float eps, float momentum, double* partial, float* mean, float* rstd,
-                   float* running_mean, float* running_var, cudaStream_t st) {
+                   float* running_mean, float* running_var, const BnExchange* ex, cudaStream_t st) {
   MAED_CHECK_ARG(x && partial && mean && rstd && M >= 1 && C >= 1, "bn_train_stats: bad argument");
   MAED_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_train_stats: running buffers come in pairs");
-  MAED_PROPAGATE(bn_partial(nullptr, x, nullptr, nullptr, M, C, 0, partial, st));
-  bn_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, bn_chunks(M), M, C, eps, momentum, mean, rstd, running_mean,
-                                                         running_var);
+  double* sums;
+  MAED_PROPAGATE(bn_sums(nullptr, x, nullptr, nullptr, M, C, 0, partial, ex, &sums, st));
+  bn_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, eps, momentum, mean, rstd, running_mean, running_var);
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
 }
@@ -192,22 +223,20 @@ int bn_relu_mask(float* d, const float* x, const float* mean, const float* rstd,
   return MAED_OK;
 }
 
-__global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int chunks, int C, float scale, float* __restrict__ sums,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+// dgamma / dbeta from THIS rank's sums (the data-parallel gradient reduction adds the ranks up, as with SyncBatchNorm)
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C, float scale, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int k = 0; k < chunks; ++k) { s += partial[((long long)k * 2) * C + c]; q += partial[((long long)k * 2 + 1) * C + c]; }
-  sums[c] = (float)s;
-  sums[C + c] = (float)q;
-  dbeta[c] = scale * (float)s;
-  dgamma[c] = scale * (float)q;
+  dbeta[c] = scale * (float)sums[c];
+  dgamma[c] = scale * (float)sums[C + c];
 }
-// dx = gamma * rstd * (dy - mean(dy) - xhat * mean(dy * xhat)) -> planes
+// dx = gamma * rstd * (dy - mean(dy) - xhat * mean(dy * xhat)) -> planes; the means are over all rows of all ranks
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ sums,
-                                    long long total4, int C, float inv_m, __half* __restrict__ dx_hi, long long dx_plane) {
+                                    const float* __restrict__ rstd, const float* __restrict__ gamma, const double* __restrict__ sums,
+                                    long long total4, int C, __half* __restrict__ dx_hi, long long dx_plane) {
   const int c4n = C >> 2;
+  const float inv_m = (float)(1.0 / sums[2 * C]);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4n) * 4;
     const float4 g = reinterpret_cast<const float4*>(dy)[i], v = reinterpret_cast<const float4*>(x)[i];
@@ -217,22 +246,31 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
     for (int k = 0; k < 4; ++k) {
       const float rs = rstd[c + k];
       const float xh = (xv[k] - mean[c + k]) * rs;
-      o[k] = gamma[c + k] * rs * (gv[k] - sums[c + k] * inv_m - xh * sums[C + c + k] * inv_m);
+      o[k] = gamma[c + k] * rs * (gv[k] - (float)sums[c + k] * inv_m - xh * (float)sums[C + c + k] * inv_m);
     }
     store_split4(dx_hi + 4 * i, dx_plane, make_float4(o[0], o[1], o[2], o[3]));
   }
 }
 int bn_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, long long M, int C,
-           float scale, double* partial, float* sums, float* dgamma, float* dbeta, __half* dx_hi, long long dx_plane,
+           float scale, double* partial, float* dgamma, float* dbeta, __half* dx_hi, long long dx_plane, const BnExchange* ex,
            cudaStream_t st) {
-  MAED_CHECK_ARG(dy && x && mean && rstd && gamma && partial && sums && dgamma && dbeta && dx_hi, "bn_bwd: null argument");
+  MAED_CHECK_ARG(dy && x && mean && rstd && gamma && partial && dgamma && dbeta && dx_hi, "bn_bwd: null argument");
   MAED_CHECK_ARG(C % 4 == 0 && dx_plane % 4 == 0, "bn_bwd: C and the plane stride must be multiples of 4");
-  MAED_PROPAGATE(bn_partial(dy, x, mean, rstd, M, C, 1, partial, st));
-  bn_finalize_bwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, bn_chunks(M), C, scale, sums, dgamma, dbeta);
+  // parameter gradients need the LOCAL sums: reduce without the exchange first, then exchange for dx
+  double* local;
+  MAED_PROPAGATE(bn_sums(dy, x, mean, rstd, M, C, 1, partial, nullptr, &local, st));
+  bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(local, C, scale, dgamma, dbeta);
   MAED_BW_LAUNCH_CHECK();
+  const double* sums = local;
+  if (ex && ex->fn) {
+    MAED_CHECK_ARG(ex->buf && ex->capacity >= 2 * C + 1, "BatchNorm exchange buffer too small");
+    MAED_CUDA_CHECK(cudaMemcpyAsync(ex->buf, local, (size_t)(2 * C + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    const int rc = ex->fn(ex->user, 2 * C + 1);
+    MAED_CHECK_ARG(rc == 0, "BatchNorm gradient-statistics exchange failed (callback returned %d)", rc);
+    sums = ex->buf;
+  }
   const long long total4 = M * (C / 4);
-  bn_bwd_apply_kernel<<<grid_for(total4, 256), 256, 0, st>>>(dy, x, mean, rstd, gamma, sums, total4, C, 1.0f / (float)M, dx_hi,
-                                                            dx_plane);
+  bn_bwd_apply_kernel<<<grid_for(total4, 256), 256, 0, st>>>(dy, x, mean, rstd, gamma, sums, total4, C, dx_hi, dx_plane);
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
 }

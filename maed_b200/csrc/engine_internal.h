@@ -4,6 +4,7 @@
 #include <string>
 #include <vector>
 
+#include "bwd_kernels.h"
 #include "engine.h"
 
 namespace maed {
@@ -49,6 +50,7 @@ struct Engine {
   };
   std::vector<CnnConv> cnn;
   size_t off_cnn_scratch = 0;               // fp32 scratch for one BN-scaled weight tensor (pack time only)
+  BnExchange bn_exchange{nullptr, nullptr, nullptr, 0};   // SyncBatchNorm hook of the 'cnn' training path (train_set_exchange)
   int feat_dim() const { return cfg.encoder == ENC_CNN ? 2048 : 768; }
   int np() const { return cfg.nsplit == 3 ? 2 : 1; }
 };

@@ -120,7 +120,7 @@ struct TrainWs {
   std::vector<long long> out_plane;
   unsigned char* pool_idx;
   std::vector<float*> bn_mean, bn_rstd;          // 'cnn': batch statistics of every BatchNorm (tape)
-  double* bn_partial; float* bn_sums;            // 'cnn': scratch of the BatchNorm reductions
+  double* bn_partial;                            // 'cnn': scratch of the BatchNorm reductions
   float* tok;                                    // proj output [BT*196, 768]
   std::vector<SteTape> ste;
   float* x_final;
@@ -311,7 +311,7 @@ void carve_cnn(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& 
     max_xt = max_ll(max_xt, (long long)L.Cout * ld8(Mo));
     max_slab = max_ll(max_slab, (long long)splitk_slab_floats(L.Cout, kc_pad, (int)Mo));
     max_wg = max_ll(max_wg, (long long)L.Cout * kc_pad);
-    max_partial = std::max(max_partial, bn_partial_doubles(Mo, L.Cout));
+    max_partial = std::max(max_partial, bn_scratch_doubles(Mo, L.Cout));
   }
   w.pool_idx = (unsigned char*)take((size_t)BT * 3136 * 64);
   const int HD = e.cfg.hidden_dim, F = e.feat_dim();
@@ -335,7 +335,6 @@ void carve_cnn(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& 
   w.slabs = (float*)take((size_t)max_slab * 4);
   w.colsum_scratch = (float*)take((size_t)kColsumChunks * 2048 * 4);
   w.bn_partial = (double*)take(max_partial * 8);
-  w.bn_sums = (float*)take((size_t)2 * 2048 * 4);
   for (int i = 0; i < 8; ++i) w.small[i] = (float*)take((size_t)BT * 2048 * 4);
   w.small_plane = (long long)BT * 2048; w.small_p = (__half*)take((size_t)w.small_plane * 4);
   w.anc_grad = (float*)take(36 * 95 * 4);
@@ -400,6 +399,13 @@ static int cnn_train_pack(const Engine& e, const void* const* params, void* tpac
   return MAED_OK;
 }
 
+int train_set_exchange(Engine* e, int (*fn)(void*, int), void* user, double* buf, int capacity) {
+  MAED_CHECK_ARG(e, "train_set_exchange: null engine");
+  MAED_CHECK_ARG(!fn || (buf && capacity >= 2 * 2048 + 1), "train_set_exchange: the buffer must hold 2 * 2048 + 1 doubles");
+  e->bn_exchange = BnExchange{fn, user, buf, capacity};
+  return MAED_OK;
+}
+
 int train_pack(const Engine* ep, const void* const* params, void* tpack, cudaStream_t st) {
   MAED_CHECK_ARG(ep, "train_pack: null engine");
   MAED_PROPAGATE(check_train_cfg(*ep));
@@ -456,7 +462,7 @@ static int conv_fwd(const Ctx& c, int l) {
   const long long res_plane = L.res_layer >= 0 ? w.out_plane[L.res_layer] : 0;
   if (c.net.bn) {                                          // BatchNorm2d.train(): batch statistics + running-buffer update
     MAED_PROPAGATE(bn_train_stats(w.convout[l], M, L.Cout, 1e-5f, 0.1f, w.bn_partial, w.bn_mean[l], w.bn_rstd[l],
-                                  const_cast<float*>(c.P(L.g_idx + 2)), const_cast<float*>(c.P(L.g_idx + 3)), c.st));
+                                  const_cast<float*>(c.P(L.g_idx + 2)), const_cast<float*>(c.P(L.g_idx + 3)), &c.e.bn_exchange, c.st));
     return bn_apply(w.convout[l], w.bn_mean[l], w.bn_rstd[l], c.P(L.g_idx), c.P(L.g_idx + 1), M, L.Cout, L.relu, res, res_plane,
                     w.out[l], w.out_plane[l], c.st);
   }
@@ -496,8 +502,9 @@ static int decoder_fwd(const Ctx& c, int C, float dropout_p, unsigned long long 
 
 // ================================================================================== 'cnn' encoder: training path
 // conv (un-folded weights) -> BatchNorm2d on the statistics of the batch (running buffers updated in place, momentum 0.1)
-// -> (+ identity) -> ReLU; MaxPool(3, 2, 1) keeps its arg-max; 7x7 average pool; KTD decoder.  Single process: the statistics
-// are those of this rank's batch (no SyncBatchNorm exchange).
+// -> (+ identity) -> ReLU; MaxPool(3, 2, 1) keeps its arg-max; 7x7 average pool; KTD decoder.  SyncBatchNorm (reference
+// train.py:95): when an exchange callback is installed (train_set_exchange) the per-channel sums of every BatchNorm, forward
+// and backward, are added up over the data-parallel ranks before they are used.
 static int cnn_train_forward(const Engine& e, const void* const* params, const void* packed, const float* x_in, int N, int T, void* workspace, size_t workspace_bytes, float dropout_p, unsigned long long seed,
                              const TrainOutputs* outs, cudaStream_t st) {
   const int BT = N * T;
@@ -515,7 +522,7 @@ static int cnn_train_forward(const Engine& e, const void* const* params, const v
     MAED_PROPAGATE(gemm_plain(c, w.col, w.col_plane, BT * 12544, kStemKPad, c.H(L.fw_off), 64LL * kStemKPad, 64, nullptr, ACT_NONE,
                               nullptr, OUT_F32, w.convout[0], 0));
     MAED_PROPAGATE(bn_train_stats(w.convout[0], (long long)BT * 12544, 64, 1e-5f, 0.1f, w.bn_partial, w.bn_mean[0], w.bn_rstd[0],
-                                  const_cast<float*>(c.P(L.g_idx + 2)), const_cast<float*>(c.P(L.g_idx + 3)), st));
+                                  const_cast<float*>(c.P(L.g_idx + 2)), const_cast<float*>(c.P(L.g_idx + 3)), &e.bn_exchange, st));
     MAED_PROPAGATE(maxpool3x3s2_idx(w.convout[0], w.bn_mean[0], w.bn_rstd[0], c.P(L.g_idx), c.P(L.g_idx + 1), BT, 112, 112, 64,
                                     w.out[0], w.out_plane[0], w.pool_idx, st));
   }
@@ -634,7 +641,7 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
   // ---- norm backward -> dconv planes [Mo, Cout] in pl_a; dgamma / dbeta
   if (c.net.bn) {
     MAED_PROPAGATE(bn_bwd(d_y, w.convout[l], w.bn_mean[l], w.bn_rstd[l], c.P(L.g_idx), Mo, L.Cout, c.inv_ls, w.bn_partial,
-                          w.bn_sums, c.G(L.g_idx), c.G(L.g_idx + 1), w.pl_a, w.pl_a_plane, c.st));
+                          c.G(L.g_idx), c.G(L.g_idx + 1), w.pl_a, w.pl_a_plane, &c.e.bn_exchange, c.st));
   } else {
     MAED_PROPAGATE(groupnorm_bwd(d_y, w.convout[l], w.stats[l], c.P(L.g_idx), BT, HWo, L.Cout, 1e-5f, w.red, w.dgb, w.pl_a,
                                  w.pl_a_plane, c.st));

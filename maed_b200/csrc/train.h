@@ -25,4 +25,8 @@ int train_backward(const Engine* e, const void* const* params, const void* packe
                    int T, void* workspace, size_t workspace_bytes, const float* d_pose6d, const float* d_shape,
                    const float* d_cam, float loss_scale, float dropout_p, float* const* grads, cudaStream_t st);
 
+// SyncBatchNorm hook of the 'cnn' training path: fn(user, n) must add the first n doubles of `buf` (device memory, at least
+// 2 * 2048 + 1 doubles) up over the data-parallel ranks in stream order; fn == nullptr removes the hook (per-rank statistics).
+int train_set_exchange(Engine* e, int (*fn)(void*, int), void* user, double* buf, int capacity);
+
 }  // namespace maed

@@ -134,6 +134,32 @@ class TrainState:
         self.workspace = None
         self.loss_scale = 4096.0
         self.step_seed = 0
+        self._exchange = None
+
+    def ensure_exchange(self, model, dev):
+        """SyncBatchNorm for encoder='cnn' under data parallelism (the reference converts every BatchNorm with
+        nn.SyncBatchNorm.convert_sync_batchnorm, train.py:95): the engine hands the per-channel sums of each BatchNorm to this
+        callback, which adds them up over the ranks with ONE small all-reduce (NCCL over NVLink on the GPU box, stream-ordered;
+        gloo in the CPU tests).  `model.sync_batchnorm = False` keeps per-rank statistics."""
+        import torch.distributed as dist
+        want = (model.encoder_type.lower() == "cnn" and getattr(model, "sync_batchnorm", True) and dist.is_available()
+                and dist.is_initialized() and dist.get_world_size() > 1)
+        if want and self._exchange is None:
+            buf = torch.zeros(2 * 2048 + 1, dtype=torch.float64, device=dev)
+
+            def exchange(_user, n):
+                try:
+                    dist.all_reduce(buf[:n])
+                    return 0
+                except Exception:                       # an exception must not unwind through the C frames
+                    return 1
+
+            fn = _lib.EXCHANGE_FN(exchange)
+            _lib.call("maed_train_set_exchange", model._engine, fn, None, _lib.ptr(buf), buf.numel())
+            self._exchange = (buf, fn)                  # keep the buffer and the ctypes thunk alive
+        elif not want and self._exchange is not None:
+            _lib.call("maed_train_set_exchange", model._engine, _lib.EXCHANGE_FN(0), None, None, 0)
+            self._exchange = None
 
     def ensure_grads(self, tensors):
         """(Re)allocates the flat gradient buffer (engine parameter order, every tensor padded to 4 elements) and
@@ -181,6 +207,7 @@ class MaedTrainFunction(torch.autograd.Function):
             # keyed by the pack generation, not by _packed_key: FusedAdam updates parameters behind autograd's version
             # counters, so the key can repeat although the weights changed (invalidate_cache() forces a re-pack)
             st.ensure_tpack(eng, model._param_ptrs, model._pack_gen, dev)
+            st.ensure_exchange(model, dev)
             ws = st.ensure_workspace(eng, N * T, dev)
             f32 = dict(dtype=torch.float32, device=dev)
             pose = torch.empty(N * T, 144, **f32)

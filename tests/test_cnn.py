@@ -1,11 +1,13 @@
-"""encoder='cnn' (torchvision ResNet-50 + decoder; reference lib/models/maed.py:35-37), inference.
+"""encoder='cnn' (torchvision ResNet-50 + decoder; reference lib/models/maed.py:35-37): inference and training.
 
 CPU (default suite):
   * oracle/maed_oracle.py's ResNet-50 restatement against golden vectors of the UNMODIFIED reference (tests/golden/cnn_*.npz,
     made by tests/golden/make_golden.py through torchvision's own resnet50) -> the oracle is pinned;
   * the host module's state_dict keys / shapes against the reference's (stored in the same files);
   * the real cnn_engine.cu / cnn_kernels.cu sources on the CUDA-on-CPU test build (tests/emu): whole forward against the
-    golden vectors, and the three new kernels against torch.
+    golden vectors, the new kernels against torch, the training step (train()-mode BatchNorm) against gradients and running
+    buffers of the unmodified reference (tests/golden/grads_cnn_ktd.npz) through the C ABI and through the product modules, and
+    a 2-rank gloo run of the SyncBatchNorm exchange against the reference's full-batch step.
 GPU (`-m gpu`): the product library against the golden vectors and the oracle.  Written without GPU access, so these run
 behind MAED_B200_TRAIN_TESTS=1 / the subprocess canary (tests/test_zz_training_canary.py) like the training path.
 """
@@ -183,6 +185,63 @@ def test_product_training_step_on_the_emulator(harness):
         opt.step()
         assert all(torch.equal(before[n], b) for n, b in m.named_buffers())
         assert not torch.equal(w0, m.encoder.conv1.weight)
+
+
+def _syncbn_worker(rank, world, port, q):
+    """One data-parallel rank: its clip of the golden batch, SyncBatchNorm exchange over gloo, gradients summed over ranks."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.setdefault("MAED_EMU_THREADS", "4")
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import harness
+        from maed_b200.models import MAED
+        z, N, T, seed, A, B, C = _grad_case()
+        assert N == world
+        with harness.product_on_cpu():
+            m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)
+            synth.fill_module_(m, seed)
+            m = m.train().enable_training(True, dropout_p=0.0)
+            x = synth.synth_frames(N, T, seed)[rank:rank + 1]                    # this rank's clip
+            rows = slice(rank * T, (rank + 1) * T)
+            d = m(x)["_debug"]
+            out_err = max(rel_err(d[kk], z["out_" + k][rows]) for k, kk in (("pose", "pose6d"), ("shape", "shape"), ("cam", "cam")))
+            loss = (d["pose6d"] * A[rows]).sum() + (d["shape"] * B[rows]).sum() + (d["cam"] * C[rows]).sum()
+            loss.backward()
+            for p in m.parameters():                                              # sum (not mean): the golden loss is a sum over frames
+                dist.all_reduce(p.grad)
+            if rank == 0:
+                _check_grads(z, {k: p.grad for k, p in m.named_parameters()}, dict(m.named_buffers()))
+            q.put((rank, out_err, None))
+    except Exception as e:                                                        # noqa: BLE001
+        import traceback
+        q.put((rank, None, traceback.format_exc()[-2000:] + repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_syncbn_two_ranks_gloo_match_the_full_batch_reference(harness):
+    """2 ranks x 1 clip with the SyncBatchNorm exchange == the reference's single-process step on the 2-clip batch: outputs of
+    each rank's frames, running buffers, and the rank-summed gradients of all 161 parameters."""
+    import socket
+
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, out_err, err in res:
+        assert err is None, "rank %d: %s" % (rank, err)
+        assert out_err < 2e-4, (rank, out_err)
 
 
 # ------------------------------------------------------------------------------------------------ per-kernel checks
