@@ -213,7 +213,13 @@ def run_train(args):
     build.build()
     st_mode = args.st_mode or MODE
     torch.manual_seed(0)
-    model = MAED("ste", 6, 12, st_mode, DECODER, 1024).to(dev).train().enable_training(True)
+    cnn = args.encoder == "cnn"
+    # 'cnn': the literal stage-1 shape (configs/config_stage1.yaml: 128 images per GPU, T = 1, torchvision ResNet-50 encoder)
+    CLIPS_PER_GPU, T = (128, 1) if cnn else (globals()["CLIPS_PER_GPU"], globals()["T"])
+    model = MAED("cnn" if cnn else "ste", 6, 12, st_mode, DECODER, 1024)
+    if cnn:
+        synth.fill_module_(model, 0)              # running statistics / affine parameters of a plausible BatchNorm state
+    model = model.to(dev).train().enable_training(True)
     opt = train.FusedAdam.for_model(model, lr=1e-4, weight_decay=1e-5)          # configs/config_stage2.yaml:63-66
     xs = [synth.synth_frames(CLIPS_PER_GPU, T, 300 + i).to(dev) for i in range(4)]
     target = torch.zeros(CLIPS_PER_GPU, T, 85, device=dev)
@@ -288,14 +294,18 @@ def run_train(args):
     if rank == 0:
         peaks, peak_src = load_peaks()
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-        step_tflops = 3.0 * CLIPS_PER_GPU * GFLOP_PER_CLIP / 1000.0 / (ms_total / args.steps / 1000.0)
+        gflop_per_clip = 8.174 * T if cnn else GFLOP_PER_CLIP                     # ResNet-50: 8.17 GFLOP per frame
+        step_tflops = 3.0 * CLIPS_PER_GPU * gflop_per_clip / 1000.0 / (ms_total / args.steps / 1000.0)
         print(json.dumps({
-            "metric": "clips/sec (T=16, 224x224, bs=8/gpu), MAED ste-%s+ktd train step (fwd+bwd+Adam)" % st_mode,
+            "metric": ("images/sec (224x224, bs=128/gpu, T=1), MAED cnn(ResNet-50)+ktd train step (fwd+bwd+Adam)" if cnn else
+                       "clips/sec (T=16, 224x224, bs=8/gpu), MAED ste-%s+ktd train step (fwd+bwd+Adam)" % st_mode),
             "mode": "train", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 hi/lo split operands for forward, data- and weight-gradient GEMMs; fp32 reductions / Adam",
             "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]: 1xB200 bs=8 T=16 train step (fwd+bwd+Adam), random-init",
+            "config": {"workload": ("configs/config_stage1.yaml shape: 128 images per GPU, encoder='cnn', train step, BatchNorm on "
+                                    "batch statistics (SyncBatchNorm exchange when N > 1)") if cnn else
+                                   "BASELINE configs[2]: 1xB200 bs=8 T=16 train step (fwd+bwd+Adam), random-init",
                        "clips_per_gpu": CLIPS_PER_GPU, "seq_len": T, "st_mode": st_mode, "decoder": DECODER,
                        "loss": ("reference LossVideo, stage-2 weights, fused CUDA loss (keypoint terms act on the zero body model "
                                 "unless SMPL assets are loaded)") if args.loss == "fused" else
@@ -323,6 +333,8 @@ def main():
                     help="forward: BASELINE configs[1] (the driver's metric); train: configs[2] fwd+bwd+Adam (opt-in)")
     ap.add_argument("--loss", default="mse", choices=["mse", "fused"],
                     help="train mode only: 'fused' = the reference's LossVideo through maed_b200.loss (not yet GPU-validated)")
+    ap.add_argument("--encoder", default="ste", choices=["ste", "cnn"],
+                    help="train mode only: 'cnn' = the stage-1 shape, 128 images per GPU (not yet GPU-validated)")
     ap.add_argument("--st-mode", default=None, help="train mode only: parallel (default) or series")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -30,3 +30,6 @@ fi
 # (6) train step (configs[2]): MSE loss first, then the reference loss through the fused kernel
 timeout 900 python bench.py --mode train --steps 5 --warmup 3 > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err; echo "train bench exit $?"; cut -c1-400 gpurun_out/bench_train.json
 timeout 900 python bench.py --mode train --loss fused --steps 5 --warmup 3 > gpurun_out/bench_train_fused.json 2> gpurun_out/bench_train_fused.err; echo "train bench (fused loss) exit $?"; cut -c1-400 gpurun_out/bench_train_fused.json
+# (7) encoder='cnn': inference at the stage-1 shape, then its train step
+timeout 600 python scripts/bench_cnn.py --steps 10 --warmup 3 > gpurun_out/bench_cnn.json 2> gpurun_out/bench_cnn.err; echo "cnn bench exit $?"; cut -c1-400 gpurun_out/bench_cnn.json
+timeout 900 python bench.py --mode train --encoder cnn --steps 5 --warmup 3 > gpurun_out/bench_train_cnn.json 2> gpurun_out/bench_train_cnn.err; echo "cnn train bench exit $?"; cut -c1-400 gpurun_out/bench_train_cnn.json
