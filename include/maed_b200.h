@@ -219,6 +219,18 @@ size_t maed_bwd_wgrad_slab_floats(int Mo, int No, int R);
 int maed_bwd_wgrad_splitk(const void* A, long long a_plane, int lda, const void* B, long long b_plane, int ldb, int Mo, int No,
                           int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, void* stream);
 int maed_bwd_split_transposed(const float* w, int N, int K, void* out_hi, long long plane, void* stream);
+/* nn.BatchNorm2d in train() mode over x [M, C] (rows = N*H*W): batch statistics (mean / rstd out; running buffers updated with
+ * `momentum` and the unbiased variance when given), y = relu?(xhat * gamma + beta (+ residual planes)) -> planes; when dy is
+ * given also the backward: dgamma / dbeta (scaled) and dx planes.  scratch: maed_bwd_batchnorm_scratch_doubles(M, C) doubles. */
+size_t maed_bwd_batchnorm_scratch_doubles(long long M, int C);
+int maed_bwd_batchnorm(const float* x, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                       float* running_mean, float* running_var, int relu, const void* res_hi, long long res_plane, void* y_hi,
+                       long long y_plane, float* mean, float* rstd, const float* dy, float scale, float* dgamma, float* dbeta,
+                       void* dx_hi, long long dx_plane, double* scratch, void* stream);
+/* nn.MaxPool2d(3, 2, 1) on fp32 NHWC -> planes + arg-max tap (0..8) per element; when d_out [n,OH,OW,C] is given also the
+ * backward d_x [n,H,W,C] (gather over the windows of each pixel). */
+int maed_bwd_maxpool3x3s2(const float* x, int n_img, int H, int W, int C, void* out_hi, long long out_plane, unsigned char* idx,
+                          const float* d_out, float* d_x, void* stream);
 int maed_bwd_prep_conv_weight_dgrad(const float* w, int Cout, int Cin, int KH, int KW, int standardize, void* out_hi,
                                     long long plane, void* stream);
 int maed_bwd_dropout(float* x, long long n, float p, unsigned long long seed, unsigned char* mask, float* d, void* stream);

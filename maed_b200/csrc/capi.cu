@@ -220,6 +220,24 @@ int maed_bwd_groupnorm(const float* dy, const float* x, int n_img, int HW, int C
   MAED_PROPAGATE(gn_stats(x, n_img, HW, C, stats_scratch, st));
   return groupnorm_bwd(dy, x, stats_scratch, gamma, n_img, HW, C, eps, red, dgb_partial, (__half*)dx_hi, dx_plane, st);
 }
+size_t maed_bwd_batchnorm_scratch_doubles(long long M, int C) { return bn_scratch_doubles(M, C); }
+int maed_bwd_batchnorm(const float* x, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                       float* running_mean, float* running_var, int relu, const void* res_hi, long long res_plane, void* y_hi,
+                       long long y_plane, float* mean, float* rstd, const float* dy, float scale, float* dgamma, float* dbeta,
+                       void* dx_hi, long long dx_plane, double* scratch, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_PROPAGATE(bn_train_stats(x, M, C, eps, momentum, scratch, mean, rstd, running_mean, running_var, nullptr, st));
+  MAED_PROPAGATE(bn_apply(x, mean, rstd, gamma, beta, M, C, relu, (const __half*)res_hi, res_plane, (__half*)y_hi, y_plane, st));
+  if (!dy) return MAED_OK;
+  return bn_bwd(dy, x, mean, rstd, gamma, M, C, scale, scratch, dgamma, dbeta, (__half*)dx_hi, dx_plane, nullptr, st);
+}
+int maed_bwd_maxpool3x3s2(const float* x, int n_img, int H, int W, int C, void* out_hi, long long out_plane, unsigned char* idx,
+                          const float* d_out, float* d_x, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MAED_PROPAGATE(maxpool3x3s2_idx(x, nullptr, nullptr, nullptr, nullptr, n_img, H, W, C, (__half*)out_hi, out_plane, idx, st));
+  if (!d_out) return MAED_OK;
+  return maxpool3x3s2_bwd(d_out, idx, n_img, H, W, C, d_x, st);
+}
 int maed_bwd_wstd(const float* g, int k_pad, const float* w, int Cout, int Cin, int KH, int KW, float eps, float scale, float* dw,
                   void* stream) {
   return wstd_bwd(g, k_pad, w, Cout, Cin, KH, KW, eps, scale, dw, (cudaStream_t)stream);

@@ -358,3 +358,63 @@ def test_dropout(L):
     keep = mask.float().mean().item()
     assert abs(keep - 0.5) < 5e-3
     assert torch.equal(x, mask.float() * 2.0) and torch.equal(d, x)
+
+
+# ------------------------------------------------------------------------------------ 'cnn' encoder training kernels
+@pytest.mark.parametrize("M,Cc,relu,res", [(1000, 64, 1, 0), (37, 256, 0, 0), (6272, 128, 1, 1)])
+def test_batchnorm_train_forward_backward(L, M, Cc, relu, res):
+    """nn.BatchNorm2d.train() + (residual) + ReLU against torch autograd in float64, incl. the running-buffer update."""
+    _lib, ops = L
+    x = _rand(M, Cc, seed=40) * 1.7 + 0.3
+    gamma, beta = _rand(Cc, seed=41) * 0.2 + 1.0, _rand(Cc, seed=42) * 0.1
+    rm, rv = _rand(Cc, seed=43) * 0.1, _rand(Cc, seed=44).abs() + 0.5
+    dy = _rand(M, Cc, seed=45)
+    resid = _planes(_rand(M, Cc, seed=46), ops) if res else None
+    rm0, rv0 = rm.clone(), rv.clone()
+    y = torch.zeros(2, M, Cc, dtype=torch.float16, device=DEV)
+    dx = torch.zeros_like(y)
+    mean, rstd, dg, db = [torch.zeros(Cc, device=DEV) for _ in range(4)]
+    lib = _lib.load()
+    scratch = torch.zeros(lib.maed_bwd_batchnorm_scratch_doubles(M, Cc), dtype=torch.float64, device=DEV)
+    # reference (float64 autograd): the ReLU mask is applied to dy by the caller in the engine, so compare with relu'(y) * dy
+    xd = x.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rmd, rvd = rm0.double().clone(), rv0.double().clone()
+    yr = F.batch_norm(xd.reshape(M, Cc, 1, 1), rmd, rvd, gd, bd, True, 0.1, 1e-5).reshape(M, Cc)
+    if res:
+        yr = yr + _join(resid)
+    pre = yr
+    if relu:
+        yr = torch.relu(yr)
+    dy_eff = dy.double() * ((pre > 0).double() if relu else 1.0)
+    yr_sum = (yr * dy.double()).sum()
+    gx, gg, gb = torch.autograd.grad(yr_sum, [xd, gd, bd])
+    dy_in = dy_eff.float().contiguous()
+    _lib.call("maed_bwd_batchnorm", _lib.ptr(x), C.c_longlong(M), Cc, _lib.ptr(gamma), _lib.ptr(beta), C.c_float(1e-5),
+              C.c_float(0.1), _lib.ptr(rm), _lib.ptr(rv), relu, _lib.ptr(resid), C.c_longlong(M * Cc if res else 0), _lib.ptr(y),
+              C.c_longlong(M * Cc), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dy_in), C.c_float(0.5), _lib.ptr(dg), _lib.ptr(db),
+              _lib.ptr(dx), C.c_longlong(M * Cc), _lib.ptr(scratch), _lib.stream_ptr())
+    assert rel_err(_join(y), yr.detach()) < 2e-6
+    assert rel_err(rm, rmd) < 1e-6 and rel_err(rv, rvd) < 1e-6
+    assert rel_err(_join(dx), gx) < 2e-5
+    assert rel_err(dg, 0.5 * gg) < 2e-5 and rel_err(db, 0.5 * gb) < 2e-5
+
+
+@pytest.mark.parametrize("n,H,W,Cc", [(2, 12, 10, 8), (1, 7, 9, 4), (3, 112, 112, 64)])
+def test_maxpool3x3s2_forward_backward(L, n, H, W, Cc):
+    _lib, ops = L
+    if _is_emu() and H > 100:
+        pytest.skip("large case: GPU only")
+    x = _rand(n, H, W, Cc, seed=50) - 1.0
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    d_out = _rand(n, OH, OW, Cc, seed=51)
+    out = torch.zeros(2, n, OH, OW, Cc, dtype=torch.float16, device=DEV)
+    idx = torch.zeros(n, OH, OW, Cc, dtype=torch.uint8, device=DEV)
+    d_x = torch.full((n, H, W, Cc), float("nan"), device=DEV)
+    _lib.call("maed_bwd_maxpool3x3s2", _lib.ptr(x), n, H, W, Cc, _lib.ptr(out), C.c_longlong(out[0].numel()), _lib.ptr(idx),
+              _lib.ptr(d_out), _lib.ptr(d_x), _lib.stream_ptr())
+    xr = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    (gr,) = torch.autograd.grad((yr * d_out.double().permute(0, 3, 1, 2)).sum(), xr)
+    assert rel_err(_join(out), yr.detach().permute(0, 2, 3, 1)) < 1e-6
+    assert rel_err(d_x, gr.permute(0, 2, 3, 1)) < 1e-6
