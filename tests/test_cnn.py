@@ -187,6 +187,33 @@ def test_product_training_step_on_the_emulator(harness):
         assert not torch.equal(w0, m.encoder.conv1.weight)
 
 
+def test_stage1_training_loop_on_the_emulator(harness):
+    """The stage-1 loop of the reference (trainer.py:195,240-245: preds = model(images); loss = criterion(preds, target_img=...);
+    loss.backward(); optimizer.step()) with the product modules only: 'cnn' encoder, fused LossImage, FusedAdam."""
+    from oracle import loss_oracle as LO
+    with harness.product_on_cpu():
+        from maed_b200.loss import Loss
+        from maed_b200.models import MAED
+        from maed_b200.train import FusedAdam
+        m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)
+        synth.fill_module_(m, 3)
+        m = m.train().enable_training(True, dropout_p=0.0)
+        crit = Loss(e_loss_weight=300., e_3d_loss_weight=600., e_pose_loss_weight=60., e_shape_loss_weight=0.06, device="cpu")
+        opt = FusedAdam.for_model(m, lr=2e-4, weight_decay=1e-5)
+        images = synth.synth_frames(3, 1, 3)                                   # image batch: T = 1 (trainer.py:177-179)
+        _, target, _ = LO.synth_loss_case(0, 3, 1, 5, image=True)
+        losses = []
+        for _ in range(3):
+            opt.zero_grad()
+            loss, terms = crit(m(images), target_img=target)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+            assert set(terms) == {"loss_kp_2d", "loss_kp_3d", "loss_shape", "loss_pose", "loss_norm"}
+        assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+        assert int(m.encoder.bn1.num_batches_tracked) == 3
+
+
 def _syncbn_worker(rank, world, port, q):
     """One data-parallel rank: its clip of the golden batch, SyncBatchNorm exchange over gloo, gradients summed over ranks."""
     import torch.distributed as dist
