@@ -147,6 +147,7 @@ int maxpool3x3s2_idx(const float* x, const float* mean, const float* rstd, const
                      int W, int C, __half* out_hi, long long plane, unsigned char* idx, cudaStream_t st);
 int maxpool3x3s2_bwd(const float* d_out, const unsigned char* idx, int n_img, int H, int W, int C, float* d_x, cudaStream_t st);
 int avgpool_bwd(const float* d_feat, int BT, int P, int C, float* d_map, cudaStream_t st);
+int add_cols_f32(float* dst, int ldd, const float* src, int lds, int R, int n, int accumulate, cudaStream_t st);
 int wgrad_permute(const float* g, int k_pad, int Cout, int Cin, int KH, int KW, float scale, float* dw, cudaStream_t st);
 
 }  // namespace maed

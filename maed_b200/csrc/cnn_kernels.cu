@@ -398,4 +398,21 @@ int wgrad_permute(const float* g, int k_pad, int Cout, int Cin, int KH, int KW, 
   return MAED_OK;
 }
 
+// dst[r, 0..n) (+)= src[r, 0..n) for R rows with independent row strides (slices of the iterative regressor's input gradient)
+__global__ void add_cols_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ src, int lds, long long total, int n,
+                                int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / n;
+    const int c = (int)(i % n);
+    const float v = src[r * lds + c];
+    dst[r * ldd + c] = accumulate ? dst[r * ldd + c] + v : v;
+  }
+}
+int add_cols_f32(float* dst, int ldd, const float* src, int lds, int R, int n, int accumulate, cudaStream_t st) {
+  const long long total = (long long)R * n;
+  add_cols_kernel<<<grid_for(total, 256), 256, 0, st>>>(dst, ldd, src, lds, total, n, accumulate);
+  MAED_BW_LAUNCH_CHECK();
+  return MAED_OK;
+}
+
 }  // namespace maed

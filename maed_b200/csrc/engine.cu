@@ -36,7 +36,7 @@ __global__ void broadcast_row_kernel(const float* __restrict__ src, int C, long 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[i % C];
 }
-static int broadcast_row(const float* src, int C, int R, float* dst, cudaStream_t st) {
+int broadcast_row(const float* src, int C, int R, float* dst, cudaStream_t st) {
   const long long total = (long long)R * C;
   broadcast_row_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(src, C, total, dst);
   count_launch();

@@ -78,6 +78,9 @@ int run_decoder(const Engine& e, const void* const* params, const uint8_t* packe
 // planes (hi + lo when plane != 0) -> fp32, n elements (debug taps)
 int planes_to_f32(const __half* hi, long long plane, long long n, float* out, cudaStream_t st);
 
+// dst[r, :] = src[0..C) for R rows
+int broadcast_row(const float* src, int C, int R, float* dst, cudaStream_t st);
+
 // ---- 'cnn' encoder (cnn_engine.cu)
 void cnn_add_params(Engine& e, int (*add_param)(Engine&, const std::string&, long long));
 void cnn_add_packed(Engine& e, size_t& off);

@@ -126,6 +126,8 @@ struct TrainWs {
   float* x_final;
   float* cls_ln; float* h1; float* h2; float* base; unsigned char* mask1; unsigned char* mask2;
   float* feat_copy; float* pose_copy;
+  // iterative regressor (spin.py:51-74): input, hidden activations (post dropout) and dropout masks of the 3 iterations
+  float* it_xc[3]; float* it_h1[3]; float* it_h2[3]; unsigned char* it_m1[3]; unsigned char* it_m2[3]; float* it_dxc;
   // ---- scratch shared by forward and backward
   __half* col; long long col_plane;              // im2col matrix / small planes
   __half* pl_a; long long pl_a_plane;            // generic planes (max rows*3072 or M*C)
@@ -203,6 +205,17 @@ void carve(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& w) {
   w.mask2 = (unsigned char*)take((size_t)BT * HD);
   w.feat_copy = (float*)take((size_t)BT * C * 4);
   w.pose_copy = (float*)take((size_t)BT * 144 * 4);
+  if (e.cfg.decoder == DEC_ITERATIVE) {
+    const int KI = e.feat_dim() + 157;
+    for (int i = 0; i < 3; ++i) {
+      w.it_xc[i] = (float*)take((size_t)BT * KI * 4);
+      w.it_h1[i] = (float*)take((size_t)BT * HD * 4);
+      w.it_h2[i] = (float*)take((size_t)BT * HD * 4);
+      w.it_m1[i] = (unsigned char*)take((size_t)BT * HD);
+      w.it_m2[i] = (unsigned char*)take((size_t)BT * HD);
+    }
+    w.it_dxc = (float*)take((size_t)BT * KI * 4);
+  }
   // ---- scratch
   const long long ste_big = rows * 4 * C;                                   // rows x 3072
   max_xt = max_ll(max_xt, (long long)4 * C * ld8(rows));
@@ -322,6 +335,17 @@ void carve_cnn(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& 
   w.mask2 = (unsigned char*)take((size_t)BT * HD);
   w.feat_copy = (float*)take((size_t)BT * F * 4);
   w.pose_copy = (float*)take((size_t)BT * 144 * 4);
+  if (e.cfg.decoder == DEC_ITERATIVE) {
+    const int KI = e.feat_dim() + 157;
+    for (int i = 0; i < 3; ++i) {
+      w.it_xc[i] = (float*)take((size_t)BT * KI * 4);
+      w.it_h1[i] = (float*)take((size_t)BT * HD * 4);
+      w.it_h2[i] = (float*)take((size_t)BT * HD * 4);
+      w.it_m1[i] = (unsigned char*)take((size_t)BT * HD);
+      w.it_m2[i] = (unsigned char*)take((size_t)BT * HD);
+    }
+    w.it_dxc = (float*)take((size_t)BT * KI * 4);
+  }
   w.col_plane = max_ll(max_col, 8); w.col = (__half*)take((size_t)w.col_plane * 4);
   w.pl_a_plane = max_mc; w.pl_a = (__half*)take((size_t)max_mc * 4);
   w.pl_t_plane = max_xt; w.pl_t = (__half*)take((size_t)max_xt * 4);
@@ -382,7 +406,6 @@ static int check_train_cfg(const Engine& e) {
   const int m = e.cfg.mode;
   MAED_CHECK_ARG(e.cfg.encoder == ENC_CNN || m == MODE_PARALLEL || m == MODE_SERIES || m == MODE_VANILLA,
                  "training supports st_mode parallel / series / vanilla (got mode %d)", m);
-  MAED_CHECK_ARG(e.cfg.decoder == DEC_KTD, "training supports the KTD decoder only");
   MAED_CHECK_ARG(e.cfg.nsplit == 3, "training runs in split precision (precision='split')");
   return MAED_OK;
 }
@@ -481,8 +504,36 @@ static int tail_gemm(const Ctx& c, const float* a_f32, int K, size_t w_off, int 
 }
 
 // KTD decoder forward from the encoder feature w.feat_copy [BT, F] (reference ktd.py:69-88), dropout masks kept
+// iterative regressor forward (reference spin.py:51-74), fp32 CUDA-core GEMMs like the inference engine; tape: it_*
+static int decoder_fwd_iterative(const Ctx& c, int C, float dropout_p, unsigned long long seed, const TrainOutputs* outs) {
+  const Engine& e = c.e;
+  TrainWs& w = c.w;
+  const int BT = c.BT, HD = e.cfg.hidden_dim, KI = C + 157;
+  cudaStream_t st = c.st;
+  MAED_PROPAGATE(broadcast_row(c.P(e.i_init_pose), 144, BT, w.pose_copy, st));
+  MAED_PROPAGATE(broadcast_row(c.P(e.i_init_shape), 10, BT, outs->shape, st));
+  MAED_PROPAGATE(broadcast_row(c.P(e.i_init_cam), 3, BT, outs->cam, st));
+  for (int it = 0; it < 3; ++it) {
+    MAED_PROPAGATE(concat_cols(w.feat_copy, C, w.pose_copy, 144, outs->shape, 10, outs->cam, 3, BT, w.it_xc[it], st));
+    MAED_PROPAGATE(linear_f32(w.it_xc[it], KI, c.P(e.i_fc1_w), KI, c.P(e.i_fc1_b), BT, HD, KI, 0, nullptr, 0, w.it_h1[it], HD, st));
+    if (dropout_p > 0.f)
+      MAED_PROPAGATE(dropout_fwd(w.it_h1[it], (long long)BT * HD, dropout_p, seed + 2 * it, w.it_m1[it], st));
+    MAED_PROPAGATE(linear_f32(w.it_h1[it], HD, c.P(e.i_fc2_w), HD, c.P(e.i_fc2_b), BT, HD, HD, 0, nullptr, 0, w.it_h2[it], HD, st));
+    if (dropout_p > 0.f)
+      MAED_PROPAGATE(dropout_fwd(w.it_h2[it], (long long)BT * HD, dropout_p, (seed + 2 * it + 1) ^ 0x5851F42D4C957F2Dull, w.it_m2[it], st));
+    MAED_PROPAGATE(linear_f32(w.it_h2[it], HD, c.P(e.i_decpose_w), HD, c.P(e.i_decpose_b), BT, 144, HD, 0, w.pose_copy, 144,
+                              w.pose_copy, 144, st));
+    MAED_PROPAGATE(linear_f32(w.it_h2[it], HD, c.P(e.i_shape_w), HD, c.P(e.i_shape_b), BT, 10, HD, 0, outs->shape, 10, outs->shape, 10, st));
+    MAED_PROPAGATE(linear_f32(w.it_h2[it], HD, c.P(e.i_cam_w), HD, c.P(e.i_cam_b), BT, 3, HD, 0, outs->cam, 3, outs->cam, 3, st));
+  }
+  MAED_CUDA_CHECK(cudaMemcpyAsync(outs->pose6d, w.pose_copy, (size_t)BT * 144 * 4, cudaMemcpyDeviceToDevice, st));
+  if (outs->feat) MAED_CUDA_CHECK(cudaMemcpyAsync(outs->feat, w.feat_copy, (size_t)BT * C * 4, cudaMemcpyDeviceToDevice, st));
+  return MAED_OK;
+}
+
 static int decoder_fwd(const Ctx& c, int C, float dropout_p, unsigned long long seed, const TrainOutputs* outs) {
   const Engine& e = c.e;
+  if (e.cfg.decoder == DEC_ITERATIVE) return decoder_fwd_iterative(c, C, dropout_p, seed, outs);
   TrainWs& w = c.w;
   const int BT = c.BT, HD = e.cfg.hidden_dim;
   cudaStream_t st = c.st;
@@ -708,9 +759,54 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
 
 // KTD decoder backward (reference ktd.py:69-88): parameter gradients of the heads, fc2, fc1 and d_feat [BT, C] (C = feature
 // width: 768 'ste', 2048 'cnn').  The loss scale enters here: every activation gradient below carries it.
+// iterative regressor backward: walks the 3 iterations in reverse; the state gradients (pose / shape / cam) flow both into the
+// heads of the previous iteration and, through the concatenated input, into fc1; weight gradients accumulate over iterations
+static int decoder_bwd_iterative(const Ctx& c, int C, const float* d_pose6d, const float* d_shape, const float* d_cam,
+                                 float loss_scale, float dropout_p, float* d_feat) {
+  const Engine& e = c.e;
+  TrainWs& w = c.w;
+  const int BT = c.BT, HD = e.cfg.hidden_dim, KI = C + 157;
+  cudaStream_t st = c.st;
+  float** sm = w.small;
+  float* dP = sm[0]; float* dS = sm[1]; float* dC = sm[2]; float* d_h2 = sm[5]; float* d_h1 = sm[6];
+  MAED_PROPAGATE(scale_f32(d_pose6d, loss_scale, (long long)BT * 144, dP, st));
+  MAED_PROPAGATE(scale_f32(d_shape, loss_scale, (long long)BT * 10, dS, st));
+  MAED_PROPAGATE(scale_f32(d_cam, loss_scale, (long long)BT * 3, dC, st));
+  for (int it = 2; it >= 0; --it) {
+    const float beta = it == 2 ? 0.f : 1.f;                // weight gradients: written by the first visited iteration, then added
+    const int acc = it == 2 ? 0 : 1;
+    // heads: state_{it+1} = head(h2_it) + state_it
+    MAED_PROPAGATE(sgemm_f32(1, 0, 144, HD, BT, c.inv_ls, dP, 144, w.it_h2[it], HD, beta, c.G(e.i_decpose_w), HD, st));
+    MAED_PROPAGATE(colsum_f32(dP, 144, BT, 144, c.inv_ls, acc, w.colsum_scratch, c.G(e.i_decpose_b), st));
+    MAED_PROPAGATE(sgemm_f32(1, 0, 10, HD, BT, c.inv_ls, dS, 10, w.it_h2[it], HD, beta, c.G(e.i_shape_w), HD, st));
+    MAED_PROPAGATE(colsum_f32(dS, 10, BT, 10, c.inv_ls, acc, w.colsum_scratch, c.G(e.i_shape_b), st));
+    MAED_PROPAGATE(sgemm_f32(1, 0, 3, HD, BT, c.inv_ls, dC, 3, w.it_h2[it], HD, beta, c.G(e.i_cam_w), HD, st));
+    MAED_PROPAGATE(colsum_f32(dC, 3, BT, 3, c.inv_ls, acc, w.colsum_scratch, c.G(e.i_cam_b), st));
+    MAED_PROPAGATE(sgemm_f32(0, 0, BT, HD, 144, 1.f, dP, 144, c.P(e.i_decpose_w), HD, 0.f, d_h2, HD, st));
+    MAED_PROPAGATE(sgemm_f32(0, 0, BT, HD, 10, 1.f, dS, 10, c.P(e.i_shape_w), HD, 1.f, d_h2, HD, st));
+    MAED_PROPAGATE(sgemm_f32(0, 0, BT, HD, 3, 1.f, dC, 3, c.P(e.i_cam_w), HD, 1.f, d_h2, HD, st));
+    if (dropout_p > 0.f) MAED_PROPAGATE(dropout_bwd(d_h2, (long long)BT * HD, dropout_p, w.it_m2[it], st));
+    // fc2
+    MAED_PROPAGATE(sgemm_f32(1, 0, HD, HD, BT, c.inv_ls, d_h2, HD, w.it_h1[it], HD, beta, c.G(e.i_fc2_w), HD, st));
+    MAED_PROPAGATE(colsum_f32(d_h2, HD, BT, HD, c.inv_ls, acc, w.colsum_scratch, c.G(e.i_fc2_b), st));
+    MAED_PROPAGATE(sgemm_f32(0, 0, BT, HD, HD, 1.f, d_h2, HD, c.P(e.i_fc2_w), HD, 0.f, d_h1, HD, st));
+    if (dropout_p > 0.f) MAED_PROPAGATE(dropout_bwd(d_h1, (long long)BT * HD, dropout_p, w.it_m1[it], st));
+    // fc1 on xc = [feat | pose | shape | cam]
+    MAED_PROPAGATE(sgemm_f32(1, 0, HD, KI, BT, c.inv_ls, d_h1, HD, w.it_xc[it], KI, beta, c.G(e.i_fc1_w), KI, st));
+    MAED_PROPAGATE(colsum_f32(d_h1, HD, BT, HD, c.inv_ls, acc, w.colsum_scratch, c.G(e.i_fc1_b), st));
+    MAED_PROPAGATE(sgemm_f32(0, 0, BT, KI, HD, 1.f, d_h1, HD, c.P(e.i_fc1_w), KI, 0.f, w.it_dxc, KI, st));
+    MAED_PROPAGATE(add_cols_f32(d_feat, C, w.it_dxc, KI, BT, C, acc, st));
+    MAED_PROPAGATE(add_cols_f32(dP, 144, w.it_dxc + C, KI, BT, 144, 1, st));
+    MAED_PROPAGATE(add_cols_f32(dS, 10, w.it_dxc + C + 144, KI, BT, 10, 1, st));
+    MAED_PROPAGATE(add_cols_f32(dC, 3, w.it_dxc + C + 154, KI, BT, 3, 1, st));
+  }
+  return MAED_OK;
+}
+
 static int decoder_bwd(const Ctx& c, int C, const float* d_pose6d, const float* d_shape, const float* d_cam, float loss_scale,
                        float dropout_p, float* d_feat) {
   const Engine& e = c.e;
+  if (e.cfg.decoder == DEC_ITERATIVE) return decoder_bwd_iterative(c, C, d_pose6d, d_shape, d_cam, loss_scale, dropout_p, d_feat);
   TrainWs& w = c.w;
   const int BT = c.BT, HD = e.cfg.hidden_dim;
   cudaStream_t st = c.st;

@@ -251,9 +251,8 @@ class MaedTrainFunction(torch.autograd.Function):
 def train_forward(model, x, J_regressor=None):
     """MAED.forward in train() mode with autograd enabled (called from maed_b200.models.maed.MAED.forward)."""
     is_cnn = model.encoder_type.lower() == "cnn"
-    if (not is_cnn and model._cfg.mode not in (_lib.MODES[m] for m in _TRAIN_MODES)) or model.decoder_type.lower() != "ktd":
-        raise NotImplementedError("maed_b200 training supports st_mode in %s (or encoder='cnn') with the KTD decoder"
-                                  % (_TRAIN_MODES,))
+    if not is_cnn and model._cfg.mode not in (_lib.MODES[m] for m in _TRAIN_MODES):
+        raise NotImplementedError("maed_b200 training supports st_mode in %s (or encoder='cnn')" % (_TRAIN_MODES,))
     if model.precision != "split":
         raise NotImplementedError("maed_b200 training runs in precision='split'")
     if not x.is_cuda:

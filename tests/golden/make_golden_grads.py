@@ -29,6 +29,9 @@ CASES = {
     # encoder='cnn' in train() mode: BatchNorm normalises with the statistics of the batch and updates its running buffers
     # (dropout modules stay in eval mode: random); also stores the running statistics after the step
     "grads_cnn_ktd": ("vanilla", "ktd", 2, 2, 14, "cnn"),
+    # iterative regressor (spin.py:51-74): three passes through the same fc1 / fc2 / heads, state fed back into fc1
+    "grads_vanilla_iterative": ("vanilla", "iterative", 1, 2, 15),
+    "grads_cnn_iterative": ("vanilla", "iterative", 3, 1, 16, "cnn"),
 }
 NSAMP = 8
 

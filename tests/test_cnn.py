@@ -91,6 +91,7 @@ def test_emulated_engine_matches_reference_golden(harness, name):
 
 # ------------------------------------------------------------------------------------------------ training path
 GRADS = "grads_cnn_ktd"        # reference in train() mode (BatchNorm on batch statistics), dropout modules in eval mode
+GRADS_ITER = "grads_cnn_iterative"   # same with the iterative regressor (spin.py:51-74), 3 images
 
 
 def _digest(g, nsamp=8):
@@ -118,20 +119,22 @@ def _check_grads(z, grads_by_name, buffers_by_name):
     print("%s: worst %s %.2e" % (GRADS, worst[0], worst[1]))
 
 
-def _grad_case():
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", GRADS + ".npz"))
+def _grad_case(name=GRADS):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
     N, T, seed = [int(v) for v in z["meta"]]
     A, B, C = [synth.synth_tensor("grad_probe.%s" % k, (N * T, n), seed) for k, n in (("pose", 144), ("shape", 10), ("cam", 3))]
     return z, N, T, seed, A, B, C
 
 
-def test_oracle_training_gradients_match_reference():
+@pytest.mark.parametrize("name", [GRADS, GRADS_ITER])
+def test_oracle_training_gradients_match_reference(name):
     """oracle autograd with train()-mode BatchNorm == the reference's gradients and running-buffer updates."""
-    z, N, T, seed, A, B, C = _grad_case()
+    z, N, T, seed, A, B, C = _grad_case(name)
+    dec = str(z["decoder"])
     from maed_b200.models import MAED
-    m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)
+    m = MAED("cnn", 6, 12, "vanilla", dec, 1024, mean_params=synth.mean_params())
     synth.fill_module_(m, seed)
-    L, g, outs = O.maed_param_grads(synth.synth_frames(N, T, seed), state_dict_of(m), A, B, C, "vanilla", "ktd", encoder="cnn")
+    L, g, outs = O.maed_param_grads(synth.synth_frames(N, T, seed), state_dict_of(m), A, B, C, "vanilla", dec, encoder="cnn")
     assert abs(float(L) - float(z["loss"])) < 1e-6
     for k in [str(s) for s in z["names"]]:
         assert abs(_digest(g[k])[0] - float(z["g_stats/" + k][0])) <= 1e-5 * float(z["g_stats/" + k][0]), k
@@ -139,12 +142,13 @@ def test_oracle_training_gradients_match_reference():
         assert rel_err(outs["buffers"][k], z["buf/" + k]) < 1e-6, k
 
 
-def test_emulated_training_matches_reference_gradients(harness):
-    """cnn_train_forward / backward (real sources on the CUDA-on-CPU build) through the C ABI: outputs, all 161 parameter
-    gradients and the 106 running buffers against the unmodified reference in train() mode."""
-    z, N, T, seed, A, B, C = _grad_case()
+@pytest.mark.parametrize("name", [GRADS, GRADS_ITER])
+def test_emulated_training_matches_reference_gradients(harness, name):
+    """cnn_train_forward / backward (real sources on the CUDA-on-CPU build) through the C ABI: outputs, every parameter
+    gradient (161 encoder + decoder tensors) and the 106 running buffers against the unmodified reference in train() mode."""
+    z, N, T, seed, A, B, C = _grad_case(name)
     from maed_b200.models import MAED
-    m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)
+    m = MAED("cnn", 6, 12, "vanilla", str(z["decoder"]), 1024, mean_params=synth.mean_params())
     synth.fill_module_(m, seed)
     em = harness.EmuModel(m)
     out = em.train_forward(synth.synth_frames(N, T, seed))
@@ -212,6 +216,29 @@ def test_stage1_training_loop_on_the_emulator(harness):
             assert set(terms) == {"loss_kp_2d", "loss_kp_3d", "loss_shape", "loss_pose", "loss_norm"}
         assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
         assert int(m.encoder.bn1.num_batches_tracked) == 3
+
+
+def test_iterative_decoder_dropout_masks_are_replayed(harness):
+    """train()-mode dropout of the iterative regressor (spin.py:66-69, six masks per step): the backward must replay the masks
+    of the forward — checked by linearity: with the same seed, gradients for probes (A, B, C) and (2A, 2B, 2C) differ by
+    exactly 2, and a different seed gives different gradients."""
+    z, N, T, seed, A, B, C = _grad_case(GRADS_ITER)
+    from maed_b200.models import MAED
+    m = MAED("cnn", 6, 12, "vanilla", "iterative", 1024, mean_params=synth.mean_params())
+    synth.fill_module_(m, seed)
+    x = synth.synth_frames(N, T, seed)
+    key = "decoder.fc1.weight"
+
+    def run(scale, sd):
+        em = harness.EmuModel(m)                          # (train()-mode BatchNorm normalises with batch statistics: no carry-over)
+        out = em.train_forward(x, dropout_p=0.5, seed=sd)
+        return out, em.train_backward(scale * A, scale * B, scale * C, loss_scale=1024.0, dropout_p=0.5)[key]
+
+    o1, g1 = run(1.0, 7)
+    _, g2 = run(2.0, 7)
+    o3, g3 = run(1.0, 8)
+    assert torch.isfinite(g1).all() and rel_err(g2, 2.0 * g1) < 1e-5
+    assert rel_err(o3["pose6d"], o1["pose6d"]) > 1e-3 and rel_err(g3, g1) > 1e-3
 
 
 def _syncbn_worker(rank, world, port, q):

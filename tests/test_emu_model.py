@@ -46,13 +46,13 @@ def _digest(g, nsamp=8):
     return g.norm().item(), g[torch.from_numpy(idx)].numpy()
 
 
-@pytest.mark.parametrize("name", ["grads_vanilla_ktd", "grads_series_ktd", "grads_parallel_ktd"])
+@pytest.mark.parametrize("name", ["grads_vanilla_ktd", "grads_series_ktd", "grads_parallel_ktd", "grads_vanilla_iterative"])
 def test_emulated_training_matches_reference_gradients(harness, name):
     from maed_b200.models import MAED
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     N, T, seed = [int(v) for v in z["meta"]]
     mode = str(z["mode"])
-    m = MAED("ste", 6, 12, mode, "ktd", 1024)
+    m = MAED("ste", 6, 12, mode, str(z["decoder"]), 1024, mean_params=synth.mean_params())
     synth.fill_module_(m, seed)
     em = harness.EmuModel(m)
     x = synth.synth_frames(N, T, seed)
