@@ -259,6 +259,20 @@ int maed_smpl_forward(const maed_smpl_assets* assets, const float* betas, const 
                       int n_reg, float* verts, float* joints, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Geometry tail of the training path (maed_b200/csrc/decode_bwd.cu): gradients through rot6d -> rotation matrix -> angle-axis
+ * (reference lib/utils/geometry.py:320-334,58-223) and the weak-perspective keypoint projection (lib/models/spin.py:113-157);
+ * the forward of the first is maed_op_decode_outputs.
+ * ---------------------------------------------------------------------------------------------- */
+/* d_pose6d [R,144] = J_rotmat^T d_rotmat [R,24,9] (or NULL) + J_aa^T d_aa (72 values per frame at row stride ld_aa, e.g. theta + 3
+ * with ld_aa = 85; or NULL) */
+int maed_decode_pose_backward(const float* pose6d, int R, const float* d_rotmat, const float* d_aa, int ld_aa, float* d_pose6d,
+                              void* stream);
+/* d_kp2d == NULL: kp2d [R,J,2] = project(kp3d [R,J,3] or NULL (zeros), cam [R,3]);  otherwise the backward: d_cam [R,3] and, when
+ * d_kp3d != NULL, d_kp3d [R,J,3] */
+int maed_project_keypoints(const float* kp3d, const float* cam, int R, int J, float* kp2d, const float* d_kp2d, float* d_cam,
+                           float* d_kp3d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused training loss (maed_b200/csrc/loss.cu): replaces `self.criterion(preds, ...)` (reference lib/core/trainer.py:254 ->
  * lib/core/loss.py:159-210 LossVideo / :214-283 LossImage) — every term of the reference and its gradient with respect to
  * the predictions in three launches, no host synchronisation.

@@ -111,6 +111,9 @@ SIGNATURES = {
     "maed_bwd_split_transposed": (_I, [_P, _I, _I, _P, _L, _P]),
     "maed_bwd_prep_conv_weight_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "maed_bwd_dropout": (_I, [_P, _L, _F, _U, _P, _P, _P]),
+    # ---- geometry tail (training)
+    "maed_decode_pose_backward": (_I, [_P, _I, _P, _P, _I, _P, _P]),
+    "maed_project_keypoints": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     # ---- fused loss
     "maed_loss_scratch_bytes": (_Z, [_I, _I]),
     "maed_loss_forward_backward": (_I, [_P, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _I, C.POINTER(MaedLossWeights), _P, _P, _P, _P,

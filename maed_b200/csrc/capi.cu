@@ -320,6 +320,17 @@ int maed_smpl_forward(const maed_smpl_assets* assets, const float* betas, const 
 }
 
 
+// ---- geometry tail of the training path
+int maed_decode_pose_backward(const float* pose6d, int R, const float* d_rotmat, const float* d_aa, int ld_aa, float* d_pose6d,
+                              void* stream) {
+  return decode_pose_backward(pose6d, R, d_rotmat, d_aa, ld_aa, d_pose6d, (cudaStream_t)stream);
+}
+int maed_project_keypoints(const float* kp3d, const float* cam, int R, int J, float* kp2d, const float* d_kp2d, float* d_cam,
+                           float* d_kp3d, void* stream) {
+  if (!d_kp2d) return project_keypoints_forward(kp3d, cam, R, J, kp2d, (cudaStream_t)stream);
+  return project_keypoints_backward(kp3d, cam, R, J, d_kp2d, d_cam, d_kp3d, (cudaStream_t)stream);
+}
+
 // ---- fused loss
 static_assert(sizeof(maed_loss_weights) == sizeof(LossWeights), "maed_loss_weights must mirror LossWeights");
 size_t maed_loss_scratch_bytes(int M2, int M3) { return loss_scratch_bytes(M2, M3); }

@@ -103,6 +103,12 @@ int ktd_tree(const float* base, int ld, const float* w_anc, int R, float* pose6d
 // (reference geometry.py:320-334,58-223; ktd.py:94-124; spin.py:113-157)
 int decode_outputs(const float* pose6d, const float* shape, const float* cam, int R, const float* kp3d, int n_joints,
                    float* rotmat, float* theta, float* kp2d, cudaStream_t st);
+// training-path geometry tail (decode_bwd.cu): backward of pose6d -> rotmat / angle-axis, and the keypoint projection
+int decode_pose_backward(const float* pose6d, int R, const float* d_rotmat, const float* d_aa, int ld_aa, float* d_pose6d,
+                         cudaStream_t st);
+int project_keypoints_forward(const float* kp3d, const float* cam, int R, int J, float* kp2d, cudaStream_t st);
+int project_keypoints_backward(const float* kp3d, const float* cam, int R, int J, const float* d_kp2d, float* d_cam, float* d_kp3d,
+                               cudaStream_t st);
 int concat_cols(const float* a, int ca, const float* b, int cb, const float* c, int cc, const float* d, int cd, int R,
                 float* out, cudaStream_t st);
 

@@ -8,8 +8,8 @@ runs in libmaed_b200.so:
     parameter gradient written into one flat fp32 buffer; the returned gradients are views of it, so DDP hooks and
     ``optimizer.zero_grad()`` behave as with any nn.Module);
   * ``decode_outputs`` — the O(BT*24) geometry tail (rot6d -> rotmat -> angle-axis, projection; reference
-    lib/utils/geometry.py:320-334,58-223, lib/models/spin.py:113-157) in plain torch ops so that autograd links the
-    reference's ``Loss`` to the engine boundary;
+    lib/utils/geometry.py:320-334,58-223, lib/models/spin.py:113-157) as two small autograd nodes over CUDA kernels
+    (``csrc/decode_bwd.cu``), so that autograd links the reference's ``Loss`` to the engine boundary;
   * ``FusedAdam`` — torch.optim.Adam semantics (reference lib/utils/utils.py:127-131) in one kernel per step over the
     flat parameter / gradient / moment buffers;
   * ``allreduce_gradients`` — data-parallel gradient averaging over ``torch.distributed`` (NCCL over NVLink on the GPU
@@ -28,54 +28,72 @@ _TRAIN_MODES = ("parallel", "series", "vanilla")
 
 
 # ----------------------------------------------------------------------------------------------- geometry tail
-def rot6d_to_rotmat(x):
-    """reference lib/utils/geometry.py:320-334 (Gram-Schmidt on the two columns of x.view(-1, 3, 2))."""
-    x = x.reshape(-1, 3, 2)
-    a1, a2 = x[:, :, 0], x[:, :, 1]
-    b1 = torch.nn.functional.normalize(a1, dim=1, eps=1e-6)
-    b2 = torch.nn.functional.normalize(a2 - torch.einsum("bi,bi->b", b1, a2).unsqueeze(-1) * b1, dim=1, eps=1e-6)
-    b3 = torch.cross(b1, b2, dim=1)
-    return torch.stack((b1, b2, b3), dim=-1)
+class _PoseTail(torch.autograd.Function):
+    """(pose6d [R,144], shape [R,10], cam [R,3]) -> (theta [R,85] = cam | angle-axis | shape, rotmat [R,24,3,3]).
+    reference lib/utils/geometry.py:320-334 (rot6d -> rotation matrix) and :58-223 (-> angle-axis), lib/models/ktd.py:116-118.
+    Forward: the inference engine's kernel (maed_op_decode_outputs); backward: csrc/decode_bwd.cu (forward-mode derivative of
+    the same arithmetic), one launch."""
+
+    @staticmethod
+    def forward(ctx, pose6d, shape, cam):
+        if not pose6d.is_cuda:
+            raise RuntimeError("maed_b200 geometry tail runs on CUDA only; got a %s tensor — there is no CPU fallback" % pose6d.device)
+        pose6d, shape, cam = [t.contiguous().float() for t in (pose6d, shape, cam)]
+        R = pose6d.shape[0]
+        f32 = dict(dtype=torch.float32, device=pose6d.device)
+        rot, theta, dummy = torch.empty(R, 24, 3, 3, **f32), torch.empty(R, 85, **f32), torch.empty(R, 1, 2, **f32)
+        with torch.cuda.device(pose6d.device):
+            _lib.call("maed_op_decode_outputs", _lib.ptr(pose6d), _lib.ptr(shape), _lib.ptr(cam), R, None, 1, _lib.ptr(rot),
+                      _lib.ptr(theta), _lib.ptr(dummy), _lib.stream_ptr())
+        ctx.save_for_backward(pose6d)
+        return theta, rot
+
+    @staticmethod
+    def backward(ctx, d_theta, d_rot):
+        (pose6d,) = ctx.saved_tensors
+        R = pose6d.shape[0]
+        d_theta = d_theta.contiguous().float() if d_theta is not None else None
+        d_rot = d_rot.contiguous().float() if d_rot is not None else None
+        d_pose = torch.empty_like(pose6d)
+        with torch.cuda.device(pose6d.device):
+            d_aa = C.c_void_p(d_theta.data_ptr() + 12) if d_theta is not None else None       # theta[:, 3:75]
+            _lib.call("maed_decode_pose_backward", _lib.ptr(pose6d), R, _lib.ptr(d_rot), d_aa, 85, _lib.ptr(d_pose),
+                      _lib.stream_ptr())
+        if d_theta is None:
+            return d_pose, None, None
+        return d_pose, d_theta[:, 75:], d_theta[:, :3]
 
 
-def rotmat_to_angle_axis(R):
-    """reference geometry.py:58-87 -> 143-223 -> 90-140: rotation matrix -> quaternion (four masked cases on the
-    transposed matrix) -> angle-axis; NaN entries are zeroed like the reference does."""
-    m = R.reshape(-1, 3, 3).transpose(1, 2)
-    m00, m01, m02 = m[:, 0, 0], m[:, 0, 1], m[:, 0, 2]
-    m10, m11, m12 = m[:, 1, 0], m[:, 1, 1], m[:, 1, 2]
-    m20, m21, m22 = m[:, 2, 0], m[:, 2, 1], m[:, 2, 2]
-    neg_z = m22 < 1e-6
-    x_gt_y = m00 > m11
-    x_lt_ny = m00 < -m11
-    t0, t1 = 1 + m00 - m11 - m22, 1 - m00 + m11 - m22
-    t2, t3 = 1 - m00 - m11 + m22, 1 + m00 + m11 + m22
-    q0 = torch.stack([m12 - m21, t0, m01 + m10, m20 + m02], -1)
-    q1 = torch.stack([m20 - m02, m01 + m10, t1, m12 + m21], -1)
-    q2 = torch.stack([m01 - m10, m20 + m02, m12 + m21, t2], -1)
-    q3 = torch.stack([t3, m12 - m21, m20 - m02, m01 - m10], -1)
-    c0 = (neg_z & x_gt_y).unsqueeze(-1).to(R.dtype)
-    c1 = (neg_z & ~x_gt_y).unsqueeze(-1).to(R.dtype)
-    c2 = (~neg_z & x_lt_ny).unsqueeze(-1).to(R.dtype)
-    c3 = (~neg_z & ~x_lt_ny).unsqueeze(-1).to(R.dtype)
-    q = q0 * c0 + q1 * c1 + q2 * c2 + q3 * c3
-    t = t0.unsqueeze(-1) * c0 + t1.unsqueeze(-1) * c1 + t2.unsqueeze(-1) * c2 + t3.unsqueeze(-1) * c3
-    q = 0.5 * q / torch.sqrt(t)
-    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-    s2 = x * x + y * y + z * z
-    s = torch.sqrt(s2)
-    two_theta = 2.0 * torch.where(w < 0.0, torch.atan2(-s, -w), torch.atan2(s, w))
-    k = torch.where(s2 > 0.0, two_theta / s, torch.full_like(s, 2.0))
-    aa = torch.stack([x * k, y * k, z * k], -1)
-    return torch.where(torch.isnan(aa), torch.zeros_like(aa), aa)
+class _Project(torch.autograd.Function):
+    """kp_2d = weak-perspective projection of kp_3d (or of zero joints) by cam, reference lib/models/spin.py:113-157."""
 
+    @staticmethod
+    def forward(ctx, kp3d, cam, n_joints):
+        cam = cam.contiguous().float()
+        if not cam.is_cuda:
+            raise RuntimeError("maed_b200 geometry tail runs on CUDA only; got a %s tensor — there is no CPU fallback" % cam.device)
+        kp3d = kp3d.contiguous().float() if kp3d is not None else None
+        R = cam.shape[0]
+        kp2d = torch.empty(R, n_joints, 2, dtype=torch.float32, device=cam.device)
+        with torch.cuda.device(cam.device):
+            _lib.call("maed_project_keypoints", _lib.ptr(kp3d), _lib.ptr(cam), R, n_joints, _lib.ptr(kp2d), None, None, None,
+                      _lib.stream_ptr())
+        ctx.save_for_backward(cam) if kp3d is None else ctx.save_for_backward(cam, kp3d)
+        ctx.n_joints = n_joints
+        return kp2d
 
-def project_keypoints(joints, cam):
-    """reference lib/models/spin.py:113-157: weak-perspective camera -> translation, focal 5000, normalised by 112."""
-    t = torch.stack([cam[:, 1], cam[:, 2], 2 * 5000.0 / (224.0 * cam[:, 0] + 1e-9)], dim=-1)
-    pts = joints + t.unsqueeze(1)
-    pts = pts / pts[:, :, -1:]
-    return 5000.0 * pts[:, :, :2] / 112.0
+    @staticmethod
+    def backward(ctx, d_kp2d):
+        saved = ctx.saved_tensors
+        cam, kp3d = saved[0], (saved[1] if len(saved) > 1 else None)
+        R = cam.shape[0]
+        d_kp2d = d_kp2d.contiguous().float()
+        d_cam = torch.empty_like(cam)
+        d_kp3d = torch.empty_like(kp3d) if kp3d is not None and ctx.needs_input_grad[0] else None
+        with torch.cuda.device(cam.device):
+            _lib.call("maed_project_keypoints", _lib.ptr(kp3d), _lib.ptr(cam), R, ctx.n_joints, None, _lib.ptr(d_kp2d),
+                      _lib.ptr(d_cam), _lib.ptr(d_kp3d), _lib.stream_ptr())
+        return d_kp3d, d_cam, None
 
 
 def smpl_forward_torch(betas, rotmats, head, J_regressor=None):
@@ -110,14 +128,14 @@ def smpl_forward_torch(betas, rotmats, head, J_regressor=None):
 def decode_outputs(pose6d, shape, cam, n_joints=49, smpl_head=None, J_regressor=None):
     """reference lib/models/ktd.py:94-124.  Without a body model (see SMPLHead) verts / joints are zeros."""
     nt = pose6d.shape[0]
-    rot = rot6d_to_rotmat(pose6d).reshape(nt, 24, 3, 3)
+    theta, rot = _PoseTail.apply(pose6d, shape, cam)
     if smpl_head is not None and smpl_head.has_assets:
         verts, kp3d = smpl_forward_torch(shape, rot, smpl_head, J_regressor)
+        kp2d = _Project.apply(kp3d, cam, kp3d.shape[1])
     else:
         verts, kp3d = pose6d.new_zeros(nt, 6890, 3), pose6d.new_zeros(nt, n_joints, 3)
-    aa = rotmat_to_angle_axis(rot.reshape(-1, 3, 3)).reshape(nt, 72)
-    return {"theta": torch.cat([cam, aa, shape], dim=1), "verts": verts, "kp_2d": project_keypoints(kp3d, cam), "kp_3d": kp3d,
-            "rotmat": rot}
+        kp2d = _Project.apply(None, cam, n_joints)
+    return {"theta": theta, "verts": verts, "kp_2d": kp2d, "kp_3d": kp3d, "rotmat": rot}
 
 
 # --------------------------------------------------------------------------------------------- engine state

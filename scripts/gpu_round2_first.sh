@@ -8,6 +8,7 @@ echo "=== backward kernels"; timeout 900 python -m pytest -q -m gpu --timeout 30
 grep -E "passed|failed|^FAILED|^ERROR" gpurun_out/bwd_ops.log | tail -n 45
 echo "=== SMPL tier"; timeout 600 python -m pytest -q -m gpu --timeout 300 tests/test_smpl.py > gpurun_out/smpl.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/smpl.log
 echo "=== 'cnn' encoder"; timeout 600 python -m pytest -q -m gpu --timeout 300 -s tests/test_cnn.py > gpurun_out/cnn.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/cnn.log
+echo "=== geometry tail"; timeout 300 python -m pytest -q -m gpu --timeout 120 tests/test_geometry_tail.py > gpurun_out/geometry.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/geometry.log
 echo "=== fused loss"; timeout 300 python -m pytest -q -m gpu --timeout 120 tests/test_loss.py > gpurun_out/loss.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/loss.log
 echo "=== training path"; timeout 1200 python -m pytest -q -m gpu --timeout 600 -s tests/test_train.py > gpurun_out/train.log 2>&1; echo "exit $?"
 grep -E "passed|failed|^FAILED|^ERROR|worst" gpurun_out/train.log | tail -n 30

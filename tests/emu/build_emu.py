@@ -21,7 +21,7 @@ LIB = os.path.join(OUT, "libmaed_emu.so")
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
 # compiled from the real sources through the shim
-CU_SOURCES = ["kernels.cu", "decoder.cu", "bwd_kernels.cu", "bwd_kernels2.cu", "attention_bwd.cu", "smpl.cu", "loss.cu",
+CU_SOURCES = ["kernels.cu", "decoder.cu", "bwd_kernels.cu", "bwd_kernels2.cu", "attention_bwd.cu", "smpl.cu", "loss.cu", "decode_bwd.cu",
               "cnn_kernels.cu", "cnn_engine.cu", "engine.cu", "train.cu", "capi.cu"]
 # tensor-core / TMA translation units replaced by tc_stubs.cpp
 REPLACED = ["gemm_host.cu", "gemm_gn_sm100.cu", "stem_sm100.cu", "attention.cu", "gemm_splitk_sm100.cu"]

@@ -2,7 +2,7 @@
 CTA-pair GEMM).
 
 Their GPU tests (the ``cuda`` parametrisations of tests/test_bwd_ops.py, tests/test_smpl.py, tests/test_cnn.py,
-tests/test_loss.py, tests/test_train.py, tests/test_gemm_pair.py) stay behind MAED_B200_TRAIN_TESTS=1 so that a first-contact
+tests/test_loss.py, tests/test_geometry_tail.py, tests/test_train.py, tests/test_gemm_pair.py) stay behind MAED_B200_TRAIN_TESTS=1 so that a first-contact
 failure cannot turn the validated suite red or poison its CUDA context.  This file runs them ONCE, last (file name), each test
 file in its OWN subprocess (a trap or an illegal address in one kernel leaves a sticky error in that process only) with a hard
 time limit per file and overall:
@@ -22,7 +22,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # most certain first; the CTA-pair GEMM (never run, hand-written cluster protocol) last
-FILES = ["test_loss.py", "test_cnn.py", "test_smpl.py", "test_bwd_ops.py", "test_train.py", "test_gemm_pair.py"]
+FILES = ["test_loss.py", "test_geometry_tail.py", "test_cnn.py", "test_smpl.py", "test_bwd_ops.py", "test_train.py", "test_gemm_pair.py"]
 TOTAL_BUDGET_S, PER_FILE_S, PER_TEST_S = 480, 200, 90
 
 
