@@ -179,21 +179,23 @@ class TrainState:
             _lib.call("maed_train_set_exchange", model._engine, _lib.EXCHANGE_FN(0), None, None, 0)
             self._exchange = None
 
-    def ensure_grads(self, tensors):
-        """(Re)allocates the flat gradient buffer (engine parameter order, every tensor padded to 4 elements) and
-        returns FRESH views of it: autograd's AccumulateGrad adopts a gradient tensor nobody else references instead
-        of cloning it, so ``p.grad`` aliases the flat buffer (one all-reduce / one Adam launch covers everything)."""
+    def ensure_grads(self, tensors, is_param=None):
+        """(Re)allocates the flat gradient buffer (engine table order, every PARAMETER padded to 4 elements; buffers of the
+        table — the BatchNorm running statistics of encoder='cnn' — get no slot and a NULL pointer) and returns FRESH views of
+        it (None for buffers): autograd's AccumulateGrad adopts a gradient tensor nobody else references instead of cloning
+        it, so ``p.grad`` aliases the flat buffer (one all-reduce / one Adam launch covers everything)."""
         dev = tensors[0].device
-        total = sum((t.numel() + 3) // 4 * 4 for t in tensors)
+        is_param = is_param if is_param is not None else [True] * len(tensors)
+        total = sum((t.numel() + 3) // 4 * 4 for t, p in zip(tensors, is_param) if p)
         if self.flat_grad is None or self.flat_grad.numel() != total or self.flat_grad.device != dev:
             self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
             self.grad_offsets, off = [], 0
-            for t in tensors:
-                self.grad_offsets.append(off)
-                off += (t.numel() + 3) // 4 * 4
+            for t, p in zip(tensors, is_param):
+                self.grad_offsets.append(off if p else None)
+                off += (t.numel() + 3) // 4 * 4 if p else 0
             base = self.flat_grad.data_ptr()
-            self.grad_ptrs = (C.c_void_p * len(tensors))(*[base + 4 * o for o in self.grad_offsets])
-        return [self.flat_grad[o:o + t.numel()].view(t.shape) for o, t in zip(self.grad_offsets, tensors)]
+            self.grad_ptrs = (C.c_void_p * len(tensors))(*[None if o is None else base + 4 * o for o in self.grad_offsets])
+        return [None if o is None else self.flat_grad[o:o + t.numel()].view(t.shape) for o, t in zip(self.grad_offsets, tensors)]
 
     def ensure_tpack(self, eng, params_arr, key, dev):
         lib = _lib.load()
@@ -250,7 +252,8 @@ class MaedTrainFunction(torch.autograd.Function):
         N, T = x.shape[:2]
         dev = x.device
         tensors = model._tensor_table()
-        views = st.ensure_grads(tensors)
+        param_names = {n for n, _ in model._train_param_order}
+        views = st.ensure_grads(tensors, [n in param_names for n in model._param_names])
         z = lambda g, n: (torch.zeros(N * T, n, dtype=torch.float32, device=dev) if g is None  # noqa: E731
                           else g.contiguous().float())
         d_pose, d_shape, d_cam = z(d_pose, 144), z(d_shape, 10), z(d_cam, 3)
@@ -319,12 +322,10 @@ class FusedAdam(torch.optim.Optimizer):
         TrainState.flat_grad) and builds the single-launch optimiser."""
         model._get_engine()
         tensors = model._tensor_table()
+        # parameters only, in engine table order: the table of encoder='cnn' interleaves BatchNorm running buffers with the
+        # parameters, and Adam (weight decay!) must not touch those — same filter as TrainState.ensure_grads
         param_names = {n for n, _ in model.named_parameters()}
-        if any(n not in param_names for n in model._param_names):
-            # the engine table of encoder='cnn' interleaves BatchNorm running buffers with the parameters: they must not be
-            # touched by Adam (weight decay!), so no flat single-launch layout — one launch per parameter tensor
-            return cls([{"params": p, "name": n} for n, p in model.named_parameters()], lr=lr, betas=betas, eps=eps,
-                       weight_decay=weight_decay, model=model)
+        tensors = [t for t, n in zip(tensors, model._param_names) if n in param_names]
         total = sum((t.numel() + 3) // 4 * 4 for t in tensors)
         flat = torch.zeros(total, dtype=torch.float32, device=tensors[0].device)
         off = 0

@@ -183,7 +183,7 @@ def test_product_training_step_on_the_emulator(harness):
         m = _product_training_step("cpu")
         from maed_b200.train import FusedAdam
         opt = FusedAdam.for_model(m, lr=1e-3, weight_decay=1e-2)
-        assert opt._flat is None                                             # running buffers must stay out of Adam's reach
+        assert opt._flat is not None and opt._flat["p"].numel() == m._train_state.flat_grad.numel()   # one launch, parameters only
         before = {n: b.clone() for n, b in m.named_buffers()}
         w0 = m.encoder.conv1.weight.detach().clone()
         opt.step()
