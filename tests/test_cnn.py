@@ -89,6 +89,15 @@ def test_emulated_engine_matches_reference_golden(harness, name):
         assert rel_err(synth.tap_digest(nchw)[0], g["dig_%s_sub" % ref]) < 1e-4, mine
 
 
+def test_emulated_engine_fp16_fast_mode(harness):
+    """precision='fp16' (single MMA, hi planes only): the lo planes of the workspace stay unwritten (NaN-poisoned by the
+    harness) and must never be read — residual planes included."""
+    g, meta = load_golden("cnn_ktd")
+    em = harness.EmuModel(build_model(meta, precision="fp16"))
+    o = em.forward(synth.synth_frames(meta["N"], meta["T"], meta["seed"]))
+    assert not torch.isnan(o["feat"]).any() and rel_err(o["feat"], g["tap_feat"]) < 2e-3
+
+
 # ------------------------------------------------------------------------------------------------ training path
 GRADS = "grads_cnn_ktd"        # reference in train() mode (BatchNorm on batch statistics), dropout modules in eval mode
 GRADS_ITER = "grads_cnn_iterative"   # same with the iterative regressor (spin.py:51-74), 3 images

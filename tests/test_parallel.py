@@ -112,3 +112,78 @@ def test_allreduce_gradients_two_ranks_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(r[1] and r[2] for r in res), res
+
+
+# ------------------------------------------------------------- torch DistributedDataParallel around the product module
+def _ddp_worker(rank, world, port, q):
+    """reference train.py:113: DistributedDataParallel(model, broadcast_buffers=False) around the model in train() mode; the
+    engine's single autograd node must feed DDP's per-parameter hooks (every parameter gets a gradient) and the averaged
+    gradients must land in the engine's flat gradient buffer."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "emu"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.setdefault("MAED_EMU_THREADS", "4")
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import harness
+        from maed_b200.models import MAED
+        from oracle import synth
+        with harness.product_on_cpu():
+            m = MAED("ste", 1, 12, "vanilla", "ktd", 1024)
+            synth.fill_module_(m, 21)
+            m = m.train().enable_training(True, dropout_p=0.0)
+            ddp = torch.nn.parallel.DistributedDataParallel(m, broadcast_buffers=False)
+            x = synth.synth_frames(world, 1, 21)[rank:rank + 1]
+            A, B, C_ = [synth.synth_tensor("grad_probe.%s" % k, (world, n), 21) for k, n in (("pose", 144), ("shape", 10), ("cam", 3))]
+            d = ddp(x)["_debug"]
+            ((d["pose6d"] * A[rank:rank + 1]).sum() + (d["shape"] * B[rank:rank + 1]).sum() + (d["cam"] * C_[rank:rank + 1]).sum()).backward()
+            st = m._train_state
+            ok_all = all(p.grad is not None for p in m.parameters())
+            in_flat = all(st.flat_grad.data_ptr() <= p.grad.data_ptr() < st.flat_grad.data_ptr() + 4 * st.flat_grad.numel()
+                          for p in m.parameters())
+            picks = ["encoder.patch_embed.backbone.stem.conv.weight", "encoder.blocks.0.attn.qkv.weight", "decoder.fc2.bias",
+                     "encoder.pos_embed"]
+            named = dict(m.named_parameters())
+            q.put((rank, ok_all, in_flat, {k: named[k].grad.detach().numpy().copy() for k in picks}, None))   # numpy: pickled by value
+    except Exception as e:                                                        # noqa: BLE001
+        import traceback
+        q.put((rank, False, False, {}, traceback.format_exc()[-2500:] + repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_torch_ddp_wraps_the_training_module_two_ranks_gloo():
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "emu"))
+    import harness
+    from maed_b200.models import MAED
+    from oracle import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    # meanwhile: the same two frames in ONE process -> sum of the per-frame gradients = 2 x DDP's average
+    with harness.product_on_cpu():
+        m = MAED("ste", 1, 12, "vanilla", "ktd", 1024)
+        synth.fill_module_(m, 21)
+        m = m.train().enable_training(True, dropout_p=0.0)
+        A, B, C_ = [synth.synth_tensor("grad_probe.%s" % k, (2, n), 21) for k, n in (("pose", 144), ("shape", 10), ("cam", 3))]
+        d = m(synth.synth_frames(2, 1, 21))["_debug"]
+        ((d["pose6d"] * A).sum() + (d["shape"] * B).sum() + (d["cam"] * C_).sum()).backward()
+        ref = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok_all, in_flat, grads, err in res:
+        assert err is None, "rank %d: %s" % (rank, err)
+        assert ok_all and in_flat, (rank, ok_all, in_flat)
+        for k, g in grads.items():
+            e = ((2.0 * torch.from_numpy(g) - ref[k]).norm() / ref[k].norm()).item()
+            assert e < 2e-3, (rank, k, e)
+    for k in res[0][3]:
+        assert (res[0][3][k] == res[1][3][k]).all(), k                    # both ranks hold the same averaged gradient
