@@ -62,7 +62,12 @@ def test_joint_selection_and_regressor_override():
 
 
 def test_training_tail_body_model_matches_oracle_and_is_differentiable():
-    """maed_b200.train.smpl_forward_torch (the autograd tail of the training path) against the oracle restatement."""
+    """maed_b200.train.smpl_forward_torch (the autograd tail of the training path) against the oracle restatement; the
+    geometry nodes around it (csrc/decode_bwd.cu) run on the CUDA-on-CPU test build."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+    import harness
     from maed_b200 import train
     from maed_b200.models.modules import SMPLHead
     a = S.synthetic_assets(4)
@@ -70,11 +75,12 @@ def test_training_tail_body_model_matches_oracle_and_is_differentiable():
     betas = (0.4 * torch.randn(3, 10)).requires_grad_(True)
     pose6d = torch.randn(3, 144, requires_grad=True)
     cam = torch.tensor([[0.9, 0.1, -0.1]]).repeat(3, 1)
-    out = train.decode_outputs(pose6d, betas, cam, 49, head)
-    v_ref, j_ref = S.smpl_forward(betas.detach().double(), out["rotmat"].detach().double(),
-                                  {k: (v.double() if v.dtype.is_floating_point else v) for k, v in a.items()})
-    assert (out["verts"].double() - v_ref).abs().max() < 1e-5 and (out["kp_3d"].double() - j_ref).abs().max() < 1e-5
-    (out["kp_2d"].square().sum() + out["kp_3d"].sum()).backward()
-    assert pose6d.grad is not None and betas.grad is not None and torch.isfinite(pose6d.grad).all() and pose6d.grad.abs().sum() > 0
-    out17 = train.decode_outputs(pose6d, betas, cam, 17, head, a["J_regressor_h36m"])
-    assert out17["kp_3d"].shape == (3, 17, 3)
+    with harness.product_on_cpu():
+        out = train.decode_outputs(pose6d, betas, cam, 49, head)
+        v_ref, j_ref = S.smpl_forward(betas.detach().double(), out["rotmat"].detach().double(),
+                                      {k: (v.double() if v.dtype.is_floating_point else v) for k, v in a.items()})
+        assert (out["verts"].double() - v_ref).abs().max() < 1e-5 and (out["kp_3d"].double() - j_ref).abs().max() < 1e-5
+        (out["kp_2d"].square().sum() + out["kp_3d"].sum()).backward()
+        assert pose6d.grad is not None and betas.grad is not None and torch.isfinite(pose6d.grad).all() and pose6d.grad.abs().sum() > 0
+        out17 = train.decode_outputs(pose6d, betas, cam, 17, head, a["J_regressor_h36m"])
+        assert out17["kp_3d"].shape == (3, 17, 3)
