@@ -152,7 +152,7 @@ int maed_engine_forward(const maed_engine* e, const void* const* params, const v
  * Training path (maed_b200/csrc/train.cu): forward with a saved-activation tape + backward to every parameter.
  * Replaces `loss.backward()` through lib/models/maed.py:52-66 (reference lib/core/trainer.py:238-255); the boundary
  * is the decoder output pose6d / shape / cam (the geometry tail behind it stays under autograd).
- * Supported: encoder 'ste' with st_mode parallel / series / vanilla, encoder 'cnn' (BatchNorm on batch statistics, optional
+ * Supported: encoder 'ste' with st_mode parallel / series / vanilla / temporal, encoder 'cnn' (BatchNorm on batch statistics, optional
  * SyncBatchNorm exchange), both decoders (KTD, iterative regressor), split precision.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct maed_train_outputs {

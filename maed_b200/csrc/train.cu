@@ -404,8 +404,9 @@ size_t train_workspace_bytes(const Engine* e, int BT) {
 
 static int check_train_cfg(const Engine& e) {
   const int m = e.cfg.mode;
-  MAED_CHECK_ARG(e.cfg.encoder == ENC_CNN || m == MODE_PARALLEL || m == MODE_SERIES || m == MODE_VANILLA,
-                 "training supports st_mode parallel / series / vanilla (got mode %d)", m);
+  MAED_CHECK_ARG(e.cfg.encoder == ENC_CNN || m == MODE_PARALLEL || m == MODE_SERIES || m == MODE_VANILLA || m == MODE_TEMPORAL,
+                 "training supports st_mode parallel / series / vanilla / temporal (got mode %d: the joint 'coupling' attention "
+                 "has no backward yet)", m);
   MAED_CHECK_ARG(e.cfg.nsplit == 3, "training runs in split precision (precision='split')");
   return MAED_OK;
 }
@@ -632,6 +633,20 @@ int train_forward(const Engine* ep, const void* const* params, const void* packe
     const Engine::SteOff& of = e.blk_off[i];
     SteTape& t = w.ste[i];
     float* x_out = (i + 1 < cf.num_blocks) ? w.ste[i + 1].x_in : w.x_final;
+    if (cf.mode == MODE_TEMPORAL) {
+      // vision_transformer.py:167-173: token mean of LN1(x) -> qkv -> attention across the T frames -> proj, broadcast over
+      // the tokens.  Tape: pooled[:, :C] = the token mean, qkv / ao planes of BT rows, logits[:, :C] = proj output.
+      MAED_PROPAGATE(layernorm_f32(t.x_in, C, c.P(ix.n1), c.P(ix.n1 + 1), rows, C, 1e-6f, w.dxs, st));
+      MAED_PROPAGATE(token_mean(w.dxs, BT, ntok, C, t.pooled, C, 0, st));
+      MAED_PROPAGATE(split_f32(t.pooled, w.small_p, w.small_plane, (long long)BT * C, st));
+      MAED_PROPAGATE(gemm_plain(c, w.small_p, w.small_plane, BT, C, c.H(of.qkv), 3 * CC, 3 * C, c.P(ix.qkv_b), ACT_NONE, nullptr,
+                                OUT_F16_SPLIT, t.qkv, w.qkv_plane));
+      MAED_PROPAGATE(attn_temporal(t.qkv, w.qkv_plane, N, T, 1, heads, scale, nullptr, t.ao, w.ln_plane, st));
+      MAED_PROPAGATE(gemm_plain(c, t.ao, w.ln_plane, BT, C, c.H(of.proj), CC, C, c.P(ix.proj_b), ACT_NONE, nullptr, OUT_F32,
+                                t.logits, 0));
+      MAED_CUDA_CHECK(cudaMemcpyAsync(t.x_mid, t.x_in, (size_t)rows * C * 4, cudaMemcpyDeviceToDevice, st));
+      MAED_PROPAGATE(broadcast_add(t.x_mid, t.logits, BT, ntok, C, st));
+    } else {
     MAED_PROPAGATE(layernorm_planes(t.x_in, C, c.P(ix.n1), c.P(ix.n1 + 1), rows, C, 1e-6f, t.ln1, w.ln_plane, st));
     MAED_PROPAGATE(gemm_plain(c, t.ln1, w.ln_plane, rows, C, c.H(of.qkv), 3 * CC, 3 * C, c.P(ix.qkv_b), ACT_NONE, nullptr,
                               OUT_F16_SPLIT, t.qkv, w.qkv_plane));
@@ -654,6 +669,7 @@ int train_forward(const Engine* ep, const void* const* params, const void* packe
     }
     MAED_PROPAGATE(gemm_plain(c, t.ao, w.ln_plane, rows, C, c.H(of.proj), CC, C, c.P(ix.proj_b), ACT_NONE, t.x_in, OUT_F32,
                               t.x_mid, 0));
+    }
     MAED_PROPAGATE(layernorm_planes(t.x_mid, C, c.P(ix.n2), c.P(ix.n2 + 1), rows, C, 1e-6f, t.ln2, w.ln_plane, st));
     MAED_PROPAGATE(gemm_plain(c, t.ln2, w.ln_plane, rows, C, c.H(of.fc1), 4 * CC, 4 * C, c.P(ix.fc1_b), ACT_NONE, nullptr,
                               OUT_F32, t.h_pre, 0));
@@ -974,6 +990,25 @@ int train_backward(const Engine* ep, const void* const* params, const void* pack
     MAED_PROPAGATE(layernorm_bwd(dx2, C, t.x_mid, C, c.P(ix.n2), rows, C, 1e-6f, dx, dx, C, w.ln_partial, st));   // dx = d_xmid
     MAED_PROPAGATE(colsum_f32(w.ln_partial, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.n2), st));
     MAED_PROPAGATE(colsum_f32(w.ln_partial + C, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.n2 + 1), st));
+    if (cf.mode == MODE_TEMPORAL) {
+      // x_mid[bt, i] = x_in[bt, i] + v[bt],  v = proj(attn_T(qkv(mean_i LN1(x_in))))   — all BT-row problems, fp32 CUDA cores
+      float* d_v = sm[0]; float* ao32 = sm[1]; float* d_ao = sm[2]; float* d_mean = sm[3]; float* dqkv_t = w.big;   // [BT, 3C]
+      MAED_PROPAGATE(token_sum(dx, BT, ntok, C, d_v, st));
+      MAED_PROPAGATE(planes_to_f32(t.ao, w.ln_plane, (long long)BT * C, ao32, st));
+      MAED_PROPAGATE(sgemm_f32(1, 0, C, C, BT, c.inv_ls, d_v, C, ao32, C, 0.f, c.G(ix.proj_w), C, st));
+      MAED_PROPAGATE(colsum_f32(d_v, C, BT, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.proj_b), st));
+      MAED_PROPAGATE(sgemm_f32(0, 0, BT, C, C, 1.f, d_v, C, c.P(ix.proj_w), C, 0.f, d_ao, C, st));
+      MAED_PROPAGATE(attn_temporal_bwd(t.qkv, w.qkv_plane, d_ao, N, T, 1, heads, scale, 0, dqkv_t, st));
+      MAED_PROPAGATE(sgemm_f32(1, 0, 3 * C, C, BT, c.inv_ls, dqkv_t, 3 * C, t.pooled, C, 0.f, c.G(ix.qkv_w), C, st));
+      MAED_PROPAGATE(colsum_f32(dqkv_t, 3 * C, BT, 3 * C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.qkv_b), st));
+      MAED_PROPAGATE(sgemm_f32(0, 0, BT, C, 3 * C, 1.f / (float)ntok, dqkv_t, 3 * C, c.P(ix.qkv_w), C, 0.f, d_mean, C, st));
+      MAED_CUDA_CHECK(cudaMemsetAsync(dx2, 0, (size_t)rows * C * 4, st));
+      MAED_PROPAGATE(broadcast_add(dx2, d_mean, BT, ntok, C, st));                                           // d LN1 output
+      MAED_PROPAGATE(layernorm_bwd(dx2, C, t.x_in, C, c.P(ix.n1), rows, C, 1e-6f, dx, dx, C, w.ln_partial, st));
+      MAED_PROPAGATE(colsum_f32(w.ln_partial, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.n1), st));
+      MAED_PROPAGATE(colsum_f32(w.ln_partial + C, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.n1 + 1), st));
+      continue;
+    }
     // ---- attention: x_mid = x_in + proj(ao)
     MAED_PROPAGATE(split_f32(dx, w.pl_a, w.pl_a_plane, (long long)rows * C, st));
     MAED_PROPAGATE(colsum_f32(dx, C, rows, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.proj_b), st));

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 
-_TRAIN_MODES = ("parallel", "series", "vanilla")
+_TRAIN_MODES = ("parallel", "series", "vanilla", "temporal")
 
 
 # ----------------------------------------------------------------------------------------------- geometry tail

@@ -32,6 +32,7 @@ CASES = {
     # iterative regressor (spin.py:51-74): three passes through the same fc1 / fc2 / heads, state fed back into fc1
     "grads_vanilla_iterative": ("vanilla", "iterative", 1, 2, 15),
     "grads_cnn_iterative": ("vanilla", "iterative", 3, 1, 16, "cnn"),
+    "grads_temporal_ktd": ("temporal", "ktd", 1, 3, 17),          # token mean -> attention across frames only
 }
 NSAMP = 8
 
