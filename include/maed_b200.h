@@ -152,7 +152,7 @@ int maed_engine_forward(const maed_engine* e, const void* const* params, const v
  * Training path (maed_b200/csrc/train.cu): forward with a saved-activation tape + backward to every parameter.
  * Replaces `loss.backward()` through lib/models/maed.py:52-66 (reference lib/core/trainer.py:238-255); the boundary
  * is the decoder output pose6d / shape / cam (the geometry tail behind it stays under autograd).
- * Supported: encoder 'ste' with st_mode parallel / series / vanilla / temporal, encoder 'cnn' (BatchNorm on batch statistics, optional
+ * Supported: encoder 'ste' with all five st_modes, encoder 'cnn' (BatchNorm on batch statistics, optional
  * SyncBatchNorm exchange), both decoders (KTD, iterative regressor), split precision.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct maed_train_outputs {
@@ -214,8 +214,10 @@ int maed_bwd_sgemm(int transA, int transB, int M, int N, int K, float alpha, con
                    float beta, float* C, int ldc, void* stream);
 int maed_bwd_ktd_tree(const float* d_pose6d, const float* d_shape, const float* d_cam, const float* w_anc, const float* pose6d,
                       int R, float scale, float* g_total, float* d_base, int ld, float* d_w_anc, void* stream);
+/* kind: 0 spatial (per frame), 1 temporal (per token across the T frames), 2 coupling (all T * ntok tokens of a clip; needs
+ * scratch of B * heads * T * ntok * 3 floats, NULL otherwise) */
 int maed_bwd_attention(int kind, const void* qkv_hi, long long qkv_plane, const float* d_out, int B, int T, int ntok, int heads,
-                       float scale, int accumulate, float* d_qkv, void* stream);
+                       float scale, int accumulate, float* d_qkv, float* scratch, void* stream);
 size_t maed_bwd_wgrad_slab_floats(int Mo, int No, int R);
 int maed_bwd_wgrad_splitk(const void* A, long long a_plane, int lda, const void* B, long long b_plane, int ldb, int Mo, int No,
                           int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, void* stream);

@@ -105,7 +105,7 @@ SIGNATURES = {
     "maed_bwd_blend": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "maed_bwd_sgemm": (_I, [_I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P]),
     "maed_bwd_ktd_tree": (_I, [_P, _P, _P, _P, _P, _I, _F, _P, _P, _I, _P, _P]),
-    "maed_bwd_attention": (_I, [_I, _P, _L, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
+    "maed_bwd_attention": (_I, [_I, _P, _L, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
     "maed_bwd_wgrad_slab_floats": (_Z, [_I, _I, _I]),
     "maed_bwd_wgrad_splitk": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _F, _I, _P, _P, _I, _P]),
     "maed_bwd_split_transposed": (_I, [_P, _I, _I, _P, _L, _P]),

@@ -305,4 +305,161 @@ int attn_temporal_bwd(const __half* qkv_hi, long long qkv_plane, const float* d_
   return MAED_OK;
 }
 
+// ======================================================================================== generic (coupling mode)
+// Attention over `seq` contiguous rows per batch element (reference vision_transformer.py:180-204: the T * 197 tokens of a
+// clip attend to each other).  CUDA-core fp32, flash-style recomputation, deterministic, slow (an ablation mode of the
+// reference: 16x the attention work of the other modes): two kernels, one warp per query row / per key row.
+//   kernel 1 (query i): m_i, l_i (softmax statistics), D_i = dO_i . O_i, dQ_i = sum_j dS_ij K_j; keeps (m, l, D) for kernel 2
+//   kernel 2 (key j):   dK_j = sum_i dS_ij Q_i,  dV_j = sum_i P_ij dO_i          with dS = scale * P o (dO V^T - D)
+static constexpr int kGenWarps = 4;
+
+__device__ __forceinline__ void load_row64(const __half* p, long long plane, float* dst) {
+#pragma unroll
+  for (int d4 = 0; d4 < kHd; d4 += 4) {
+    const float4 v = plane ? load_planes4(p + d4, plane)
+                           : make_float4(__half2float(p[d4]), __half2float(p[d4 + 1]), __half2float(p[d4 + 2]), __half2float(p[d4 + 3]));
+    dst[d4] = v.x; dst[d4 + 1] = v.y; dst[d4 + 2] = v.z; dst[d4 + 3] = v.w;
+  }
+}
+__device__ __forceinline__ float dot_row64(const __half* p, long long plane, const float* s) {
+  float a = 0.f;
+#pragma unroll
+  for (int d4 = 0; d4 < kHd; d4 += 4) {
+    const float4 v = plane ? load_planes4(p + d4, plane)
+                           : make_float4(__half2float(p[d4]), __half2float(p[d4 + 1]), __half2float(p[d4 + 2]), __half2float(p[d4 + 3]));
+    a += v.x * s[d4] + v.y * s[d4 + 1] + v.z * s[d4 + 2] + v.w * s[d4 + 3];
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(kGenWarps * 32)
+attn_generic_bwd_q_kernel(const __half* __restrict__ qkv, long long plane, const float* __restrict__ d_out, int seq, int heads,
+                          float scale, int accumulate, float* __restrict__ d_qkv, float* __restrict__ stats) {
+  __shared__ float sq[kGenWarps][kHd], sg[kGenWarps][kHd], so[kGenWarps][kHd];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kGenWarps + warp;
+  const int h = blockIdx.y, b = blockIdx.z;
+  if (i >= seq) return;                                    // whole warp leaves together (no block barriers below)
+  const int ld = 3 * heads * kHd, ldo = heads * kHd;
+  const long long row0 = (long long)b * seq;
+  if (lane == 0) {
+    load_row64(qkv + (row0 + i) * ld + h * kHd, plane, sq[warp]);
+    for (int d = 0; d < kHd; ++d) sg[warp][d] = d_out[(row0 + i) * ldo + h * kHd + d];
+  }
+  __syncwarp();
+  const float* q = sq[warp];
+  const float* g = sg[warp];
+  // pass A: row maximum
+  float mx = -INFINITY;
+  for (int j = lane; j < seq; j += 32) mx = fmaxf(mx, scale * dot_row64(qkv + (row0 + j) * ld + heads * kHd + h * kHd, plane, q));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  // pass B: l = sum exp, o = sum exp * V   (per-lane partials, then a fixed-order warp reduction)
+  float l = 0.f, acc[kHd];
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) acc[d] = 0.f;
+  for (int j = lane; j < seq; j += 32) {
+    const float e = expf(scale * dot_row64(qkv + (row0 + j) * ld + heads * kHd + h * kHd, plane, q) - mx);
+    l += e;
+    float v[kHd];
+    load_row64(qkv + (row0 + j) * ld + 2 * heads * kHd + h * kHd, plane, v);
+#pragma unroll
+    for (int d = 0; d < kHd; ++d) acc[d] += e * v[d];
+  }
+  l = warp_sum(l);
+  float D = 0.f;
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) D += warp_sum(acc[d]) * g[d];
+  D /= l;
+  if (lane == 0) {
+    float* st = stats + ((long long)(b * heads + h) * seq + i) * 3;
+    st[0] = mx; st[1] = l; st[2] = D;
+  }
+  // pass C: dQ_i = sum_j scale * P_ij (dO_i . V_j - D) K_j
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) acc[d] = 0.f;
+  const float inv_l = 1.0f / l;
+  for (int j = lane; j < seq; j += 32) {
+    float k[kHd];
+    load_row64(qkv + (row0 + j) * ld + heads * kHd + h * kHd, plane, k);
+    float sdot = 0.f;
+#pragma unroll
+    for (int d = 0; d < kHd; ++d) sdot += q[d] * k[d];
+    const float pij = expf(scale * sdot - mx) * inv_l;
+    const float dp = dot_row64(qkv + (row0 + j) * ld + 2 * heads * kHd + h * kHd, plane, g);
+    const float ds = scale * pij * (dp - D);
+#pragma unroll
+    for (int d = 0; d < kHd; ++d) acc[d] += ds * k[d];
+  }
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) {
+    const float t = warp_sum(acc[d]);
+    if (lane == (d & 31)) so[warp][d] = t;
+  }
+  __syncwarp();
+  for (int d = lane; d < kHd; d += 32) {
+    float* o = d_qkv + (row0 + i) * ld + h * kHd + d;
+    *o = (accumulate ? *o : 0.f) + so[warp][d];
+  }
+}
+
+__global__ void __launch_bounds__(kGenWarps * 32)
+attn_generic_bwd_kv_kernel(const __half* __restrict__ qkv, long long plane, const float* __restrict__ d_out, int seq, int heads,
+                           float scale, int accumulate, float* __restrict__ d_qkv, const float* __restrict__ stats) {
+  __shared__ float sk[kGenWarps][kHd], sv[kGenWarps][kHd], so[kGenWarps][2 * kHd];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * kGenWarps + warp;
+  const int h = blockIdx.y, b = blockIdx.z;
+  if (j >= seq) return;
+  const int ld = 3 * heads * kHd, ldo = heads * kHd;
+  const long long row0 = (long long)b * seq;
+  if (lane == 0) {
+    load_row64(qkv + (row0 + j) * ld + heads * kHd + h * kHd, plane, sk[warp]);
+    load_row64(qkv + (row0 + j) * ld + 2 * heads * kHd + h * kHd, plane, sv[warp]);
+  }
+  __syncwarp();
+  const float* k = sk[warp];
+  const float* v = sv[warp];
+  float dk[kHd], dv[kHd];
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+  for (int i = lane; i < seq; i += 32) {
+    const float* st = stats + ((long long)(b * heads + h) * seq + i) * 3;
+    float q[kHd];
+    load_row64(qkv + (row0 + i) * ld + h * kHd, plane, q);
+    const float* g = d_out + (row0 + i) * ldo + h * kHd;
+    float sdot = 0.f, dp = 0.f;
+#pragma unroll
+    for (int d = 0; d < kHd; ++d) { sdot += q[d] * k[d]; dp += g[d] * v[d]; }
+    const float pij = expf(scale * sdot - st[0]) / st[1];
+    const float ds = scale * pij * (dp - st[2]);
+#pragma unroll
+    for (int d = 0; d < kHd; ++d) { dk[d] += ds * q[d]; dv[d] += pij * g[d]; }
+  }
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) {
+    const float a = warp_sum(dk[d]), c = warp_sum(dv[d]);
+    if (lane == (d & 31)) { so[warp][d] = a; so[warp][kHd + d] = c; }
+  }
+  __syncwarp();
+  for (int d = lane; d < kHd; d += 32) {
+    float* ok = d_qkv + (row0 + j) * ld + heads * kHd + h * kHd + d;
+    float* ov = d_qkv + (row0 + j) * ld + 2 * heads * kHd + h * kHd + d;
+    *ok = (accumulate ? *ok : 0.f) + so[warp][d];
+    *ov = (accumulate ? *ov : 0.f) + so[warp][kHd + d];
+  }
+}
+
+// stats: batch * heads * seq * 3 floats of scratch
+int attn_generic_bwd(const __half* qkv_hi, long long qkv_plane, const float* d_out, int batch, int seq, int heads, float scale,
+                     int accumulate, float* d_qkv, float* stats, cudaStream_t st) {
+  MAED_CHECK_ARG(qkv_hi && d_out && d_qkv && stats && batch >= 1 && seq >= 1 && heads >= 1, "attn_generic_bwd: bad argument");
+  const dim3 grid(cdiv(seq, kGenWarps), heads, batch);
+  attn_generic_bwd_q_kernel<<<grid, kGenWarps * 32, 0, st>>>(qkv_hi, qkv_plane, d_out, seq, heads, scale, accumulate, d_qkv, stats);
+  MAED_BW_LAUNCH_CHECK();
+  attn_generic_bwd_kv_kernel<<<grid, kGenWarps * 32, 0, st>>>(qkv_hi, qkv_plane, d_out, seq, heads, scale, accumulate, d_qkv, stats);
+  MAED_BW_LAUNCH_CHECK();
+  return MAED_OK;
+}
+
 }  // namespace maed

@@ -123,6 +123,11 @@ int gemm_wgrad_splitk(const __half* A, long long a_plane, int lda, const __half*
                       int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd,
                       cudaStream_t st);
 
+// generic attention backward over `seq` contiguous rows per batch element ('coupling' mode, vision_transformer.py:180-204);
+// stats: batch * heads * seq * 3 floats of scratch
+int attn_generic_bwd(const __half* qkv_hi, long long qkv_plane, const float* d_out, int batch, int seq, int heads, float scale,
+                     int accumulate, float* d_qkv, float* stats, cudaStream_t st);
+
 // ---- 'cnn' encoder training (cnn_kernels.cu): BatchNorm2d with batch statistics, MaxPool2d(3, 2, 1) with arg-max, pools
 // SyncBatchNorm hook: when `fn` is set, the per-channel sums (2C + 1 doubles: sum, sum of products, row count) are placed in
 // `buf` (device memory owned by the caller) and fn(user, n) must add the first n doubles up over the data-parallel ranks

@@ -283,10 +283,14 @@ int maed_bwd_ktd_tree(const float* d_pose6d, const float* d_shape, const float* 
   return ktd_anc_wgrad(g_total, pose6d, R, scale, d_w_anc, st);
 }
 int maed_bwd_attention(int kind, const void* qkv_hi, long long qkv_plane, const float* d_out, int B, int T, int ntok, int heads,
-                       float scale, int accumulate, float* d_qkv, void* stream) {
+                       float scale, int accumulate, float* d_qkv, float* scratch, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (kind == 0) return attn_spatial_bwd((const __half*)qkv_hi, qkv_plane, d_out, B * T, ntok, heads, scale, accumulate, d_qkv, st);
   if (kind == 1) return attn_temporal_bwd((const __half*)qkv_hi, qkv_plane, d_out, B, T, ntok, heads, scale, accumulate, d_qkv, st);
+  if (kind == 2) {   // 'coupling': joint attention over the T * ntok tokens of a clip; scratch = softmax statistics
+    MAED_CHECK_ARG(scratch, "maed_bwd_attention(kind 2): scratch of B * heads * T * ntok * 3 floats required");
+    return attn_generic_bwd((const __half*)qkv_hi, qkv_plane, d_out, B, T * ntok, heads, scale, accumulate, d_qkv, scratch, st);
+  }
   set_error("maed_bwd_attention: unknown kind %d", kind);
   return MAED_ERR_ARG;
 }

@@ -404,9 +404,7 @@ size_t train_workspace_bytes(const Engine* e, int BT) {
 
 static int check_train_cfg(const Engine& e) {
   const int m = e.cfg.mode;
-  MAED_CHECK_ARG(e.cfg.encoder == ENC_CNN || m == MODE_PARALLEL || m == MODE_SERIES || m == MODE_VANILLA || m == MODE_TEMPORAL,
-                 "training supports st_mode parallel / series / vanilla / temporal (got mode %d: the joint 'coupling' attention "
-                 "has no backward yet)", m);
+  MAED_CHECK_ARG(e.cfg.encoder == ENC_CNN || (m >= MODE_VANILLA && m <= MODE_TEMPORAL), "training: unknown st_mode %d", m);
   MAED_CHECK_ARG(e.cfg.nsplit == 3, "training runs in split precision (precision='split')");
   return MAED_OK;
 }
@@ -664,6 +662,8 @@ int train_forward(const Engine* ep, const void* const* params, const void* packe
       MAED_PROPAGATE(gemm_plain(c, t.ao_s, w.ln_plane, rows, C, c.H(of.qkv), 3 * CC, 3 * C, c.P(ix.qkv_b), ACT_NONE, nullptr,
                                 OUT_F16_SPLIT, t.qkv2, w.qkv_plane));
       MAED_PROPAGATE(attn_temporal(t.qkv2, w.qkv_plane, N, T, ntok, heads, scale, nullptr, t.ao, w.ln_plane, st));
+    } else if (cf.mode == MODE_COUPLING) {                 // joint attention over the T * 197 tokens of a clip
+      MAED_PROPAGATE(attn_generic(t.qkv, w.qkv_plane, N, T * ntok, heads, scale, ntok, T, nullptr, t.ao, w.ln_plane, st));
     } else {
       MAED_PROPAGATE(attn_spatial(t.qkv, w.qkv_plane, BT, ntok, heads, scale, 3, nullptr, t.ao, w.ln_plane, st));
     }
@@ -1034,6 +1034,8 @@ int train_backward(const Engine* ep, const void* const* params, const void* pack
       MAED_PROPAGATE(gemm_plain(c, w.pl_a, w.pl_a_plane, rows, 3 * C, c.TH(tt.qkv), 3 * CC, C, nullptr, ACT_NONE, nullptr, OUT_F32,
                                 w.dxs, 0));                                                               // d_ao_s
       MAED_PROPAGATE(attn_spatial_bwd(t.qkv, w.qkv_plane, w.dxs, BT, ntok, heads, scale, 0, dqkv, st));
+    } else if (cf.mode == MODE_COUPLING) {
+      MAED_PROPAGATE(attn_generic_bwd(t.qkv, w.qkv_plane, d_ao, N, T * ntok, heads, scale, 0, dqkv, w.dxt, st));   // dxt: statistics
     } else {
       MAED_PROPAGATE(attn_spatial_bwd(t.qkv, w.qkv_plane, d_ao, BT, ntok, heads, scale, 0, dqkv, st));
     }

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 
-_TRAIN_MODES = ("parallel", "series", "vanilla", "temporal")
+_TRAIN_MODES = ("parallel", "series", "vanilla", "temporal", "coupling")
 
 
 # ----------------------------------------------------------------------------------------------- geometry tail

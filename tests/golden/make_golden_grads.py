@@ -33,6 +33,7 @@ CASES = {
     "grads_vanilla_iterative": ("vanilla", "iterative", 1, 2, 15),
     "grads_cnn_iterative": ("vanilla", "iterative", 3, 1, 16, "cnn"),
     "grads_temporal_ktd": ("temporal", "ktd", 1, 3, 17),          # token mean -> attention across frames only
+    "grads_coupling_ktd": ("coupling", "ktd", 1, 2, 18),          # joint attention over the T * 197 tokens of the clip
 }
 NSAMP = 8
 

@@ -258,13 +258,18 @@ def _attention_ref(qkv, B, T, ntok, heads, scale, kind):
     if kind == "spatial":
         a = (q @ k.transpose(-2, -1) * scale).softmax(-1)
         return (a @ v).transpose(1, 2).reshape(BT * ntok, heads * 64)
+    if kind == "coupling":                      # all T * ntok tokens of a clip attend to each other
+        rc = lambda t: t.reshape(B, T, heads, ntok, 64).transpose(1, 2).reshape(B, heads, T * ntok, 64)  # noqa: E731
+        a = (rc(q) @ rc(k).transpose(-2, -1) * scale).softmax(-1)
+        return (a @ rc(v)).reshape(B, heads, T, ntok, 64).permute(0, 2, 3, 1, 4).reshape(BT * ntok, heads * 64)
     r = lambda t: t.reshape(B, T, heads, ntok, 64).permute(0, 2, 3, 1, 4)  # noqa: E731
     a = (r(q) @ r(k).transpose(-2, -1) * scale).softmax(-1)
     return (a @ r(v)).permute(0, 3, 2, 1, 4).reshape(BT * ntok, heads * 64)
 
 
 @pytest.mark.parametrize("kind,B,T,ntok", [("spatial", 2, 2, 197), ("spatial", 1, 3, 60), ("temporal", 2, 16, 197),
-                                           ("temporal", 3, 5, 33), ("temporal", 2, 1, 20), ("temporal", 1, 32, 50)])
+                                           ("temporal", 3, 5, 33), ("temporal", 2, 1, 20), ("temporal", 1, 32, 50),
+                                           ("coupling", 2, 3, 37), ("coupling", 1, 2, 197)])
 def test_attention_bwd(L, kind, B, T, ntok):
     _lib, ops = L
     heads = 12
@@ -274,8 +279,9 @@ def test_attention_bwd(L, kind, B, T, ntok):
     qd = _join(p).requires_grad_(True)
     _attention_ref(qd, B, T, ntok, heads, 0.125, kind).backward(d_out.double())
     d_qkv = torch.full_like(qkv, 1.0)
-    _lib.call("maed_bwd_attention", 0 if kind == "spatial" else 1, _lib.ptr(p), C.c_longlong(p[0].numel()), _lib.ptr(d_out), B, T,
-              ntok, heads, C.c_float(0.125), 1, _lib.ptr(d_qkv), _lib.stream_ptr())
+    scratch = torch.empty(B * heads * T * ntok * 3, device=DEV) if kind == "coupling" else None
+    _lib.call("maed_bwd_attention", {"spatial": 0, "temporal": 1, "coupling": 2}[kind], _lib.ptr(p), C.c_longlong(p[0].numel()),
+              _lib.ptr(d_out), B, T, ntok, heads, C.c_float(0.125), 1, _lib.ptr(d_qkv), _lib.ptr(scratch), _lib.stream_ptr())
     assert rel_err(d_qkv, qd.grad + 1.0) < 2e-5, kind
 
 

@@ -47,7 +47,7 @@ def _digest(g, nsamp=8):
 
 
 @pytest.mark.parametrize("name", ["grads_vanilla_ktd", "grads_series_ktd", "grads_parallel_ktd", "grads_vanilla_iterative",
-                                  "grads_temporal_ktd"])
+                                  "grads_temporal_ktd", "grads_coupling_ktd"])
 def test_emulated_training_matches_reference_gradients(harness, name):
     # default suite: the stage-2 mode and the iterative decoder; vanilla / series (also covered through the product modules in
     # tests/test_train.py) with MAED_EMU_FULL=1 — keeps the CPU suite at a few minutes

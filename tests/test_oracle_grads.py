@@ -10,7 +10,7 @@ from oracle import maed_oracle as O
 from oracle import synth
 from helpers import GOLDEN_DIR, reference_shapes
 
-CASES = ["grads_parallel_ktd", "grads_series_ktd", "grads_vanilla_ktd", "grads_vanilla_iterative", "grads_temporal_ktd"]
+CASES = ["grads_parallel_ktd", "grads_series_ktd", "grads_vanilla_ktd", "grads_vanilla_iterative", "grads_temporal_ktd", "grads_coupling_ktd"]
 
 
 def load_grad_case(name):
