@@ -133,3 +133,29 @@ def test_fused_loss_matches_reference_golden_gpu(lib, name):
     z, kind, preds, d3, d2, kw = _case(name)
     total, d, grads = _product(kind, preds, d3, d2, kw, "cuda")
     _check(z, total.cpu(), {k: v.cpu() for k, v in d.items()}, [g.cpu() for g in grads])
+
+
+def test_stage2_iteration_with_the_fused_loss_on_the_emulator(harness):
+    """reference trainer.py:188,240-245 with the product modules: 'ste' model in train() mode -> LossVideo (3-D labelled clips +
+    2-D-only clips in one batch, trainer.py:181-187) -> backward -> FusedAdam; the loss must be finite and go down."""
+    from oracle import synth
+    with harness.product_on_cpu():
+        from maed_b200.loss import Loss
+        from maed_b200.models import MAED
+        from maed_b200.train import FusedAdam
+        m = MAED("ste", 1, 12, "vanilla", "ktd", 1024)
+        synth.fill_module_(m, 4)
+        m = m.train().enable_training(True, dropout_p=0.0)
+        crit = Loss(e_loss_weight=300., e_3d_loss_weight=600., e_pose_loss_weight=60., e_shape_loss_weight=0.06, device="cpu")
+        opt = FusedAdam.for_model(m, lr=2e-4, weight_decay=1e-5)
+        _, d3, d2 = LO.synth_loss_case(1, 1, 2, 9)                               # 1 clip with 2-D labels only + 1 clip with 3-D labels
+        x = synth.synth_frames(2, 2, 9)                                          # the 2-D clip comes first (loss.py:171-176)
+        losses = []
+        for _ in range(2):
+            opt.zero_grad()
+            loss, terms = crit(m(x), target_3d=d3, target_2d=d2)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        assert all(np.isfinite(losses)) and losses[1] < losses[0], losses
+        assert list(terms) == ["loss_kp_2d", "loss_kp_3d", "loss_shape", "loss_pose", "loss_norm"]
