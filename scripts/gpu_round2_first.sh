@@ -36,3 +36,5 @@ timeout 600 python scripts/bench_cnn.py --steps 10 --warmup 3 > gpurun_out/bench
 timeout 900 python bench.py --mode train --encoder cnn --steps 5 --warmup 3 > gpurun_out/bench_train_cnn.json 2> gpurun_out/bench_train_cnn.err; echo "cnn train bench exit $?"; cut -c1-400 gpurun_out/bench_train_cnn.json
 # (8) configs[4] shape (bs=4, T=32) on one GPU
 timeout 600 python scripts/bench_config5.py --steps 10 --warmup 3 > gpurun_out/bench_config5.json 2> gpurun_out/bench_config5.err; echo "config5 bench exit $?"; cut -c1-300 gpurun_out/bench_config5.json
+# (9) per-kernel timing of the training kernels at the bench shapes
+timeout 600 python scripts/bench_train_kernels.py > gpurun_out/train_kernels.log 2>&1; echo "train kernels exit $?"; tail -n 12 gpurun_out/train_kernels.log
