@@ -289,11 +289,13 @@ __global__ void maxpool3x3s2_idx_kernel(const float* __restrict__ x, const float
     const long long n = m / ((long long)OW * OH);
     float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     unsigned char bi[4] = {0, 0, 0, 0};
-    float sh[4] = {0.f, 0.f, 0.f, 0.f}, mu[4] = {0.f, 0.f, 0.f, 0.f};
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
     if (mean) {                                            // x -> relu(BatchNorm(x)) on the fly (the stem)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { mu[k] = mean[c + k]; sh[k] = beta[c + k]; }
+      for (int k = 0; k < 4; ++k) { mu[k] = mean[c + k]; sc[k] = rstd[c + k]; sh[k] = beta[c + k]; }
     }
+    const float4 gm = mean ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float gk[4] = {gm.x, gm.y, gm.z, gm.w};
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int ih = oh * 2 + r - 1;
@@ -306,7 +308,7 @@ __global__ void maxpool3x3s2_idx_kernel(const float* __restrict__ x, const float
         float vv[4] = {v.x, v.y, v.z, v.w};
         if (mean) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) vv[k] = fmaxf((vv[k] - mu[k]) * rstd[c + k] * gamma[c + k] + sh[k], 0.f);
+          for (int k = 0; k < 4; ++k) vv[k] = fmaxf((vv[k] - mu[k]) * sc[k] * gk[k] + sh[k], 0.f);   // same order as bn_apply
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
