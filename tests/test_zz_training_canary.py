@@ -23,7 +23,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # most certain first; the CTA-pair GEMM (never run, hand-written cluster protocol) last
 FILES = ["test_loss.py", "test_geometry_tail.py", "test_cnn.py", "test_smpl.py", "test_bwd_ops.py", "test_train.py", "test_gemm_pair.py"]
-TOTAL_BUDGET_S, PER_FILE_S, PER_TEST_S = 600, 240, 120
+TOTAL_BUDGET_S, PER_FILE_S, PER_TEST_S = 660, 330, 200    # test_train.py runs oracle autograd on the host CPU
 
 
 @pytest.mark.gpu
