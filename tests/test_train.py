@@ -49,12 +49,13 @@ def _slow_on_emu():
         pytest.skip("long on the emulator: set MAED_EMU_FULL=1")
 
 
-GRAD_CASES = ["grads_vanilla_ktd", "grads_series_ktd", "grads_parallel_ktd"]
+GRAD_CASES = ["grads_vanilla_ktd", "grads_series_ktd", "grads_parallel_ktd", "grads_vanilla_iterative", "grads_temporal_ktd",
+              "grads_coupling_ktd"]
 
 
-def _model(mode, seed, lib):
+def _model(mode, seed, lib, decoder="ktd"):
     from maed_b200.models import MAED
-    m = MAED("ste", 6, 12, mode, "ktd", 1024)
+    m = MAED("ste", 6, 12, mode, decoder, 1024, mean_params=synth.mean_params())
     synth.fill_module_(m, seed)
     return m.to(DEV).train().enable_training(True, dropout_p=0.0)
 
@@ -95,7 +96,7 @@ def test_gradients_match_reference_digests(lib, name):
         _slow_on_emu()
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     N, T, seed = [int(v) for v in z["meta"]]
-    m = _model(str(z["mode"]), seed, lib)
+    m = _model(str(z["mode"]), seed, lib, str(z["decoder"]))
     A, B, C_ = _probes(N * T, seed)
     loss = _loss(m(synth.synth_frames(N, T, seed).to(DEV)), A, B, C_)
     assert abs(loss.item() - float(z["loss"])) < 1e-3 * max(1.0, abs(float(z["loss"])))
