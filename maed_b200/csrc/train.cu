@@ -558,7 +558,6 @@ static int decoder_fwd(const Ctx& c, int C, float dropout_p, unsigned long long 
 static int cnn_train_forward(const Engine& e, const void* const* params, const void* packed, const float* x_in, int N, int T, void* workspace, size_t workspace_bytes, float dropout_p, unsigned long long seed,
                              const TrainOutputs* outs, cudaStream_t st) {
   const int BT = N * T;
-  MAED_CHECK_ARG(BT >= 2, "train_forward(cnn): BatchNorm in train() mode needs more than one frame per channel statistic");
   const Net net = build_cnn_net(e);
   TrainWs w;
   carve_cnn(e, net, BT, (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023), w);
