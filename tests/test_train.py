@@ -168,7 +168,8 @@ def test_fused_adam_matches_torch_adam(lib):
     # step 1 sees identical gradients: the two optimisers must agree to rounding.  The 1e-9 parameter differences that
     # leaves are amplified to ~1e-2 in the step-2 gradients (random weight-standardised backbone, ReLU / arg-max flips), so
     # the second comparison only guards against gross errors such as stale derived weights.
-    for step, tol in ((1, 1e-7), (2, 2e-4)):
+    steps = ((1, 1e-7), (2, 2e-4)) if (DEV == "cuda" or _EMU_FULL) else ((1, 1e-7),)     # step 2 on the emulator: MAED_EMU_FULL=1
+    for step, tol in steps:
         for m, o in ((m1, o1), (m2, o2)):
             o.zero_grad(set_to_none=True)
             _loss(m(x), A, B, C_).backward()
