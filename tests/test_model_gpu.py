@@ -129,4 +129,4 @@ def test_forward_subclips_equals_the_evaluator_loop():
         ref = torch.stack([p[k] for p in per], dim=2)            # (N, T, sf, ...) like np.stack(axis=2)
         ref = ref.reshape(2, 6, *ref.shape[3:])
         assert got[k].shape == ref.shape, k
-        assert rel_err(got[k], ref) < 1e-5, k
+        assert rel_err(got[k], ref) < 1e-4, k              # an index error would be O(1); batch-size dependent rounding is ~1e-6
