@@ -142,6 +142,7 @@ def test_gradients_match_oracle_autograd(lib):
 
 
 def test_loss_scale_invariance_and_determinism(lib):
+    _slow_on_emu()          # (the emulator's copy of this check: tests/test_emu_model.py, grads_vanilla_ktd, MAED_EMU_FULL=1)
     m = _model("vanilla", 5, lib)
     nt = 2 if DEV == "cuda" else 1
     x = synth.synth_frames(1, nt, 5).to(DEV)
