@@ -3,8 +3,7 @@
   * ``emu``  (CPU, runs in the default `-m "not gpu"` suite): the REAL kernel sources of maed_b200/csrc compiled by g++
     against the CUDA-on-CPU shim (tests/emu/): checks the index logic, reductions and formulas of every CUDA-core kernel;
     the tcgen05 split-K kernel cannot run there (its case is skipped, the conv data-gradient case uses the contract stub);
-  * ``cuda`` (`-m gpu`): the product library on a B200.  Written after round 1's GPU budget was spent: NOT yet run on
-    hardware, therefore skipped unless MAED_B200_TRAIN_TESTS=1 (round 2 starts by running them).
+  * ``cuda`` (`-m gpu`): the product library on a B200 (green on hardware since round 2).
 """
 import ctypes as C
 import os
@@ -19,9 +18,7 @@ from helpers import rel_err
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 
 DEV = "cuda"
-_CUDA_MARKS = [pytest.mark.gpu,
-               pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
-                                  reason="training path not yet validated on a GPU (set MAED_B200_TRAIN_TESTS=1)")]
+_CUDA_MARKS = [pytest.mark.gpu]
 
 
 @pytest.fixture(params=["emu", pytest.param("cuda", marks=_CUDA_MARKS)])

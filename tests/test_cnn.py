@@ -8,8 +8,7 @@ CPU (default suite):
     golden vectors, the new kernels against torch, the training step (train()-mode BatchNorm) against gradients and running
     buffers of the unmodified reference (tests/golden/grads_cnn_ktd.npz) through the C ABI and through the product modules, and
     a 2-rank gloo run of the SyncBatchNorm exchange against the reference's full-batch step.
-GPU (`-m gpu`): the product library against the golden vectors and the oracle.  Written without GPU access, so these run
-behind MAED_B200_TRAIN_TESTS=1 / the subprocess canary (tests/test_zz_training_canary.py) like the training path.
+GPU (`-m gpu`): the product library against the golden vectors and the oracle.  Green on hardware since round 2.
 """
 import os
 import sys
@@ -25,8 +24,6 @@ from oracle import synth
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 CASES = ["cnn_ktd", "cnn_iterative"]
-GATED = pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
-                           reason="not yet validated on a GPU: runs in the canary / with MAED_B200_TRAIN_TESTS=1")
 
 
 @pytest.fixture(scope="module")
@@ -370,7 +367,6 @@ def test_cnn_kernels_emulated(harness):
 
 # ---------------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
-@GATED
 def test_cnn_kernels_gpu(lib):
     from maed_b200 import _lib
     _run_ops(lib, _lib.stream_ptr(), "cuda")
@@ -378,7 +374,6 @@ def test_cnn_kernels_gpu(lib):
 
 
 @pytest.mark.gpu
-@GATED
 @pytest.mark.parametrize("name", CASES)
 def test_cnn_forward_matches_reference_golden_gpu(name):
     g, meta = load_golden(name)
@@ -396,7 +391,6 @@ def test_cnn_forward_matches_reference_golden_gpu(name):
 
 
 @pytest.mark.gpu
-@GATED
 def test_cnn_forward_matches_oracle_on_fresh_input_gpu():
     """bs = 2 x T = 4 (a different batch than the golden files), KTD decoder, against the pinned oracle."""
     from maed_b200.models import MAED
@@ -414,6 +408,5 @@ def test_cnn_forward_matches_oracle_on_fresh_input_gpu():
 
 
 @pytest.mark.gpu
-@GATED
 def test_cnn_training_step_matches_reference_gradients_gpu(lib):
     _product_training_step("cuda")

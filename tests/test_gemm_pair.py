@@ -1,7 +1,6 @@
 """GPU: the CTA-pair (tcgen05 cta_group::2) GEMM of csrc/gemm2_sm100.cuh against float64 matmul and against the validated
-single-CTA kernel.  The kernel was written without GPU access (opt-in, MAED_B200_GEMM_2CTA=1, read once per process), so the
-test body runs in a subprocess with the variable set and, like every not-yet-validated path, behind MAED_B200_TRAIN_TESTS=1 /
-the canary (tests/test_zz_training_canary.py)."""
+single-CTA kernel.  The kernel is selected per process (MAED_B200_GEMM_2CTA=1, read once), so the
+test body runs in a subprocess with the variable set."""
 import os
 import subprocess
 import sys
@@ -35,9 +34,12 @@ for M, N, K, bn in [(256, 256, 64, 0), (512, 128, 192, 0), (25216, 768, 768, 0),
         assert e < 2e-5, (M, N, K, bn, nsplit, e)
     bias, res = rnd(N, seed=6), rnd(M, N, seed=7)
     out = ops.gemm(pa, pb, bias=bias, act=ops.ACT_GELU, out_mode=ops.OUT_F16_SPLIT)
-    assert rel_err(ops.join(out), F.gelu(ref + bias.double())) < 3e-6, ("gelu/split", M, N, K)
+    tol = 3e-6 if K <= 256 else 2e-5          # fp32 tensor-core accumulation over K up to 3072, as in test_ops_gpu.test_gemm_plain
+    e = rel_err(ops.join(out), F.gelu(ref + bias.double()))
+    assert e < tol, ("gelu/split", M, N, K, e)
     out = ops.gemm(pa, pb, bias=bias, residual=res)
-    assert rel_err(out, ref + bias.double() + res.double()) < 3e-6, ("residual", M, N, K)
+    e = rel_err(out, ref + bias.double() + res.double())
+    assert e < tol, ("residual", M, N, K, e)
 # implicit-GEMM convs (5-D TMA A operand): even / odd numbers of 128-row tiles, the three map sizes of the backbones
 for n, H, Cin, Cout, k in [(4, 56, 64, 128, 3), (3, 28, 128, 128, 3), (5, 14, 256, 256, 3), (2, 14, 64, 128, 1)]:
     x = rnd(n, Cin, H, H, seed=8 + n)
@@ -56,8 +58,6 @@ print("PAIR_GEMM_OK worst %%.2e" %% worst)
 
 @pytest.mark.gpu
 @pytest.mark.timeout(200)
-@pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
-                    reason="not yet validated on a GPU: runs in the canary / with MAED_B200_TRAIN_TESTS=1")
 def test_pair_gemm_matches_float64_in_a_subprocess():
     env = dict(os.environ, MAED_B200_GEMM_2CTA="1")
     r = subprocess.run([sys.executable, "-c", BODY % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=180)

@@ -12,8 +12,7 @@ from oracle import maed_oracle as O
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 DEV = "cuda"
-_CUDA_MARKS = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
-                                                   reason="not yet validated on a GPU (set MAED_B200_TRAIN_TESTS=1)")]
+_CUDA_MARKS = [pytest.mark.gpu]
 
 
 @pytest.fixture(params=["emu", pytest.param("cuda", marks=_CUDA_MARKS)])

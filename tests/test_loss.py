@@ -22,8 +22,6 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu
 CASES = ["loss_video_stage2", "loss_video_accl", "loss_video_novalid", "loss_image_stage1"]
 KW = {"e_loss_weight": "w_kp2d", "e_3d_loss_weight": "w_kp3d", "e_pose_loss_weight": "w_pose", "e_shape_loss_weight": "w_shape",
       "e_smpl_norm_loss": "w_norm", "e_smpl_accl_loss": "w_accl"}
-GATED = pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
-                           reason="not yet validated on a GPU: runs in the canary / with MAED_B200_TRAIN_TESTS=1")
 
 
 def _case(name):
@@ -127,7 +125,6 @@ def test_cpu_tensors_fail_loudly():
 
 
 @pytest.mark.gpu
-@GATED
 @pytest.mark.parametrize("name", CASES)
 def test_fused_loss_matches_reference_golden_gpu(lib, name):
     z, kind, preds, d3, d2, kw = _case(name)

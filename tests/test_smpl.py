@@ -1,7 +1,6 @@
 """SMPL forward kernels (csrc/smpl.cu) against oracle/smpl_oracle.py on the seeded synthetic asset pack, and the wiring of
 verts / kp_3d / kp_2d into MAED.forward.  Two backends (see tests/test_bwd_ops.py): ``emu`` = the real kernel sources on
-the CUDA-on-CPU shim (default CPU suite), ``cuda`` = the product library on a B200 — written after round 1's GPU budget,
-NOT yet run on hardware, skipped unless MAED_B200_TRAIN_TESTS=1."""
+the CUDA-on-CPU shim (default CPU suite), ``cuda`` = the product library on a B200 (`-m gpu`; green on hardware since round 2)."""
 import ctypes as C
 import os
 import sys
@@ -16,9 +15,7 @@ from oracle import synth
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 
-_CUDA_MARKS = [pytest.mark.gpu,
-               pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
-                                  reason="SMPL tier not yet validated on a GPU (set MAED_B200_TRAIN_TESTS=1)")]
+_CUDA_MARKS = [pytest.mark.gpu]
 
 
 @pytest.fixture(params=["emu", pytest.param("cuda", marks=_CUDA_MARKS)])
@@ -76,7 +73,6 @@ def test_smpl_forward_matches_oracle(dev, R, use_reg):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"), reason="SMPL tier not yet validated on a GPU")
 def test_model_outputs_with_body_model(lib):
     from maed_b200.models import MAED
     a = S.synthetic_assets(1)

@@ -6,8 +6,7 @@ tests/test_bwd_ops.py):
   * ``emu``  — CPU, default suite: product Python code + real CUDA-core kernel sources + engine/train orchestration on the
     CUDA-on-CPU shim (tests/emu/harness.py::product_on_cpu); the tcgen05 kernels are contract stubs there.  The long cases
     run only with MAED_EMU_FULL=1 (the digest check of all three modes is in tests/test_emu_model.py either way);
-  * ``cuda`` — `-m gpu`, the product library on a B200.  Written after round 1's GPU budget was spent: NOT yet run on
-    hardware, skipped unless MAED_B200_TRAIN_TESTS=1 (round 2 starts by running them).
+  * ``cuda`` — `-m gpu`, the product library on a B200 (green on hardware since round 2).
 """
 import os
 import sys
@@ -23,9 +22,7 @@ from oracle import synth
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 
 DEV = "cuda"
-_CUDA_MARKS = [pytest.mark.gpu,
-               pytest.mark.skipif(not os.environ.get("MAED_B200_TRAIN_TESTS"),
-                                  reason="training path not yet validated on a GPU (set MAED_B200_TRAIN_TESTS=1)")]
+_CUDA_MARKS = [pytest.mark.gpu]
 _EMU_FULL = bool(os.environ.get("MAED_EMU_FULL"))
 
 
@@ -86,7 +83,8 @@ def test_tape_forward_matches_inference(lib, mode):
         ref = m.eval()(x, _debug=True)
     for k in ("pose6d", "shape", "cam"):
         assert rel_err(out["_debug"][k], ref["_debug"][k]) < 1e-5, k
-    assert rel_err(out["theta"], ref["theta"]) < 1e-4 and rel_err(out["rotmat"], ref["rotmat"]) < 1e-5
+    # the tape forward runs GroupNorm unfused (fp32 conv output kept for the backward): different summation order than inference
+    assert rel_err(out["theta"], ref["theta"]) < 1e-4 and rel_err(out["rotmat"], ref["rotmat"]) < 5e-5
     assert out["theta"].requires_grad
 
 
