@@ -112,10 +112,32 @@ def _cpu_state():
     return {k: v.detach() for k, v in list(m.named_parameters()) + list(m.named_buffers())}
 
 
-def best_cpu_threads(sd):
+def cpu_forward_fn():
+    """(callable x -> output dict, kind, description) of the CPU arm: the reference's OWN modules (unmodified
+    lib/models from /root/reference or its verbatim git-ignored copy oracle/_ref/, imported through oracle/ref_shim.py)
+    when that tree is present — kind "reference" —, else the pinned oracle port (oracle/maed_oracle.py) — kind "port"."""
+    from oracle import synth
+    try:
+        from oracle import ref_shim
+        if ref_shim.reference_available():
+            cwd = os.getcwd()
+            try:
+                model = ref_shim.build_reference_model(MODE, DECODER)
+            finally:
+                os.chdir(cwd)
+            synth.fill_module_(model, 0)
+            model.eval()
+            return (lambda x: model(x)), "reference", "unmodified reference lib.models.MAED (%s)" % ref_shim.REFERENCE_ROOT
+    except Exception as e:                                # missing torchvision etc.: fall back to the port, say why
+        sys.stderr.write("bench.py: reference import failed (%s); CPU arm uses the oracle port\n" % e)
+    from oracle import maed_oracle as O
+    sd = _cpu_state()
+    return (lambda x: O.maed_forward(x, sd, MODE, DECODER)), "port", "oracle/maed_oracle.py (CPU restatement pinned to the reference's golden vectors)"
+
+
+def best_cpu_threads(fwd):
     """PyTorch CPU ops do not scale to every core of a 100+-core host (the first run used all 128 threads and was
     15x slower than 8 threads); pick the thread count that is fastest on a 2-frame probe clip."""
-    from oracle import maed_oracle as O
     from oracle import synth
     cores = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
@@ -124,9 +146,9 @@ def best_cpu_threads(sd):
     with torch.no_grad():
         for c in cands:
             torch.set_num_threads(c)
-            O.maed_forward(x, sd, MODE, DECODER)
+            fwd(x)
             t0 = time.perf_counter()
-            O.maed_forward(x, sd, MODE, DECODER)
+            fwd(x)
             dt = time.perf_counter() - t0
             if dt < best_t:
                 best, best_t = c, dt
@@ -134,34 +156,40 @@ def best_cpu_threads(sd):
     return best
 
 
-def cpu_port_clips_per_s(n_clips, reps, threads=None):
-    """The oracle (CPU restatement of the reference's algorithm, fp32 PyTorch ops) on the host cores."""
-    from oracle import maed_oracle as O
+def cpu_clips_per_s(n_clips, reps, warmup=0, budget_s=None):
+    """Times `reps` forwards of n_clips x T=16 on the host cores; returns (per-step seconds, kind, description, n_clips).
+    With `budget_s` the batch per step is halved (8 -> 4 -> 2 -> 1 clips) until warmup + reps steps fit the budget, judged
+    from a one-clip probe."""
     from oracle import synth
-    sd = _cpu_state()
-    if threads:
-        torch.set_num_threads(threads)
-    else:
-        best_cpu_threads(sd)
+    fwd, kind, desc = cpu_forward_fn()
+    best_cpu_threads(fwd)
+    if budget_s:
+        x1 = synth.synth_frames(1, T, 2)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            fwd(x1)
+            t1 = time.perf_counter() - t0
+        while n_clips > 1 and n_clips * t1 * (warmup + reps) > budget_s:
+            n_clips //= 2
     x = synth.synth_frames(n_clips, T, 0)
     times = []
     with torch.no_grad():
-        for _ in range(reps):
+        for i in range(warmup + reps):
             t0 = time.perf_counter()
-            O.maed_forward(x, sd, MODE, DECODER)
-            times.append(time.perf_counter() - t0)
-    return times
+            fwd(x)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return times, kind, desc, n_clips
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm for the path on this box's host cores.  /root/reference
-    cannot travel to the GPU box, so this is the pinned oracle port (oracle/maed_oracle.py); each step is a bounded
-    sample (1 clip of T=16) of the same workload."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, same metric /
+    config as the CUDA arm.  Every step is the FULL batch of configs[1] (8 clips x T=16) when the run fits 150 s, else a
+    bounded sample of it (stated in config.sample)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_clips = 1
-    times = cpu_port_clips_per_s(n_clips, args.warmup + args.steps)[args.warmup:]
+    times, kind, desc, n_clips = cpu_clips_per_s(CLIPS_PER_GPU, args.steps, args.warmup, budget_s=150.0)
     total = sum(times)
     val = n_clips * len(times) / total
     line = {
@@ -169,10 +197,13 @@ def run_reference(args):
         "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "1 clip x T=16 per step (bounded sample of the 8-clip batch)",
+        "config": {"workload": WORKLOAD, "clips_per_gpu": CLIPS_PER_GPU, "seq_len": T, "st_mode": MODE, "decoder": DECODER,
+                   "sample": ("none: every step is the full batch of 8 clips x T=16" if n_clips == CLIPS_PER_GPU else
+                              "%d clips x T=16 per step (bounded sample of the 8-clip batch: the full batch would exceed the "
+                              "150 s budget of this arm on this host)" % n_clips),
                    "device": "host CPU (%d logical cores), torch %s, %d threads (fastest of 8/16/32/64/all on a probe clip)" % (os.cpu_count() or 1, torch.__version__, torch.get_num_threads())},
-        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": "%d x (1 clip, T=16) forward, oracle/maed_oracle.py" % len(times)},
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": "%d x (%d clips, T=16) forward, %s" % (len(times), n_clips, desc)},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -200,55 +231,43 @@ def time_dominant_gemm(dev, reps=20):
     return 2.0 * M * N * K / 1e12, ms
 
 
-def run_train(args):
-    """BASELINE configs[2]/[3]: bs = 8 clips x T = 16 per GPU, forward + backward + Adam, random init, synthetic clips;
-    N > 1: one all-reduce of the flat gradient buffer per step (data parallel over clips).  The loss is the reference's
-    parameter-space terms on theta (MSE), the keypoint terms need the SMPL tier.  NOTE: the training path was written
-    after round 1's GPU budget; this mode is not part of the driver's default metric."""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --mode train: no CUDA device")
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
-    from maed_b200 import build, ops, train
+def train_measure(args, dev, dist, world, rank, local, st_mode, encoder="ste", loss_kind="mse", steps=None, sampler_cls=None):
+    """BASELINE configs[2]/[3]: bs = 8 clips x T = 16 per GPU, forward + backward + Adam, random init, synthetic clips
+    (reference lib/core/trainer.py:238-255: preds = model(inp); loss.backward(); optimizer.step()).  N > 1: data parallel over
+    clips, the flat gradient buffer (288.5 MB fp32) is all-reduced over NCCL / NVLink every step (reference train.py:113).
+    Returns a dict (rank 0) or None."""
+    from maed_b200 import ops, train
     from maed_b200.models import MAED
     from oracle import synth
-    build.build()
-    st_mode = args.st_mode or MODE
+    steps = steps or args.steps
     torch.manual_seed(0)
-    cnn = args.encoder == "cnn"
+    cnn = encoder == "cnn"
     # 'cnn': the literal stage-1 shape (configs/config_stage1.yaml: 128 images per GPU, T = 1, torchvision ResNet-50 encoder)
-    CLIPS_PER_GPU, T = (128, 1) if cnn else (globals()["CLIPS_PER_GPU"], globals()["T"])
+    clips, Tt = (128, 1) if cnn else (CLIPS_PER_GPU, T)
     model = MAED("cnn" if cnn else "ste", 6, 12, st_mode, DECODER, 1024)
     if cnn:
         synth.fill_module_(model, 0)              # running statistics / affine parameters of a plausible BatchNorm state
-    model = model.to(dev).train().enable_training(True)
+    model = model.to(dev).train()
     opt = train.FusedAdam.for_model(model, lr=1e-4, weight_decay=1e-5)          # configs/config_stage2.yaml:63-66
-    xs = [synth.synth_frames(CLIPS_PER_GPU, T, 300 + i).to(dev) for i in range(4)]
-    target = torch.zeros(CLIPS_PER_GPU, T, 85, device=dev)
+    xs = [synth.synth_frames(clips, Tt, 300 + i).to(dev) for i in range(4)]
+    target = torch.zeros(clips, Tt, 85, device=dev)
     target[..., 0] = 1.0
     h_loss = torch.empty(1).pin_memory()
     criterion, target_3d = None, None
-    if args.loss == "fused":
+    if loss_kind == "fused":
         # the reference's LossVideo (lib/core/loss.py:159-210) with the stage-2 weights (configs/config_stage2.yaml:34-40) on
         # synthetic targets of the trainer's shapes (SURVEY.md 8d config 3), through the fused CUDA loss (maed_b200/loss.py)
         from maed_b200.loss import Loss
         criterion = Loss(e_loss_weight=300., e_3d_loss_weight=600., e_pose_loss_weight=60., e_shape_loss_weight=0.06,
                          e_smpl_norm_loss=1., e_smpl_accl_loss=0., device=dev)
         g = torch.Generator().manual_seed(5)
-        ones = torch.ones(CLIPS_PER_GPU, T, 49, 1)
-        th = 0.2 * torch.randn(CLIPS_PER_GPU, T, 85, generator=g)
+        ones = torch.ones(clips, Tt, 49, 1)
+        th = 0.2 * torch.randn(clips, Tt, 85, generator=g)
         th[..., :3] = torch.tensor([1.0, 0.0, 0.0])
-        target_3d = {"kp_2d": torch.cat([2 * torch.rand(CLIPS_PER_GPU, T, 49, 2, generator=g) - 1, ones], -1).to(dev),
-                     "kp_3d": torch.cat([0.3 * torch.randn(CLIPS_PER_GPU, T, 49, 3, generator=g), ones], -1).to(dev),
-                     "theta": th.to(dev), "w_smpl": torch.ones(CLIPS_PER_GPU, T, device=dev)}
+        target_3d = {"kp_2d": torch.cat([2 * torch.rand(clips, Tt, 49, 2, generator=g) - 1, ones], -1).to(dev),
+                     "kp_3d": torch.cat([0.3 * torch.randn(clips, Tt, 49, 3, generator=g), ones], -1).to(dev),
+                     "theta": th.to(dev), "w_smpl": torch.ones(clips, Tt, device=dev)}
+    ar_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 
     def step(x):
         opt.zero_grad(set_to_none=True)
@@ -258,14 +277,16 @@ def run_train(args):
             loss = ((model(x)["theta"] - target) ** 2).mean()
         loss.backward()
         if dist:
+            ar_ev[0].record()
             train.allreduce_gradients(model, world)
+            ar_ev[1].record()
         opt.step()
         return loss
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 3)):
         step(xs[i % 4])
     torch.cuda.synchronize(dev)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = sampler_cls(local) if (sampler_cls and rank == 0) else None
     if dist:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -275,7 +296,7 @@ def run_train(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     _profile(True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         loss = step(xs[i % 4])
     e1.record()
     torch.cuda.synchronize(dev)
@@ -283,19 +304,21 @@ def run_train(args):
     launches = ops.launch_count() - l0
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ar_ms = torch.tensor([ar_ev[0].elapsed_time(ar_ev[1]) if dist else 0.0], device=dev)
     if dist:
         dist.barrier()
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ar_ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    value = world * CLIPS_PER_GPU * args.steps / (ms_total / 1000.0)
+    value = world * clips * steps / (ms_total / 1000.0)
     # end to end: pinned host frames -> H2D -> train step -> D2H of the loss, every step
-    hx = [synth.synth_frames(CLIPS_PER_GPU, T, 400 + i).pin_memory() for i in range(2)]
+    hx = [synth.synth_frames(clips, Tt, 400 + i).pin_memory() for i in range(2)]
     dxb = torch.empty_like(xs[0])
     if dist:
         dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         dxb.copy_(hx[i % 2], non_blocking=True)
         h_loss.copy_(step(dxb).detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
@@ -303,58 +326,43 @@ def run_train(args):
     if dist:
         dist.barrier()
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        peaks, peak_src = load_peaks()
-        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-        gflop_per_clip = 8.174 * T if cnn else GFLOP_PER_CLIP                     # ResNet-50: 8.17 GFLOP per frame
-        step_tflops = 3.0 * CLIPS_PER_GPU * gflop_per_clip / 1000.0 / (ms_total / args.steps / 1000.0)
-        print(json.dumps({
-            "metric": ("images/sec (224x224, bs=128/gpu, T=1), MAED cnn(ResNet-50)+ktd train step (fwd+bwd+Adam)" if cnn else
-                       "clips/sec (T=16, 224x224, bs=8/gpu), MAED ste-%s+ktd train step (fwd+bwd+Adam)" % st_mode),
-            "mode": "train", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 hi/lo split operands for forward, data- and weight-gradient GEMMs; fp32 reductions / Adam",
-            "data": "synthetic",
-            "config": {"workload": ("configs/config_stage1.yaml shape: 128 images per GPU, encoder='cnn', train step, BatchNorm on "
-                                    "batch statistics (SyncBatchNorm exchange when N > 1)") if cnn else
-                                   "BASELINE configs[2]: 1xB200 bs=8 T=16 train step (fwd+bwd+Adam), random-init",
-                       "clips_per_gpu": CLIPS_PER_GPU, "seq_len": T, "st_mode": st_mode, "decoder": DECODER,
-                       "loss": ("reference LossVideo, stage-2 weights, fused CUDA loss (keypoint terms act on the zero body model "
-                                "unless SMPL assets are loaded)") if args.loss == "fused" else
-                               "MSE on theta (the reference's parameter-space terms; keypoint terms need the SMPL tier)",
-                       "parallelism": "data parallel x%d, one all-reduce of the flat gradient buffer per step" % world},
-            "clocks": clocks, "gpu_launches": int(launches), "final_loss": float(loss.item()),
-            "e2e": {"value": world * CLIPS_PER_GPU * args.steps / (float(e2e_ms.item()) / 1000.0), "unit": "clips/s",
-                    "h2d_bytes_per_step": xs[0].numel() * 4, "d2h_bytes_per_step": 4},
-            "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf, "peak_source": peak_src,
-                         "achieved": step_tflops, "frac": step_tflops / peak_tf, "traffic": None,
-                         "note": "whole step, algorithmic FLOPs = 3 x forward (SURVEY.md 8d)"},
-        }))
-    if dist:
-        dist.destroy_process_group()
+    final_loss = float(loss.item())
+    grad_bytes = model._train_state.flat_grad.numel() * 4
+    del model, opt, xs, dxb
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peaks, peak_src = load_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    gflop_per_clip = 8.174 * Tt if cnn else GFLOP_PER_CLIP                     # ResNet-50: 8.17 GFLOP per frame
+    step_tflops = 3.0 * clips * gflop_per_clip / 1000.0 / (ms_total / steps / 1000.0)
+    return {
+        "metric": ("images/sec (224x224, bs=128/gpu, T=1), MAED cnn(ResNet-50)+ktd train step (fwd+bwd+Adam)" if cnn else
+                   "clips/sec (T=16, 224x224, bs=8/gpu), MAED ste-%s+ktd train step (fwd+bwd+Adam)" % st_mode),
+        "mode": "train", "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 hi/lo split operands for forward, data- and weight-gradient GEMMs; fp32 reductions / Adam",
+        "data": "synthetic",
+        "config": {"workload": ("configs/config_stage1.yaml shape: 128 images per GPU, encoder='cnn', train step, BatchNorm on "
+                                "batch statistics (SyncBatchNorm exchange when N > 1)") if cnn else
+                               "BASELINE configs[2] (N=1) / configs[3] shape (N>1): bs=8/gpu T=16 train step (fwd+bwd+Adam), random-init",
+                   "clips_per_gpu": clips, "seq_len": Tt, "st_mode": st_mode, "decoder": DECODER,
+                   "loss": ("reference LossVideo, stage-2 weights, fused CUDA loss (keypoint terms act on the zero body model "
+                            "unless SMPL assets are loaded)") if loss_kind == "fused" else
+                           "MSE on theta (the reference's parameter-space terms; keypoint terms need the SMPL tier)",
+                   "parallelism": "data parallel x%d, one NCCL all-reduce of the flat gradient buffer per step" % world},
+        "clocks": clocks, "gpu_launches": int(launches), "final_loss": final_loss,
+        "collective": {"kind": "all-reduce (NCCL, flat fp32 gradient buffer)", "bytes_per_step": grad_bytes,
+                       "ms_last_step_max_over_ranks": float(ar_ms.item()), "overlapped_with_backward": False} if dist else None,
+        "e2e": {"value": world * clips * steps / (float(e2e_ms.item()) / 1000.0), "unit": "clips/s",
+                "h2d_bytes_per_step": clips * Tt * 3 * 224 * 224 * 4, "d2h_bytes_per_step": 4},
+        "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf, "peak_source": peak_src + ", bf16_tflops_sustained",
+                     "achieved": step_tflops, "frac": step_tflops / peak_tf, "traffic": None,
+                     "note": "whole step per GPU, algorithmic FLOPs = 3 x forward (SURVEY.md 8d)"},
+    }
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="maed_b200", choices=["maed_b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
-                    help="forward: BASELINE configs[1] (the driver's metric); train: configs[2] fwd+bwd+Adam (opt-in)")
-    ap.add_argument("--loss", default="mse", choices=["mse", "fused"],
-                    help="train mode only: 'fused' = the reference's LossVideo through maed_b200.loss (not yet GPU-validated)")
-    ap.add_argument("--encoder", default="ste", choices=["ste", "cnn"],
-                    help="train mode only: 'cnn' = the stage-1 shape, 128 images per GPU (not yet GPU-validated)")
-    ap.add_argument("--st-mode", default=None, help="train mode only: parallel (default) or series")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.mode == "train":
-        return run_train(args)
-
+def _init(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -368,8 +376,50 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
-    from maed_b200 import build, ops
-    build.build()
+    from maed_b200 import build
+    if local == 0:
+        build.build()                                     # one builder per node; the other ranks wait for the .so
+    if dist:
+        dist.barrier()
+    return world, rank, local, dev, dist
+
+
+def run_train(args):
+    """--mode train: the train step as the bench line (configs[2] at N=1, the configs[3] shape under torchrun)."""
+    world, rank, local, dev, dist = _init(args)
+    line = train_measure(args, dev, dist, world, rank, local, args.st_mode or MODE, args.encoder, args.loss,
+                         sampler_cls=ClockSampler)
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="maed_b200", choices=["maed_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="forward mode: skip the nested train-step measurement")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward: BASELINE configs[1] (the driver's metric, with the train step nested under \"train\"); "
+                         "train: the configs[2]/[3] train step (fwd+bwd+Adam, NCCL gradient all-reduce at N>1) as the line")
+    ap.add_argument("--loss", default="mse", choices=["mse", "fused"],
+                    help="train mode only: 'fused' = the reference's LossVideo through maed_b200.loss")
+    ap.add_argument("--encoder", default="ste", choices=["ste", "cnn"],
+                    help="train mode only: 'cnn' = the stage-1 shape, 128 images per GPU")
+    ap.add_argument("--st-mode", default=None, help="train mode only: parallel (default) or series")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.mode == "train":
+        return run_train(args)
+
+    world, rank, local, dev, dist = _init(args)
+    from maed_b200 import ops
     model = build_model(dev)
     from oracle import synth
     # 4 distinct device-resident batches (308 MB > 126 MB L2), rotated; a step also streams ~4.5 GB of workspace
@@ -404,12 +454,12 @@ def main():
     value = world * CLIPS_PER_GPU * args.steps / (ms_total / 1000.0)
 
     # ---------------------------------------------------------------- end-to-end through the public API ("e2e"):
-    # host pinned frames -> H2D -> MAED.forward -> D2H of theta/rotmat, every step, copies inside the timed region;
+    # host pinned frames -> H2D -> MAED.forward -> D2H of all five outputs the reference's evaluator pulls
+    # (lib/core/evaluate.py:80-84: theta, verts, kp_2d, kp_3d, rotmat), every step, copies inside the timed region;
     # the H2D of step i+1 runs on a side stream while step i computes (what a pin_memory DataLoader + non_blocking does).
     hx = [synth.synth_frames(CLIPS_PER_GPU, T, 200 + i).pin_memory() for i in range(2)]
     dx = [torch.empty_like(xs[0]) for _ in range(2)]
-    h_theta = torch.empty(CLIPS_PER_GPU, T, 85).pin_memory()
-    h_rot = torch.empty(CLIPS_PER_GPU, T, 24, 3, 3).pin_memory()
+    h_out = {k: torch.empty(v.shape).pin_memory() for k, v in out.items() if k in ("theta", "verts", "kp_2d", "kp_3d", "rotmat")}
     copy_stream = torch.cuda.Stream(dev)
     main_stream = torch.cuda.current_stream(dev)
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -430,8 +480,8 @@ def main():
             main_stream.wait_event(ready[cur])
             o = model(dx[cur])
             consumed[cur].record(main_stream)
-            h_theta.copy_(o["theta"], non_blocking=True)
-            h_rot.copy_(o["rotmat"], non_blocking=True)
+            for k, h in h_out.items():
+                h.copy_(o[k], non_blocking=True)
             main_stream.synchronize()               # the caller reads the result of every step
 
     e2e_loop(2)
@@ -447,7 +497,15 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * CLIPS_PER_GPU * args.steps / (float(e2e_ms.item()) / 1000.0)
     h2d = xs[0].numel() * 4
-    d2h = (h_theta.numel() + h_rot.numel()) * 4
+    d2h = sum(h.numel() for h in h_out.values()) * 4
+    del xs, dx, out
+    model._workspace = None
+    torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- nested: the train step (configs[2]; configs[3] shape at N>1)
+    train_line = None
+    if not args.no_train:
+        train_line = train_measure(args, dev, dist, world, rank, local, MODE, steps=min(args.steps, 10))
 
     if rank != 0:
         if dist:
@@ -458,6 +516,7 @@ def main():
     tf_launch, gemm_ms = time_dominant_gemm(dev)
     achieved = tf_launch / (gemm_ms / 1000.0)
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    peak_burst = float(peaks.get("bf16_tflops", peak_tf))          # the GEMM is timed alone (20 launches): burst peak
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tpath):
@@ -476,18 +535,20 @@ def main():
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<256> (STE mlp.fc1 25216x3072x768, split)",
-                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": traffic, "peak_source": peak_src + ", bf16_tflops_sustained",
+                     "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,
+                     "traffic": traffic, "peak_source": peak_src + ", bf16_tflops (burst: the kernel is timed alone); "
+                     "whole_step_frac_of_peak uses bf16_tflops_sustained = %.1f" % peak_tf,
                      "algorithmic_tflop_per_launch": tf_launch, "ms_per_launch": gemm_ms,
                      "note": "algorithmic FLOPs (2MNK); the split path issues 3x that on the tensor pipe",
                      "whole_step_algorithmic_tflops_per_gpu": step_tflops,
                      "whole_step_frac_of_peak": step_tflops / peak_tf},
     }
+    if train_line is not None:
+        line["train"] = train_line
     if world == 1 and not args.no_cpu_baseline:
-        times = cpu_port_clips_per_s(1, 3)[1:]
-        line["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "clips/s", "cores": torch.get_num_threads(),
-                                "kind": "port", "sample": "2 x (1 clip, T=16) forward after 1 warm-up, oracle/maed_oracle.py "
-                                "(CPU restatement pinned to the reference's golden vectors)"}
+        times, kind, desc, _ = cpu_clips_per_s(2, 2, warmup=1)
+        line["cpu_baseline"] = {"value": 2 * len(times) / sum(times), "unit": "clips/s", "cores": torch.get_num_threads(),
+                                "kind": kind, "sample": "2 x (2 clips, T=16) forward after 1 warm-up, %s" % desc}
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

@@ -182,9 +182,11 @@ int maed_train_backward(const maed_engine* e, const void* const* params, const v
                         const float* x, int N, int T, void* workspace, size_t workspace_bytes, const float* d_pose6d,
                         const float* d_shape, const float* d_cam, float loss_scale, float dropout_p, float* const* grads,
                         void* stream);
-/* torch.optim.Adam step on flat fp32 buffers (reference lib/utils/utils.py:127-131); g is multiplied by grad_scale */
-int maed_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, int step, float grad_scale, void* stream);
+/* torch.optim.Adam step on flat fp32 buffers (reference lib/utils/utils.py:127-131); g is multiplied by grad_scale.  The
+ * hyper-parameters are doubles: like torch, the scalar coefficients (1 - beta, lr / (1 - beta1^step), ...) are formed in double
+ * on the host and rounded to fp32 once. */
+int maed_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int step, float grad_scale, void* stream);
 
 /* per-op entry points of the backward kernels (unit tests; semantics in maed_b200/csrc/bwd_kernels.h) */
 int maed_bwd_transpose_planes(const void* in_hi, long long in_plane, int R, int C, int ld_in, void* out_hi, long long out_plane,

@@ -15,6 +15,7 @@ _P = C.c_void_p
 _I = C.c_int
 _L = C.c_longlong
 _F = C.c_float
+_D = C.c_double
 _Z = C.c_size_t
 
 
@@ -87,7 +88,7 @@ SIGNATURES = {
     "maed_train_pack": (_I, [_P, c_void_pp, _P, _P]),
     "maed_train_forward": (_I, [_P, c_void_pp, _P, _P, _I, _I, _P, _Z, _F, _U, C.POINTER(MaedTrainOutputs), _P]),
     "maed_train_backward": (_I, [_P, c_void_pp, _P, _P, _P, _I, _I, _P, _Z, _P, _P, _P, _F, _F, c_void_pp, _P]),
-    "maed_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "maed_adam_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _I, _F, _P]),
     "maed_bwd_transpose_planes": (_I, [_P, _L, _I, _I, _I, _P, _L, _I, _P]),
     "maed_bwd_colsum": (_I, [_P, _L, _I, _I, _F, _I, _P, _P, _P]),
     "maed_bwd_layernorm": (_I, [_P, _L, _P, _L, _P, _I, _I, _F, _P, _P, _L, _P, _P, _P, _P, _P]),

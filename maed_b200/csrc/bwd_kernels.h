@@ -105,8 +105,8 @@ int ktd_tree_bwd(const float* d_pose6d, const float* d_shape, const float* d_cam
 int ktd_anc_wgrad(const float* g_total, const float* pose6d, int R, float scale, float* d_w_anc, cudaStream_t st);
 
 // ---- Adam (torch.optim.Adam semantics: L2 weight decay added to the gradient, bias-corrected moments)
-int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-              float weight_decay, int step, float grad_scale, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2, double eps,
+              double weight_decay, int step, float grad_scale, cudaStream_t st);
 
 // ---- attention backward (attention_bwd.cu); qkv planes as in the forward, d_out fp32 [BT*ntok, H*64],
 // d_qkv fp32 [BT*ntok, 3*H*64]; `accumulate` adds to d_qkv instead of overwriting it

@@ -228,24 +228,27 @@ int ktd_anc_wgrad(const float* g_total, const float* pose6d, int R, float scale,
 // torch.optim.Adam (reference lib/utils/utils.py:127-131): g += wd * p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                            long long n, float omb1, float b2, float omb2, float eps, float wd, float step_size, float bc2_sqrt,
                             float grad_scale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float pi = p[i];
     const float gi = g[i] * grad_scale + wd * pi;
-    const float mi = b1 * m[i] + (1.0f - b1) * gi;
-    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    const float m0 = m[i];
+    const float mi = m0 + omb1 * (gi - m0);               // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = b2 * v[i] + omb2 * gi * gi;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     m[i] = mi;
     v[i] = vi;
-    p[i] = pi - (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
   }
 }
-int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-              float weight_decay, int step, float grad_scale, cudaStream_t st) {
+int adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2, double eps,
+              double weight_decay, int step, float grad_scale, cudaStream_t st) {
   MAED_CHECK_ARG(step >= 1, "adam_step: step counts from 1");
-  const float bc1 = 1.0f - powf(beta1, (float)step);
-  const float bc2 = sqrtf(1.0f - powf(beta2, (float)step));
-  adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  // scalar coefficients in double, rounded to fp32 once (torch/optim/adam.py::_single_tensor_adam)
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2_sqrt = sqrt(1.0 - pow(beta2, (double)step));
+  adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
+                                               (float)weight_decay, (float)(lr / bc1), (float)bc2_sqrt, grad_scale);
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
 }

@@ -189,8 +189,8 @@ int maed_train_backward(const maed_engine* e, const void* const* params, const v
   return train_backward(reinterpret_cast<const Engine*>(e), params, packed, tpack, x, N, T, workspace, workspace_bytes, d_pose6d,
                         d_shape, d_cam, loss_scale, dropout_p, grads, (cudaStream_t)stream);
 }
-int maed_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, int step, float grad_scale, void* stream) {
+int maed_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int step, float grad_scale, void* stream) {
   return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream);
 }
 

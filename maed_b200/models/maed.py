@@ -6,11 +6,14 @@ CUDA: tcgen05/TMA GEMMs and attention, fused norm kernels) through one C-ABI cal
 
 Differences a caller can observe (documented in INTEGRATION.md):
   * inputs must be CUDA float32 tensors — there is no CPU / eager fallback, by design;
-  * `forward` is inference-only unless `enable_training()` is called (the CUDA training path of maed_b200/train.py
-    is written but not yet validated on a GPU; opt-in until then);
-  * `encoder='cnn'` (torchvision ResNet-50, stage-1 config): eval() folds BatchNorm into the conv weights; the training
-    path normalises with the statistics of this rank's batch (no SyncBatchNorm exchange between ranks yet);
-  * `decoder.smpl.*` buffers do not exist (smplx and the SMPL assets are absent): `verts`/`kp_3d` are zeros.
+  * in `train()` mode with autograd enabled `forward` runs the CUDA training path (maed_b200/train.py: activation tape,
+    backward kernels to every parameter) exactly like the reference module under `loss.backward()`; `eval()` or
+    `torch.no_grad()` runs the fused inference engine;
+  * `encoder='cnn'` (torchvision ResNet-50, stage-1 config): eval() folds BatchNorm into the conv weights; train() uses batch
+    statistics and, under `torch.distributed` with more than one rank, exchanges them like `nn.SyncBatchNorm`
+    (reference train.py:95; `model.sync_batchnorm = False` keeps per-rank statistics);
+  * `decoder.smpl.*` buffers do not exist (smplx and the SMPL assets are absent): `verts`/`kp_3d` are zeros unless a body
+    model is installed with `load_smpl_assets()`.
 """
 import ctypes as C
 import os
@@ -68,7 +71,7 @@ class MAED(nn.Module):
         self._pack_gen = 0
         self._workspace = None
         self._param_ptrs = None
-        self._training_enabled = False
+        self._training_enabled = True
         self._train_dropout_p = None
         self._train_state = None
 
@@ -182,9 +185,9 @@ class MAED(nn.Module):
         return self._run(x)["feat"].reshape(N, T, -1)
 
     def enable_training(self, flag=True, dropout_p=None):
-        """Route train()-mode forwards (with autograd enabled) through the engine's training path
-        (maed_b200/train.py: saved-activation tape + CUDA backward).  Opt-in while that path awaits its GPU validation;
-        the environment variable MAED_B200_TRAINING=1 enables it for every model."""
+        """train()-mode forwards with autograd enabled run the engine's training path (maed_b200/train.py: saved-activation
+        tape + CUDA backward) — the default.  `enable_training(False)` turns train()-mode forwards into graph-less inference
+        calls (with a warning); `dropout_p` overrides the decoders' nn.Dropout() probability (0.0 for parity runs)."""
         self._training_enabled = bool(flag)
         self._train_dropout_p = dropout_p       # None: nn.Dropout() default 0.5 (ktd.py:54-56); 0.0 for parity runs
         return self
@@ -194,13 +197,13 @@ class MAED(nn.Module):
         placeholder body model verts are zeros, so J_regressor @ verts is zeros as well."""
         wants_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if wants_grad and kwargs.get("_allow_train_mode") is None:
-            if getattr(self, "_training_enabled", False) or os.environ.get("MAED_B200_TRAINING"):
+            if getattr(self, "_training_enabled", True):
                 from .. import train as _train
                 return _train.train_forward(self, x, J_regressor)
             import warnings
-            warnings.warn("maed_b200.MAED.forward is inference-only unless enable_training() was called: outputs carry no "
-                          "autograd graph and train()-mode dropout (reference ktd.py:54-56) is not applied; call .eval() "
-                          "for inference.", RuntimeWarning, stacklevel=2)
+            warnings.warn("maed_b200.MAED: the training path was switched off with enable_training(False): outputs carry no "
+                          "autograd graph and train()-mode dropout (reference ktd.py:54-56) is not applied.",
+                          RuntimeWarning, stacklevel=2)
         with torch.no_grad():
             return self._forward_inference(x, J_regressor, **kwargs)
 

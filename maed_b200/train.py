@@ -15,8 +15,10 @@ runs in libmaed_b200.so:
   * ``allreduce_gradients`` — data-parallel gradient averaging over ``torch.distributed`` (NCCL over NVLink on the GPU
     box, gloo in the CPU tests): one all-reduce of the flat gradient buffer.
 
-STATUS: written at the end of round 1 after the GPU budget was spent — compiled, CPU-side logic tested, NOT yet run on a
-B200.  The GPU tests (tests/test_bwd_ops.py, tests/test_train.py) are skipped unless MAED_B200_TRAIN_TESTS=1.
+Several forwards may be outstanding before one backward (the reference's stage-2 iteration runs the video batch and the
+image batch through the model, then ONE ``loss.backward()``: lib/core/trainer.py:186-202): every forward owns its tape
+workspace (``TapePool``), and a backward that finds gradients already present accumulates instead of overwriting
+(``TrainState.grad_targets``), so ``zero_grad(set_to_none=False)`` and micro-batch accumulation behave as with any nn.Module.
 """
 import ctypes as C
 
@@ -139,17 +141,74 @@ def decode_outputs(pose6d, shape, cam, n_joints=49, smpl_head=None, J_regressor=
 
 
 # --------------------------------------------------------------------------------------------- engine state
+class TapePool:
+    """Tape workspaces of the outstanding training forwards.  A forward takes the smallest free buffer that fits (or
+    allocates one); its autograd node holds it through a `_Tape` and returns it after the backward — or when the graph is
+    dropped without a backward (`_Tape.__del__`).  At most `keep` idle buffers stay cached."""
+
+    def __init__(self, keep=2):
+        self.free, self.keep = [], keep
+
+    def take(self, nbytes, dev):
+        best = None
+        for i, t in enumerate(self.free):
+            if t.numel() >= nbytes and t.device == dev and (best is None or t.numel() < self.free[best].numel()):
+                best = i
+        if best is not None:
+            return self.free.pop(best)
+        self.free = [t for t in self.free if t.device == dev]        # stale devices / too small: let them go first
+        if len(self.free) >= self.keep:
+            self.free.pop(0)
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+    def give(self, t):
+        if len(self.free) < self.keep:
+            self.free.append(t)
+
+
+class _Tape:
+    def __init__(self, pool, ws):
+        self.pool, self.ws = pool, ws
+
+    def release(self):
+        if self.ws is not None:
+            self.pool.give(self.ws)
+            self.ws = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def _mix64(*vals):
+    """splitmix64-style hash of a few integers -> dropout seed (steps, ranks and models get unrelated mask streams)."""
+    h = 0x9E3779B97F4A7C15
+    for v in vals:
+        h = (h ^ (int(v) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+        h = (h + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        h = ((h ^ (h >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        h = ((h ^ (h >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        h ^= h >> 31
+    return h
+
+
 class TrainState:
-    """Per-model buffers of the training path: flat gradient buffer, derived dgrad weights, tape workspace."""
+    """Per-model buffers of the training path: flat gradient buffer, derived dgrad weights, tape workspaces."""
 
     def __init__(self, model):
         self.model = model
         self.flat_grad = None
+        self.spares = []                  # [(flat buffer, pointer array)]: targets of backwards that must not touch flat_grad
+        self.in_flight = set()            # handed to autograd, not yet accumulated (0 = flat_grad, k = spares[k - 1])
+        self._sentinel = None
+        self._sentinel_handle = None
         self.grad_offsets = None
         self.grad_ptrs = None
         self.tpack = None
         self.tpack_key = None
-        self.workspace = None
+        self.tapes = TapePool()
         self.loss_scale = 4096.0
         self.step_seed = 0
         self._exchange = None
@@ -179,23 +238,94 @@ class TrainState:
             _lib.call("maed_train_set_exchange", model._engine, _lib.EXCHANGE_FN(0), None, None, 0)
             self._exchange = None
 
-    def ensure_grads(self, tensors, is_param=None):
-        """(Re)allocates the flat gradient buffer (engine table order, every PARAMETER padded to 4 elements; buffers of the
-        table — the BatchNorm running statistics of encoder='cnn' — get no slot and a NULL pointer) and returns FRESH views of
-        it (None for buffers): autograd's AccumulateGrad adopts a gradient tensor nobody else references instead of cloning
-        it, so ``p.grad`` aliases the flat buffer (one all-reduce / one Adam launch covers everything)."""
+    def _layout(self, tensors, is_param):
+        """(Re)allocates the flat gradient buffer: engine table order, every PARAMETER padded to 4 elements; buffers of the
+        table — the BatchNorm running statistics of encoder='cnn' — get no slot and a NULL pointer."""
         dev = tensors[0].device
-        is_param = is_param if is_param is not None else [True] * len(tensors)
         total = sum((t.numel() + 3) // 4 * 4 for t, p in zip(tensors, is_param) if p)
         if self.flat_grad is None or self.flat_grad.numel() != total or self.flat_grad.device != dev:
             self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.spares = []
+            self.in_flight.clear()
             self.grad_offsets, off = [], 0
             for t, p in zip(tensors, is_param):
                 self.grad_offsets.append(off if p else None)
                 off += (t.numel() + 3) // 4 * 4 if p else 0
-            base = self.flat_grad.data_ptr()
-            self.grad_ptrs = (C.c_void_p * len(tensors))(*[None if o is None else base + 4 * o for o in self.grad_offsets])
-        return [None if o is None else self.flat_grad[o:o + t.numel()].view(t.shape) for o, t in zip(self.grad_offsets, tensors)]
+            self.grad_ptrs = self._ptr_array(self.flat_grad)
+
+    def _ptr_array(self, flat):
+        base = flat.data_ptr()
+        return (C.c_void_p * len(self.grad_offsets))(*[None if o is None else base + 4 * o for o in self.grad_offsets])
+
+    def _views(self, flat, tensors):
+        return [None if o is None else flat[o:o + t.numel()].view(t.shape) for o, t in zip(self.grad_offsets, tensors)]
+
+    def grad_targets(self, tensors, is_param, params):
+        """Where this backward writes, and what it hands to autograd: (pointer array for the engine, gradient tensors in
+        table order or None, buffer to add the result into or None).
+
+        Normal step (no gradient present on any parameter, nothing parked): the engine writes the flat buffer itself and
+        autograd receives FRESH views of it — AccumulateGrad adopts a gradient tensor nobody else references instead of
+        cloning it, so ``p.grad`` aliases the flat buffer (one all-reduce / one Adam launch covers all 72 M parameters).
+        Otherwise the engine writes a spare flat buffer:
+          * a further forward's node in the same backward pass (the reference's video + image iteration): the first node's
+            views are still parked in autograd's input buffers (``in_flight``; a post-accumulate hook on one sentinel
+            parameter tells when they have been consumed).  The spare is added to the parked buffer on the device (one
+            launch) and autograd receives no gradients from this node — its own out-of-place summation would detach
+            ``p.grad`` from the flat buffer;
+          * micro-batch accumulation / ``zero_grad(set_to_none=False)``: autograd receives views of the spare and
+            AccumulateGrad adds them to the existing ``p.grad`` in place."""
+        self._layout(tensors, is_param)
+        sentinel = next((p for p in params if p.requires_grad), None)
+        if sentinel is not None and self._sentinel is not sentinel:
+            if self._sentinel_handle is not None:
+                self._sentinel_handle.remove()
+            self._sentinel_handle = sentinel.register_post_accumulate_grad_hook(lambda _p: self.in_flight.clear())
+            self._sentinel = sentinel
+
+        def buffer(k):
+            while k > len(self.spares):
+                buf = torch.zeros_like(self.flat_grad)
+                self.spares.append((buf, self._ptr_array(buf)))
+            return (self.flat_grad, self.grad_ptrs) if k == 0 else self.spares[k - 1]
+
+        if self.in_flight:
+            parked = next(iter(self.in_flight))
+            buf, ptrs = buffer(1 if parked != 1 else 2)
+            return ptrs, None, buffer(parked)[0]
+        k = 0 if all(p.grad is None for p in params) else 1
+        self.in_flight.add(k)
+        buf, ptrs = buffer(k)
+        return ptrs, self._views(buf, tensors), None
+
+    def flatten_grads(self, params_in_table_order):
+        """Re-binds every .grad to its slot of the flat buffer (copying if it lives elsewhere).  No-op in the normal case;
+        needed when autograd had to sum out of place (p.grad is then an ordinary tensor).  False if a gradient is missing."""
+        if self.grads_are_flat(params_in_table_order):
+            return True
+        if self.flat_grad is None or any(p.grad is None for p in params_in_table_order):
+            return False
+        offs = [o for o in self.grad_offsets if o is not None]
+        if len(offs) != len(params_in_table_order):
+            return False
+        with torch.no_grad():
+            for p, o in zip(params_in_table_order, offs):
+                v = self.flat_grad[o:o + p.numel()].view(p.shape)
+                if p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad)
+                    p.grad = v
+        return True
+
+    def grads_are_flat(self, params_in_table_order):
+        """True when every parameter's .grad is the view of the flat buffer at its slot (what FusedAdam's one-launch step and
+        the one-call all-reduce rely on)."""
+        if self.flat_grad is None:
+            return False
+        base = self.flat_grad.data_ptr()
+        offs = [o for o in self.grad_offsets if o is not None]
+        if len(offs) != len(params_in_table_order):
+            return False
+        return all(p.grad is not None and p.grad.data_ptr() == base + 4 * o for p, o in zip(params_in_table_order, offs))
 
     def ensure_tpack(self, eng, params_arr, key, dev):
         lib = _lib.load()
@@ -206,12 +336,16 @@ class TrainState:
             _lib.call("maed_train_pack", eng, params_arr, _lib.ptr(self.tpack), _lib.stream_ptr())
             self.tpack_key = key
 
-    def ensure_workspace(self, eng, n_frames, dev):
-        nbytes = _lib.load().maed_train_workspace_bytes(eng, n_frames)
-        if self.workspace is None or self.workspace.numel() < nbytes or self.workspace.device != dev:
-            self.workspace = None                       # release before the (large) re-allocation
-            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        return self.workspace
+
+def _rank():
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def _weights_key(model, params):
+    """Changes whenever a parameter is written: autograd's version counters (torch optimisers, in-place edits) plus the
+    counter FusedAdam bumps (its kernel writes parameter memory behind those counters)."""
+    return (getattr(model, "_weights_gen", 0), sum(p._version for p in params))
 
 
 class MaedTrainFunction(torch.autograd.Function):
@@ -228,44 +362,60 @@ class MaedTrainFunction(torch.autograd.Function):
             # counters, so the key can repeat although the weights changed (invalidate_cache() forces a re-pack)
             st.ensure_tpack(eng, model._param_ptrs, model._pack_gen, dev)
             st.ensure_exchange(model, dev)
-            ws = st.ensure_workspace(eng, N * T, dev)
+            nbytes = _lib.load().maed_train_workspace_bytes(eng, N * T)
+            tape = _Tape(st.tapes, st.tapes.take(nbytes, dev))          # this forward's own tape (see TapePool)
             f32 = dict(dtype=torch.float32, device=dev)
             pose = torch.empty(N * T, 144, **f32)
             shape = torch.empty(N * T, 10, **f32)
             cam = torch.empty(N * T, 3, **f32)
             outs = _lib.MaedTrainOutputs(None, _lib.ptr(pose), _lib.ptr(shape), _lib.ptr(cam))
             st.step_seed += 1
-            seed = (int(torch.initial_seed()) * 1000003 + st.step_seed) & 0xFFFFFFFFFFFFFFFF
-            _lib.call("maed_train_forward", eng, model._param_ptrs, _lib.ptr(model._packed), _lib.ptr(x), N, T, _lib.ptr(ws),
-                      C.c_size_t(ws.numel()), C.c_float(dropout_p), C.c_ulonglong(seed), C.byref(outs), _lib.stream_ptr())
+            st.in_flight.clear()                        # no backward pass is running while a forward is being recorded
+            seed = _mix64(torch.initial_seed(), st.step_seed, _rank())   # per step AND per data-parallel rank
+            _lib.call("maed_train_forward", eng, model._param_ptrs, _lib.ptr(model._packed), _lib.ptr(x), N, T, _lib.ptr(tape.ws),
+                      C.c_size_t(tape.ws.numel()), C.c_float(dropout_p), C.c_ulonglong(seed), C.byref(outs), _lib.stream_ptr())
         ctx.model, ctx.x, ctx.dropout_p, ctx.n_params = model, x, dropout_p, len(params)
-        ctx.tape_id = st.step_seed
+        ctx.tape, ctx.weights_key = tape, _weights_key(model, params)
         return pose, shape, cam
 
     @staticmethod
     def backward(ctx, d_pose, d_shape, d_cam):
-        model, x = ctx.model, ctx.x
+        model, x, tape = ctx.model, ctx.x, ctx.tape
         st = model._train_state
-        if ctx.tape_id != st.step_seed:
-            raise RuntimeError("maed_b200: backward() after another training forward of the same model — the engine keeps "
-                               "ONE activation tape per model (no retain_graph / interleaved forwards)")
+        if tape is None or tape.ws is None:
+            raise RuntimeError("maed_b200: backward() a second time through the same forward — the activation tape was "
+                               "released after the first backward (retain_graph is not supported)")
+        if ctx.weights_key != _weights_key(model, [p for _, p in model._train_param_order]):
+            raise RuntimeError("maed_b200: the parameters changed between this forward and its backward (optimizer.step() or "
+                               "an in-place edit): the taped activations no longer match the weights")
         N, T = x.shape[:2]
         dev = x.device
         tensors = model._tensor_table()
         param_names = {n for n, _ in model._train_param_order}
-        views = st.ensure_grads(tensors, [n in param_names for n in model._param_names])
+        params = [p for _, p in model._train_param_order]
+        ptrs, views, add_into = st.grad_targets(tensors, [n in param_names for n in model._param_names], params)
         z = lambda g, n: (torch.zeros(N * T, n, dtype=torch.float32, device=dev) if g is None  # noqa: E731
                           else g.contiguous().float())
         d_pose, d_shape, d_cam = z(d_pose, 144), z(d_shape, 10), z(d_cam, 3)
         with torch.cuda.device(dev):
             _lib.call("maed_train_backward", model._engine, model._param_ptrs, _lib.ptr(model._packed), _lib.ptr(st.tpack),
-                      _lib.ptr(x), N, T, _lib.ptr(st.workspace), C.c_size_t(st.workspace.numel()), _lib.ptr(d_pose),
-                      _lib.ptr(d_shape), _lib.ptr(d_cam), C.c_float(st.loss_scale), C.c_float(ctx.dropout_p), st.grad_ptrs,
+                      _lib.ptr(x), N, T, _lib.ptr(tape.ws), C.c_size_t(tape.ws.numel()), _lib.ptr(d_pose),
+                      _lib.ptr(d_shape), _lib.ptr(d_cam), C.c_float(st.loss_scale), C.c_float(ctx.dropout_p), ptrs,
                       _lib.stream_ptr())
+        tape.release()
+        ctx.tape = None
+        if add_into is not None:                           # a parked buffer of this backward pass collects the sum
+            spare = st.spares[0][0] if ptrs is st.spares[0][1] else st.spares[1][0]
+            add_into.add_(spare)
+            return (None, None, None) + (None,) * ctx.n_params
         by_name = dict(zip(model._param_names, views))
+        accumulate = ptrs is not st.grad_ptrs             # a spare buffer: its views must not become a p.grad
         grads = []
         for name, p in model._train_param_order:
-            grads.append(by_name[name] if p.requires_grad else None)
+            g = by_name[name] if p.requires_grad else None
+            if g is not None and accumulate and p.grad is None:
+                g = g.clone()                           # would be adopted and then overwritten by the next spare write
+            grads.append(g)
         return (None, None, None) + tuple(grads)
 
 
@@ -309,7 +459,11 @@ class FusedAdam(torch.optim.Optimizer):
     (``[{'params': p, 'name': n} ...]``).  With ``FusedAdam.for_model(model, ...)`` the parameters are flattened into
     one buffer laid out like the engine's flat gradient buffer and the whole step is ONE kernel launch; otherwise one
     launch per parameter tensor.  Pass ``model=`` so the packed tensor-core weights are re-derived after the step
-    (the kernel writes parameter memory behind autograd's version counters)."""
+    (the kernel writes parameter memory behind autograd's version counters).
+
+    ``state_dict()`` / ``load_state_dict()`` use torch.optim.Adam's layout (per parameter ``step``, ``exp_avg``,
+    ``exp_avg_sq``), so the reference's checkpoints resume here and vice versa (lib/core/trainer.py:335,359); in the flat
+    mode the per-parameter moments are views of the flat moment buffers."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, model=None):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
@@ -319,45 +473,103 @@ class FusedAdam(torch.optim.Optimizer):
     @classmethod
     def for_model(cls, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         """Flattens the model's parameters (engine order, each padded to a multiple of 4 elements — the layout of
-        TrainState.flat_grad) and builds the single-launch optimiser."""
+        TrainState.flat_grad) and builds the single-launch optimiser.  Call it AFTER ``model.to(device)``: moving the
+        module afterwards re-allocates the parameters outside the flat buffer (``step()`` checks and says so)."""
         model._get_engine()
         tensors = model._tensor_table()
         # parameters only, in engine table order: the table of encoder='cnn' interleaves BatchNorm running buffers with the
-        # parameters, and Adam (weight decay!) must not touch those — same filter as TrainState.ensure_grads
-        param_names = {n for n, _ in model.named_parameters()}
-        tensors = [t for t, n in zip(tensors, model._param_names) if n in param_names]
-        total = sum((t.numel() + 3) // 4 * 4 for t in tensors)
+        # parameters, and Adam (weight decay!) must not touch those — same filter as TrainState.grad_targets
+        named = dict(model.named_parameters())
+        names = [n for n in model._param_names if n in named]
+        params = [named[n] for n in names]
+        total = sum((p.numel() + 3) // 4 * 4 for p in params)
         flat = torch.zeros(total, dtype=torch.float32, device=tensors[0].device)
-        off = 0
+        offsets, off = [], 0
         with torch.no_grad():
-            for t in tensors:
-                n = t.numel()
-                flat[off:off + n].copy_(t.reshape(-1))
-                t.data = flat[off:off + n].view(t.shape)
+            for p in params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.reshape(-1))
+                p.data = flat[off:off + n].view(p.shape)
+                offsets.append(off)
                 off += (n + 3) // 4 * 4
         model.invalidate_cache()
         opt = cls([{"params": p, "name": n} for n, p in model.named_parameters()], lr=lr, betas=betas, eps=eps,
                   weight_decay=weight_decay, model=model)
-        opt._flat = {"p": flat, "m": torch.zeros_like(flat), "v": torch.zeros_like(flat), "step": 0}
+        opt._flat = {"p": flat, "m": torch.zeros_like(flat), "v": torch.zeros_like(flat), "step": 0, "params": params,
+                     "offsets": offsets}
+        opt._bind_flat_state()
         return opt
+
+    def _bind_flat_state(self):
+        """Optimizer.state[p] = views of the flat moment buffers (what state_dict() serialises)."""
+        f = self._flat
+        for p, off in zip(f["params"], f["offsets"]):
+            n = p.numel()
+            self.state[p] = {"step": torch.tensor(float(f["step"])), "exp_avg": f["m"][off:off + n].view(p.shape),
+                             "exp_avg_sq": f["v"][off:off + n].view(p.shape)}
+
+    def state_dict(self):
+        if self._flat is not None:
+            for p in self._flat["params"]:
+                self.state[p]["step"] = torch.tensor(float(self._flat["step"]))
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)             # replaces self.state by copies of the loaded tensors
+        f = self._flat
+        if f is None:
+            for s in self.state.values():
+                if "step" in s:
+                    s["step"] = int(float(s["step"]))
+            return
+        steps = set()
+        with torch.no_grad():
+            for p, off in zip(f["params"], f["offsets"]):
+                s = self.state.get(p)
+                if not s:
+                    continue
+                n = p.numel()
+                f["m"][off:off + n].copy_(s["exp_avg"].reshape(-1))
+                f["v"][off:off + n].copy_(s["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(s["step"])))
+        if len(steps) > 1:
+            raise RuntimeError("FusedAdam (flat): the loaded per-parameter step counts differ: %s" % sorted(steps))
+        f["step"] = steps.pop() if steps else 0
+        self._bind_flat_state()
 
     def _kernel(self, p, g, m, v, n, group, step, grad_scale):
         b1, b2 = group["betas"]
         with torch.cuda.device(p.device):
             _lib.call("maed_adam_step", _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), C.c_longlong(n),
-                      C.c_float(group["lr"]), C.c_float(b1), C.c_float(b2), C.c_float(group["eps"]),
-                      C.c_float(group["weight_decay"]), step, C.c_float(grad_scale), _lib.stream_ptr())
+                      C.c_double(group["lr"]), C.c_double(b1), C.c_double(b2), C.c_double(group["eps"]),
+                      C.c_double(group["weight_decay"]), step, C.c_float(grad_scale), _lib.stream_ptr())
+
+    def _flat_ready(self, st):
+        """The one-launch path needs (a) every parameter still inside the flat parameter buffer, (b) every .grad the view of
+        the engine's flat gradient buffer at the same offset, (c) one set of hyper-parameters."""
+        f = self._flat
+        base = f["p"].data_ptr()
+        if any(p.data_ptr() != base + 4 * o for p, o in zip(f["params"], f["offsets"])):
+            raise RuntimeError("FusedAdam.for_model: the model's parameters no longer live in the optimiser's flat buffer "
+                               "(model.to()/.cuda()/load of new tensors after for_model?) — build the optimiser after moving "
+                               "the model")
+        if st is None or not st.flatten_grads(f["params"]):
+            return False
+        g0 = self.param_groups[0]
+        key = lambda g: (g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"])  # noqa: E731
+        return all(key(g) == key(g0) for g in self.param_groups)
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale=1.0):
         loss = closure() if closure is not None else None
         st = getattr(self._model, "_train_state", None) if self._model is not None else None
-        if self._flat is not None and st is not None and st.flat_grad is not None \
-                and st.flat_grad.numel() == self._flat["p"].numel():
+        if self._flat is not None and self._flat_ready(st):
             f = self._flat
             f["step"] += 1
             self._kernel(f["p"], st.flat_grad, f["m"], f["v"], f["p"].numel(), self.param_groups[0], f["step"], grad_scale)
         else:
+            if self._flat is not None:
+                self._flat["step"] += 1
             for group in self.param_groups:
                 for p in group["params"]:
                     if p.grad is None:
@@ -367,10 +579,12 @@ class FusedAdam(torch.optim.Optimizer):
                     s = self.state[p]
                     if not s:
                         s["step"], s["exp_avg"], s["exp_avg_sq"] = 0, torch.zeros_like(p), torch.zeros_like(p)
-                    s["step"] += 1
+                    step = self._flat["step"] if self._flat is not None else int(float(s["step"])) + 1
+                    s["step"] = step
                     g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                    self._kernel(p, g, s["exp_avg"], s["exp_avg_sq"], p.numel(), group, s["step"], grad_scale)
+                    self._kernel(p, g, s["exp_avg"], s["exp_avg_sq"], p.numel(), group, step, grad_scale)
         if self._model is not None:
+            self._model._weights_gen = getattr(self._model, "_weights_gen", 0) + 1
             self._model.invalidate_cache()
         return loss
 
@@ -383,7 +597,8 @@ def allreduce_gradients(model, world_size=None):
         return
     ws = world_size or dist.get_world_size()
     st = getattr(model, "_train_state", None)
-    if st is not None and st.flat_grad is not None:
+    order = getattr(model, "_train_param_order", None)
+    if st is not None and order is not None and st.flatten_grads([p for _, p in order]):
         dist.all_reduce(st.flat_grad)
         st.flat_grad.div_(ws)
         return

@@ -1,9 +1,9 @@
 """TEST INFRASTRUCTURE ONLY — imports the UNMODIFIED reference (`/root/reference/lib/models`) on CPU.
 
-Only usable in the build container (``/root/reference`` does not exist on the GPU box).  It is used
-by ``tests/golden/make_golden.py`` to generate the committed golden vectors and by
-``tests/test_oracle_vs_reference.py`` (skipped when the reference tree is absent) to pin
-``oracle/maed_oracle.py`` against the reference's own code.
+The tree is ``/root/reference`` in the build container and its verbatim, git-ignored copy ``oracle/_ref/``
+(``oracle/vendor_ref.py``, made by ``__graft_entry__.build()``) on the GPU box.  Used by
+``tests/golden/make_golden*.py`` to generate the committed golden vectors and by ``bench.py --impl reference``
+/ the ``cpu_baseline`` leg to time the reference's own code on the host cores.
 
 The reference cannot be imported as-is on torch 2.11 / offline:
   * ``lib/models/vision_transformer.py:19,23`` import modules removed from torch / torchvision;
@@ -26,7 +26,17 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("MAED_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # oracle/vendor_ref.py (GPU box)
+
+
+def _find_root():
+    for c in (os.environ.get("MAED_REFERENCE_ROOT"), "/root/reference", _VENDORED):
+        if c and os.path.isfile(os.path.join(c, "lib", "models", "maed.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

@@ -346,8 +346,8 @@ def test_adam_matches_torch(L):
     for i, g in enumerate(gs):
         ref.grad = g.clone()
         opt.step()
-        _lib.call("maed_adam_step", _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), C.c_longlong(p.numel()), C.c_float(1e-2),
-                  C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8), C.c_float(1e-3), i + 1, C.c_float(1.0), _lib.stream_ptr())
+        _lib.call("maed_adam_step", _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), C.c_longlong(p.numel()), C.c_double(1e-2),
+                  C.c_double(0.9), C.c_double(0.999), C.c_double(1e-8), C.c_double(1e-3), i + 1, C.c_float(1.0), _lib.stream_ptr())
     assert rel_err(p, ref.detach()) < 1e-6
 
 

@@ -80,8 +80,9 @@ def test_cpu_input_fails_loudly():
         m(torch.zeros(1, 1, 3, 224, 224))
 
 
-def test_train_mode_warns_inference_only():
-    """The backward / train step is not built yet: calling the module in train() mode must say so (loudly)."""
+def test_train_mode_runs_the_training_path_by_default():
+    """train()-mode forwards go to the CUDA training path (no opt-in, like the reference module); on a CPU tensor that path
+    fails loudly as well, and enable_training(False) turns the call into a warned, graph-less inference call."""
     import warnings
     from maed_b200.models import MAED
     m = MAED("ste", 1, 12, "vanilla", "ktd").train()
@@ -89,4 +90,10 @@ def test_train_mode_warns_inference_only():
         warnings.simplefilter("always")
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             m(torch.zeros(1, 1, 3, 224, 224))
-    assert any("inference-only" in str(x.message) for x in w)
+    assert not any("switched off" in str(x.message) for x in w)
+    m.enable_training(False)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m(torch.zeros(1, 1, 3, 224, 224))
+    assert any("switched off" in str(x.message) for x in w)

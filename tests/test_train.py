@@ -175,6 +175,71 @@ def test_fused_adam_matches_torch_adam(lib):
             o.step()
         for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
             assert rel_err(a, b) < tol, (step, k)
+        if step == 1:
+            _check_adam_state_dicts(m1, o1, m2, o2)
+
+
+def _check_adam_state_dicts(m1, o1, m2, o2):
+    """FusedAdam.state_dict() has torch.optim.Adam's layout and content (the reference checkpoints and resumes its optimiser,
+    lib/core/trainer.py:335,359), and load_state_dict() restores the flat moments and the step count."""
+    from maed_b200.train import FusedAdam
+    sd1, sd2 = o1.state_dict(), o2.state_dict()
+    assert len(sd1["state"]) == len(sd2["state"]) == len(list(m1.parameters()))
+    for i in sd2["state"]:
+        a, b = sd1["state"][i], sd2["state"][i]
+        assert float(a["step"]) == float(b["step"]) == 1.0
+        assert rel_err(a["exp_avg"], b["exp_avg"]) < 1e-6 and rel_err(a["exp_avg_sq"], b["exp_avg_sq"]) < 1e-6
+    # torch Adam's checkpoint -> a fresh flat FusedAdam: moments land in the flat buffers, the next step is step 2
+    m3 = _model("vanilla", 6, None)
+    o3 = FusedAdam.for_model(m3, lr=1e-4, weight_decay=1e-5)
+    o3.load_state_dict(sd2)
+    assert o3._flat["step"] == 1
+    assert rel_err(o3._flat["m"], o1._flat["m"]) < 1e-6 and rel_err(o3._flat["v"], o1._flat["v"]) < 1e-6
+    p0 = o3._flat["params"][0]
+    assert o3.state[p0]["exp_avg"].data_ptr() == o3._flat["m"].data_ptr()            # still views of the flat buffers
+    # parameters re-allocated after for_model (model.to() / .cuda()): the one-launch step must refuse, not silently detach
+    p0.data = p0.data.clone()
+    with pytest.raises(RuntimeError, match="no longer live in the optimiser's flat buffer"):
+        o3.step()
+
+
+def test_two_forwards_one_backward_and_gradient_accumulation(lib):
+    """The reference's stage-2 iteration (lib/core/trainer.py:186-202): model(video batch), model(image batch), ONE
+    loss.backward() — every forward keeps its own tape and the second node accumulates.  Then the two other ways a
+    gradient can already be present at backward time: zero_grad(set_to_none=False) and micro-batch accumulation."""
+    m = _model("vanilla", 9, lib)
+    x1, x2 = synth.synth_frames(1, 1, 9).to(DEV), synth.synth_frames(1, 1, 10).to(DEV)
+    P1, P2 = _probes(1, 9), _probes(1, 10)
+    flat = lambda: torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()  # noqa: E731
+    gs = []
+    for x, P in ((x1, P1), (x2, P2)):
+        m.zero_grad(set_to_none=True)
+        _loss(m(x), *P).backward()
+        gs.append(flat())
+    st = m._train_state
+    params = [p for _, p in m._train_param_order]
+    # two outstanding forwards, one backward
+    m.zero_grad(set_to_none=True)
+    o1, o2 = m(x1), m(x2)
+    (_loss(o1, *P1) + _loss(o2, *P2)).backward()
+    assert torch.equal(flat(), gs[0] + gs[1])
+    assert st.grads_are_flat(params)                          # p.grad still aliases the flat buffer after the accumulation
+    # zero_grad(set_to_none=False): gradients present (zeros) -> the backward must ADD, not alias-and-double
+    m.zero_grad(set_to_none=False)
+    _loss(m(x1), *P1).backward()
+    assert torch.equal(flat(), gs[0])
+    # micro-batch accumulation: no zero_grad in between
+    _loss(m(x2), *P2).backward()
+    assert torch.equal(flat(), gs[0] + gs[1])
+    assert st.grads_are_flat(params)
+    # a dropped graph returns its tape to the pool; a second backward through a used graph says so
+    o = m(x1)
+    loss = _loss(o, *P1)
+    loss.backward()
+    with pytest.raises(RuntimeError):
+        loss.backward()
+    del o, loss
+    assert len(st.tapes.free) >= 1
 
 
 def test_short_fit_reduces_loss(lib):
