@@ -223,6 +223,9 @@ int maed_bwd_attention(int kind, const void* qkv_hi, long long qkv_plane, const 
 size_t maed_bwd_wgrad_slab_floats(int Mo, int No, int R);
 int maed_bwd_wgrad_splitk(const void* A, long long a_plane, int lda, const void* B, long long b_plane, int ldb, int Mo, int No,
                           int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, void* stream);
+/* the same on row-major operands: D[Mo, No] (+)= scale * dY[R, Mo]^T X[R, No_x] (MN-major tcgen05 operands, no transposes) */
+int maed_bwd_wgrad_rows(const void* dY, long long dy_plane, int ld_dy, const void* X, long long x_plane, int ld_x, int No_x, int Mo,
+                        int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, void* stream);
 int maed_bwd_split_transposed(const float* w, int N, int K, void* out_hi, long long plane, void* stream);
 /* nn.BatchNorm2d in train() mode over x [M, C] (rows = N*H*W): batch statistics (mean / rstd out; running buffers updated with
  * `momentum` and the unbiased variance when given), y = relu?(xhat * gamma + beta (+ residual planes)) -> planes; when dy is

@@ -122,6 +122,11 @@ size_t splitk_slab_floats(int Mo, int No, int R);
 int gemm_wgrad_splitk(const __half* A, long long a_plane, int lda, const __half* B, long long b_plane, int ldb, int Mo,
                       int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd,
                       cudaStream_t st);
+// the same contraction on row-major operands (no transposed copies): dY [R, Mo] (ld_dy), X [R, No_x] (ld_x), planes;
+// D [Mo, No], No >= No_x a multiple of 32, columns No_x..No are written as zeros
+int gemm_wgrad_rows(const __half* dY, long long dy_plane, int ld_dy, const __half* X, long long x_plane, int ld_x, int No_x,
+                    int Mo, int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd,
+                    cudaStream_t st);
 
 // generic attention backward over `seq` contiguous rows per batch element ('coupling' mode, vision_transformer.py:180-204);
 // stats: batch * heads * seq * 3 floats of scratch

@@ -300,6 +300,11 @@ int maed_bwd_wgrad_splitk(const void* A, long long a_plane, int lda, const void*
   return gemm_wgrad_splitk((const __half*)A, a_plane, lda, (const __half*)B, b_plane, ldb, Mo, No, R, nsplit, scale, accumulate,
                            slabs, D, ldd, (cudaStream_t)stream);
 }
+int maed_bwd_wgrad_rows(const void* dY, long long dy_plane, int ld_dy, const void* X, long long x_plane, int ld_x, int No_x, int Mo,
+                        int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, void* stream) {
+  return gemm_wgrad_rows((const __half*)dY, dy_plane, ld_dy, (const __half*)X, x_plane, ld_x, No_x, Mo, No, R, nsplit, scale,
+                         accumulate, slabs, D, ldd, (cudaStream_t)stream);
+}
 int maed_bwd_split_transposed(const float* w, int N, int K, void* out_hi, long long plane, void* stream) {
   return split_f32_transposed(w, N, K, (__half*)out_hi, plane, (cudaStream_t)stream);
 }

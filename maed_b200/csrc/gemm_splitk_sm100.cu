@@ -1,6 +1,12 @@
 // Split-K tcgen05 GEMM for the weight gradients of the MAED training path.
 //
-//   D[Mo, No] (+)= scale * sum_r A[Mo, r] * B[No, r]          A = dY^T, B = X^T (planes, r contiguous)
+//   D[Mo, No] (+)= scale * sum_r A[Mo, r] * B[No, r]          A = dY^T, B = X^T (planes)
+//
+// Two operand layouts: `gemm_wgrad_splitk` takes A and B with r contiguous (K-major UMMA operands, the forward GEMM's layout);
+// `gemm_wgrad_rows` (MN = true) takes dY [R, Mo] and X [R, No] as the training tape holds them — rows = r — and feeds them to
+// tcgen05.mma as MN-major operands (instruction-descriptor transpose bits, 64 x 64 TMA boxes whose 128-byte swizzled rows hold
+// 64 consecutive output rows / columns of one r), so the weight gradients need no transposed copies of dY and X
+// (round 2: `transpose_planes` was 11 % of the train step).
 //
 // The reduction dimension r is the number of activation rows (25 216 tokens ... 1.6 M stem pixels) while Mo x No is a
 // weight matrix of at most a few hundred tiles, so the K loop is cut into `S` slices: tile index = (slice, m, n), every
@@ -29,7 +35,7 @@ struct SplitKParams {
 
 constexpr int kBM = 128, kBK = 64, kThreads = 256, kStagesMax = 8;
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SplitKParams p) {
   using namespace sm100;
@@ -81,8 +87,17 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* sB = sA + nplanes * kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], nplanes * (kABytes + kBBytes));
           for (int pl = 0; pl < nplanes; ++pl) {
-            tma_load_3d(sA + pl * kABytes, &tmA, &full_bar[stage], kb * kBK, m_tile * kBM, pl);
-            tma_load_3d(sB + pl * kBBytes, &tmB, &full_bar[stage], kb * kBK, n_tile * BLOCK_N, pl);
+            if (MN) {       // [64-wide MN block][64 rows of r][128 B]: 8 KB per block, the layout umma_desc_mn_sw128 describes
+#pragma unroll
+              for (int mb = 0; mb < kBM / 64; ++mb)
+                tma_load_3d(sA + pl * kABytes + mb * 8192, &tmA, &full_bar[stage], m_tile * kBM + mb * 64, kb * kBK, pl);
+#pragma unroll
+              for (int nb = 0; nb < BLOCK_N / 64; ++nb)
+                tma_load_3d(sB + pl * kBBytes + nb * 8192, &tmB, &full_bar[stage], n_tile * BLOCK_N + nb * 64, kb * kBK, pl);
+            } else {
+              tma_load_3d(sA + pl * kABytes, &tmA, &full_bar[stage], kb * kBK, m_tile * kBM, pl);
+              tma_load_3d(sB + pl * kBBytes, &tmB, &full_bar[stage], kb * kBK, n_tile * BLOCK_N, pl);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -90,7 +105,12 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_f16(kBM, BLOCK_N, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(kBM, BLOCK_N, 0, MN ? 1 : 0, MN ? 1 : 0);
+      // operand descriptor of the k-th 16-deep K step of a stage: K-major = 32 bytes along the 128-byte rows; MN-major = 16
+      // rows of r (two 8-row swizzle atoms, SBO = 1024 B), 64-wide MN blocks 8 KB apart (LBO)
+      auto desc = [](uint32_t base, int k) -> uint64_t {
+        return MN ? umma_desc_mn_sw128(base + k * 2048, 8192, 1024) : umma_desc_k_sw128(base + k * 32);
+      };
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -109,12 +129,12 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t bH = aH + nplanes * kABytes;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t da = umma_desc_k_sw128(aH + k * 32);
-            const uint64_t db = umma_desc_k_sw128(bH + k * 32);
+            const uint64_t da = desc(aH, k);
+            const uint64_t db = desc(bH, k);
             umma_f16(d_tmem, da, db, idesc, (kb != kb0) || (k != 0));
             if (p.nsplit == 3) {
-              const uint64_t dal = umma_desc_k_sw128(aH + kABytes + k * 32);
-              const uint64_t dbl = umma_desc_k_sw128(bH + kBBytes + k * 32);
+              const uint64_t dal = desc(aH + kABytes, k);
+              const uint64_t dbl = desc(bH + kBBytes, k);
               umma_f16(d_tmem, dal, db, idesc, 1);
               umma_f16(d_tmem, da, dbl, idesc, 1);
             }
@@ -193,15 +213,42 @@ SliceChoice choose_slices(int Mo, int No, int R) {
   return c;
 }
 
-template <int BN>
+template <int BN, bool MN>
 int launch_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, const SplitKParams& p, int grid, size_t smem,
                   cudaStream_t st) {
   static size_t attr = 0;
   if (smem > attr) {
-    MAED_CUDA_CHECK(cudaFuncSetAttribute(gemm_splitk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MAED_CUDA_CHECK(cudaFuncSetAttribute(gemm_splitk_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  gemm_splitk_kernel<BN><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  gemm_splitk_kernel<BN, MN><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  MAED_BW_LAUNCH_CHECK();
+  return MAED_OK;
+}
+
+// shared tail of the two entry points: slicing, launch, ordered slab reduction
+template <bool MN>
+int run_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, const SliceChoice& c, int Mo, int No, int nsplit, float scale,
+               int accumulate, float* slabs, float* D, int ldd, cudaStream_t st) {
+  const int np = nsplit == 3 ? 2 : 1;
+  SplitKParams p;
+  p.M = Mo; p.N = No; p.num_k_blocks = c.nkb; p.kb_per_slice = c.kb_per; p.slices = c.slices; p.nsplit = nsplit;
+  p.m_tiles = c.m_tiles; p.n_tiles = c.n_tiles; p.slabs = slabs;
+  const size_t stage_bytes = (size_t)np * (kBM * kBK * 2 + c.block_n * kBK * 2);
+  int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+  if (stages > kStagesMax) stages = kStagesMax;
+  MAED_CHECK_ARG(stages >= 2, "gemm_wgrad_splitk: tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = 1024 + stages * stage_bytes + 256;
+  const int tiles = c.m_tiles * c.n_tiles * c.slices;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  int rc;
+  if (c.block_n == 256) rc = launch_splitk<256, MN>(tmA, tmB, p, grid, smem, st);
+  else if (c.block_n == 128) rc = launch_splitk<128, MN>(tmA, tmB, p, grid, smem, st);
+  else rc = launch_splitk<64, MN>(tmA, tmB, p, grid, smem, st);
+  MAED_PROPAGATE(rc);
+  const long long mn = (long long)Mo * No;
+  splitk_reduce_kernel<<<bw::grid_for(mn, 256), 256, 0, st>>>(slabs, c.slices, mn, No, scale, accumulate, D, ldd);
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
 }
@@ -244,26 +291,38 @@ int gemm_wgrad_splitk(const __half* A, long long a_plane, int lda, const __half*
     const uint32_t box[3] = {(uint32_t)kBK, (uint32_t)c.block_n, 1};
     MAED_PROPAGATE(make_tmap_f16(&tmB, B, 3, dims, str, box));
   }
-  SplitKParams p;
-  p.M = Mo; p.N = No; p.num_k_blocks = c.nkb; p.kb_per_slice = c.kb_per; p.slices = c.slices; p.nsplit = nsplit;
-  p.m_tiles = c.m_tiles; p.n_tiles = c.n_tiles; p.slabs = slabs;
-  const size_t stage_bytes = (size_t)np * (kBM * kBK * 2 + c.block_n * kBK * 2);
-  int stages = (int)((227 * 1024 - 2048) / stage_bytes);
-  if (stages > kStagesMax) stages = kStagesMax;
-  MAED_CHECK_ARG(stages >= 2, "gemm_wgrad_splitk: tile does not fit shared memory");
-  p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + 256;
-  const int tiles = c.m_tiles * c.n_tiles * c.slices;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  int rc;
-  if (c.block_n == 256) rc = launch_splitk<256>(tmA, tmB, p, grid, smem, st);
-  else if (c.block_n == 128) rc = launch_splitk<128>(tmA, tmB, p, grid, smem, st);
-  else rc = launch_splitk<64>(tmA, tmB, p, grid, smem, st);
-  MAED_PROPAGATE(rc);
-  const long long mn = (long long)Mo * No;
-  splitk_reduce_kernel<<<bw::grid_for(mn, 256), 256, 0, st>>>(slabs, c.slices, mn, No, scale, accumulate, D, ldd);
-  MAED_BW_LAUNCH_CHECK();
-  return MAED_OK;
+  return run_splitk<false>(tmA, tmB, c, Mo, No, nsplit, scale, accumulate, slabs, D, ldd, st);
+}
+
+// Same contraction on the operands as the tape holds them: dY [R, Mo] (row stride ld_dy), X [R, No_x] (row stride ld_x), both
+// fp16 hi/lo planes; D [Mo, No] with No >= No_x a multiple of 32 — columns No_x..No of D come out as zeros (TMA zero-fills the
+// out-of-range part of a box; used for the stem's 152 -> 160 columns).
+int gemm_wgrad_rows(const __half* dY, long long dy_plane, int ld_dy, const __half* X, long long x_plane, int ld_x, int No_x,
+                    int Mo, int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd,
+                    cudaStream_t st) {
+  MAED_CHECK_ARG(dY && X && slabs && D, "gemm_wgrad_rows: null argument");
+  MAED_CHECK_ARG(Mo >= 1 && No >= 32 && No % 32 == 0 && R >= 1 && No_x >= 1 && No_x <= No,
+                 "gemm_wgrad_rows: bad shape Mo=%d No=%d (%d) R=%d", Mo, No, No_x, R);
+  MAED_CHECK_ARG(ld_dy % 8 == 0 && ld_x % 8 == 0 && ld_dy >= Mo && ld_x >= No_x, "gemm_wgrad_rows: row strides must be multiples "
+                 "of 8 and cover the rows (ld_dy=%d Mo=%d ld_x=%d No=%d)", ld_dy, Mo, ld_x, No_x);
+  MAED_CHECK_ARG(nsplit == 1 || nsplit == 3, "gemm_wgrad_rows: nsplit must be 1 or 3");
+  MAED_CHECK_ARG(ldd >= No, "gemm_wgrad_rows: ldd=%d < No=%d", ldd, No);
+  const int np = nsplit == 3 ? 2 : 1;
+  SliceChoice c = choose_slices(Mo, No, R);
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[3] = {(uint64_t)Mo, (uint64_t)R, (uint64_t)np};
+    const uint64_t str[2] = {(uint64_t)ld_dy * 2, (uint64_t)(np == 2 ? dy_plane : (long long)R * ld_dy) * 2};
+    const uint32_t box[3] = {64, (uint32_t)kBK, 1};
+    MAED_PROPAGATE(make_tmap_f16(&tmA, dY, 3, dims, str, box));
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)No_x, (uint64_t)R, (uint64_t)np};
+    const uint64_t str[2] = {(uint64_t)ld_x * 2, (uint64_t)(np == 2 ? x_plane : (long long)R * ld_x) * 2};
+    const uint32_t box[3] = {64, (uint32_t)kBK, 1};
+    MAED_PROPAGATE(make_tmap_f16(&tmB, X, 3, dims, str, box));
+  }
+  return run_splitk<true>(tmA, tmB, c, Mo, No, nsplit, scale, accumulate, slabs, D, ldd, st);
 }
 
 }  // namespace maed

@@ -31,7 +31,6 @@ namespace maed {
 namespace {
 
 size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
-int ld8(long long r) { return (int)((r + 7) / 8 * 8); }
 
 // ------------------------------------------------------------------------------------ backbone layer table
 struct ConvL {
@@ -131,8 +130,6 @@ struct TrainWs {
   // ---- scratch shared by forward and backward
   __half* col; long long col_plane;              // im2col matrix / small planes
   __half* pl_a; long long pl_a_plane;            // generic planes (max rows*3072 or M*C)
-  __half* pl_t; long long pl_t_plane;            // transposed planes of a gradient
-  __half* pl_x; long long pl_x_plane;            // transposed planes of an activation / im2col matrix
   __half* dil; long long dil_plane;
   float* fa; float* fb; float* fc; float* fd;    // fp32 activation-gradient buffers (backbone size)
   float* big;                                    // fp32 [rows, 3072]
@@ -154,7 +151,7 @@ void carve(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& w) {
   auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off = align_up(off + bytes); return p; };
   const int nl = (int)net.L.size();
   w.out.resize(nl); w.convout.resize(nl); w.stats.resize(nl); w.out_plane.resize(nl);
-  long long max_mc = 0, max_col = 0, max_xt = 0, max_slab = 0, max_wg = 0;
+  long long max_mc = 0, max_col = 0, max_slab = 0, max_wg = 0;
   for (int l = 0; l < nl; ++l) {
     const ConvL& L = net.L[l];
     const long long Mo = L.Mout(BT);
@@ -167,8 +164,6 @@ void carve(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& w) {
     const int kc = (l == 0) ? kStemKPad : L.Kcols();
     const int kc_pad = (kc + 31) / 32 * 32;
     if (L.k > 1 || L.stride > 1) max_col = max_ll(max_col, Mo * kc);
-    max_xt = max_ll(max_xt, (long long)kc_pad * ld8(Mo));
-    max_xt = max_ll(max_xt, (long long)L.Cout * ld8(Mo));
     max_slab = max_ll(max_slab, (long long)splitk_slab_floats(L.Cout, kc_pad, (int)Mo));
     max_wg = max_ll(max_wg, (long long)L.Cout * kc_pad);
   }
@@ -218,13 +213,9 @@ void carve(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& w) {
   }
   // ---- scratch
   const long long ste_big = rows * 4 * C;                                   // rows x 3072
-  max_xt = max_ll(max_xt, (long long)4 * C * ld8(rows));
-  max_xt = max_ll(max_xt, 1024LL * ld8((long long)BT * 196));
   const long long pl_elems = max_ll(max_mc, ste_big);
   w.col_plane = max_ll(max_col, 8); w.col = (__half*)take((size_t)w.col_plane * 4);
   w.pl_a_plane = pl_elems; w.pl_a = (__half*)take((size_t)pl_elems * 4);
-  w.pl_t_plane = max_xt; w.pl_t = (__half*)take((size_t)max_xt * 4);
-  w.pl_x_plane = max_xt; w.pl_x = (__half*)take((size_t)max_xt * 4);
   w.dil_plane = max_mc; w.dil = (__half*)take((size_t)max_mc * 4);
   w.fa = (float*)take((size_t)max_mc * 4);
   w.fb = (float*)take((size_t)max_mc * 4);
@@ -305,7 +296,7 @@ void carve_cnn(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& 
   const int nl = (int)net.L.size();
   w.out.resize(nl); w.convout.resize(nl); w.stats.assign(nl, nullptr); w.out_plane.resize(nl);
   w.bn_mean.resize(nl); w.bn_rstd.resize(nl);
-  long long max_mc = 0, max_col = 0, max_xt = 0, max_slab = 0, max_wg = 0;
+  long long max_mc = 0, max_col = 0, max_slab = 0, max_wg = 0;
   size_t max_partial = 0;
   for (int l = 0; l < nl; ++l) {
     const ConvL& L = net.L[l];
@@ -320,8 +311,6 @@ void carve_cnn(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& 
     const int kc = (l == 0) ? kStemKPad : L.Kcols();
     const int kc_pad = (kc + 31) / 32 * 32;
     if (L.k > 1 || L.stride > 1) max_col = max_ll(max_col, Mo * kc);
-    max_xt = max_ll(max_xt, (long long)kc_pad * ld8(Mo));
-    max_xt = max_ll(max_xt, (long long)L.Cout * ld8(Mo));
     max_slab = max_ll(max_slab, (long long)splitk_slab_floats(L.Cout, kc_pad, (int)Mo));
     max_wg = max_ll(max_wg, (long long)L.Cout * kc_pad);
     max_partial = std::max(max_partial, bn_scratch_doubles(Mo, L.Cout));
@@ -348,8 +337,6 @@ void carve_cnn(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& 
   }
   w.col_plane = max_ll(max_col, 8); w.col = (__half*)take((size_t)w.col_plane * 4);
   w.pl_a_plane = max_mc; w.pl_a = (__half*)take((size_t)max_mc * 4);
-  w.pl_t_plane = max_xt; w.pl_t = (__half*)take((size_t)max_xt * 4);
-  w.pl_x_plane = max_xt; w.pl_x = (__half*)take((size_t)max_xt * 4);
   w.dil_plane = max_mc; w.dil = (__half*)take((size_t)max_mc * 4);
   w.fa = (float*)take((size_t)max_mc * 4);
   w.fb = (float*)take((size_t)max_mc * 4);
@@ -687,12 +674,8 @@ int train_forward(const Engine* ep, const void* const* params, const void* packe
 // dW [Nw, Kw] = scale * dY^T X  for a linear layer; dY, X as planes [R, *] (dense rows)
 static int linear_wgrad(const Ctx& c, const __half* dy, long long dy_plane, int Nw, const __half* x, long long x_plane, int Kw,
                         int R, int accumulate, float* dW) {
-  TrainWs& w = c.w;
-  const int ld = ld8(R);
-  MAED_PROPAGATE(transpose_planes(dy, dy_plane, R, Nw, Nw, w.pl_t, w.pl_t_plane, ld, c.st));
-  MAED_PROPAGATE(transpose_planes(x, x_plane, R, Kw, Kw, w.pl_x, w.pl_x_plane, ld, c.st));
-  return gemm_wgrad_splitk(w.pl_t, w.pl_t_plane, ld, w.pl_x, w.pl_x_plane, ld, Nw, Kw, R, 3, c.inv_ls, accumulate, w.slabs, dW,
-                           Kw, c.st);
+  // MN-major tcgen05 operands straight from the tape: no transposed copies of dY / X (gemm_splitk_sm100.cu)
+  return gemm_wgrad_rows(dy, dy_plane, Nw, x, x_plane, Kw, Kw, Nw, Kw, R, 3, c.inv_ls, accumulate, c.w.slabs, dW, Kw, c.st);
 }
 
 // Backward of one conv + GroupNorm layer.  d_y: gradient w.r.t. the GN output (ReLU mask already applied), fp32
@@ -715,11 +698,9 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
     MAED_PROPAGATE(colsum_f32(w.dgb + L.Cout, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx + 1), c.st));
   }
   // ---- weight gradient: dW_hat [Cout, kc] = dconv^T * im2col(x), then through the weight standardisation
-  const int ld = ld8(Mo);
   const int kc = (l == 0) ? kStemKPad : L.Kcols();
-  const int kc_pad = (kc + 31) / 32 * 32;                  // split-K output width (multiple of 32); extra rows are zero
+  const int kc_pad = (kc + 31) / 32 * 32;                  // split-K output width (multiple of 32); extra columns are zero
   const int pad = L.pad_top();
-  MAED_PROPAGATE(transpose_planes(w.pl_a, w.pl_a_plane, (int)Mo, L.Cout, L.Cout, w.pl_t, w.pl_t_plane, ld, c.st));
   const __half* xm;                                        // [Mo, kc] activation matrix of the wgrad
   long long xm_plane;
   if (l == 0) {
@@ -732,13 +713,10 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
                                L.Hout, L.Hout, w.col, w.col_plane, c.st));
     xm = w.col; xm_plane = w.col_plane;
   }
-  if (kc_pad != kc) {                                      // rows kc..kc_pad of the transposed matrix must read as zeros
-    MAED_CUDA_CHECK(cudaMemsetAsync(w.pl_x + (long long)kc * ld, 0, (size_t)(kc_pad - kc) * ld * 2, c.st));
-    MAED_CUDA_CHECK(cudaMemsetAsync(w.pl_x + w.pl_x_plane + (long long)kc * ld, 0, (size_t)(kc_pad - kc) * ld * 2, c.st));
-  }
-  MAED_PROPAGATE(transpose_planes(xm, xm_plane, (int)Mo, kc, kc, w.pl_x, w.pl_x_plane, ld, c.st));
-  MAED_PROPAGATE(gemm_wgrad_splitk(w.pl_t, w.pl_t_plane, ld, w.pl_x, w.pl_x_plane, ld, L.Cout, kc_pad, (int)Mo, 3, 1.0f, 0,
-                                   w.slabs, w.wg, kc_pad, c.st));
+  // dconv [Mo, Cout] and the activation matrix [Mo, kc] feed the tensor cores as MN-major operands (no transposed copies);
+  // columns kc..kc_pad of dW_hat come out as zeros
+  MAED_PROPAGATE(gemm_wgrad_rows(w.pl_a, w.pl_a_plane, L.Cout, xm, xm_plane, kc, kc, L.Cout, kc_pad, (int)Mo, 3, 1.0f, 0,
+                                 w.slabs, w.wg, kc_pad, c.st));
   if (c.net.bn)                                            // plain conv: only the [Cout][kh][kw][Cin] -> OIHW permute
     MAED_PROPAGATE(wgrad_permute(w.wg, kc_pad, L.Cout, L.Cin, L.k, L.k, c.inv_ls, c.G(L.w_idx), c.st));
   else

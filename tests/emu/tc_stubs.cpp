@@ -425,4 +425,48 @@ int gemm_wgrad_splitk(const __half* A, long long a_plane, int lda, const __half*
   return MAED_OK;
 }
 
+int gemm_wgrad_rows(const __half* dY, long long dy_plane, int ld_dy, const __half* X, long long x_plane, int ld_x, int No_x,
+                    int Mo, int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, cudaStream_t) {
+  Prof prof(4);
+  MAED_CHECK_ARG(dY && X && slabs && D, "gemm_wgrad_rows: null argument");
+  MAED_CHECK_ARG(Mo >= 1 && No >= 32 && No % 32 == 0 && R >= 1 && No_x >= 1 && No_x <= No,
+                 "gemm_wgrad_rows: bad shape Mo=%d No=%d (%d) R=%d", Mo, No, No_x, R);
+  MAED_CHECK_ARG(ld_dy % 8 == 0 && ld_x % 8 == 0 && ld_dy >= Mo && ld_x >= No_x, "gemm_wgrad_rows: row strides must be multiples "
+                 "of 8 and cover the rows (ld_dy=%d Mo=%d ld_x=%d No=%d)", ld_dy, Mo, ld_x, No_x);
+  MAED_CHECK_ARG(nsplit == 1 || nsplit == 3, "gemm_wgrad_rows: nsplit must be 1 or 3");
+  MAED_CHECK_ARG(ldd >= No, "gemm_wgrad_rows: ldd=%d < No=%d", ldd, No);
+  const int np = nsplit == 3 ? 2 : 1;
+  {
+    const uint64_t dims[3] = {(uint64_t)Mo, (uint64_t)R, (uint64_t)np};
+    const uint64_t str[2] = {(uint64_t)ld_dy * 2, (uint64_t)(np == 2 ? dy_plane : (long long)R * ld_dy) * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    MAED_PROPAGATE(check_tmap("wgrad dY", dY, 3, dims, str, box));
+    MAED_CHECK_ARG(np == 1 || dy_plane >= (long long)(R - 1) * ld_dy + Mo, "wgrad: dY planes overlap");
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)No_x, (uint64_t)R, (uint64_t)np};
+    const uint64_t str[2] = {(uint64_t)ld_x * 2, (uint64_t)(np == 2 ? x_plane : (long long)R * ld_x) * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    MAED_PROPAGATE(check_tmap("wgrad X", X, 3, dims, str, box));
+    MAED_CHECK_ARG(np == 1 || x_plane >= (long long)(R - 1) * ld_x + No_x, "wgrad: X planes overlap");
+  }
+  // dense fp32 copies of hi + lo, transposed to [Mo, R] / [No, R] for the shared NT kernel
+  std::vector<float> Yf((size_t)R * Mo), Xf((size_t)R * No_x), At((size_t)Mo * R), Bt((size_t)No * R, 0.f), C((size_t)Mo * No);
+  planes_to_dense(dY, np == 2 ? dy_plane : 0, R, ld_dy, Mo, Yf.data());
+  planes_to_dense(X, np == 2 ? x_plane : 0, R, ld_x, No_x, Xf.data());
+  for (long long r = 0; r < R; ++r) {
+    for (int m = 0; m < Mo; ++m) At[(size_t)m * R + r] = Yf[(size_t)r * Mo + m];
+    for (int n = 0; n < No_x; ++n) Bt[(size_t)n * R + r] = Xf[(size_t)r * No_x + n];
+  }
+  sgemm_nt(Mo, No, R, At.data(), Bt.data(), C.data());
+  for (long long m = 0; m < Mo; ++m)
+    for (int n = 0; n < No; ++n) {
+      const float v = scale * C[(size_t)m * No + n];
+      D[m * ldd + n] = accumulate ? D[m * ldd + n] + v : v;
+    }
+  slabs[0] = 0.f;                              // the real kernel scribbles over the slab scratch
+  count_launch(2);
+  return MAED_OK;
+}
+
 }  // namespace maed

@@ -298,6 +298,24 @@ def test_wgrad_splitk(L, Mo, No, R):
     assert rel_err(D, ref) < 2e-5
 
 
+@pytest.mark.parametrize("Mo,No,No_x,R", [(768, 3072, 3072, 25216), (3072, 768, 768, 25216), (64, 64, 64, 12544), (2304, 768, 768, 1970),
+                                          (64, 160, 152, 25088), (1024, 512, 512, 392), (256, 576, 576, 3136), (192, 96, 72, 70)])
+def test_wgrad_rows(L, Mo, No, No_x, R):
+    """dW = scale * dY^T X on row-major operands (MN-major tcgen05 descriptors): what train.cu calls for every weight gradient."""
+    _lib, ops = L
+    if _is_emu():
+        pytest.skip("tcgen05 split-K kernel: hardware only (the emulator holds a contract stub)")
+    dY, X = _rand(R, Mo, scale=0.05, seed=44), _rand(R, No_x, scale=0.05, seed=45)
+    py, px = _planes(dY, ops), _planes(X, ops)
+    ref = torch.ones(Mo, No, dtype=torch.float64, device=DEV)
+    ref[:, :No_x] += 0.5 * _join(py).t() @ _join(px)
+    slabs = torch.empty(_lib.load().maed_bwd_wgrad_slab_floats(Mo, No, R), device=DEV)
+    D = torch.ones(Mo, No, device=DEV)
+    _lib.call("maed_bwd_wgrad_rows", _lib.ptr(py), C.c_longlong(py[0].numel()), Mo, _lib.ptr(px), C.c_longlong(px[0].numel()), No_x,
+              No_x, Mo, No, R, 3, C.c_float(0.5), 1, _lib.ptr(slabs), _lib.ptr(D), No, _lib.stream_ptr())
+    assert rel_err(D, ref) < 2e-5
+
+
 def test_split_transposed(L):
     _lib, _ = L
     w = _rand(2304, 768, scale=0.05, seed=36)
