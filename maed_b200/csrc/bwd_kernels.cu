@@ -243,85 +243,92 @@ static constexpr int kLnBwdBlocks = 148 * 2;
 static constexpr int kLnBwdWarps = 8;
 int ln_bwd_partial_rows() { return kLnBwdBlocks * kLnBwdWarps; }
 
-__global__ void __launch_bounds__(kLnBwdWarps * 32)
+// One warp per row, NV float4 per lane (C = 128 NV).  Round 2: templated on NV (C = 768 used arrays sized for 1024), x and dy of
+// a row are both requested before the first reduction (12 independent 16-byte loads per lane in flight), gamma is re-read
+// through L1 instead of living in registers, and two 256-thread blocks fit an SM (the first version ran at 20 % of HBM peak).
+template <int NV>
+__global__ void __launch_bounds__(kLnBwdWarps * 32, 2)
 layernorm_bwd_kernel(const float* __restrict__ dy, long long dy_stride, const float* __restrict__ x, long long x_stride,
-                     const float* __restrict__ gamma, int rows, int C, float eps, const float* __restrict__ dx_add,
+                     const float* __restrict__ gamma, int rows, float eps, const float* __restrict__ dx_add,
                      float* __restrict__ dx_out, long long dx_stride, float* __restrict__ partial) {
+  constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * kLnBwdWarps + (threadIdx.x >> 5);
   const int W = gridDim.x * kLnBwdWarps;
-  const int nv = C >> 7;                                   // float4 per lane (C % 128 == 0, C <= 1024)
-  float4 gam[8], dgam[8], dbet[8];
+  float4 dgam[NV], dbet[NV];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NV; ++j) {
     dgam[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     dbet[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < nv) gam[j] = *reinterpret_cast<const float4*>(gamma + (j * 32 + lane) * 4);
   }
   for (int row = wg; row < rows; row += W) {
     const float* xr = x + (long long)row * x_stride;
     const float* dr = dy + (long long)row * dy_stride;
-    float4 v[8], g[8];
+    float4 v[NV], g[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = *reinterpret_cast<const float4*>(xr + (j * 32 + lane) * 4);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) g[j] = *reinterpret_cast<const float4*>(dr + (j * 32 + lane) * 4);
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nv) {
-        v[j] = *reinterpret_cast<const float4*>(xr + (j * 32 + lane) * 4);
-        s += v[j].x + v[j].y + v[j].z + v[j].w;
-      }
+    for (int j = 0; j < NV; ++j) s += v[j].x + v[j].y + v[j].z + v[j].w;
     const float mean = warp_sum(s) / (float)C;
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nv) {
-        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
-        q += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
-      }
+    for (int j = 0; j < NV; ++j) {
+      v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+      q += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    }
     const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
     float s1 = 0.f, s2 = 0.f;                              // sum(dy*gamma), sum(dy*gamma*xhat)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nv) {
-        const float4 d = *reinterpret_cast<const float4*>(dr + (j * 32 + lane) * 4);
-        v[j].x *= rstd; v[j].y *= rstd; v[j].z *= rstd; v[j].w *= rstd;          // xhat
-        dgam[j].x += d.x * v[j].x; dgam[j].y += d.y * v[j].y; dgam[j].z += d.z * v[j].z; dgam[j].w += d.w * v[j].w;
-        dbet[j].x += d.x; dbet[j].y += d.y; dbet[j].z += d.z; dbet[j].w += d.w;
-        g[j] = make_float4(d.x * gam[j].x, d.y * gam[j].y, d.z * gam[j].z, d.w * gam[j].w);
-        s1 += g[j].x + g[j].y + g[j].z + g[j].w;
-        s2 += g[j].x * v[j].x + g[j].y * v[j].y + g[j].z * v[j].z + g[j].w * v[j].w;
-      }
+    for (int j = 0; j < NV; ++j) {
+      const float4 d = g[j];
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + (j * 32 + lane) * 4));
+      v[j].x *= rstd; v[j].y *= rstd; v[j].z *= rstd; v[j].w *= rstd;          // xhat
+      dgam[j].x += d.x * v[j].x; dgam[j].y += d.y * v[j].y; dgam[j].z += d.z * v[j].z; dgam[j].w += d.w * v[j].w;
+      dbet[j].x += d.x; dbet[j].y += d.y; dbet[j].z += d.z; dbet[j].w += d.w;
+      g[j] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += g[j].x + g[j].y + g[j].z + g[j].w;
+      s2 += g[j].x * v[j].x + g[j].y * v[j].y + g[j].z * v[j].z + g[j].w * v[j].w;
+    }
     const float m1 = warp_sum(s1) / (float)C, m2 = warp_sum(s2) / (float)C;
     float* o = dx_out + (long long)row * dx_stride;
     const float* a = dx_add ? dx_add + (long long)row * dx_stride : nullptr;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nv) {
-        float4 r;
-        r.x = rstd * (g[j].x - m1 - v[j].x * m2);
-        r.y = rstd * (g[j].y - m1 - v[j].y * m2);
-        r.z = rstd * (g[j].z - m1 - v[j].z * m2);
-        r.w = rstd * (g[j].w - m1 - v[j].w * m2);
-        if (a) {
-          const float4 b = *reinterpret_cast<const float4*>(a + (j * 32 + lane) * 4);
-          r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
-        }
-        *reinterpret_cast<float4*>(o + (j * 32 + lane) * 4) = r;
+    for (int j = 0; j < NV; ++j) {
+      float4 r;
+      r.x = rstd * (g[j].x - m1 - v[j].x * m2);
+      r.y = rstd * (g[j].y - m1 - v[j].y * m2);
+      r.z = rstd * (g[j].z - m1 - v[j].z * m2);
+      r.w = rstd * (g[j].w - m1 - v[j].w * m2);
+      if (a) {
+        const float4 b = *reinterpret_cast<const float4*>(a + (j * 32 + lane) * 4);
+        r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
       }
+      *reinterpret_cast<float4*>(o + (j * 32 + lane) * 4) = r;
+    }
   }
   float* pr = partial + (long long)wg * 2 * C;
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (j < nv) {
-      *reinterpret_cast<float4*>(pr + (j * 32 + lane) * 4) = dgam[j];
-      *reinterpret_cast<float4*>(pr + C + (j * 32 + lane) * 4) = dbet[j];
-    }
+  for (int j = 0; j < NV; ++j) {
+    *reinterpret_cast<float4*>(pr + (j * 32 + lane) * 4) = dgam[j];
+    *reinterpret_cast<float4*>(pr + C + (j * 32 + lane) * 4) = dbet[j];
+  }
 }
 int layernorm_bwd(const float* dy, long long dy_stride, const float* x, long long x_stride, const float* gamma, int rows,
                   int C, float eps, const float* dx_add, float* dx_out, long long dx_stride, float* partial,
                   cudaStream_t st) {
   MAED_CHECK_ARG(C % 128 == 0 && C <= 1024, "layernorm_bwd: C=%d unsupported (multiple of 128, <= 1024)", C);
-  layernorm_bwd_kernel<<<kLnBwdBlocks, kLnBwdWarps * 32, 0, st>>>(dy, dy_stride, x, x_stride, gamma, rows, C, eps, dx_add,
-                                                                  dx_out, dx_stride, partial);
+#define MAED_LN_BWD(NV)                                                                                                       \
+  case NV:                                                                                                                    \
+    layernorm_bwd_kernel<NV><<<kLnBwdBlocks, kLnBwdWarps * 32, 0, st>>>(dy, dy_stride, x, x_stride, gamma, rows, eps, dx_add, \
+                                                                         dx_out, dx_stride, partial);                         \
+    break;
+  switch (C / 128) {
+    MAED_LN_BWD(1) MAED_LN_BWD(2) MAED_LN_BWD(3) MAED_LN_BWD(4) MAED_LN_BWD(5) MAED_LN_BWD(6) MAED_LN_BWD(7) MAED_LN_BWD(8)
+  }
+#undef MAED_LN_BWD
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
 }

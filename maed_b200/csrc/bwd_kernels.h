@@ -112,6 +112,9 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, double 
 // d_qkv fp32 [BT*ntok, 3*H*64]; `accumulate` adds to d_qkv instead of overwriting it
 int attn_spatial_bwd(const __half* qkv_hi, long long qkv_plane, const float* d_out, int BT, int ntok, int heads, float scale,
                      int accumulate, float* d_qkv, cudaStream_t st);
+// tcgen05 version (attention_bwd_sm100.cu): d_out given as fp16 hi/lo planes [BT*ntok, heads*64]; ntok <= 208
+int attn_spatial_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int BT, int ntok,
+                        int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st);
 int attn_temporal_bwd(const __half* qkv_hi, long long qkv_plane, const float* d_out, int B, int T, int ntok, int heads,
                       float scale, int accumulate, float* d_qkv, cudaStream_t st);
 

@@ -291,6 +291,13 @@ int maed_bwd_attention(int kind, const void* qkv_hi, long long qkv_plane, const 
     MAED_CHECK_ARG(scratch, "maed_bwd_attention(kind 2): scratch of B * heads * T * ntok * 3 floats required");
     return attn_generic_bwd((const __half*)qkv_hi, qkv_plane, d_out, B, T * ntok, heads, scale, accumulate, d_qkv, scratch, st);
   }
+  if (kind == 3) {   // spatial on the tensor cores; scratch = 2 * B*T*ntok * heads*64 halfs (hi / lo planes of d_out)
+    MAED_CHECK_ARG(scratch, "maed_bwd_attention(kind 3): scratch of B*T*ntok * heads*64 floats required");
+    const long long n = (long long)B * T * ntok * heads * 64;
+    MAED_PROPAGATE(split_f32(d_out, (__half*)scratch, n, n, st));
+    return attn_spatial_bwd_tc((const __half*)qkv_hi, qkv_plane, (const __half*)scratch, n, B * T, ntok, heads, scale, accumulate,
+                               d_qkv, st);
+  }
   set_error("maed_bwd_attention: unknown kind %d", kind);
   return MAED_ERR_ARG;
 }

@@ -54,7 +54,7 @@ struct Net {
   std::vector<BlockL> B;
   bool bn = false;             // 'cnn' encoder: BatchNorm2d (batch statistics) instead of weight standardisation + GroupNorm
   size_t tp_proj;              // dgrad weights of patch_embed.proj
-  struct SteT { size_t qkv, proj, fc1, fc2; };
+  struct SteT { size_t qkv, proj, fc1, fc2, ts; };
   std::vector<SteT> ste;
   size_t tpack_bytes;
 };
@@ -102,6 +102,7 @@ Net build_net(const Engine& e) {
     t.proj = planes(CC);
     t.fc1 = planes(4 * CC);
     t.fc2 = planes(4 * CC);
+    t.ts = e.cfg.mode == MODE_PARALLEL ? planes(4 * CC) : 0;        // attentive-addition linear [2C, 2C] (parallel mode only)
     n.ste.push_back(t);
   }
   n.tpack_bytes = off;
@@ -438,6 +439,8 @@ int train_pack(const Engine* ep, const void* const* params, void* tpack, cudaStr
     MAED_PROPAGATE(split_f32_transposed(P(ix.proj_w), C, C, (__half*)(tp + net.ste[i].proj), CC, st));
     MAED_PROPAGATE(split_f32_transposed(P(ix.fc1_w), 4 * C, C, (__half*)(tp + net.ste[i].fc1), 4 * CC, st));
     MAED_PROPAGATE(split_f32_transposed(P(ix.fc2_w), C, 4 * C, (__half*)(tp + net.ste[i].fc2), 4 * CC, st));
+    if (e.cfg.mode == MODE_PARALLEL)
+      MAED_PROPAGATE(split_f32_transposed(P(ix.ts_w), 2 * C, 2 * C, (__half*)(tp + net.ste[i].ts), 4 * CC, st));
   }
   return MAED_OK;
 }
@@ -671,6 +674,16 @@ int train_forward(const Engine* ep, const void* const* params, const void* packe
 }
 
 // ------------------------------------------------------------------------------------------- backward
+// spatial attention backward on the tensor cores (attention_bwd_sm100.cu): d_out -> fp16 hi/lo planes in pl_a (free at every
+// call site: the planes of the previous linear's gradient have been consumed), d_qkv overwritten
+static int spatial_bwd(const Ctx& c, const __half* qkv, const float* d_out, float* dqkv) {
+  TrainWs& w = c.w;
+  const int heads = c.e.cfg.num_heads;
+  const long long n = (long long)c.BT * 197 * heads * 64;
+  MAED_PROPAGATE(split_f32(d_out, w.pl_a, w.pl_a_plane, n, c.st));
+  return attn_spatial_bwd_tc(qkv, w.qkv_plane, w.pl_a, w.pl_a_plane, c.BT, 197, heads, 0.125f, 0, dqkv, c.st);
+}
+
 // dW [Nw, Kw] = scale * dY^T X  for a linear layer; dY, X as planes [R, *] (dense rows)
 static int linear_wgrad(const Ctx& c, const __half* dy, long long dy_plane, int Nw, const __half* x, long long x_plane, int Kw,
                         int R, int accumulate, float* dW) {
@@ -998,9 +1011,12 @@ int train_backward(const Engine* ep, const void* const* params, const void* pack
       MAED_PROPAGATE(blend_bwd(d_ao, t.xs, t.xt, t.logits, BT, ntok, C, d_logits, w.dxs, w.dxt, st));
       MAED_PROPAGATE(sgemm_f32(1, 0, 2 * C, 2 * C, BT, c.inv_ls, d_logits, 2 * C, t.pooled, 2 * C, 0.f, c.G(ix.ts_w), 2 * C, st));
       MAED_PROPAGATE(colsum_f32(d_logits, 2 * C, BT, 2 * C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.ts_b), st));
-      MAED_PROPAGATE(sgemm_f32(0, 0, BT, 2 * C, 2 * C, 1.f, d_logits, 2 * C, c.P(ix.ts_w), 2 * C, 0.f, d_pool, 2 * C, st));
+      // d_pool = d_logits W_ts on the tensor cores (the fp32 CUDA-core GEMM took 0.4 ms per block for these 128 rows)
+      MAED_PROPAGATE(split_f32(d_logits, w.small_p, w.small_plane, (long long)BT * 2 * C, st));
+      MAED_PROPAGATE(gemm_plain(c, w.small_p, w.small_plane, BT, 2 * C, c.TH(tt.ts), 4 * CC, 2 * C, nullptr, ACT_NONE, nullptr, OUT_F32,
+                                d_pool, 0));
       MAED_PROPAGATE(blend_bwd_pool(d_pool, BT, ntok, C, w.dxs, w.dxt, st));
-      MAED_PROPAGATE(attn_spatial_bwd(t.qkv, w.qkv_plane, w.dxs, BT, ntok, heads, scale, 0, dqkv, st));
+      MAED_PROPAGATE(spatial_bwd(c, t.qkv, w.dxs, dqkv));
       MAED_PROPAGATE(attn_temporal_bwd(t.qkv, w.qkv_plane, w.dxt, N, T, ntok, heads, scale, 1, dqkv, st));
     } else if (cf.mode == MODE_SERIES) {
       // ao = temporal(qkv2), qkv2 = qkv(ao_s), ao_s = spatial(qkv), qkv = qkv(ln1): the qkv weights are used twice
@@ -1010,11 +1026,11 @@ int train_backward(const Engine* ep, const void* const* params, const void* pack
       MAED_PROPAGATE(linear_wgrad(c, w.pl_a, w.pl_a_plane, 3 * C, t.ao_s, w.ln_plane, C, rows, 0, c.G(ix.qkv_w)));
       MAED_PROPAGATE(gemm_plain(c, w.pl_a, w.pl_a_plane, rows, 3 * C, c.TH(tt.qkv), 3 * CC, C, nullptr, ACT_NONE, nullptr, OUT_F32,
                                 w.dxs, 0));                                                               // d_ao_s
-      MAED_PROPAGATE(attn_spatial_bwd(t.qkv, w.qkv_plane, w.dxs, BT, ntok, heads, scale, 0, dqkv, st));
+      MAED_PROPAGATE(spatial_bwd(c, t.qkv, w.dxs, dqkv));
     } else if (cf.mode == MODE_COUPLING) {
       MAED_PROPAGATE(attn_generic_bwd(t.qkv, w.qkv_plane, d_ao, N, T * ntok, heads, scale, 0, dqkv, w.dxt, st));   // dxt: statistics
     } else {
-      MAED_PROPAGATE(attn_spatial_bwd(t.qkv, w.qkv_plane, d_ao, BT, ntok, heads, scale, 0, dqkv, st));
+      MAED_PROPAGATE(spatial_bwd(c, t.qkv, d_ao, dqkv));
     }
     const int acc = cf.mode == MODE_SERIES ? 1 : 0;
     MAED_PROPAGATE(split_f32(dqkv, w.pl_a, w.pl_a_plane, (long long)rows * 3 * C, st));

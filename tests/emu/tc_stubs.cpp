@@ -425,6 +425,27 @@ int gemm_wgrad_splitk(const __half* A, long long a_plane, int lda, const __half*
   return MAED_OK;
 }
 
+// ------------------------------------------------------------------------- spatial attention backward (tcgen05 kernel)
+// contract: the CUDA-core kernel of attention_bwd.cu (compiled from the real source) on d_out = hi + lo
+int attn_spatial_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int BT, int ntok,
+                        int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st) {
+  MAED_CHECK_ARG(qkv_hi && dout_hi && d_qkv, "attn_spatial_bwd_tc: null argument");
+  MAED_CHECK_ARG(ntok >= 1 && ntok <= 208, "attn_spatial_bwd_tc: ntok=%d unsupported (1..208)", ntok);
+  const long long rows = (long long)BT * ntok;
+  const int ld3 = 3 * heads * 64, ldo = heads * 64;
+  MAED_CHECK_ARG(qkv_plane >= rows * ld3 && dout_plane >= rows * ldo && qkv_plane % 8 == 0 && dout_plane % 8 == 0,
+                 "attn_spatial_bwd_tc: operand planes overlap or are misaligned");
+  {
+    const uint64_t dims[3] = {(uint64_t)ldo, (uint64_t)rows, 2};
+    const uint64_t str[2] = {(uint64_t)ldo * 2, (uint64_t)dout_plane * 2};
+    const uint32_t box[3] = {64, 208, 1};
+    MAED_PROPAGATE(check_tmap("attn bwd dO", dout_hi, 3, dims, str, box));
+  }
+  std::vector<float> d((size_t)rows * ldo);
+  planes_to_dense(dout_hi, dout_plane, rows, ldo, ldo, d.data());
+  return attn_spatial_bwd(qkv_hi, qkv_plane, d.data(), BT, ntok, heads, scale, accumulate, d_qkv, st);
+}
+
 int gemm_wgrad_rows(const __half* dY, long long dy_plane, int ld_dy, const __half* X, long long x_plane, int ld_x, int No_x,
                     int Mo, int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, cudaStream_t) {
   Prof prof(4);

@@ -117,26 +117,43 @@ def test_gradients_match_reference_digests(lib, name):
     print("%s: worst %s %.2e" % (name, worst[0], worst[1]))
 
 
+def _group(k):
+    if "backbone" in k:
+        return "backbone." + k.split("backbone.")[1].split(".")[0] + ("." + k.split("stages.")[1].split(".")[0] if "stages." in k else "")
+    if ".blocks." in k:
+        return "ste.blocks"
+    return "decoder" if k.startswith("decoder") else "ste.other"
+
+
 def test_gradients_match_oracle_autograd(lib):
-    """Every entry of every parameter gradient against autograd over the CPU oracle (parallel mode, 2 clips x 2 frames)."""
+    """Every entry of every parameter gradient against FLOAT64 autograd over the CPU oracle (parallel mode, 2 clips x 2
+    frames).  The fp32 oracle itself differs from the fp64 one by worst 1.7e-2 / median 2.3e-3 per parameter on this random
+    weight-standardised network (ReLU / arg-max flips, x80 backbone amplification): that is the noise floor of ANY fp32-class
+    implementation, so the gates are: median <= 5e-3 overall, every layer group's median <= 1e-2, no parameter above 5e-2."""
     _slow_on_emu()
     seed, N, T = 33, 2, 2
     m = _model("parallel", seed, lib)
     A, B, C_ = _probes(N * T, seed)
     x = synth.synth_frames(N, T, seed)
     _loss(m(x.to(DEV)), A, B, C_).backward()
-    sd = {k: v.cpu() for k, v in state_dict_of(m).items()}
-    _, ref, _ = O.maed_param_grads(x, sd, A.cpu(), B.cpu(), C_.cpu(), "parallel", "ktd")
-    worst, errs = ("", 0.0), []
+    dbl = lambda t: t.detach().cpu().double() if t.dtype.is_floating_point else t.detach().cpu()  # noqa: E731
+    sd = {k: dbl(v) for k, v in state_dict_of(m).items()}
+    _, ref, _ = O.maed_param_grads(x.double(), sd, dbl(A), dbl(B), dbl(C_), "parallel", "ktd")
+    assert next(iter(ref.values())).dtype == torch.float64
+    worst, errs, groups = ("", 0.0), [], {}
     for k, p in m.named_parameters():
         e = rel_err(p.grad, ref[k])
         errs.append(e)
+        groups.setdefault(_group(k), []).append(e)
         if e > worst[1]:
             worst = (k, e)
-        # gate = 3x the fp32 noise floor (fp32 vs fp64 oracle autograd: worst 1.7e-2, median 2.3e-3)
         assert e < 5e-2, "%s: relative gradient error %.3e" % (k, e)
-    assert float(np.median(errs)) < 1e-2, "median relative gradient error %.3e" % float(np.median(errs))
-    print("worst parameter-gradient error vs oracle autograd: %s %.2e, median %.2e" % (worst + (float(np.median(errs)),)))
+    med = float(np.median(errs))
+    print("parameter gradients vs float64 oracle autograd: worst %s %.2e, median %.2e" % (worst + (med,)))
+    for g, v in sorted(groups.items()):
+        print("  %-24s n=%3d median %.2e max %.2e" % (g, len(v), float(np.median(v)), max(v)))
+        assert float(np.median(v)) < 1e-2, "%s: median relative gradient error %.3e" % (g, float(np.median(v)))
+    assert med < 5e-3, "median relative gradient error %.3e" % med
 
 
 def test_loss_scale_invariance_and_determinism(lib):
