@@ -168,6 +168,14 @@ typedef struct maed_train_outputs {
  * NCCL over NVLink on the GPU box, gloo in the CPU tests) and return 0.  fn == NULL: statistics of this rank's batch only. */
 typedef int (*maed_exchange_fn)(void* user, int n_doubles);
 int maed_train_set_exchange(maed_engine* e, maed_exchange_fn fn, void* user, double* buffer, int capacity_doubles);
+/* Backward progress hook (overlap of the data-parallel gradient exchange with the backward; the role of DDP's bucketed
+ * all-reduce, reference train.py:113): during maed_train_backward fn(user, first, end) is called on the host, in stream order,
+ * when the gradients of the engine parameters with table index in [first, end) are final — encoder = 'ste': after STE block k
+ * (k = num_blocks - 1 ... 0) the range [first parameter of block k, first parameter of block k + 1 or table end for the last
+ * block: final norm, pre_logits and the decoder are behind the blocks in the table], finally [0, first parameter of block 0)
+ * (embeddings, backbone, patch projection).  fn must return 0.  fn == NULL removes the hook. */
+typedef int (*maed_progress_fn)(void* user, int first_param, int end_param);
+int maed_train_set_progress(maed_engine* e, maed_progress_fn fn, void* user);
 size_t maed_train_pack_bytes(const maed_engine* e);
 size_t maed_train_workspace_bytes(const maed_engine* e, int n_frames);
 /* derived weights of the data-gradient GEMMs; redo after every parameter update (like maed_engine_pack) */

@@ -44,6 +44,7 @@ class MaedLossWeights(C.Structure):
 
 
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)     # maed_exchange_fn
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int)     # maed_progress_fn
 _U = C.c_ulonglong
 MODES = {"vanilla": 0, "parallel": 1, "series": 2, "coupling": 3, "temporal": 4}
 DECODERS = {"ktd": 0, "iterative": 1}
@@ -83,6 +84,7 @@ SIGNATURES = {
     "maed_engine_forward": (_I, [_P, c_void_pp, _P, _P, _I, _I, _P, _Z, C.POINTER(MaedOutputs), c_void_pp, _P]),
     # ---- training path
     "maed_train_set_exchange": (_I, [_P, EXCHANGE_FN, _P, _P, _I]),
+    "maed_train_set_progress": (_I, [_P, PROGRESS_FN, _P]),
     "maed_train_pack_bytes": (_Z, [_P]),
     "maed_train_workspace_bytes": (_Z, [_P, _I]),
     "maed_train_pack": (_I, [_P, c_void_pp, _P, _P]),

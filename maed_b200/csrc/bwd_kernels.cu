@@ -93,6 +93,46 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ in_f, const __hal
   }
   partial[(long long)chunk * C + c] = s;
 }
+// Vectorised stage 1 (round 2): a thread owns 4 adjacent columns (one 16-byte load per row; planes: 8 bytes hi + 8 bytes lo)
+// and walks its row chunk four rows at a time with independent accumulators, so every thread keeps 4 loads in flight (the
+// scalar version ran the 310 MB fc1 bias gradient at 1.6 TB/s).  Fixed summation order: deterministic like the scalar kernel.
+template <bool kPlanes>
+__global__ void colsum_stage1_vec4_kernel(const float* __restrict__ in_f, const __half* __restrict__ in_h, long long plane,
+                                          long long ld, int R, int C, float* __restrict__ partial) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int chunk = blockIdx.y;
+  const int per = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = chunk * per, r1 = min(R, r0 + per);
+  if (c >= C) return;
+  float4 acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load = [&](int r) -> float4 {
+    if (kPlanes) {
+      const uint2 h = *reinterpret_cast<const uint2*>(in_h + (long long)r * ld + c);
+      const uint2 l = *reinterpret_cast<const uint2*>(in_h + (long long)r * ld + c + plane);
+      const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+      const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l23 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+      return make_float4(h01.x + l01.x, h01.y + l01.y, h23.x + l23.x, h23.y + l23.y);
+    }
+    return *reinterpret_cast<const float4*>(in_f + (long long)r * ld + c);
+  };
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = load(r + u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+  }
+  for (; r < r1; ++r) { const float4 v = load(r); acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w; }
+  float4 s;
+  s.x = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x);
+  s.y = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
+  s.z = (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z);
+  s.w = (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w);
+  *reinterpret_cast<float4*>(partial + (long long)chunk * C + c) = s;
+}
 __global__ void colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int C, float scale, int accumulate,
                                      float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,6 +145,18 @@ static int colsum_impl(const float* in_f, const __half* in_h, long long plane, l
                        int accumulate, float* scratch, float* out, cudaStream_t st) {
   MAED_CHECK_ARG(R >= 1 && C >= 1 && scratch && out, "colsum: bad arguments R=%d C=%d", R, C);
   int chunks = R < kColsumChunks ? R : kColsumChunks;
+  const bool vec4 = (C % 4 == 0) && (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(scratch) % 16 == 0) &&
+                    (in_h ? (reinterpret_cast<uintptr_t>(in_h) % 8 == 0 && plane % 4 == 0) : (reinterpret_cast<uintptr_t>(in_f) % 16 == 0));
+  if (vec4) {
+    const int threads = C >= 256 ? 64 : 32;                // 4 columns per thread; narrow blocks keep >= 148 CTAs for C = 768
+    const dim3 vgrid(cdiv(C, 4 * threads), chunks);
+    if (in_h) colsum_stage1_vec4_kernel<true><<<vgrid, threads, 0, st>>>(nullptr, in_h, plane, ld, R, C, scratch);
+    else colsum_stage1_vec4_kernel<false><<<vgrid, threads, 0, st>>>(in_f, nullptr, 0, ld, R, C, scratch);
+    MAED_BW_LAUNCH_CHECK();
+    colsum_stage2_kernel<<<cdiv(C, 128), 128, 0, st>>>(scratch, chunks, C, scale, accumulate, out);
+    MAED_BW_LAUNCH_CHECK();
+    return MAED_OK;
+  }
   const dim3 grid(cdiv(C, 128), chunks);
   if (in_h) colsum_stage1_kernel<true><<<grid, 128, 0, st>>>(nullptr, in_h, plane, ld, R, C, scratch);
   else colsum_stage1_kernel<false><<<grid, 128, 0, st>>>(in_f, nullptr, 0, ld, R, C, scratch);

@@ -17,7 +17,7 @@ int transpose_planes(const __half* in_hi, long long in_plane, int R, int C, int 
 // fp32 [R, C] rows (row stride ld_in) -> planes [R, C] dense (split_f32 with a row gather)
 int split_rows_f32(const float* in, long long ld_in, int R, int C, __half* out_hi, long long out_plane, cudaStream_t st);
 // out[c] (+)= scale * sum_r in[r, c];  scratch: kColsumChunks * C floats.  Deterministic two-stage reduction.
-static constexpr int kColsumChunks = 64;
+static constexpr int kColsumChunks = 256;
 int colsum_f32(const float* in, long long ld, int R, int C, float scale, int accumulate, float* scratch, float* out,
                cudaStream_t st);
 int colsum_planes(const __half* in_hi, long long plane, long long ld, int R, int C, float scale, int accumulate,

@@ -169,6 +169,9 @@ static_assert(sizeof(maed_train_outputs) == sizeof(TrainOutputs), "maed_train_ou
 int maed_train_set_exchange(maed_engine* e, maed_exchange_fn fn, void* user, double* buffer, int capacity_doubles) {
   return train_set_exchange(reinterpret_cast<Engine*>(e), fn, user, buffer, capacity_doubles);
 }
+int maed_train_set_progress(maed_engine* e, maed_progress_fn fn, void* user) {
+  return train_set_progress(reinterpret_cast<Engine*>(e), fn, user);
+}
 size_t maed_train_pack_bytes(const maed_engine* e) { return train_pack_bytes(reinterpret_cast<const Engine*>(e)); }
 size_t maed_train_workspace_bytes(const maed_engine* e, int n_frames) {
   return train_workspace_bytes(reinterpret_cast<const Engine*>(e), n_frames);

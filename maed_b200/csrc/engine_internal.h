@@ -51,6 +51,8 @@ struct Engine {
   std::vector<CnnConv> cnn;
   size_t off_cnn_scratch = 0;               // fp32 scratch for one BN-scaled weight tensor (pack time only)
   BnExchange bn_exchange{nullptr, nullptr, nullptr, 0};   // SyncBatchNorm hook of the 'cnn' training path (train_set_exchange)
+  // backward progress hook (train_set_progress): called on the host after the kernels of a stage have been ENQUEUED
+  struct Progress { int (*fn)(void* user, int first_param, int end_param); void* user; } progress{nullptr, nullptr};
   int feat_dim() const { return cfg.encoder == ENC_CNN ? 2048 : 768; }
   int np() const { return cfg.nsplit == 3 ? 2 : 1; }
 };

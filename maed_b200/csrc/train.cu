@@ -416,6 +416,12 @@ int train_set_exchange(Engine* e, int (*fn)(void*, int), void* user, double* buf
   return MAED_OK;
 }
 
+int train_set_progress(Engine* e, int (*fn)(void*, int, int), void* user) {
+  MAED_CHECK_ARG(e, "train_set_progress: null engine");
+  e->progress = Engine::Progress{fn, user};
+  return MAED_OK;
+}
+
 int train_pack(const Engine* ep, const void* const* params, void* tpack, cudaStream_t st) {
   MAED_CHECK_ARG(ep, "train_pack: null engine");
   MAED_PROPAGATE(check_train_cfg(*ep));
@@ -1041,6 +1047,11 @@ int train_backward(const Engine* ep, const void* const* params, const void* pack
     MAED_PROPAGATE(layernorm_bwd(dx2, C, t.x_in, C, c.P(ix.n1), rows, C, 1e-6f, dx, dx, C, w.ln_partial, st));    // dx = d_xin
     MAED_PROPAGATE(colsum_f32(w.ln_partial, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.n1), st));
     MAED_PROPAGATE(colsum_f32(w.ln_partial + C, 2 * C, lnr, C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.n1 + 1), st));
+    // gradients of block i and of everything behind it in the table (later blocks, final norm, pre_logits, decoder) are final
+    if (e.progress.fn) {
+      const int hi = (i + 1 < cf.num_blocks) ? e.blk[i + 1].n1 : (int)e.names.size();
+      MAED_CHECK_ARG(e.progress.fn(e.progress.user, ix.n1, hi) == 0, "train_backward: the progress callback failed");
+    }
   }
 
   // ================================================================================== patch embedding
@@ -1097,6 +1108,8 @@ int train_backward(const Engine* ep, const void* const* params, const void* pack
   MAED_PROPAGATE(maxpool_gn_relu_bwd(d_pool, w.pool_idx, w.convout[0], w.stats[0], c.P(e.i_stem_g), c.P(e.i_stem_g + 1), BT, 112,
                                      112, 64, 1e-5f, d_y, st));
   MAED_PROPAGATE(conv_layer_bwd(c, 0, d_y, nullptr, nullptr, nullptr));
+  if (e.progress.fn && cf.num_blocks > 0)
+    MAED_CHECK_ARG(e.progress.fn(e.progress.user, 0, e.blk[0].n1) == 0, "train_backward: the progress callback failed");
   return MAED_OK;
 }
 

@@ -29,4 +29,10 @@ int train_backward(const Engine* e, const void* const* params, const void* packe
 // 2 * 2048 + 1 doubles) up over the data-parallel ranks in stream order; fn == nullptr removes the hook (per-rank statistics).
 int train_set_exchange(Engine* e, int (*fn)(void*, int), void* user, double* buf, int capacity);
 
+// Backward progress hook for overlapping the data-parallel gradient exchange with the rest of the backward: during
+// train_backward, fn(user, first, end) is called on the host (in stream order: every kernel writing those gradients has been
+// enqueued) when the gradients of the engine parameters with table index in [first, end) are final.  'ste': the tail range
+// [blocks.k ..., table end) after block k (k = num_blocks - 1 ... 0), then [0, blocks.0) at the end.  fn == nullptr: no hook.
+int train_set_progress(Engine* e, int (*fn)(void*, int, int), void* user);
+
 }  // namespace maed

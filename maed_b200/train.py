@@ -212,6 +212,45 @@ class TrainState:
         self.loss_scale = 4096.0
         self.step_seed = 0
         self._exchange = None
+        # overlapped data-parallel gradient exchange (overlap_gradient_allreduce)
+        self.overlap = False
+        self._progress = None             # ctypes thunk of the engine's backward progress hook (kept alive here)
+        self._overlap_live = False        # this backward writes flat_grad itself under an initialised process group
+        self._works = []                  # outstanding async all-reduces of this backward
+        self._avg_in_collective = True
+
+    def set_overlap(self, model, on):
+        """Installs / removes the engine's backward progress hook: as soon as the kernels producing a contiguous range of the
+        flat gradient buffer have been enqueued, that range is all-reduced asynchronously (NCCL runs it on its own stream
+        behind the compute stream's work so far), so the exchange of the STE blocks' gradients overlaps the rest of the
+        backward — what DDP's bucketed all-reduce does for the reference (train.py:113)."""
+        import torch.distributed as dist
+        self.overlap = bool(on)
+        if not on:
+            if self._progress is not None:
+                _lib.call("maed_train_set_progress", model._engine, _lib.PROGRESS_FN(0), None)
+                self._progress = None
+            return
+
+        def progress(_user, first, end):
+            try:
+                if not self._overlap_live:
+                    return 0
+                offs = self.grad_offsets
+                lo = next(o for o in offs[first:] if o is not None)
+                hi = next((o for o in offs[end:] if o is not None), self.flat_grad.numel())
+                if hi > lo:
+                    op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+                    self._works.append(dist.all_reduce(self.flat_grad[lo:hi], op=op, async_op=True))
+                return 0
+            except Exception:                           # an exception must not unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        model._get_engine()
+        self._progress = _lib.PROGRESS_FN(progress)
+        _lib.call("maed_train_set_progress", model._engine, self._progress, None)
 
     def ensure_exchange(self, model, dev):
         """SyncBatchNorm for encoder='cnn' under data parallelism (the reference converts every BatchNorm with
@@ -394,6 +433,13 @@ class MaedTrainFunction(torch.autograd.Function):
         param_names = {n for n, _ in model._train_param_order}
         params = [p for _, p in model._train_param_order]
         ptrs, views, add_into = st.grad_targets(tensors, [n in param_names for n in model._param_names], params)
+        st._works = []
+        st._overlap_live = False
+        if st.overlap and ptrs is st.grad_ptrs:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                st._overlap_live = True
+                st._avg_in_collective = dist.get_backend() == "nccl"        # gloo has no AVG: sum, then divide
         z = lambda g, n: (torch.zeros(N * T, n, dtype=torch.float32, device=dev) if g is None  # noqa: E731
                           else g.contiguous().float())
         d_pose, d_shape, d_cam = z(d_pose, 144), z(d_shape, 10), z(d_cam, 3)
@@ -402,6 +448,7 @@ class MaedTrainFunction(torch.autograd.Function):
                       _lib.ptr(x), N, T, _lib.ptr(tape.ws), C.c_size_t(tape.ws.numel()), _lib.ptr(d_pose),
                       _lib.ptr(d_shape), _lib.ptr(d_cam), C.c_float(st.loss_scale), C.c_float(ctx.dropout_p), ptrs,
                       _lib.stream_ptr())
+        st._overlap_live = False
         tape.release()
         ctx.tape = None
         if add_into is not None:                           # a parked buffer of this backward pass collects the sum
@@ -589,14 +636,34 @@ class FusedAdam(torch.optim.Optimizer):
         return loss
 
 
+def overlap_gradient_allreduce(model, on=True):
+    """Data-parallel training without torch DDP: exchange the gradients WHILE the backward is still running.  After this
+    call every ``loss.backward()`` through the model all-reduces the flat gradient buffer range by range as the engine finishes
+    it (STE block by block, then embeddings + backbone); ``allreduce_gradients(model)`` after the backward then only waits for
+    those collectives (stream-ordered) instead of reducing 288.5 MB in one exposed call."""
+    model._get_engine()
+    if getattr(model, "_train_state", None) is None:
+        model._train_state = TrainState(model)
+    model._train_state.set_overlap(model, on)
+    return model
+
+
 def allreduce_gradients(model, world_size=None):
     """Average the parameter gradients over the data-parallel ranks with ONE all-reduce of the flat gradient buffer
-    (reference: DDP's bucketed all-reduce, train.py:113; 288.5 MB fp32 per step).  No-op without torch.distributed."""
+    (reference: DDP's bucketed all-reduce, train.py:113; 288.5 MB fp32 per step) — or, after overlap_gradient_allreduce(),
+    wait for the range-wise all-reduces the backward already launched.  No-op without torch.distributed."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return
     ws = world_size or dist.get_world_size()
     st = getattr(model, "_train_state", None)
+    if st is not None and st._works:
+        for w in st._works:
+            w.wait()                                    # stream-ordered on NCCL: later kernels wait, the host does not
+        st._works = []
+        if not st._avg_in_collective:
+            st.flat_grad.div_(ws)
+        return
     order = getattr(model, "_train_param_order", None)
     if st is not None and order is not None and st.flatten_grads([p for _, p in order]):
         dist.all_reduce(st.flat_grad)

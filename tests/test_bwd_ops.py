@@ -65,14 +65,16 @@ def test_transpose_planes(L):
     assert torch.equal(out[0], p[0].t()) and torch.equal(out[1], p[1].t())
 
 
-def test_colsum(L):
+@pytest.mark.parametrize("R,Cc,ld", [(3000, 333, 333), (3001, 768, 768), (130, 64, 128), (7, 1536, 1536)])
+def test_colsum(L, R, Cc, ld):
+    """scalar path (odd widths) and the 16-byte vectorised path (C, ld multiples of 4); scratch = 256 chunks x C floats"""
     _lib, _ = L
-    x = _rand(3000, 333, seed=2)
-    scratch = torch.empty(64 * 333, device=DEV)
-    out = torch.full((333,), 5.0, device=DEV)
-    _lib.call("maed_bwd_colsum", _lib.ptr(x), C.c_longlong(333), 3000, 333, C.c_float(0.5), 1, _lib.ptr(scratch), _lib.ptr(out),
+    x = _rand(R, ld, seed=2)
+    scratch = torch.empty(256 * Cc, device=DEV)
+    out = torch.full((Cc,), 5.0, device=DEV)
+    _lib.call("maed_bwd_colsum", _lib.ptr(x), C.c_longlong(ld), R, Cc, C.c_float(0.5), 1, _lib.ptr(scratch), _lib.ptr(out),
               _lib.stream_ptr())
-    assert rel_err(out, 5.0 + 0.5 * x.double().sum(0)) < 1e-6
+    assert rel_err(out, 5.0 + 0.5 * x[:, :Cc].double().sum(0)) < 1e-6
 
 
 @pytest.mark.parametrize("rows,C_", [(777, 768), (64, 1024), (5, 128)])

@@ -82,11 +82,13 @@ def _grad_worker(rank, world, port, q):
         m = Holder()
         # (1) flat-buffer path: what the engine's backward leaves behind (p.grad are views of TrainState.flat_grad)
         st = train.TrainState(m)
-        views = st.ensure_grads([m.a, m.b])
+        st._layout([m.a, m.b], [True, True])
+        views = st._views(st.flat_grad, [m.a, m.b])
         for p, v in zip((m.a, m.b), views):
             v.fill_(float(rank + 1))
             p.grad = v
         m._train_state = st
+        m._train_param_order = [("a", m.a), ("b", m.b)]
         train.allreduce_gradients(m)
         flat_ok = bool((m.a.grad == 1.5).all() and (m.b.grad == 1.5).all() and m.a.grad.data_ptr() == st.flat_grad.data_ptr())
         # (2) per-parameter fallback (no engine state)
@@ -152,6 +154,79 @@ def _ddp_worker(rank, world, port, q):
         q.put((rank, False, False, {}, traceback.format_exc()[-2500:] + repr(e)))
     finally:
         dist.destroy_process_group()
+
+
+def _overlap_worker(rank, world, port, q):
+    """No torch DDP: overlap_gradient_allreduce() — the engine's backward progress hook launches one asynchronous all-reduce
+    per finished range of the flat gradient buffer; allreduce_gradients() afterwards only waits for them."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "emu"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.setdefault("MAED_EMU_THREADS", "4")
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import harness
+        from maed_b200 import train
+        from maed_b200.models import MAED
+        from oracle import synth
+        with harness.product_on_cpu():
+            m = MAED("ste", 2, 12, "vanilla", "ktd", 1024)
+            synth.fill_module_(m, 21)
+            m = m.train().enable_training(True, dropout_p=0.0)
+            train.overlap_gradient_allreduce(m)
+            x = synth.synth_frames(world, 1, 21)[rank:rank + 1]
+            A, B, C_ = [synth.synth_tensor("grad_probe.%s" % k, (world, n), 21) for k, n in (("pose", 144), ("shape", 10), ("cam", 3))]
+            d = m(x)["_debug"]
+            ((d["pose6d"] * A[rank:rank + 1]).sum() + (d["shape"] * B[rank:rank + 1]).sum() + (d["cam"] * C_[rank:rank + 1]).sum()).backward()
+            st = m._train_state
+            n_works = len(st._works)                       # 2 blocks + the embeddings / backbone range
+            train.allreduce_gradients(m)
+            flat = st.grads_are_flat([p for _, p in m._train_param_order])
+            picks = ["encoder.patch_embed.backbone.stem.conv.weight", "encoder.blocks.0.attn.qkv.weight",
+                     "encoder.blocks.1.mlp.fc2.bias", "decoder.fc2.bias", "encoder.pos_embed", "encoder.cls_token"]
+            named = dict(m.named_parameters())
+            q.put((rank, n_works, flat, {k: named[k].grad.detach().numpy().copy() for k in picks}, None))
+    except Exception as e:                                                        # noqa: BLE001
+        import traceback
+        q.put((rank, 0, False, {}, traceback.format_exc()[-2500:] + repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_gradient_allreduce_two_ranks_gloo():
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "emu"))
+    import harness
+    from maed_b200.models import MAED
+    from oracle import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    with harness.product_on_cpu():                       # meanwhile: both frames in ONE process = 2 x the average
+        m = MAED("ste", 2, 12, "vanilla", "ktd", 1024)
+        synth.fill_module_(m, 21)
+        m = m.train().enable_training(True, dropout_p=0.0)
+        A, B, C_ = [synth.synth_tensor("grad_probe.%s" % k, (2, n), 21) for k, n in (("pose", 144), ("shape", 10), ("cam", 3))]
+        d = m(synth.synth_frames(2, 1, 21))["_debug"]
+        ((d["pose6d"] * A).sum() + (d["shape"] * B).sum() + (d["cam"] * C_).sum()).backward()
+        ref = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    for rank, n_works, flat, grads, err in res:
+        assert err is None, "rank %d: %s" % (rank, err)
+        assert n_works == 3 and flat, (rank, n_works, flat)
+        for k, g in grads.items():
+            e = ((2.0 * torch.from_numpy(g) - ref[k]).norm() / ref[k].norm()).item()
+            assert e < 2e-3, (rank, k, e)
+    for k in res[0][3]:
+        assert (res[0][3][k] == res[1][3][k]).all(), k
 
 
 def test_torch_ddp_wraps_the_training_module_two_ranks_gloo():

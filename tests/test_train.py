@@ -127,32 +127,39 @@ def _group(k):
 
 def test_gradients_match_oracle_autograd(lib):
     """Every entry of every parameter gradient against FLOAT64 autograd over the CPU oracle (parallel mode, 2 clips x 2
-    frames).  The fp32 oracle itself differs from the fp64 one by worst 1.7e-2 / median 2.3e-3 per parameter on this random
-    weight-standardised network (ReLU / arg-max flips, x80 backbone amplification): that is the noise floor of ANY fp32-class
-    implementation, so the gates are: median <= 5e-3 overall, every layer group's median <= 1e-2, no parameter above 5e-2."""
+    frames).  On this random weight-standardised network the gradients of the early layers are ill-conditioned (ReLU /
+    arg-max flips, x80 backbone amplification): the reference's own arithmetic in fp32 (the oracle run in float32) differs
+    from float64 by ~2e-2 in stage 0.  The yardstick is therefore measured in the same test: the CUDA path must be as close
+    to float64 as an fp32 run of the reference is — per layer group median <= 2 x the fp32 oracle's + 1e-3 — and, absolutely,
+    overall median <= 5e-3 with no parameter above 5e-2."""
     _slow_on_emu()
     seed, N, T = 33, 2, 2
     m = _model("parallel", seed, lib)
     A, B, C_ = _probes(N * T, seed)
     x = synth.synth_frames(N, T, seed)
     _loss(m(x.to(DEV)), A, B, C_).backward()
-    dbl = lambda t: t.detach().cpu().double() if t.dtype.is_floating_point else t.detach().cpu()  # noqa: E731
-    sd = {k: dbl(v) for k, v in state_dict_of(m).items()}
-    _, ref, _ = O.maed_param_grads(x.double(), sd, dbl(A), dbl(B), dbl(C_), "parallel", "ktd")
+    cpu = lambda t: t.detach().cpu()  # noqa: E731
+    dbl = lambda t: cpu(t).double() if t.dtype.is_floating_point else cpu(t)  # noqa: E731
+    sd32 = {k: cpu(v) for k, v in state_dict_of(m).items()}
+    _, ref, _ = O.maed_param_grads(x.double(), {k: dbl(v) for k, v in sd32.items()}, dbl(A), dbl(B), dbl(C_), "parallel", "ktd")
+    _, g32, _ = O.maed_param_grads(x, sd32, cpu(A), cpu(B), cpu(C_), "parallel", "ktd")
     assert next(iter(ref.values())).dtype == torch.float64
     worst, errs, groups = ("", 0.0), [], {}
     for k, p in m.named_parameters():
         e = rel_err(p.grad, ref[k])
         errs.append(e)
-        groups.setdefault(_group(k), []).append(e)
+        groups.setdefault(_group(k), ([], []))
+        groups[_group(k)][0].append(e)
+        groups[_group(k)][1].append(rel_err(g32[k], ref[k]))
         if e > worst[1]:
             worst = (k, e)
         assert e < 5e-2, "%s: relative gradient error %.3e" % (k, e)
     med = float(np.median(errs))
     print("parameter gradients vs float64 oracle autograd: worst %s %.2e, median %.2e" % (worst + (med,)))
-    for g, v in sorted(groups.items()):
-        print("  %-24s n=%3d median %.2e max %.2e" % (g, len(v), float(np.median(v)), max(v)))
-        assert float(np.median(v)) < 1e-2, "%s: median relative gradient error %.3e" % (g, float(np.median(v)))
+    for g, (ours, f32) in sorted(groups.items()):
+        mo, mf = float(np.median(ours)), float(np.median(f32))
+        print("  %-24s n=%3d median %.2e max %.2e   | fp32 oracle: median %.2e max %.2e" % (g, len(ours), mo, max(ours), mf, max(f32)))
+        assert mo < 2.0 * mf + 1e-3, "%s: median relative gradient error %.3e (fp32 oracle: %.3e)" % (g, mo, mf)
     assert med < 5e-3, "median relative gradient error %.3e" % med
 
 
