@@ -53,26 +53,9 @@ def synthetic_mean_params():
     return synth.mean_params()
 
 
-def load_reference():
-    """Returns the reference's ``lib.models`` module (with MAED), importing it once."""
-    if "models" in _loaded:
-        return _loaded["models"]
-    if not reference_available():
-        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
-
-    # scratch CWD with synthetic stand-ins for the licensed SMPL data files
-    scratch = tempfile.mkdtemp(prefix="maed_ref_cwd_")
-    os.makedirs(os.path.join(scratch, "data", "smpl_data"))
-    np.save(os.path.join(scratch, "data", "smpl_data", "J_regressor_extra.npy"),
-            np.zeros((9, 6890), np.float32))
-    mp = synthetic_mean_params()
-    np.savez(os.path.join(scratch, "data", "smpl_data", "smpl_mean_params.npz"),
-             pose=mp["pose"], shape=mp["shape"], cam=mp["cam"])
-    os.chdir(scratch)
-    _loaded["scratch"] = scratch
-
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+def install_import_shims():
+    """sys.modules stand-ins for what the reference imports but this image lacks (torch._six, torchvision.models.utils, yacs,
+    smplx); idempotent.  Nothing under the reference tree is modified."""
 
     m = types.ModuleType("torch._six")
     m.container_abcs = collections.abc
@@ -119,6 +102,29 @@ def load_reference():
     lb = types.ModuleType("smplx.lbs")
     lb.vertices2joints = vertices2joints
     sys.modules.update({"smplx": sx, "smplx.body_models": bm, "smplx.lbs": lb})
+
+
+def load_reference():
+    """Returns the reference's ``lib.models`` module (with MAED), importing it once."""
+    if "models" in _loaded:
+        return _loaded["models"]
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+
+    # scratch CWD with synthetic stand-ins for the licensed SMPL data files
+    scratch = tempfile.mkdtemp(prefix="maed_ref_cwd_")
+    os.makedirs(os.path.join(scratch, "data", "smpl_data"))
+    np.save(os.path.join(scratch, "data", "smpl_data", "J_regressor_extra.npy"),
+            np.zeros((9, 6890), np.float32))
+    mp = synthetic_mean_params()
+    np.savez(os.path.join(scratch, "data", "smpl_data", "smpl_mean_params.npz"),
+             pose=mp["pose"], shape=mp["shape"], cam=mp["cam"])
+    os.chdir(scratch)
+    _loaded["scratch"] = scratch
+
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    install_import_shims()
 
     import warnings
     with warnings.catch_warnings():
