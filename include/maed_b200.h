@@ -199,6 +199,9 @@ int maed_adam_step(float* p, const float* g, float* m, float* v, long long n, do
 /* per-op entry points of the backward kernels (unit tests; semantics in maed_b200/csrc/bwd_kernels.h) */
 int maed_bwd_transpose_planes(const void* in_hi, long long in_plane, int R, int C, int ld_in, void* out_hi, long long out_plane,
                               int ld_out, void* stream);
+/* column sums (bias / affine gradients): two-stage, fixed order.  `scratch` of maed_bwd_colsum / maed_bwd_layernorm holds
+ * maed_bwd_colsum_chunks() * C floats (2 * C for the LayerNorm entry: gamma and beta partials) */
+int maed_bwd_colsum_chunks(void);
 int maed_bwd_colsum(const float* in, long long ld, int R, int C, float scale, int accumulate, float* scratch, float* out,
                     void* stream);
 int maed_bwd_layernorm(const float* dy, long long dy_stride, const float* x, long long x_stride, const float* gamma, int rows,

@@ -92,6 +92,7 @@ SIGNATURES = {
     "maed_train_backward": (_I, [_P, c_void_pp, _P, _P, _P, _I, _I, _P, _Z, _P, _P, _P, _F, _F, c_void_pp, _P]),
     "maed_adam_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _I, _F, _P]),
     "maed_bwd_transpose_planes": (_I, [_P, _L, _I, _I, _I, _P, _L, _I, _P]),
+    "maed_bwd_colsum_chunks": (_I, []),
     "maed_bwd_colsum": (_I, [_P, _L, _I, _I, _F, _I, _P, _P, _P]),
     "maed_bwd_layernorm": (_I, [_P, _L, _P, _L, _P, _I, _I, _F, _P, _P, _L, _P, _P, _P, _P, _P]),
     "maed_bwd_layernorm_partial_rows": (_I, []),

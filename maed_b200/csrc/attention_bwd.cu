@@ -203,8 +203,8 @@ attn_temporal_bwd_kernel(const __half* __restrict__ qkv, long long plane, const 
   float* sg = sv + T * kLd;
   float* sP = sg + T * kLd;
   float* sD = sP + T * (T + 1);
-  const int n = (int)(prob % ntok);
-  const int h = (int)((prob / ntok) % heads);
+  const int h = (int)(prob % heads);                  // heads fastest: adjacent warps touch adjacent 128-byte head slices
+  const int n = (int)((prob / heads) % ntok);
   const int b = (int)(prob / ((long long)ntok * heads));
   const int ld = 3 * heads * kHd, ldo = heads * kHd;
   // gather: lane covers 2 columns (d = 2*lane, 2*lane+1) of every frame row

@@ -202,6 +202,7 @@ int maed_bwd_transpose_planes(const void* in_hi, long long in_plane, int R, int 
                               int ld_out, void* stream) {
   return transpose_planes((const __half*)in_hi, in_plane, R, C, ld_in, (__half*)out_hi, out_plane, ld_out, (cudaStream_t)stream);
 }
+int maed_bwd_colsum_chunks(void) { return kColsumChunks; }
 int maed_bwd_colsum(const float* in, long long ld, int R, int C, float scale, int accumulate, float* scratch, float* out,
                     void* stream) {
   return colsum_f32(in, ld, R, C, scale, accumulate, scratch, out, (cudaStream_t)stream);

@@ -62,7 +62,7 @@ def main():
     x, dy = torch.randn(rows, Cm, device=dev), torch.randn(rows, Cm, device=dev)
     gamma = torch.ones(Cm, device=dev)
     pr = lib.maed_bwd_layernorm_partial_rows()
-    partial, scratch = torch.empty(pr, 2 * Cm, device=dev), torch.empty(64 * 2 * Cm, device=dev)
+    partial, scratch = torch.empty(pr, 2 * Cm, device=dev), torch.empty(lib.maed_bwd_colsum_chunks() * 2 * Cm, device=dev)
     dx, dg, db = torch.empty_like(x), torch.empty(Cm, device=dev), torch.empty(Cm, device=dev)
     ms = timed(lambda: _lib.call("maed_bwd_layernorm", _lib.ptr(dy), C.c_longlong(Cm), _lib.ptr(x), C.c_longlong(Cm), _lib.ptr(gamma),
                                  rows, Cm, C.c_float(1e-6), None, _lib.ptr(dx), C.c_longlong(Cm), _lib.ptr(partial),

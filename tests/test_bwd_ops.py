@@ -70,7 +70,7 @@ def test_colsum(L, R, Cc, ld):
     """scalar path (odd widths) and the 16-byte vectorised path (C, ld multiples of 4); scratch = 256 chunks x C floats"""
     _lib, _ = L
     x = _rand(R, ld, seed=2)
-    scratch = torch.empty(256 * Cc, device=DEV)
+    scratch = torch.empty(_lib.load().maed_bwd_colsum_chunks() * Cc, device=DEV)
     out = torch.full((Cc,), 5.0, device=DEV)
     _lib.call("maed_bwd_colsum", _lib.ptr(x), C.c_longlong(ld), R, Cc, C.c_float(0.5), 1, _lib.ptr(scratch), _lib.ptr(out),
               _lib.stream_ptr())
@@ -88,7 +88,7 @@ def test_layernorm_bwd(L, rows, C_):
     F.layer_norm(xd, (C_,), gd, bd, 1e-6).backward(dy.double())
     pr = _lib.load().maed_bwd_layernorm_partial_rows()
     partial = torch.empty(pr, 2 * C_, device=DEV)
-    scratch = torch.empty(64 * 2 * C_, device=DEV)
+    scratch = torch.empty(_lib.load().maed_bwd_colsum_chunks() * 2 * C_, device=DEV)
     dx, dg, db = torch.empty_like(x), torch.empty(C_, device=DEV), torch.empty(C_, device=DEV)
     _lib.call("maed_bwd_layernorm", _lib.ptr(dy), C.c_longlong(C_), _lib.ptr(x), C.c_longlong(C_), _lib.ptr(gamma), rows, C_,
               C.c_float(1e-6), _lib.ptr(add), _lib.ptr(dx), C.c_longlong(C_), _lib.ptr(partial), _lib.ptr(scratch), _lib.ptr(dg),

@@ -50,9 +50,9 @@ GRAD_CASES = ["grads_vanilla_ktd", "grads_series_ktd", "grads_parallel_ktd", "gr
               "grads_coupling_ktd"]
 
 
-def _model(mode, seed, lib, decoder="ktd"):
+def _model(mode, seed, lib, decoder="ktd", num_blocks=6):
     from maed_b200.models import MAED
-    m = MAED("ste", 6, 12, mode, decoder, 1024, mean_params=synth.mean_params())
+    m = MAED("ste", num_blocks, 12, mode, decoder, 1024, mean_params=synth.mean_params())
     synth.fill_module_(m, seed)
     return m.to(DEV).train().enable_training(True, dropout_p=0.0)
 
@@ -182,7 +182,8 @@ def test_loss_scale_invariance_and_determinism(lib):
 
 def test_fused_adam_matches_torch_adam(lib):
     from maed_b200.train import FusedAdam
-    m1, m2 = _model("vanilla", 6, lib), _model("vanilla", 6, lib)
+    nb = 6 if DEV == "cuda" else 1                                             # (one STE block on the emulator: CPU suite time)
+    m1, m2 = _model("vanilla", 6, lib, num_blocks=nb), _model("vanilla", 6, lib, num_blocks=nb)
     nt = 2 if DEV == "cuda" else 1
     x = synth.synth_frames(1, nt, 6).to(DEV)
     A, B, C_ = _probes(nt, 6)
@@ -214,7 +215,7 @@ def _check_adam_state_dicts(m1, o1, m2, o2):
         assert float(a["step"]) == float(b["step"]) == 1.0
         assert rel_err(a["exp_avg"], b["exp_avg"]) < 1e-6 and rel_err(a["exp_avg_sq"], b["exp_avg_sq"]) < 1e-6
     # torch Adam's checkpoint -> a fresh flat FusedAdam: moments land in the flat buffers, the next step is step 2
-    m3 = _model("vanilla", 6, None)
+    m3 = _model("vanilla", 6, None, num_blocks=len(m1.encoder.blocks))
     o3 = FusedAdam.for_model(m3, lr=1e-4, weight_decay=1e-5)
     o3.load_state_dict(sd2)
     assert o3._flat["step"] == 1
@@ -231,7 +232,7 @@ def test_two_forwards_one_backward_and_gradient_accumulation(lib):
     """The reference's stage-2 iteration (lib/core/trainer.py:186-202): model(video batch), model(image batch), ONE
     loss.backward() — every forward keeps its own tape and the second node accumulates.  Then the two other ways a
     gradient can already be present at backward time: zero_grad(set_to_none=False) and micro-batch accumulation."""
-    m = _model("vanilla", 9, lib)
+    m = _model("vanilla", 9, lib, num_blocks=1 if DEV == "cpu" else 6)      # (one STE block on the emulator: CPU suite time)
     x1, x2 = synth.synth_frames(1, 1, 9).to(DEV), synth.synth_frames(1, 1, 10).to(DEV)
     P1, P2 = _probes(1, 9), _probes(1, 10)
     flat = lambda: torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()  # noqa: E731
