@@ -276,6 +276,12 @@ size_t maed_smpl_scratch_bytes(int n_frames);
 /* betas [R,10], rotmat [R,24,3,3] -> verts [R,6890,3]; joints [R,49,3], or [R,n_reg,3] = J_regressor @ verts when given */
 int maed_smpl_forward(const maed_smpl_assets* assets, const float* betas, const float* rotmat, int R, const float* J_regressor,
                       int n_reg, float* verts, float* joints, void* scratch, size_t scratch_bytes, void* stream);
+/* backward of the same: d_verts [R,6890,3] (or NULL) and d_joints [R,49 | n_reg,3] -> d_betas [R,10], d_rotmat [R,24,3,3]
+ * (what the reference's keypoint losses back-propagate through the body model, lib/core/loss.py:178-192) */
+size_t maed_smpl_backward_scratch_bytes(int n_frames);
+int maed_smpl_backward(const maed_smpl_assets* assets, const float* betas, const float* rotmat, int R, const float* J_regressor,
+                       int n_reg, const float* d_verts, const float* d_joints, float* d_betas, float* d_rotmat, void* scratch,
+                       size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Geometry tail of the training path (maed_b200/csrc/decode_bwd.cu): gradients through rot6d -> rotation matrix -> angle-axis

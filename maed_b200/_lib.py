@@ -126,6 +126,8 @@ SIGNATURES = {
     # ---- SMPL
     "maed_smpl_scratch_bytes": (_Z, [_I]),
     "maed_smpl_forward": (_I, [C.POINTER(MaedSmplAssets), _P, _P, _I, _P, _I, _P, _P, _P, _Z, _P]),
+    "maed_smpl_backward_scratch_bytes": (_Z, [_I]),
+    "maed_smpl_backward": (_I, [C.POINTER(MaedSmplAssets), _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _Z, _P]),
 }
 
 _lib = None

@@ -338,7 +338,13 @@ int maed_smpl_forward(const maed_smpl_assets* assets, const float* betas, const 
   return smpl_forward(reinterpret_cast<const SmplAssets*>(assets), betas, rotmat, R, J_regressor, n_reg, verts, joints, scratch,
                       scratch_bytes, (cudaStream_t)stream);
 }
-
+size_t maed_smpl_backward_scratch_bytes(int n_frames) { return smpl_backward_scratch_bytes(n_frames); }
+int maed_smpl_backward(const maed_smpl_assets* assets, const float* betas, const float* rotmat, int R, const float* J_regressor,
+                       int n_reg, const float* d_verts, const float* d_joints, float* d_betas, float* d_rotmat, void* scratch,
+                       size_t scratch_bytes, void* stream) {
+  return smpl_backward(reinterpret_cast<const SmplAssets*>(assets), betas, rotmat, R, J_regressor, n_reg, d_verts, d_joints, d_betas,
+                       d_rotmat, scratch, scratch_bytes, (cudaStream_t)stream);
+}
 
 // ---- geometry tail of the training path
 int maed_decode_pose_backward(const float* pose6d, int R, const float* d_rotmat, const float* d_aa, int ld_aa, float* d_pose6d,

@@ -22,4 +22,11 @@ size_t smpl_scratch_bytes(int BT);
 int smpl_forward(const SmplAssets* a, const float* betas, const float* rotmat, int BT, const float* J_regressor, int n_reg,
                  float* verts, float* joints, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
+// gradients of (verts, joints) w.r.t. (betas, rotmat): d_verts [BT,6890,3] or nullptr, d_joints [BT,49 | n_reg,3] ->
+// d_betas [BT,10], d_rotmat [BT,24,3,3] (overwritten).  scratch: smpl_backward_scratch_bytes(BT).
+size_t smpl_backward_scratch_bytes(int BT);
+int smpl_backward(const SmplAssets* a, const float* betas, const float* rotmat, int BT, const float* J_regressor, int n_reg,
+                  const float* d_verts, const float* d_joints, float* d_betas, float* d_rotmat, void* scratch,
+                  size_t scratch_bytes, cudaStream_t st);
+
 }  // namespace maed

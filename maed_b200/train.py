@@ -98,33 +98,57 @@ class _Project(torch.autograd.Function):
         return d_kp3d, d_cam, None
 
 
-def smpl_forward_torch(betas, rotmats, head, J_regressor=None):
-    """Differentiable SMPL forward for the training tail (keypoint losses need d kp / d pose, d shape): the algorithm of
-    smplx.lbs.lbs as in csrc/smpl.cu, on the buffers of `SMPLHead` (torch matmuls: ~2 GFLOP per 128 frames).
-    betas [B,10], rotmats [B,24,3,3] -> verts [B,6890,3], joints [B,49,3] (or J_regressor @ verts)."""
-    B = betas.shape[0]
-    v_shaped = head.v_template.reshape(1, -1) + betas @ head.shapedirs.t()                  # [B, 20670]
-    J = (head.J_template.reshape(1, -1) + betas @ head.J_shapedirs.t()).reshape(B, 24, 3)
-    pose_feature = (rotmats[:, 1:] - torch.eye(3, dtype=rotmats.dtype, device=rotmats.device)).reshape(B, 207)
-    v_posed = (v_shaped + pose_feature @ head.posedirs).reshape(B, 6890, 3)
-    parents = head.parents.tolist()
-    bottom = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=rotmats.dtype, device=rotmats.device).expand(B, 1, 4)
-    G = []
-    for j in range(24):
-        rel = J[:, j] - (J[:, parents[j]] if parents[j] >= 0 else 0)
-        M = torch.cat([torch.cat([rotmats[:, j], rel.unsqueeze(-1)], dim=2), bottom], dim=1)
-        G.append(M if parents[j] < 0 else G[parents[j]] @ M)
-    G = torch.stack(G, dim=1)
-    joints24 = G[:, :, :3, 3]
-    A_t = G[:, :, :3, 3] - torch.einsum("bjrc,bjc->bjr", G[:, :, :3, :3], J)
-    A = torch.cat([G[:, :, :3, :3], A_t.unsqueeze(-1)], dim=3).reshape(B, 24, 12)
-    T = torch.einsum("vj,bjk->bvk", head.lbs_weights, A).reshape(B, 6890, 3, 4)
-    verts = torch.einsum("bvrc,bvc->bvr", T[..., :3], v_posed) + T[..., 3]
-    if J_regressor is not None:
-        return verts, torch.einsum("jv,bvk->bjk", J_regressor.to(verts), verts)
-    extra = verts[:, head.extra_vertex_ids.long()]
-    reg = torch.einsum("jv,bvk->bjk", head.J_regressor_extra, verts)
-    return verts, torch.cat([joints24, extra, reg], dim=1)[:, head.joint_map.long()]
+def _smpl_assets(head, dev):
+    if head.v_template.device != dev:
+        head.to(dev)
+    return _lib.MaedSmplAssets(*[_lib.ptr(getattr(head, k)) for k in (
+        "v_template", "shapedirs", "posedirs", "J_template", "J_shapedirs", "lbs_weights", "J_regressor_extra", "parents",
+        "extra_vertex_ids", "joint_map")])
+
+
+class _SmplBody(torch.autograd.Function):
+    """(betas [R,10], rotmat [R,24,3,3]) -> (verts [R,6890,3], joints [R,49,3] or J_regressor @ verts): the body model of the
+    decoders (reference lib/models/ktd.py:100-114 -> lib/models/smpl.py:84-106 -> smplx.lbs.lbs) with BOTH directions in
+    csrc/smpl.cu (maed_smpl_forward / maed_smpl_backward), so the keypoint losses reach pose and shape through CUDA kernels."""
+
+    @staticmethod
+    def forward(ctx, betas, rotmat, head, J_regressor):
+        if not betas.is_cuda:
+            raise RuntimeError("maed_b200 SMPL kernels run on CUDA only; got a %s tensor — there is no CPU fallback" % betas.device)
+        betas, rotmat = betas.contiguous().float(), rotmat.contiguous().float()
+        dev, R = betas.device, betas.shape[0]
+        reg = J_regressor.to(dev, torch.float32).contiguous() if J_regressor is not None else None
+        nj = reg.shape[0] if reg is not None else head.n_joints
+        f32 = dict(dtype=torch.float32, device=dev)
+        verts, joints = torch.empty(R, 6890, 3, **f32), torch.empty(R, nj, 3, **f32)
+        with torch.cuda.device(dev):
+            assets = _smpl_assets(head, dev)
+            nbytes = _lib.load().maed_smpl_scratch_bytes(R)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.call("maed_smpl_forward", C.byref(assets), _lib.ptr(betas), _lib.ptr(rotmat), R, _lib.ptr(reg),
+                      0 if reg is None else reg.shape[0], _lib.ptr(verts), _lib.ptr(joints), _lib.ptr(scratch), C.c_size_t(nbytes),
+                      _lib.stream_ptr())
+        ctx.save_for_backward(betas, rotmat)
+        ctx.head, ctx.reg = head, reg
+        return verts, joints
+
+    @staticmethod
+    def backward(ctx, d_verts, d_joints):
+        betas, rotmat = ctx.saved_tensors
+        head, reg = ctx.head, ctx.reg
+        dev, R = betas.device, betas.shape[0]
+        nj = reg.shape[0] if reg is not None else head.n_joints
+        d_verts = d_verts.contiguous().float() if d_verts is not None else None
+        d_joints = d_joints.contiguous().float() if d_joints is not None else torch.zeros(R, nj, 3, dtype=torch.float32, device=dev)
+        d_betas, d_rot = torch.empty_like(betas), torch.empty_like(rotmat)
+        with torch.cuda.device(dev):
+            assets = _smpl_assets(head, dev)
+            nbytes = _lib.load().maed_smpl_backward_scratch_bytes(R)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.call("maed_smpl_backward", C.byref(assets), _lib.ptr(betas), _lib.ptr(rotmat), R, _lib.ptr(reg),
+                      0 if reg is None else reg.shape[0], _lib.ptr(d_verts), _lib.ptr(d_joints), _lib.ptr(d_betas), _lib.ptr(d_rot),
+                      _lib.ptr(scratch), C.c_size_t(nbytes), _lib.stream_ptr())
+        return d_betas, d_rot, None, None
 
 
 def decode_outputs(pose6d, shape, cam, n_joints=49, smpl_head=None, J_regressor=None):
@@ -132,7 +156,7 @@ def decode_outputs(pose6d, shape, cam, n_joints=49, smpl_head=None, J_regressor=
     nt = pose6d.shape[0]
     theta, rot = _PoseTail.apply(pose6d, shape, cam)
     if smpl_head is not None and smpl_head.has_assets:
-        verts, kp3d = smpl_forward_torch(shape, rot, smpl_head, J_regressor)
+        verts, kp3d = _SmplBody.apply(shape, rot, smpl_head, J_regressor)
         kp2d = _Project.apply(kp3d, cam, kp3d.shape[1])
     else:
         verts, kp3d = pose6d.new_zeros(nt, 6890, 3), pose6d.new_zeros(nt, n_joints, 3)

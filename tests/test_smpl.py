@@ -72,6 +72,46 @@ def test_smpl_forward_matches_oracle(dev, R, use_reg):
     assert rel_err(kp2d, O.project_keypoints(j_ref.float(), cam.cpu())) < 1e-5
 
 
+@pytest.mark.parametrize("R,use_reg", [(3, False), (2, True), (37, False)])
+def test_smpl_backward_matches_oracle_autograd(dev, R, use_reg):
+    """maed_smpl_backward (d_verts, d_joints -> d_betas, d_rotmat) against float64 autograd over the oracle restatement; the
+    49-joint map repeats joints (summed), the vertex-selected joints scatter into d_verts, J_regressor rows replace them."""
+    from maed_b200 import _lib
+    from maed_b200.models.modules import SMPLHead
+    if R > 8 and dev == "cpu":
+        pytest.skip("larger batch: hardware only")
+    a = S.synthetic_assets(2)
+    a64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in a.items()}
+    head = SMPLHead().load_assets(a).to(dev)
+    betas, rot = _inputs(R, 60)
+    g = torch.Generator().manual_seed(61)
+    nj = 17 if use_reg else 49
+    d_verts, d_joints = torch.randn(R, 6890, 3, generator=g), torch.randn(R, nj, 3, generator=g) * 10.0
+    reg = a["J_regressor_h36m"] if use_reg else None
+    bd, rd = betas.double().requires_grad_(True), rot.double().requires_grad_(True)
+    v_ref, j_ref = S.smpl_forward(bd, rd, a64, reg.double() if use_reg else None)
+    ((v_ref * d_verts.double()).sum() + (j_ref * d_joints.double()).sum()).backward()
+    assets = _lib.MaedSmplAssets(*[_lib.ptr(getattr(head, k)) for k in (
+        "v_template", "shapedirs", "posedirs", "J_template", "J_shapedirs", "lbs_weights", "J_regressor_extra", "parents",
+        "extra_vertex_ids", "joint_map")])
+    nbytes = _lib.load().maed_smpl_backward_scratch_bytes(R)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    t = [x.to(dev).contiguous() for x in (betas, rot, d_verts, d_joints)]
+    regd = reg.to(dev).contiguous() if use_reg else None
+    d_betas, d_rot = torch.empty(R, 10, device=dev), torch.empty(R, 24, 3, 3, device=dev)
+    _lib.call("maed_smpl_backward", C.byref(assets), _lib.ptr(t[0]), _lib.ptr(t[1]), R, _lib.ptr(regd), 17 if use_reg else 0,
+              _lib.ptr(t[2]), _lib.ptr(t[3]), _lib.ptr(d_betas), _lib.ptr(d_rot), _lib.ptr(scratch), C.c_size_t(nbytes),
+              _lib.stream_ptr())
+    assert rel_err(d_betas, bd.grad) < 2e-5 and rel_err(d_rot, rd.grad) < 2e-5
+    # without a vertex gradient (what the reference's losses produce: only the joints are penalised)
+    bd.grad = rd.grad = None
+    _, j_ref = S.smpl_forward(bd, rd, a64, reg.double() if use_reg else None)
+    (j_ref * d_joints.double()).sum().backward()
+    _lib.call("maed_smpl_backward", C.byref(assets), _lib.ptr(t[0]), _lib.ptr(t[1]), R, _lib.ptr(regd), 17 if use_reg else 0,
+              None, _lib.ptr(t[3]), _lib.ptr(d_betas), _lib.ptr(d_rot), _lib.ptr(scratch), C.c_size_t(nbytes), _lib.stream_ptr())
+    assert rel_err(d_betas, bd.grad) < 2e-5 and rel_err(d_rot, rd.grad) < 2e-5
+
+
 @pytest.mark.gpu
 def test_model_outputs_with_body_model(lib):
     from maed_b200.models import MAED

@@ -62,8 +62,9 @@ def test_joint_selection_and_regressor_override():
 
 
 def test_training_tail_body_model_matches_oracle_and_is_differentiable():
-    """maed_b200.train.smpl_forward_torch (the autograd tail of the training path) against the oracle restatement; the
-    geometry nodes around it (csrc/decode_bwd.cu) run on the CUDA-on-CPU test build."""
+    """The autograd tail of the training path — rot6d -> rotmat (csrc/decode_bwd.cu), the body model (csrc/smpl.cu, forward
+    and backward kernels behind maed_b200.train._SmplBody), the projection — on the CUDA-on-CPU test build against the oracle
+    restatement, values and gradients (float64 autograd over the oracle)."""
     import os
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
@@ -82,5 +83,13 @@ def test_training_tail_body_model_matches_oracle_and_is_differentiable():
         assert (out["verts"].double() - v_ref).abs().max() < 1e-5 and (out["kp_3d"].double() - j_ref).abs().max() < 1e-5
         (out["kp_2d"].square().sum() + out["kp_3d"].sum()).backward()
         assert pose6d.grad is not None and betas.grad is not None and torch.isfinite(pose6d.grad).all() and pose6d.grad.abs().sum() > 0
+        # the same scalar through the oracle in float64
+        from oracle import maed_oracle as O
+        p64, b64 = pose6d.detach().double().requires_grad_(True), betas.detach().double().requires_grad_(True)
+        a64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in a.items()}
+        _, j64 = S.smpl_forward(b64, O.rot6d_to_rotmat(p64).reshape(3, 24, 3, 3), a64)
+        (O.project_keypoints(j64, cam.double()).square().sum() + j64.sum()).backward()
+        err = lambda x, y: ((x.double() - y).norm() / y.norm()).item()  # noqa: E731
+        assert err(pose6d.grad, p64.grad) < 1e-4 and err(betas.grad, b64.grad) < 1e-4
         out17 = train.decode_outputs(pose6d, betas, cam, 17, head, a["J_regressor_h36m"])
         assert out17["kp_3d"].shape == (3, 17, 3)
