@@ -229,7 +229,8 @@ int maed_bwd_ktd_tree(const float* d_pose6d, const float* d_shape, const float* 
                       int R, float scale, float* g_total, float* d_base, int ld, float* d_w_anc, void* stream);
 /* kind: 0 spatial (per frame; CUDA-core cross-check), 1 temporal (per token across the T frames), 2 coupling (all T * ntok tokens
  * of a clip; needs scratch of B * heads * T * ntok * 3 floats), 3 spatial on the tensor cores (tcgen05, ntok <= 208: what the train
- * step runs; scratch of B*T*ntok * heads*64 floats holds the fp16 hi/lo planes of d_out); scratch NULL otherwise */
+ * step runs; scratch of B*T*ntok * heads*64 floats holds the fp16 hi/lo planes of d_out), 4 temporal on the tensor cores (same
+ * kernel on TMA-gathered {64, 128/T, T} tiles, T in {4, 8, 16, 32}; scratch as for 3); scratch NULL otherwise */
 int maed_bwd_attention(int kind, const void* qkv_hi, long long qkv_plane, const float* d_out, int B, int T, int ntok, int heads,
                        float scale, int accumulate, float* d_qkv, float* scratch, void* stream);
 size_t maed_bwd_wgrad_slab_floats(int Mo, int No, int R);

@@ -657,6 +657,10 @@ int attn_temporal(const __half* qkv_hi, long long qkv_plane, int B, int T, int n
                   __half* out_hi, long long out_plane, cudaStream_t st) {
   MAED_CHECK_ARG(T >= 1 && T <= 32, "attn_temporal: T=%d unsupported (1..32)", T);
   MAED_CHECK_ARG(qkv_plane % 8 == 0 && out_plane % 4 == 0, "attn_temporal: plane strides must be 16-byte aligned");
+  // tensor-core version (TMA-gathered 128-row tiles); MAED_B200_TEMPORAL_TC=0 selects the CUDA-core kernel below
+  static const bool tc_on = [] { const char* v = getenv("MAED_B200_TEMPORAL_TC"); return !(v && v[0] == '0'); }();
+  if (tc_on && attn_temporal_tc_supported(T, qkv_plane) && (!out_hi || out_plane % 8 == 0))
+    return attn_temporal_tc(qkv_hi, qkv_plane, B, T, ntok, heads, scale, out_f32, out_hi, out_plane, st);
   const long long total = (long long)B * heads * ntok;
   const long long cap = (long long)sm_count() * 32;
 #define TEMPORAL_LAUNCH(SEGS, TMAX, WARPS)                                                                          \

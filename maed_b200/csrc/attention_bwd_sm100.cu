@@ -19,6 +19,9 @@
 //
 // Split precision as everywhere on the path: every operand is an fp16 hi/lo pair, three MMAs per product (hi*hi + lo*hi +
 // hi*lo), fp32 accumulation in TMEM, so the gradients are fp32-class (tests: 2e-5 against float64 autograd).
+// The same kernel serves the TEMPORAL attention (vision_transformer.py:216-228; template TEMPORAL): an item is then (clip, head,
+// group of NPT = 128 / T tokens), its operand tiles are TMA boxes {64, NPT, T} of the qkv / dO planes (row r = t * NPT + n, see
+// attention_temporal_sm100.cu) and "valid key of query row i" means "same token" (c mod NPT == i mod NPT) instead of c < ntok.
 // First version: the phases of an item run one after the other (one thread issues the TMA loads and the MMAs, eight warps
 // do the element-wise work); round-2 measurement decides whether the phases need software pipelining like the forward kernel.
 #include "bwd_kernels.h"
@@ -37,11 +40,12 @@ constexpr int kBufBytes = kRows * 128; // one plane of one operand: 208 rows x 1
 constexpr int kThreadsB = 384;         // warp 0: TMA + MMA issue, warp 1: TMEM alloc, warps 4-11: element-wise (2 threads / row)
 constexpr int kSplit = 112;            // column split: [0,112) | [112,208)  (orientation A halves, orientation B chunks)
 // TMEM column maps
-constexpr uint32_t kS = 0, kP = 208, kDQ = 416;            // orientation A: S | dP -> dS | dQ
+constexpr uint32_t kS = 0, kP = 208, kDQ = 416;            // orientation A: S | dP -> dS | dQ  (temporal: 128 of the 208 columns)
 constexpr uint32_t kST = 0, kPT = 112, kDV = 224, kDK = 288;   // orientation B: S^T -> P^T | dP^T -> dS^T | dV | dK
 
 struct BwdParams {
   int BT, ntok, heads;
+  int T, groups;                       // temporal: frames per clip, token groups per (clip, head); BT = clips
   float scale, scale_log2e;
   float* d_qkv;                        // fp32 [BT*ntok, 3*heads*64]
   int accumulate;
@@ -66,9 +70,11 @@ __device__ __forceinline__ void pack16(const float (&v)[16], uint32_t (&pk)[16])
   }
 }
 
+template <bool TEMPORAL, int NPT>
 __global__ void __launch_bounds__(kThreadsB, 1)
-attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
   using namespace sm100;
+  constexpr int ROWS = TEMPORAL ? 128 : kRows;            // key rows / score columns of an item
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // operand buffers [hi | lo]; an M = 128 tile starting at row 128 reads 48 rows past its buffer into the next one (finite fp16
@@ -88,13 +94,15 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int items = p.BT * p.heads;
+  const int items = TEMPORAL ? p.BT * p.heads * p.groups : p.BT * p.heads;
   const int ntok = p.ntok;
-  const int tiles = (ntok + 127) / 128;                   // 128-row tiles of queries (orientation A) / keys (orientation B)
-  const int chunks = ntok > kSplit ? 2 : 1;               // query column chunks of orientation B
+  const int tiles = TEMPORAL ? 1 : (ntok + 127) / 128;    // 128-row tiles of queries (orientation A) / keys (orientation B)
+  const int chunks = (TEMPORAL || ntok > kSplit) ? 2 : 1; // query column chunks of orientation B
   const int ld3 = 3 * p.heads * kD;
 
   for (int i = threadIdx.x; i < 6144 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sPad)[i] = 0u;
+  if (TEMPORAL)   // token groups at the end of a frame leave part of a tile unwritten by TMA: start from finite (zero) operands
+    for (int i = threadIdx.x; i < 8 * kBufBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0 && elect_one()) { prefetch_tmap(&tmQKV); prefetch_tmap(&tmDO); }
   if (warp == 1 && elect_one()) {
     mbar_init(ld_full, 1);
@@ -135,20 +143,31 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           umma_f16_ts(d, a_tmem + kk * 16, bl, idesc, 1);
         }
       };
-      constexpr uint32_t id208 = umma_idesc_f16(128, kRows, 0, 0, 0);
+      constexpr uint32_t id208 = umma_idesc_f16(128, ROWS, 0, 0, 0);
       constexpr uint32_t id112 = umma_idesc_f16(128, kSplit, 0, 0, 0);
-      constexpr uint32_t id96 = umma_idesc_f16(128, kRows - kSplit, 0, 0, 0);
+      constexpr uint32_t id96 = umma_idesc_f16(128, ROWS - kSplit, 0, 0, 0);
       constexpr uint32_t id64 = umma_idesc_f16(128, kD, 0, 0, 1);          // B MN-major
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int bt = item / p.heads, h = item % p.heads;
-        const int row0 = bt * ntok;
         // ---- operands of the item (the previous item's MMAs have all retired: its last ew_done was waited for below)
-        mbar_arrive_expect_tx(ld_full, 8 * kBufBytes);
-        for (int pl = 0; pl < 2; ++pl) {
-          tma_load_3d(sDO + pl * kBufBytes, &tmDO, ld_full, h * kD, row0, pl);
-          tma_load_3d(sQ + pl * kBufBytes, &tmQKV, ld_full, h * kD, row0, pl);
-          tma_load_3d(sK + pl * kBufBytes, &tmQKV, ld_full, p.heads * kD + h * kD, row0, pl);
-          tma_load_3d(sV + pl * kBufBytes, &tmQKV, ld_full, 2 * p.heads * kD + h * kD, row0, pl);
+        if (TEMPORAL) {
+          const int g = item % p.groups, h = (item / p.groups) % p.heads, b = item / (p.groups * p.heads);
+          mbar_arrive_expect_tx(ld_full, 8 * 128 * 128);
+          for (int pl = 0; pl < 2; ++pl) {
+            tma_load_5d(sDO + pl * kBufBytes, &tmDO, ld_full, h * kD, g * NPT, 0, b, pl);
+            tma_load_5d(sQ + pl * kBufBytes, &tmQKV, ld_full, h * kD, g * NPT, 0, b, pl);
+            tma_load_5d(sK + pl * kBufBytes, &tmQKV, ld_full, p.heads * kD + h * kD, g * NPT, 0, b, pl);
+            tma_load_5d(sV + pl * kBufBytes, &tmQKV, ld_full, 2 * p.heads * kD + h * kD, g * NPT, 0, b, pl);
+          }
+        } else {
+          const int bt = item / p.heads, h = item % p.heads;
+          const int row0 = bt * ntok;
+          mbar_arrive_expect_tx(ld_full, 8 * kBufBytes);
+          for (int pl = 0; pl < 2; ++pl) {
+            tma_load_3d(sDO + pl * kBufBytes, &tmDO, ld_full, h * kD, row0, pl);
+            tma_load_3d(sQ + pl * kBufBytes, &tmQKV, ld_full, h * kD, row0, pl);
+            tma_load_3d(sK + pl * kBufBytes, &tmQKV, ld_full, p.heads * kD + h * kD, row0, pl);
+            tma_load_3d(sV + pl * kBufBytes, &tmQKV, ld_full, 2 * p.heads * kD + h * kD, row0, pl);
+          }
         }
         mbar_wait(ld_full, ph_ld);
         ph_ld ^= 1;
@@ -160,7 +179,7 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           umma_commit(mma_done);
           mbar_wait(ew_done, ph_ew); ph_ew ^= 1;                           // dS_g in TMEM (over dP), lse / D in shared memory
           tc_fence_after();
-          mma_ts(tmem_base + kDQ, tmem_base + kP, aK, kRows / 16, false, id64);   // dQ_g = dS_g K
+          mma_ts(tmem_base + kDQ, tmem_base + kP, aK, ROWS / 16, false, id64);    // dQ_g = dS_g K
           umma_commit(mma_done);
           mbar_wait(ew_done, ph_ew); ph_ew ^= 1;                           // dQ_g has left TMEM
           tc_fence_after();
@@ -175,7 +194,7 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             umma_commit(mma_done);
             mbar_wait(ew_done, ph_ew); ph_ew ^= 1;                         // P^T, dS^T written back in place
             tc_fence_after();
-            const int ks = (c == 0 ? kSplit : kRows - kSplit) / 16;
+            const int ks = (c == 0 ? kSplit : ROWS - kSplit) / 16;
             mma_ts(tmem_base + kDV, tmem_base + kST, aDO + i0 * 128, ks, c != 0, id64);   // dV_t += P^T dO_c
             mma_ts(tmem_base + kDK, tmem_base + kPT, aQ + i0 * 128, ks, c != 0, id64);    // dK_t += dS^T Q_c
             // (tcgen05.mma executes in issue order: the next chunk's S^T / dP^T may overwrite these operands behind them)
@@ -197,6 +216,9 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
     const uint32_t pair_bar = 1 + wq;
     const float c2 = p.scale_log2e;
     uint32_t ph_mma = 0;
+    const int my_nl = trow % NPT;                         // temporal: token of this thread's tile row within the group
+    // is score column `col` (key index in orientation A, query index in orientation B) paired with this thread's row?
+    auto valid = [&](int col) -> bool { return TEMPORAL ? ((col % NPT) == my_nl) : (col < ntok); };
     auto arrive_ew = [&]() {
       tc_fence_before();
       __syncwarp();
@@ -214,12 +236,29 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       }
     };
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const int bt = item / p.heads, h = item % p.heads;
-      float* out_item = p.d_qkv + (long long)bt * ntok * ld3 + h * kD + half * 32;
+      // global row of this thread's tile row `r` (query row in orientation A, key row in orientation B), or -1
+      int h, tg = 0, tb = 0;
+      long long row_base;
+      if (TEMPORAL) {
+        tg = item % p.groups; h = (item / p.groups) % p.heads; tb = item / (p.groups * p.heads);
+        row_base = 0;
+      } else {
+        const int bt = item / p.heads;
+        h = item % p.heads;
+        row_base = (long long)bt * ntok;
+      }
+      auto grow = [&](int r) -> long long {
+        if (TEMPORAL) {
+          const int n = tg * NPT + r % NPT, t = r / NPT;
+          return (n < ntok && t < p.T) ? ((long long)tb * p.T + t) * ntok + n : -1;
+        }
+        return r < ntok ? row_base + r : -1;
+      };
+      float* out_item = p.d_qkv + h * kD + half * 32;
       // ------------------------------------------------------------------------------------------ orientation A
       for (int g = 0; g < tiles; ++g) {
         const uint32_t tS = tmem_base + kS + lane_off, tP = tmem_base + kP + lane_off, tQ = tmem_base + kDQ + lane_off;
-        const int cbeg = half ? kSplit : 0, cend = half ? kRows : kSplit;
+        const int cbeg = half ? kSplit : 0, cend = half ? ROWS : kSplit;
         mbar_wait(mma_done, ph_mma); ph_mma ^= 1;
         tc_fence_after();
         uint32_t r[32], q[32];
@@ -233,7 +272,7 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j < ncols && col0 + j < ntok) mx = fmaxf(mx, __uint_as_float(r[j]));
+            if (j < ncols && valid(col0 + j)) mx = fmaxf(mx, __uint_as_float(r[j]));
         }
         x_mine[0] = mx;
         bar_sync(pair_bar, 64);
@@ -252,7 +291,7 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j < ncols && col0 + j < ntok) {
+            if (j < ncols && valid(col0 + j)) {
               const float e = ex2(__uint_as_float(r[j]) * c2 - mb);
               sum += e;
               dot = fmaf(e, __uint_as_float(q[j]), dot);
@@ -281,7 +320,7 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float e = ex2(__uint_as_float(r16[j]) * c2 - mb);
-            v[j] = (col0 + j < ntok) ? e * ps * (__uint_as_float(q16[j]) - Di) : 0.f;
+            v[j] = valid(col0 + j) ? e * ps * (__uint_as_float(q16[j]) - Di) : 0.f;
           }
           pack16(v, pk);
           tmem_st_32x32b_x16(tP + col0, pk);
@@ -295,8 +334,8 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         tmem_ld_32x32b_x32(tQ + half * 32, r);
         tmem_ld_wait();
         arrive_ew();
-        const int qi = g * 128 + trow;
-        if (qi < ntok) store32(r, out_item + (long long)qi * ld3);
+        const long long qrow = grow(g * 128 + trow);
+        if (qrow >= 0) store32(r, out_item + qrow * ld3);
       }
       // ------------------------------------------------------------------------------------------ orientation B
       bar_sync(5, 256);                                   // lse / D of every query row written (all element-wise warps)
@@ -304,8 +343,8 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         const uint32_t tST = tmem_base + kST + lane_off, tPT = tmem_base + kPT + lane_off;
         for (int c = 0; c < chunks; ++c) {
           const int i0 = c * kSplit;
-          const int ni = c == 0 ? kSplit : kRows - kSplit;            // 112 | 96 query columns
-          const int cbeg = half ? 64 : 0, cend = half ? ni : 64;
+          const int ni = c == 0 ? kSplit : ROWS - kSplit;             // 112 | 96 (temporal: 16) query columns
+          const int cbeg = half ? 64 : 0, cend = half ? ni : min(64, ni);
           mbar_wait(mma_done, ph_mma); ph_mma ^= 1;
           tc_fence_after();
 #pragma unroll 1
@@ -323,7 +362,7 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
               const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const bool ok = i + u < ntok;
+                const bool ok = valid(i + u);
                 const float pr = ok ? ex2(__uint_as_float(r16[j4 + u]) * c2 - ls[u]) : 0.f;
                 pv[j4 + u] = pr;
                 dv[j4 + u] = ok ? pr * p.scale * (__uint_as_float(q16[j4 + u]) - dd[u]) : 0.f;
@@ -345,10 +384,10 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         tmem_ld_32x32b_x32(tmem_base + kDK + lane_off + half * 32, rk);
         tmem_ld_wait();
         arrive_ew();
-        const int kj = t * 128 + trow;
-        if (kj < ntok) {
-          store32(rk, out_item + (long long)kj * ld3 + p.heads * kD);
-          store32(rv, out_item + (long long)kj * ld3 + 2 * p.heads * kD);
+        const long long krow = grow(t * 128 + trow);
+        if (krow >= 0) {
+          store32(rk, out_item + krow * ld3 + p.heads * kD);
+          store32(rv, out_item + krow * ld3 + 2 * p.heads * kD);
         }
       }
     }
@@ -358,6 +397,8 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
+
+constexpr size_t kBwdSmem = 1024 + 8 * (size_t)kBufBytes + 6144 + (256 + 256 + 2 * 128 * 4) * sizeof(float) + 64;
 
 }  // namespace
 
@@ -384,19 +425,62 @@ int attn_spatial_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half*
     MAED_PROPAGATE(make_tmap_f16(&tmDO, dout_hi, 3, dims, str, box));
   }
   BwdParams p;
-  p.BT = BT; p.ntok = ntok; p.heads = heads; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
+  p.BT = BT; p.ntok = ntok; p.heads = heads; p.T = 1; p.groups = 1; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.d_qkv = d_qkv; p.accumulate = accumulate;
-  const size_t smem = 1024 + 8 * (size_t)kBufBytes + 6144 + (256 + 256 + 2 * 128 * 4) * sizeof(float) + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    MAED_CUDA_CHECK(cudaFuncSetAttribute(attn_spatial_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MAED_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
     attr_set = true;
   }
   const int items = BT * heads;
   const int grid = items < sm_count() ? items : sm_count();
-  attn_spatial_bwd_tc_kernel<<<grid, kThreadsB, smem, st>>>(tmQKV, tmDO, p);
+  attn_bwd_tc_kernel<false, 1><<<grid, kThreadsB, kBwdSmem, st>>>(tmQKV, tmDO, p);
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
+}
+
+template <int NPT>
+static int launch_temporal_bwd(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const BwdParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MAED_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    attr_set = true;
+  }
+  const int items = p.BT * p.heads * p.groups;
+  const int grid = items < sm_count() ? items : sm_count();
+  attn_bwd_tc_kernel<true, NPT><<<grid, kThreadsB, kBwdSmem, st>>>(tmQKV, tmDO, p);
+  MAED_BW_LAUNCH_CHECK();
+  return MAED_OK;
+}
+
+// temporal attention backward on the same kernel: B clips, T frames (4, 8, 16, 32), d_out as fp16 hi/lo planes [B*T*ntok, heads*64]
+int attn_temporal_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int B, int T,
+                         int ntok, int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st) {
+  MAED_CHECK_ARG(qkv_hi && dout_hi && d_qkv, "attn_temporal_bwd_tc: null argument");
+  MAED_CHECK_ARG(T == 4 || T == 8 || T == 16 || T == 32, "attn_temporal_bwd_tc: T=%d unsupported (4, 8, 16, 32)", T);
+  const long long rows = (long long)B * T * ntok;
+  const int ld3 = 3 * heads * kD, ldo = heads * kD, npt = 128 / T;
+  MAED_CHECK_ARG(qkv_plane >= rows * ld3 && dout_plane >= rows * ldo && qkv_plane % 8 == 0 && dout_plane % 8 == 0,
+                 "attn_temporal_bwd_tc: operand planes overlap or are misaligned");
+  CUtensorMap tmQKV, tmDO;
+  auto tmap5 = [&](CUtensorMap* tm, const __half* base, long long plane, int ld) -> int {
+    const uint64_t dims[5] = {(uint64_t)ld, (uint64_t)ntok, (uint64_t)T, (uint64_t)B, 2};
+    const uint64_t str[4] = {(uint64_t)ld * 2, (uint64_t)ntok * ld * 2, (uint64_t)T * ntok * ld * 2, (uint64_t)plane * 2};
+    const uint32_t box[5] = {64, (uint32_t)npt, (uint32_t)T, 1, 1};
+    return make_tmap_f16(tm, base, 5, dims, str, box);
+  };
+  MAED_PROPAGATE(tmap5(&tmQKV, qkv_hi, qkv_plane, ld3));
+  MAED_PROPAGATE(tmap5(&tmDO, dout_hi, dout_plane, ldo));
+  BwdParams p;
+  p.BT = B; p.ntok = ntok; p.heads = heads; p.T = T; p.groups = (ntok + npt - 1) / npt; p.scale = scale;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.d_qkv = d_qkv; p.accumulate = accumulate;
+  switch (npt) {
+    case 32: return launch_temporal_bwd<32>(tmQKV, tmDO, p, st);
+    case 16: return launch_temporal_bwd<16>(tmQKV, tmDO, p, st);
+    case 8: return launch_temporal_bwd<8>(tmQKV, tmDO, p, st);
+    default: return launch_temporal_bwd<4>(tmQKV, tmDO, p, st);
+  }
 }
 
 }  // namespace maed

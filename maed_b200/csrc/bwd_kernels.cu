@@ -133,13 +133,25 @@ __global__ void colsum_stage1_vec4_kernel(const float* __restrict__ in_f, const 
   s.w = (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w);
   *reinterpret_cast<float4*>(partial + (long long)chunk * C + c) = s;
 }
-__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int C, float scale, int accumulate,
-                                     float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// stage 2: 32 columns per block, 8 threads per column walk the chunk partials k = g, g + 8, ... (independent loads in flight),
+// then a fixed-order sum of the 8 group sums: deterministic, and ~4 us instead of 14 us for 256 chunks (192 launches per step).
+__global__ void __launch_bounds__(256)
+colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int C, float scale, int accumulate,
+                     float* __restrict__ out) {
+  __shared__ float s_g[8][33];
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
-  for (int k = 0; k < chunks; ++k) s += partial[(long long)k * C + c];
-  out[c] = (accumulate ? out[c] : 0.f) + scale * s;
+  if (c < C)
+    for (int k = g; k < chunks; k += 8) s += partial[(long long)k * C + c];
+  s_g[g][cl] = s;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s_g[k][cl];
+    out[c] = (accumulate ? out[c] : 0.f) + scale * t;
+  }
 }
 static int colsum_impl(const float* in_f, const __half* in_h, long long plane, long long ld, int R, int C, float scale,
                        int accumulate, float* scratch, float* out, cudaStream_t st) {
@@ -153,7 +165,7 @@ static int colsum_impl(const float* in_f, const __half* in_h, long long plane, l
     if (in_h) colsum_stage1_vec4_kernel<true><<<vgrid, threads, 0, st>>>(nullptr, in_h, plane, ld, R, C, scratch);
     else colsum_stage1_vec4_kernel<false><<<vgrid, threads, 0, st>>>(in_f, nullptr, 0, ld, R, C, scratch);
     MAED_BW_LAUNCH_CHECK();
-    colsum_stage2_kernel<<<cdiv(C, 128), 128, 0, st>>>(scratch, chunks, C, scale, accumulate, out);
+    colsum_stage2_kernel<<<cdiv(C, 32), 256, 0, st>>>(scratch, chunks, C, scale, accumulate, out);
     MAED_BW_LAUNCH_CHECK();
     return MAED_OK;
   }
@@ -161,7 +173,7 @@ static int colsum_impl(const float* in_f, const __half* in_h, long long plane, l
   if (in_h) colsum_stage1_kernel<true><<<grid, 128, 0, st>>>(nullptr, in_h, plane, ld, R, C, scratch);
   else colsum_stage1_kernel<false><<<grid, 128, 0, st>>>(in_f, nullptr, 0, ld, R, C, scratch);
   MAED_BW_LAUNCH_CHECK();
-  colsum_stage2_kernel<<<cdiv(C, 128), 128, 0, st>>>(scratch, chunks, C, scale, accumulate, out);
+  colsum_stage2_kernel<<<cdiv(C, 32), 256, 0, st>>>(scratch, chunks, C, scale, accumulate, out);
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
 }

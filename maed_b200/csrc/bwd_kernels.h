@@ -115,6 +115,9 @@ int attn_spatial_bwd(const __half* qkv_hi, long long qkv_plane, const float* d_o
 // tcgen05 version (attention_bwd_sm100.cu): d_out given as fp16 hi/lo planes [BT*ntok, heads*64]; ntok <= 208
 int attn_spatial_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int BT, int ntok,
                         int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st);
+// temporal attention backward on the same tcgen05 kernel (TMA-gathered {64, 128/T, T} tiles); T in {4, 8, 16, 32}
+int attn_temporal_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int B, int T,
+                         int ntok, int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st);
 int attn_temporal_bwd(const __half* qkv_hi, long long qkv_plane, const float* d_out, int B, int T, int ntok, int heads,
                       float scale, int accumulate, float* d_qkv, cudaStream_t st);
 

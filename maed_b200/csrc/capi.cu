@@ -302,6 +302,13 @@ int maed_bwd_attention(int kind, const void* qkv_hi, long long qkv_plane, const 
     return attn_spatial_bwd_tc((const __half*)qkv_hi, qkv_plane, (const __half*)scratch, n, B * T, ntok, heads, scale, accumulate,
                                d_qkv, st);
   }
+  if (kind == 4) {   // temporal on the tensor cores; scratch as for kind 3
+    MAED_CHECK_ARG(scratch, "maed_bwd_attention(kind 4): scratch of B*T*ntok * heads*64 floats required");
+    const long long n = (long long)B * T * ntok * heads * 64;
+    MAED_PROPAGATE(split_f32(d_out, (__half*)scratch, n, n, st));
+    return attn_temporal_bwd_tc((const __half*)qkv_hi, qkv_plane, (const __half*)scratch, n, B, T, ntok, heads, scale, accumulate,
+                                d_qkv, st);
+  }
   set_error("maed_bwd_attention: unknown kind %d", kind);
   return MAED_ERR_ARG;
 }

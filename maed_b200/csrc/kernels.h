@@ -82,6 +82,10 @@ int broadcast_add(float* x, const float* v, int BT, int ntok, int C, cudaStream_
 // qkv planes: [BT*ntok, 3*H*64] (q | k | v, head-major inside each).  Outputs fp32 or planes [BT*ntok, H*64].
 int attn_spatial(const __half* qkv_hi, long long qkv_plane, int BT, int ntok, int heads, float scale, int nsplit,
                  float* out_f32, __half* out_hi, long long out_plane, cudaStream_t st);
+// tcgen05 version (attention_temporal_sm100.cu): T in {4, 8, 16, 32}, split precision; attn_temporal dispatches to it
+bool attn_temporal_tc_supported(int T, long long qkv_plane);
+int attn_temporal_tc(const __half* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads, float scale, float* out_f32,
+                     __half* out_hi, long long out_plane, cudaStream_t st);
 int attn_temporal(const __half* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads, float scale,
                   float* out_f32, __half* out_hi, long long out_plane, cudaStream_t st);
 // generic CUDA-core fp32 attention over `seq` tokens addressed as row = base(b) + i*row_step (coupling mode,

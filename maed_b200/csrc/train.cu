@@ -690,6 +690,19 @@ static int spatial_bwd(const Ctx& c, const __half* qkv, const float* d_out, floa
   return attn_spatial_bwd_tc(qkv, w.qkv_plane, w.pl_a, w.pl_a_plane, c.BT, 197, heads, 0.125f, 0, dqkv, c.st);
 }
 
+// temporal attention backward: tensor-core kernel when T is 4 / 8 / 16 / 32 and a token group is full (ntok >= 128 / T)
+static int temporal_bwd(const Ctx& c, const __half* qkv, const float* d_out, int ntok, int accumulate, float* dqkv) {
+  TrainWs& w = c.w;
+  const int heads = c.e.cfg.num_heads, T = c.T;
+  static const bool tc_on = [] { const char* v = getenv("MAED_B200_TEMPORAL_TC"); return !(v && v[0] == '0'); }();
+  if (tc_on && (T == 4 || T == 8 || T == 16 || T == 32) && ntok >= 128 / T) {
+    const long long n = (long long)c.BT * ntok * heads * 64;
+    MAED_PROPAGATE(split_f32(d_out, w.pl_a, w.pl_a_plane, n, c.st));
+    return attn_temporal_bwd_tc(qkv, w.qkv_plane, w.pl_a, w.pl_a_plane, c.N, T, ntok, heads, 0.125f, accumulate, dqkv, c.st);
+  }
+  return attn_temporal_bwd(qkv, w.qkv_plane, d_out, c.N, T, ntok, heads, 0.125f, accumulate, dqkv, c.st);
+}
+
 // dW [Nw, Kw] = scale * dY^T X  for a linear layer; dY, X as planes [R, *] (dense rows)
 static int linear_wgrad(const Ctx& c, const __half* dy, long long dy_plane, int Nw, const __half* x, long long x_plane, int Kw,
                         int R, int accumulate, float* dW) {
@@ -1023,10 +1036,10 @@ int train_backward(const Engine* ep, const void* const* params, const void* pack
                                 d_pool, 0));
       MAED_PROPAGATE(blend_bwd_pool(d_pool, BT, ntok, C, w.dxs, w.dxt, st));
       MAED_PROPAGATE(spatial_bwd(c, t.qkv, w.dxs, dqkv));
-      MAED_PROPAGATE(attn_temporal_bwd(t.qkv, w.qkv_plane, w.dxt, N, T, ntok, heads, scale, 1, dqkv, st));
+      MAED_PROPAGATE(temporal_bwd(c, t.qkv, w.dxt, ntok, 1, dqkv));
     } else if (cf.mode == MODE_SERIES) {
       // ao = temporal(qkv2), qkv2 = qkv(ao_s), ao_s = spatial(qkv), qkv = qkv(ln1): the qkv weights are used twice
-      MAED_PROPAGATE(attn_temporal_bwd(t.qkv2, w.qkv_plane, d_ao, N, T, ntok, heads, scale, 0, dqkv, st));
+      MAED_PROPAGATE(temporal_bwd(c, t.qkv2, d_ao, ntok, 0, dqkv));
       MAED_PROPAGATE(split_f32(dqkv, w.pl_a, w.pl_a_plane, (long long)rows * 3 * C, st));
       MAED_PROPAGATE(colsum_f32(dqkv, 3 * C, rows, 3 * C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.qkv_b), st));
       MAED_PROPAGATE(linear_wgrad(c, w.pl_a, w.pl_a_plane, 3 * C, t.ao_s, w.ln_plane, C, rows, 0, c.G(ix.qkv_w)));

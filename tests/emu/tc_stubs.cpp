@@ -446,6 +446,19 @@ int attn_spatial_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half*
   return attn_spatial_bwd(qkv_hi, qkv_plane, d.data(), BT, ntok, heads, scale, accumulate, d_qkv, st);
 }
 
+int attn_temporal_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int B, int T,
+                         int ntok, int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st) {
+  MAED_CHECK_ARG(qkv_hi && dout_hi && d_qkv, "attn_temporal_bwd_tc: null argument");
+  MAED_CHECK_ARG(T == 4 || T == 8 || T == 16 || T == 32, "attn_temporal_bwd_tc: T=%d unsupported (4, 8, 16, 32)", T);
+  const long long rows = (long long)B * T * ntok;
+  const int ld3 = 3 * heads * 64, ldo = heads * 64;
+  MAED_CHECK_ARG(qkv_plane >= rows * ld3 && dout_plane >= rows * ldo && qkv_plane % 8 == 0 && dout_plane % 8 == 0,
+                 "attn_temporal_bwd_tc: operand planes overlap or are misaligned");
+  std::vector<float> d((size_t)rows * ldo);
+  planes_to_dense(dout_hi, dout_plane, rows, ldo, ldo, d.data());
+  return attn_temporal_bwd(qkv_hi, qkv_plane, d.data(), B, T, ntok, heads, scale, accumulate, d_qkv, st);
+}
+
 int gemm_wgrad_rows(const __half* dY, long long dy_plane, int ld_dy, const __half* X, long long x_plane, int ld_x, int No_x,
                     int Mo, int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, cudaStream_t) {
   Prof prof(4);
