@@ -239,6 +239,11 @@ int maed_bwd_wgrad_splitk(const void* A, long long a_plane, int lda, const void*
 /* the same on row-major operands: D[Mo, No] (+)= scale * dY[R, Mo]^T X[R, No_x] (MN-major tcgen05 operands, no transposes) */
 int maed_bwd_wgrad_rows(const void* dY, long long dy_plane, int ld_dy, const void* X, long long x_plane, int ld_x, int No_x, int Mo,
                         int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, void* stream);
+/* weight gradient of a stride-1 KH x KW convolution with an implicit im2col operand (5-D TMA boxes of the NHWC planes shifted by
+ * the tap): D[Cout, KH*KW*Cin] (+)= scale * dY[n_img*H*W, Cout]^T im2col(x[n_img, H, W, Cin]); layout [Cout][kh][kw][Cin];
+ * slabs: maed_bwd_wgrad_slab_floats(Cout, KH*KW*Cin, n_img*H*W) floats */
+int maed_bwd_wgrad_conv(const void* dY, long long dy_plane, const void* X, long long x_plane, int n_img, int H, int W, int Cin,
+                        int Cout, int KH, int KW, int pad, float scale, int accumulate, float* slabs, float* D, int ldd, void* stream);
 int maed_bwd_split_transposed(const float* w, int N, int K, void* out_hi, long long plane, void* stream);
 /* nn.BatchNorm2d in train() mode over x [M, C] (rows = N*H*W): batch statistics (mean / rstd out; running buffers updated with
  * `momentum` and the unbiased variance when given), y = relu?(xhat * gamma + beta (+ residual planes)) -> planes; when dy is

@@ -113,6 +113,7 @@ SIGNATURES = {
     "maed_bwd_wgrad_slab_floats": (_Z, [_I, _I, _I]),
     "maed_bwd_wgrad_splitk": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _F, _I, _P, _P, _I, _P]),
     "maed_bwd_wgrad_rows": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _I, _P]),
+    "maed_bwd_wgrad_conv": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _I, _P]),
     "maed_bwd_split_transposed": (_I, [_P, _I, _I, _P, _L, _P]),
     "maed_bwd_prep_conv_weight_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "maed_bwd_dropout": (_I, [_P, _L, _F, _U, _P, _P, _P]),

@@ -108,6 +108,12 @@ int ktd_anc_wgrad(const float* g_total, const float* pose6d, int R, float scale,
 int adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2, double eps,
               double weight_decay, int step, float grad_scale, cudaStream_t st);
 
+// weight gradient of a stride-1 k x k conv without an im2col matrix (implicit operand: 5-D TMA boxes of the NHWC planes shifted by
+// the tap): D[Cout, k*k*Cin] (+)= scale * dY^T im2col(x); dY [n_img*H*W, Cout], x [n_img, H, W, Cin]; Cin, Cout multiples of 64
+int gemm_wgrad_conv(const __half* dY, long long dy_plane, const __half* X, long long x_plane, int n_img, int H, int W, int Cin,
+                    int Cout, int KH, int KW, int pad, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd,
+                    cudaStream_t st);
+
 // ---- attention backward (attention_bwd.cu); qkv planes as in the forward, d_out fp32 [BT*ntok, H*64],
 // d_qkv fp32 [BT*ntok, 3*H*64]; `accumulate` adds to d_qkv instead of overwriting it
 int attn_spatial_bwd(const __half* qkv_hi, long long qkv_plane, const float* d_out, int BT, int ntok, int heads, float scale,

@@ -323,6 +323,11 @@ int maed_bwd_wgrad_rows(const void* dY, long long dy_plane, int ld_dy, const voi
   return gemm_wgrad_rows((const __half*)dY, dy_plane, ld_dy, (const __half*)X, x_plane, ld_x, No_x, Mo, No, R, nsplit, scale,
                          accumulate, slabs, D, ldd, (cudaStream_t)stream);
 }
+int maed_bwd_wgrad_conv(const void* dY, long long dy_plane, const void* X, long long x_plane, int n_img, int H, int W, int Cin,
+                        int Cout, int KH, int KW, int pad, float scale, int accumulate, float* slabs, float* D, int ldd, void* stream) {
+  return gemm_wgrad_conv((const __half*)dY, dy_plane, (const __half*)X, x_plane, n_img, H, W, Cin, Cout, KH, KW, pad, 3, scale,
+                         accumulate, slabs, D, ldd, (cudaStream_t)stream);
+}
 int maed_bwd_split_transposed(const float* w, int N, int K, void* out_hi, long long plane, void* stream) {
   return split_f32_transposed(w, N, K, (__half*)out_hi, plane, (cudaStream_t)stream);
 }

@@ -26,7 +26,9 @@ namespace {
 
 struct SplitKParams {
   int M, N;                    // output rows / cols (Mo, No)
-  int num_k_blocks;            // ceil(R / 64)
+  int num_k_blocks;            // ceil(R / 64); conv mode: n_img * patches
+  // conv mode (implicit im2col): a K block = one tile_h x tile_w (= 64 pixel) patch of one image
+  int conv, patches, tiles_w, tile_h, tile_w, Cin, KW, pad;
   int kb_per_slice, slices;
   int nsplit, stages;
   int m_tiles, n_tiles;
@@ -87,7 +89,22 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* sB = sA + nplanes * kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], nplanes * (kABytes + kBBytes));
           for (int pl = 0; pl < nplanes; ++pl) {
-            if (MN) {       // [64-wide MN block][64 rows of r][128 B]: 8 KB per block, the layout umma_desc_mn_sw128 describes
+            if (MN && p.conv) {
+              // implicit im2col: dY patch {64 channels, tile_w, tile_h} and, per 64-column block of the [kh][kw][Cin] weight
+              // row, the SAME patch of x shifted by the tap (TMA zero-fills the padding and ragged patch borders)
+              const int img = kb / p.patches, rem = kb % p.patches;
+              const int h0 = (rem / p.tiles_w) * p.tile_h, w0 = (rem % p.tiles_w) * p.tile_w;
+#pragma unroll
+              for (int mb = 0; mb < kBM / 64; ++mb)
+                tma_load_5d(sA + pl * kABytes + mb * 8192, &tmA, &full_bar[stage], m_tile * kBM + mb * 64, w0, h0, img, pl);
+#pragma unroll
+              for (int nb = 0; nb < BLOCK_N / 64; ++nb) {
+                const int col = n_tile * BLOCK_N + nb * 64;
+                const int tap = col / p.Cin, cin0 = col % p.Cin;
+                tma_load_5d(sB + pl * kBBytes + nb * 8192, &tmB, &full_bar[stage], cin0, w0 + tap % p.KW - p.pad,
+                            h0 + tap / p.KW - p.pad, img, pl);
+              }
+            } else if (MN) {       // [64-wide MN block][64 rows of r][128 B]: 8 KB per block, the layout umma_desc_mn_sw128 describes
 #pragma unroll
               for (int mb = 0; mb < kBM / 64; ++mb)
                 tma_load_3d(sA + pl * kABytes + mb * 8192, &tmA, &full_bar[stage], m_tile * kBM + mb * 64, kb * kBK, pl);
@@ -197,12 +214,12 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ slabs, int slices
 }
 
 struct SliceChoice { int block_n, m_tiles, n_tiles, nkb, kb_per, slices; };
-SliceChoice choose_slices(int Mo, int No, int R) {
+SliceChoice choose_slices(int Mo, int No, int R, int nkb_override = 0) {
   SliceChoice c;
   c.block_n = (No % 256 == 0) ? 256 : (No % 128 == 0) ? 128 : 64;
   c.m_tiles = cdiv(Mo, kBM);
   c.n_tiles = cdiv(No, c.block_n);
-  c.nkb = cdiv(R, kBK);
+  c.nkb = nkb_override ? nkb_override : cdiv(R, kBK);
   const int tiles = c.m_tiles * c.n_tiles;
   int s = (2 * sm_count() + tiles - 1) / tiles;
   if (s > 64) s = 64;
@@ -229,9 +246,10 @@ int launch_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, const SplitKPa
 // shared tail of the two entry points: slicing, launch, ordered slab reduction
 template <bool MN>
 int run_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, const SliceChoice& c, int Mo, int No, int nsplit, float scale,
-               int accumulate, float* slabs, float* D, int ldd, cudaStream_t st) {
+               int accumulate, float* slabs, float* D, int ldd, cudaStream_t st, const SplitKParams* conv = nullptr) {
   const int np = nsplit == 3 ? 2 : 1;
-  SplitKParams p;
+  SplitKParams p = conv ? *conv : SplitKParams();
+  if (!conv) p.conv = 0;
   p.M = Mo; p.N = No; p.num_k_blocks = c.nkb; p.kb_per_slice = c.kb_per; p.slices = c.slices; p.nsplit = nsplit;
   p.m_tiles = c.m_tiles; p.n_tiles = c.n_tiles; p.slabs = slabs;
   const size_t stage_bytes = (size_t)np * (kBM * kBK * 2 + c.block_n * kBK * 2);
@@ -262,9 +280,8 @@ size_t splitk_slab_floats(int Mo, int No, int R) {
   const SliceChoice c = choose_slices(Mo, No, R);
   const int tiles = c.m_tiles * c.n_tiles;
   int s = (2 * sm_count() + tiles - 1) / tiles;
-  if (s > 64) s = 64;
-  if (s > c.nkb) s = c.nkb;
-  if (s < c.slices) s = c.slices;
+  if (s > 64) s = 64;                                   // (no clamp by the K-block count: the implicit-conv mode has more K
+  if (s < c.slices) s = c.slices;                       //  blocks than R / 64 when its pixel patches are ragged)
   return (size_t)s * Mo * No;
 }
 
@@ -323,6 +340,52 @@ int gemm_wgrad_rows(const __half* dY, long long dy_plane, int ld_dy, const __hal
     MAED_PROPAGATE(make_tmap_f16(&tmB, X, 3, dims, str, box));
   }
   return run_splitk<true>(tmA, tmB, c, Mo, No, nsplit, scale, accumulate, slabs, D, ldd, st);
+}
+
+// 64-pixel patch (tile_h x tile_w) covering an H x W map with the fewest patches
+static void wgrad_patch_shape(int H, int W, int* th, int* tw) {
+  int best = 1 << 30;
+  *th = 8; *tw = 8;
+  for (int h = 1; h <= 64; h *= 2) {
+    const int w = 64 / h;
+    const int n = cdiv(H, h) * cdiv(W, w);
+    if (n < best) { best = n; *th = h; *tw = w; }
+  }
+}
+int wgrad_conv_k_blocks(int n_img, int H, int W) {
+  int th, tw;
+  wgrad_patch_shape(H, W, &th, &tw);
+  return n_img * cdiv(H, th) * cdiv(W, tw);
+}
+
+// Weight gradient of a stride-1 k x k convolution without an im2col matrix: D[Cout, k*k*Cin] (+)= scale * sum over the output
+// pixels of dY[pixel, Cout]^T x[pixel shifted by the tap, Cin].  dY [n_img*H*W, Cout] and x NHWC [n_img, H, W, Cin] are fp16
+// hi/lo planes; Cin and Cout multiples of 64; `pad` = zero padding at the top / left.
+int gemm_wgrad_conv(const __half* dY, long long dy_plane, const __half* X, long long x_plane, int n_img, int H, int W, int Cin,
+                    int Cout, int KH, int KW, int pad, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd,
+                    cudaStream_t st) {
+  MAED_CHECK_ARG(dY && X && slabs && D, "gemm_wgrad_conv: null argument");
+  MAED_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && KH >= 1 && KW >= 1 && n_img >= 1, "gemm_wgrad_conv: bad shape Cin=%d Cout=%d",
+                 Cin, Cout);
+  MAED_CHECK_ARG(nsplit == 3, "gemm_wgrad_conv: split precision only");
+  const int No = KH * KW * Cin;
+  MAED_CHECK_ARG(ldd >= No, "gemm_wgrad_conv: ldd=%d < %d", ldd, No);
+  SplitKParams cp;
+  cp.conv = 1; cp.Cin = Cin; cp.KW = KW; cp.pad = pad;
+  wgrad_patch_shape(H, W, &cp.tile_h, &cp.tile_w);
+  cp.tiles_w = cdiv(W, cp.tile_w);
+  cp.patches = cdiv(H, cp.tile_h) * cp.tiles_w;
+  const SliceChoice c = choose_slices(Cout, No, 0, n_img * cp.patches);
+  CUtensorMap tmA, tmB;
+  auto tmap5 = [&](CUtensorMap* tm, const __half* base, long long plane, int Cc) -> int {
+    const uint64_t dims[5] = {(uint64_t)Cc, (uint64_t)W, (uint64_t)H, (uint64_t)n_img, 2};
+    const uint64_t str[4] = {(uint64_t)Cc * 2, (uint64_t)W * Cc * 2, (uint64_t)H * W * Cc * 2, (uint64_t)plane * 2};
+    const uint32_t box[5] = {64, (uint32_t)cp.tile_w, (uint32_t)cp.tile_h, 1, 1};
+    return make_tmap_f16(tm, base, 5, dims, str, box);
+  };
+  MAED_PROPAGATE(tmap5(&tmA, dY, dy_plane, Cout));
+  MAED_PROPAGATE(tmap5(&tmB, X, x_plane, Cin));
+  return run_splitk<true>(tmA, tmB, c, Cout, No, nsplit, scale, accumulate, slabs, D, ldd, st, &cp);
 }
 
 }  // namespace maed

@@ -740,6 +740,11 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
     xm = w.col; xm_plane = w.col_plane;
   } else if (L.k == 1 && L.stride == 1) {
     xm = w.out[L.in_layer]; xm_plane = w.out_plane[L.in_layer];
+  } else if (L.stride == 1 && L.Cin % 64 == 0 && L.Cout % 64 == 0) {
+    // stride-1 k x k: no im2col matrix, the split-K kernel reads the tap-shifted patches of x itself
+    xm = nullptr; xm_plane = 0;
+    MAED_PROPAGATE(gemm_wgrad_conv(w.pl_a, w.pl_a_plane, w.out[L.in_layer], w.out_plane[L.in_layer], BT, L.Hin, L.Hin, L.Cin, L.Cout,
+                                   L.k, L.k, pad, 3, 1.0f, 0, w.slabs, w.wg, kc_pad, c.st));
   } else {
     MAED_PROPAGATE(im2col_nhwc(w.out[L.in_layer], w.out_plane[L.in_layer], BT, L.Hin, L.Hin, L.Cin, L.k, L.k, L.stride, pad, pad,
                                L.Hout, L.Hout, w.col, w.col_plane, c.st));
@@ -747,8 +752,9 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
   }
   // dconv [Mo, Cout] and the activation matrix [Mo, kc] feed the tensor cores as MN-major operands (no transposed copies);
   // columns kc..kc_pad of dW_hat come out as zeros
-  MAED_PROPAGATE(gemm_wgrad_rows(w.pl_a, w.pl_a_plane, L.Cout, xm, xm_plane, kc, kc, L.Cout, kc_pad, (int)Mo, 3, 1.0f, 0,
-                                 w.slabs, w.wg, kc_pad, c.st));
+  if (xm)
+    MAED_PROPAGATE(gemm_wgrad_rows(w.pl_a, w.pl_a_plane, L.Cout, xm, xm_plane, kc, kc, L.Cout, kc_pad, (int)Mo, 3, 1.0f, 0,
+                                   w.slabs, w.wg, kc_pad, c.st));
   if (c.net.bn)                                            // plain conv: only the [Cout][kh][kw][Cin] -> OIHW permute
     MAED_PROPAGATE(wgrad_permute(w.wg, kc_pad, L.Cout, L.Cin, L.k, L.k, c.inv_ls, c.G(L.w_idx), c.st));
   else

@@ -460,6 +460,24 @@ int attn_temporal_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half
 }
 
 int gemm_wgrad_rows(const __half* dY, long long dy_plane, int ld_dy, const __half* X, long long x_plane, int ld_x, int No_x,
+                    int Mo, int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, cudaStream_t);
+// contract: explicit im2col (the real CUDA-core kernel) followed by the row-major weight gradient
+int gemm_wgrad_conv(const __half* dY, long long dy_plane, const __half* X, long long x_plane, int n_img, int H, int W, int Cin,
+                    int Cout, int KH, int KW, int pad, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd,
+                    cudaStream_t st) {
+  MAED_CHECK_ARG(dY && X && slabs && D, "gemm_wgrad_conv: null argument");
+  MAED_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && KH >= 1 && KW >= 1 && n_img >= 1, "gemm_wgrad_conv: bad shape Cin=%d Cout=%d",
+                 Cin, Cout);
+  MAED_CHECK_ARG(nsplit == 3, "gemm_wgrad_conv: split precision only");
+  const int No = KH * KW * Cin;
+  MAED_CHECK_ARG(ldd >= No, "gemm_wgrad_conv: ldd=%d < %d", ldd, No);
+  const long long M = (long long)n_img * H * W;
+  std::vector<__half> col((size_t)2 * M * No);
+  MAED_PROPAGATE(im2col_nhwc(X, x_plane, n_img, H, W, Cin, KH, KW, 1, pad, pad, H, W, col.data(), M * No, st));
+  return gemm_wgrad_rows(dY, dy_plane, Cout, col.data(), M * No, No, No, Cout, No, (int)M, nsplit, scale, accumulate, slabs, D, ldd, st);
+}
+
+int gemm_wgrad_rows(const __half* dY, long long dy_plane, int ld_dy, const __half* X, long long x_plane, int ld_x, int No_x,
                     int Mo, int No, int R, int nsplit, float scale, int accumulate, float* slabs, float* D, int ldd, cudaStream_t) {
   Prof prof(4);
   MAED_CHECK_ARG(dY && X && slabs && D, "gemm_wgrad_rows: null argument");

@@ -326,6 +326,30 @@ def test_wgrad_rows(L, Mo, No, No_x, R):
     assert rel_err(D, ref) < 2e-5
 
 
+@pytest.mark.parametrize("n,H,Cin,Cout,k", [(3, 56, 64, 64, 3), (2, 28, 128, 128, 3), (5, 14, 256, 256, 3), (2, 7, 512, 512, 3),
+                                            (1, 14, 64, 128, 1)])
+def test_wgrad_conv_implicit(L, n, H, Cin, Cout, k):
+    """dW of a stride-1 k x k convolution with the implicit im2col operand (tap-shifted 5-D TMA patches) against the weight
+    gradient of torch's conv2d in float64 ([Cout][kh][kw][Cin] layout, padding k // 2)."""
+    _lib, ops = L
+    if _is_emu() and n * H * H > 2000:
+        pytest.skip("larger maps: hardware only (the emulator holds a contract stub)")
+    x = _rand(n, H, H, Cin, seed=46)                                             # NHWC
+    dy = _rand(n * H * H, Cout, scale=0.1, seed=47)
+    px, py = _planes(x.reshape(-1, Cin), ops), _planes(dy, ops)
+    xd = _join(px).reshape(n, H, H, Cin).permute(0, 3, 1, 2)
+    wd = torch.zeros(Cout, Cin, k, k, dtype=torch.float64, device=DEV, requires_grad=True)
+    y = torch.nn.functional.conv2d(xd, wd, padding=k // 2)
+    y.backward(_join(py).reshape(n, H, H, Cout).permute(0, 3, 1, 2))
+    ref = 0.5 * wd.grad.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin) + 1.0
+    No = k * k * Cin
+    slabs = torch.empty(_lib.load().maed_bwd_wgrad_slab_floats(Cout, No, n * H * H), device=DEV)
+    D = torch.ones(Cout, No, device=DEV)
+    _lib.call("maed_bwd_wgrad_conv", _lib.ptr(py), C.c_longlong(py[0].numel()), _lib.ptr(px), C.c_longlong(px[0].numel()), n, H, H,
+              Cin, Cout, k, k, k // 2, C.c_float(0.5), 1, _lib.ptr(slabs), _lib.ptr(D), No, _lib.stream_ptr())
+    assert rel_err(D, ref) < 2e-5
+
+
 def test_split_transposed(L):
     _lib, _ = L
     w = _rand(2304, 768, scale=0.05, seed=36)
