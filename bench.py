@@ -244,7 +244,13 @@ def train_measure(args, dev, dist, world, rank, local, st_mode, encoder="ste", l
     cnn = encoder == "cnn"
     # 'cnn': the literal stage-1 shape (configs/config_stage1.yaml: 128 images per GPU, T = 1, torchvision ResNet-50 encoder)
     clips, Tt = (128, 1) if cnn else (CLIPS_PER_GPU, T)
-    model = MAED("cnn" if cnn else "ste", 6, 12, st_mode, DECODER, 1024)
+    if getattr(args, "clips", None):
+        clips = args.clips
+    if getattr(args, "seq_len", None):
+        Tt = args.seq_len
+    # T = 32 (BASELINE configs[4]): the reference's temp_embed has 16 rows (vision_transformer.py:364); the extension is a
+    # 32-row parameter (DESIGN.md / SURVEY.md 8d config 5)
+    model = MAED("cnn" if cnn else "ste", 6, 12, st_mode, DECODER, 1024, temp_frames=max(16, Tt))
     if cnn:
         synth.fill_module_(model, 0)              # running statistics / affine parameters of a plausible BatchNorm state
     model = model.to(dev).train()
@@ -337,18 +343,20 @@ def train_measure(args, dev, dist, world, rank, local, st_mode, encoder="ste", l
         return None
     peaks, peak_src = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-    gflop_per_clip = 8.174 * Tt if cnn else GFLOP_PER_CLIP                     # ResNet-50: 8.17 GFLOP per frame
+    gflop_per_clip = 8.174 * Tt if cnn else GFLOP_PER_CLIP * Tt / T            # ResNet-50: 8.17 GFLOP per frame
     step_tflops = 3.0 * clips * gflop_per_clip / 1000.0 / (ms_total / steps / 1000.0)
     return {
-        "metric": ("images/sec (224x224, bs=128/gpu, T=1), MAED cnn(ResNet-50)+ktd train step (fwd+bwd+Adam)" if cnn else
-                   "clips/sec (T=16, 224x224, bs=8/gpu), MAED ste-%s+ktd train step (fwd+bwd+Adam)" % st_mode),
+        "metric": ("images/sec (224x224, bs=%d/gpu, T=1), MAED cnn(ResNet-50)+ktd train step (fwd+bwd+Adam)" % clips if cnn else
+                   "clips/sec (T=%d, 224x224, bs=%d/gpu), MAED ste-%s+ktd train step (fwd+bwd+Adam)" % (Tt, clips, st_mode)),
         "mode": "train", "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 hi/lo split operands for forward, data- and weight-gradient GEMMs; fp32 reductions / Adam",
         "data": "synthetic",
         "config": {"workload": ("configs/config_stage1.yaml shape: 128 images per GPU, encoder='cnn', train step, BatchNorm on "
                                 "batch statistics (SyncBatchNorm exchange when N > 1)") if cnn else
-                               "BASELINE configs[2] (N=1) / configs[3] shape (N>1): bs=8/gpu T=16 train step (fwd+bwd+Adam), random-init",
+                               ("BASELINE configs[4] shape: bs=4/gpu T=32 train step (temp_embed extended to 32 rows), random-init"
+                                if Tt == 32 else
+                                "BASELINE configs[2] (N=1) / configs[3] shape (N>1): bs=8/gpu T=16 train step (fwd+bwd+Adam), random-init"),
                    "clips_per_gpu": clips, "seq_len": Tt, "st_mode": st_mode, "decoder": DECODER,
                    "loss": ("reference LossVideo, stage-2 weights, fused CUDA loss (keypoint terms act on the zero body model "
                             "unless SMPL assets are loaded)") if loss_kind == "fused" else
@@ -423,6 +431,8 @@ def main():
     ap.add_argument("--encoder", default="ste", choices=["ste", "cnn"],
                     help="train mode only: 'cnn' = the stage-1 shape, 128 images per GPU")
     ap.add_argument("--st-mode", default=None, help="train mode only: parallel (default) or series")
+    ap.add_argument("--clips", type=int, default=None, help="train mode only: clips (images for 'cnn') per GPU")
+    ap.add_argument("--seq-len", type=int, default=None, help="train mode only: frames per clip (32 = BASELINE configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -551,7 +561,8 @@ def main():
                      "traffic": traffic, "peak_source": peak_src + ", bf16_tflops (burst: the kernel is timed alone); "
                      "whole_step_frac_of_peak uses bf16_tflops_sustained = %.1f" % peak_tf,
                      "algorithmic_tflop_per_launch": tf_launch, "ms_per_launch": gemm_ms,
-                     "note": "algorithmic FLOPs (2MNK); the split path issues 3x that on the tensor pipe",
+                     "note": "algorithmic FLOPs (2MNK); the split-precision path issues 3x that on the tensor pipe (DESIGN.md §3)",
+                     "issued_tflops": 3.0 * achieved, "issued_frac_of_sustained_peak": 3.0 * achieved / peak_tf,
                      "whole_step_algorithmic_tflops_per_gpu": step_tflops,
                      "whole_step_frac_of_peak": step_tflops / peak_tf},
     }

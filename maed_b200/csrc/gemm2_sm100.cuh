@@ -1,5 +1,6 @@
 // CTA-pair variant of the tcgen05 GEMM of gemm_sm100.cuh (opt-in: MAED_B200_GEMM_2CTA=1; plain and implicit-conv A operands;
-// written at the end of round 1 WITHOUT GPU access — compiled and SASS-checked, not yet run).
+// parity green on a B200 in round 2: tests/test_gemm_pair.py; fc1 414 vs 396 TFLOP/s for the single-CTA kernel with the same
+// direct-store epilogue, 430 for the single-CTA kernel with the TMA-store epilogue, which therefore stayed the default).
 //
 // Why: the 128 x 256 split-precision tile of gemm_tc_kernel is shared-memory-bandwidth bound (profiles/README.md: MMA operand
 // reads 96 B/clk + TMA fills 62 B/clk against 128 B/clk; tensor pipe 65-73 %).  With tcgen05.mma.cta_group::2 two CTAs of a

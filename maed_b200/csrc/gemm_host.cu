@@ -202,7 +202,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     const uint32_t box[3] = {64, 128, 1};
     MAED_PROPAGATE(make_tmap_f16(&tmA, g.A, 3, dims, str, box));
   }
-  // opt-in CTA-pair path (MAED_B200_GEMM_2CTA=1): plain GEMMs with at least one full pair tile; not yet validated on a GPU
+  // opt-in CTA-pair path (MAED_B200_GEMM_2CTA=1): plain GEMMs with at least one full pair tile
   static const bool pair_on = getenv("MAED_B200_GEMM_2CTA") != nullptr;
   if (pair_on && p.m_tiles >= 2 && (g.N % 128) == 0 && (g.force_block_n == 0 || g.force_block_n >= 128)) {
     const int bn2 = g.force_block_n ? g.force_block_n : ((g.N % 256) == 0 ? 256 : 128);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Forward throughput of encoder='cnn' (torchvision ResNet-50 + KTD) on one B200 — the literal stage-1 shape
 (configs/config_stage1.yaml: 128 images per GPU, T = 1) and the BASELINE shape (8 clips x T = 16 = 128 frames: the same
-engine work).  Not part of the driver's bench contract (bench.py keeps the headline 'ste' metric); written without GPU access.
+engine work).  Not part of the driver's bench contract (bench.py keeps the headline 'ste' metric).
 
     python scripts/bench_cnn.py [--steps 20] [--warmup 5] [--no-cpu-baseline]
 """

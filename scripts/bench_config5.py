@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4] shape on one GPU: 4 clips x T = 32 frames, 'parallel' + KTD, forward (the long-clip stress of the
 temporal attention; the model carries a 32-row temp_embed, see DESIGN.md / SURVEY.md 8d config 5).  Not part of the driver's
-bench contract; written without GPU access.
+bench contract.
 
     python scripts/bench_config5.py [--steps 20] [--warmup 5] [--train]
 """

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel timing of the training path's kernels at the bench shapes (8 clips x T=16: 25 216 token rows, 128 frames) with
 CUDA events: algorithmic bytes / FLOPs per launch against the measured peaks (MEASURED_PEAKS.json).  For round 2: which backward
-kernels are worth optimising first.  Written without GPU access; every call goes through the C ABI like the tests do.
+kernels are worth optimising first.  Every call goes through the C ABI like the tests do.
 
     python scripts/bench_train_kernels.py [--reps 10]
 """

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, GPU call 1: run every not-yet-validated test file un-gated, one process per file, full logs kept.
 mkdir -p gpurun_out
-export MAED_B200_TRAIN_TESTS=1 MAED_B200_NO_CANARY=1
+
 nvidia-smi --query-gpu=name,memory.total --format=csv,noheader
 for f in test_bwd_ops test_geometry_tail test_loss test_smpl test_cnn test_gemm_pair test_train; do
   echo "=== $f"

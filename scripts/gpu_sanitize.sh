@@ -3,7 +3,7 @@
 # of bug the CUDA-on-CPU test build cannot see: its fibers run one at a time).  Slow (10-50x): per-kernel tests only.
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_sanitize.sh'
 mkdir -p gpurun_out
-export MAED_B200_TRAIN_TESTS=1 MAED_B200_NO_CANARY=1
+
 SEL="layernorm or groupnorm or batchnorm or maxpool or colsum or transpose or gelu or dropout or ktd or blend or wstd or adam or dilate or scatter"
 for tool in memcheck racecheck; do
   echo "=== compute-sanitizer --tool $tool (backward kernels)"

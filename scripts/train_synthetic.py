@@ -11,7 +11,7 @@ model, criterion and optimiser are the drop-ins, the loop is the reference's:
 
 --ddp wraps the model in torch DistributedDataParallel exactly like reference train.py:113 (stage 1: the SyncBatchNorm exchange of
 maed_b200 replaces convert_sync_batchnorm, train.py:95); without it the flat-buffer path (FusedAdam + allreduce_gradients) is used.
-Written without GPU access (round 1); needs a B200.
+Needs a B200.
 """
 import argparse
 import os
