@@ -487,10 +487,19 @@ def main():
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
+    d2h_stream = torch.cuda.Stream(dev)
+    h_outs = [h_out, {k: torch.empty_like(v).pin_memory() for k, v in h_out.items()}]
+    done = [torch.cuda.Event() for _ in range(2)]
+    read = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_loop(steps):
+        """H2D of step i+1 (copy stream) and D2H of step i-1's five outputs (second copy stream) run under step i's compute;
+        the host waits for the results of step i-1 before it launches step i+1, and for the last step at the end — every
+        step's input copy and result read is inside the timed region."""
         with torch.cuda.stream(copy_stream):
             dx[0].copy_(hx[0], non_blocking=True)
             ready[0].record(copy_stream)
+        keep = [None, None]
         for i in range(steps):
             cur, nxt = i % 2, (i + 1) % 2
             if i + 1 < steps:
@@ -502,9 +511,16 @@ def main():
             main_stream.wait_event(ready[cur])
             o = model(dx[cur])
             consumed[cur].record(main_stream)
-            for k, h in h_out.items():
-                h.copy_(o[k], non_blocking=True)
-            main_stream.synchronize()               # the caller reads the result of every step
+            done[cur].record(main_stream)
+            keep[cur] = o                                   # the outputs stay alive until their copy has been issued and read
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done[cur])
+                for k, h in h_outs[cur].items():
+                    h.copy_(o[k], non_blocking=True)
+                read[cur].record(d2h_stream)
+            if i >= 1:
+                read[nxt].synchronize()                     # the caller reads the result of step i-1 while step i computes
+        read[(steps - 1) % 2].synchronize()
 
     e2e_loop(2)
     if dist:

@@ -49,9 +49,9 @@ def _digest(g, nsamp=8):
 @pytest.mark.parametrize("name", ["grads_vanilla_ktd", "grads_series_ktd", "grads_parallel_ktd", "grads_vanilla_iterative",
                                   "grads_temporal_ktd", "grads_coupling_ktd"])
 def test_emulated_training_matches_reference_gradients(harness, name):
-    # default suite: the stage-2 mode and the iterative decoder; vanilla / series (also covered through the product modules in
-    # tests/test_train.py) with MAED_EMU_FULL=1 — keeps the CPU suite at a few minutes
-    if name in ("grads_vanilla_ktd", "grads_series_ktd") and not os.environ.get("MAED_EMU_FULL"):
+    # default suite: the stage-2 mode and the iterative decoder; the other modes (series is covered through the product modules
+    # in tests/test_train.py; every case runs on the GPU in `-m gpu`) with MAED_EMU_FULL=1 — keeps the CPU suite at a few minutes
+    if name not in ("grads_parallel_ktd", "grads_vanilla_iterative") and not os.environ.get("MAED_EMU_FULL"):
         pytest.skip("long on the emulator: set MAED_EMU_FULL=1")
     from maed_b200.models import MAED
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
