@@ -230,7 +230,9 @@ int maed_bwd_ktd_tree(const float* d_pose6d, const float* d_shape, const float* 
 /* kind: 0 spatial (per frame; CUDA-core cross-check), 1 temporal (per token across the T frames), 2 coupling (all T * ntok tokens
  * of a clip; needs scratch of B * heads * T * ntok * 3 floats), 3 spatial on the tensor cores (tcgen05, ntok <= 208: what the train
  * step runs; scratch of B*T*ntok * heads*64 floats holds the fp16 hi/lo planes of d_out), 4 temporal on the tensor cores (same
- * kernel on TMA-gathered {64, 128/T, T} tiles, T in {4, 8, 16, 32}; scratch as for 3); scratch NULL otherwise */
+ * kernel on TMA-gathered {64, 128/T, T} tiles, T in {4, 8, 16, 32}; scratch as for 3), 5 / 6 = 3 / 4 the way the train step runs
+ * them: the forward kernel leaves its row log-sum-exp, D = rowsum(dO o O) is precomputed, and the backward needs one element-wise
+ * pass per score tile (scratch: 2 * rows*heads*64 + 2 * rows*heads floats); scratch NULL otherwise */
 int maed_bwd_attention(int kind, const void* qkv_hi, long long qkv_plane, const float* d_out, int B, int T, int ntok, int heads,
                        float scale, int accumulate, float* d_qkv, float* scratch, void* stream);
 size_t maed_bwd_wgrad_slab_floats(int Mo, int No, int R);

@@ -48,6 +48,7 @@ struct SpatialParams {
   long long out_plane;
   int ldo;                                // heads * 64
   int f32_tma;                            // fp32 output leaves by TMA store (out_f32 only, no planes requested)
+  float* lse;                             // optional [BT*ntok, heads]: log2-domain log-sum-exp of every query row (training tape)
   int direct_store;                       // debug knob (MAED_B200_ATTN_DIRECT=1): per-thread global stores instead of TMA
   long long* dbg;                         // optional clock64 timeline of CTA 0 ([item][32] slots), MAED_B200_ATTN_DBG=1
 };
@@ -327,6 +328,8 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         SM_STAMP(3);
         named_bar_sync(pair_bar, 64);
         const float inv = 1.0f / (sum + x_peer[1]);
+        if (p.lse != nullptr && half == 0 && qrow < p.ntok)      // the backward recomputes P = exp2(s c - lse) in one pass
+          p.lse[((long long)bt * p.ntok + qrow) * p.heads + h] = mb + log2f(sum + x_peer[1]);
         // epilogue: O / sum.  O is pulled into registers and released at once (the other tile's P V may start);
         // the fp16 hi/lo planes go through a swizzled staging tile and leave by TMA store, so the softmax warps
         // never wait on global-memory back-pressure.
@@ -427,7 +430,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 }
 
 int attn_spatial(const __half* qkv_hi, long long qkv_plane, int BT, int ntok, int heads, float scale, int nsplit,
-                 float* out_f32, __half* out_hi, long long out_plane, cudaStream_t st) {
+                 float* out_f32, __half* out_hi, long long out_plane, cudaStream_t st, float* lse) {
   MAED_CHECK_ARG(ntok >= 1 && ntok <= kKvRows, "attn_spatial: ntok=%d unsupported (1..%d)", ntok, kKvRows);
   MAED_CHECK_ARG(nsplit == 1 || nsplit == 3, "attn_spatial: nsplit must be 1 or 3");
   const int np = nsplit == 3 ? 2 : 1;
@@ -469,6 +472,7 @@ int attn_spatial(const __half* qkv_hi, long long qkv_plane, int BT, int ntok, in
   }
   SpatialParams p;
   p.f32_tma = f32_tma ? 1 : 0;
+  p.lse = lse;
   p.BT = BT; p.ntok = ntok; p.heads = heads; p.nplanes = np;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out_f32 = out_f32; p.out_hi = out_hi; p.out_plane = out_plane; p.ldo = heads * kHeadDim;
@@ -654,13 +658,14 @@ __global__ void attn_temporal_kernel(const __half* __restrict__ qkv, long long p
 }
 
 int attn_temporal(const __half* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads, float scale, float* out_f32,
-                  __half* out_hi, long long out_plane, cudaStream_t st) {
+                  __half* out_hi, long long out_plane, cudaStream_t st, float* lse) {
   MAED_CHECK_ARG(T >= 1 && T <= 32, "attn_temporal: T=%d unsupported (1..32)", T);
   MAED_CHECK_ARG(qkv_plane % 8 == 0 && out_plane % 4 == 0, "attn_temporal: plane strides must be 16-byte aligned");
   // tensor-core version (TMA-gathered 128-row tiles); MAED_B200_TEMPORAL_TC=0 selects the CUDA-core kernel below
   static const bool tc_on = [] { const char* v = getenv("MAED_B200_TEMPORAL_TC"); return !(v && v[0] == '0'); }();
   if (tc_on && attn_temporal_tc_supported(T, qkv_plane) && (!out_hi || out_plane % 8 == 0))
-    return attn_temporal_tc(qkv_hi, qkv_plane, B, T, ntok, heads, scale, out_f32, out_hi, out_plane, st);
+    return attn_temporal_tc(qkv_hi, qkv_plane, B, T, ntok, heads, scale, out_f32, out_hi, out_plane, st, lse);
+  MAED_CHECK_ARG(lse == nullptr, "attn_temporal: the row statistics are only produced by the tensor-core kernel (T=%d)", T);
   const long long total = (long long)B * heads * ntok;
   const long long cap = (long long)sm_count() * 32;
 #define TEMPORAL_LAUNCH(SEGS, TMAX, WARPS)                                                                          \

@@ -49,6 +49,9 @@ struct BwdParams {
   float scale, scale_log2e;
   float* d_qkv;                        // fp32 [BT*ntok, 3*heads*64]
   int accumulate;
+  // optional, both [rows, heads]: the forward's log2-domain row log-sum-exp and D = rowsum(dO o O).  When given, orientation A is
+  // ONE element-wise pass (dS = exp2(S c - lse) (dP - D) scale) instead of three (row max, row sum + D, dS) with two exchanges
+  const float* lse_in; const float* d_in;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -262,6 +265,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         mbar_wait(mma_done, ph_mma); ph_mma ^= 1;
         tc_fence_after();
         uint32_t r[32], q[32];
+        float mb, Di, ps;
+        if (p.lse_in != nullptr) {
+          // statistics saved by the forward kernel (lse) and precomputed from dO and O (D): no reduction passes, no exchange
+          const long long qrow_s = grow(g * 128 + trow);
+          mb = qrow_s >= 0 ? p.lse_in[qrow_s * p.heads + h] : INFINITY;       // rows outside the item: exp2(-inf) = 0
+          Di = qrow_s >= 0 ? p.d_in[qrow_s * p.heads + h] : 0.f;
+          ps = p.scale;
+          if (half == 0) {
+            lse[g * 128 + trow] = mb;
+            Dr[g * 128 + trow] = Di;
+          }
+        } else {
         // pass 1: row max of the raw scores over the valid keys of this half
         float mx = -INFINITY;
 #pragma unroll 1
@@ -277,7 +292,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         x_mine[0] = mx;
         bar_sync(pair_bar, 64);
         mx = fmaxf(mx, x_peer[0]);
-        const float mb = mx * c2;
+        mb = mx * c2;
         // pass 2: row sum of e = exp2(s c - max c) and sum of e * dP
         float sum = 0.f, dot = 0.f;
 #pragma unroll 1
@@ -303,13 +318,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         sum += x_peer[1];
         dot += x_peer[2];
         const float inv = 1.0f / sum;
-        const float Di = dot * inv;
+        Di = dot * inv;
         if (half == 0) {
           lse[g * 128 + trow] = mb + log2f(sum);
           Dr[g * 128 + trow] = Di;
         }
+        ps = inv * p.scale;
+        }
         // pass 3: dS = (e / sum) (dP - D_i) scale, written over dP as fp16 hi/lo pairs (zero for padded keys); 16 columns a time
-        const float ps = inv * p.scale;
 #pragma unroll 1
         for (int col0 = cbeg; col0 < cend; col0 += 16) {
           uint32_t r16[16], q16[16], pk[16];
@@ -403,7 +419,8 @@ constexpr size_t kBwdSmem = 1024 + 8 * (size_t)kBufBytes + 6144 + (256 + 256 + 2
 }  // namespace
 
 int attn_spatial_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int BT, int ntok,
-                        int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st) {
+                        int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st, const float* lse, const float* Dv) {
+  MAED_CHECK_ARG((lse == nullptr) == (Dv == nullptr), "attn_spatial_bwd_tc: lse and D come together");
   MAED_CHECK_ARG(qkv_hi && dout_hi && d_qkv, "attn_spatial_bwd_tc: null argument");
   MAED_CHECK_ARG(ntok >= 1 && ntok <= kRows, "attn_spatial_bwd_tc: ntok=%d unsupported (1..%d)", ntok, kRows);
   MAED_CHECK_ARG(BT >= 1 && heads >= 1, "attn_spatial_bwd_tc: bad batch");
@@ -426,7 +443,7 @@ int attn_spatial_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half*
   }
   BwdParams p;
   p.BT = BT; p.ntok = ntok; p.heads = heads; p.T = 1; p.groups = 1; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
-  p.d_qkv = d_qkv; p.accumulate = accumulate;
+  p.d_qkv = d_qkv; p.accumulate = accumulate; p.lse_in = lse; p.d_in = Dv;
   static bool attr_set = false;
   if (!attr_set) {
     MAED_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
@@ -455,7 +472,9 @@ static int launch_temporal_bwd(const CUtensorMap& tmQKV, const CUtensorMap& tmDO
 
 // temporal attention backward on the same kernel: B clips, T frames (4, 8, 16, 32), d_out as fp16 hi/lo planes [B*T*ntok, heads*64]
 int attn_temporal_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int B, int T,
-                         int ntok, int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st) {
+                         int ntok, int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st, const float* lse,
+                         const float* Dv) {
+  MAED_CHECK_ARG((lse == nullptr) == (Dv == nullptr), "attn_temporal_bwd_tc: lse and D come together");
   MAED_CHECK_ARG(qkv_hi && dout_hi && d_qkv, "attn_temporal_bwd_tc: null argument");
   MAED_CHECK_ARG(T == 4 || T == 8 || T == 16 || T == 32, "attn_temporal_bwd_tc: T=%d unsupported (4, 8, 16, 32)", T);
   const long long rows = (long long)B * T * ntok;
@@ -474,7 +493,7 @@ int attn_temporal_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half
   BwdParams p;
   p.BT = B; p.ntok = ntok; p.heads = heads; p.T = T; p.groups = (ntok + npt - 1) / npt; p.scale = scale;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.d_qkv = d_qkv; p.accumulate = accumulate;
+  p.d_qkv = d_qkv; p.accumulate = accumulate; p.lse_in = lse; p.d_in = Dv;
   switch (npt) {
     case 32: return launch_temporal_bwd<32>(tmQKV, tmDO, p, st);
     case 16: return launch_temporal_bwd<16>(tmQKV, tmDO, p, st);

@@ -29,6 +29,7 @@ struct TemporalParams {
   int B, T, ntok, heads, groups;               // groups = ceil(ntok / NPT) token groups per (clip, head)
   float scale_log2e;
   float* out_f32; __half* out_hi; long long out_plane;
+  float* lse;                                  // optional [B*T*ntok, heads]: log2-domain log-sum-exp of every row (training tape)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -164,6 +165,8 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Tempora
       __syncwarp();
       if (lane == 0) mbar_arrive(ew_done);
       const float inv = 1.0f / sum;
+      if (p.lse != nullptr && g * NPT + nl < p.ntok)
+        p.lse[(((long long)b * p.T + t) * p.ntok + g * NPT + nl) * p.heads + h] = mb + log2f(sum);
       mbar_wait(mma_done, ph); ph ^= 1;
       tc_fence_after();
       uint32_t o0[32], o1[32];
@@ -246,7 +249,7 @@ int launch_temporal_fwd(const CUtensorMap& tm, const TemporalParams& p, cudaStre
 bool attn_temporal_tc_supported(int T, long long qkv_plane) { return (T == 4 || T == 8 || T == 16 || T == 32) && qkv_plane != 0; }
 
 int attn_temporal_tc(const __half* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads, float scale, float* out_f32,
-                     __half* out_hi, long long out_plane, cudaStream_t st) {
+                     __half* out_hi, long long out_plane, cudaStream_t st, float* lse) {
   MAED_CHECK_ARG(attn_temporal_tc_supported(T, qkv_plane), "attn_temporal_tc: T=%d unsupported (4, 8, 16, 32; split precision)", T);
   MAED_CHECK_ARG(qkv_hi && (out_f32 || out_hi), "attn_temporal_tc: null argument");
   const int npt = 128 / T, ld = 3 * heads * 64;
@@ -256,7 +259,7 @@ int attn_temporal_tc(const __half* qkv_hi, long long qkv_plane, int B, int T, in
   TemporalParams p;
   p.B = B; p.T = T; p.ntok = ntok; p.heads = heads; p.groups = (ntok + npt - 1) / npt;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.out_f32 = out_f32; p.out_hi = out_hi; p.out_plane = out_plane;
+  p.out_f32 = out_f32; p.out_hi = out_hi; p.out_plane = out_plane; p.lse = lse;
   switch (npt) {
     case 32: return launch_temporal_fwd<32>(tm, p, st);
     case 16: return launch_temporal_fwd<16>(tm, p, st);

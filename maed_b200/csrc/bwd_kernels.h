@@ -119,11 +119,18 @@ int gemm_wgrad_conv(const __half* dY, long long dy_plane, const __half* X, long 
 int attn_spatial_bwd(const __half* qkv_hi, long long qkv_plane, const float* d_out, int BT, int ntok, int heads, float scale,
                      int accumulate, float* d_qkv, cudaStream_t st);
 // tcgen05 version (attention_bwd_sm100.cu): d_out given as fp16 hi/lo planes [BT*ntok, heads*64]; ntok <= 208
+// lse / Dv (optional, together, both [rows, heads]): the forward's log2-domain row log-sum-exp (attn_spatial / attn_temporal `lse`
+// output) and D = rowsum(dO o O) (attn_rowdot) — with them the score-orientation pass needs no reductions
 int attn_spatial_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int BT, int ntok,
-                        int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st);
+                        int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st, const float* lse = nullptr,
+                        const float* Dv = nullptr);
+// D[row, h] = sum_d dO[row, h*64 + d] * O[row, h*64 + d]; O as fp32 [rows, heads*64] or as fp16 hi/lo planes (exactly one non-null)
+int attn_rowdot(const float* d_out, const float* o_f32, const __half* o_hi, long long o_plane, long long rows, int heads, float* D,
+                cudaStream_t st);
 // temporal attention backward on the same tcgen05 kernel (TMA-gathered {64, 128/T, T} tiles); T in {4, 8, 16, 32}
 int attn_temporal_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int B, int T,
-                         int ntok, int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st);
+                         int ntok, int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st, const float* lse = nullptr,
+                         const float* Dv = nullptr);
 int attn_temporal_bwd(const __half* qkv_hi, long long qkv_plane, const float* d_out, int B, int T, int ntok, int heads,
                       float scale, int accumulate, float* d_qkv, cudaStream_t st);
 

@@ -253,4 +253,40 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, double 
   return MAED_OK;
 }
 
+// ----------------------------------------------------------------- D = rowsum(dO o O) per (row, head) for the attention backward
+// One warp per row; a lane owns every 32nd float4 of the row, 16 lanes share a head (64 columns = 16 float4): heads 2k and 2k + 1
+// are reduced in the two half-warps.
+__global__ void __launch_bounds__(256)
+attn_rowdot_kernel(const float* __restrict__ d_out, const float* __restrict__ o_f32, const __half* __restrict__ o_hi, long long o_plane,
+                   long long rows, int heads, float* __restrict__ D) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int C = heads * 64;
+  const float* dr = d_out + row * C;
+  for (int k = 0; 2 * k < heads; ++k) {
+    const int col = (k * 32 + lane) * 4;                   // head = 2k + lane / 16
+    float s = 0.f;
+    if (col < C) {
+      const float4 d = *reinterpret_cast<const float4*>(dr + col);
+      float4 o;
+      if (o_f32) o = *reinterpret_cast<const float4*>(o_f32 + row * C + col);
+      else o = load_planes4(o_hi + row * C + col, o_plane);
+      s = d.x * o.x + d.y * o.y + d.z * o.z + d.w * o.w;
+    }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const int h = 2 * k + (lane >> 4);
+    if ((lane & 15) == 0 && h < heads) D[row * heads + h] = s;
+  }
+}
+int attn_rowdot(const float* d_out, const float* o_f32, const __half* o_hi, long long o_plane, long long rows, int heads, float* D,
+                cudaStream_t st) {
+  MAED_CHECK_ARG(d_out && D && ((o_f32 != nullptr) != (o_hi != nullptr)), "attn_rowdot: d_out, D and exactly one form of O required");
+  MAED_CHECK_ARG(rows >= 1 && heads >= 1, "attn_rowdot: bad shape");
+  attn_rowdot_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(d_out, o_f32, o_hi, o_plane, rows, heads, D);
+  MAED_BW_LAUNCH_CHECK();
+  return MAED_OK;
+}
+
 }  // namespace maed

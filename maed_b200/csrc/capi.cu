@@ -309,6 +309,24 @@ int maed_bwd_attention(int kind, const void* qkv_hi, long long qkv_plane, const 
     return attn_temporal_bwd_tc((const __half*)qkv_hi, qkv_plane, (const __half*)scratch, n, B, T, ntok, heads, scale, accumulate,
                                 d_qkv, st);
   }
+  if (kind == 5 || kind == 6) {
+    // the train step's arrangement: forward kernel with row statistics, D = rowsum(dO o O), then the one-pass backward.
+    // scratch (floats): [n] planes of d_out | [n] forward output | [rows*heads] lse | [rows*heads] D,  n = rows * heads * 64
+    MAED_CHECK_ARG(scratch, "maed_bwd_attention(kind 5/6): scratch of 2 * rows*heads*64 + 2 * rows*heads floats required");
+    const long long rows = (long long)B * T * ntok, n = rows * heads * 64;
+    float* o = scratch + n;
+    float* lse = o + n;
+    float* Dv = lse + rows * heads;
+    if (kind == 5) MAED_PROPAGATE(attn_spatial((const __half*)qkv_hi, qkv_plane, B * T, ntok, heads, scale, 3, o, nullptr, 0, st, lse));
+    else MAED_PROPAGATE(attn_temporal_tc((const __half*)qkv_hi, qkv_plane, B, T, ntok, heads, scale, o, nullptr, 0, st, lse));
+    MAED_PROPAGATE(attn_rowdot(d_out, o, nullptr, 0, rows, heads, Dv, st));
+    MAED_PROPAGATE(split_f32(d_out, (__half*)scratch, n, n, st));
+    if (kind == 5)
+      return attn_spatial_bwd_tc((const __half*)qkv_hi, qkv_plane, (const __half*)scratch, n, B * T, ntok, heads, scale, accumulate,
+                                 d_qkv, st, lse, Dv);
+    return attn_temporal_bwd_tc((const __half*)qkv_hi, qkv_plane, (const __half*)scratch, n, B, T, ntok, heads, scale, accumulate,
+                                d_qkv, st, lse, Dv);
+  }
   set_error("maed_bwd_attention: unknown kind %d", kind);
   return MAED_ERR_ARG;
 }

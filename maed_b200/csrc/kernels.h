@@ -81,13 +81,13 @@ int broadcast_add(float* x, const float* v, int BT, int ntok, int C, cudaStream_
 // ---- attention (attention.cu)
 // qkv planes: [BT*ntok, 3*H*64] (q | k | v, head-major inside each).  Outputs fp32 or planes [BT*ntok, H*64].
 int attn_spatial(const __half* qkv_hi, long long qkv_plane, int BT, int ntok, int heads, float scale, int nsplit,
-                 float* out_f32, __half* out_hi, long long out_plane, cudaStream_t st);
+                 float* out_f32, __half* out_hi, long long out_plane, cudaStream_t st, float* lse = nullptr);   // lse: optional [BT*ntok, heads] log2-domain row statistics
 // tcgen05 version (attention_temporal_sm100.cu): T in {4, 8, 16, 32}, split precision; attn_temporal dispatches to it
 bool attn_temporal_tc_supported(int T, long long qkv_plane);
 int attn_temporal_tc(const __half* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads, float scale, float* out_f32,
-                     __half* out_hi, long long out_plane, cudaStream_t st);
+                     __half* out_hi, long long out_plane, cudaStream_t st, float* lse = nullptr);
 int attn_temporal(const __half* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads, float scale,
-                  float* out_f32, __half* out_hi, long long out_plane, cudaStream_t st);
+                  float* out_f32, __half* out_hi, long long out_plane, cudaStream_t st, float* lse = nullptr);
 // generic CUDA-core fp32 attention over `seq` tokens addressed as row = base(b) + i*row_step (coupling mode,
 // and the cross-check of the tcgen05 kernel in tests)
 int attn_generic(const __half* qkv_hi, long long qkv_plane, int batch, int seq, int heads, float scale,

@@ -32,6 +32,12 @@ namespace {
 
 size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
 
+// the tcgen05 temporal kernels (forward with row statistics, backward) apply when T is 4 / 8 / 16 / 32 and a token group is full
+bool temporal_tc(int T, int ntok) {
+  static const bool tc_on = [] { const char* v = getenv("MAED_B200_TEMPORAL_TC"); return !(v && v[0] == '0'); }();
+  return tc_on && (T == 4 || T == 8 || T == 16 || T == 32) && ntok >= 128 / T;
+}
+
 // ------------------------------------------------------------------------------------ backbone layer table
 struct ConvL {
   int Hin, Cin, Cout, k, stride, Hout, relu;
@@ -113,6 +119,7 @@ Net build_net(const Engine& e) {
 struct SteTape {
   float* x_in; __half* ln1; __half* qkv; float* xs; float* xt; __half* ao_s; __half* qkv2; float* pooled; float* logits;
   __half* ao; float* x_mid; __half* ln2; float* h_pre; __half* hid;
+  float* lse_s; float* lse_t;          // [rows, heads] log2-domain row log-sum-exp of the spatial / temporal attention (tcgen05 kernels)
 };
 struct TrainWs {
   // ---- tape
@@ -135,6 +142,7 @@ struct TrainWs {
   float* fa; float* fb; float* fc; float* fd;    // fp32 activation-gradient buffers (backbone size)
   float* big;                                    // fp32 [rows, 3072]
   float* dxs; float* dxt;
+  float* attn_D;                                 // [rows, heads] D = rowsum(dO o O) of the attention backward
   float* wg;                                     // fp32 dW_hat temp
   float* slabs;
   float* red; float* dgb; float* colsum_scratch; float* ln_partial;
@@ -190,6 +198,8 @@ void carve(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& w) {
     t.ln2 = (__half*)take((size_t)w.ln_plane * 4);
     t.h_pre = (float*)take((size_t)rows * 4 * C * 4);
     t.hid = (__half*)take((size_t)w.hid_plane * 4);
+    t.lse_s = (float*)take((size_t)rows * e.cfg.num_heads * 4);
+    t.lse_t = (float*)take((size_t)rows * e.cfg.num_heads * 4);
   }
   w.x_final = (float*)take((size_t)rows * C * 4);
   const int HD = e.cfg.hidden_dim;
@@ -225,6 +235,7 @@ void carve(const Engine& e, const Net& net, int BT, uint8_t* base, TrainWs& w) {
   w.big = (float*)take((size_t)ste_big * 4);
   w.dxs = (float*)take((size_t)rows * C * 4);
   w.dxt = (float*)take((size_t)rows * C * 4);
+  w.attn_D = (float*)take((size_t)rows * e.cfg.num_heads * 4);
   // split-K slabs / weight-gradient temp: also cover the STE and proj linears
   const int lin_shapes[6][2] = {{3 * C, C}, {C, C}, {4 * C, C}, {C, 4 * C}, {C, 1024}, {2 * C, 2 * C}};
   for (int i = 0; i < 6; ++i) {
@@ -643,9 +654,10 @@ int train_forward(const Engine* ep, const void* const* params, const void* packe
     MAED_PROPAGATE(layernorm_planes(t.x_in, C, c.P(ix.n1), c.P(ix.n1 + 1), rows, C, 1e-6f, t.ln1, w.ln_plane, st));
     MAED_PROPAGATE(gemm_plain(c, t.ln1, w.ln_plane, rows, C, c.H(of.qkv), 3 * CC, 3 * C, c.P(ix.qkv_b), ACT_NONE, nullptr,
                               OUT_F16_SPLIT, t.qkv, w.qkv_plane));
+    float* lse_t = temporal_tc(T, ntok) ? t.lse_t : nullptr;     // only the tensor-core temporal kernel produces row statistics
     if (cf.mode == MODE_PARALLEL) {
-      MAED_PROPAGATE(attn_temporal(t.qkv, w.qkv_plane, N, T, ntok, heads, scale, t.xt, nullptr, 0, st));
-      MAED_PROPAGATE(attn_spatial(t.qkv, w.qkv_plane, BT, ntok, heads, scale, 3, t.xs, nullptr, 0, st));
+      MAED_PROPAGATE(attn_temporal(t.qkv, w.qkv_plane, N, T, ntok, heads, scale, t.xt, nullptr, 0, st, lse_t));
+      MAED_PROPAGATE(attn_spatial(t.qkv, w.qkv_plane, BT, ntok, heads, scale, 3, t.xs, nullptr, 0, st, t.lse_s));
       MAED_PROPAGATE(token_mean(t.xs, BT, ntok, C, t.pooled, 2 * C, 0, st));
       MAED_PROPAGATE(token_mean(t.xt, BT, ntok, C, t.pooled, 2 * C, C, st));
       MAED_PROPAGATE(split_f32(t.pooled, w.small_p, w.small_plane, (long long)BT * 2 * C, st));
@@ -653,14 +665,14 @@ int train_forward(const Engine* ep, const void* const* params, const void* packe
                                 OUT_F32, t.logits, 0));
       MAED_PROPAGATE(ts_blend(t.xs, t.xt, t.logits, BT, ntok, C, t.ao, w.ln_plane, st));
     } else if (cf.mode == MODE_SERIES) {
-      MAED_PROPAGATE(attn_spatial(t.qkv, w.qkv_plane, BT, ntok, heads, scale, 3, nullptr, t.ao_s, w.ln_plane, st));
+      MAED_PROPAGATE(attn_spatial(t.qkv, w.qkv_plane, BT, ntok, heads, scale, 3, nullptr, t.ao_s, w.ln_plane, st, t.lse_s));
       MAED_PROPAGATE(gemm_plain(c, t.ao_s, w.ln_plane, rows, C, c.H(of.qkv), 3 * CC, 3 * C, c.P(ix.qkv_b), ACT_NONE, nullptr,
                                 OUT_F16_SPLIT, t.qkv2, w.qkv_plane));
-      MAED_PROPAGATE(attn_temporal(t.qkv2, w.qkv_plane, N, T, ntok, heads, scale, nullptr, t.ao, w.ln_plane, st));
+      MAED_PROPAGATE(attn_temporal(t.qkv2, w.qkv_plane, N, T, ntok, heads, scale, nullptr, t.ao, w.ln_plane, st, lse_t));
     } else if (cf.mode == MODE_COUPLING) {                 // joint attention over the T * 197 tokens of a clip
       MAED_PROPAGATE(attn_generic(t.qkv, w.qkv_plane, N, T * ntok, heads, scale, ntok, T, nullptr, t.ao, w.ln_plane, st));
     } else {
-      MAED_PROPAGATE(attn_spatial(t.qkv, w.qkv_plane, BT, ntok, heads, scale, 3, nullptr, t.ao, w.ln_plane, st));
+      MAED_PROPAGATE(attn_spatial(t.qkv, w.qkv_plane, BT, ntok, heads, scale, 3, nullptr, t.ao, w.ln_plane, st, t.lse_s));
     }
     MAED_PROPAGATE(gemm_plain(c, t.ao, w.ln_plane, rows, C, c.H(of.proj), CC, C, c.P(ix.proj_b), ACT_NONE, t.x_in, OUT_F32,
                               t.x_mid, 0));
@@ -682,23 +694,28 @@ int train_forward(const Engine* ep, const void* const* params, const void* packe
 // ------------------------------------------------------------------------------------------- backward
 // spatial attention backward on the tensor cores (attention_bwd_sm100.cu): d_out -> fp16 hi/lo planes in pl_a (free at every
 // call site: the planes of the previous linear's gradient have been consumed), d_qkv overwritten
-static int spatial_bwd(const Ctx& c, const __half* qkv, const float* d_out, float* dqkv) {
+// (lse: the forward's row statistics; O: the forward's output as fp32 or as planes — D = rowsum(dO o O) replaces two passes)
+static int spatial_bwd(const Ctx& c, const __half* qkv, const float* d_out, float* dqkv, const float* lse, const float* o_f32,
+                       const __half* o_hi, long long o_plane) {
   TrainWs& w = c.w;
   const int heads = c.e.cfg.num_heads;
-  const long long n = (long long)c.BT * 197 * heads * 64;
+  const long long rows = (long long)c.BT * 197, n = rows * heads * 64;
+  MAED_PROPAGATE(attn_rowdot(d_out, o_f32, o_hi, o_plane, rows, heads, w.attn_D, c.st));
   MAED_PROPAGATE(split_f32(d_out, w.pl_a, w.pl_a_plane, n, c.st));
-  return attn_spatial_bwd_tc(qkv, w.qkv_plane, w.pl_a, w.pl_a_plane, c.BT, 197, heads, 0.125f, 0, dqkv, c.st);
+  return attn_spatial_bwd_tc(qkv, w.qkv_plane, w.pl_a, w.pl_a_plane, c.BT, 197, heads, 0.125f, 0, dqkv, c.st, lse, w.attn_D);
 }
 
 // temporal attention backward: tensor-core kernel when T is 4 / 8 / 16 / 32 and a token group is full (ntok >= 128 / T)
-static int temporal_bwd(const Ctx& c, const __half* qkv, const float* d_out, int ntok, int accumulate, float* dqkv) {
+static int temporal_bwd(const Ctx& c, const __half* qkv, const float* d_out, int ntok, int accumulate, float* dqkv,
+                        const float* lse, const float* o_f32, const __half* o_hi, long long o_plane) {
   TrainWs& w = c.w;
   const int heads = c.e.cfg.num_heads, T = c.T;
-  static const bool tc_on = [] { const char* v = getenv("MAED_B200_TEMPORAL_TC"); return !(v && v[0] == '0'); }();
-  if (tc_on && (T == 4 || T == 8 || T == 16 || T == 32) && ntok >= 128 / T) {
-    const long long n = (long long)c.BT * ntok * heads * 64;
+  if (temporal_tc(T, ntok)) {
+    const long long rows = (long long)c.BT * ntok, n = rows * heads * 64;
+    MAED_PROPAGATE(attn_rowdot(d_out, o_f32, o_hi, o_plane, rows, heads, w.attn_D, c.st));
     MAED_PROPAGATE(split_f32(d_out, w.pl_a, w.pl_a_plane, n, c.st));
-    return attn_temporal_bwd_tc(qkv, w.qkv_plane, w.pl_a, w.pl_a_plane, c.N, T, ntok, heads, 0.125f, accumulate, dqkv, c.st);
+    return attn_temporal_bwd_tc(qkv, w.qkv_plane, w.pl_a, w.pl_a_plane, c.N, T, ntok, heads, 0.125f, accumulate, dqkv, c.st, lse,
+                                w.attn_D);
   }
   return attn_temporal_bwd(qkv, w.qkv_plane, d_out, c.N, T, ntok, heads, 0.125f, accumulate, dqkv, c.st);
 }
@@ -1041,21 +1058,21 @@ int train_backward(const Engine* ep, const void* const* params, const void* pack
       MAED_PROPAGATE(gemm_plain(c, w.small_p, w.small_plane, BT, 2 * C, c.TH(tt.ts), 4 * CC, 2 * C, nullptr, ACT_NONE, nullptr, OUT_F32,
                                 d_pool, 0));
       MAED_PROPAGATE(blend_bwd_pool(d_pool, BT, ntok, C, w.dxs, w.dxt, st));
-      MAED_PROPAGATE(spatial_bwd(c, t.qkv, w.dxs, dqkv));
-      MAED_PROPAGATE(temporal_bwd(c, t.qkv, w.dxt, ntok, 1, dqkv));
+      MAED_PROPAGATE(spatial_bwd(c, t.qkv, w.dxs, dqkv, t.lse_s, t.xs, nullptr, 0));
+      MAED_PROPAGATE(temporal_bwd(c, t.qkv, w.dxt, ntok, 1, dqkv, t.lse_t, t.xt, nullptr, 0));
     } else if (cf.mode == MODE_SERIES) {
       // ao = temporal(qkv2), qkv2 = qkv(ao_s), ao_s = spatial(qkv), qkv = qkv(ln1): the qkv weights are used twice
-      MAED_PROPAGATE(temporal_bwd(c, t.qkv2, d_ao, ntok, 0, dqkv));
+      MAED_PROPAGATE(temporal_bwd(c, t.qkv2, d_ao, ntok, 0, dqkv, t.lse_t, nullptr, t.ao, w.ln_plane));
       MAED_PROPAGATE(split_f32(dqkv, w.pl_a, w.pl_a_plane, (long long)rows * 3 * C, st));
       MAED_PROPAGATE(colsum_f32(dqkv, 3 * C, rows, 3 * C, c.inv_ls, 0, w.colsum_scratch, c.G(ix.qkv_b), st));
       MAED_PROPAGATE(linear_wgrad(c, w.pl_a, w.pl_a_plane, 3 * C, t.ao_s, w.ln_plane, C, rows, 0, c.G(ix.qkv_w)));
       MAED_PROPAGATE(gemm_plain(c, w.pl_a, w.pl_a_plane, rows, 3 * C, c.TH(tt.qkv), 3 * CC, C, nullptr, ACT_NONE, nullptr, OUT_F32,
                                 w.dxs, 0));                                                               // d_ao_s
-      MAED_PROPAGATE(spatial_bwd(c, t.qkv, w.dxs, dqkv));
+      MAED_PROPAGATE(spatial_bwd(c, t.qkv, w.dxs, dqkv, t.lse_s, nullptr, t.ao_s, w.ln_plane));
     } else if (cf.mode == MODE_COUPLING) {
       MAED_PROPAGATE(attn_generic_bwd(t.qkv, w.qkv_plane, d_ao, N, T * ntok, heads, scale, 0, dqkv, w.dxt, st));   // dxt: statistics
     } else {
-      MAED_PROPAGATE(spatial_bwd(c, t.qkv, d_ao, dqkv));
+      MAED_PROPAGATE(spatial_bwd(c, t.qkv, d_ao, dqkv, t.lse_s, nullptr, t.ao, w.ln_plane));
     }
     const int acc = cf.mode == MODE_SERIES ? 1 : 0;
     MAED_PROPAGATE(split_f32(dqkv, w.pl_a, w.pl_a_plane, (long long)rows * 3 * C, st));

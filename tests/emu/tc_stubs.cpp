@@ -306,7 +306,7 @@ int stem_conv(const float* x, int n_img, const __half* w_hi, long long w_plane, 
 // softmax(q k^T * scale) v over the rows  row(i) of each (group, head); rows given by a callback
 template <class RowFn>
 static void attention_ref(const __half* qkv, long long plane, long long groups, int seq, int heads, float scale, RowFn row_of,
-                          float* out_f32, __half* out_hi, long long out_plane) {
+                          float* out_f32, __half* out_hi, long long out_plane, float* lse = nullptr) {
   Prof prof(3);
   const int ldq = 3 * heads * 64, C = heads * 64;
   parallel_for(groups * heads, [&](long long gh) {
@@ -331,6 +331,7 @@ static void attention_ref(const __half* qkv, long long plane, long long groups, 
       }
       float sum = 0.f;
       for (int j = 0; j < seq; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
+      if (lse) lse[row_of(g, i) * heads + h] = (mx + logf(sum)) * 1.4426950408889634f;     // log2 domain, like the kernels
       float o[64];
       for (int d = 0; d < 64; ++d) o[d] = 0.f;
       for (int j = 0; j < seq; ++j) {
@@ -348,7 +349,7 @@ static void attention_ref(const __half* qkv, long long plane, long long groups, 
 }
 
 int attn_spatial(const __half* qkv_hi, long long qkv_plane, int BT, int ntok, int heads, float scale, int nsplit,
-                 float* out_f32, __half* out_hi, long long out_plane, cudaStream_t) {
+                 float* out_f32, __half* out_hi, long long out_plane, cudaStream_t, float* lse) {
   MAED_CHECK_ARG(ntok >= 1 && ntok <= 208, "attn_spatial: ntok=%d unsupported (1..208)", ntok);
   MAED_CHECK_ARG(nsplit == 1 || nsplit == 3, "attn_spatial: nsplit must be 1 or 3");
   const int np = nsplit == 3 ? 2 : 1;
@@ -363,18 +364,23 @@ int attn_spatial(const __half* qkv_hi, long long qkv_plane, int BT, int ntok, in
                    "attn_spatial: output planes must be 16-byte aligned and at least rows*heads*64 apart");
   MAED_CHECK_ARG(out_f32 || out_hi, "attn_spatial: no output");
   attention_ref(qkv_hi, np == 2 ? qkv_plane : 0, BT, ntok, heads, scale,
-                [=](long long g, int i) { return g * ntok + i; }, out_f32, out_hi, out_plane);
+                [=](long long g, int i) { return g * ntok + i; }, out_f32, out_hi, out_plane, lse);
   return MAED_OK;
 }
 
 int attn_temporal(const __half* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads, float scale, float* out_f32,
-                  __half* out_hi, long long out_plane, cudaStream_t) {
+                  __half* out_hi, long long out_plane, cudaStream_t, float* lse) {
   MAED_CHECK_ARG(T >= 1 && T <= 32, "attn_temporal: T=%d unsupported (1..32)", T);
   MAED_CHECK_ARG(qkv_plane % 8 == 0 && out_plane % 4 == 0, "attn_temporal: plane strides must be 16-byte aligned");
   // group = (clip b, token n); row(i) = (b*T + i)*ntok + n
   attention_ref(qkv_hi, qkv_plane, (long long)B * ntok, T, heads, scale,
-                [=](long long g, int i) { return ((g / ntok) * T + i) * ntok + (g % ntok); }, out_f32, out_hi, out_plane);
+                [=](long long g, int i) { return ((g / ntok) * T + i) * ntok + (g % ntok); }, out_f32, out_hi, out_plane, lse);
   return MAED_OK;
+}
+int attn_temporal_tc(const __half* qkv_hi, long long qkv_plane, int B, int T, int ntok, int heads, float scale, float* out_f32,
+                     __half* out_hi, long long out_plane, cudaStream_t st, float* lse) {
+  MAED_CHECK_ARG((T == 4 || T == 8 || T == 16 || T == 32) && qkv_plane != 0, "attn_temporal_tc: T=%d unsupported", T);
+  return attn_temporal(qkv_hi, qkv_plane, B, T, ntok, heads, scale, out_f32, out_hi, out_plane, st, lse);
 }
 
 int attn_generic(const __half* qkv_hi, long long qkv_plane, int batch, int seq, int heads, float scale, int, int,
@@ -427,8 +433,19 @@ int gemm_wgrad_splitk(const __half* A, long long a_plane, int lda, const __half*
 
 // ------------------------------------------------------------------------- spatial attention backward (tcgen05 kernel)
 // contract: the CUDA-core kernel of attention_bwd.cu (compiled from the real source) on d_out = hi + lo
+// (lse / Dv: the real kernel's shortcut around two reduction passes; the contract — the gradients — does not depend on them, but
+//  they must be what the forward / attn_rowdot produce: checked here against a recomputation on a few rows)
 int attn_spatial_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int BT, int ntok,
-                        int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st) {
+                        int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st, const float* lse, const float* Dv) {
+  MAED_CHECK_ARG((lse == nullptr) == (Dv == nullptr), "attn_spatial_bwd_tc: lse and D come together");
+  if (lse) {
+    std::vector<float> chk((size_t)BT * ntok * heads), o((size_t)BT * ntok * heads * 64);
+    attention_ref(qkv_hi, qkv_plane, BT, ntok, heads, scale, [=](long long g, int i) { return g * ntok + i; }, o.data(), nullptr, 0,
+                  chk.data());
+    for (long long i = 0; i < (long long)BT * ntok * heads; i += 37)
+      MAED_CHECK_ARG(fabsf(chk[i] - lse[i]) <= 1e-3f * (1.f + fabsf(chk[i])), "attn_spatial_bwd_tc: lse[%lld] = %f, expected %f", i,
+                     (double)lse[i], (double)chk[i]);
+  }
   MAED_CHECK_ARG(qkv_hi && dout_hi && d_qkv, "attn_spatial_bwd_tc: null argument");
   MAED_CHECK_ARG(ntok >= 1 && ntok <= 208, "attn_spatial_bwd_tc: ntok=%d unsupported (1..208)", ntok);
   const long long rows = (long long)BT * ntok;
@@ -447,7 +464,17 @@ int attn_spatial_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half*
 }
 
 int attn_temporal_bwd_tc(const __half* qkv_hi, long long qkv_plane, const __half* dout_hi, long long dout_plane, int B, int T,
-                         int ntok, int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st) {
+                         int ntok, int heads, float scale, int accumulate, float* d_qkv, cudaStream_t st, const float* lse,
+                         const float* Dv) {
+  MAED_CHECK_ARG((lse == nullptr) == (Dv == nullptr), "attn_temporal_bwd_tc: lse and D come together");
+  if (lse) {
+    std::vector<float> chk((size_t)B * T * ntok * heads), o((size_t)B * T * ntok * heads * 64);
+    attention_ref(qkv_hi, qkv_plane, (long long)B * ntok, T, heads, scale,
+                  [=](long long g, int i) { return ((g / ntok) * T + i) * ntok + (g % ntok); }, o.data(), nullptr, 0, chk.data());
+    for (long long i = 0; i < (long long)B * T * ntok * heads; i += 37)
+      MAED_CHECK_ARG(fabsf(chk[i] - lse[i]) <= 1e-3f * (1.f + fabsf(chk[i])), "attn_temporal_bwd_tc: lse[%lld] = %f, expected %f", i,
+                     (double)lse[i], (double)chk[i]);
+  }
   MAED_CHECK_ARG(qkv_hi && dout_hi && d_qkv, "attn_temporal_bwd_tc: null argument");
   MAED_CHECK_ARG(T == 4 || T == 8 || T == 16 || T == 32, "attn_temporal_bwd_tc: T=%d unsupported (4, 8, 16, 32)", T);
   const long long rows = (long long)B * T * ntok;

@@ -254,7 +254,7 @@ def test_ktd_tree_bwd(L):
 def _attention_ref(qkv, B, T, ntok, heads, scale, kind):
     BT = B * T
     q, k, v = qkv.reshape(BT, ntok, 3, heads, 64).permute(2, 0, 3, 1, 4)
-    if kind in ("spatial", "spatial_tc"):
+    if kind == "spatial":
         a = (q @ k.transpose(-2, -1) * scale).softmax(-1)
         return (a @ v).transpose(1, 2).reshape(BT * ntok, heads * 64)
     if kind == "coupling":                      # all T * ntok tokens of a clip attend to each other
@@ -271,6 +271,9 @@ def _attention_ref(qkv, B, T, ntok, heads, scale, kind):
                                            ("spatial_tc", 1, 1, 113), ("spatial_tc", 2, 1, 208), ("temporal", 2, 16, 197),
                                            ("temporal_tc", 2, 16, 197), ("temporal_tc", 8, 16, 197), ("temporal_tc", 3, 8, 50),
                                            ("temporal_tc", 1, 32, 64), ("temporal_tc", 2, 4, 33),
+                                           ("spatial_fast", 2, 2, 197), ("spatial_fast", 8, 16, 197), ("spatial_fast", 1, 3, 60),
+                                           ("temporal_fast", 2, 16, 197), ("temporal_fast", 8, 16, 197), ("temporal_fast", 1, 32, 64),
+                                           ("temporal_fast", 3, 8, 50),
                                            ("temporal", 3, 5, 33), ("temporal", 2, 1, 20), ("temporal", 1, 32, 50),
                                            ("coupling", 2, 3, 37), ("coupling", 1, 2, 197)])
 def test_attention_bwd(L, kind, B, T, ntok):
@@ -280,14 +283,16 @@ def test_attention_bwd(L, kind, B, T, ntok):
     d_out = _rand(B * T * ntok, heads * 64, seed=33)
     p = _planes(qkv, ops)
     qd = _join(p).requires_grad_(True)
-    _attention_ref(qd, B, T, ntok, heads, 0.125, kind.replace("temporal_tc", "temporal")).backward(d_out.double())
+    _attention_ref(qd, B, T, ntok, heads, 0.125, kind.split("_")[0]).backward(d_out.double())
     d_qkv = torch.full_like(qkv, 1.0)
     scratch = torch.empty(B * heads * T * ntok * 3, device=DEV) if kind == "coupling" else None
-    if kind in ("spatial_tc", "temporal_tc"):        # tcgen05 kernels (the emulator runs contract stubs): scratch = planes of d_out
+    if kind in ("spatial_tc", "temporal_tc", "spatial_fast", "temporal_fast"):
+        # tcgen05 kernels (the emulator runs contract stubs); *_fast: with the forward's row statistics, as the train step does
         if _is_emu() and B * T > 40:
             pytest.skip("bench-sized case: hardware only")
-        scratch = torch.empty(B * T * ntok * heads * 64, device=DEV)
-    _lib.call("maed_bwd_attention", {"spatial": 0, "temporal": 1, "coupling": 2, "spatial_tc": 3, "temporal_tc": 4}[kind], _lib.ptr(p), C.c_longlong(p[0].numel()),
+        rows = B * T * ntok
+        scratch = torch.empty(rows * heads * 64 * (2 if kind.endswith("fast") else 1) + 2 * rows * heads, device=DEV)
+    _lib.call("maed_bwd_attention", {"spatial": 0, "temporal": 1, "coupling": 2, "spatial_tc": 3, "temporal_tc": 4, "spatial_fast": 5, "temporal_fast": 6}[kind], _lib.ptr(p), C.c_longlong(p[0].numel()),
               _lib.ptr(d_out), B, T, ntok, heads, C.c_float(0.125), 1, _lib.ptr(d_qkv), _lib.ptr(scratch), _lib.stream_ptr())
     assert rel_err(d_qkv, qd.grad + 1.0) < 2e-5, kind
 
