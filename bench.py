@@ -98,14 +98,14 @@ def _profile(on):
 
 def build_model(device):
     from maed_b200.models import MAED
-    from oracle import synth          # deterministic random-init weights of that architecture (test infrastructure)
+    from maed_b200 import synth          # deterministic random-init weights of that architecture
     m = MAED("ste", 6, 12, MODE, DECODER, 1024)
     synth.fill_module_(m, 0)
     return m.to(device).eval()
 
 
 def _cpu_state():
-    from oracle import synth
+    from maed_b200 import synth
     from maed_b200.models import MAED
     m = MAED("ste", 6, 12, MODE, DECODER, 1024)
     synth.fill_module_(m, 0)
@@ -116,7 +116,7 @@ def cpu_forward_fn():
     """(callable x -> output dict, kind, description) of the CPU arm: the reference's OWN modules (unmodified
     lib/models from /root/reference or its verbatim git-ignored copy oracle/_ref/, imported through oracle/ref_shim.py)
     when that tree is present — kind "reference" —, else the pinned oracle port (oracle/maed_oracle.py) — kind "port"."""
-    from oracle import synth
+    from maed_b200 import synth
     try:
         from oracle import ref_shim
         if ref_shim.reference_available():
@@ -138,7 +138,7 @@ def cpu_forward_fn():
 def best_cpu_threads(fwd):
     """PyTorch CPU ops do not scale to every core of a 100+-core host (the first run used all 128 threads and was
     15x slower than 8 threads); pick the thread count that is fastest on a 2-frame probe clip."""
-    from oracle import synth
+    from maed_b200 import synth
     cores = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
     x = synth.synth_frames(1, 2, 1)
@@ -160,7 +160,7 @@ def cpu_clips_per_s(n_clips, reps, warmup=0, budget_s=None):
     """Times `reps` forwards of n_clips x T=16 on the host cores; returns (per-step seconds, kind, description, n_clips).
     With `budget_s` the batch per step is halved (8 -> 4 -> 2 -> 1 clips) until warmup + reps steps fit the budget, judged
     from a one-clip probe."""
-    from oracle import synth
+    from maed_b200 import synth
     fwd, kind, desc = cpu_forward_fn()
     best_cpu_threads(fwd)
     if budget_s:
@@ -238,7 +238,7 @@ def train_measure(args, dev, dist, world, rank, local, st_mode, encoder="ste", l
     Returns a dict (rank 0) or None."""
     from maed_b200 import ops, train
     from maed_b200.models import MAED
-    from oracle import synth
+    from maed_b200 import synth
     steps = steps or args.steps
     torch.manual_seed(0)
     cnn = encoder == "cnn"
@@ -443,7 +443,7 @@ def main():
     world, rank, local, dev, dist = _init(args)
     from maed_b200 import ops
     model = build_model(dev)
-    from oracle import synth
+    from maed_b200 import synth
     # 4 distinct device-resident batches (308 MB > 126 MB L2), rotated; a step also streams ~4.5 GB of workspace
     xs = [synth.synth_frames(CLIPS_PER_GPU, T, 100 + i).to(dev) for i in range(4)]
     for i in range(args.warmup):

@@ -134,10 +134,13 @@ int prep_conv_weight(const float* w, int Cout, int Cin, int KH, int KW, int k_pa
 // ------------------------------------------------------------------------------------------- im2col
 // Stem gather: a block builds the A rows of 32 consecutive output pixels of one output row in shared
 // memory (reads coalesced along the input row), then writes whole rows (16-byte stores).
-__global__ void im2col_stem_kernel(const float* __restrict__ x, int Cin, int H, int W, int KH, int KW, int stride,
+// CIN_ / KW_ > 0: compile-time shape (the 7x7 RGB stem: divisions by constants), 0: the runtime arguments
+template <int CIN_, int KW_>
+__global__ void im2col_stem_kernel(const float* __restrict__ x, int Cin_rt, int H, int W, int KH, int KW_rt, int stride,
                                    int pad_t, int pad_l, int OH, int OW, int k_pad, __half* __restrict__ hi,
                                    long long plane) {
   extern __shared__ float tile[];                       // [32][k_pad + 4]
+  const int Cin = CIN_ > 0 ? CIN_ : Cin_rt, KW = KW_ > 0 ? KW_ : KW_rt;
   const int ldt = k_pad + 4;                            // row stride = 28 (mod 32) for k_pad = 152: see the gather below
   const int tiles_w = (OW + 31) / 32;
   const int tw = blockIdx.x % tiles_w;
@@ -146,8 +149,7 @@ __global__ void im2col_stem_kernel(const float* __restrict__ x, int Cin, int H, 
   const int ow0 = tw * 32;
   const int Kreal = KH * KW * Cin;
   // gather: a warp fills 8 pixels x 4 columns per step (lane = 8 * column + pixel): with a row stride of 4 * odd floats the
-  // 32 shared-memory writes fall into 32 different banks (the first version wrote 32 pixels of one column: 8-way conflicts,
-  // 1.15 ms for the 128-frame stem), and every group of 8 lanes still reads one contiguous run of the input row
+  // 32 shared-memory writes fall into 32 different banks, and every group of 8 lanes reads one contiguous run of the input row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int units = 4 * (k_pad / 4);
   for (int u = warp; u < units; u += nwarps) {
@@ -163,14 +165,23 @@ __global__ void im2col_stem_kernel(const float* __restrict__ x, int Cin, int H, 
     tile[px * ldt + k] = v;
   }
   __syncthreads();
-  const int chunks = k_pad / 4;
+  // rows leave as 16-byte stores: 8 columns -> 8 hi halfs + 8 lo halfs (k_pad is a multiple of 8)
+  const int chunks = k_pad / 8;
   for (int idx = threadIdx.x; idx < 32 * chunks; idx += blockDim.x) {
     const int px = idx / chunks, ch = idx % chunks;
     const int ow = ow0 + px;
     if (ow >= OW) continue;
     const long long m = ((long long)n * OH + oh) * OW + ow;
-    const float4 v = *reinterpret_cast<const float4*>(&tile[px * ldt + ch * 4]);
-    store_split4(hi + m * k_pad + ch * 4, plane, v);
+    const float4 v0 = *reinterpret_cast<const float4*>(&tile[px * ldt + ch * 8]);
+    const float4 v1 = *reinterpret_cast<const float4*>(&tile[px * ldt + ch * 8 + 4]);
+    __half2 h0, l0, h1, l1, h2, l2, h3, l3;
+    split2(v0.x, v0.y, h0, l0); split2(v0.z, v0.w, h1, l1); split2(v1.x, v1.y, h2, l2); split2(v1.z, v1.w, h3, l3);
+    __half* o = hi + m * k_pad + ch * 8;
+    *reinterpret_cast<uint4*>(o) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                              *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+    if (plane)
+      *reinterpret_cast<uint4*>(o + plane) = make_uint4(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1),
+                                                        *reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&l3));
   }
 }
 int im2col_stem(const float* x, int n_img, int Cin, int H, int W, int KH, int KW, int stride, int pad_t, int pad_l,
@@ -178,8 +189,12 @@ int im2col_stem(const float* x, int n_img, int Cin, int H, int W, int KH, int KW
   MAED_CHECK_ARG(k_pad % 8 == 0, "im2col_stem: k_pad must be a multiple of 8");
   const int tiles_w = (OW + 31) / 32;
   const size_t smem = (size_t)32 * (k_pad + 4) * sizeof(float);
-  im2col_stem_kernel<<<n_img * OH * tiles_w, 256, smem, st>>>(x, Cin, H, W, KH, KW, stride, pad_t, pad_l, OH, OW, k_pad,
-                                                             out_hi, plane);
+  if (Cin == 3 && KW == 7)
+    im2col_stem_kernel<3, 7><<<n_img * OH * tiles_w, 256, smem, st>>>(x, Cin, H, W, KH, KW, stride, pad_t, pad_l, OH, OW, k_pad,
+                                                                     out_hi, plane);
+  else
+    im2col_stem_kernel<0, 0><<<n_img * OH * tiles_w, 256, smem, st>>>(x, Cin, H, W, KH, KW, stride, pad_t, pad_l, OH, OW, k_pad,
+                                                                     out_hi, plane);
   LAUNCH_CHECK();
   return MAED_OK;
 }

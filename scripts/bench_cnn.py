@@ -31,7 +31,7 @@ def main():
     from maed_b200 import build, ops
     from maed_b200.models import MAED
     from oracle import maed_oracle as O
-    from oracle import synth
+    from maed_b200 import synth
     build.build()
     dev = torch.device("cuda", 0)
     m = MAED("cnn", 6, 12, "vanilla", "ktd", 1024)

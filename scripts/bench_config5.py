@@ -29,7 +29,7 @@ def main():
     import bench
     from maed_b200 import build, ops, train
     from maed_b200.models import MAED
-    from oracle import synth
+    from maed_b200 import synth
     build.build()
     dev = torch.device("cuda", 0)
     m = MAED("ste", 6, 12, "parallel", "ktd", 1024, temp_frames=32)

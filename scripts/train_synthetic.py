@@ -52,7 +52,7 @@ def main():
     from maed_b200 import build, train
     from maed_b200.loss import Loss
     from maed_b200.models import MAED
-    from oracle import synth                      # deterministic random-init weights / frames (test infrastructure)
+    from maed_b200 import synth                      # deterministic random-init weights / frames
     build.build()
     if args.stage == 1:
         model, n, T = MAED("cnn", 6, 12, "vanilla", "ktd", 1024), 128, 1
