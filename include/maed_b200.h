@@ -208,8 +208,11 @@ int maed_bwd_layernorm(const float* dy, long long dy_stride, const float* x, lon
                        int C, float eps, const float* dx_add, float* dx_out, long long dx_stride, float* partial,
                        float* scratch, float* dgamma, float* dbeta, void* stream);
 int maed_bwd_layernorm_partial_rows(void);
+/* relu_beta: NULL, or the layer's beta when a ReLU followed the norm and dy is the gradient behind that ReLU (the mask is
+   recomputed from x); order: image order of the two passes over dy / x (0 up/up, 1 down/up, 2 up/down — L2 reuse only) */
 int maed_bwd_groupnorm(const float* dy, const float* x, int n_img, int HW, int C, const float* gamma, float eps,
-                       double* stats_scratch, float* red, float* dgb_partial, void* dx_hi, long long dx_plane, void* stream);
+                       double* stats_scratch, float* red, float* dgb_partial, void* dx_hi, long long dx_plane,
+                       const float* relu_beta, int order, void* stream);
 int maed_bwd_wstd(const float* g, int k_pad, const float* w, int Cout, int Cin, int KH, int KW, float eps, float scale, float* dw,
                   void* stream);
 int maed_bwd_gelu(const float* d_hid, const float* pre, long long n, void* out_hi, long long out_plane, void* stream);

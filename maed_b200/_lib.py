@@ -96,7 +96,7 @@ SIGNATURES = {
     "maed_bwd_colsum": (_I, [_P, _L, _I, _I, _F, _I, _P, _P, _P]),
     "maed_bwd_layernorm": (_I, [_P, _L, _P, _L, _P, _I, _I, _F, _P, _P, _L, _P, _P, _P, _P, _P]),
     "maed_bwd_layernorm_partial_rows": (_I, []),
-    "maed_bwd_groupnorm": (_I, [_P, _P, _I, _I, _I, _P, _F, _P, _P, _P, _P, _L, _P]),
+    "maed_bwd_groupnorm": (_I, [_P, _P, _I, _I, _I, _P, _F, _P, _P, _P, _P, _L, _P, _I, _P]),
     "maed_bwd_batchnorm_scratch_doubles": (_Z, [_L, _I]),
     "maed_bwd_batchnorm": (_I, [_P, _L, _I, _P, _P, _F, _F, _P, _P, _I, _P, _L, _P, _L, _P, _P, _P, _F, _P, _P, _P, _L, _P, _P]),
     "maed_bwd_maxpool3x3s2": (_I, [_P, _I, _I, _I, _I, _P, _L, _P, _P, _P, _P]),

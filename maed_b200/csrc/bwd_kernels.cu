@@ -204,8 +204,10 @@ int scale_f32(const float* a, float s, long long n, float* out, cudaStream_t st)
 }
 
 // ---------------------------------------------------------------------------------- elementwise backward
-__global__ void relu_mask_kernel(float* __restrict__ d, const __half* __restrict__ act, long long n4) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+// reverse: walk from the end of the tensor (the part its producer wrote last is still in L2)
+__global__ void relu_mask_kernel(float* __restrict__ d, const __half* __restrict__ act, long long n4, int reverse) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n4; j += (long long)gridDim.x * blockDim.x) {
+    const long long i = reverse ? n4 - 1 - j : j;
     float4 v = reinterpret_cast<float4*>(d)[i];
     const uint2 a = reinterpret_cast<const uint2*>(act)[i];
     const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
@@ -217,9 +219,9 @@ __global__ void relu_mask_kernel(float* __restrict__ d, const __half* __restrict
     reinterpret_cast<float4*>(d)[i] = v;
   }
 }
-int relu_mask_f32(float* d, const __half* act_hi, long long n, cudaStream_t st) {
+int relu_mask_f32(float* d, const __half* act_hi, long long n, cudaStream_t st, int reverse) {
   MAED_CHECK_ARG(n % 4 == 0, "relu_mask_f32: n must be a multiple of 4");
-  relu_mask_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(d, act_hi, n / 4);
+  relu_mask_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(d, act_hi, n / 4, reverse);
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
 }
@@ -411,11 +413,15 @@ __device__ __forceinline__ void gn_group_stats(const double* stats, int n, int H
   __syncthreads();
 }
 // stage 1: per (image, hw-chunk, channel): A = sum dy*xhat, B = sum dy.   grid (chunks, n_img), 256 threads.
+// relu_gb (gamma, beta of the layer) != nullptr: the GroupNorm was followed by a ReLU and dy is the gradient w.r.t. the ReLU's
+// OUTPUT; the mask (xhat * gamma + beta > 0, the forward's own expression) is applied on the fly instead of by a separate pass
+// over dy.  reverse: images in descending order (see groupnorm_bwd).
 __global__ void gn_bwd_stage1_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                     const double* __restrict__ stats, int HW, int C, float eps, float* __restrict__ part) {
+                                     const double* __restrict__ stats, int HW, int C, float eps, float* __restrict__ part,
+                                     const float* __restrict__ relu_g, const float* __restrict__ relu_b, int reverse) {
   __shared__ float s_mean[32], s_rstd[32];
   __shared__ float s_a[256], s_b[256];
-  const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const int n = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   gn_group_stats(stats, n, HW, C, eps, s_mean, s_rstd);
   const int gsz = C / 32;
   const int per = (HW + chunks - 1) / chunks;
@@ -425,11 +431,13 @@ __global__ void gn_bwd_stage1_kernel(const float* __restrict__ dy, const float* 
   if (C <= 256) {
     const int c = threadIdx.x % C, rr = threadIdx.x / C, rstep = 256 / C;
     const float mean = s_mean[c / gsz], rstd = s_rstd[c / gsz];
+    const float mg = relu_g ? relu_g[c] : 0.f, mb = relu_g ? relu_b[c] : 1.f;     // no ReLU: xhat * 0 + 1 > 0 always
     float a = 0.f, b = 0.f;
     for (int hw = hw0 + rr; hw < hw1; hw += rstep) {
       const long long off = base + (long long)hw * C + c;
-      const float d = dy[off];
-      a += d * (x[off] - mean) * rstd;
+      const float xhat = (x[off] - mean) * rstd;
+      const float d = (xhat * mg + mb > 0.f) ? dy[off] : 0.f;
+      a += d * xhat;
       b += d;
     }
     s_a[threadIdx.x] = a;
@@ -443,11 +451,13 @@ __global__ void gn_bwd_stage1_kernel(const float* __restrict__ dy, const float* 
   } else {
     for (int c = threadIdx.x; c < C; c += 256) {
       const float mean = s_mean[c / gsz], rstd = s_rstd[c / gsz];
+      const float mg = relu_g ? relu_g[c] : 0.f, mb = relu_g ? relu_b[c] : 1.f;
       float a = 0.f, b = 0.f;
       for (int hw = hw0; hw < hw1; ++hw) {
         const long long off = base + (long long)hw * C + c;
-        const float d = dy[off];
-        a += d * (x[off] - mean) * rstd;
+        const float xhat = (x[off] - mean) * rstd;
+        const float d = (xhat * mg + mb > 0.f) ? dy[off] : 0.f;
+        a += d * xhat;
         b += d;
       }
       po[c] = a;
@@ -479,9 +489,9 @@ __global__ void gn_bwd_stage2_kernel(const float* __restrict__ part, int chunks,
 __global__ void gn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                     const double* __restrict__ stats, const float* __restrict__ gamma,
                                     const float* __restrict__ red, int HW, int C, float eps, __half* __restrict__ out,
-                                    long long out_plane) {
+                                    long long out_plane, const float* __restrict__ relu_b, int reverse) {
   __shared__ float s_mean[32], s_rstd[32], s_m1[32], s_m2[32];
-  const int n = blockIdx.y;
+  const int n = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   gn_group_stats(stats, n, HW, C, eps, s_mean, s_rstd);
   if (threadIdx.x < 32) {
     const float cnt = (float)HW * (float)(C / 32);
@@ -498,19 +508,26 @@ __global__ void gn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
     const float4 d = *reinterpret_cast<const float4*>(dy + off);
     const float4 v = *reinterpret_cast<const float4*>(x + off);
     const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 b4 = relu_b ? *reinterpret_cast<const float4*>(relu_b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float dd[4] = {d.x, d.y, d.z, d.w}, vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w};
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
     float r[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int grp = (c + e) / gsz;
       const float xhat = (vv[e] - s_mean[grp]) * s_rstd[grp];
-      r[e] = s_rstd[grp] * (dd[e] * gg[e] - s_m1[grp] - xhat * s_m2[grp]);
+      const float de = (!relu_b || xhat * gg[e] + bb[e] > 0.f) ? dd[e] : 0.f;
+      r[e] = s_rstd[grp] * (de * gg[e] - s_m1[grp] - xhat * s_m2[grp]);
     }
     store_split4(out + off, out_plane, make_float4(r[0], r[1], r[2], r[3]));
   }
 }
+// relu_beta != nullptr: dy is the gradient behind the ReLU that followed this GroupNorm (mask recomputed, see stage 1).
+// order 0: both passes walk the images upwards; 1: the producer of dy wrote it upwards, so the statistics pass walks DOWN (the
+// last images are still in L2) and the apply pass UP again (the first images were read last); 2: the mirror image of 1.
 int groupnorm_bwd(const float* dy, const float* x, const double* stats, const float* gamma, int n_img, int HW, int C,
-                  float eps, float* red, float* dgb_partial, __half* dx_hi, long long dx_plane, cudaStream_t st) {
+                  float eps, float* red, float* dgb_partial, __half* dx_hi, long long dx_plane, cudaStream_t st,
+                  const float* relu_beta, int order) {
   MAED_CHECK_ARG(C % 32 == 0 && C % 4 == 0 && (C <= 256 ? 256 % C == 0 : true) && C <= 4096,
                  "groupnorm_bwd: C=%d unsupported", C);
   // the stage-1 partials live at the tail of `red`'s scratch: caller provides red with n_img*(64 + 16*2*C) floats
@@ -519,7 +536,8 @@ int groupnorm_bwd(const float* dy, const float* x, const double* stats, const fl
   if (chunks < 1) chunks = 1;
   if (chunks > HW) chunks = HW;
   float* part = red + (long long)n_img * 64;
-  gn_bwd_stage1_kernel<<<dim3(chunks, n_img), 256, 0, st>>>(dy, x, stats, HW, C, eps, part);
+  gn_bwd_stage1_kernel<<<dim3(chunks, n_img), 256, 0, st>>>(dy, x, stats, HW, C, eps, part, relu_beta ? gamma : nullptr, relu_beta,
+                                                            order == 1);
   MAED_BW_LAUNCH_CHECK();
   gn_bwd_stage2_kernel<<<n_img, 256, 2 * C * sizeof(float), st>>>(part, chunks, gamma, C, dgb_partial, red);
   MAED_BW_LAUNCH_CHECK();
@@ -528,7 +546,8 @@ int groupnorm_bwd(const float* dy, const float* x, const double* stats, const fl
   const int maxb = cdiv(per_img, 256);
   if (bpi > maxb) bpi = maxb;
   if (bpi < 1) bpi = 1;
-  gn_bwd_apply_kernel<<<dim3(bpi, n_img), 256, 0, st>>>(dy, x, stats, gamma, red, HW, C, eps, dx_hi, dx_plane);
+  gn_bwd_apply_kernel<<<dim3(bpi, n_img), 256, 0, st>>>(dy, x, stats, gamma, red, HW, C, eps, dx_hi, dx_plane, relu_beta,
+                                                        order == 2);
   MAED_BW_LAUNCH_CHECK();
   return MAED_OK;
 }

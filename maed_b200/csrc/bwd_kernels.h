@@ -29,7 +29,7 @@ int scale_f32(const float* a, float s, long long n, float* out, cudaStream_t st)
 
 // ---- elementwise backward
 // d[i] = hi[i] > 0 ? d[i] : 0            (ReLU mask taken from the saved post-ReLU activation planes)
-int relu_mask_f32(float* d, const __half* act_hi, long long n, cudaStream_t st);
+int relu_mask_f32(float* d, const __half* act_hi, long long n, cudaStream_t st, int reverse = 0);
 // d_pre = d_hid * gelu'(pre) -> planes    (exact erf GELU, reference vision_transformer.py:100)
 int gelu_bwd(const float* d_hid, const float* pre, long long n, __half* out_hi, long long out_plane, cudaStream_t st);
 // y = gelu(pre) -> planes                 (training forward keeps `pre`)
@@ -51,7 +51,10 @@ int layernorm_bwd(const float* dy, long long dy_stride, const float* x, long lon
 //   dx = rstd * (dy*gamma - mean_g(dy*gamma) - xhat * mean_g(dy*gamma*xhat)) -> planes
 //   dgb_partial: [n_img][2][C] per-image (sum dy*xhat | sum dy); red: [n_img][32][2] floats (scratch)
 int groupnorm_bwd(const float* dy, const float* x, const double* stats, const float* gamma, int n_img, int HW, int C,
-                  float eps, float* red, float* dgb_partial, __half* dx_hi, long long dx_plane, cudaStream_t st);
+                  float eps, float* red, float* dgb_partial, __half* dx_hi, long long dx_plane, cudaStream_t st,
+                  const float* relu_beta = nullptr, int order = 0);
+//   relu_beta: the layer's beta when a ReLU followed the norm and dy is the gradient behind that ReLU (the mask
+//   xhat*gamma+beta > 0 is recomputed on the fly); order: image order of the two passes (0 up/up, 1 down/up, 2 up/down)
 
 // ---- weight standardisation backward (reference resnetv2.py:86-89): g = dL/dW_hat in the packed layout
 // [Cout][kh][kw][Cin] (row stride k_pad) -> dW OIHW = scale * ((g - mean g)/(std+eps) - w_hat * mean(g*w_hat)/std)

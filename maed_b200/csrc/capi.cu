@@ -218,11 +218,13 @@ int maed_bwd_layernorm(const float* dy, long long dy_stride, const float* x, lon
   return colsum_f32(partial + C, 2 * C, pr, C, 1.f, 0, scratch, dbeta, st);
 }
 int maed_bwd_groupnorm(const float* dy, const float* x, int n_img, int HW, int C, const float* gamma, float eps,
-                       double* stats_scratch, float* red, float* dgb_partial, void* dx_hi, long long dx_plane, void* stream) {
+                       double* stats_scratch, float* red, float* dgb_partial, void* dx_hi, long long dx_plane,
+                       const float* relu_beta, int order, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   MAED_CUDA_CHECK(cudaMemsetAsync(stats_scratch, 0, (size_t)n_img * 64 * sizeof(double), st));
-  MAED_PROPAGATE(gn_stats(x, n_img, HW, C, stats_scratch, st));
-  return groupnorm_bwd(dy, x, stats_scratch, gamma, n_img, HW, C, eps, red, dgb_partial, (__half*)dx_hi, dx_plane, st);
+  MAED_PROPAGATE(gn_stats(x, n_img, HW, C, stats_scratch, st, order == 1));
+  return groupnorm_bwd(dy, x, stats_scratch, gamma, n_img, HW, C, eps, red, dgb_partial, (__half*)dx_hi, dx_plane, st, relu_beta,
+                       order);
 }
 size_t maed_bwd_batchnorm_scratch_doubles(long long M, int C) { return bn_scratch_doubles(M, C); }
 int maed_bwd_batchnorm(const float* x, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,

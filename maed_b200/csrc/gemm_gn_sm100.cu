@@ -19,6 +19,8 @@
 //
 // Versus the unfused pipeline (GEMM writes fp32, gn_stats reads it, gn_apply reads it again and writes planes)
 // this removes 12 of the 16 bytes of HBM traffic per conv-output element.  In-kernel timeline: scripts/dbg_gn_timeline.py.
+#include <cstdlib>
+
 #include "gemm_host.h"
 #include "kernels.h"
 #include "sm100_ptx.cuh"
@@ -33,7 +35,8 @@ static constexpr int kGnMaxCluster = 8;
 template <int BN> struct ResSlots { static constexpr int value = (BN <= 64) ? 3 : 2; };
 
 struct GemmGnParams {
-  int HW, C, K, num_k_blocks, nsplit, stages;
+  int HW, C, K, num_k_blocks, nsplit, stages;   // stages: depth of the A ring
+  int b_stages, b_shared;      // depth of the B ring; b_shared: one B load per K block serves all tiles of the CTA
   int tiles_per_image, tpc, n_blocks, cluster, items;
   uint32_t a_tx_bytes;
   uint32_t o_tx_bytes;         // bytes of one 32-channel half-box plane (rows x 64 B)
@@ -86,10 +89,15 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic ST/LD)
   const int np = p.nsplit == 3 ? 2 : 1;
-  const uint32_t stage_bytes = np * (kABytes + kBBytes);
+  // operand rings: A slots [stages][np][128 x 64] then B slots [b_stages][np][BN x 64].  They are separate because a B
+  // block (a K slice of the weights) is the same for every M tile of the item: with b_shared the loops run K-block-outer /
+  // tile-inner and each B block crosses the L2 -> SM port once per item instead of once per tile.  These kernels are bound
+  // by that port (A + B bytes per MMA cycle), not by the tensor pipe.
+  const uint32_t a_slot = np * kABytes, b_slot = np * kBBytes;
+  uint8_t* sBring = smem + (size_t)p.stages * a_slot;
   // staging after the pipeline stages.  Shortcut layers: [2 groups][kResSlots][hi | lo][128 rows x 64 B] half-boxes (the
   // shortcut lands here by TMA, is updated IN PLACE and stored by TMA); other layers: [2 groups][hi | lo][128 x 128 B] boxes.
-  uint8_t* sOut = smem + (size_t)p.stages * stage_bytes;
+  uint8_t* sOut = sBring + (size_t)p.b_stages * b_slot;
   uint8_t* sRes = sOut;
   double* s_warp_part = reinterpret_cast<double*>(sOut + p.box_bytes);     // [2 groups][4 warps][32 groups][2]
   double* s_parts = s_warp_part + 2 * 4 * 32 * 2;                          // [2 groups][8 ranks][32 groups][2]
@@ -103,7 +111,9 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* parts_full = half_empty + 2;                                   // [2 buf]
   uint64_t* res_full = parts_full + 2;                                     // [2 groups][4 slots]: slot may be used by the epilogue
   uint64_t* box_ready = res_full + 8;                                      // [2 groups][4 slots]: slot holds a finished result
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(box_ready + 8);
+  uint64_t* b_full = box_ready + 8;                                        // [2] B ring
+  uint64_t* b_empty = b_full + 2;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(b_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CS = p.cluster;
@@ -115,6 +125,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && elect_one()) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO); prefetch_tmap(&tmOw); if (p.res) prefetch_tmap(&tmR); }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int t = 0; t < 2 * kGnMaxTpc; ++t) mbar_init(&tile_full[t], 1);
     for (int h = 0; h < 2; ++h) { mbar_init(&half_empty[h], 4); mbar_init(&parts_full[h], CS * G); }
     for (int h = 0; h < 8; ++h) { mbar_init(&res_full[h], 1); mbar_init(&box_ready[h], 128); }
@@ -131,6 +142,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================================================================ TMA producer
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
+      int sb = 0; uint32_t bphase = 0;
       for (int item = cluster_id; item < p.items; item += n_clusters) {
         const int img = item / p.n_blocks, nb = item % p.n_blocks;
         if (p.res) {
@@ -144,24 +156,30 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
           }
         }
-        for (int tl = 0; tl < my_tiles; ++tl) {
-          const int t = t_lo + tl;
-          int h0 = 0, w0 = 0;
-          if (p.conv) { h0 = (t / p.tiles_w) * p.tile_h; w0 = (t % p.tiles_w) * p.tile_w; }
-          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int n_outer = p.b_shared ? p.num_k_blocks : my_tiles, n_inner = p.b_shared ? my_tiles : p.num_k_blocks;
+        for (int o = 0; o < n_outer; ++o) {
+          for (int i = 0; i < n_inner; ++i) {
+            const int kb = p.b_shared ? o : i, tl = p.b_shared ? i : o;
+            if (!p.b_shared || i == 0) {
+              mbar_wait(&b_empty[sb], bphase ^ 1);
+              uint8_t* sB = sBring + (size_t)sb * b_slot;
+              mbar_arrive_expect_tx(&b_full[sb], np * kBBytes);
+              for (int pl = 0; pl < np; ++pl) tma_load_3d(sB + pl * kBBytes, &tmB, &b_full[sb], kb * 64, nb * BN, pl);
+              if (++sb == p.b_stages) { sb = 0; bphase ^= 1; }
+            }
+            const int t = t_lo + tl;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sA = smem + (size_t)stage * stage_bytes;
-            uint8_t* sB = sA + np * kABytes;
-            mbar_arrive_expect_tx(&full_bar[stage], np * (p.a_tx_bytes + kBBytes));
+            uint8_t* sA = smem + (size_t)stage * a_slot;
+            mbar_arrive_expect_tx(&full_bar[stage], np * p.a_tx_bytes);
             for (int pl = 0; pl < np; ++pl) {
               if (p.conv) {
+                const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
                 const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
                 tma_load_5d(sA + pl * kABytes, &tmA, &full_bar[stage], cb * 64, w0 + tap % p.KW - p.pad_w,
                             h0 + tap / p.KW - p.pad_h, img, pl);
               } else {
                 tma_load_3d(sA + pl * kABytes, &tmA, &full_bar[stage], kb * 64, img * p.HW + t * 128, pl);
               }
-              tma_load_3d(sB + pl * kBBytes, &tmB, &full_bar[stage], kb * 64, nb * BN, pl);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -173,18 +191,22 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(128, BN, 0);
       int stage = 0; uint32_t phase = 0;
+      int sb = 0; uint32_t bphase = 0;
       uint32_t j = 0;
       for (int item = cluster_id; item < p.items; item += n_clusters, ++j) {
         const uint32_t half = j & 1, hphase = (j >> 1) & 1;      // epilogue group `half` handles this item
         mbar_wait(&half_empty[half], hphase ^ 1);
         tc_fence_after();
-        for (int tl = 0; tl < my_tiles; ++tl) {
-          const uint32_t d = tmem_base + half * 256 + tl * BN;
-          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int n_outer = p.b_shared ? p.num_k_blocks : my_tiles, n_inner = p.b_shared ? my_tiles : p.num_k_blocks;
+        for (int o = 0; o < n_outer; ++o) {
+          for (int i = 0; i < n_inner; ++i) {
+            const int kb = p.b_shared ? o : i, tl = p.b_shared ? i : o;
+            const uint32_t d = tmem_base + half * 256 + tl * BN;
+            if (!p.b_shared || i == 0) mbar_wait(&b_full[sb], bphase);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t aH = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t bH = aH + np * kABytes;
+            const uint32_t aH = smem_u32(smem + (size_t)stage * a_slot);
+            const uint32_t bH = smem_u32(sBring + (size_t)sb * b_slot);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t da = umma_desc_k_sw128(aH + k * 32), db = umma_desc_k_sw128(bH + k * 32);
@@ -195,6 +217,10 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             umma_commit(&empty_bar[stage]);
+            if (!p.b_shared || i == n_inner - 1) {
+              umma_commit(&b_empty[sb]);
+              if (++sb == p.b_stages) { sb = 0; bphase ^= 1; }
+            }
             if (kb == p.num_k_blocks - 1) umma_commit(&tile_full[half * kGnMaxTpc + tl]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -465,16 +491,17 @@ template <int BN, int GSZ>
 static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
                      const CUtensorMap& tmOw, GemmGnParams& p, cudaStream_t st) {
   const int np = p.nsplit == 3 ? 2 : 1;
-  const size_t stage_bytes = (size_t)np * (128 * 64 * 2 + BN * 64 * 2);
+  const size_t a_slot = (size_t)np * 128 * 64 * 2, b_slot = (size_t)np * BN * 64 * 2;
   p.res_slots = p.res ? ResSlots<BN>::value : 2;
   p.box_bytes = 2 * p.res_slots * 16384;
   const size_t fixed = 1024 + p.box_bytes + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
-                       (2 * kGnMaxStages + 2 * kGnMaxTpc + 20) * 8 + 64;
-  int stages = (int)((232448 - fixed) / stage_bytes);
+                       (2 * kGnMaxStages + 2 * kGnMaxTpc + 24) * 8 + 64;
+  p.b_stages = 2;
+  int stages = (int)((232448 - fixed - p.b_stages * b_slot) / a_slot);
   if (stages > kGnMaxStages) stages = kGnMaxStages;
   if (stages < 2) { set_error("gemm_gn: tile too large for shared memory"); return MAED_ERR_UNSUPPORTED; }
   p.stages = stages;
-  const size_t smem = fixed + (size_t)stages * stage_bytes;
+  const size_t smem = fixed + (size_t)stages * a_slot + (size_t)p.b_stages * b_slot;
   static bool attr_set = false;
   if (!attr_set) {
     MAED_CUDA_CHECK(cudaFuncSetAttribute(gemm_gn_kernel<BN, GSZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -540,7 +567,11 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   int bn, cluster, tpc;
   if (a.res) {
     // shortcut layers are epilogue-bound: 64-wide blocks leave shared memory for 3 shortcut slots (2 TMA loads in flight)
-    if (p.tiles_per_image <= 2) { bn = 64; tpc = 2; cluster = 1; }
+    // ... except with at most 2 tiles per image (stage 2: 14 x 14): there the L2 -> SM port is the bound and a 128-wide
+    // block halves the number of times the image's A tiles are fetched (MAED_B200_GN_RES_BN128=0: the 64-wide plan)
+    static const bool res128 = !(getenv("MAED_B200_GN_RES_BN128") && atoi(getenv("MAED_B200_GN_RES_BN128")) == 0);
+    if (p.tiles_per_image <= 2 && res128 && a.C % 128 == 0 && 128 % gsz == 0) { bn = 128; tpc = 2; cluster = 1; }
+    else if (p.tiles_per_image <= 2) { bn = 64; tpc = 2; cluster = 1; }
     else if (p.tiles_per_image <= 8) { bn = 64; tpc = 4; cluster = 2; }
     else if (p.tiles_per_image <= 32) { bn = 64; tpc = 4; cluster = 8; }
     else return MAED_ERR_UNSUPPORTED;
@@ -553,6 +584,8 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   if (bn % gsz != 0 || (bn / 2) % gsz != 0 || a.C % bn != 0 || tpc * bn > 256 || tpc * cluster < p.tiles_per_image)
     return MAED_ERR_UNSUPPORTED;
   p.cluster = cluster; p.tpc = tpc;
+  static const bool b_shared = !(getenv("MAED_B200_GN_BSHARED") && atoi(getenv("MAED_B200_GN_BSHARED")) == 0);
+  p.b_shared = b_shared ? 1 : 0;
   p.n_blocks = a.C / bn;
   p.items = a.n_img * p.n_blocks;
   if (a.conv) {

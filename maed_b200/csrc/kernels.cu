@@ -237,11 +237,12 @@ int im2col_nhwc(const __half* in_hi, long long in_plane, int n_img, int H, int W
 
 // ---------------------------------------------------------------------------------------- GroupNorm
 // grid (chunks, n_img).  A thread owns 4 consecutive channels and strides over the pixel rows of its chunk.
-__global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int rows_per_chunk, double* __restrict__ stats) {
+__global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int rows_per_chunk, double* __restrict__ stats,
+                                int reverse) {
   __shared__ double gs[32], gq[32];
   if (threadIdx.x < 32) { gs[threadIdx.x] = 0.0; gq[threadIdx.x] = 0.0; }
   __syncthreads();
-  const int n = blockIdx.y;
+  const int n = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   const int c4n = C >> 2;
   const int rows_per_iter = blockDim.x / c4n;            // blockDim is a multiple of c4n (or c4n >= blockDim)
   const int gsz = C / 32;
@@ -283,7 +284,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int 
     atomicAdd(&stats[((long long)n * 32 + threadIdx.x) * 2 + 1], gq[threadIdx.x]);
   }
 }
-int gn_stats(const float* x, int n_img, int HW, int C, double* stats, cudaStream_t st) {
+int gn_stats(const float* x, int n_img, int HW, int C, double* stats, cudaStream_t st, int reverse) {
   MAED_CHECK_ARG(C % 32 == 0 && C >= 32, "gn_stats: C=%d must be a multiple of 32", C);
   const int threads = 256;
   const int c4n = C / 4;
@@ -294,7 +295,7 @@ int gn_stats(const float* x, int n_img, int HW, int C, double* stats, cudaStream
   if (chunks < 1) chunks = 1;
   const int rows_per_chunk = cdiv(HW, chunks);
   chunks = cdiv(HW, rows_per_chunk);
-  gn_stats_kernel<<<dim3(chunks, n_img), threads, 0, st>>>(x, HW, C, rows_per_chunk, stats);
+  gn_stats_kernel<<<dim3(chunks, n_img), threads, 0, st>>>(x, HW, C, rows_per_chunk, stats, reverse);
   LAUNCH_CHECK();
   return MAED_OK;
 }
@@ -316,9 +317,9 @@ __device__ __forceinline__ void gn_load_stats(const double* stats, int n, int HW
 __global__ void gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, float eps,
                                 int relu, const __half* __restrict__ res, long long res_plane, __half* __restrict__ out,
-                                long long out_plane) {
+                                long long out_plane, int reverse) {
   __shared__ float s_mean[32], s_rstd[32];
-  const int n = blockIdx.y;
+  const int n = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   gn_load_stats(stats, n, HW, C, eps, s_mean, s_rstd);
   const int c4n = C >> 2, gsz = C / 32;
   const long long total = (long long)HW * c4n;
@@ -344,14 +345,14 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, const double* __res
 }
 int gn_apply(const float* x, const double* stats, const float* gamma, const float* beta, int n_img, int HW, int C,
              float eps, int relu, const __half* res_hi, long long res_plane, __half* out_hi, long long out_plane,
-             cudaStream_t st) {
+             cudaStream_t st, int reverse) {
   const long long per_img = (long long)HW * C / 4;
   int bpi = cdiv((long long)sm_count() * 8, n_img);
   const int maxb = cdiv(per_img, 256);
   if (bpi > maxb) bpi = maxb;
   if (bpi < 1) bpi = 1;
   gn_apply_kernel<<<dim3(bpi, n_img), 256, 0, st>>>(x, stats, gamma, beta, HW, C, eps, relu, res_hi, res_plane, out_hi,
-                                                    out_plane);
+                                                    out_plane, reverse);
   LAUNCH_CHECK();
   return MAED_OK;
 }

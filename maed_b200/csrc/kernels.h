@@ -37,11 +37,12 @@ int stem_conv(const float* x, int n_img, const __half* w_hi, long long w_plane, 
 
 // ---- GroupNorm(32 groups, eps) over NHWC fp32 conv outputs (reference resnetv2.py:45-49)
 // stats: double [n_img][32][2] = (sum, sumsq), must be zeroed by the caller (gn_stats accumulates).
-int gn_stats(const float* x, int n_img, int HW, int C, double* stats, cudaStream_t st);
+// reverse (here and in gn_apply): walk the images downwards — the producer of x wrote upwards, its last images are still in L2
+int gn_stats(const float* x, int n_img, int HW, int C, double* stats, cudaStream_t st, int reverse = 0);
 // y = relu?( (x-mean)*rstd*gamma + beta (+ residual) ) -> planes
 int gn_apply(const float* x, const double* stats, const float* gamma, const float* beta, int n_img, int HW, int C,
              float eps, int relu, const __half* res_hi, long long res_plane, __half* out_hi, long long out_plane,
-             cudaStream_t st);
+             cudaStream_t st, int reverse = 0);
 // stem: GN + ReLU + MaxPool2dSame(3, stride 2) fused (reference resnetv2.py:61-72)
 int gn_apply_maxpool(const float* x, const double* stats, const float* gamma, const float* beta, int n_img, int H,
                      int W, int C, float eps, __half* out_hi, long long out_plane, cudaStream_t st);

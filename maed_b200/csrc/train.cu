@@ -496,7 +496,8 @@ static int conv_fwd(const Ctx& c, int l) {
                     w.out[l], w.out_plane[l], c.st);
   }
   MAED_CUDA_CHECK(cudaMemsetAsync(w.stats[l], 0, (size_t)BT * 64 * 8, c.st));
-  MAED_PROPAGATE(gn_stats(w.convout[l], BT, L.Hout * L.Hout, L.Cout, w.stats[l], c.st));
+  // the conv GEMM wrote convout upwards: statistics walk the images downwards (the tail is still in L2), the apply pass upwards
+  MAED_PROPAGATE(gn_stats(w.convout[l], BT, L.Hout * L.Hout, L.Cout, w.stats[l], c.st, 1));
   MAED_PROPAGATE(gn_apply(w.convout[l], w.stats[l], c.P(L.g_idx), c.P(L.g_idx + 1), BT, L.Hout * L.Hout, L.Cout, 1e-5f, L.relu,
                           res, res_plane, w.out[l], w.out_plane[l], c.st));
   return MAED_OK;
@@ -730,7 +731,10 @@ static int linear_wgrad(const Ctx& c, const __half* dy, long long dy_plane, int 
 // Backward of one conv + GroupNorm layer.  d_y: gradient w.r.t. the GN output (ReLU mask already applied), fp32
 // [Mout, Cout].  Writes the parameter gradients; when d_in != nullptr also d_in = dgrad (+ d_in_add), fp32 [Min, Cin]
 // (d_in may alias d_in_add).  tmp_f32: scratch of Mout*Cin floats (1x1 stride-2 data gradient only).
-static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_in_add, float* d_in, float* tmp_f32) {
+// relu_fused: d_y is the gradient behind the ReLU that follows this layer's GroupNorm and the mask has NOT been applied yet (the
+// GroupNorm backward recomputes it; BatchNorm layers ignore the flag, their callers mask d_y themselves).  order: see groupnorm_bwd.
+static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_in_add, float* d_in, float* tmp_f32,
+                          bool relu_fused = false, int order = 0) {
   const ConvL& L = c.net.L[l];
   TrainWs& w = c.w;
   const int BT = c.BT;
@@ -742,9 +746,13 @@ static int conv_layer_bwd(const Ctx& c, int l, const float* d_y, const float* d_
                           c.G(L.g_idx), c.G(L.g_idx + 1), w.pl_a, w.pl_a_plane, &c.e.bn_exchange, c.st));
   } else {
     MAED_PROPAGATE(groupnorm_bwd(d_y, w.convout[l], w.stats[l], c.P(L.g_idx), BT, HWo, L.Cout, 1e-5f, w.red, w.dgb, w.pl_a,
-                                 w.pl_a_plane, c.st));
-    MAED_PROPAGATE(colsum_f32(w.dgb, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx), c.st));
-    MAED_PROPAGATE(colsum_f32(w.dgb + L.Cout, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx + 1), c.st));
+                                 w.pl_a_plane, c.st, relu_fused ? c.P(L.g_idx + 1) : nullptr, order));
+    if (c.G(L.g_idx + 1) == c.G(L.g_idx) + L.Cout) {       // gamma and beta gradients are neighbours in the flat buffer: one pass
+      MAED_PROPAGATE(colsum_f32(w.dgb, 2 * L.Cout, BT, 2 * L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx), c.st));
+    } else {
+      MAED_PROPAGATE(colsum_f32(w.dgb, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx), c.st));
+      MAED_PROPAGATE(colsum_f32(w.dgb + L.Cout, 2 * L.Cout, BT, L.Cout, c.inv_ls, 0, w.colsum_scratch, c.G(L.g_idx + 1), c.st));
+    }
   }
   // ---- weight gradient: dW_hat [Cout, kc] = dconv^T * im2col(x), then through the weight standardisation
   const int kc = (l == 0) ? kStemKPad : L.Kcols();
@@ -931,7 +939,7 @@ static int cnn_train_backward(const Engine& e, const void* const* params, const 
     const ConvL& L3 = net.L[bl.c3];
     const ConvL& L2 = net.L[bl.c2];
     const ConvL& L1 = net.L[bl.c1];
-    MAED_PROPAGATE(relu_mask_f32(g, w.out[bl.c3], L3.Mout(BT) * L3.Cout, st));
+    MAED_PROPAGATE(relu_mask_f32(g, w.out[bl.c3], L3.Mout(BT) * L3.Cout, st, 1));
     const float* shortcut_grad = g;
     float* d_xin = g;
     if (bl.ds >= 0) {
@@ -940,9 +948,9 @@ static int cnn_train_backward(const Engine& e, const void* const* params, const 
       d_xin = d_short;
     }
     MAED_PROPAGATE(conv_layer_bwd(c, bl.c3, g, nullptr, d_t2, nullptr));
-    MAED_PROPAGATE(relu_mask_f32(d_t2, w.out[bl.c2], L2.Mout(BT) * L2.Cout, st));
+    MAED_PROPAGATE(relu_mask_f32(d_t2, w.out[bl.c2], L2.Mout(BT) * L2.Cout, st, 1));
     MAED_PROPAGATE(conv_layer_bwd(c, bl.c2, d_t2, nullptr, d_t1, nullptr));
-    MAED_PROPAGATE(relu_mask_f32(d_t1, w.out[bl.c1], L1.Mout(BT) * L1.Cout, st));
+    MAED_PROPAGATE(relu_mask_f32(d_t1, w.out[bl.c1], L1.Mout(BT) * L1.Cout, st, 1));
     MAED_PROPAGATE(conv_layer_bwd(c, bl.c1, d_t1, shortcut_grad, d_xin, nullptr));
     if (bl.ds >= 0) std::swap(bufs[0], bufs[1]);
   }
@@ -1123,19 +1131,19 @@ int train_backward(const Engine* ep, const void* const* params, const void* pack
     const ConvL& L3 = net.L[bl.c3];
     const ConvL& L2 = net.L[bl.c2];
     const ConvL& L1 = net.L[bl.c1];
-    MAED_PROPAGATE(relu_mask_f32(g, w.out[bl.c3], L3.Mout(BT) * L3.Cout, st));
+    // ReLU behind the block sum: g is read three times (shortcut, c3, downsample), so this mask is materialised — walking
+    // downwards, g was written upwards by the GEMM before.  The ReLUs behind c1 / c2 are folded into their GroupNorm backward.
+    MAED_PROPAGATE(relu_mask_f32(g, w.out[bl.c3], L3.Mout(BT) * L3.Cout, st, 1));
     const float* shortcut_grad = g;
     float* d_xin = g;
     if (bl.ds >= 0) {
-      MAED_PROPAGATE(conv_layer_bwd(c, bl.ds, g, nullptr, d_short, d_t2));
+      MAED_PROPAGATE(conv_layer_bwd(c, bl.ds, g, nullptr, d_short, d_t2, false, 2));
       shortcut_grad = d_short;
       d_xin = d_short;
     }
-    MAED_PROPAGATE(conv_layer_bwd(c, bl.c3, g, nullptr, d_t2, nullptr));
-    MAED_PROPAGATE(relu_mask_f32(d_t2, w.out[bl.c2], L2.Mout(BT) * L2.Cout, st));
-    MAED_PROPAGATE(conv_layer_bwd(c, bl.c2, d_t2, nullptr, d_t1, nullptr));
-    MAED_PROPAGATE(relu_mask_f32(d_t1, w.out[bl.c1], L1.Mout(BT) * L1.Cout, st));
-    MAED_PROPAGATE(conv_layer_bwd(c, bl.c1, d_t1, shortcut_grad, d_xin, nullptr));
+    MAED_PROPAGATE(conv_layer_bwd(c, bl.c3, g, nullptr, d_t2, nullptr, false, bl.ds >= 0 ? 0 : 2));
+    MAED_PROPAGATE(conv_layer_bwd(c, bl.c2, d_t2, nullptr, d_t1, nullptr, true, 1));
+    MAED_PROPAGATE(conv_layer_bwd(c, bl.c1, d_t1, shortcut_grad, d_xin, nullptr, true, 1));
     if (bl.ds >= 0) std::swap(bufs[0], bufs[1]);            // the block-input gradient now lives in d_short's buffer
   }
   // stem: max-pool + ReLU + GroupNorm + conv (no data gradient: the input frames need none)

@@ -108,7 +108,7 @@ def main():
     red, dgb = torch.empty(n * (64 + 32 * Cc), device=dev), torch.empty(n, 2, Cc, device=dev)
     dxp = torch.empty(2, n, HW, Cc, dtype=torch.float16, device=dev)
     ms = timed(lambda: _lib.call("maed_bwd_groupnorm", _lib.ptr(dy), _lib.ptr(x), n, HW, Cc, _lib.ptr(gamma), C.c_float(1e-5), _lib.ptr(stats),
-                                 _lib.ptr(red), _lib.ptr(dgb), _lib.ptr(dxp), C.c_longlong(dxp[0].numel()), st()), args.reps)
+                                 _lib.ptr(red), _lib.ptr(dgb), _lib.ptr(dxp), C.c_longlong(dxp[0].numel()), None, 0, st()), args.reps)
     rec("groupnorm_bwd (+ stats) 128x3136x256", ms, gbytes=n * HW * Cc * (4 + 4 + 4 + 4 + 4) / 1e9)
     # ---- BatchNorm train forward + backward on the same map ('cnn' layer1 output)
     M = n * HW

@@ -97,21 +97,32 @@ def test_layernorm_bwd(L, rows, C_):
     assert rel_err(dg, gd.grad) < 2e-6 and rel_err(db, bd.grad) < 2e-6
 
 
-@pytest.mark.parametrize("n,HW,C_", [(3, 196, 256), (2, 3136, 64), (2, 49, 1024), (5, 784, 128), (1, 200, 512)])
-def test_groupnorm_bwd(L, n, HW, C_):
+@pytest.mark.parametrize("n,HW,C_,relu,order", [(3, 196, 256, 0, 0), (2, 3136, 64, 1, 1), (2, 49, 1024, 0, 2), (5, 784, 128, 1, 2),
+                                                (1, 200, 512, 1, 0), (4, 196, 256, 1, 1)])
+def test_groupnorm_bwd(L, n, HW, C_, relu, order):
+    """relu: dy is the gradient behind the ReLU that follows the norm (mask recomputed inside the kernels, reference
+    resnetv2.py:35-49 GroupNormAct); order: the zig-zag image orders of the two passes (results must not depend on it)."""
     _lib, _ = L
     x, dy = _rand(n, HW, C_, seed=7), _rand(n, HW, C_, seed=8)
     gamma = 1 + 0.1 * _rand(C_, seed=9)
+    beta = 0.2 * _rand(C_, seed=10)
     xd = x.double().permute(0, 2, 1).reshape(n, C_, HW, 1).requires_grad_(True)
     gd = gamma.double().requires_grad_(True)
-    bd = torch.zeros(C_, dtype=torch.float64, device=DEV, requires_grad=True)
-    F.group_norm(xd, 32, gd, bd, 1e-5).backward(dy.double().permute(0, 2, 1).reshape(n, C_, HW, 1))
+    bd = beta.double().requires_grad_(True)
+    y = F.group_norm(xd, 32, gd, bd, 1e-5)
+    if relu:
+        # keep the comparison away from the kink: elements whose pre-activation is within fp32 rounding of 0 get no gradient
+        safe = (y.detach().abs() > 1e-4).to(dy.dtype).reshape(n, C_, HW).permute(0, 2, 1)
+        dy = dy * safe.float()
+        y = F.relu(y)
+    y.backward(dy.double().permute(0, 2, 1).reshape(n, C_, HW, 1))
     stats = torch.empty(n * 64, dtype=torch.float64, device=DEV)
     red = torch.empty(n * (64 + 32 * C_), device=DEV)
     dgb = torch.empty(n, 2, C_, device=DEV)
     dx = torch.empty(2, n, HW, C_, dtype=torch.float16, device=DEV)
     _lib.call("maed_bwd_groupnorm", _lib.ptr(dy), _lib.ptr(x), n, HW, C_, _lib.ptr(gamma), C.c_float(1e-5), _lib.ptr(stats),
-              _lib.ptr(red), _lib.ptr(dgb), _lib.ptr(dx), C.c_longlong(dx[0].numel()), _lib.stream_ptr())
+              _lib.ptr(red), _lib.ptr(dgb), _lib.ptr(dx), C.c_longlong(dx[0].numel()), _lib.ptr(beta) if relu else None, order,
+              _lib.stream_ptr())
     ref_dx = xd.grad.reshape(n, C_, HW).permute(0, 2, 1)
     assert rel_err(_join(dx), ref_dx) < 1e-5
     assert rel_err(dgb[:, 0].double().sum(0), gd.grad) < 1e-5 and rel_err(dgb[:, 1].double().sum(0), bd.grad) < 1e-5
