@@ -420,49 +420,55 @@ __global__ void gn_bwd_stage1_kernel(const float* __restrict__ dy, const float* 
                                      const double* __restrict__ stats, int HW, int C, float eps, float* __restrict__ part,
                                      const float* __restrict__ relu_g, const float* __restrict__ relu_b, int reverse) {
   __shared__ float s_mean[32], s_rstd[32];
-  __shared__ float s_a[256], s_b[256];
+  __shared__ float4 s_a[256], s_b[256];
   const int n = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   gn_group_stats(stats, n, HW, C, eps, s_mean, s_rstd);
-  const int gsz = C / 32;
+  const int gsz = C / 32, c4n = C >> 2;
   const int per = (HW + chunks - 1) / chunks;
   const int hw0 = chunk * per, hw1 = min(HW, hw0 + per);
   const long long base = (long long)n * HW * C;
   float* po = part + ((long long)n * chunks + chunk) * 2 * C;
-  if (C <= 256) {
-    const int c = threadIdx.x % C, rr = threadIdx.x / C, rstep = 256 / C;
-    const float mean = s_mean[c / gsz], rstd = s_rstd[c / gsz];
-    const float mg = relu_g ? relu_g[c] : 0.f, mb = relu_g ? relu_b[c] : 1.f;     // no ReLU: xhat * 0 + 1 > 0 always
-    float a = 0.f, b = 0.f;
+  // a thread owns 4 neighbouring channels (16-byte loads of dy and x, both issued before either is used); with C / 4 <= 256
+  // threads per row the block walks 256 / (C / 4) rows per step, wider maps loop over their channel quads
+  const bool tiled = c4n <= 256 && 256 % c4n == 0;
+  const int rstep = tiled ? 256 / c4n : 1;
+  for (int c4 = tiled ? threadIdx.x % c4n : threadIdx.x; c4 < c4n; c4 += 256) {
+    const int c = c4 * 4, rr = tiled ? threadIdx.x / c4n : 0;
+    float m[4], r[4], mg[4], mb[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      m[e] = s_mean[(c + e) / gsz]; r[e] = s_rstd[(c + e) / gsz];
+      mg[e] = relu_g ? relu_g[c + e] : 0.f; mb[e] = relu_g ? relu_b[c + e] : 1.f;     // no ReLU: xhat * 0 + 1 > 0 always
+    }
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int hw = hw0 + rr; hw < hw1; hw += rstep) {
       const long long off = base + (long long)hw * C + c;
-      const float xhat = (x[off] - mean) * rstd;
-      const float d = (xhat * mg + mb > 0.f) ? dy[off] : 0.f;
-      a += d * xhat;
-      b += d;
-    }
-    s_a[threadIdx.x] = a;
-    s_b[threadIdx.x] = b;
-    __syncthreads();
-    if (threadIdx.x < C) {
-      for (int k = 1; k < rstep; ++k) { a += s_a[threadIdx.x + k * C]; b += s_b[threadIdx.x + k * C]; }
-      po[c] = a;
-      po[C + c] = b;
-    }
-  } else {
-    for (int c = threadIdx.x; c < C; c += 256) {
-      const float mean = s_mean[c / gsz], rstd = s_rstd[c / gsz];
-      const float mg = relu_g ? relu_g[c] : 0.f, mb = relu_g ? relu_b[c] : 1.f;
-      float a = 0.f, b = 0.f;
-      for (int hw = hw0; hw < hw1; ++hw) {
-        const long long off = base + (long long)hw * C + c;
-        const float xhat = (x[off] - mean) * rstd;
-        const float d = (xhat * mg + mb > 0.f) ? dy[off] : 0.f;
-        a += d * xhat;
-        b += d;
+      const float4 xv = *reinterpret_cast<const float4*>(x + off);
+      const float4 dv = *reinterpret_cast<const float4*>(dy + off);
+      const float xx[4] = {xv.x, xv.y, xv.z, xv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xhat = (xx[e] - m[e]) * r[e];
+        const float d = (xhat * mg[e] + mb[e] > 0.f) ? dd[e] : 0.f;
+        a[e] += d * xhat;
+        b[e] += d;
       }
-      po[c] = a;
-      po[C + c] = b;
     }
+    float4 av = make_float4(a[0], a[1], a[2], a[3]), bv = make_float4(b[0], b[1], b[2], b[3]);
+    if (tiled && rstep > 1) {
+      s_a[threadIdx.x] = av;
+      s_b[threadIdx.x] = bv;
+      __syncthreads();                                     // uniform: tiled blocks run the c4 loop exactly once
+      if (threadIdx.x >= c4n) break;
+      for (int k = 1; k < rstep; ++k) {
+        const float4 pa = s_a[threadIdx.x + k * c4n], pb = s_b[threadIdx.x + k * c4n];
+        av.x += pa.x; av.y += pa.y; av.z += pa.z; av.w += pa.w;
+        bv.x += pb.x; bv.y += pb.y; bv.z += pb.z; bv.w += pb.w;
+      }
+    }
+    *reinterpret_cast<float4*>(po + c) = av;
+    *reinterpret_cast<float4*>(po + C + c) = bv;
   }
 }
 // stage 2: sum the chunks -> dgb_partial[n][2][C]; group sums red[n][g] = (sum_c gamma*B, sum_c gamma*A).  grid n_img.
@@ -528,10 +534,9 @@ __global__ void gn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
 int groupnorm_bwd(const float* dy, const float* x, const double* stats, const float* gamma, int n_img, int HW, int C,
                   float eps, float* red, float* dgb_partial, __half* dx_hi, long long dx_plane, cudaStream_t st,
                   const float* relu_beta, int order) {
-  MAED_CHECK_ARG(C % 32 == 0 && C % 4 == 0 && (C <= 256 ? 256 % C == 0 : true) && C <= 4096,
-                 "groupnorm_bwd: C=%d unsupported", C);
+  MAED_CHECK_ARG(C % 32 == 0 && C <= 4096, "groupnorm_bwd: C=%d unsupported", C);
   // the stage-1 partials live at the tail of `red`'s scratch: caller provides red with n_img*(64 + 16*2*C) floats
-  int chunks = cdiv(2LL * sm_count(), n_img);
+  int chunks = cdiv(8LL * sm_count(), n_img);             // several waves of blocks: no tail imbalance at 2-3 blocks per SM
   if (chunks > 16) chunks = 16;
   if (chunks < 1) chunks = 1;
   if (chunks > HW) chunks = HW;
