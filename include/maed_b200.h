@@ -80,6 +80,11 @@ int maed_op_groupnorm(const float* x, int n_img, int HW, int C, const float* gam
                       int relu, const void* res_hi, long long res_plane, void* out_hi, long long out_plane,
                       double* stats_scratch, void* stream);
 /* stem: GN + ReLU + MaxPool2dSame(3,2) (reference resnetv2.py:61-72,245-274) */
+/* GroupNorm of the training forward: same result as maed_op_groupnorm, one thread-block cluster per image when the shape allows
+   (x leaves HBM once); `stats` [n_img][32][2] doubles (sum, sum of squares) is an OUTPUT kept on the tape for maed_bwd_groupnorm */
+int maed_op_groupnorm_train(const float* x, int n_img, int HW, int C, const float* gamma, const float* beta, float eps, int relu,
+                            const void* res_hi, long long res_plane, void* out_hi, long long out_plane, double* stats,
+                            void* stream);
 int maed_op_groupnorm_maxpool(const float* x, int n_img, int H, int W, int C, const float* gamma, const float* beta,
                               float eps, void* out_hi, long long out_plane, double* stats_scratch, void* stream);
 /* 'cnn' encoder (torchvision ResNet-50, reference lib/models/maed.py:35-37), inference:

@@ -68,6 +68,7 @@ SIGNATURES = {
     "maed_op_conv_gn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _L, _P, _L, _P, _P]),
     "maed_op_stem_conv": (_I, [_P, _I, _P, _L, _I, _I, _P, _P, _P]),
     "maed_op_groupnorm": (_I, [_P, _I, _I, _I, _P, _P, _F, _I, _P, _L, _P, _L, _P, _P]),
+    "maed_op_groupnorm_train": (_I, [_P, _I, _I, _I, _P, _P, _F, _I, _P, _L, _P, _L, _P, _P]),
     "maed_op_groupnorm_maxpool": (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _L, _P, _P]),
     "maed_op_layernorm": (_I, [_P, _L, _P, _P, _I, _I, _F, _P, _L, _P]),
     "maed_op_attention": (_I, [_I, _P, _L, _I, _I, _I, _I, _F, _I, _P, _P, _L, _P]),

@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmaed_b200.so")
 SOURCES = ["gemm_host.cu", "kernels.cu", "attention.cu", "stem_sm100.cu", "gemm_gn_sm100.cu", "decoder.cu", "engine.cu",
            "cnn_kernels.cu", "cnn_engine.cu",
-           "bwd_kernels.cu", "bwd_kernels2.cu", "attention_bwd.cu", "attention_bwd_sm100.cu", "attention_temporal_sm100.cu", "gemm_splitk_sm100.cu", "train.cu", "smpl.cu", "loss.cu", "decode_bwd.cu", "capi.cu"]
+           "bwd_kernels.cu", "bwd_kernels2.cu", "gn_cluster.cu", "attention_bwd.cu", "attention_bwd_sm100.cu", "attention_temporal_sm100.cu", "gemm_splitk_sm100.cu", "train.cu", "smpl.cu", "loss.cu", "decode_bwd.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -535,6 +535,12 @@ int groupnorm_bwd(const float* dy, const float* x, const double* stats, const fl
                   float eps, float* red, float* dgb_partial, __half* dx_hi, long long dx_plane, cudaStream_t st,
                   const float* relu_beta, int order) {
   MAED_CHECK_ARG(C % 32 == 0 && C <= 4096, "groupnorm_bwd: C=%d unsupported", C);
+#ifndef MAED_EMU
+  {                                                        // one cluster per image (gn_cluster.cu): dy and x leave HBM once
+    const int rc = groupnorm_bwd_cluster(dy, x, stats, gamma, relu_beta, n_img, HW, C, eps, dgb_partial, dx_hi, dx_plane, st);
+    if (rc != MAED_ERR_UNSUPPORTED) return rc;
+  }
+#endif
   // the stage-1 partials live at the tail of `red`'s scratch: caller provides red with n_img*(64 + 16*2*C) floats
   int chunks = cdiv(8LL * sm_count(), n_img);             // several waves of blocks: no tail imbalance at 2-3 blocks per SM
   if (chunks > 16) chunks = 16;

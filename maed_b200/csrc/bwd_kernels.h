@@ -56,6 +56,16 @@ int groupnorm_bwd(const float* dy, const float* x, const double* stats, const fl
 //   relu_beta: the layer's beta when a ReLU followed the norm and dy is the gradient behind that ReLU (the mask
 //   xhat*gamma+beta > 0 is recomputed on the fly); order: image order of the two passes (0 up/up, 1 down/up, 2 up/down)
 
+// gn_cluster.cu: the same two operations with one thread-block cluster per image (single HBM read of x / dy, second pass from
+// L2); MAED_ERR_UNSUPPORTED (nothing launched) for shapes they do not cover or with MAED_B200_GN_CLUSTER=0 -> multi-kernel path.
+// The forward variant also writes the (sum, sumsq) statistics [n_img][32][2] the backward reads.
+int groupnorm_fwd_cluster(const float* x, const float* gamma, const float* beta, int n_img, int HW, int C, float eps, int relu,
+                          const __half* res_hi, long long res_plane, __half* out_hi, long long out_plane, double* stats,
+                          cudaStream_t st);
+int groupnorm_bwd_cluster(const float* dy, const float* x, const double* stats, const float* gamma, const float* relu_beta,
+                          int n_img, int HW, int C, float eps, float* dgb_partial, __half* dx_hi, long long dx_plane,
+                          cudaStream_t st);
+
 // ---- weight standardisation backward (reference resnetv2.py:86-89): g = dL/dW_hat in the packed layout
 // [Cout][kh][kw][Cin] (row stride k_pad) -> dW OIHW = scale * ((g - mean g)/(std+eps) - w_hat * mean(g*w_hat)/std)
 int wstd_bwd(const float* g, int k_pad, const float* w, int Cout, int Cin, int KH, int KW, float eps, float scale,

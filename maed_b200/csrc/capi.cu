@@ -110,6 +110,17 @@ int maed_op_groupnorm(const float* x, int n_img, int HW, int C, const float* gam
   return gn_apply(x, stats_scratch, gamma, beta, n_img, HW, C, eps, relu, (const __half*)res_hi, res_plane, (__half*)out_hi,
                   out_plane, st);
 }
+int maed_op_groupnorm_train(const float* x, int n_img, int HW, int C, const float* gamma, const float* beta, float eps, int relu,
+                            const void* res_hi, long long res_plane, void* out_hi, long long out_plane, double* stats,
+                            void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+#ifndef MAED_EMU
+  const int rc = groupnorm_fwd_cluster(x, gamma, beta, n_img, HW, C, eps, relu, (const __half*)res_hi, res_plane, (__half*)out_hi,
+                                       out_plane, stats, st);
+  if (rc != MAED_ERR_UNSUPPORTED) return rc;
+#endif
+  return maed_op_groupnorm(x, n_img, HW, C, gamma, beta, eps, relu, res_hi, res_plane, out_hi, out_plane, stats, stream);
+}
 int maed_op_groupnorm_maxpool(const float* x, int n_img, int H, int W, int C, const float* gamma, const float* beta, float eps,
                               void* out_hi, long long out_plane, double* stats_scratch, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;

@@ -495,6 +495,13 @@ static int conv_fwd(const Ctx& c, int l) {
     return bn_apply(w.convout[l], w.bn_mean[l], w.bn_rstd[l], c.P(L.g_idx), c.P(L.g_idx + 1), M, L.Cout, L.relu, res, res_plane,
                     w.out[l], w.out_plane[l], c.st);
   }
+#ifndef MAED_EMU
+  {                                                        // one cluster per image: statistics + apply with a single HBM read of convout
+    const int rc = groupnorm_fwd_cluster(w.convout[l], c.P(L.g_idx), c.P(L.g_idx + 1), BT, L.Hout * L.Hout, L.Cout, 1e-5f, L.relu, res,
+                                         res_plane, w.out[l], w.out_plane[l], w.stats[l], c.st);
+    if (rc != MAED_ERR_UNSUPPORTED) return rc;
+  }
+#endif
   MAED_CUDA_CHECK(cudaMemsetAsync(w.stats[l], 0, (size_t)BT * 64 * 8, c.st));
   // the conv GEMM wrote convout upwards: statistics walk the images downwards (the tail is still in L2), the apply pass upwards
   MAED_PROPAGATE(gn_stats(w.convout[l], BT, L.Hout * L.Hout, L.Cout, w.stats[l], c.st, 1));

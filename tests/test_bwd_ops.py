@@ -97,6 +97,31 @@ def test_layernorm_bwd(L, rows, C_):
     assert rel_err(dg, gd.grad) < 2e-6 and rel_err(db, bd.grad) < 2e-6
 
 
+@pytest.mark.parametrize("n,HW,C_,relu,res", [(3, 196, 256, 1, 0), (2, 3136, 64, 1, 0), (3, 196, 1024, 1, 1), (5, 784, 128, 0, 0),
+                                              (2, 784, 512, 1, 1), (1, 50, 256, 0, 1)])
+def test_groupnorm_train_forward(L, n, HW, C_, relu, res):
+    """GroupNorm of the training forward (cluster-per-image kernel on the GPU, the multi-kernel path on the emulator): planes
+    and the (sum, sumsq) statistics it leaves on the tape, vs torch float64 (reference resnetv2.py:35-49)."""
+    _lib, ops = L
+    x = _rand(n, HW, C_, scale=2.0, seed=21) + 0.3
+    gamma, beta = 1 + 0.1 * _rand(C_, seed=22), 0.1 * _rand(C_, seed=23)
+    r = _rand(n, HW, C_, seed=24) if res else None
+    rp = ops.split(r) if res else None
+    out = torch.empty(2, n, HW, C_, dtype=torch.float16, device=DEV)
+    stats = torch.full((n, 32, 2), -1.0, dtype=torch.float64, device=DEV)
+    _lib.call("maed_op_groupnorm_train", _lib.ptr(x), n, HW, C_, _lib.ptr(gamma), _lib.ptr(beta), C.c_float(1e-5), relu,
+              _lib.ptr(rp) if res else None, C.c_longlong(rp[0].numel() if res else 0), _lib.ptr(out), C.c_longlong(out[0].numel()),
+              _lib.ptr(stats), _lib.stream_ptr())
+    ref = F.group_norm(x.permute(0, 2, 1).double(), 32, gamma.double(), beta.double(), 1e-5).permute(0, 2, 1)
+    if res:
+        ref = ref + r.double()
+    if relu:
+        ref = F.relu(ref)
+    assert rel_err(_join(out), ref) < 1e-6
+    xg = x.double().reshape(n, HW, 32, C_ // 32)
+    assert rel_err(stats[:, :, 0], xg.sum((1, 3))) < 1e-6 and rel_err(stats[:, :, 1], (xg * xg).sum((1, 3))) < 1e-6
+
+
 @pytest.mark.parametrize("n,HW,C_,relu,order", [(3, 196, 256, 0, 0), (2, 3136, 64, 1, 1), (2, 49, 1024, 0, 2), (5, 784, 128, 1, 2),
                                                 (1, 200, 512, 1, 0), (4, 196, 256, 1, 1)])
 def test_groupnorm_bwd(L, n, HW, C_, relu, order):
