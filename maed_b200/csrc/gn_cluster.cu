@@ -27,7 +27,6 @@ using namespace bw;
 
 namespace {
 
-constexpr int kThreads = 512;
 
 struct GnClusterParams {
   int HW, C, CS, relu;
@@ -41,6 +40,7 @@ struct GnClusterParams {
 };
 
 // shared memory: float4 acc[2][kThreads] | float part[2][C] | float grp[32][2] | float mean[32], rstd[32]
+template <int kThreads>
 __device__ __forceinline__ void reduce_rows(float4* acc, float* part, int C, int c4n, int rstep, const float4& av,
                                             const float4& bv) {
   acc[threadIdx.x] = av;
@@ -58,8 +58,11 @@ __device__ __forceinline__ void reduce_rows(float4* acc, float* part, int C, int
   }
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(kThreads, 2) gn_cluster_kernel(const GnClusterParams p) {
+// kThreads = 512, 2 CTAs per SM: the general shape.  kThreads = 128, up to 8 CTAs per SM: small maps whose whole batch fits
+// the L2 — all clusters of the grid are resident at once, so the phases of different images overlap instead of running in
+// waves (a CTA's life is a chain of ~8 memory / cluster-barrier latencies).
+template <bool BWD, int kThreads>
+__global__ void __launch_bounds__(kThreads, kThreads == 128 ? 8 : 2) gn_cluster_kernel(const GnClusterParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int C = p.C, HW = p.HW, CS = p.CS, c4n = C >> 2, gsz = C / 32;
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_cluster_kernel(const GnCluster
         for (int e = 0; e < 4; ++e) { a[e] += xx[e]; b[e] += xx[e] * xx[e]; }
       }
     }
-    reduce_rows(acc, part, C, c4n, rstep, make_float4(a[0], a[1], a[2], a[3]), make_float4(b[0], b[1], b[2], b[3]));
+    reduce_rows<kThreads>(acc, part, C, c4n, rstep, make_float4(a[0], a[1], a[2], a[3]), make_float4(b[0], b[1], b[2], b[3]));
   }
   cluster.sync();
   // ----------------------------------------------------------------------------------------------- exchange
@@ -221,38 +224,48 @@ bool cluster_enabled() {
   return on;
 }
 
-template <bool BWD>
-int launch(GnClusterParams& p, int n_img, cudaStream_t st) {
-  const int C = p.C;
-  // a thread owns 4 channels and a CTA row step covers whole rows; the exchange gives every CTA whole groups
-  if (!cluster_enabled() || C % 32 != 0 || C / 4 > kThreads || kThreads % (C / 4) != 0) return MAED_ERR_UNSUPPORTED;
-  const int CS = 8;
-  if (p.HW < CS || C / CS > kThreads) return MAED_ERR_UNSUPPORTED;
-  p.CS = CS;
-  size_t smem = 2 * kThreads * sizeof(float4) + (size_t)(2 * C + 64 + 64) * sizeof(float);
-  // residency: the images in flight (clusters resident x bytes the two passes share) should fit the L2 (126 MB): large
-  // images get one CTA per SM by asking for more than half of the shared memory
-  const double per_image = (double)p.HW * C * 4.0 * (BWD ? 2.0 : 1.0);
-  if (per_image * (2.0 * sm_count() / CS) > 64e6 && smem < 120 * 1024) smem = 120 * 1024;
+template <bool BWD, int kThreads>
+int launch_t(GnClusterParams& p, int n_img, size_t smem_floor, cudaStream_t st) {
+  size_t smem = 2 * kThreads * sizeof(float4) + (size_t)(2 * p.C + 64 + 64) * sizeof(float);
+  if (smem < smem_floor) smem = smem_floor;
   static bool attr_set = false;
   if (!attr_set) {
-    MAED_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    MAED_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<BWD, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(n_img * CS);
+  cfg.gridDim = dim3(n_img * p.CS);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = p.CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MAED_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_cluster_kernel<BWD>, p));
+  MAED_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_cluster_kernel<BWD, kThreads>, p));
   count_launch();
   return MAED_OK;
+}
+
+template <bool BWD>
+int launch(GnClusterParams& p, int n_img, cudaStream_t st) {
+  const int C = p.C, c4n = C / 4, CS = 8;
+  // a thread owns 4 channels and a CTA row step covers whole rows; the exchange gives every CTA whole groups
+  if (!cluster_enabled() || C % 32 != 0 || p.HW < CS) return MAED_ERR_UNSUPPORTED;
+  p.CS = CS;
+  // what the two passes share must stay in the L2 (126 MB, half of it as budget) between them
+  const double per_image = (double)p.HW * C * 4.0 * (BWD ? 2.0 : 1.0);
+  const double budget = 64e6;
+  if (c4n <= 128 && 128 % c4n == 0 && C / CS <= 128 && per_image * n_img <= budget &&
+      (long long)n_img * CS <= 7LL * sm_count())
+    return launch_t<BWD, 128>(p, n_img, 0, st);                        // the whole batch in flight
+  if (c4n > 512 || 512 % c4n != 0 || C / CS > 512) return MAED_ERR_UNSUPPORTED;
+  if (per_image * (2.0 * sm_count() / CS) <= budget) return launch_t<BWD, 512>(p, n_img, 0, st);
+  // larger images would need one CTA per SM to fit: measured slower than the multi-kernel path (574 vs 366 us on the
+  // 56 x 56 x 256 maps), which streams with several times the threads in flight
+  return MAED_ERR_UNSUPPORTED;
 }
 
 }  // namespace
