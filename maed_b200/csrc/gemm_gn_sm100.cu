@@ -111,9 +111,9 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* parts_full = half_empty + 2;                                   // [2 buf]
   uint64_t* res_full = parts_full + 2;                                     // [2 groups][4 slots]: slot may be used by the epilogue
   uint64_t* box_ready = res_full + 8;                                      // [2 groups][4 slots]: slot holds a finished result
-  uint64_t* b_full = box_ready + 8;                                        // [2] B ring
-  uint64_t* b_empty = b_full + 2;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(b_empty + 2);
+  uint64_t* b_full = box_ready + 8;                                        // [kGnMaxStages] B ring
+  uint64_t* b_empty = b_full + kGnMaxStages;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(b_empty + kGnMaxStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CS = p.cluster;
@@ -125,7 +125,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && elect_one()) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO); prefetch_tmap(&tmOw); if (p.res) prefetch_tmap(&tmR); }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int t = 0; t < 2 * kGnMaxTpc; ++t) mbar_init(&tile_full[t], 1);
     for (int h = 0; h < 2; ++h) { mbar_init(&half_empty[h], 4); mbar_init(&parts_full[h], CS * G); }
     for (int h = 0; h < 8; ++h) { mbar_init(&res_full[h], 1); mbar_init(&box_ready[h], 128); }
@@ -495,10 +495,11 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   p.res_slots = p.res ? ResSlots<BN>::value : 2;
   p.box_bytes = 2 * p.res_slots * 16384;
   const size_t fixed = 1024 + p.box_bytes + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
-                       (2 * kGnMaxStages + 2 * kGnMaxTpc + 24) * 8 + 64;
-  p.b_stages = 2;
-  int stages = (int)((232448 - fixed - p.b_stages * b_slot) / a_slot);
+                       (4 * kGnMaxStages + 2 * kGnMaxTpc + 20) * 8 + 64;
+  // shared B blocks turn over once per K block: two slots; otherwise the B ring is as deep as the A ring (one B per A tile)
+  int stages = p.b_shared ? (int)((232448 - fixed - 2 * b_slot) / a_slot) : (int)((232448 - fixed) / (a_slot + b_slot));
   if (stages > kGnMaxStages) stages = kGnMaxStages;
+  p.b_stages = p.b_shared ? 2 : stages;
   if (stages < 2) { set_error("gemm_gn: tile too large for shared memory"); return MAED_ERR_UNSUPPORTED; }
   p.stages = stages;
   const size_t smem = fixed + (size_t)stages * a_slot + (size_t)p.b_stages * b_slot;
@@ -584,8 +585,11 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   if (bn % gsz != 0 || (bn / 2) % gsz != 0 || a.C % bn != 0 || tpc * bn > 256 || tpc * cluster < p.tiles_per_image)
     return MAED_ERR_UNSUPPORTED;
   p.cluster = cluster; p.tpc = tpc;
+  // one B load per K block for all tiles of the CTA: measured (profiles/r02_fwd_step_per_launch_v3_l2.txt) -25 % bytes through
+  // the L2 -> SM port everywhere, but faster only with 2 tiles per CTA (stage 1/2: -3 .. -8 %); with 4 tiles per CTA all tiles
+  // of an item finish together and the epilogue loses its head start (stage 0: +4 .. +12 %)
   static const bool b_shared = !(getenv("MAED_B200_GN_BSHARED") && atoi(getenv("MAED_B200_GN_BSHARED")) == 0);
-  p.b_shared = b_shared ? 1 : 0;
+  p.b_shared = (b_shared && tpc <= 2) ? 1 : 0;
   p.n_blocks = a.C / bn;
   p.items = a.n_img * p.n_blocks;
   if (a.conv) {
