@@ -76,15 +76,22 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int BN, int GSZ>
+// PAIR: the two CTAs of a cluster (tiles 0 and 1 of a 14 x 14 image) issue ONE tcgen05.mma.cta_group::2 per step (M = 256):
+// each CTA stages its own 128 rows of A and only HALF of the B block, so a BN = 256 block fits (64 KB per stage) and the
+// shared-memory traffic per MMA cycle drops from 128 + 85 B/clk (128 x 128 tiles) to 64 + 42 B/clk.  Protocol as in
+// gemm2_sm100.cuh: operand-full barriers live in the leader (rank 0) and collect the bytes of both producers, empty / tile-full
+// barriers are signalled in both CTAs by multicast commits, the TMEM-half release collects all eight epilogue warps of the pair
+// in the leader.  Everything behind the accumulator (statistics exchange over DSMEM, epilogue, I/O streams) is per CTA as before.
+template <int BN, int GSZ, bool PAIR>
 __global__ void __launch_bounds__(kGnThreads, 1)
 gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ CUtensorMap tmOw, const GemmGnParams p) {
   using namespace sm100;
   constexpr int G = BN / GSZ;                 // groups in the channel block
-  static_assert(G >= 1 && G <= 32 && BN % 32 == 0 && BN <= 128, "unsupported block / group shape");
-  constexpr uint32_t kABytes = 128 * 64 * 2, kBBytes = BN * 64 * 2;
+  static_assert(G >= 1 && G <= 32 && BN % 32 == 0 && BN <= 256 && (BN <= 128 || PAIR), "unsupported block / group shape");
+  constexpr uint32_t kABytes = 128 * 64 * 2, kBBytes = (PAIR ? BN / 2 : BN) * 64 * 2;   // PAIR: this CTA's half of the B block
+  constexpr int kCoef = BN > 128 ? BN : 128;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic ST/LD)
@@ -102,8 +109,8 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   double* s_warp_part = reinterpret_cast<double*>(sOut + p.box_bytes);     // [2 groups][4 warps][32 groups][2]
   double* s_parts = s_warp_part + 2 * 4 * 32 * 2;                          // [2 groups][8 ranks][32 groups][2]
   float* s_mr = reinterpret_cast<float*>(s_parts + 2 * kGnMaxCluster * 32 * 2);   // [2 groups][32][2] mean, rstd
-  float* s_coef = s_mr + 2 * 64;                                           // [2 groups][a_c[128] | b_c[128]]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_coef + 2 * 256);
+  float* s_coef = s_mr + 2 * 64;                                           // [2 groups][a_c[kCoef] | b_c[kCoef]]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_coef + 2 * 2 * kCoef);
   uint64_t* full_bar = bars;                                               // [stages]
   uint64_t* empty_bar = bars + kGnMaxStages;
   uint64_t* tile_full = bars + 2 * kGnMaxStages;                           // [2 halves][kGnMaxTpc]
@@ -127,11 +134,14 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int t = 0; t < 2 * kGnMaxTpc; ++t) mbar_init(&tile_full[t], 1);
-    for (int h = 0; h < 2; ++h) { mbar_init(&half_empty[h], 4); mbar_init(&parts_full[h], CS * G); }
+    for (int h = 0; h < 2; ++h) { mbar_init(&half_empty[h], PAIR ? 8 : 4); mbar_init(&parts_full[h], CS * G); }
     for (int h = 0; h < 8; ++h) { mbar_init(&res_full[h], 1); mbar_init(&box_ready[h], 128); }
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_base_ptr, 512); tmem_relinquish(); }
+  if (warp == 2) {
+    if (PAIR) { tmem_alloc_pair(tmem_base_ptr, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_base_ptr, 512); tmem_relinquish(); }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -163,20 +173,33 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!p.b_shared || i == 0) {
               mbar_wait(&b_empty[sb], bphase ^ 1);
               uint8_t* sB = sBring + (size_t)sb * b_slot;
-              mbar_arrive_expect_tx(&b_full[sb], np * kBBytes);
-              for (int pl = 0; pl < np; ++pl) tma_load_3d(sB + pl * kBBytes, &tmB, &b_full[sb], kb * 64, nb * BN, pl);
+              if (PAIR) {
+                if (crank == 0) mbar_arrive_expect_tx(&b_full[sb], 2 * np * kBBytes);
+                const uint32_t lead = map_to_cta(smem_u32(&b_full[sb]), 0);
+                for (int pl = 0; pl < np; ++pl)
+                  tma_load_3d_pair(sB + pl * kBBytes, &tmB, lead, kb * 64, nb * BN + (int)crank * (BN / 2), pl);
+              } else {
+                mbar_arrive_expect_tx(&b_full[sb], np * kBBytes);
+                for (int pl = 0; pl < np; ++pl) tma_load_3d(sB + pl * kBBytes, &tmB, &b_full[sb], kb * 64, nb * BN, pl);
+              }
               if (++sb == p.b_stages) { sb = 0; bphase ^= 1; }
             }
             const int t = t_lo + tl;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sA = smem + (size_t)stage * a_slot;
-            mbar_arrive_expect_tx(&full_bar[stage], np * p.a_tx_bytes);
+            if (!PAIR || crank == 0) mbar_arrive_expect_tx(&full_bar[stage], (PAIR ? 2 : 1) * np * p.a_tx_bytes);
+            const uint32_t lead = PAIR ? map_to_cta(smem_u32(&full_bar[stage]), 0) : 0;
             for (int pl = 0; pl < np; ++pl) {
               if (p.conv) {
                 const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
                 const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
-                tma_load_5d(sA + pl * kABytes, &tmA, &full_bar[stage], cb * 64, w0 + tap % p.KW - p.pad_w,
-                            h0 + tap / p.KW - p.pad_h, img, pl);
+                if (PAIR)
+                  tma_load_5d_pair(sA + pl * kABytes, &tmA, lead, cb * 64, w0 + tap % p.KW - p.pad_w, h0 + tap / p.KW - p.pad_h, img, pl);
+                else
+                  tma_load_5d(sA + pl * kABytes, &tmA, &full_bar[stage], cb * 64, w0 + tap % p.KW - p.pad_w,
+                              h0 + tap / p.KW - p.pad_h, img, pl);
+              } else if (PAIR) {
+                tma_load_3d_pair(sA + pl * kABytes, &tmA, lead, kb * 64, img * p.HW + t * 128, pl);
               } else {
                 tma_load_3d(sA + pl * kABytes, &tmA, &full_bar[stage], kb * 64, img * p.HW + t * 128, pl);
               }
@@ -188,8 +211,8 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================================================================================== MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_f16(128, BN, 0);
+    if ((!PAIR || crank == 0) && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 256 : 128, BN, 0);
       int stage = 0; uint32_t phase = 0;
       int sb = 0; uint32_t bphase = 0;
       uint32_t j = 0;
@@ -210,18 +233,28 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t da = umma_desc_k_sw128(aH + k * 32), db = umma_desc_k_sw128(bH + k * 32);
-              umma_f16(d, da, db, idesc, (kb | k) != 0);
-              if (np == 2) {
-                umma_f16(d, umma_desc_k_sw128(aH + kABytes + k * 32), db, idesc, 1);
-                umma_f16(d, da, umma_desc_k_sw128(bH + kBBytes + k * 32), idesc, 1);
+              if (PAIR) {
+                umma_f16_pair(d, da, db, idesc, (kb | k) != 0);
+                if (np == 2) {
+                  umma_f16_pair(d, umma_desc_k_sw128(aH + kABytes + k * 32), db, idesc, 1);
+                  umma_f16_pair(d, da, umma_desc_k_sw128(bH + kBBytes + k * 32), idesc, 1);
+                }
+              } else {
+                umma_f16(d, da, db, idesc, (kb | k) != 0);
+                if (np == 2) {
+                  umma_f16(d, umma_desc_k_sw128(aH + kABytes + k * 32), db, idesc, 1);
+                  umma_f16(d, da, umma_desc_k_sw128(bH + kBBytes + k * 32), idesc, 1);
+                }
               }
             }
-            umma_commit(&empty_bar[stage]);
+            if (PAIR) umma_commit_pair(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
             if (!p.b_shared || i == n_inner - 1) {
-              umma_commit(&b_empty[sb]);
+              if (PAIR) umma_commit_pair(&b_empty[sb], 3); else umma_commit(&b_empty[sb]);
               if (++sb == p.b_stages) { sb = 0; bphase ^= 1; }
             }
-            if (kb == p.num_k_blocks - 1) umma_commit(&tile_full[half * kGnMaxTpc + tl]);
+            if (kb == p.num_k_blocks - 1) {
+              if (PAIR) umma_commit_pair(&tile_full[half * kGnMaxTpc + tl], 3); else umma_commit(&tile_full[half * kGnMaxTpc + tl]);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -296,7 +329,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t lane_off = (uint32_t)(qw * 32) << 16;
     double* wpart = s_warp_part + grp * (4 * 32 * 2);     // [4 warps][32 groups][2]
     float* mr = s_mr + grp * 64;
-    float* coef = s_coef + grp * 256;
+    float* coef = s_coef + grp * 2 * kCoef;
     const int bar_a = 1 + grp * 2, bar_b = 2 + grp * 2;
     const uint32_t t_half = tmem_base + grp * 256 + lane_off;
     uint32_t jj = 0;                           // per-group item counter
@@ -390,12 +423,12 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (dbg_on) p.dbg[jj * 8 + 3] = clock64();
       named_bar(bar_b, 128);
-      if (gt < BN) {                           // y = v * a_c + b_c
-        const int c = gt, g = c / GSZ;
+      for (int c = gt; c < BN; c += 128) {     // y = v * a_c + b_c
+        const int g = c / GSZ;
         const float ga = __ldg(p.gamma + nb * BN + c), be = __ldg(p.beta + nb * BN + c);
         const float a = mr[g * 2 + 1] * ga;
         coef[c] = a;
-        coef[128 + c] = be - mr[g * 2] * a;
+        coef[kCoef + c] = be - mr[g * 2] * a;
       }
       named_bar(bar_a, 128);
       // ------------------------------------------- pass 2: normalise, shortcut, ReLU, split -> smem boxes -> TMA stores
@@ -427,7 +460,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 a4 = *reinterpret_cast<const float4*>(ca + i);
-          const float4 b4 = *reinterpret_cast<const float4*>(ca + 128 + i);
+          const float4 b4 = *reinterpret_cast<const float4*>(ca + kCoef + i);
           v[i] = __uint_as_float(r[i]) * a4.x + b4.x;
           v[i + 1] = __uint_as_float(r[i + 1]) * a4.y + b4.y;
           v[i + 2] = __uint_as_float(r[i + 2]) * a4.z + b4.z;
@@ -476,25 +509,30 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (dbg_on) p.dbg[jj * 8 + 5] = clock64();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&half_empty[grp]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(map_to_cta(smem_u32(&half_empty[grp]), 0));     // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(&half_empty[grp]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <int BN, int GSZ>
+template <int BN, int GSZ, bool PAIR = false>
 static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
                      const CUtensorMap& tmOw, GemmGnParams& p, cudaStream_t st) {
   const int np = p.nsplit == 3 ? 2 : 1;
-  const size_t a_slot = (size_t)np * 128 * 64 * 2, b_slot = (size_t)np * BN * 64 * 2;
+  const size_t a_slot = (size_t)np * 128 * 64 * 2, b_slot = (size_t)np * (PAIR ? BN / 2 : BN) * 64 * 2;
   p.res_slots = p.res ? ResSlots<BN>::value : 2;
   p.box_bytes = 2 * p.res_slots * 16384;
-  const size_t fixed = 1024 + p.box_bytes + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 512) * 4 +
+  const size_t fixed = 1024 + p.box_bytes + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 4 * (BN > 128 ? BN : 128)) * 4 +
                        (4 * kGnMaxStages + 2 * kGnMaxTpc + 20) * 8 + 64;
   // shared B blocks turn over once per K block: two slots; otherwise the B ring is as deep as the A ring (one B per A tile)
   int stages = p.b_shared ? (int)((232448 - fixed - 2 * b_slot) / a_slot) : (int)((232448 - fixed) / (a_slot + b_slot));
@@ -505,7 +543,7 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   const size_t smem = fixed + (size_t)stages * a_slot + (size_t)p.b_stages * b_slot;
   static bool attr_set = false;
   if (!attr_set) {
-    MAED_CUDA_CHECK(cudaFuncSetAttribute(gemm_gn_kernel<BN, GSZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    MAED_CUDA_CHECK(cudaFuncSetAttribute(gemm_gn_kernel<BN, GSZ, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -524,14 +562,14 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   if (!max_clusters[p.cluster]) {
     cfg.gridDim = dim3(sm_count() / p.cluster * p.cluster);
     int n = 0;
-    MAED_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, gemm_gn_kernel<BN, GSZ>, &cfg));
+    MAED_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, gemm_gn_kernel<BN, GSZ, PAIR>, &cfg));
     if (n < 1) { set_error("gemm_gn: cluster of %d CTAs cannot be scheduled", p.cluster); return MAED_ERR_UNSUPPORTED; }
     max_clusters[p.cluster] = n;
   }
   int n_clusters = max_clusters[p.cluster];
   if (n_clusters > p.items) n_clusters = p.items;
   cfg.gridDim = dim3(n_clusters * p.cluster);
-  MAED_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_gn_kernel<BN, GSZ>, tmA, tmB, tmO, tmR, tmOw, p));
+  MAED_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_gn_kernel<BN, GSZ, PAIR>, tmA, tmB, tmO, tmR, tmOw, p));
   count_launch();
   return MAED_OK;
 }
@@ -566,7 +604,12 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   // channel-block width, tiles per CTA and cluster size: an image's tiles x BN columns must fit half of the TMEM
   // (256 columns) of the CTAs of one cluster
   int bn, cluster, tpc;
-  if (a.res) {
+  bool pair = false;
+  // 14 x 14 maps (exactly two M tiles per image): the two CTAs of a cluster work as a cta_group::2 pair on 256-wide blocks
+  // (MAED_B200_GN_PAIR=0: the single-CTA plans below)
+  static const bool pair_on = !(getenv("MAED_B200_GN_PAIR") && atoi(getenv("MAED_B200_GN_PAIR")) == 0);
+  if (pair_on && p.tiles_per_image == 2 && a.C % 256 == 0 && (gsz == 8 || gsz == 32)) { bn = 256; tpc = 1; cluster = 2; pair = true; }
+  else if (a.res) {
     // shortcut layers are epilogue-bound: 64-wide blocks leave shared memory for 3 shortcut slots (2 TMA loads in flight)
     // ... except with at most 2 tiles per image (stage 2: 14 x 14): there the L2 -> SM port is the bound and a 128-wide
     // block halves the number of times the image's A tiles are fetched (MAED_B200_GN_RES_BN128=0: the 64-wide plan)
@@ -607,7 +650,7 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   {
     const uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)a.C, (uint64_t)np};
     const uint64_t str[2] = {(uint64_t)p.K * 2, (uint64_t)(np == 2 ? a.b_plane : (long long)a.C * p.K) * 2};
-    const uint32_t box[3] = {64, (uint32_t)bn, 1};
+    const uint32_t box[3] = {64, (uint32_t)(pair ? bn / 2 : bn), 1};      // a pair CTA stages its half of the block
     MAED_PROPAGATE(make_tmap_f16(&tmB, a.B, 3, dims, str, box));
   }
   // output planes [n_img, HW (or H, W), C] x 2 planes; 64-channel x one-tile boxes, 128-byte swizzle
@@ -636,6 +679,8 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
     }
   }
   if (!a.res) tmR = tmO;
+  if (pair && gsz == 8) return launch_gn<256, 8, true>(tmA, tmB, tmO, tmR, tmOw, p, st);
+  if (pair && gsz == 32) return launch_gn<256, 32, true>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 128 && gsz == 4) return launch_gn<128, 4>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 128 && gsz == 8) return launch_gn<128, 8>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 128 && gsz == 16) return launch_gn<128, 16>(tmA, tmB, tmO, tmR, tmOw, p, st);
