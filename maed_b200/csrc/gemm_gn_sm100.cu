@@ -170,25 +170,27 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int o = 0; o < n_outer; ++o) {
           for (int i = 0; i < n_inner; ++i) {
             const int kb = p.b_shared ? o : i, tl = p.b_shared ? i : o;
-            if (!p.b_shared || i == 0) {
+            if (p.b_shared && i == 0) {                    // shared B block: its own ring and barriers (never with PAIR)
               mbar_wait(&b_empty[sb], bphase ^ 1);
               uint8_t* sB = sBring + (size_t)sb * b_slot;
-              if (PAIR) {
-                if (crank == 0) mbar_arrive_expect_tx(&b_full[sb], 2 * np * kBBytes);
-                const uint32_t lead = map_to_cta(smem_u32(&b_full[sb]), 0);
-                for (int pl = 0; pl < np; ++pl)
-                  tma_load_3d_pair(sB + pl * kBBytes, &tmB, lead, kb * 64, nb * BN + (int)crank * (BN / 2), pl);
-              } else {
-                mbar_arrive_expect_tx(&b_full[sb], np * kBBytes);
-                for (int pl = 0; pl < np; ++pl) tma_load_3d(sB + pl * kBBytes, &tmB, &b_full[sb], kb * 64, nb * BN, pl);
-              }
+              mbar_arrive_expect_tx(&b_full[sb], np * kBBytes);
+              for (int pl = 0; pl < np; ++pl) tma_load_3d(sB + pl * kBBytes, &tmB, &b_full[sb], kb * 64, nb * BN, pl);
               if (++sb == p.b_stages) { sb = 0; bphase ^= 1; }
             }
             const int t = t_lo + tl;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sA = smem + (size_t)stage * a_slot;
-            if (!PAIR || crank == 0) mbar_arrive_expect_tx(&full_bar[stage], (PAIR ? 2 : 1) * np * p.a_tx_bytes);
+            // otherwise B slot `stage` travels with A slot `stage` under the same pair of barriers
+            const uint32_t tx = np * (p.a_tx_bytes + (p.b_shared ? 0u : kBBytes));
+            if (!PAIR || crank == 0) mbar_arrive_expect_tx(&full_bar[stage], (PAIR ? 2 : 1) * tx);
             const uint32_t lead = PAIR ? map_to_cta(smem_u32(&full_bar[stage]), 0) : 0;
+            if (!p.b_shared) {
+              uint8_t* sB = sBring + (size_t)stage * b_slot;
+              for (int pl = 0; pl < np; ++pl) {
+                if (PAIR) tma_load_3d_pair(sB + pl * kBBytes, &tmB, lead, kb * 64, nb * BN + (int)crank * (BN / 2), pl);
+                else tma_load_3d(sB + pl * kBBytes, &tmB, &full_bar[stage], kb * 64, nb * BN, pl);
+              }
+            }
             for (int pl = 0; pl < np; ++pl) {
               if (p.conv) {
                 const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
@@ -225,11 +227,11 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < n_inner; ++i) {
             const int kb = p.b_shared ? o : i, tl = p.b_shared ? i : o;
             const uint32_t d = tmem_base + half * 256 + tl * BN;
-            if (!p.b_shared || i == 0) mbar_wait(&b_full[sb], bphase);
+            if (p.b_shared && i == 0) mbar_wait(&b_full[sb], bphase);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t aH = smem_u32(smem + (size_t)stage * a_slot);
-            const uint32_t bH = smem_u32(sBring + (size_t)sb * b_slot);
+            const uint32_t bH = smem_u32(sBring + (size_t)(p.b_shared ? sb : stage) * b_slot);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t da = umma_desc_k_sw128(aH + k * 32), db = umma_desc_k_sw128(bH + k * 32);
@@ -248,8 +250,8 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             if (PAIR) umma_commit_pair(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
-            if (!p.b_shared || i == n_inner - 1) {
-              if (PAIR) umma_commit_pair(&b_empty[sb], 3); else umma_commit(&b_empty[sb]);
+            if (p.b_shared && i == n_inner - 1) {
+              umma_commit(&b_empty[sb]);
               if (++sb == p.b_stages) { sb = 0; bphase ^= 1; }
             }
             if (kb == p.num_k_blocks - 1) {
@@ -608,7 +610,9 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   // 14 x 14 maps (exactly two M tiles per image): the two CTAs of a cluster work as a cta_group::2 pair on 256-wide blocks
   // (MAED_B200_GN_PAIR=0: the single-CTA plans below)
   static const bool pair_on = !(getenv("MAED_B200_GN_PAIR") && atoi(getenv("MAED_B200_GN_PAIR")) == 0);
-  if (pair_on && p.tiles_per_image == 2 && a.C % 256 == 0 && (gsz == 8 || gsz == 32)) { bn = 256; tpc = 1; cluster = 2; pair = true; }
+  // measured: 3x3 126 -> 103 us (tensor pipe 53 -> 66 %), 1x1 63 -> 58 us; the 1024-channel shortcut layers are epilogue-bound
+  // and lose with 256-wide blocks (97 -> 108 us), so they keep the single-CTA plan
+  if (pair_on && p.tiles_per_image == 2 && !a.res && a.C % 256 == 0 && gsz == 8) { bn = 256; tpc = 1; cluster = 2; pair = true; }
   else if (a.res) {
     // shortcut layers are epilogue-bound: 64-wide blocks leave shared memory for 3 shortcut slots (2 TMA loads in flight)
     // ... except with at most 2 tiles per image (stage 2: 14 x 14): there the L2 -> SM port is the bound and a 128-wide
@@ -632,7 +636,7 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   // the L2 -> SM port everywhere, but faster only with 2 tiles per CTA (stage 1/2: -3 .. -8 %); with 4 tiles per CTA all tiles
   // of an item finish together and the epilogue loses its head start (stage 0: +4 .. +12 %)
   static const bool b_shared = !(getenv("MAED_B200_GN_BSHARED") && atoi(getenv("MAED_B200_GN_BSHARED")) == 0);
-  p.b_shared = (b_shared && tpc <= 2) ? 1 : 0;
+  p.b_shared = (b_shared && tpc == 2 && !pair) ? 1 : 0;
   p.n_blocks = a.C / bn;
   p.items = a.n_img * p.n_blocks;
   if (a.conv) {
@@ -680,7 +684,6 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   }
   if (!a.res) tmR = tmO;
   if (pair && gsz == 8) return launch_gn<256, 8, true>(tmA, tmB, tmO, tmR, tmOw, p, st);
-  if (pair && gsz == 32) return launch_gn<256, 32, true>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 128 && gsz == 4) return launch_gn<128, 4>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 128 && gsz == 8) return launch_gn<128, 8>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 128 && gsz == 16) return launch_gn<128, 16>(tmA, tmB, tmO, tmR, tmOw, p, st);
