@@ -153,6 +153,13 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       int sb = 0; uint32_t bphase = 0;
+      // this one thread must hand out a stage every few hundred cycles (384 tensor cycles per stage on the 64-wide blocks): no
+      // integer divisions inside the loop — tile origins once per kernel, the K block -> (tap row, tap column, channel block)
+      // decomposition by counting
+      const int h00 = p.conv ? (t_lo / p.tiles_w) * p.tile_h : 0, w00 = p.conv ? (t_lo % p.tiles_w) * p.tile_w : 0;
+      const int wlim = p.tiles_w * p.tile_w;
+      int h0 = h00, w0 = w00;
+      int cb = 0, tr = 0, ts = 0;
       for (int item = cluster_id; item < p.items; item += n_clusters) {
         const int img = item / p.n_blocks, nb = item % p.n_blocks;
         if (p.res) {
@@ -170,6 +177,14 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int o = 0; o < n_outer; ++o) {
           for (int i = 0; i < n_inner; ++i) {
             const int kb = p.b_shared ? o : i, tl = p.b_shared ? i : o;
+            if (!p.b_shared || i == 0) {                   // a new K block
+              if (kb == 0) { cb = 0; tr = 0; ts = 0; }
+              else if (++cb == p.cin_blocks) { cb = 0; if (++ts == p.KW) { ts = 0; ++tr; } }
+            }
+            if (p.b_shared || i == 0) {                    // a new tile (row-major over the image)
+              if (tl == 0) { h0 = h00; w0 = w00; }
+              else { w0 += p.tile_w; if (w0 >= wlim) { w0 = 0; h0 += p.tile_h; } }
+            }
             if (p.b_shared && i == 0) {                    // shared B block: its own ring and barriers (never with PAIR)
               mbar_wait(&b_empty[sb], bphase ^ 1);
               uint8_t* sB = sBring + (size_t)sb * b_slot;
@@ -193,13 +208,11 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             for (int pl = 0; pl < np; ++pl) {
               if (p.conv) {
-                const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
-                const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
                 if (PAIR)
-                  tma_load_5d_pair(sA + pl * kABytes, &tmA, lead, cb * 64, w0 + tap % p.KW - p.pad_w, h0 + tap / p.KW - p.pad_h, img, pl);
+                  tma_load_5d_pair(sA + pl * kABytes, &tmA, lead, cb * 64, w0 + ts - p.pad_w, h0 + tr - p.pad_h, img, pl);
                 else
-                  tma_load_5d(sA + pl * kABytes, &tmA, &full_bar[stage], cb * 64, w0 + tap % p.KW - p.pad_w,
-                              h0 + tap / p.KW - p.pad_h, img, pl);
+                  tma_load_5d(sA + pl * kABytes, &tmA, &full_bar[stage], cb * 64, w0 + ts - p.pad_w, h0 + tr - p.pad_h,
+                              img, pl);
               } else if (PAIR) {
                 tma_load_3d_pair(sA + pl * kABytes, &tmA, lead, kb * 64, img * p.HW + t * 128, pl);
               } else {
