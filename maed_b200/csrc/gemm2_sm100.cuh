@@ -119,6 +119,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           h0 = th * p.tile_h;
           w0 = tw * p.tile_w;
         }
+        int cb = 0, r = 0, s = 0;                                   // K block -> (tap row, tap column, channel block) by counting
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
@@ -127,14 +128,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t leader_full = map_to_cta(smem_u32(&full_bar[stage]), 0);
           for (int pl = 0; pl < nplanes; ++pl) {
             if (p.conv) {
-              const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
-              const int r = tap / p.KW, s = tap % p.KW;
               tma_load_5d_pair(sA + pl * kABytes, &tmA, leader_full, cb * kBlockK, w0 + s - p.pad_w, h0 + r - p.pad_h, img, pl);
             } else {
               tma_load_3d_pair(sA + pl * kABytes, &tmA, leader_full, kb * kBlockK, row0, pl);
             }
             tma_load_3d_pair(sB + pl * kBBytes, &tmB, leader_full, kb * kBlockK, col0, pl);
           }
+          if (++cb == p.cin_blocks) { cb = 0; if (++s == p.KW) { s = 0; ++r; } }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }

@@ -180,6 +180,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           h0 = th * p.tile_h;
           w0 = tw * p.tile_w;
         }
+        // K block -> (tap row r, tap column s, channel block cb) by counting: this one thread feeds a stage every 384 tensor
+        // cycles on the 64-wide tiles, integer divisions per stage would make it the bottleneck (measured in gemm_gn_sm100.cu)
+        int cb = 0, r = 0, s = 0;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
@@ -187,8 +190,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_arrive_expect_tx(&full_bar[stage], nplanes * (p.a_tx_bytes + kBBytes));
           for (int pl = 0; pl < nplanes; ++pl) {
             if (p.conv) {
-              const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
-              const int r = tap / p.KW, s = tap % p.KW;
               tma_load_5d(sA + pl * kABytes, &tmA, &full_bar[stage], cb * kBlockK, w0 + s - p.pad_w,
                           h0 + r - p.pad_h, img, pl);
             } else {
@@ -196,6 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tma_load_3d(sB + pl * kBBytes, &tmB, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N, pl);
           }
+          if (++cb == p.cin_blocks) { cb = 0; if (++s == p.KW) { s = 0; ++r; } }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }

@@ -83,6 +83,21 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int m_tile = mn / p.n_tiles, n_tile = mn % p.n_tiles;
         const int kb0 = slice * p.kb_per_slice;
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_slice);
+        // conv mode: everything that needs an integer division is formed once per tile — the tap / channel offset of each
+        // 64-column block of the weight row, and the first patch of the slice; later patches follow by counting (this thread
+        // must hand out a stage every few hundred tensor cycles)
+        int b_cin0[BLOCK_N / 64], b_dw[BLOCK_N / 64], b_dh[BLOCK_N / 64];
+        int img = 0, ph = 0, pw = 0;
+        if (MN && p.conv) {
+#pragma unroll
+          for (int nb = 0; nb < BLOCK_N / 64; ++nb) {
+            const int col = n_tile * BLOCK_N + nb * 64;
+            const int tap = col / p.Cin;
+            b_cin0[nb] = col % p.Cin; b_dw[nb] = tap % p.KW - p.pad; b_dh[nb] = tap / p.KW - p.pad;
+          }
+          const int rem = kb0 % p.patches;
+          img = kb0 / p.patches; ph = rem / p.tiles_w; pw = rem % p.tiles_w;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
@@ -92,17 +107,13 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (MN && p.conv) {
               // implicit im2col: dY patch {64 channels, tile_w, tile_h} and, per 64-column block of the [kh][kw][Cin] weight
               // row, the SAME patch of x shifted by the tap (TMA zero-fills the padding and ragged patch borders)
-              const int img = kb / p.patches, rem = kb % p.patches;
-              const int h0 = (rem / p.tiles_w) * p.tile_h, w0 = (rem % p.tiles_w) * p.tile_w;
+              const int h0 = ph * p.tile_h, w0 = pw * p.tile_w;
 #pragma unroll
               for (int mb = 0; mb < kBM / 64; ++mb)
                 tma_load_5d(sA + pl * kABytes + mb * 8192, &tmA, &full_bar[stage], m_tile * kBM + mb * 64, w0, h0, img, pl);
 #pragma unroll
               for (int nb = 0; nb < BLOCK_N / 64; ++nb) {
-                const int col = n_tile * BLOCK_N + nb * 64;
-                const int tap = col / p.Cin, cin0 = col % p.Cin;
-                tma_load_5d(sB + pl * kBBytes + nb * 8192, &tmB, &full_bar[stage], cin0, w0 + tap % p.KW - p.pad,
-                            h0 + tap / p.KW - p.pad, img, pl);
+                tma_load_5d(sB + pl * kBBytes + nb * 8192, &tmB, &full_bar[stage], b_cin0[nb], w0 + b_dw[nb], h0 + b_dh[nb], img, pl);
               }
             } else if (MN) {       // [64-wide MN block][64 rows of r][128 B]: 8 KB per block, the layout umma_desc_mn_sw128 describes
 #pragma unroll
@@ -115,6 +126,9 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               tma_load_3d(sA + pl * kABytes, &tmA, &full_bar[stage], kb * kBK, m_tile * kBM, pl);
               tma_load_3d(sB + pl * kBBytes, &tmB, &full_bar[stage], kb * kBK, n_tile * BLOCK_N, pl);
             }
+          }
+          if (MN && p.conv) {                              // next patch of the image, row-major; then the next image
+            if (++pw == p.tiles_w) { pw = 0; if (++ph * p.tiles_w >= p.patches) { ph = 0; ++img; } }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
