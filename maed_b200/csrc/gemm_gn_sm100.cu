@@ -405,23 +405,31 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (dbg_on) p.dbg[jj * 8 + 1] = clock64();
       named_bar(bar_a, 128);
       if (dbg_on) p.dbg[jj * 8 + 2] = clock64();
-      // ---- CTA partial of group g (thread g), pushed to every CTA of the cluster (including this one)
+      // ---- CTA partial of every group, pushed to every CTA of the cluster (including this one).  One thread per (group, peer):
+      // a remote release-arrive costs ~1.2 k cycles and a thread's arrives serialise — with one thread per group walking the 8
+      // peers the exchange took 10-13 k cycles per item (in-kernel timeline, round 2), i.e. a third of the item period.
+      if (CS > 1) {
+        const uint32_t lb = smem_u32(&parts_full[grp]);
+        for (int idx = gt; idx < G * CS; idx += 128) {
+          const int g = idx % G, r = idx / G;
+          double sv = 0.0, qv = 0.0;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) { sv += wpart[(w4 * 32 + g) * 2]; qv += wpart[(w4 * 32 + g) * 2 + 1]; }
+          const uint32_t ra = mapa_u32(smem_u32(s_parts + ((grp * kGnMaxCluster + crank) * 32 + g) * 2), r);
+          st_dsmem_f64(ra, sv);
+          st_dsmem_f64(ra + 8, qv);
+          mbar_arrive_remote(mapa_u32(lb, r));
+        }
+      }
       if (gt < G) {
         const int g = gt;
         double sv = 0.0, qv = 0.0;
-#pragma unroll
-        for (int w4 = 0; w4 < 4; ++w4) { sv += wpart[(w4 * 32 + g) * 2]; qv += wpart[(w4 * 32 + g) * 2 + 1]; }
-        double* slot = s_parts + ((grp * kGnMaxCluster + crank) * 32 + g) * 2;
         if (CS > 1) {
-          const uint32_t la = smem_u32(slot), lb = smem_u32(&parts_full[grp]);
-          for (int r = 0; r < CS; ++r) {
-            const uint32_t ra = mapa_u32(la, r);
-            st_dsmem_f64(ra, sv);
-            st_dsmem_f64(ra + 8, qv);
-            mbar_arrive_remote(mapa_u32(lb, r));
-          }
           mbar_wait_cluster(&parts_full[grp], hphase);
         } else {
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) { sv += wpart[(w4 * 32 + g) * 2]; qv += wpart[(w4 * 32 + g) * 2 + 1]; }
+          double* slot = s_parts + ((grp * kGnMaxCluster + crank) * 32 + g) * 2;
           slot[0] = sv; slot[1] = qv;
         }
         sv = 0.0; qv = 0.0;
