@@ -13,9 +13,9 @@
 //     pass 1   per-group sum / sum of squares of the valid rows (as soon as a tile's MMAs retire)
 //     reduce   warp shuffles -> smem (CTA) -> every CTA pushes its partials into all peers' shared memory (DSMEM stores
 //              + remote mbarrier arrive); no cluster-wide barrier, so producers never stall on the epilogue
-//     pass 2   TMEM -> v*a_c + b_c (folded mean/rstd/gamma/beta) (+ shortcut, read from its input slot) -> ReLU -> fp16
-//              hi/lo written into an output slot (64-byte-swizzled half-box) -> mbarrier arrive; the I/O stream stores
-//              output slots and refills input slots with TMA.  No named barrier, no per-thread global access.
+//     pass 2   TMEM -> v*a_c + b_c (folded mean/rstd/gamma/beta) (+ shortcut, read from its smem slot) -> ReLU -> fp16
+//              hi/lo written IN PLACE into the slot (64-byte-swizzled half-box) -> mbarrier arrive; the I/O stream
+//              stores the slot with TMA and refills it.  No named barrier, no per-thread global access.
 //
 // Versus the unfused pipeline (GEMM writes fp32, gn_stats reads it, gn_apply reads it again and writes planes)
 // this removes 12 of the 16 bytes of HBM traffic per conv-output element.  In-kernel timeline: scripts/dbg_gn_timeline.py.
@@ -31,6 +31,8 @@ static constexpr int kGnThreads = 384;       // warp 0 TMA, 1 MMA, 2 TMEM alloc,
 static constexpr int kGnMaxTpc = 4;
 static constexpr int kGnMaxStages = 4;
 static constexpr int kGnMaxCluster = 8;
+// shortcut prefetch slots of the epilogue (iterations in flight + 1): 3 when shared memory allows (BN = 64), else 2
+template <int BN> struct ResSlots { static constexpr int value = (BN <= 64) ? 3 : 2; };
 
 struct GemmGnParams {
   int HW, C, K, num_k_blocks, nsplit, stages;   // stages: depth of the A ring
@@ -38,8 +40,8 @@ struct GemmGnParams {
   int tiles_per_image, tpc, n_blocks, cluster, items;
   uint32_t a_tx_bytes;
   uint32_t o_tx_bytes;         // bytes of one 32-channel half-box plane (rows x 64 B)
-  uint32_t box_bytes;          // staging bytes after the pipeline stages: 2 groups x (in_slots + out_slots) x 16 KB
-  int in_slots, out_slots;     // shortcut (input) and result (output) half-box slots per epilogue group
+  uint32_t box_bytes;          // staging bytes after the pipeline stages: 2 groups x res_slots x 16 KB
+  int res_slots;               // staging half-box slots per epilogue group (2 or 3)
   int conv, H, W, cin_blocks, KW, pad_h, pad_w, tile_h, tile_w, tiles_h, tiles_w;
   const float* gamma; const float* beta; float eps; int relu;
   const __half* res; long long res_plane;
@@ -96,11 +98,12 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int np = p.nsplit == 3 ? 2 : 1;
   // operand rings: A slots [stages][np][128 x 64] then B slots [b_stages][np][BN x 64].  They are separate because a B
   // block (a K slice of the weights) is the same for every M tile of the item: with b_shared the loops run K-block-outer /
-  // tile-inner and each B block is fetched (and written into shared memory) once per item instead of once per tile.
+  // tile-inner and each B block crosses the L2 -> SM port once per item instead of once per tile.  These kernels are bound
+  // by that port (A + B bytes per MMA cycle), not by the tensor pipe.
   const uint32_t a_slot = np * kABytes, b_slot = np * kBBytes;
   uint8_t* sBring = smem + (size_t)p.stages * a_slot;
-  // staging after the pipeline stages: [2 groups][in_slots + out_slots][hi | lo][128 rows x 64 B] half-boxes (input slots:
-  // the shortcut lands here by TMA; output slots: results, stored by TMA)
+  // staging after the pipeline stages.  Shortcut layers: [2 groups][kResSlots][hi | lo][128 rows x 64 B] half-boxes (the
+  // shortcut lands here by TMA, is updated IN PLACE and stored by TMA); other layers: [2 groups][hi | lo][128 x 128 B] boxes.
   uint8_t* sOut = sBring + (size_t)p.b_stages * b_slot;
   uint8_t* sRes = sOut;
   double* s_warp_part = reinterpret_cast<double*>(sOut + p.box_bytes);     // [2 groups][4 warps][32 groups][2]
@@ -275,48 +278,43 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 2 || warp == 3) {
     // ============================================================ epilogue I/O streams (one thread per epilogue group)
     // All global traffic of pass 2 is bulk + asynchronous and issued from here, so the epilogue warps never block on a
-    // named barrier.  Input (shortcut) and output staging are SEPARATE slots since round 2: with in-place slots a slot could
-    // only be refilled after its store had read it, so the TMA load latency (~1.8 k cycles) sat in every iteration (2 slots:
-    // 2.8 k cycles per 32-column iteration, 3 slots: 1.5 k; in-kernel timeline).  Now
-    //   in slot :  TMA load -> in_full -> epilogue reads it -> in_free (128 arrivals) -> refilled for iteration it + NI
-    //   out slot:  out_free -> epilogue writes the result -> out_ready (128 arrivals) -> TMA store -> store has read it -> out_free
+    // named barrier: they wait for a slot (res_full), update it in place and signal box_ready.
+    //   slot life cycle:  [TMA load of the shortcut half-box | plain arrive]  -> res_full -> epilogue -> box_ready
+    //                     -> TMA store -> (store has read the slot) -> refill
     if (elect_one()) {
       const int grp = warp - 2;
-      const int NI = p.in_slots, NO = p.out_slots;
+      const int RS = p.res_slots;
       constexpr int NCH = BN / 32;
-      uint8_t* ibase = sRes + (size_t)grp * ((NI + NO) * 16384);
-      const uint8_t* obase = ibase + NI * 16384;
-      uint64_t* in_full = res_full + grp * 4;               // [2], count 1 (+ tx bytes)
-      uint64_t* out_free = res_full + grp * 4 + 2;          // [2], count 1
-      uint64_t* out_ready = box_ready + grp * 4;            // [2], count 128
-      uint64_t* in_free = box_ready + grp * 4 + 2;          // [2], count 128
-      uint32_t n_fill = 0, n_store = 0;                     // running counters of this stream (slot = n % N, parity = (n / N) & 1)
+      uint8_t* rbase = sRes + (size_t)grp * (RS * 16384);
+      uint64_t* rfull = res_full + grp * 4;
+      uint64_t* bready = box_ready + grp * 4;
+      uint32_t n_fill = 0, n_store = 0;                   // running slot counters of this stream
       for (int item = cluster_id + grp * n_clusters; item < p.items; item += 2 * n_clusters) {
         const int img = item / p.n_blocks, nb = item % p.n_blocks;
         const int n_it = my_tiles * NCH;
-        auto fill = [&](int it) {                           // shortcut half-box of iteration `it` -> in slot n_fill % NI
-          const uint32_t slot = n_fill % NI;
-          if (n_fill >= (uint32_t)NI) mbar_wait(&in_free[slot], ((n_fill / NI) - 1) & 1);   // its previous content has been read
-          const int tl = it / NCH, c0 = (it % NCH) * 32, t = t_lo + tl;
-          uint8_t* dst = ibase + slot * 16384;
-          mbar_arrive_expect_tx(&in_full[slot], 2 * p.o_tx_bytes);
-          for (int pl = 0; pl < 2; ++pl) {
-            if (p.conv) tma_load_5d(dst + pl * 8192, &tmR, &in_full[slot], nb * BN + c0, (t % p.tiles_w) * p.tile_w, (t / p.tiles_w) * p.tile_h, img, pl);
-            else tma_load_4d(dst + pl * 8192, &tmR, &in_full[slot], nb * BN + c0, t * 128, img, pl);
+        auto fill = [&](int it) {                         // make slot (n_fill % RS) usable for iteration `it`
+          const uint32_t slot = n_fill % RS;
+          if (p.res) {
+            const int tl = it / NCH, c0 = (it % NCH) * 32, t = t_lo + tl;
+            uint8_t* dst = rbase + slot * 16384;
+            mbar_arrive_expect_tx(&rfull[slot], 2 * p.o_tx_bytes);
+            for (int pl = 0; pl < 2; ++pl) {
+              if (p.conv) tma_load_5d(dst + pl * 8192, &tmR, &rfull[slot], nb * BN + c0, (t % p.tiles_w) * p.tile_w, (t / p.tiles_w) * p.tile_h, img, pl);
+              else tma_load_4d(dst + pl * 8192, &tmR, &rfull[slot], nb * BN + c0, t * 128, img, pl);
+            }
+          } else {
+            mbar_arrive(&rfull[slot]);
           }
           ++n_fill;
         };
-        if (NI) for (int i = 0; i < NI && i < n_it; ++i) fill(i);
+        tma_store_wait_read<0>();                         // every slot of the previous item has been stored
+        for (int i = 0; i < RS - 1 && i < n_it; ++i) fill(i);
         for (int it = 0; it < n_it; ++it) {
-          if (NI && it + NI < n_it) fill(it + NI);          // returns once iteration `it` has consumed its input slot
-          if (NO == 1 && n_store >= 1) {                    // single output slot: release it when the previous store has read it
-            tma_store_wait_read<0>();
-            mbar_arrive(&out_free[0]);
-          }
-          const uint32_t slot = n_store % NO;
-          mbar_wait(&out_ready[slot], (n_store / NO) & 1);
+          const uint32_t slot = n_store % RS;
+          mbar_wait(&bready[slot], (n_store / RS) & 1);
+          ++n_store;
           const int tl = it / NCH, c0 = (it % NCH) * 32, t = t_lo + tl, ch = nb * BN + c0;
-          const uint8_t* sb = obase + slot * 16384;
+          const uint8_t* sb = rbase + slot * 16384;
           if (p.conv) {
             const int h0 = (t / p.tiles_w) * p.tile_h, w0 = (t % p.tiles_w) * p.tile_w;
             tma_store_5d(&tmO, sb, ch, w0, h0, img, 0);
@@ -326,11 +324,10 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_4d(&tmO, sb + 8192, ch, t * 128, img, 1);
           }
           tma_store_commit();
-          if (NO == 2) {                                    // two output slots: all stores but this one have read theirs
-            tma_store_wait_read<1>();
-            if (n_store >= 1) mbar_arrive(&out_free[(n_store - 1) & 1]);
+          if (it + RS - 1 < n_it) {
+            tma_store_wait_read<1>();                     // every store but the one just issued has released its slot
+            fill(it + RS - 1);
           }
-          ++n_store;
         }
       }
       tma_store_wait_all();
@@ -351,7 +348,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int bar_a = 1 + grp * 2, bar_b = 2 + grp * 2;
     const uint32_t t_half = tmem_base + grp * 256 + lane_off;
     uint32_t jj = 0;                           // per-group item counter
-    uint32_t n_in = 0, n_out = 0;              // running input / output slot counters of this group (slot = n % N, parity = (n / N) & 1)
+    uint32_t res_use = 0;                      // running slot counter of this group (slot = n % RS, parity = (n / RS) & 1)
     for (int item = cluster_id + grp * n_clusters; item < p.items; item += 2 * n_clusters, ++jj) {
       const int img = item / p.n_blocks, nb = item % p.n_blocks;
       const uint32_t hphase = jj & 1;
@@ -464,20 +461,16 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // 32-column chunk is loaded while the current one is processed.
       if (dbg_on) p.dbg[jj * 8 + 4] = clock64();
       // Iteration = (tile, 32-channel chunk).  All global traffic of the epilogue is bulk and asynchronous:
-      //   * the shortcut half-box (128 rows x 32 channels, hi + lo plane) of iteration it + NI is fetched by TMA into an input
-      //     slot while earlier iterations compute (row-per-thread loads touched 32 cache lines per instruction and made the
-      //     LSU the bottleneck); the slot is handed back as soon as it has been read;
-      //   * results are staged in a 64-byte-swizzled half-box (an output slot) and written by TMA stores (clipped at the image
-      //     edge).
+      //   * the shortcut half-box (128 rows x 32 channels, hi + lo plane) of iteration it + kResSlots is fetched by TMA into
+      //     a shared-memory slot while earlier iterations compute (row-per-thread loads touched 32 cache lines per
+      //     instruction and made the LSU the bottleneck);
+      //   * results are staged in a 64-byte-swizzled half-box and written by TMA stores (clipped at the image edge).
       constexpr int NCH = BN / 32;
       const int n_it = my_tiles * NCH;
-      const int NI = p.in_slots, NO = p.out_slots;
-      uint8_t* ibase = sRes + (size_t)grp * ((NI + NO) * 16384);
-      uint8_t* obase = ibase + NI * 16384;
-      uint64_t* in_full = res_full + grp * 4;
-      uint64_t* out_free = res_full + grp * 4 + 2;
-      uint64_t* out_ready = box_ready + grp * 4;
-      uint64_t* in_free = box_ready + grp * 4 + 2;
+      const int RS = p.res_slots;
+      uint8_t* rbase = sRes + (size_t)grp * (RS * 16384);
+      uint64_t* rfull = res_full + grp * 4;
+      uint64_t* bready = box_ready + grp * 4;
       const uint32_t sw = (row_in_tile >> 1) & 3;                          // 64-byte swizzle: chunk ^= (row >> 1) & 3
 #pragma unroll 1
       for (int it = 0; it < n_it; ++it) {
@@ -496,11 +489,11 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           v[i + 2] = __uint_as_float(r[i + 2]) * a4.z + b4.z;
           v[i + 3] = __uint_as_float(r[i + 3]) * a4.w + b4.w;
         }
+        const uint32_t slot = res_use % RS;
+        mbar_wait(&rfull[slot], (res_use / RS) & 1);                       // slot free (and, with a shortcut, loaded)
+        ++res_use;
+        uint8_t* box = rbase + slot * 16384 + row_in_tile * 64;            // this thread's row: hi at +0, lo at +8192
         if (p.res) {
-          const uint32_t islot = n_in % NI;
-          mbar_wait(&in_full[islot], (n_in / NI) & 1);                     // the shortcut half-box has landed
-          ++n_in;
-          const uint8_t* box = ibase + islot * 16384 + row_in_tile * 64;   // this thread's row: hi at +0, lo at +8192
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 H = *reinterpret_cast<const uint4*>(box + ((q ^ sw) << 4));
@@ -514,18 +507,13 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[q * 8 + 2 * k + 1] += a.y + b.y;
             }
           }
-          mbar_arrive(&in_free[islot]);                                    // read: the I/O stream may refill it
         }
         if (p.relu) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        const uint32_t oslot = n_out % NO;
-        mbar_wait(&out_free[oslot], ((n_out / NO) & 1) ^ 1);               // its previous store has read it (first use: free)
-        ++n_out;
-        uint8_t* box = obase + oslot * 16384 + row_in_tile * 64;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 4; ++q) {                                      // in place: each thread touches only its own row
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -539,7 +527,7 @@ gemm_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           *reinterpret_cast<uint4*>(box + 8192 + ((q ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         fence_proxy_async();                                               // generic-proxy writes -> visible to the TMA store
-        mbar_arrive(&out_ready[oslot]);
+        mbar_arrive(&bready[slot]);
       }
       if (dbg_on) p.dbg[jj * 8 + 5] = clock64();
       tc_fence_before();
@@ -565,11 +553,8 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      const CUtensorMap& tmOw, GemmGnParams& p, cudaStream_t st) {
   const int np = p.nsplit == 3 ? 2 : 1;
   const size_t a_slot = (size_t)np * 128 * 64 * 2, b_slot = (size_t)np * (PAIR ? BN / 2 : BN) * 64 * 2;
-  // shortcut layers: 2 input slots when shared memory allows (BN = 64: the load of iteration it + 2 is in flight), else 1,
-  // and one output slot; other layers: two output slots
-  p.in_slots = p.res ? (BN <= 64 ? 2 : 1) : 0;
-  p.out_slots = p.res ? 1 : 2;
-  p.box_bytes = 2 * (p.in_slots + p.out_slots) * 16384;
+  p.res_slots = p.res ? ResSlots<BN>::value : 2;
+  p.box_bytes = 2 * p.res_slots * 16384;
   const size_t fixed = 1024 + p.box_bytes + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 4 * (BN > 128 ? BN : 128)) * 4 +
                        (4 * kGnMaxStages + 2 * kGnMaxTpc + 20) * 8 + 64;
   // shared B blocks turn over once per K block: two slots; otherwise the B ring is as deep as the A ring (one B per A tile)
