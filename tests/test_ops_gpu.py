@@ -145,7 +145,11 @@ def test_groupnorm(ops, HW, C, relu, res):
 @pytest.mark.parametrize("n,H,Cin,C,k,relu,res", [(5, 56, 64, 256, 1, True, True), (3, 56, 64, 64, 3, True, False),
                                                   (6, 28, 128, 512, 1, False, False), (4, 28, 128, 128, 3, True, False),
                                                   (9, 14, 256, 1024, 1, True, True), (7, 14, 256, 256, 3, True, False),
-                                                  (2, 56, 256, 128, 1, True, False), (40, 14, 1024, 256, 1, True, False)])
+                                                  (2, 56, 256, 128, 1, True, False), (40, 14, 1024, 256, 1, True, False),
+                                                  # many images: every cluster works through several items per epilogue group, so
+                                                  # the slot / barrier phases that carry over from item to item are exercised
+                                                  (48, 28, 128, 512, 1, True, True), (40, 14, 256, 1024, 1, True, True),
+                                                  (24, 56, 64, 256, 1, True, True), (64, 14, 256, 256, 3, True, False)])
 def test_conv_gn_fused(ops, n, H, Cin, C, k, relu, res):
     """Fused tcgen05 conv + GroupNorm (+shortcut, ReLU), incl. the 4- and 8-CTA cluster (DSMEM) variants, vs PyTorch."""
     x = _rand(n, Cin, H, H, seed=50)
