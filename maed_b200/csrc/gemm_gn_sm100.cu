@@ -31,8 +31,6 @@ static constexpr int kGnThreads = 384;       // warp 0 TMA, 1 MMA, 2 TMEM alloc,
 static constexpr int kGnMaxTpc = 4;
 static constexpr int kGnMaxStages = 4;
 static constexpr int kGnMaxCluster = 8;
-// shortcut prefetch slots of the epilogue (iterations in flight + 1): 3 when shared memory allows (BN = 64), else 2
-template <int BN> struct ResSlots { static constexpr int value = (BN <= 64) ? 3 : 2; };
 
 struct GemmGnParams {
   int HW, C, K, num_k_blocks, nsplit, stages;   // stages: depth of the A ring
@@ -553,12 +551,20 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      const CUtensorMap& tmOw, GemmGnParams& p, cudaStream_t st) {
   const int np = p.nsplit == 3 ? 2 : 1;
   const size_t a_slot = (size_t)np * 128 * 64 * 2, b_slot = (size_t)np * (PAIR ? BN / 2 : BN) * 64 * 2;
-  p.res_slots = p.res ? ResSlots<BN>::value : 2;
-  p.box_bytes = 2 * p.res_slots * 16384;
-  const size_t fixed = 1024 + p.box_bytes + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 4 * (BN > 128 ? BN : 128)) * 4 +
-                       (4 * kGnMaxStages + 2 * kGnMaxTpc + 20) * 8 + 64;
-  // shared B blocks turn over once per K block: two slots; otherwise the B ring is as deep as the A ring (one B per A tile)
-  int stages = p.b_shared ? (int)((232448 - fixed - 2 * b_slot) / a_slot) : (int)((232448 - fixed) / (a_slot + b_slot));
+  // shortcut layers: 3 staging slots per group (2 shortcut loads in flight: 1.5 k cycles per 32-column iteration instead of 2.8 k)
+  // whenever the operand rings still get two stages
+  size_t fixed = 0;
+  int stages = 0;
+  for (p.res_slots = p.res ? 3 : 2; p.res_slots >= 2; --p.res_slots) {
+    p.box_bytes = 2 * p.res_slots * 16384;
+    fixed = 1024 + p.box_bytes + (2 * 4 * 32 * 2 + 2 * kGnMaxCluster * 32 * 2) * 8 + (128 + 4 * (BN > 128 ? BN : 128)) * 4 +
+            (4 * kGnMaxStages + 2 * kGnMaxTpc + 20) * 8 + 64;
+    // shared B blocks turn over once per K block: two slots; otherwise the B ring is as deep as the A ring (one B per A tile)
+    stages = p.b_shared ? (int)(((long long)232448 - (long long)fixed - 2 * (long long)b_slot) / (long long)a_slot)
+                        : (int)(((long long)232448 - (long long)fixed) / (long long)(a_slot + b_slot));
+    if (stages >= 2) break;
+  }
+  if (p.res_slots < 2) p.res_slots = 2;
   if (stages > kGnMaxStages) stages = kGnMaxStages;
   p.b_stages = p.b_shared ? 2 : stages;
   if (stages < 2) { set_error("gemm_gn: tile too large for shared memory"); return MAED_ERR_UNSUPPORTED; }
@@ -633,7 +639,11 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   static const bool pair_on = !(getenv("MAED_B200_GN_PAIR") && atoi(getenv("MAED_B200_GN_PAIR")) == 0);
   // measured: 3x3 126 -> 103 us (tensor pipe 53 -> 66 %), 1x1 63 -> 58 us; the 1024-channel shortcut layers are epilogue-bound
   // and lose with 256-wide blocks (97 -> 108 us), so they keep the single-CTA plan
+  // shortcut layers of those maps (1024 channels): pairs on 128-wide blocks — a stage is 48 KB, which leaves room for the third
+  // staging slot per group (MAED_B200_GN_PAIR_RES=0: the single-CTA plan)
+  static const bool pair_res = !(getenv("MAED_B200_GN_PAIR_RES") && atoi(getenv("MAED_B200_GN_PAIR_RES")) == 0);
   if (pair_on && p.tiles_per_image == 2 && !a.res && a.C % 256 == 0 && gsz == 8) { bn = 256; tpc = 1; cluster = 2; pair = true; }
+  else if (pair_on && pair_res && p.tiles_per_image == 2 && a.res && a.C % 128 == 0 && gsz == 32) { bn = 128; tpc = 1; cluster = 2; pair = true; }
   else if (a.res) {
     // shortcut layers are epilogue-bound: 64-wide blocks leave shared memory for 3 shortcut slots (2 TMA loads in flight)
     // ... except with at most 2 tiles per image (stage 2: 14 x 14): there the L2 -> SM port is the bound and a 128-wide
@@ -705,6 +715,7 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   }
   if (!a.res) tmR = tmO;
   if (pair && gsz == 8) return launch_gn<256, 8, true>(tmA, tmB, tmO, tmR, tmOw, p, st);
+  if (pair && gsz == 32) return launch_gn<128, 32, true>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 128 && gsz == 4) return launch_gn<128, 4>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 128 && gsz == 8) return launch_gn<128, 8>(tmA, tmB, tmO, tmR, tmOw, p, st);
   if (bn == 128 && gsz == 16) return launch_gn<128, 16>(tmA, tmB, tmO, tmR, tmOw, p, st);
