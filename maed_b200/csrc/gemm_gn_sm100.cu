@@ -639,9 +639,9 @@ int conv_gn_fused(const ConvGnArgs& a, cudaStream_t st) {
   static const bool pair_on = !(getenv("MAED_B200_GN_PAIR") && atoi(getenv("MAED_B200_GN_PAIR")) == 0);
   // measured: 3x3 126 -> 103 us (tensor pipe 53 -> 66 %), 1x1 63 -> 58 us; the 1024-channel shortcut layers are epilogue-bound
   // and lose with 256-wide blocks (97 -> 108 us), so they keep the single-CTA plan
-  // shortcut layers of those maps (1024 channels): pairs on 128-wide blocks — a stage is 48 KB, which leaves room for the third
-  // staging slot per group (MAED_B200_GN_PAIR_RES=0: the single-CTA plan)
-  static const bool pair_res = !(getenv("MAED_B200_GN_PAIR_RES") && atoi(getenv("MAED_B200_GN_PAIR_RES")) == 0);
+  // shortcut layers of those maps (1024 channels) as pairs on 128-wide blocks (a stage is 48 KB, which leaves room for the third
+  // staging slot per group): measured 100 vs 98 us for the single-CTA plan — opt-in only (MAED_B200_GN_PAIR_RES=1)
+  static const bool pair_res = getenv("MAED_B200_GN_PAIR_RES") && atoi(getenv("MAED_B200_GN_PAIR_RES")) == 1;
   if (pair_on && p.tiles_per_image == 2 && !a.res && a.C % 256 == 0 && gsz == 8) { bn = 256; tpc = 1; cluster = 2; pair = true; }
   else if (pair_on && pair_res && p.tiles_per_image == 2 && a.res && a.C % 128 == 0 && gsz == 32) { bn = 128; tpc = 1; cluster = 2; pair = true; }
   else if (a.res) {
