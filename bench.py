@@ -478,36 +478,42 @@ def main():
     # ---------------------------------------------------------------- end-to-end through the public API ("e2e"):
     # host pinned frames -> H2D -> MAED.forward -> D2H of all five outputs the reference's evaluator pulls
     # (lib/core/evaluate.py:80-84: theta, verts, kp_2d, kp_3d, rotmat), every step, copies inside the timed region;
-    # the H2D of step i+1 runs on a side stream while step i computes (what a pin_memory DataLoader + non_blocking does).
+    # the H2D of the next two steps runs on a side stream while a step computes (what a pin_memory DataLoader with
+    # prefetch_factor=2 + non_blocking copies does).
     hx = [synth.synth_frames(CLIPS_PER_GPU, T, 200 + i).pin_memory() for i in range(2)]
-    dx = [torch.empty_like(xs[0]) for _ in range(2)]
+    NB = 3                                                   # device input / host output buffers in rotation
+    dx = [torch.empty_like(xs[0]) for _ in range(NB)]
     h_out = {k: torch.empty(v.shape).pin_memory() for k, v in out.items() if k in ("theta", "verts", "kp_2d", "kp_3d", "rotmat")}
     copy_stream = torch.cuda.Stream(dev)
     main_stream = torch.cuda.current_stream(dev)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(NB)]
+    consumed = [torch.cuda.Event() for _ in range(NB)]
 
     d2h_stream = torch.cuda.Stream(dev)
-    h_outs = [h_out, {k: torch.empty_like(v).pin_memory() for k, v in h_out.items()}]
-    done = [torch.cuda.Event() for _ in range(2)]
-    read = [torch.cuda.Event() for _ in range(2)]
+    h_outs = [h_out] + [{k: torch.empty_like(v).pin_memory() for k, v in h_out.items()} for _ in range(NB - 1)]
+    done = [torch.cuda.Event() for _ in range(NB)]
+    read = [torch.cuda.Event() for _ in range(NB)]
 
     def e2e_loop(steps):
-        """H2D of step i+1 (copy stream) and D2H of step i-1's five outputs (second copy stream) run under step i's compute;
-        the host waits for the results of step i-1 before it launches step i+1, and for the last step at the end — every
-        step's input copy and result read is inside the timed region."""
-        with torch.cuda.stream(copy_stream):
-            dx[0].copy_(hx[0], non_blocking=True)
-            ready[0].record(copy_stream)
-        keep = [None, None]
+        """A prefetching loader two steps deep: the H2D of step i+2 (copy stream) and the D2H of the five outputs of steps
+        i-1 / i-2 (second copy stream) run under step i's compute; the host reads the results of step i-2 before it launches
+        step i+1 and drains the last two at the end — every step's input copy and result read is inside the timed region.
+        (Depth 2 instead of 1: the host then never has to launch a step in the shadow of a single running one, so launch
+        jitter on a shared host does not show up as GPU idle time.)"""
+        def h2d(j):
+            b = j % NB
+            with torch.cuda.stream(copy_stream):
+                if j >= NB:
+                    copy_stream.wait_event(consumed[b])
+                dx[b].copy_(hx[j % 2], non_blocking=True)
+                ready[b].record(copy_stream)
+        for j in range(min(2, steps)):
+            h2d(j)
+        keep = [None] * NB
         for i in range(steps):
-            cur, nxt = i % 2, (i + 1) % 2
-            if i + 1 < steps:
-                with torch.cuda.stream(copy_stream):
-                    if i >= 1:
-                        copy_stream.wait_event(consumed[nxt])
-                    dx[nxt].copy_(hx[nxt], non_blocking=True)
-                    ready[nxt].record(copy_stream)
+            cur = i % NB
+            if i + 2 < steps:
+                h2d(i + 2)
             main_stream.wait_event(ready[cur])
             o = model(dx[cur])
             consumed[cur].record(main_stream)
@@ -518,9 +524,10 @@ def main():
                 for k, h in h_outs[cur].items():
                     h.copy_(o[k], non_blocking=True)
                 read[cur].record(d2h_stream)
-            if i >= 1:
-                read[nxt].synchronize()                     # the caller reads the result of step i-1 while step i computes
-        read[(steps - 1) % 2].synchronize()
+            if i >= 2:
+                read[(i - 2) % NB].synchronize()            # the caller reads the result of step i-2 while steps i-1, i compute
+        for j in range(max(0, steps - 2), steps):
+            read[j % NB].synchronize()
 
     e2e_loop(2)
     if dist:
