@@ -4,6 +4,7 @@
 // is launched from here on the caller's stream, so a whole forward costs one ctypes call and can be captured in
 // a CUDA graph.
 #include "engine_internal.h"
+#include "fork_join.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -289,10 +290,12 @@ int engine_pack(const Engine* e, const void* const* params, void* packed, cudaSt
   uint8_t* pk = (uint8_t*)packed;
   auto P = [&](int i) { return (const float*)params[i]; };
   auto H = [&](size_t off) { return (__half*)(pk + off); };
+  // ~90 independent small kernels and ~70 small copies: spread over side streams, joined before the dependent tail
+  ForkJoin fj(st);
   if (e->cfg.encoder == ENC_CNN) {
     MAED_PROPAGATE(cnn_pack(*e, params, packed, st));
   } else {
-    MAED_PROPAGATE(prep_conv_weight(P(e->i_stem_w), 64, 3, 7, 7, kStemKPad, 1, H(e->off_stem), 64LL * kStemKPad, st));
+    MAED_PROPAGATE(prep_conv_weight(P(e->i_stem_w), 64, 3, 7, 7, kStemKPad, 1, H(e->off_stem), 64LL * kStemKPad, fj.next()));
     int prev = 64, bi = 0;
     for (int s = 0; s < 3; ++s) {
       const int out = kStageOut[s], mid = out / 4;
@@ -300,25 +303,25 @@ int engine_pack(const Engine* e, const void* const* params, void* packed, cudaSt
         const Engine::BlockIdx& ix = e->bb[bi];
         const Engine::BlockOff& of = e->bb_off[bi];
         if (b == 0)
-          MAED_PROPAGATE(prep_conv_weight(P(ix.ds_w), out, prev, 1, 1, prev, 1, H(of.ds), (long long)out * prev, st));
-        MAED_PROPAGATE(prep_conv_weight(P(ix.c1_w), mid, prev, 1, 1, prev, 1, H(of.c1), (long long)mid * prev, st));
-        MAED_PROPAGATE(prep_conv_weight(P(ix.c2_w), mid, mid, 3, 3, 9 * mid, 1, H(of.c2), (long long)mid * mid * 9, st));
-        MAED_PROPAGATE(prep_conv_weight(P(ix.c3_w), out, mid, 1, 1, mid, 1, H(of.c3), (long long)out * mid, st));
+          MAED_PROPAGATE(prep_conv_weight(P(ix.ds_w), out, prev, 1, 1, prev, 1, H(of.ds), (long long)out * prev, fj.next()));
+        MAED_PROPAGATE(prep_conv_weight(P(ix.c1_w), mid, prev, 1, 1, prev, 1, H(of.c1), (long long)mid * prev, fj.next()));
+        MAED_PROPAGATE(prep_conv_weight(P(ix.c2_w), mid, mid, 3, 3, 9 * mid, 1, H(of.c2), (long long)mid * mid * 9, fj.next()));
+        MAED_PROPAGATE(prep_conv_weight(P(ix.c3_w), out, mid, 1, 1, mid, 1, H(of.c3), (long long)out * mid, fj.next()));
         prev = out;
       }
     }
-    MAED_PROPAGATE(split_f32(P(e->i_proj_w), H(e->off_proj), 768LL * 1024, 768LL * 1024, st));
+    MAED_PROPAGATE(split_f32(P(e->i_proj_w), H(e->off_proj), 768LL * 1024, 768LL * 1024, fj.next()));
     const long long CC = 768LL * 768;
     for (int i = 0; i < e->cfg.num_blocks; ++i) {
       const Engine::SteIdx& ix = e->blk[i];
       const Engine::SteOff& of = e->blk_off[i];
-      MAED_PROPAGATE(split_f32(P(ix.qkv_w), H(of.qkv), 3 * CC, 3 * CC, st));
-      MAED_PROPAGATE(split_f32(P(ix.proj_w), H(of.proj), CC, CC, st));
-      MAED_PROPAGATE(split_f32(P(ix.fc1_w), H(of.fc1), 4 * CC, 4 * CC, st));
-      MAED_PROPAGATE(split_f32(P(ix.fc2_w), H(of.fc2), 4 * CC, 4 * CC, st));
-      if (e->cfg.mode == MODE_PARALLEL) MAED_PROPAGATE(split_f32(P(ix.ts_w), H(of.ts), 4 * CC, 4 * CC, st));
+      MAED_PROPAGATE(split_f32(P(ix.qkv_w), H(of.qkv), 3 * CC, 3 * CC, fj.next()));
+      MAED_PROPAGATE(split_f32(P(ix.proj_w), H(of.proj), CC, CC, fj.next()));
+      MAED_PROPAGATE(split_f32(P(ix.fc1_w), H(of.fc1), 4 * CC, 4 * CC, fj.next()));
+      MAED_PROPAGATE(split_f32(P(ix.fc2_w), H(of.fc2), 4 * CC, 4 * CC, fj.next()));
+      if (e->cfg.mode == MODE_PARALLEL) MAED_PROPAGATE(split_f32(P(ix.ts_w), H(of.ts), 4 * CC, 4 * CC, fj.next()));
     }
-    MAED_PROPAGATE(split_f32(P(e->i_pl_w), H(e->off_pl), CC, CC, st));
+    MAED_PROPAGATE(split_f32(P(e->i_pl_w), H(e->off_pl), CC, CC, fj.next()));
   }  // !cnn
   if (e->cfg.decoder == DEC_KTD) {
     // joint_regs.j.weight [6, HD + 6k] -> Wx rows (first HD columns), ancestor blocks (last 6k columns), biases
@@ -332,14 +335,16 @@ int engine_pack(const Engine* e, const void* const* params, void* packed, cudaSt
       const float* wj = P(e->i_joint0 + 2 * j);
       const float* bjs = P(e->i_joint0 + 2 * j + 1);
       const size_t src_pitch = (size_t)(HD + 6 * k) * 4;
+      cudaStream_t js = fj.next();
       MAED_CUDA_CHECK(cudaMemcpy2DAsync(wx + (size_t)j * 6 * HD, (size_t)HD * 4, wj, src_pitch, (size_t)HD * 4, 6,
-                                        cudaMemcpyDeviceToDevice, st));
+                                        cudaMemcpyDeviceToDevice, js));
       if (k > 0)
         MAED_CUDA_CHECK(cudaMemcpy2DAsync(wa + aoff, (size_t)6 * k * 4, wj + HD, src_pitch, (size_t)6 * k * 4, 6,
-                                          cudaMemcpyDeviceToDevice, st));
-      MAED_CUDA_CHECK(cudaMemcpyAsync(bj + j * 6, bjs, 24, cudaMemcpyDeviceToDevice, st));
+                                          cudaMemcpyDeviceToDevice, js));
+      MAED_CUDA_CHECK(cudaMemcpyAsync(bj + j * 6, bjs, 24, cudaMemcpyDeviceToDevice, js));
       aoff += 36 * k;
     }
+    MAED_PROPAGATE(fj.join());
     // tensor-core operands of the tail: fc1, fc2 and one [192, HD] head matrix = [24 joint bases (144) | shape (10) |
     // cam (3) | 35 zero rows] with its bias vector
     const long long F = e->feat_dim();

@@ -21,6 +21,7 @@
 
 #include "bwd_kernels.h"
 #include "engine_internal.h"
+#include "fork_join.h"
 #include "gemm_host.h"
 #include "gemm_sm100.cuh"
 #include "kernels.h"
@@ -442,24 +443,25 @@ int train_pack(const Engine* ep, const void* const* params, void* tpack, cudaStr
   const Net net = build_net(e);
   uint8_t* tp = (uint8_t*)(((uintptr_t)tpack + 1023) & ~(uintptr_t)1023);
   auto P = [&](int i) { return (const float*)params[i]; };
+  ForkJoin fj(st);                                         // ~85 independent small kernels: side streams, joined at the end
   for (size_t l = 1; l < net.L.size(); ++l) {
     const ConvL& L = net.L[l];
     MAED_PROPAGATE(prep_conv_weight_dgrad(P(L.w_idx), L.Cout, L.Cin, L.k, L.k, 1, (__half*)(tp + L.tp_off),
-                                          (long long)L.Cout * L.Cin * L.k * L.k, st));
+                                          (long long)L.Cout * L.Cin * L.k * L.k, fj.next()));
   }
-  MAED_PROPAGATE(split_f32_transposed(P(e.i_proj_w), 768, 1024, (__half*)(tp + net.tp_proj), 768LL * 1024, st));
+  MAED_PROPAGATE(split_f32_transposed(P(e.i_proj_w), 768, 1024, (__half*)(tp + net.tp_proj), 768LL * 1024, fj.next()));
   const int C = 768;
   const long long CC = (long long)C * C;
   for (int i = 0; i < e.cfg.num_blocks; ++i) {
     const Engine::SteIdx& ix = e.blk[i];
-    MAED_PROPAGATE(split_f32_transposed(P(ix.qkv_w), 3 * C, C, (__half*)(tp + net.ste[i].qkv), 3 * CC, st));
-    MAED_PROPAGATE(split_f32_transposed(P(ix.proj_w), C, C, (__half*)(tp + net.ste[i].proj), CC, st));
-    MAED_PROPAGATE(split_f32_transposed(P(ix.fc1_w), 4 * C, C, (__half*)(tp + net.ste[i].fc1), 4 * CC, st));
-    MAED_PROPAGATE(split_f32_transposed(P(ix.fc2_w), C, 4 * C, (__half*)(tp + net.ste[i].fc2), 4 * CC, st));
+    MAED_PROPAGATE(split_f32_transposed(P(ix.qkv_w), 3 * C, C, (__half*)(tp + net.ste[i].qkv), 3 * CC, fj.next()));
+    MAED_PROPAGATE(split_f32_transposed(P(ix.proj_w), C, C, (__half*)(tp + net.ste[i].proj), CC, fj.next()));
+    MAED_PROPAGATE(split_f32_transposed(P(ix.fc1_w), 4 * C, C, (__half*)(tp + net.ste[i].fc1), 4 * CC, fj.next()));
+    MAED_PROPAGATE(split_f32_transposed(P(ix.fc2_w), C, 4 * C, (__half*)(tp + net.ste[i].fc2), 4 * CC, fj.next()));
     if (e.cfg.mode == MODE_PARALLEL)
-      MAED_PROPAGATE(split_f32_transposed(P(ix.ts_w), 2 * C, 2 * C, (__half*)(tp + net.ste[i].ts), 4 * CC, st));
+      MAED_PROPAGATE(split_f32_transposed(P(ix.ts_w), 2 * C, 2 * C, (__half*)(tp + net.ste[i].ts), 4 * CC, fj.next()));
   }
-  return MAED_OK;
+  return fj.join();
 }
 
 // -------------------------------------------------------------------------------------------- forward
